@@ -1,0 +1,87 @@
+"""ctypes binding of libagnn.so (the C ABI declared in include/agnn.h).
+
+There is deliberately no fallback: if the library is missing or a call fails the
+caller gets an exception.  ``build()`` compiles it in-tree with nvcc for sm_100a
+(``analysisgnn_b200/csrc/Makefile``); the built ``.so`` is git-ignored but ships
+to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libagnn.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+MAX_SEG = 32
+MAX_REL = 16
+F32, BF16 = 0, 1
+SCALE_NONE, SCALE_MEAN = 0, 1
+COMBINE_CONCAT, COMBINE_SUM = 0, 1
+REL_IDENTITY_IF_EMPTY = 1
+
+
+class AgnnError(RuntimeError):
+    pass
+
+
+class Coo(C.Structure):
+    _fields_ = [("row", C.c_void_p), ("col", C.c_void_p), ("etype", C.c_void_p), ("n_edges", C.c_int64),
+                ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("n_rel", C.c_int32), ("reserved", C.c_int32),
+                ("rowptr_off", C.c_int64), ("edge_off", C.c_int64)]
+
+
+class Rel(C.Structure):
+    _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("src", C.c_void_p), ("ld_src", C.c_int64),
+                ("nbr_deg_rowptr", C.c_void_p), ("out_col", C.c_int32), ("flags", C.c_int32)]
+
+
+_PROTOTYPES = {
+    "agnn_version": (C.c_int, []),
+    "agnn_last_error": (C.c_char_p, []),
+    "agnn_csr_build_workspace": (C.c_size_t, [C.c_int, C.POINTER(Coo)]),
+    "agnn_csr_build": (C.c_int, [C.c_int, C.POINTER(Coo), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    "agnn_gather_reduce": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Rel),
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                     C.c_int64, C.c_void_p]),
+    "agnn_rowscale_sum": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.POINTER(Rel), C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libagnn.so in-tree (nvcc, -gencode arch=compute_100a,code=sm_100a)."""
+    proc = subprocess.run(["make", "-C", CSRC, "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise AgnnError("building libagnn.so failed:\n" + proc.stdout[-4000:] + proc.stderr[-4000:])
+    if verbose:
+        print(proc.stdout)
+    return LIB_PATH
+
+
+def exported_symbols():
+    return sorted(_PROTOTYPES)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise AgnnError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU or PyTorch fallback for the CUDA path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "libagnn") -> None:
+    if rc != 0:
+        raise AgnnError(f"{what} failed ({rc}): {lib().agnn_last_error().decode()}")

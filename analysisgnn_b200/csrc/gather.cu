@@ -1,0 +1,310 @@
+// Relation-fused CSR gather-reduce (forward and, on the transposed CSR, backward)
+// for the message-passing layers.  See include/agnn.h for the exact semantics and
+// the reference lines replaced (gnn.py:70-74, :511, :539; hgnn.py:406-407;
+// analysis.py:586; PyG SAGEConv mean aggregation).
+//
+// Mapping: a group of LANES threads owns one output row and walks the row's CSR
+// segment of every relation in turn; each lane keeps V 16-byte column vectors in
+// fp32 registers.  Neighbour rows are fetched with 128-bit read-only loads, four
+// edges in flight per group.  No atomics: the sum over a row runs in CSR (= input
+// edge) order, so results are deterministic run to run.
+//
+// Roofline: HBM.  Algorithmic bytes per launch:
+//   sum_r E_r * (F*b + 4)  gathered rows + col ids
+//   + n_rows * n_out_slices * F*b  written  (+ self / copy rows read)
+//   + 4 * n_rel * (n_rows + 1)     rowptr
+#include "common.cuh"
+
+namespace agnn {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+struct GatherParams {
+  int n_rows, n_feat, n_rel, scale, combine;
+  int copy_col;
+  agnn_rel_t rel[AGNN_MAX_REL];
+  const void* self_add;
+  int64_t ld_self;
+  const void* copy;
+  int64_t ld_copy;
+  void* out;
+  int64_t ld_out;
+};
+
+template <typename T, int LANES, int V>
+__global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_constant__ GatherParams p) {
+  using VT = Vec16<T>;
+  constexpr int E = VT::E;
+  constexpr int kRowsPerBlock = kThreads / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int F = p.n_feat;
+  T* const out = static_cast<T*>(p.out);
+
+  for (int row = blockIdx.x * kRowsPerBlock + threadIdx.x / LANES; row < p.n_rows;
+       row += gridDim.x * kRowsPerBlock) {
+    float selfv[V][E];
+    if (p.self_add) {
+      const T* sp = static_cast<const T*>(p.self_add) + (int64_t)row * p.ld_self;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = (v * LANES + lane) * E;
+        if (c < F) VT::load_nc(sp + c, selfv[v]);
+      }
+    }
+    float tot[V][E];
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int e = 0; e < E; ++e) tot[v][e] = 0.f;
+
+    for (int r = 0; r < p.n_rel; ++r) {
+      const agnn_rel_t& R = p.rel[r];
+      const T* src = static_cast<const T*>(R.src);
+      float acc[V][E];
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[v][e] = 0.f;
+      float s = 1.f;
+
+      if ((R.flags & AGNN_REL_IDENTITY_IF_EMPTY) && __ldg(R.rowptr + p.n_rows) == __ldg(R.rowptr)) {
+        const T* rp = src + (int64_t)row * R.ld_src;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int c = (v * LANES + lane) * E;
+          if (c < F) VT::load_nc(rp + c, acc[v]);
+        }
+      } else {
+        const int beg = __ldg(R.rowptr + row), end = __ldg(R.rowptr + row + 1);
+        for (int k = beg; k < end; k += kUnroll) {
+          int idx[kUnroll];
+          float w[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            idx[u] = (k + u < end) ? __ldg(R.col + k + u) : -1;
+            w[u] = 1.f;
+          }
+          if (R.nbr_deg_rowptr) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+              if (idx[u] >= 0) {
+                const int d = __ldg(R.nbr_deg_rowptr + idx[u] + 1) - __ldg(R.nbr_deg_rowptr + idx[u]);
+                w[u] = 1.f / (float)max(d, 1);
+              }
+          }
+          float x[kUnroll][V][E];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (idx[u] >= 0) {
+              const T* rp = src + (int64_t)idx[u] * R.ld_src;
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                const int c = (v * LANES + lane) * E;
+                if (c < F) VT::load_nc(rp + c, x[u][v]);
+              }
+            }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (idx[u] >= 0) {
+#pragma unroll
+              for (int v = 0; v < V; ++v)
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[v][e] = fmaf(w[u], x[u][v][e], acc[v][e]);
+            }
+        }
+        if (p.combine == AGNN_COMBINE_CONCAT && p.self_add) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[v][e] += selfv[v][e];
+        }
+        if (p.scale == AGNN_SCALE_MEAN) s = 1.f / (float)max(end - beg, 1);
+      }
+
+      if (p.combine == AGNN_COMBINE_CONCAT) {
+        T* op = out + (int64_t)row * p.ld_out + R.out_col;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int c = (v * LANES + lane) * E;
+          if (c < F) {
+            float o[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) o[e] = acc[v][e] * s;
+            VT::store(op + c, o);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int e = 0; e < E; ++e) tot[v][e] = fmaf(acc[v][e], s, tot[v][e]);
+      }
+    }
+
+    if (p.combine == AGNN_COMBINE_SUM) {
+      T* op = out + (int64_t)row * p.ld_out + p.rel[0].out_col;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = (v * LANES + lane) * E;
+        if (c < F) {
+          float o[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) o[e] = tot[v][e] + (p.self_add ? selfv[v][e] : 0.f);
+          VT::store(op + c, o);
+        }
+      }
+    }
+    if (p.copy) {
+      const T* cp = static_cast<const T*>(p.copy) + (int64_t)row * p.ld_copy;
+      T* op = out + (int64_t)row * p.ld_out + p.copy_col;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = (v * LANES + lane) * E;
+        if (c < F) {
+          float t[E];
+          VT::load_nc(cp + c, t);
+          VT::store(op + c, t);
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int LANES, int V>
+int launch(const GatherParams& p, cudaStream_t stream) {
+  constexpr int kRowsPerBlock = kThreads / LANES;
+  int64_t blocks = ceil_div(p.n_rows, kRowsPerBlock);
+  const int64_t cap = (int64_t)kNumSM * 8;  // 8 resident CTAs/SM; grid-stride beyond that
+  if (blocks > cap) blocks = cap;
+  gather_reduce_kernel<T, LANES, V><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  return check_launch("gather_reduce");
+}
+
+template <typename T>
+int dispatch(const GatherParams& p, cudaStream_t stream) {
+  const int vecs = p.n_feat / Vec16<T>::E;  // 16-byte vectors per row
+  if (vecs <= 8) return launch<T, 8, 1>(p, stream);
+  if (vecs <= 16) return launch<T, 16, 1>(p, stream);
+  if (vecs <= 32) return launch<T, 32, 1>(p, stream);
+  if (vecs <= 64) return launch<T, 32, 2>(p, stream);
+  if (vecs <= 128) return launch<T, 32, 4>(p, stream);
+  return fail(AGNN_ERR_UNSUPPORTED, "gather_reduce: n_feat %d too wide (max %d)", p.n_feat, 128 * Vec16<T>::E);
+}
+
+int check_matrix(const char* what, const void* ptr, int64_t ld, int elem_bytes) {
+  if (!aligned16(ptr) || (ld * elem_bytes) % 16 != 0)
+    return fail(AGNN_ERR_ARG, "%s must be 16-byte aligned with a 16-byte multiple row stride", what);
+  return AGNN_OK;
+}
+
+// ---- self-term gradient: out = base + sum_r in[:, slice_r] / max(deg_r, 1) ----
+struct RowScaleParams {
+  int n_rows, n_feat, n_rel;
+  agnn_rel_t rel[AGNN_MAX_REL];
+  const void* in;
+  int64_t ld_in;
+  const void* base;
+  int64_t ld_base;
+  void* out;
+  int64_t ld_out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) rowscale_sum_kernel(const __grid_constant__ RowScaleParams p) {
+  using VT = Vec16<T>;
+  constexpr int E = VT::E;
+  const int vecs = p.n_feat / E;
+  const int64_t total = (int64_t)p.n_rows * vecs;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+    const int row = (int)(i / vecs), c = (int)(i % vecs) * E;
+    float acc[E];
+    if (p.base) {
+      VT::load_nc(static_cast<const T*>(p.base) + (int64_t)row * p.ld_base + c, acc);
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    }
+    for (int r = 0; r < p.n_rel; ++r) {
+      const agnn_rel_t& R = p.rel[r];
+      if ((R.flags & AGNN_REL_IDENTITY_IF_EMPTY) && __ldg(R.rowptr + p.n_rows) == __ldg(R.rowptr)) continue;
+      const int d = __ldg(R.rowptr + row + 1) - __ldg(R.rowptr + row);
+      const float s = 1.f / (float)max(d, 1);
+      float t[E];
+      VT::load_nc(static_cast<const T*>(p.in) + (int64_t)row * p.ld_in + R.out_col + c, t);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] = fmaf(t[e], s, acc[e]);
+    }
+    VT::store(static_cast<T*>(p.out) + (int64_t)row * p.ld_out + c, acc);
+  }
+}
+
+}  // namespace
+}  // namespace agnn
+
+using namespace agnn;
+
+extern "C" int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
+                                  const agnn_rel_t* rels, const void* self_add, int64_t ld_self, const void* copy,
+                                  int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out,
+                                  agnn_stream_t stream) {
+  if (n_rows < 0 || n_feat <= 0 || n_rel < 1 || n_rel > AGNN_MAX_REL || !rels || !out)
+    return fail(AGNN_ERR_ARG, "gather_reduce: bad sizes (n_rows=%d n_feat=%d n_rel=%d)", n_rows, n_feat, n_rel);
+  if (dtype != AGNN_F32 && dtype != AGNN_BF16) return fail(AGNN_ERR_ARG, "gather_reduce: dtype %d", dtype);
+  if ((scale != AGNN_SCALE_NONE && scale != AGNN_SCALE_MEAN) ||
+      (combine != AGNN_COMBINE_CONCAT && combine != AGNN_COMBINE_SUM))
+    return fail(AGNN_ERR_ARG, "gather_reduce: bad scale/combine");
+  const int eb = dtype == AGNN_F32 ? 4 : 2, ev = 16 / eb;
+  if (n_feat % ev) return fail(AGNN_ERR_UNSUPPORTED, "gather_reduce: n_feat %d is not a multiple of %d", n_feat, ev);
+  if (n_rows == 0) return AGNN_OK;
+  GatherParams p;
+  p.n_rows = n_rows; p.n_feat = n_feat; p.n_rel = n_rel; p.scale = scale; p.combine = combine;
+  p.copy_col = copy_col;
+  p.self_add = self_add; p.ld_self = ld_self; p.copy = copy; p.ld_copy = ld_copy; p.out = out; p.ld_out = ld_out;
+  int rc;
+  if ((rc = check_matrix("gather_reduce: out", out, ld_out, eb))) return rc;
+  if (self_add && (rc = check_matrix("gather_reduce: self_add", self_add, ld_self, eb))) return rc;
+  if (copy && ((rc = check_matrix("gather_reduce: copy", copy, ld_copy, eb)) || copy_col % ev))
+    return rc ? rc : fail(AGNN_ERR_ARG, "gather_reduce: copy_col must be a multiple of %d", ev);
+  for (int r = 0; r < n_rel; ++r) {
+    p.rel[r] = rels[r];
+    if (!rels[r].src || !rels[r].rowptr) return fail(AGNN_ERR_ARG, "gather_reduce: relation %d has null pointers", r);
+    if ((rc = check_matrix("gather_reduce: src", rels[r].src, rels[r].ld_src, eb))) return rc;
+    if (rels[r].out_col % ev) return fail(AGNN_ERR_ARG, "gather_reduce: out_col must be a multiple of %d", ev);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == AGNN_F32 ? dispatch<float>(p, st) : dispatch<__nv_bfloat16>(p, st);
+}
+
+extern "C" int agnn_rowscale_sum(int32_t n_rows, int32_t n_feat, int dtype, int n_rel, const agnn_rel_t* rels,
+                                 const void* in, int64_t ld_in, const void* base, int64_t ld_base, void* out,
+                                 int64_t ld_out, agnn_stream_t stream) {
+  if (n_rows < 0 || n_feat <= 0 || n_rel < 1 || n_rel > AGNN_MAX_REL || !rels || !in || !out)
+    return fail(AGNN_ERR_ARG, "rowscale_sum: bad arguments");
+  if (dtype != AGNN_F32 && dtype != AGNN_BF16) return fail(AGNN_ERR_ARG, "rowscale_sum: dtype %d", dtype);
+  const int eb = dtype == AGNN_F32 ? 4 : 2, ev = 16 / eb;
+  if (n_feat % ev) return fail(AGNN_ERR_UNSUPPORTED, "rowscale_sum: n_feat %d is not a multiple of %d", n_feat, ev);
+  if (n_rows == 0) return AGNN_OK;
+  int rc;
+  if ((rc = check_matrix("rowscale_sum: in", in, ld_in, eb)) || (rc = check_matrix("rowscale_sum: out", out, ld_out, eb)))
+    return rc;
+  if (base && (rc = check_matrix("rowscale_sum: base", base, ld_base, eb))) return rc;
+  RowScaleParams p;
+  p.n_rows = n_rows; p.n_feat = n_feat; p.n_rel = n_rel;
+  p.in = in; p.ld_in = ld_in; p.base = base; p.ld_base = ld_base; p.out = out; p.ld_out = ld_out;
+  for (int r = 0; r < n_rel; ++r) {
+    p.rel[r] = rels[r];
+    if (!rels[r].rowptr)
+      return fail(AGNN_ERR_ARG, "rowscale_sum: relation %d has a null rowptr", r);
+    if (rels[r].out_col % ev) return fail(AGNN_ERR_ARG, "rowscale_sum: column offsets must be multiples of %d", ev);
+  }
+  const int64_t total = (int64_t)n_rows * (n_feat / ev);
+  int64_t blocks = ceil_div(total, kThreads);
+  if (blocks > (int64_t)kNumSM * 8) blocks = (int64_t)kNumSM * 8;
+  if (dtype == AGNN_F32)
+    rowscale_sum_kernel<float><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(p);
+  else
+    rowscale_sum_kernel<__nv_bfloat16><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("rowscale_sum");
+}

@@ -1,0 +1,187 @@
+"""Device-side graph structure for the message-passing kernels.
+
+Everything the layers need from a batch's ``edge_index`` tensors is one call of
+``agnn_csr_build`` (include/agnn.h): per relation a CSR keyed on the REDUCE side
+(used by the forward) and a CSR keyed on the GATHERED side (the transposed graph,
+used by the backward), both stable in input edge order, int32.
+
+Two layouts mirror the two conventions in the reference:
+
+* ``TypedCSR``  -- one node space, ``edge_index [2,E]`` + ``edge_type [E]``; the
+  in-tree layers reduce at ``edge_index[0]`` reading ``edge_index[1]``
+  (analysisgnn/models/core/gnn.py:70-74, hgnn.py:480-483).
+* ``HeteroCSR`` -- PyG ``edge_index_dict``; reduces at row 1 reading row 0.
+
+Structures are cached per batch (``cached``), keyed on the identity and version
+of the index tensors, so a stack of L layers builds them once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.AgnnError(f"{what} must be a CUDA tensor: analysisgnn_b200 has no CPU path")
+
+
+def _index_row(t: torch.Tensor) -> torch.Tensor:
+    """A stride-1 int64 view (or copy) of a 1-D index tensor."""
+    if t.dtype != torch.int64:
+        t = t.long()
+    if t.dim() != 1:
+        raise ValueError("index rows must be 1-D")
+    return t if t.stride(0) == 1 or t.numel() <= 1 else t.contiguous()
+
+
+class Segment:
+    """One COO segment handed to agnn_csr_build."""
+
+    def __init__(self, row, col, n_rows, n_cols, etype=None, n_rel=1):
+        self.row, self.col = _index_row(row), _index_row(col)
+        self.etype = None if etype is None else _index_row(etype)
+        self.n_rows, self.n_cols, self.n_rel = int(n_rows), int(n_cols), int(n_rel)
+        self.n_edges = int(self.row.numel())
+        if self.col.numel() != self.n_edges or (self.etype is not None and self.etype.numel() != self.n_edges):
+            raise ValueError("row / col / etype must have the same length")
+
+
+class CSR:
+    """Result for one segment: ``rowptr`` [n_rel, n_rows+1] (absolute positions in
+    ``col`` / ``perm``), ``col`` [E] gathered-side ids, ``perm`` [E] input positions."""
+
+    __slots__ = ("rowptr", "col", "perm", "n_rows", "n_cols", "n_rel", "n_edges")
+
+    def __init__(self, rowptr, col, perm, seg: Segment):
+        self.rowptr, self.col, self.perm = rowptr, col, perm
+        self.n_rows, self.n_cols, self.n_rel, self.n_edges = seg.n_rows, seg.n_cols, seg.n_rel, seg.n_edges
+
+
+def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) -> List[CSR]:
+    """Convert COO segments to CSR on the GPU (one library call per 32 segments)."""
+    if not segments:
+        return []
+    device = device if device is not None else segments[0].row.device
+    for s in segments:
+        _require_cuda(s.row, "edge_index")
+    lib = _lib.lib()
+    key_total = sum(s.n_rel * (s.n_rows + 1) for s in segments)
+    edge_total = sum(s.n_edges for s in segments)
+    rowptr = torch.empty(key_total, dtype=torch.int32, device=device)
+    col = torch.empty(max(edge_total, 1), dtype=torch.int32, device=device)
+    perm = torch.empty(max(edge_total, 1), dtype=torch.int32, device=device)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    out, k_off, e_off = [], 0, 0
+    for lo in range(0, len(segments), _lib.MAX_SEG):
+        chunk = segments[lo:lo + _lib.MAX_SEG]
+        arr = (_lib.Coo * len(chunk))()
+        for i, s in enumerate(chunk):
+            arr[i].row = s.row.data_ptr() if s.n_edges else None
+            arr[i].col = s.col.data_ptr() if s.n_edges else None
+            arr[i].etype = s.etype.data_ptr() if (s.etype is not None and s.n_edges) else None
+            arr[i].n_edges, arr[i].n_rows, arr[i].n_cols, arr[i].n_rel = s.n_edges, s.n_rows, s.n_cols, s.n_rel
+            arr[i].rowptr_off, arr[i].edge_off = k_off, e_off
+            keys = s.n_rel * (s.n_rows + 1)
+            out.append(CSR(rowptr[k_off:k_off + keys].view(s.n_rel, s.n_rows + 1), col[e_off:e_off + s.n_edges],
+                           perm[e_off:e_off + s.n_edges], s))
+            k_off += keys
+            e_off += s.n_edges
+        ws_bytes = lib.agnn_csr_build_workspace(len(chunk), arr)
+        if ws_bytes == 0:
+            raise _lib.AgnnError("agnn_csr_build_workspace: " + lib.agnn_last_error().decode())
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        _lib.check(lib.agnn_csr_build(len(chunk), arr, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
+                                      status.data_ptr(), ws.data_ptr(), ws_bytes, stream), "agnn_csr_build")
+    if validate and int(status.item()) != 0:
+        raise ValueError("edge_index contains node ids outside [0, num_nodes)")
+    return out
+
+
+class TypedCSR:
+    """In-tree convention: ``fwd`` reduces at ``edge_index[0]`` (rows) reading
+    ``edge_index[1]``; ``bwd`` is the transposed graph.  ``n_rel`` relations with
+    codes ``0..n_rel-1`` in ``edge_type`` (``None`` = a single relation)."""
+
+    def __init__(self, edge_index, edge_type, n_rows, n_cols=None, n_rel=1, reduce_row=0, validate=False):
+        n_cols = n_rows if n_cols is None else n_cols
+        r, c = edge_index[reduce_row], edge_index[1 - reduce_row]
+        self.fwd, self.bwd = build_csr(
+            [Segment(r, c, n_rows, n_cols, edge_type, n_rel), Segment(c, r, n_cols, n_rows, edge_type, n_rel)],
+            validate=validate)
+        self.n_rows, self.n_cols, self.n_rel = int(n_rows), int(n_cols), int(n_rel)
+        self.n_edges = int(edge_index.shape[1])
+
+
+class HeteroCSR:
+    """PyG convention for an ``edge_index_dict``: per edge type ``(src, rel, dst)``
+    ``fwd[et]`` has rows = dst nodes / cols = src ids, ``bwd[et]`` rows = src nodes /
+    cols = dst ids."""
+
+    def __init__(self, edge_index_dict, num_nodes: Dict[str, int], validate=False):
+        self.edge_types: List[Tuple[str, str, str]] = [tuple(et) for et in edge_index_dict.keys()]
+        self.num_nodes = {k: int(v) for k, v in num_nodes.items()}
+        segs = []
+        for et in self.edge_types:
+            ei = edge_index_dict[et]
+            ns, nd = self.num_nodes[et[0]], self.num_nodes[et[2]]
+            segs.append(Segment(ei[1], ei[0], nd, ns))
+            segs.append(Segment(ei[0], ei[1], ns, nd))
+        built = build_csr(segs, validate=validate)
+        self.fwd = {et: built[2 * i] for i, et in enumerate(self.edge_types)}
+        self.bwd = {et: built[2 * i + 1] for i, et in enumerate(self.edge_types)}
+        self.n_edges = {et: self.fwd[et].n_edges for et in self.edge_types}
+
+
+# ---------------------------------------------------------------------- cache
+
+class _StructureCache:
+    """Small LRU keyed on tensor identity + version.  Entries hold the index
+    tensors, so an address can never be recycled under a live key."""
+
+    def __init__(self, capacity=8):
+        self.capacity = capacity
+        self.entries: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+    def get(self, tensors: Sequence[torch.Tensor], extra: tuple, make):
+        key = tuple((id(t), t._version, tuple(t.shape)) for t in tensors) + extra
+        hit = self.entries.get(key)
+        if hit is not None:
+            self.entries.move_to_end(key)
+            return hit[1]
+        value = make()
+        self.entries[key] = (list(tensors), value)
+        while len(self.entries) > self.capacity:
+            self.entries.popitem(last=False)
+        return value
+
+    def clear(self):
+        self.entries.clear()
+
+
+_cache = _StructureCache()
+
+
+def clear_cache():
+    _cache.clear()
+
+
+def typed_csr(edge_index, edge_type, n_rows, n_rel, reduce_row=0, n_cols=None) -> TypedCSR:
+    tensors = [edge_index] + ([edge_type] if edge_type is not None else [])
+    return _cache.get(tensors, ("typed", int(n_rows), int(n_cols or n_rows), int(n_rel), reduce_row),
+                      lambda: TypedCSR(edge_index, edge_type, n_rows, n_cols, n_rel, reduce_row))
+
+
+def hetero_csr(edge_index_dict, num_nodes: Dict[str, int]) -> HeteroCSR:
+    if isinstance(edge_index_dict, HeteroCSR):
+        return edge_index_dict
+    ets = list(edge_index_dict.keys())
+    tensors = [edge_index_dict[et] for et in ets]
+    extra = ("hetero", tuple(ets), tuple(sorted(num_nodes.items())))
+    return _cache.get(tensors, extra, lambda: HeteroCSR(edge_index_dict, num_nodes))

@@ -1,0 +1,284 @@
+"""Thin Python wrappers over the C ABI + the autograd Functions built from them.
+
+Tensors cross the boundary as raw device pointers (``tensor.data_ptr()``) on the
+current CUDA stream; nothing here allocates inside the library or synchronises.
+Dense contractions go through ``linalg`` (this repo's GEMM entry points).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, linalg
+from .graph import CSR, HeteroCSR, TypedCSR
+
+_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported feature dtype {t.dtype} (float32 and bfloat16 only)") from None
+
+
+def _rows2d(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{what} must be a 2-D view with unit column stride")
+    if not t.is_cuda:
+        raise _lib.AgnnError(f"{what} must be a CUDA tensor: analysisgnn_b200 has no CPU path")
+    return t
+
+
+@dataclass
+class Rel:
+    """One relation of a fused gather launch (mirrors agnn_rel_t)."""
+    rowptr: torch.Tensor                     # int32 [n_rows + 1]
+    col: torch.Tensor                        # int32, base that rowptr values index into
+    src: torch.Tensor                        # [n_src, F] view, unit column stride
+    out_col: int = 0
+    nbr_deg_rowptr: Optional[torch.Tensor] = None
+    flags: int = 0
+
+
+def _pack(rels: Sequence[Rel], n_feat: int, dtype) -> "ctypes.Array":
+    if not 1 <= len(rels) <= _lib.MAX_REL:
+        raise ValueError(f"1..{_lib.MAX_REL} relations per launch, got {len(rels)}")
+    arr = (_lib.Rel * len(rels))()
+    for i, r in enumerate(rels):
+        src = _rows2d(r.src, "src")
+        if src.dtype != dtype or src.shape[1] != n_feat:
+            raise ValueError("all gathered matrices must share dtype and feature count with the output")
+        arr[i].rowptr = r.rowptr.data_ptr()
+        arr[i].col = r.col.data_ptr()
+        arr[i].src = src.data_ptr()
+        arr[i].ld_src = src.stride(0)
+        arr[i].nbr_deg_rowptr = r.nbr_deg_rowptr.data_ptr() if r.nbr_deg_rowptr is not None else None
+        arr[i].out_col = int(r.out_col)
+        arr[i].flags = int(r.flags)
+    return arr
+
+
+def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: bool, concat: bool,
+                  self_add: Optional[torch.Tensor] = None, copy: Optional[torch.Tensor] = None,
+                  copy_col: int = 0) -> torch.Tensor:
+    """agnn_gather_reduce on ``out`` ([n_rows, >= n_feat] view).  See include/agnn.h."""
+    out = _rows2d(out, "out")
+    n_rows = out.shape[0]
+    arr = _pack(rels, n_feat, out.dtype)
+    sa = _rows2d(self_add, "self_add") if self_add is not None else None
+    cp = _rows2d(copy, "copy") if copy is not None else None
+    stream = torch.cuda.current_stream(out.device).cuda_stream
+    _lib.check(_lib.lib().agnn_gather_reduce(
+        n_rows, n_feat, _dtype_code(out), _lib.SCALE_MEAN if mean else _lib.SCALE_NONE,
+        _lib.COMBINE_CONCAT if concat else _lib.COMBINE_SUM, len(rels), arr,
+        sa.data_ptr() if sa is not None else None, sa.stride(0) if sa is not None else 0,
+        cp.data_ptr() if cp is not None else None, cp.stride(0) if cp is not None else 0, int(copy_col),
+        out.data_ptr(), out.stride(0), stream), "agnn_gather_reduce")
+    return out
+
+
+def rowscale_sum(rels: Sequence[Rel], inp: torch.Tensor, out: torch.Tensor, n_feat: int,
+                 base: Optional[torch.Tensor] = None) -> torch.Tensor:
+    inp, out = _rows2d(inp, "in"), _rows2d(out, "out")
+    arr = (_lib.Rel * len(rels))()
+    for i, r in enumerate(rels):
+        arr[i].rowptr = r.rowptr.data_ptr()
+        arr[i].out_col = int(r.out_col)
+        arr[i].flags = int(r.flags)
+    b = _rows2d(base, "base") if base is not None else None
+    stream = torch.cuda.current_stream(out.device).cuda_stream
+    _lib.check(_lib.lib().agnn_rowscale_sum(
+        out.shape[0], n_feat, _dtype_code(out), len(rels), arr, inp.data_ptr(), inp.stride(0),
+        b.data_ptr() if b is not None else None, b.stride(0) if b is not None else 0,
+        out.data_ptr(), out.stride(0), stream), "agnn_rowscale_sum")
+    return out
+
+
+# ------------------------------------------------------------------------------
+# single-relation segmented reductions with autograd (MetricalConvLayer scatters,
+# onset pooling, MetricalGNN beat/measure initialisation)
+# ------------------------------------------------------------------------------
+
+class _SegmentReduce(torch.autograd.Function):
+    """out[i] = s_i * (self_i + sum_{k in row i} src[col[k]])  on ``csr.fwd`` relation 0;
+    backward runs the same kernel on ``csr.bwd``."""
+
+    @staticmethod
+    def forward(ctx, src, self_add, csr: TypedCSR, mean: bool):
+        src = src.contiguous()
+        f = src.shape[1]
+        out = torch.empty((csr.n_rows, f), dtype=src.dtype, device=src.device)
+        sa = self_add.contiguous() if self_add is not None else None
+        gather_reduce([Rel(csr.fwd.rowptr[0], csr.fwd.col, src)], out, f, mean=mean, concat=True, self_add=sa)
+        ctx.csr, ctx.mean, ctx.has_self = csr, mean, self_add is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        csr, f = ctx.csr, g.shape[1]
+        g = g.contiguous()
+        d_src = torch.empty((csr.n_cols, f), dtype=g.dtype, device=g.device)
+        deg = csr.fwd.rowptr[0] if ctx.mean else None
+        gather_reduce([Rel(csr.bwd.rowptr[0], csr.bwd.col, g, nbr_deg_rowptr=deg)], d_src, f, mean=False,
+                      concat=True)
+        d_self = None
+        if ctx.has_self:
+            if ctx.mean:
+                d_self = torch.empty_like(g)
+                rowscale_sum([Rel(csr.fwd.rowptr[0], csr.fwd.col, g)], g, d_self, f)
+            else:
+                d_self = g
+        return d_src, d_self, None, None
+
+
+def segment_sum(src, csr: TypedCSR):
+    """``scatter_add(src[e_gather], e_reduce, out=zeros)`` (gnn.py:511,539; hgnn.py:406-407)."""
+    return _SegmentReduce.apply(src, None, csr, False)
+
+
+def segment_mean_self(src, self_add, csr: TypedCSR):
+    """``scatter(src[e_gather], e_reduce, out=self.clone(), reduce='mean')`` (gnn.py:74; analysis.py:586)."""
+    return _SegmentReduce.apply(src, self_add, csr, True)
+
+
+# ------------------------------------------------------------------------------
+# in-tree HeteroConv{SageConvScatter}: one fused layer
+# ------------------------------------------------------------------------------
+
+class _IntreeSageLayer(torch.autograd.Function):
+    """All relations of a reference ``HeteroConv(module=SageConvScatter)`` layer
+    (analysisgnn/models/core/hgnn.py:479-484 over gnn.py:62-76) in 2 GEMMs + 1 gather:
+
+        H = x Wn_cat^T + bn_cat                              [N, R*F]
+        A = [x || S_1 .. S_R],  S_r = (x + sum_j H_r[j]) / max(deg_r, 1)  (H_r itself if E_r == 0)
+        Z = A Wc^T + bc                                      [N, F']
+
+    ``Wc``/``bc`` carry the relation reduction (mean or sum) folded in by the caller.
+    """
+
+    @staticmethod
+    def forward(ctx, x, wn_cat, bn_cat, wc, bc, csr: TypedCSR):
+        x = x.contiguous()
+        n, f = x.shape
+        r = csr.n_rel
+        h = linalg.linear(x, wn_cat, bn_cat)                                     # [N, R*F]
+        a = torch.empty((n, (r + 1) * f), dtype=x.dtype, device=x.device)
+        rels = [Rel(csr.fwd.rowptr[k], csr.fwd.col, h[:, k * f:(k + 1) * f], out_col=(k + 1) * f,
+                    flags=_lib.REL_IDENTITY_IF_EMPTY) for k in range(r)]
+        gather_reduce(rels, a, f, mean=True, concat=True, self_add=x, copy=x, copy_col=0)
+        z = linalg.linear(a, wc, bc)
+        ctx.save_for_backward(x, a, wn_cat, wc)
+        ctx.csr = csr
+        ctx.has_bias = (bn_cat is not None, bc is not None)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, a, wn_cat, wc = ctx.saved_tensors
+        csr, (n, f), r = ctx.csr, x.shape, ctx.csr.n_rel
+        dz = dz.contiguous()
+        da = linalg.mm(dz, wc)                                                   # [N, (R+1)F]
+        dwc = linalg.mm_tn(dz, a) if ctx.needs_input_grad[3] else None
+        dbc = dz.sum(0) if ctx.has_bias[1] and ctx.needs_input_grad[4] else None
+        dh = torch.empty((n, r * f), dtype=x.dtype, device=x.device)
+        rels_t = [Rel(csr.bwd.rowptr[k], csr.bwd.col, da[:, (k + 1) * f:(k + 2) * f], out_col=k * f,
+                      nbr_deg_rowptr=csr.fwd.rowptr[k], flags=_lib.REL_IDENTITY_IF_EMPTY) for k in range(r)]
+        gather_reduce(rels_t, dh, f, mean=False, concat=True)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            rels_s = [Rel(csr.fwd.rowptr[k], csr.fwd.col, da, out_col=(k + 1) * f,
+                          flags=_lib.REL_IDENTITY_IF_EMPTY) for k in range(r)]
+            rowscale_sum(rels_s, da, dx, f, base=da[:, :f])
+            linalg.mm(dh, wn_cat, out=dx, accumulate=True)
+        dwn = linalg.mm_tn(dh, x) if ctx.needs_input_grad[1] else None
+        dbn = dh.sum(0) if ctx.has_bias[0] and ctx.needs_input_grad[2] else None
+        return dx, dwn, dbn, dwc, dbc, None
+
+
+def intree_sage_layer(x, wn_cat, bn_cat, wc, bc, csr: TypedCSR):
+    return _IntreeSageLayer.apply(x, wn_cat, bn_cat, wc, bc, csr)
+
+
+# ------------------------------------------------------------------------------
+# PyG-style HeteroConv{SAGEConv}: one fused layer over all node types
+# ------------------------------------------------------------------------------
+
+class _HeteroSageLayer(torch.autograd.Function):
+    """PyG ``HeteroConv({et: SAGEConv}, aggr)`` (+ optional ReLU) for every destination
+    type at once.  Per destination type t with incoming relations r_1..r_k:
+
+        A_t = [x_t || mean_{r_1}(x_src) || .. || mean_{r_k}(x_src)]    (one gather launch)
+        out_t = A_t [sum_r Wr_r | Wl_1 | .. | Wl_k]^T + sum_r b_r      (one GEMM)
+
+    argument layout: (plan, csr, relu, *tensors) with tensors = x per node type
+    (plan.node_types order), then (Wcat_t, b_t) per destination type.
+    """
+
+    @staticmethod
+    def forward(ctx, plan, csr: HeteroCSR, relu: bool, *tensors):
+        nt = len(plan.node_types)
+        xs = {t: tensors[i].contiguous() for i, t in enumerate(plan.node_types)}
+        outs, saved = [], []
+        for j, t in enumerate(plan.dst_types):
+            wcat, bias = tensors[nt + 2 * j], tensors[nt + 2 * j + 1]
+            x_t = xs[t]
+            f = x_t.shape[1]
+            rel_list = plan.incoming[t]
+            a = torch.empty((x_t.shape[0], (len(rel_list) + 1) * f), dtype=x_t.dtype, device=x_t.device)
+            rels = [Rel(csr.fwd[et].rowptr[0], csr.fwd[et].col, xs[et[0]], out_col=(k + 1) * f)
+                    for k, et in enumerate(rel_list)]
+            gather_reduce(rels, a, f, mean=True, concat=True, copy=x_t, copy_col=0)
+            o = linalg.linear(a, wcat, bias, relu=relu)
+            outs.append(o)
+            saved += [a, wcat, o]
+        ctx.save_for_backward(*saved)
+        ctx.plan, ctx.csr, ctx.relu = plan, csr, relu
+        ctx.feat = {t: xs[t].shape[1] for t in plan.node_types}
+        ctx.rows = {t: xs[t].shape[0] for t in plan.node_types}
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        plan, csr = ctx.plan, ctx.csr
+        nt = len(plan.node_types)
+        grads = [None] * (nt + 2 * len(plan.dst_types))
+        da = {}
+        for j, t in enumerate(plan.dst_types):
+            a, wcat, o = ctx.saved_tensors[3 * j:3 * j + 3]
+            g = douts[j]
+            if g is None:
+                continue
+            g = linalg.relu_backward(g, o) if ctx.relu else g.contiguous()
+            da[t] = linalg.mm(g, wcat)
+            if ctx.needs_input_grad[3 + nt + 2 * j]:
+                grads[nt + 2 * j] = linalg.mm_tn(g, a)
+            if ctx.needs_input_grad[3 + nt + 2 * j + 1]:
+                grads[nt + 2 * j + 1] = g.sum(0)
+        for i, s in enumerate(plan.node_types):
+            if not ctx.needs_input_grad[3 + i]:
+                continue
+            f = ctx.feat[s]
+            rels = []
+            for et in plan.outgoing[s]:
+                dst = et[2]
+                if dst not in da:
+                    continue
+                k = plan.incoming[dst].index(et)
+                rels.append(Rel(csr.bwd[et].rowptr[0], csr.bwd[et].col, da[dst][:, (k + 1) * f:(k + 2) * f],
+                                nbr_deg_rowptr=csr.fwd[et].rowptr[0]))
+            root = da[s][:, :f] if s in da else None
+            if not rels:
+                grads[i] = root.contiguous() if root is not None else None
+                continue
+            dx = torch.empty((ctx.rows[s], f), dtype=rels[0].src.dtype, device=rels[0].src.device)
+            gather_reduce(rels, dx, f, mean=False, concat=False, self_add=root)
+            grads[i] = dx
+        return (None, None, None, *grads)
+
+
+def hetero_sage_layer(plan, csr: HeteroCSR, relu: bool, xs: Sequence[torch.Tensor], params: Sequence[torch.Tensor]):
+    return _HeteroSageLayer.apply(plan, csr, relu, *xs, *params)

@@ -1,0 +1,142 @@
+/*
+ * agnn.h -- C ABI of libagnn.so: the B200 (sm_100a) kernels behind AnalysisGNN's
+ * heterogeneous message-passing hot path.
+ *
+ * The reference (manoskary/analysisgnn) is 100% Python and has no FFI: the seam
+ * is a set of torch.nn.Module forward calls.  Each entry point below names the
+ * reference code whose arithmetic it replaces (paths relative to the reference
+ * root).  The host-side mirror of those modules lives in analysisgnn_b200/nn/ and
+ * reaches this library through ctypes (analysisgnn_b200/_lib.py); INTEGRATION.md
+ * shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless a parameter is
+ *     documented as a host array (the small descriptor arrays are host arrays
+ *     that are copied into kernel parameters at launch);
+ *   - no allocation, no synchronisation, no host<->device copy inside: every
+ *     call only enqueues kernels on `stream` (a cudaStream_t), so calls can be
+ *     captured in CUDA graphs;
+ *   - return value 0 = ok, negative = error (agnn_last_error() gives the text,
+ *     thread-local);
+ *   - feature matrices are row-major; `ld_*` are row strides in ELEMENTS;
+ *     rows must be 16-byte aligned (ld * sizeof(elem) % 16 == 0) and the feature
+ *     count a multiple of 4 (f32) / 8 (bf16);
+ *   - index outputs are int32; COO inputs are int64 as PyTorch / PyG hand them over.
+ */
+#ifndef AGNN_H_
+#define AGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* agnn_stream_t; /* cudaStream_t */
+
+#define AGNN_OK 0
+#define AGNN_ERR_ARG (-1)
+#define AGNN_ERR_CUDA (-2)
+#define AGNN_ERR_WORKSPACE (-3)
+#define AGNN_ERR_UNSUPPORTED (-4)
+
+#define AGNN_F32 0
+#define AGNN_BF16 1
+
+#define AGNN_MAX_SEG 32 /* COO segments per agnn_csr_build call */
+#define AGNN_MAX_REL 16 /* relations fused in one gather / attention launch */
+
+int agnn_version(void);
+const char* agnn_last_error(void);
+
+/* ------------------------------------------------------------------ CSR build
+ * Replaces: the per-relation boolean mask + edge_index[:, mask] of
+ * analysisgnn/models/core/hgnn.py:480-483, and the index_sort / CSC conversion
+ * PyG's NeighborSampler does (third-party).
+ *
+ * One call converts up to AGNN_MAX_SEG COO segments to relation-major CSR.  For
+ * segment s, rows are ordered by (relation, row) and ties keep INPUT ORDER
+ * (stable), so results are bit-identical to a stable sort:
+ *   rowptr[rowptr_off + r*(n_rows+1) + i] .. [.. + i + 1]  delimit, inside the
+ *   segment's own block col[edge_off ..], the entries of row i of relation r;
+ *   col[.]  = gathered-side node id, perm[.] = input edge position.
+ * Edges whose etype is outside [0, n_rel) are dropped.  An edge with a node id
+ * out of range sets *status to 1 and is dropped (status must be zeroed by the
+ * caller; it is only ever written with 1).
+ */
+typedef struct agnn_coo {
+  const int64_t* row;   /* reduce-side node id of each edge           */
+  const int64_t* col;   /* gathered-side node id of each edge         */
+  const int64_t* etype; /* relation id of each edge, or NULL (all 0)  */
+  int64_t n_edges;
+  int32_t n_rows; /* node count on the reduce side   */
+  int32_t n_cols; /* node count on the gathered side */
+  int32_t n_rel;
+  int32_t reserved;
+  int64_t rowptr_off; /* element offset of this segment's [n_rel*(n_rows+1)] block in rowptr */
+  int64_t edge_off;   /* element offset of this segment's [n_edges] block in col / perm       */
+} agnn_coo_t;
+
+/* bytes of scratch agnn_csr_build needs for these segments (host arithmetic only) */
+size_t agnn_csr_build_workspace(int n_seg, const agnn_coo_t* segs /* host */);
+
+int agnn_csr_build(int n_seg, const agnn_coo_t* segs /* host */, int32_t* rowptr, int32_t* col,
+                   int32_t* perm, int32_t* status, void* workspace, size_t workspace_bytes,
+                   agnn_stream_t stream);
+
+/* ------------------------------------------------------------ gather-reduce
+ * Replaces: h[edge_index[1]] + torch_scatter.scatter(..., out=x.clone(),
+ * reduce='mean') of SageConvScatter (analysisgnn/models/core/gnn.py:70-74), the
+ * scatter_add pairs of MetricalConvLayer (gnn.py:511, 539) and MetricalGNN
+ * (hgnn.py:406-407), onset pooling (analysisgnn/models/analysis.py:586), PyG
+ * SAGEConv's mean aggregation (third-party) -- and, run on the transposed CSR,
+ * the backward of each.  Warp-per-row segmented reduction, no atomics; the sum
+ * over a row runs in CSR (= input edge) order, in fp32.
+ *
+ * For every row i and relation r:
+ *     acc_r = sum_{k in rowptr_r[i] .. rowptr_r[i+1]}  w_k * src_r[col_r[k], :]
+ *     w_k   = 1 / max(deg(col_r[k]), 1) from nbr_deg_rowptr if given, else 1
+ * AGNN_COMBINE_CONCAT:  out[i, out_col_r : +F] = s_i * (self_add[i] + acc_r)
+ * AGNN_COMBINE_SUM:     out[i, out_col_0 : +F] = self_add[i] + sum_r s_i,r * acc_r
+ *     s = 1 / max(deg_r(i), 1) with AGNN_SCALE_MEAN, 1 with AGNN_SCALE_NONE
+ * A relation flagged AGNN_REL_IDENTITY_IF_EMPTY that has no edges at all (checked on
+ * the device: rowptr_r[n_rows] == rowptr_r[0], so no host sync is needed)
+ * contributes src_r[i, :] itself, unscaled, without the self term: the reference's
+ * E == 0 branch, z = W [x || h] (gnn.py:67-69).
+ * If `copy` is given, out[i, copy_col : +F] = copy[i, :] (builds [x || S] rows).
+ */
+typedef struct agnn_rel {
+  const int32_t* rowptr; /* [n_rows + 1]                                        */
+  const int32_t* col;    /* base the rowptr values index into                   */
+  const void* src;       /* gathered matrix (column slice already applied)      */
+  int64_t ld_src;
+  const int32_t* nbr_deg_rowptr; /* optional [n_src + 1]: neighbour weights     */
+  int32_t out_col;
+  int32_t flags;
+} agnn_rel_t;
+
+#define AGNN_REL_IDENTITY_IF_EMPTY 1
+
+#define AGNN_SCALE_NONE 0
+#define AGNN_SCALE_MEAN 1
+#define AGNN_COMBINE_CONCAT 0
+#define AGNN_COMBINE_SUM 1
+
+int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
+                       const agnn_rel_t* rels /* host */, const void* self_add, int64_t ld_self,
+                       const void* copy, int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out,
+                       agnn_stream_t stream);
+
+/* out[i, :] = base[i, :] (if given) + sum_r in[i, in_col_r : +F] / max(deg_r(i), 1)
+ * -- the gradient of the self term of the mean_self reduction (gnn.py:74 backward).
+ * Relations flagged AGNN_REL_IDENTITY_IF_EMPTY that are empty are skipped.  Uses rels[r].rowptr,
+ * .out_col (as the column of `in`) and .flags only. */
+int agnn_rowscale_sum(int32_t n_rows, int32_t n_feat, int dtype, int n_rel, const agnn_rel_t* rels /* host */,
+                      const void* in, int64_t ld_in, const void* base, int64_t ld_base, void* out,
+                      int64_t ld_out, agnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGNN_H_ */
