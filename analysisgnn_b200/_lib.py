@@ -17,6 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 MAX_SEG = 32
 MAX_REL = 16
+HGT_MAX_HEADS = 16
 F32, BF16 = 0, 1
 SCALE_NONE, SCALE_MEAN = 0, 1
 COMBINE_CONCAT, COMBINE_SUM = 0, 1
@@ -38,6 +39,17 @@ class Rel(C.Structure):
                 ("nbr_deg_rowptr", C.c_void_p), ("out_col", C.c_int32), ("flags", C.c_int32)]
 
 
+class HgtRel(C.Structure):
+    _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("t_rowptr", C.c_void_p), ("t_col", C.c_void_p),
+                ("k", C.c_void_p), ("v", C.c_void_p), ("ld_kv", C.c_int64), ("dk", C.c_void_p), ("dv", C.c_void_p),
+                ("ld_dkv", C.c_int64), ("n_src", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ParamChunk(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("param_off", C.c_int64), ("arena_off", C.c_int64), ("count", C.c_int32),
+                ("param_aligned", C.c_int32)]
+
+
 _PROTOTYPES = {
     "agnn_version": (C.c_int, []),
     "agnn_last_error": (C.c_char_p, []),
@@ -49,9 +61,37 @@ _PROTOTYPES = {
                                      C.c_int64, C.c_void_p]),
     "agnn_rowscale_sum": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.POINTER(Rel), C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "agnn_hgt_attn_fwd": (C.c_int, [C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HgtRel), C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "agnn_hgt_attn_bwd_dst_blocks": (C.c_int, [C.c_int32]),
+    "agnn_hgt_attn_bwd_dst": (C.c_int, [C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HgtRel), C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                        C.c_void_p]),
+    "agnn_hgt_attn_bwd_src": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HgtRel), C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "agnn_optim_chunk_elems": (C.c_int, []),
+    "agnn_sumsq_blocks": (C.c_int, [C.c_int64]),
+    "agnn_sumsq_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "agnn_adamw_clip_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                       C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                       C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
+_launches = 0
+
+
+def count_launches(n: int) -> None:
+    """Book-keeping of kernels launched through the C ABI (reported by bench.py)."""
+    global _launches
+    _launches += n
+
+
+def launches() -> int:
+    return _launches
 
 
 def build(verbose: bool = False) -> str:

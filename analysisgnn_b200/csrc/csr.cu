@@ -260,7 +260,7 @@ struct Layout {
   size_t off_tiles, off_count, off_list, total;
 };
 
-int make_tables(int n_seg, const agnn_coo_t* segs, SegTable& tab, Layout& lay) {
+int make_tables(int n_seg, const agnn_coo_t* segs, SegTable& tab, Layout& lay, bool need_ptrs) {
   if (n_seg < 1 || n_seg > AGNN_MAX_SEG || !segs) return fail(AGNN_ERR_ARG, "csr_build: n_seg must be 1..%d", AGNN_MAX_SEG);
   tab.n_seg = n_seg;
   int64_t key_tiles = 0, edge_blks = 0, max_key_end = 0, edges = 0;
@@ -268,7 +268,7 @@ int make_tables(int n_seg, const agnn_coo_t* segs, SegTable& tab, Layout& lay) {
     const agnn_coo_t& g = segs[s];
     if (g.n_edges < 0 || g.n_rows < 0 || g.n_cols < 0 || g.n_rel < 1 || g.rowptr_off < 0 || g.edge_off < 0)
       return fail(AGNN_ERR_ARG, "csr_build: segment %d has a negative size or n_rel < 1", s);
-    if (g.n_edges > 0 && (!g.row || !g.col)) return fail(AGNN_ERR_ARG, "csr_build: segment %d has null COO pointers", s);
+    if (need_ptrs && g.n_edges > 0 && (!g.row || !g.col)) return fail(AGNN_ERR_ARG, "csr_build: segment %d has null COO pointers", s);
     const int64_t keys = (int64_t)g.n_rel * (g.n_rows + 1);
     if (g.n_edges >= (1ll << 31) || keys >= (1ll << 31) || g.edge_off + g.n_edges >= (1ll << 31))
       return fail(AGNN_ERR_UNSUPPORTED, "csr_build: segment %d exceeds int32 indexing", s);
@@ -302,7 +302,7 @@ using namespace agnn;
 extern "C" size_t agnn_csr_build_workspace(int n_seg, const agnn_coo_t* segs) {
   SegTable tab;
   Layout lay;
-  if (make_tables(n_seg, segs, tab, lay) != AGNN_OK) return 0;
+  if (make_tables(n_seg, segs, tab, lay, false) != AGNN_OK) return 0;
   return lay.total;
 }
 
@@ -310,7 +310,7 @@ extern "C" int agnn_csr_build(int n_seg, const agnn_coo_t* segs, int32_t* rowptr
                               int32_t* status, void* workspace, size_t workspace_bytes, agnn_stream_t stream_) {
   SegTable tab;
   Layout lay;
-  int rc = make_tables(n_seg, segs, tab, lay);
+  int rc = make_tables(n_seg, segs, tab, lay, true);
   if (rc != AGNN_OK) return rc;
   if (!rowptr || !status || !workspace) return fail(AGNN_ERR_ARG, "csr_build: null output pointer");
   if (workspace_bytes < lay.total)

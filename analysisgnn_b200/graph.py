@@ -99,6 +99,7 @@ def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) 
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
         _lib.check(lib.agnn_csr_build(len(chunk), arr, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
                                       status.data_ptr(), ws.data_ptr(), ws_bytes, stream), "agnn_csr_build")
+        _lib.count_launches(8 if any(s.n_edges for s in chunk) else 4)
     if validate and int(status.item()) != 0:
         raise ValueError("edge_index contains node ids outside [0, num_nodes)")
     return out
@@ -117,6 +118,17 @@ class TypedCSR:
             validate=validate)
         self.n_rows, self.n_cols, self.n_rel = int(n_rows), int(n_cols), int(n_rel)
         self.n_edges = int(edge_index.shape[1])
+        self._t = None
+
+    def t(self) -> "TypedCSR":
+        """The transposed graph (rows <-> cols) as a view on the same arrays."""
+        if self._t is None:
+            o = object.__new__(TypedCSR)
+            o.fwd, o.bwd = self.bwd, self.fwd
+            o.n_rows, o.n_cols, o.n_rel, o.n_edges = self.n_cols, self.n_rows, self.n_rel, self.n_edges
+            o._t = self
+            self._t = o
+        return self._t
 
 
 class HeteroCSR:
@@ -165,7 +177,7 @@ class _StructureCache:
         self.entries.clear()
 
 
-_cache = _StructureCache()
+_cache = _StructureCache(capacity=64)
 
 
 def clear_cache():
@@ -185,3 +197,83 @@ def hetero_csr(edge_index_dict, num_nodes: Dict[str, int]) -> HeteroCSR:
     tensors = [edge_index_dict[et] for et in ets]
     extra = ("hetero", tuple(ets), tuple(sorted(num_nodes.items())))
     return _cache.get(tensors, extra, lambda: HeteroCSR(edge_index_dict, num_nodes))
+
+
+def edge_csr(rows: torch.Tensor, n_rows: int) -> TypedCSR:
+    """CSR whose gathered side is the EDGE list itself (col = input edge position):
+    reduces per-edge messages ``[E, F]`` at ``rows`` without atomics."""
+    def make():
+        ids = torch.arange(rows.numel(), dtype=torch.long, device=rows.device)
+        return TypedCSR(torch.stack((rows, ids)), None, n_rows, n_cols=int(rows.numel()))
+    return _cache.get([rows], ("edge", int(n_rows)), make)
+
+
+def derived(t: torch.Tensor, key: tuple, make):
+    """Cache a tensor derived from index tensor ``t`` (per batch, like the CSR)."""
+    return _cache.get([t], ("derived",) + key, make)
+
+
+class SequenceLayout:
+    """How a flat ``[n, C]`` node matrix maps to padded ``[B, T, C]`` sequences
+    (uniform lengths = a view; ragged = zero padding)."""
+
+    def __init__(self, sizes: Sequence[int], device):
+        self.sizes = [int(v) for v in sizes]
+        self.n = sum(self.sizes)
+        self.t = max(self.sizes) if self.sizes else 0
+        self.uniform = all(v == self.t for v in self.sizes)
+        if not self.uniform:
+            sz = torch.tensor(self.sizes, dtype=torch.long, device=device)
+            valid = torch.arange(self.t, device=device).unsqueeze(0) < sz.unsqueeze(1)     # [B, T]
+            self.flat_index = valid.reshape(-1).nonzero(as_tuple=False).squeeze(1)          # padded slot of node k
+            self.n_slots = len(self.sizes) * self.t
+
+    @staticmethod
+    def from_lengths(lengths: Optional[torch.Tensor], n: int) -> "SequenceLayout":
+        """``lengths`` as in analysisgnn/models/core/gnn.py:506-521: ``None`` = one sequence;
+        all-equal entries = that many nodes per sequence; otherwise a cumulative pointer
+        whose differences are the sequence lengths.  One device->host copy (cached)."""
+        if lengths is None:
+            return SequenceLayout([n], None)
+        host = lengths.detach().cpu().tolist()
+        if all(v == host[0] for v in host):
+            t = int(host[0])
+            return SequenceLayout([t] * (n // t if t else 0), lengths.device)
+        return SequenceLayout([b - a for a, b in zip(host[:-1], host[1:])], lengths.device)
+
+    def pad(self, x: torch.Tensor) -> torch.Tensor:
+        if self.uniform:
+            return x.view(-1, self.t, x.shape[1])
+        out = x.new_zeros((self.n_slots, x.shape[1]))
+        out.index_copy_(0, self.flat_index, x)
+        return out.view(-1, self.t, x.shape[1])
+
+    def unpad(self, h: torch.Tensor) -> torch.Tensor:
+        flat = h.reshape(-1, h.shape[-1])
+        return flat if self.uniform else flat.index_select(0, self.flat_index)
+
+
+def sequence_layout(lengths: Optional[torch.Tensor], n: int) -> SequenceLayout:
+    if lengths is None:
+        return SequenceLayout.from_lengths(None, n)
+    return _cache.get([lengths], ("seq", int(n)), lambda: SequenceLayout.from_lengths(lengths, n))
+
+
+def batch_layout(batch: torch.Tensor) -> SequenceLayout:
+    """Sequences = runs of equal graph id in a sorted PyG ``batch`` vector
+    (``x.split(bincount(batch))``, analysisgnn/models/cadence.py:276-279)."""
+    def make():
+        counts = torch.bincount(batch).cpu().tolist() if batch.numel() else []
+        return SequenceLayout([c for c in counts], batch.device)
+    base = batch._base if batch._base is not None else batch
+    return _cache.get([base], ("batch", int(batch.numel()), int(batch.storage_offset())), make)
+
+
+def hetero_csr_trimmed(edge_index_dict, n_edges: Dict[Tuple[str, str, str], int], num_nodes: Dict[str, int]) -> "HeteroCSR":
+    """``HeteroCSR`` of the first ``n_edges[et]`` edges of every type (what
+    ``trim_to_layer`` leaves for a deeper layer), cached on the untrimmed tensors."""
+    ets = list(edge_index_dict.keys())
+    tensors = [edge_index_dict[et] for et in ets]
+    extra = ("trim", tuple(ets), tuple(int(n_edges[et]) for et in ets), tuple(sorted(num_nodes.items())))
+    return _cache.get(tensors, extra, lambda: HeteroCSR(
+        {et: edge_index_dict[et][:, : int(n_edges[et])] for et in ets}, num_nodes))

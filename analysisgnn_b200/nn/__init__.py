@@ -1,0 +1,19 @@
+"""Drop-in ``torch.nn.Module``s for the message-passing hot path.
+
+Same class names, constructor arguments, forward arguments and ``state_dict``
+keys as the modules they replace, so reference checkpoints load unchanged:
+
+* ``intree``  -- ``SageConvScatter``, ``HeteroConv``, ``MetricalConvLayer``,
+  ``MetricalGNN`` of ``analysisgnn/models/core/{gnn,hgnn}.py``;
+* ``hetero``  -- the PyG / graphmuse shaped encoders built at
+  ``analysisgnn/models/analysis.py:444-473`` (``HybridGNN``, ``HybridHGT``,
+  ``MetricalGNN``) and their layers;
+* ``shell``   -- the hot-path part of ``TorchAnalysisGNN``
+  (``analysisgnn/models/analysis.py:421-591``).
+
+Every forward runs on libagnn.so's CUDA kernels; there is no CPU path.
+"""
+from .intree import HeteroConv, MetricalConvLayer, MetricalGNN, SageConvScatter  # noqa: F401
+from .hetero import (HeteroSAGELayer, HeteroSAGEStack, HGTConv, HeteroHGTStack, HybridGNN, HybridHGT,  # noqa: F401
+                     SAGEConv, SequenceBranch)
+from .shell import AnalysisEncoder, multitask_ce  # noqa: F401

@@ -1,0 +1,400 @@
+"""CUDA-backed PyG / graphmuse shaped encoders.
+
+The reference builds its production encoder from the third-party graphmuse package
+(``HybridGNN`` / ``HybridHGT`` / ``MetricalGNN``, analysisgnn/models/analysis.py:9,
+444-473) on top of torch_geometric's ``HeteroConv`` / ``SAGEConv`` / ``HGTConv``.
+Neither is part of the reference tree; the wiring below follows the reference's
+in-tree statement of the same stack (analysisgnn/models/cadence.py:142-176,
+229-332) and the published PyG >= 2.3 operator semantics, as fixed by this
+repo's oracle (oracle/pyg.py).  Constructor / forward
+arguments are those of the call site analysisgnn/models/analysis.py:444-473,
+576-579; parameter names follow PyG (``convs.<i>.convs.<src>__<rel>__<dst>.lin_l``).
+
+Convention (PyG): ``edge_index[0]`` = source j, ``edge_index[1]`` = target i.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import graph, ops
+
+EdgeType = Tuple[str, str, str]
+
+
+def rel_key(edge_type) -> str:
+    return "__".join(edge_type)
+
+
+class SAGEConv(nn.Module):
+    """Parameter holder of one ``SAGEConv(in, out, aggr='mean', root_weight=True)``:
+    ``lin_l(mean_j x_j) + lin_r(x_i)``.  The arithmetic runs in ``HeteroSAGELayer``
+    for all relations at once; calling this module alone runs the same fused path
+    for a single relation."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_l = nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self):
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+
+    def forward(self, x_src, x_dst, edge_index):
+        same = x_src is x_dst
+        types = ("n", "n") if same else ("s", "d")
+        et = (types[0], "to", types[1])
+        plan = LayerPlan([et], [et])
+        x_dict = {"n": x_dst} if same else {"s": x_src, "d": x_dst}
+        csr = graph.hetero_csr({et: edge_index}, {k: v.shape[0] for k, v in x_dict.items()})
+        wcat = torch.cat((self.lin_r.weight, self.lin_l.weight), dim=1)
+        xs = [x_dict[t] for t in plan.node_types]
+        return ops.hetero_sage_layer(plan, csr, False, xs, [wcat, self.lin_l.bias])[0]
+
+
+class LayerPlan:
+    """Static wiring of one hetero layer for the edge types present in a batch."""
+
+    def __init__(self, layer_edge_types: List[EdgeType], present: List[EdgeType], only_dst=None):
+        present_set = set(present)
+        self.edge_types = [et for et in layer_edge_types if et in present_set
+                           and (only_dst is None or et[2] in only_dst)]
+        self.incoming: Dict[str, List[EdgeType]] = {}
+        self.outgoing: Dict[str, List[EdgeType]] = {}
+        for et in self.edge_types:
+            self.incoming.setdefault(et[2], []).append(et)
+            self.outgoing.setdefault(et[0], []).append(et)
+        self.dst_types = list(self.incoming.keys())
+        seen = []
+        for et in self.edge_types:
+            for t in (et[0], et[2]):
+                if t not in seen:
+                    seen.append(t)
+        self.node_types = seen
+        for t in self.node_types:
+            self.outgoing.setdefault(t, [])
+
+
+class HeteroSAGELayer(nn.Module):
+    """PyG ``HeteroConv({et: SAGEConv(in, out)}, aggr)`` as one gather launch + one
+    GEMM per destination node type (ops.hetero_sage_layer)."""
+
+    def __init__(self, edge_types, in_channels, out_channels, aggr="sum"):
+        super().__init__()
+        if aggr not in ("sum", "mean"):
+            raise NotImplementedError(f"aggr={aggr!r}")
+        self.edge_types = [tuple(et) for et in edge_types]
+        self.aggr = aggr
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.convs = nn.ModuleDict({rel_key(et): SAGEConv(in_channels, out_channels) for et in self.edge_types})
+        self._plans = {}
+
+    def reset_parameters(self):
+        for c in self.convs.values():
+            c.reset_parameters()
+
+    def plan_for(self, x_dict, ei_dict, only_dst=None) -> LayerPlan:
+        present = tuple(et for et in self.edge_types if et in ei_dict and et[0] in x_dict and et[2] in x_dict)
+        key = (present, None if only_dst is None else tuple(only_dst))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = LayerPlan(self.edge_types, list(present), only_dst)
+        return plan
+
+    def forward(self, x_dict, ei_dict, csr: Optional[graph.HeteroCSR] = None, relu: bool = False, only_dst=None):
+        """``only_dst``: compute these destination types only (the caller consumes nothing else)."""
+        plan = self.plan_for(x_dict, ei_dict, only_dst)
+        if csr is None:
+            csr = graph.hetero_csr({et: ei_dict[et] for et in plan.edge_types},
+                                   {t: x_dict[t].shape[0] for t in plan.node_types})
+        params = []
+        for t in plan.dst_types:
+            convs = [self.convs[rel_key(et)] for et in plan.incoming[t]]
+            scale = 1.0 / len(convs) if self.aggr == "mean" else 1.0
+            w_root = torch.stack([c.lin_r.weight for c in convs], dim=0).sum(0) if len(convs) > 1 \
+                else convs[0].lin_r.weight
+            wcat = torch.cat([w_root] + [c.lin_l.weight for c in convs], dim=1)
+            bias = torch.stack([c.lin_l.bias for c in convs], dim=0).sum(0) if len(convs) > 1 else convs[0].lin_l.bias
+            if scale != 1.0:
+                wcat, bias = wcat * scale, bias * scale
+            params += [wcat, bias]
+        outs = ops.hetero_sage_layer(plan, csr, relu, [x_dict[t] for t in plan.node_types], params)
+        return dict(zip(plan.dst_types, outs))
+
+
+def trim_counts(layer: int, counts: List[int]) -> int:
+    """How many trailing entries ``trim_to_layer`` has dropped in total by ``layer``
+    (applied cumulatively to already-trimmed tensors, cadence.py:165-174)."""
+    return sum(counts[-k] for k in range(1, layer + 1)) if layer > 0 else 0
+
+
+def trim_inputs(layer, nodes_per_hop, edges_per_hop, x_dict, ei_dict):
+    """``torch_geometric.utils.trim_to_layer`` for dict inputs, one step (as called in
+    cadence.py:166-173): drop the outermost remaining hop's nodes and edges."""
+    if layer <= 0 or edges_per_hop is None:
+        return x_dict, ei_dict
+    x_dict = {k: v[: v.size(0) - nodes_per_hop[k][-layer]] for k, v in x_dict.items()}
+    ei_dict = {k: v[:, : v.size(1) - edges_per_hop[k][-layer]] for k, v in ei_dict.items()}
+    return x_dict, ei_dict
+
+
+def _layer_structures(conv_layers, x_dict, ei_dict, nodes_per_hop, edges_per_hop, plan_of):
+    """One ``HeteroCSR`` per layer (trimmed edge lists differ per layer), built in a
+    single batched agnn_csr_build pass and cached per batch."""
+    ets = list(ei_dict.keys())
+    sizes = {t: v.shape[0] for t, v in x_dict.items()}
+    if edges_per_hop is None:
+        csr = graph.hetero_csr(ei_dict, sizes)
+        return [csr] * len(conv_layers)
+    out = []
+    n_cur = dict(sizes)
+    e_cur = {et: ei_dict[et].shape[1] for et in ets}
+    for i in range(len(conv_layers)):
+        if i > 0:
+            n_cur = {t: n_cur[t] - nodes_per_hop[t][-i] for t in n_cur}
+            e_cur = {et: e_cur[et] - edges_per_hop[et][-i] for et in ets}
+        # slicing keeps the parent's storage, so the cache key uses (parent, length)
+        out.append(graph.hetero_csr_trimmed(ei_dict, dict(e_cur), dict(n_cur)))
+    return out
+
+
+class HeteroSAGEStack(nn.Module):
+    """cadence.py:142-176: ``trim_to_layer -> HeteroConv{SAGEConv}(aggr='sum') -> relu``, L times."""
+
+    def __init__(self, edge_types, in_channels, hidden_channels, num_layers, aggr="sum"):
+        super().__init__()
+        self.convs = nn.ModuleList(
+            HeteroSAGELayer(edge_types, in_channels if i == 0 else hidden_channels, hidden_channels, aggr)
+            for i in range(num_layers))
+
+    def forward(self, x_dict, ei_dict, nodes_per_hop=None, edges_per_hop=None, collect=None, final_types=None):
+        """``final_types``: node types the caller reads from the result; the last layer skips the rest
+        (PyG computes and discards them)."""
+        structures = _layer_structures(self.convs, x_dict, ei_dict, nodes_per_hop, edges_per_hop, None)
+        last = len(self.convs) - 1
+        for i, conv in enumerate(self.convs):
+            x_dict, ei_dict = trim_inputs(i, nodes_per_hop, edges_per_hop, x_dict, ei_dict)
+            x_dict = conv(x_dict, ei_dict, csr=structures[i], relu=True, only_dst=final_types if i == last else None)
+            if collect is not None:
+                collect.append(x_dict)
+        return x_dict
+
+
+# ------------------------------------------------------------------------ HGT
+
+class HGTConv(nn.Module):
+    """PyG >= 2.3 ``HGTConv(in, out, metadata, heads)`` on the fused attention kernel
+    (agnn_hgt_attn_fwd / _bwd): per-node-type KQV projection, per-(relation, head)
+    ``k_rel`` / ``v_rel`` applied to the source type's k, v, ``p_rel`` scaling, softmax
+    over ALL incoming edges of a target across relations (``joint_softmax=True``; the
+    pre-2.3 per-relation softmax with ``False``), ``out_lin(gelu(.))``, gated skip."""
+
+    def __init__(self, in_channels, out_channels, metadata, heads=1, joint_softmax=True):
+        super().__init__()
+        if out_channels % heads:
+            raise ValueError("out_channels must be divisible by heads")
+        self.node_types = list(metadata[0])
+        self.edge_types = [tuple(et) for et in metadata[1]]
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.joint_softmax = joint_softmax
+        d = out_channels // heads
+        self.kqv_lin = nn.ModuleDict({t: nn.Linear(in_channels, 3 * out_channels) for t in self.node_types})
+        self.out_lin = nn.ModuleDict({t: nn.Linear(out_channels, out_channels) for t in self.node_types})
+        n_rel = len(self.edge_types)
+        self.k_rel = nn.Parameter(torch.empty(heads * n_rel, d, d))   # index = head * n_rel + relation
+        self.v_rel = nn.Parameter(torch.empty(heads * n_rel, d, d))
+        self.skip = nn.ParameterDict({t: nn.Parameter(torch.ones(1)) for t in self.node_types})
+        self.p_rel = nn.ParameterDict({rel_key(et): nn.Parameter(torch.ones(1, heads)) for et in self.edge_types})
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / math.sqrt(self.k_rel.shape[1])
+        nn.init.uniform_(self.k_rel, -bound, bound)
+        nn.init.uniform_(self.v_rel, -bound, bound)
+        for lin in list(self.kqv_lin.values()) + list(self.out_lin.values()):
+            lin.reset_parameters()
+        for p in self.skip.values():
+            nn.init.ones_(p)
+        for p in self.p_rel.values():
+            nn.init.ones_(p)
+
+    def forward(self, x_dict, ei_dict, csr: Optional[graph.HeteroCSR] = None, only_dst=None):
+        H, D = self.heads, self.out_channels // self.heads
+        n_rel = len(self.edge_types)
+        present = [et for et in self.edge_types if et in ei_dict and et[0] in x_dict and et[2] in x_dict]
+        if csr is None:
+            csr = graph.hetero_csr({et: ei_dict[et] for et in present}, {t: v.shape[0] for t, v in x_dict.items()})
+        kqv = {t: self.kqv_lin[t](x) for t, x in x_dict.items()}                # [N_t, 3*H*D] = k | q | v
+        hd = H * D
+        wk_all = self.k_rel.view(H, n_rel, D, D)
+        wv_all = self.v_rel.view(H, n_rel, D, D)
+        scale = 1.0 / math.sqrt(D)
+        by_dst: Dict[str, List[EdgeType]] = {}
+        for et in present:
+            by_dst.setdefault(et[2], []).append(et)
+        out_dict = {}
+        for dst, ets in by_dst.items():
+            if only_dst is not None and dst not in only_dst:
+                continue
+            q = kqv[dst][:, hd:2 * hd]
+            ks, vs, ps = [], [], []
+            for et in ets:
+                r = self.edge_types.index(et)
+                src = kqv[et[0]]
+                n_src = src.shape[0]
+                # relation-specific key / value of the source type: per head [N, D] @ [D, D]
+                k_r = torch.bmm(src[:, :hd].reshape(n_src, H, D).transpose(0, 1), wk_all[:, r]).transpose(0, 1)
+                v_r = torch.bmm(src[:, 2 * hd:].reshape(n_src, H, D).transpose(0, 1), wv_all[:, r]).transpose(0, 1)
+                ks.append(k_r.reshape(n_src, hd))
+                vs.append(v_r.reshape(n_src, hd))
+                ps.append(self.p_rel[rel_key(et)].reshape(H) * scale)
+            agg = ops.hgt_attention(q, ks, vs, torch.stack(ps, dim=0), [csr.fwd[et] for et in ets],
+                                    [csr.bwd[et] for et in ets], H, self.joint_softmax)
+            o = self.out_lin[dst](F.gelu(agg))
+            if o.size(-1) == x_dict[dst].size(-1):
+                a = self.skip[dst].sigmoid()
+                o = a * o + (1 - a) * x_dict[dst]
+            out_dict[dst] = o
+        return out_dict
+
+
+class HeteroHGTStack(nn.Module):
+    def __init__(self, metadata, in_channels, hidden_channels, num_layers, heads, dropout=0.0, joint_softmax=True):
+        super().__init__()
+        self.dropout = dropout
+        self.convs = nn.ModuleList(
+            HGTConv(in_channels if i == 0 else hidden_channels, hidden_channels, metadata, heads, joint_softmax)
+            for i in range(num_layers))
+
+    def forward(self, x_dict, ei_dict, nodes_per_hop=None, edges_per_hop=None, collect=None, final_types=None):
+        structures = _layer_structures(self.convs, x_dict, ei_dict, nodes_per_hop, edges_per_hop, None)
+        last = len(self.convs) - 1
+        for i, conv in enumerate(self.convs):
+            x_dict, ei_dict = trim_inputs(i, nodes_per_hop, edges_per_hop, x_dict, ei_dict)
+            out = conv(x_dict, ei_dict, csr=structures[i], only_dst=final_types if i == last else None)
+            x_dict = {k: F.dropout(v.relu(), self.dropout, self.training) for k, v in out.items()}
+            if collect is not None:
+                collect.append(x_dict)
+        return x_dict
+
+
+# ------------------------------------------------------------ hybrid encoders
+
+class SequenceBranch(nn.Module):
+    """cadence.py:249-260, 276-285: split by graph -> pad -> 2-layer biGRU (cuDNN) ->
+    LayerNorm -> MLP -> unpad.  Runs on a side stream, concurrently with the
+    message-passing stack (it depends on the encoder input only)."""
+
+    def __init__(self, in_channels, hidden_channels, dropout):
+        super().__init__()
+        self.rnn = nn.GRU(input_size=in_channels, hidden_size=hidden_channels // 2, num_layers=2,
+                          batch_first=True, bidirectional=True, dropout=dropout)
+        self.rnn_norm = nn.LayerNorm(hidden_channels)
+        self.rnn_mlp = nn.Sequential(
+            nn.Linear(hidden_channels, hidden_channels), nn.ReLU(), nn.LayerNorm(hidden_channels),
+            nn.Dropout(dropout), nn.Linear(hidden_channels, hidden_channels))
+
+    def forward(self, x, batch):
+        layout = graph.batch_layout(batch)
+        seq = layout.pad(x)
+        seq, _ = self.rnn(seq)
+        seq = self.rnn_mlp(self.rnn_norm(seq))
+        return layout.unpad(seq)
+
+
+class JumpingKnowledge(nn.Module):
+    """analysisgnn/models/core/gnn.py:345-365 (LSTM attention over layer outputs)."""
+
+    def __init__(self, n_hidden, n_layers):
+        super().__init__()
+        self.lstm = nn.LSTM(n_hidden, (n_layers * n_hidden) // 2, bidirectional=True, batch_first=True)
+        self.att = nn.Linear(2 * ((n_layers * n_hidden) // 2), 1)
+
+    def forward(self, xs):
+        x = torch.stack(xs, dim=1)
+        alpha, _ = self.lstm(x)
+        alpha = torch.softmax(self.att(alpha).squeeze(-1), dim=-1)
+        return (x * alpha.unsqueeze(-1)).sum(dim=1)
+
+
+class _HybridBase(nn.Module):
+    overlap_sequence_branch = True
+
+    def forward(self, x_dict, edge_index_dict, batch_dict=None, batch_size=None, neighbor_mask_node=None,
+                neighbor_mask_edge=None, return_edge_index=False, edge_attr_dict=None):
+        x_in = x_dict["note"]
+        batch_size = x_in.size(0) if batch_size is None else batch_size
+        batch = batch_dict["note"][:batch_size] if batch_dict is not None else \
+            torch.zeros(batch_size, dtype=torch.long, device=x_in.device)
+        main = torch.cuda.current_stream(x_in.device)
+        side = ops.side_stream(x_in.device) if self.overlap_sequence_branch else None
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                x_seq = self.seq(x_in[:batch_size], batch)
+        collect = [] if self.use_jk else None
+        out = self.gnn(x_dict, edge_index_dict, neighbor_mask_node, neighbor_mask_edge, collect, ("note",))
+        if self.use_jk:
+            x_gnn = self.jk([c["note"][:batch_size] for c in collect])
+        else:
+            x_gnn = out["note"][:batch_size]
+        if side is not None:
+            main.wait_stream(side)
+            x_seq.record_stream(main)
+        else:
+            x_seq = self.seq(x_in[:batch_size], batch)
+        return self.cat_proj(torch.cat((x_gnn, x_seq), dim=-1))
+
+
+class HybridGNN(_HybridBase):
+    """graphmuse ``HybridGNN(metadata, input_channels, hidden_channels, num_layers, dropout,
+    use_jk)`` (call site analysisgnn/models/analysis.py:454-462): HeteroSAGEStack on the
+    graph + GRU branch over the target notes, joined by ``Linear(2H, H)`` (cadence.py:301-303)."""
+
+    def __init__(self, metadata, input_channels, hidden_channels, num_layers, dropout=0.5, use_jk=False):
+        super().__init__()
+        self.use_jk = use_jk
+        self.gnn = HeteroSAGEStack(metadata[1], input_channels, hidden_channels, num_layers)
+        self.seq = SequenceBranch(input_channels, hidden_channels, dropout)
+        self.cat_proj = nn.Linear(2 * hidden_channels, hidden_channels)
+        if use_jk:
+            self.jk = JumpingKnowledge(hidden_channels, num_layers)
+
+
+class HybridHGT(_HybridBase):
+    """graphmuse ``HybridHGT`` (call site analysisgnn/models/analysis.py:444-453)."""
+
+    def __init__(self, metadata, input_channels, hidden_channels, num_layers, heads=4, dropout=0.5, use_jk=False,
+                 joint_softmax=True):
+        super().__init__()
+        self.use_jk = use_jk
+        self.gnn = HeteroHGTStack(metadata, input_channels, hidden_channels, num_layers, heads, dropout, joint_softmax)
+        self.seq = SequenceBranch(input_channels, hidden_channels, dropout)
+        self.cat_proj = nn.Linear(2 * hidden_channels, hidden_channels)
+        if use_jk:
+            self.jk = JumpingKnowledge(hidden_channels, num_layers)
+
+
+class MetricalGNN(nn.Module):
+    """graphmuse-flavoured ``MetricalGNN(metadata, input_channels, hidden_channels,
+    output_channels, num_layers, dropout, use_jk, fast)`` (call shape cadence.py:232-234,
+    298-300; analysisgnn/models/analysis.py:463-473): HeteroSAGEStack -> note rows -> MLP.
+    Returns all (trimmed) note rows; callers slice ``[:batch_size]``."""
+
+    def __init__(self, metadata, input_channels, hidden_channels, output_channels, num_layers, dropout=0.5,
+                 use_jk=False, fast=True):
+        super().__init__()
+        self.gnn = HeteroSAGEStack(metadata[1], input_channels, hidden_channels, num_layers)
+        self.mlp = nn.Sequential(
+            nn.Linear(hidden_channels, hidden_channels), nn.ReLU(), nn.LayerNorm(hidden_channels),
+            nn.Dropout(dropout), nn.Linear(hidden_channels, output_channels))
+
+    def forward(self, x_dict, edge_index_dict, neighbor_mask_node=None, neighbor_mask_edge=None, **kwargs):
+        out = self.gnn(x_dict, edge_index_dict, neighbor_mask_node, neighbor_mask_edge, None, ("note",))
+        return self.mlp(out["note"])

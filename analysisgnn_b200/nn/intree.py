@@ -1,0 +1,259 @@
+"""CUDA-backed mirrors of the reference's in-tree message-passing layers.
+
+Replaces (same names / ctor / forward / state_dict keys):
+
+* ``SageConvScatter``    analysisgnn/models/core/gnn.py:39-76
+* ``HeteroConv``         analysisgnn/models/core/hgnn.py:435-484
+* ``MetricalConvLayer``  analysisgnn/models/core/gnn.py:488-540
+* ``MetricalGNN``        analysisgnn/models/core/hgnn.py:323-433
+
+Convention of these layers: reduce at ``edge_index[0]`` reading ``edge_index[1]``.
+A ``HeteroConv`` layer is ONE fused launch chain for all relations -- a grouped
+projection, one relation-fused gather kernel on the dst-sorted CSR, one output
+projection -- instead of the reference's per-relation mask / gather / 4-kernel
+scatter loop through a CPU buffer (hgnn.py:480-484).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import graph, ops
+
+
+def _xavier_relu_(linear: nn.Linear):
+    nn.init.xavier_uniform_(linear.weight, gain=nn.init.calculate_gain("relu"))
+    if linear.bias is not None:
+        nn.init.zeros_(linear.bias)
+
+
+class SageConvScatter(nn.Module):
+    """``z = W [x || s] + b``, ``s_i = (x_i + sum_{e: ei[0,e]=i} (Wn x + bn)[ei[1,e]]) / max(deg_i, 1)``;
+    with no edges at all ``z = W [x || Wn x + bn] + b`` (gnn.py:62-76)."""
+
+    def __init__(self, in_features, out_features, bias=True, in_edge_features=None):
+        super().__init__()
+        self.neigh_linear = nn.Linear(in_features, in_features, bias=bias)
+        self.linear = nn.Linear(in_features * 2, out_features, bias=bias)
+        self.in_edge_features = in_edge_features
+        if in_edge_features is not None:
+            self.edge_linear = nn.Linear(in_edge_features, in_features, bias=bias)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        _xavier_relu_(self.linear)
+        _xavier_relu_(self.neigh_linear)
+        if self.in_edge_features is not None:
+            _xavier_relu_(self.edge_linear)
+
+    def forward(self, features, edge_index, edge_features=None, neigh_feats=None):
+        n = features.shape[0]
+        if edge_index is None:
+            edge_index = torch.zeros((2, 0), dtype=torch.long, device=features.device)
+        use_edge = self.in_edge_features is not None and edge_features is not None and edge_index.shape[1] > 0
+        if neigh_feats is None and not use_edge:
+            csr = graph.typed_csr(edge_index, None, n, 1)
+            return ops.intree_sage_layer(features, self.neigh_linear.weight, self.neigh_linear.bias,
+                                         self.linear.weight, self.linear.bias, csr)
+        # rarely used options (edge features / separate neighbour features): per-edge messages,
+        # still reduced by the segmented kernel (edge-ordered CSR, no atomics)
+        h = self.neigh_linear(features if neigh_feats is None else neigh_feats)
+        if edge_index.shape[1] == 0:
+            return self.linear(torch.cat((features, h), dim=-1))
+        msg = h.index_select(0, edge_index[1])
+        if use_edge:
+            msg = msg + self.edge_linear(edge_features)
+        s = ops.segment_mean_self(msg, features, graph.edge_csr(edge_index[0], n))
+        return self.linear(torch.cat((features, s), dim=-1))
+
+
+_FOLDABLE = ("mean", "sum")
+
+
+class HeteroConv(nn.Module):
+    """Per-relation convolution + reduction over relations (hgnn.py:435-484).
+
+    ``etypes`` maps relation name -> integer code found in ``edge_type``.  With
+    ``module=SageConvScatter`` and ``reduction`` in {mean, sum} the whole layer is
+    fused (the reduction is linear, so it is folded into the output projection).
+    """
+
+    def __init__(self, in_features, out_features, etypes, in_edge_features=None, module=SageConvScatter,
+                 bias=True, reduction="mean"):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.etypes = etypes
+        if reduction not in ("mean", "sum", "concat"):
+            # max / min return a (values, indices) tuple in the reference and cannot run there;
+            # 'lstm' (HeteroAttention) is outside the hot path
+            raise NotImplementedError(f"reduction={reduction!r}")
+        self.reduction = reduction
+        self.conv = nn.ModuleDict({name: module(in_features, out_features, bias=bias,
+                                                in_edge_features=in_edge_features) for name in etypes})
+        self._lut = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for conv in self.conv.values():
+            conv.reset_parameters()
+
+    # relation index of every edge: code -> position in ``etypes`` (-1 = not a relation of this layer)
+    def _relation_ids(self, edge_type):
+        codes = list(self.etypes.values())
+        if codes == list(range(len(codes))):
+            return edge_type
+        if self._lut is None or self._lut.device != edge_type.device:
+            lut = torch.full((max(codes) + 2,), -1, dtype=torch.long)
+            for k, c in enumerate(codes):
+                lut[c] = k
+            self._lut = lut.to(edge_type.device)
+        top = self._lut.numel() - 1                      # the extra last slot maps to -1
+        return graph.derived(edge_type, ("lut", tuple(codes)), lambda: self._lut[
+            torch.where((edge_type >= 0) & (edge_type < top), edge_type, torch.full_like(edge_type, top))])
+
+    def _fusable(self, edge_features):
+        return (self.reduction in _FOLDABLE and edge_features is None
+                and all(type(c) is SageConvScatter for c in self.conv.values()))
+
+    def forward(self, x, edge_index, edge_type, edge_features=None):
+        if edge_type is None:
+            raise ValueError("Edge type must be specified")
+        names = list(self.etypes.keys())
+        r = len(names)
+        if self._fusable(edge_features):
+            f = self.in_features
+            convs = [self.conv[k] for k in names]
+            csr = graph.typed_csr(edge_index, self._relation_ids(edge_type), x.shape[0], r)
+            has_bias = convs[0].neigh_linear.bias is not None
+            wn_cat = torch.cat([c.neigh_linear.weight for c in convs], dim=0)                  # [R*F, F]
+            bn_cat = torch.cat([c.neigh_linear.bias for c in convs], dim=0) if has_bias else None
+            scale = 1.0 / r if self.reduction == "mean" else 1.0
+            w_self = torch.stack([c.linear.weight[:, :f] for c in convs], dim=0).sum(0)
+            wc = torch.cat([w_self] + [c.linear.weight[:, f:] for c in convs], dim=1) * scale  # [F', (R+1)F]
+            bc = torch.stack([c.linear.bias for c in convs], dim=0).sum(0) * scale if has_bias else None
+            return ops.intree_sage_layer(x, wn_cat, bn_cat, wc, bc, csr)
+        # generic path (other conv blocks / edge features / concat): per relation, device-resident
+        rel = self._relation_ids(edge_type)
+        outs = []
+        for k, name in enumerate(names):
+            pick = rel == k
+            ef = edge_features[pick, :] if edge_features is not None else None
+            outs.append(self.conv[name](x, edge_index[:, pick], ef))
+        if self.reduction == "concat":
+            return torch.cat(outs, dim=0)
+        out = torch.stack(outs, dim=0)
+        return out.mean(dim=0) if self.reduction == "mean" else out.sum(dim=0)
+
+
+class MetricalConvLayer(nn.Module):
+    """note -> beat/measure segmented sum, biGRU over each score's metrical sequence,
+    BatchNorm (padded positions included, gnn.py:526-531), and the segmented sum back
+    to the notes (gnn.py:488-540).  Both scatters run on the one CSR pair of the
+    note -> metrical edges (forward graph and its transpose)."""
+
+    def __init__(self, in_dim, out_dim, activation=None, dropout=0.2, bias=True):
+        super().__init__()
+        self.input_dim = in_dim
+        self.output_dim = out_dim
+        self.activation = nn.Identity() if activation is None else activation
+        self.dropout = nn.Dropout(dropout)
+        self.normalize = nn.BatchNorm1d(out_dim)
+        self.neigh = nn.Linear(in_dim, in_dim, bias=bias)
+        self.conv_out = nn.Linear(4 * in_dim, out_dim, bias=bias)
+        self.seq = nn.GRU(in_dim, in_dim, batch_first=True, bias=bias, bidirectional=True)
+
+    def reset_parameters(self):
+        self.neigh.reset_parameters()
+        self.conv_out.reset_parameters()
+        self.seq.reset_parameters()
+
+    def forward(self, x_metrical, x, edge_index, lengths):
+        n_m, n = x_metrical.size(0), x.size(0)
+        layout = graph.sequence_layout(lengths, n_m)
+        csr = graph.typed_csr(edge_index, None, n_m, 1, reduce_row=1, n_cols=n)   # rows = metrical nodes
+        gathered = ops.segment_sum(self.neigh(x), csr)                            # gnn.py:510-511
+        both = torch.cat((gathered, x_metrical), dim=-1)
+        gath_seq, both_seq = layout.pad(gathered), layout.pad(both)
+        rec = self.seq(gath_seq)[0]
+        h = self.activation(self.conv_out(torch.cat((both_seq, rec), dim=-1)))
+        h = self.dropout(self.normalize(h.transpose(1, 2))).transpose(1, 2)
+        h = layout.unpad(h)
+        out = ops.segment_sum(h, csr.t())                                         # gnn.py:539
+        return out, h
+
+
+class MetricalGNN(nn.Module):
+    """hgnn.py:323-433.  ``jk=True`` cannot run in the reference (JumpingKnowledge is
+    built with ``n_layers=hidden_features``, hgnn.py:340) and is rejected here."""
+
+    def __init__(self, input_features, hidden_features, output_features, etypes, num_layers=2, dropout=0.5,
+                 use_reledge=False, jk=False, in_edge_features=None, metrical=False, conv_block=SageConvScatter):
+        super().__init__()
+        if jk:
+            raise NotImplementedError("jk=True is unusable in the reference (hgnn.py:340)")
+        self.dropout = dropout
+        self.num_layers = num_layers
+        self.num_hidden = hidden_features
+        self.use_reledge = use_reledge
+        self.use_metrical = metrical
+        self.use_knowledge = False
+        self.convs = nn.ModuleList()
+        self.emb_beats = nn.Linear(input_features, hidden_features)
+        self.emb_measures = nn.Linear(input_features, hidden_features)
+        self.beat_convs = nn.ModuleList()
+        self.measure_convs = nn.ModuleList()
+        self.project_metrical = nn.ModuleList()
+        self.convs.append(HeteroConv(input_features, hidden_features, etypes=etypes,
+                                     in_edge_features=in_edge_features if use_reledge else None, module=conv_block))
+        for _ in range(max(num_layers - 2, 0)):
+            self.convs.append(HeteroConv(hidden_features, hidden_features, etypes=etypes, module=conv_block))
+            if metrical:
+                self._add_metrical(hidden_features, hidden_features, dropout)
+        self.convs.append(HeteroConv(hidden_features, hidden_features, etypes=etypes, module=conv_block))
+        if metrical:
+            self._add_metrical(hidden_features, output_features, dropout)
+
+    def _add_metrical(self, h_in, h_out, dropout):
+        self.beat_convs.append(MetricalConvLayer(h_in, h_out, activation=F.relu, dropout=dropout))
+        self.measure_convs.append(MetricalConvLayer(h_in, h_out, activation=F.relu, dropout=dropout))
+        self.project_metrical.append(nn.Linear(h_out * 3, h_out))
+
+    def reset_parameters(self):
+        for group in (self.convs, self.beat_convs, self.measure_convs, self.project_metrical):
+            for m in group:
+                m.reset_parameters()
+        self.emb_beats.reset_parameters()
+        self.emb_measures.reset_parameters()
+
+    def _metrical_step(self, k, h, h_beat, h_measure, beat_edges, measure_edges, beat_lengths, measure_lengths):
+        from_beats, h_beat = self.beat_convs[k](h_beat, h, beat_edges, beat_lengths)
+        from_measures, h_measure = self.measure_convs[k](h_measure, h, measure_edges, measure_lengths)
+        h = self.project_metrical[k](torch.cat((h, from_beats, from_measures), dim=-1))
+        return ops.l2norm_relu(h, relu_first=True), h_beat, h_measure
+
+    def forward(self, x, edge_index, edge_type, beat_nodes=None, measure_nodes=None, beat_edges=None,
+                measure_edges=None, rel_edge=None, beat_lengths=None, measure_lengths=None, **kwargs):
+        h_beat = h_measure = None
+        if self.use_metrical:                                                    # hgnn.py:405-407
+            n = x.size(0)
+            b_csr = graph.typed_csr(beat_edges, None, beat_nodes.size(0), 1, reduce_row=1, n_cols=n)
+            m_csr = graph.typed_csr(measure_edges, None, measure_nodes.size(0), 1, reduce_row=1, n_cols=n)
+            h_beat = ops.segment_sum(self.emb_beats(x), b_csr)
+            h_measure = ops.segment_sum(self.emb_measures(x), m_csr)
+        h = x
+        for i in range(len(self.convs) - 1):
+            if i != 0 and self.use_metrical:
+                h, h_beat, h_measure = self._metrical_step(i - 1, h, h_beat, h_measure, beat_edges, measure_edges,
+                                                           beat_lengths, measure_lengths)
+            if i == 0 and self.use_reledge:
+                h = self.convs[i](h, edge_index, edge_type, edge_features=rel_edge)
+            else:
+                h = self.convs[i](h, edge_index, edge_type)
+            h = ops.l2norm_relu(h, relu_first=False)                              # normalize, then relu (hgnn.py:421-422)
+            h = F.dropout(h, p=self.dropout, training=self.training)
+        if self.use_metrical:
+            h, h_beat, h_measure = self._metrical_step(-1, h, h_beat, h_measure, beat_edges, measure_edges,
+                                                       beat_lengths, measure_lengths)
+        return self.convs[-1](h, edge_index, edge_type)

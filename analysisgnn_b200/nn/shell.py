@@ -1,0 +1,117 @@
+"""The hot-path part of the reference's production model ``TorchAnalysisGNN``
+(analysisgnn/models/analysis.py:421-591): embeddings -> per-node-type
+``project_dict`` -> encoder -> onset pooling -> ``project_enc`` -> per-task heads.
+
+Attribute names (and therefore ``state_dict`` keys) are the reference's:
+``pitch_embedding, key_embedding, project_dict.<type>.{0,2,4}, encoder.*,
+project_enc.{0,1,3,5,7,9}, clf_dict.<task>.{0,2,3}``.  Logit fusion
+(``logit_fusion=True``, off in the reference's training default,
+analysisgnn/models/analysis.py:852) and the optional output RNN are outside the
+message-passing path and are not provided.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import graph, ops
+from .hetero import HybridGNN, HybridHGT, MetricalGNN
+
+ONSET = ("note", "onset", "note")
+
+
+def onset_pool(x, onset_edges, batch_size):
+    """analysisgnn/models/analysis.py:580-586: keep onset edges with both ends
+    ``< batch_size``, drop self loops, ``scatter_mean(x[e1], e0, out=x.clone())``
+    = ``(x_i + sum_j x_j) / max(deg_i, 1)``.  The filter is folded into the CSR build
+    (filtered edges get relation id -1 and are dropped there), so nothing is
+    compacted on the host and no shape depends on the data."""
+    def make():
+        e0, e1 = onset_edges[0], onset_edges[1]
+        keep = (e0 < batch_size) & (e1 < batch_size) & (e0 != e1)
+        return keep.long() - 1                                   # 0 = keep, -1 = dropped by agnn_csr_build
+    etype = graph.derived(onset_edges, ("onset_pool", int(batch_size)), make)
+    csr = graph.typed_csr(onset_edges, etype, int(batch_size), 1)
+    return ops.segment_mean_self(x, x, csr)
+
+
+class AnalysisEncoder(nn.Module):
+    """Constructor / ``encode`` / ``forward`` arguments of ``TorchAnalysisGNN``
+    (analysisgnn/models/analysis.py:422, 546, 571)."""
+
+    def __init__(self, metadata, in_channels, hidden_channels, out_channels, task_dict, num_layers, dropout=0.5,
+                 use_jk=False, logit_fusion=False, use_rnn=False, encoder_type="hybridgnn"):
+        super().__init__()
+        if logit_fusion or use_rnn:
+            raise NotImplementedError("logit_fusion / use_rnn are outside the message-passing hot path")
+        self.pitch_embedding = nn.Embedding(35, 64)
+        self.key_embedding = nn.Embedding(15, 64)
+        self.logit_fusion = False
+        self.use_rnn = False
+        self.hidden_channels = hidden_channels
+
+        def mlp(cin):
+            return nn.Sequential(nn.Linear(cin, hidden_channels), nn.ReLU(), nn.LayerNorm(hidden_channels),
+                                 nn.Dropout(dropout), nn.Linear(hidden_channels, hidden_channels))
+
+        self.project_dict = nn.ModuleDict({k: mlp(in_channels + 128 if k == "note" else in_channels)
+                                           for k in metadata[0]})
+        if encoder_type == "hgt":
+            self.encoder = HybridHGT(metadata=metadata, input_channels=hidden_channels,
+                                     hidden_channels=hidden_channels, num_layers=num_layers, heads=4,
+                                     dropout=dropout, use_jk=use_jk)
+        elif encoder_type == "hybridgnn":
+            self.encoder = HybridGNN(metadata=metadata, input_channels=hidden_channels,
+                                     hidden_channels=hidden_channels, num_layers=num_layers, dropout=dropout,
+                                     use_jk=use_jk)
+        elif encoder_type == "metricalgnn":
+            self.encoder = MetricalGNN(metadata=metadata, input_channels=hidden_channels,
+                                       hidden_channels=hidden_channels, output_channels=hidden_channels,
+                                       num_layers=num_layers, dropout=dropout, use_jk=use_jk, fast=True)
+        else:
+            raise ValueError(f"unknown encoder_type {encoder_type!r}")
+        self.encoder_type = encoder_type
+        self.project_enc = nn.Sequential(
+            nn.LayerNorm(2 * hidden_channels), nn.Linear(2 * hidden_channels, hidden_channels), nn.ReLU(),
+            nn.LayerNorm(hidden_channels), nn.Dropout(dropout), nn.Linear(hidden_channels, out_channels), nn.ReLU(),
+            nn.LayerNorm(out_channels), nn.Dropout(dropout), nn.Linear(out_channels, out_channels))
+        self.clf_dict = nn.ModuleDict({
+            task: nn.Sequential(nn.Linear(out_channels, out_channels // 2), nn.ReLU(),
+                                nn.LayerNorm(out_channels // 2), nn.Linear(out_channels // 2, n_cls))
+            for task, n_cls in task_dict.items()})
+
+    def encode(self, pitch_spelling, key_signature, x_dict, edge_index_dict, batch_dict, batch_size,
+               neighbor_mask_node=None, neighbor_mask_edge=None):
+        z = dict(x_dict)
+        z["note"] = torch.cat((x_dict["note"], self.pitch_embedding(pitch_spelling),
+                               self.key_embedding(key_signature)), dim=-1)
+        h = {k: self.project_dict[k](z[k]) for k in self.project_dict.keys()}
+        x = self.encoder(x_dict=h, edge_index_dict=edge_index_dict, batch_dict=batch_dict, batch_size=batch_size,
+                         neighbor_mask_node=neighbor_mask_node, neighbor_mask_edge=neighbor_mask_edge,
+                         return_edge_index=False, edge_attr_dict=None)
+        if self.encoder_type == "metricalgnn":
+            x = x[:batch_size]
+        pooled = onset_pool(x, edge_index_dict[ONSET], batch_size)
+        return self.project_enc(torch.cat((x, pooled), dim=-1))
+
+    def forward_clf(self, x, tasks=None):
+        tasks = self.clf_dict.keys() if tasks is None else tasks
+        return {t: self.clf_dict[t](x) for t in tasks}
+
+    def clf_task(self, x, task_name):
+        return self.clf_dict[task_name](x)
+
+    def forward(self, pitch_spelling, key_signature, x_dict, edge_index_dict, batch_dict, batch_size,
+                neighbor_mask_node=None, neighbor_mask_edge=None):
+        x = self.encode(pitch_spelling, key_signature, x_dict, edge_index_dict, batch_dict, batch_size,
+                        neighbor_mask_node, neighbor_mask_edge)
+        return self.forward_clf(x)
+
+
+def multitask_ce(logits, labels):
+    """Default multi-task objective of ``ContinualAnalysisGNN`` (analysisgnn/models/analysis.py:
+    881-908, 1035-1037): ``MultiTaskLoss(requires_grad=False)`` = plain sum of per-task
+    ``CrossEntropyLoss(ignore_index=-1, label_smoothing=0.1)`` divided by the number of tasks."""
+    total = sum(F.cross_entropy(logits[t], labels[t], ignore_index=-1, label_smoothing=0.1) for t in labels)
+    return total / len(labels)

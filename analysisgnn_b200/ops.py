@@ -41,6 +41,7 @@ class Rel:
     out_col: int = 0
     nbr_deg_rowptr: Optional[torch.Tensor] = None
     flags: int = 0
+    n_edges: Optional[int] = None            # edges of this relation (bench accounting only)
 
 
 def _pack(rels: Sequence[Rel], n_feat: int, dtype) -> "ctypes.Array":
@@ -61,6 +62,55 @@ def _pack(rels: Sequence[Rel], n_feat: int, dtype) -> "ctypes.Array":
     return arr
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of the aggregation kernels (bench.py's roofline):
+    ``ops.timer = KernelTimer()`` records (name, algorithmic bytes, start, stop) on the launching
+    stream; ``summary()`` synchronises and returns totals per kernel name."""
+
+    def __init__(self):
+        self.records = []
+
+    def launch(self, name: str, nbytes: int, device, fn):
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = torch.cuda.current_stream(device)
+        start.record(st)
+        fn()
+        stop.record(st)
+        self.records.append((name, nbytes, start, stop))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, nbytes, a, b in self.records:
+            d = out.setdefault(name, {"launches": 0, "bytes": 0, "ms": 0.0, "max_bytes": 0, "max_ms": 0.0})
+            ms = a.elapsed_time(b)
+            d["launches"] += 1
+            d["bytes"] += nbytes
+            d["ms"] += ms
+            if nbytes > d["max_bytes"]:
+                d["max_bytes"], d["max_ms"] = nbytes, ms
+        return out
+
+
+timer: Optional[KernelTimer] = None
+
+
+def gather_bytes(rels: Sequence[Rel], n_rows: int, n_feat: int, elem: int, concat: bool, has_self: bool,
+                 has_copy: bool) -> int:
+    """Algorithmic bytes of one agnn_gather_reduce launch: gathered rows and their
+    column ids, rows written, self / copy rows read, rowptr (and neighbour-degree reads where used)."""
+    row = n_feat * elem
+    total = 0
+    for r in rels:
+        e = int(r.n_edges)
+        total += e * (row + 4) + 4 * (n_rows + 1)
+        if r.nbr_deg_rowptr is not None:
+            total += 8 * e
+    slices = len(rels) if concat else 1
+    total += n_rows * row * (slices + int(has_self) + 2 * int(has_copy))
+    return total
+
+
 def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: bool, concat: bool,
                   self_add: Optional[torch.Tensor] = None, copy: Optional[torch.Tensor] = None,
                   copy_col: int = 0) -> torch.Tensor:
@@ -71,12 +121,21 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
     sa = _rows2d(self_add, "self_add") if self_add is not None else None
     cp = _rows2d(copy, "copy") if copy is not None else None
     stream = torch.cuda.current_stream(out.device).cuda_stream
-    _lib.check(_lib.lib().agnn_gather_reduce(
-        n_rows, n_feat, _dtype_code(out), _lib.SCALE_MEAN if mean else _lib.SCALE_NONE,
-        _lib.COMBINE_CONCAT if concat else _lib.COMBINE_SUM, len(rels), arr,
-        sa.data_ptr() if sa is not None else None, sa.stride(0) if sa is not None else 0,
-        cp.data_ptr() if cp is not None else None, cp.stride(0) if cp is not None else 0, int(copy_col),
-        out.data_ptr(), out.stride(0), stream), "agnn_gather_reduce")
+
+    def run():
+        _lib.check(_lib.lib().agnn_gather_reduce(
+            n_rows, n_feat, _dtype_code(out), _lib.SCALE_MEAN if mean else _lib.SCALE_NONE,
+            _lib.COMBINE_CONCAT if concat else _lib.COMBINE_SUM, len(rels), arr,
+            sa.data_ptr() if sa is not None else None, sa.stride(0) if sa is not None else 0,
+            cp.data_ptr() if cp is not None else None, cp.stride(0) if cp is not None else 0, int(copy_col),
+            out.data_ptr(), out.stride(0), stream), "agnn_gather_reduce")
+
+    if timer is not None and all(r.n_edges is not None for r in rels):
+        nbytes = gather_bytes(rels, n_rows, n_feat, out.element_size(), concat, sa is not None, cp is not None)
+        timer.launch("gather_reduce", nbytes, out.device, run)
+    else:
+        run()
+    _lib.count_launches(1)
     return out
 
 
@@ -94,6 +153,7 @@ def rowscale_sum(rels: Sequence[Rel], inp: torch.Tensor, out: torch.Tensor, n_fe
         out.shape[0], n_feat, _dtype_code(out), len(rels), arr, inp.data_ptr(), inp.stride(0),
         b.data_ptr() if b is not None else None, b.stride(0) if b is not None else 0,
         out.data_ptr(), out.stride(0), stream), "agnn_rowscale_sum")
+    _lib.count_launches(1)
     return out
 
 
@@ -112,7 +172,8 @@ class _SegmentReduce(torch.autograd.Function):
         f = src.shape[1]
         out = torch.empty((csr.n_rows, f), dtype=src.dtype, device=src.device)
         sa = self_add.contiguous() if self_add is not None else None
-        gather_reduce([Rel(csr.fwd.rowptr[0], csr.fwd.col, src)], out, f, mean=mean, concat=True, self_add=sa)
+        gather_reduce([Rel(csr.fwd.rowptr[0], csr.fwd.col, src, n_edges=csr.n_edges)], out, f, mean=mean, concat=True,
+                      self_add=sa)
         ctx.csr, ctx.mean, ctx.has_self = csr, mean, self_add is not None
         return out
 
@@ -122,7 +183,7 @@ class _SegmentReduce(torch.autograd.Function):
         g = g.contiguous()
         d_src = torch.empty((csr.n_cols, f), dtype=g.dtype, device=g.device)
         deg = csr.fwd.rowptr[0] if ctx.mean else None
-        gather_reduce([Rel(csr.bwd.rowptr[0], csr.bwd.col, g, nbr_deg_rowptr=deg)], d_src, f, mean=False,
+        gather_reduce([Rel(csr.bwd.rowptr[0], csr.bwd.col, g, nbr_deg_rowptr=deg, n_edges=csr.n_edges)], d_src, f, mean=False,
                       concat=True)
         d_self = None
         if ctx.has_self:
@@ -167,7 +228,7 @@ class _IntreeSageLayer(torch.autograd.Function):
         h = linalg.linear(x, wn_cat, bn_cat)                                     # [N, R*F]
         a = torch.empty((n, (r + 1) * f), dtype=x.dtype, device=x.device)
         rels = [Rel(csr.fwd.rowptr[k], csr.fwd.col, h[:, k * f:(k + 1) * f], out_col=(k + 1) * f,
-                    flags=_lib.REL_IDENTITY_IF_EMPTY) for k in range(r)]
+                    flags=_lib.REL_IDENTITY_IF_EMPTY, n_edges=csr.n_edges if k == 0 else 0) for k in range(r)]
         gather_reduce(rels, a, f, mean=True, concat=True, self_add=x, copy=x, copy_col=0)
         z = linalg.linear(a, wc, bc)
         ctx.save_for_backward(x, a, wn_cat, wc)
@@ -185,7 +246,8 @@ class _IntreeSageLayer(torch.autograd.Function):
         dbc = dz.sum(0) if ctx.has_bias[1] and ctx.needs_input_grad[4] else None
         dh = torch.empty((n, r * f), dtype=x.dtype, device=x.device)
         rels_t = [Rel(csr.bwd.rowptr[k], csr.bwd.col, da[:, (k + 1) * f:(k + 2) * f], out_col=k * f,
-                      nbr_deg_rowptr=csr.fwd.rowptr[k], flags=_lib.REL_IDENTITY_IF_EMPTY) for k in range(r)]
+                      nbr_deg_rowptr=csr.fwd.rowptr[k], flags=_lib.REL_IDENTITY_IF_EMPTY,
+                      n_edges=csr.n_edges if k == 0 else 0) for k in range(r)]
         gather_reduce(rels_t, dh, f, mean=False, concat=True)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -229,13 +291,14 @@ class _HeteroSageLayer(torch.autograd.Function):
             f = x_t.shape[1]
             rel_list = plan.incoming[t]
             a = torch.empty((x_t.shape[0], (len(rel_list) + 1) * f), dtype=x_t.dtype, device=x_t.device)
-            rels = [Rel(csr.fwd[et].rowptr[0], csr.fwd[et].col, xs[et[0]], out_col=(k + 1) * f)
-                    for k, et in enumerate(rel_list)]
+            rels = [Rel(csr.fwd[et].rowptr[0], csr.fwd[et].col, xs[et[0]], out_col=(k + 1) * f,
+                        n_edges=csr.n_edges[et]) for k, et in enumerate(rel_list)]
             gather_reduce(rels, a, f, mean=True, concat=True, copy=x_t, copy_col=0)
             o = linalg.linear(a, wcat, bias, relu=relu)
             outs.append(o)
             saved += [a, wcat, o]
         ctx.save_for_backward(*saved)
+        ctx.set_materialize_grads(False)        # an unused destination type costs nothing in backward
         ctx.plan, ctx.csr, ctx.relu = plan, csr, relu
         ctx.feat = {t: xs[t].shape[1] for t in plan.node_types}
         ctx.rows = {t: xs[t].shape[0] for t in plan.node_types}
@@ -269,7 +332,7 @@ class _HeteroSageLayer(torch.autograd.Function):
                     continue
                 k = plan.incoming[dst].index(et)
                 rels.append(Rel(csr.bwd[et].rowptr[0], csr.bwd[et].col, da[dst][:, (k + 1) * f:(k + 2) * f],
-                                nbr_deg_rowptr=csr.fwd[et].rowptr[0]))
+                                nbr_deg_rowptr=csr.fwd[et].rowptr[0], n_edges=csr.n_edges[et]))
             root = da[s][:, :f] if s in da else None
             if not rels:
                 grads[i] = root.contiguous() if root is not None else None
@@ -282,3 +345,120 @@ class _HeteroSageLayer(torch.autograd.Function):
 
 def hetero_sage_layer(plan, csr: HeteroCSR, relu: bool, xs: Sequence[torch.Tensor], params: Sequence[torch.Tensor]):
     return _HeteroSageLayer.apply(plan, csr, relu, *xs, *params)
+
+
+# ------------------------------------------------------------------------------
+# HGT attention (PyG HGTConv edge pipeline) -- agnn_hgt_attn_{fwd,bwd_dst,bwd_src}
+# ------------------------------------------------------------------------------
+
+def _hgt_pack(fwd_csrs: Sequence[CSR], bwd_csrs: Sequence[CSR], ks, vs, dks=None, dvs=None):
+    arr = (_lib.HgtRel * len(ks))()
+    for i, (cf, cb, k, v) in enumerate(zip(fwd_csrs, bwd_csrs, ks, vs)):
+        k, v = _rows2d(k, "k"), _rows2d(v, "v")
+        if k.stride(0) != v.stride(0):
+            raise ValueError("k and v of a relation must share their row stride")
+        arr[i].rowptr, arr[i].col = cf.rowptr.data_ptr(), cf.col.data_ptr()
+        arr[i].t_rowptr, arr[i].t_col = cb.rowptr.data_ptr(), cb.col.data_ptr()
+        arr[i].k, arr[i].v, arr[i].ld_kv = k.data_ptr(), v.data_ptr(), k.stride(0)
+        arr[i].n_src = k.shape[0]
+        if dks is not None:
+            arr[i].dk, arr[i].dv, arr[i].ld_dkv = dks[i].data_ptr(), dvs[i].data_ptr(), dks[i].stride(0)
+    return arr
+
+
+class _HGTAttention(torch.autograd.Function):
+    """Joint edge softmax over the given relations of one destination type.
+    Arguments: (q [N_dst, H*D], pscale [R, H] fp32, heads, fwd_csrs, bwd_csrs, *ks, *vs)."""
+
+    @staticmethod
+    def forward(ctx, q, pscale, heads, fwd_csrs, bwd_csrs, *kv):
+        r = len(fwd_csrs)
+        ks = [t.contiguous() for t in kv[:r]]
+        vs = [t.contiguous() for t in kv[r:]]
+        q = _rows2d(q, "q")
+        n, hd = q.shape
+        d = hd // heads
+        ps = pscale.detach().to(torch.float32).contiguous()
+        out = torch.empty((n, hd), dtype=q.dtype, device=q.device)
+        row_max = torch.empty((n, heads), dtype=torch.float32, device=q.device)
+        row_den = torch.empty((n, heads), dtype=torch.float32, device=q.device)
+        arr = _hgt_pack(fwd_csrs, bwd_csrs, ks, vs)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        _lib.check(_lib.lib().agnn_hgt_attn_fwd(n, heads, d, _dtype_code(q), r, arr, q.data_ptr(), q.stride(0),
+                                                ps.data_ptr(), out.data_ptr(), out.stride(0), row_max.data_ptr(),
+                                                row_den.data_ptr(), stream), "agnn_hgt_attn_fwd")
+        _lib.count_launches(1)
+        ctx.save_for_backward(q, ps, out, row_max, row_den, *ks, *vs)
+        ctx.heads, ctx.fwd_csrs, ctx.bwd_csrs = heads, fwd_csrs, bwd_csrs
+        ctx.pscale_dtype = pscale.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, ps, out, row_max, row_den = ctx.saved_tensors[:5]
+        r = len(ctx.fwd_csrs)
+        ks, vs = ctx.saved_tensors[5:5 + r], ctx.saved_tensors[5 + r:]
+        heads = ctx.heads
+        n, hd = q.shape
+        d = hd // heads
+        dout = dout.contiguous()
+        lib = _lib.lib()
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        dq = torch.empty((n, hd), dtype=q.dtype, device=q.device)
+        delta = torch.empty((n, heads), dtype=torch.float32, device=q.device)
+        blocks = lib.agnn_hgt_attn_bwd_dst_blocks(n)
+        partial = torch.empty((blocks, r * heads), dtype=torch.float32, device=q.device)
+        dks = [torch.empty_like(k) for k in ks]
+        dvs = [torch.empty_like(v) for v in vs]
+        arr = _hgt_pack(ctx.fwd_csrs, ctx.bwd_csrs, ks, vs, dks, dvs)
+        if n > 0:
+            _lib.check(lib.agnn_hgt_attn_bwd_dst(n, heads, d, _dtype_code(q), r, arr, q.data_ptr(), q.stride(0),
+                                                 ps.data_ptr(), out.data_ptr(), out.stride(0), dout.data_ptr(),
+                                                 dout.stride(0), row_max.data_ptr(), row_den.data_ptr(),
+                                                 delta.data_ptr(), dq.data_ptr(), dq.stride(0), partial.data_ptr(),
+                                                 stream), "agnn_hgt_attn_bwd_dst")
+            dps = partial.sum(0).view(r, heads).to(ctx.pscale_dtype)
+        else:
+            dps = torch.zeros((r, heads), dtype=ctx.pscale_dtype, device=q.device)
+        _lib.check(lib.agnn_hgt_attn_bwd_src(heads, d, _dtype_code(q), r, arr, q.data_ptr(), q.stride(0),
+                                             ps.data_ptr(), dout.data_ptr(), dout.stride(0), row_max.data_ptr(),
+                                             row_den.data_ptr(), delta.data_ptr(), stream), "agnn_hgt_attn_bwd_src")
+        _lib.count_launches(2)
+        return (dq, dps, None, None, None, *dks, *dvs)
+
+
+def hgt_attention(q, ks, vs, pscale, fwd_csrs, bwd_csrs, heads: int, joint_softmax: bool = True):
+    """``sum_e softmax_e(q_i . k_e * pscale) v_e`` per destination row and head.
+
+    ``joint_softmax=True``: one softmax over the incoming edges of all relations (PyG >= 2.3);
+    ``False``: one softmax per relation, results summed (pre-2.3)."""
+    if joint_softmax:
+        return _HGTAttention.apply(q, pscale, heads, list(fwd_csrs), list(bwd_csrs), *ks, *vs)
+    out = None
+    for i in range(len(ks)):
+        o = _HGTAttention.apply(q, pscale[i:i + 1], heads, [fwd_csrs[i]], [bwd_csrs[i]], ks[i], vs[i])
+        out = o if out is None else out + o
+    return out
+
+
+# ------------------------------------------------------------------------------
+# row-wise L2 normalisation + ReLU (hgnn.py:415, 421-422) and stream helper
+# ------------------------------------------------------------------------------
+
+def l2norm_relu(h, relu_first: bool):
+    """``relu_first``: ``normalize(relu(h))`` (hgnn.py:415, 431); else ``relu(normalize(h))``
+    (hgnn.py:421-422).  ``normalize`` = ``h / max(||h||_2, 1e-12)`` per row."""
+    if relu_first:
+        return torch.nn.functional.normalize(torch.relu(h), p=2.0, dim=-1)
+    return torch.relu(torch.nn.functional.normalize(h, p=2.0, dim=-1))
+
+
+_side_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _side_streams:
+        _side_streams[idx] = torch.cuda.Stream(device=idx)
+    return _side_streams[idx]

@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the message-passing hot path (BASELINE.json metric: score-graph
+nodes/s fwd+bwd, HybridGNN 3 layers / hidden 256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype fp32|bf16]
+
+Workload = BASELINE.json configs[1]: HybridGNN 3L/256 with beat + measure nodes and
+the three multi-task heads (cadence / localkey / romanNumeral) on a batch of 100
+synthetic 500-note score subgraphs per GPU; one step = CSR build + forward +
+backward + gradient allreduce (N > 1) + clip + AdamW, train mode (dropout 0.3).
+
+Prints ONE JSON line (rank 0).  `value` times the step with inputs resident in HBM;
+`e2e` times the same step from pinned host buffers (host->device copies of the batch
+and a device->host read of the loss inside the timed region).  `roofline` is the
+aggregation kernel (agnn_gather_reduce) measured with CUDA events inside the timed
+region; `cpu_baseline` is the CPU oracle on a bounded sample of the same workload.
+`--impl reference` times the reference arm: this repo's CPU restatement of the
+reference's encoder (oracle/pyg.py; the third-party graphmuse / PyG stack is not
+installable here) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TASKS = {"cadence": 4, "localkey": 50, "romanNumeral": 185}   # analysisgnn/train/train_analysisgnn.py:22-45
+CFG = dict(graphs=100, notes=500, voices=4, in_features=25, hidden=256, out=128, layers=3, dropout=0.3,
+           lr=5e-3, weight_decay=5e-3, max_norm=1.0)
+METRIC = "score-graph nodes/sec fwd+bwd (HybridGNN 3L/256)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(seed, graphs):
+    from analysisgnn_b200 import synth
+    return synth.hetero_batch(graphs, CFG["notes"], seed, voices=CFG["voices"], in_features=CFG["in_features"],
+                              task_dict=TASKS)
+
+
+def batch_tensors(b):
+    """Flat name -> tensor map of everything a step consumes (what crosses host->device)."""
+    t = {"pitch_spelling": b["pitch_spelling"], "key_signature": b["key_signature"]}
+    for k, v in b["x_dict"].items():
+        t[f"x.{k}"] = v
+    for k, v in b["edge_index_dict"].items():
+        t["ei." + "__".join(k)] = v
+    for k, v in b["batch_dict"].items():
+        t[f"batch.{k}"] = v
+    for k, v in b["labels"].items():
+        t[f"label.{k}"] = v
+    return t
+
+
+def unflatten(t, b):
+    return dict(pitch_spelling=t["pitch_spelling"], key_signature=t["key_signature"],
+                x_dict={k: t[f"x.{k}"] for k in b["x_dict"]},
+                edge_index_dict={k: t["ei." + "__".join(k)] for k in b["edge_index_dict"]},
+                batch_dict={k: t[f"batch.{k}"] for k in b["batch_dict"]},
+                labels={k: t[f"label.{k}"] for k in b["labels"]}, batch_size=b["batch_size"])
+
+
+# --------------------------------------------------------------------------- CPU arm
+
+def cpu_step_fn(graphs, seed=0):
+    """The reference arm / cpu_baseline: oracle restatement on the host cores, same step."""
+    import torch
+    from oracle import pyg as opyg
+    b = make_batch(seed, graphs)
+    torch.manual_seed(0)
+    model = opyg.AnalysisEncoderShell(b["metadata"], CFG["in_features"], CFG["hidden"], CFG["out"], TASKS,
+                                      CFG["layers"], dropout=CFG["dropout"])
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=CFG["lr"], weight_decay=CFG["weight_decay"])
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        logits = model(b["pitch_spelling"], b["key_signature"], b["x_dict"], b["edge_index_dict"], b["batch_dict"],
+                       b["batch_size"], None, None)
+        loss = opyg.multitask_ce(logits, b["labels"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), CFG["max_norm"])
+        opt.step()
+        return float(loss.detach())
+
+    return step, b["batch_size"]
+
+
+def cpu_arm(steps, warmup, budget_s, max_graphs):
+    """Times the CPU oracle on a bounded sample: the number of subgraphs per step is chosen
+    so that warmup + steps fit in ``budget_s`` seconds."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    probe_graphs = min(4, max_graphs)
+    step, nodes = cpu_step_fn(probe_graphs)
+    step()
+    t0 = time.perf_counter()
+    step()
+    per_graph = (time.perf_counter() - t0) / probe_graphs
+    graphs = int(max(1, min(max_graphs, budget_s / max(per_graph * (steps + warmup), 1e-9))))
+    if graphs != probe_graphs:
+        step, nodes = cpu_step_fn(graphs)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": nodes * steps / total, "unit": "nodes/s", "cores": cores, "kind": "port",
+            "sample": f"{graphs} of {CFG['graphs']} subgraphs x {CFG['notes']} notes per step, {steps} timed steps "
+                      f"(+{warmup} warm-up), oracle/pyg.py AnalysisEncoderShell fwd+bwd+clip+AdamW, fp32, "
+                      f"torch {cores} threads",
+            "ms_per_step": 1e3 * total / steps, "nodes_per_step": nodes}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    r = cpu_arm(steps, warmup, budget_s=150.0, max_graphs=CFG["graphs"])
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "nodes/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, cpu=True),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cpu=False):
+    return {"workload": "BASELINE configs[1]: HybridGNN 3L/256 + beat/measure nodes + cadence/localkey/romanNumeral "
+                        "heads, 100 synthetic 500-note subgraphs per GPU (4 voices, 25 note features), "
+                        "step = CSR build + fwd + bwd + clip(1.0) + AdamW, train mode dropout 0.3",
+            "subgraphs_per_gpu": CFG["graphs"], "notes_per_subgraph": CFG["notes"], "hidden": CFG["hidden"],
+            "layers": CFG["layers"], "parallelism": f"dp{args.gpus}",
+            "l2": "n/a (CPU)" if cpu else "L2 flushed between timed steps (256 MiB write); per-step activations "
+                                           "(~2 GB) also exceed the 126 MB L2"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from analysisgnn_b200 import _lib, graph, ops
+    from analysisgnn_b200 import nn as ann
+    from analysisgnn_b200.train import DataParallelTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference "
+                         "for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    if args.dtype != "fp32":
+        raise SystemExit("bench.py: the training step runs in fp32 (the reference's precision); the bf16 mode is "
+                         "covered by the parity tests only")
+    dtype = torch.float32
+
+    b = make_batch(seed=1000 + rank, graphs=CFG["graphs"])
+    host = {k: v.contiguous().pin_memory() for k, v in batch_tensors(b).items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    staging = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    n_nodes = b["batch_size"]
+    n_edges = sum(v.shape[1] for k, v in b["edge_index_dict"].items())
+
+    torch.manual_seed(0)
+    model = ann.AnalysisEncoder(b["metadata"], CFG["in_features"], CFG["hidden"], CFG["out"], TASKS, CFG["layers"],
+                                dropout=CFG["dropout"]).to(dev)
+    model.train()
+    trainer = DataParallelTrainer(model, lr=CFG["lr"], weight_decay=CFG["weight_decay"], max_norm=CFG["max_norm"],
+                                  world_size=world)
+
+    def step(tensors):
+        graph.clear_cache()                        # a new batch every step: the CSR build is part of the step
+        d = unflatten(tensors, b)
+        trainer.zero_grad()
+        logits = model(d["pitch_spelling"], d["key_signature"], d["x_dict"], d["edge_index_dict"],
+                       d["batch_dict"], d["batch_size"], None, None)
+        loss = ann.multitask_ce(logits, d["labels"])
+        loss.backward()
+        trainer.step()
+        return loss
+
+    def e2e_step():
+        for k, v in host.items():
+            staging[k].copy_(v, non_blocking=True)
+        loss = step(staging)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for a, z in ev:
+            flush.fill_(1.0)                       # L2 flush, outside the event pair
+            a.record()
+            fn()
+            z.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(z) for a, z in ev)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.timer = ops.KernelTimer()
+    launches0 = _lib.launches()
+    ms, wall = timed(lambda: step(resident), args.steps)
+    launches = _lib.launches() - launches0
+    ktimes = ops.timer.summary()
+    ops.timer = None
+    e2e_ms, _ = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss_host.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        g = ktimes.get("gather_reduce", {"launches": 0, "bytes": 0, "ms": 0.0, "max_bytes": 0, "max_ms": 0.0})
+        achieved = g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] > 0 else 0.0
+        big = g["max_bytes"] / (g["max_ms"] * 1e-3) / 1e9 if g["max_ms"] > 0 else 0.0
+        cpu = cpu_arm(steps=2, warmup=1, budget_s=20.0, max_graphs=20)
+        value = world * n_nodes * args.steps / (ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16",
+            "data": "synthetic", "config": workload_config(args),
+            "edges_per_s": world * n_edges * CFG["layers"] * args.steps / (ms * 1e-3),
+            "e2e": {"value": world * n_nodes * args.steps / (e2e_ms * 1e-3), "unit": "nodes/s",
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "agnn gather_reduce_kernel (all launches of the timed region)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "launches": g["launches"],
+                         "algorithmic_bytes_per_step": g["bytes"] / max(args.steps, 1),
+                         "kernel_ms_per_step": g["ms"] / max(args.steps, 1),
+                         "share_of_step": g["ms"] / ms if ms else None,
+                         "largest_launch": {"bytes": g["max_bytes"], "ms": g["max_ms"], "achieved": big,
+                                            "frac": big / peak}},
+            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "clocks": clocks, "wall_s": wall, "loss": final_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -136,6 +136,85 @@ int agnn_rowscale_sum(int32_t n_rows, int32_t n_feat, int dtype, int n_rel, cons
                       const void* in, int64_t ld_in, const void* base, int64_t ld_base, void* out,
                       int64_t ld_out, agnn_stream_t stream);
 
+/* ------------------------------------------------------------ HGT attention
+ * Replaces, per destination node type, the edge-level pipeline of PyG's HGTConv
+ * that graphmuse's HybridHGT runs (constructed at analysisgnn/models/analysis.py:
+ * 444-453; third-party arithmetic): q[dst] . k[src] scores,
+ * the segment softmax over every incoming edge of a destination (all relations
+ * together) and the alpha-weighted sum of v[src].  One warp per destination row,
+ * online softmax in registers, no per-edge tensors, no atomics.
+ *
+ *   s_e   = (q_i,h . k_e,h) * pscale[r(e), h]          (pscale = p_rel / sqrt(D), device array [n_rel*heads])
+ *   out_i,h = sum_e exp(s_e - max_i,h) v_e,h / (sum_e exp(s_e - max_i,h) + 1e-16)
+ *   row_max / row_den [n_dst*heads] keep max_i,h and the denominator for the backward.
+ * k / v are the relation-specific keys / values of the SOURCE type, [n_src, heads*head_dim].
+ */
+#define AGNN_HGT_MAX_HEADS 16
+
+typedef struct agnn_hgt_rel {
+  const int32_t* rowptr;   /* [n_dst + 1]  CSR keyed on the destination (fwd, bwd_dst)          */
+  const int32_t* col;      /* source ids                                                        */
+  const int32_t* t_rowptr; /* [n_src + 1]  CSR keyed on the source (bwd_src)                    */
+  const int32_t* t_col;    /* destination ids                                                   */
+  const void* k;
+  const void* v;
+  int64_t ld_kv;
+  void* dk; /* bwd_src outputs [n_src, heads*head_dim] */
+  void* dv;
+  int64_t ld_dkv;
+  int32_t n_src;
+  int32_t reserved;
+} agnn_hgt_rel_t;
+
+int agnn_hgt_attn_fwd(int32_t n_dst, int heads, int head_dim, int dtype, int n_rel,
+                      const agnn_hgt_rel_t* rels /* host */, const void* q, int64_t ld_q, const float* pscale,
+                      void* out, int64_t ld_out, float* row_max, float* row_den, agnn_stream_t stream);
+
+/* Backward, destination side: delta_i,h = dout_i,h . out_i,h; dq; and per-block partial sums of
+ * d pscale, dpscale_partial[agnn_hgt_attn_bwd_dst_blocks(n_dst)][n_rel*heads] (summed by the caller,
+ * which keeps the reduction order fixed). */
+int agnn_hgt_attn_bwd_dst_blocks(int32_t n_dst);
+int agnn_hgt_attn_bwd_dst(int32_t n_dst, int heads, int head_dim, int dtype, int n_rel,
+                          const agnn_hgt_rel_t* rels /* host */, const void* q, int64_t ld_q, const float* pscale,
+                          const void* out, int64_t ld_out, const void* dout, int64_t ld_dout,
+                          const float* row_max, const float* row_den, float* delta, void* dq, int64_t ld_dq,
+                          float* dpscale_partial, agnn_stream_t stream);
+
+/* Backward, source side: for every relation r and source row j, dk_r[j], dv_r[j] (written, not
+ * accumulated) from the transposed CSR; alpha is recomputed from row_max / row_den. */
+int agnn_hgt_attn_bwd_src(int heads, int head_dim, int dtype, int n_rel, const agnn_hgt_rel_t* rels /* host */,
+                          const void* q, int64_t ld_q, const float* pscale, const void* dout, int64_t ld_dout,
+                          const float* row_max, const float* row_den, const float* delta, agnn_stream_t stream);
+
+/* ------------------------------------------------------------ optimizer step
+ * Replaces, for data-parallel training, what Lightning runs after the reference's
+ * training_step (analysisgnn/train/train_analysisgnn.py:246-255, gradient_clip_val=1.0
+ * = clip_grad_norm_; AdamW from analysisgnn/models/analysis.py:1380): one pass for the
+ * global gradient norm and one for  g <- g * grad_scale (1/world after the NCCL sum);
+ * g <- g * min(1, max_norm / (||g|| + 1e-6));  AdamW (torch.optim.AdamW arithmetic).
+ * Gradients and both moments live in flat fp32 arenas; parameters stay in their own
+ * tensors and are reached through a device-resident chunk table (one block per chunk,
+ * at most agnn_optim_chunk_elems() elements each; arena offsets multiples of 4).
+ */
+typedef struct agnn_param_chunk {
+  void* param;          /* base of the parameter tensor (fp32, contiguous)        */
+  int64_t param_off;    /* first element of this chunk inside the parameter       */
+  int64_t arena_off;    /* first element of this chunk inside grad / m / v arenas */
+  int32_t count;        /* elements in this chunk                                 */
+  int32_t param_aligned; /* 1 if (param + param_off) is 16-byte aligned           */
+} agnn_param_chunk_t;
+
+int agnn_optim_chunk_elems(void);
+int agnn_sumsq_blocks(int64_t n);
+/* partials[agnn_sumsq_blocks(n)] = per-block sums of grad^2 (n multiple of 4, arena 16-byte aligned) */
+int agnn_sumsq_partials(const float* grad, int64_t n, float* partials, agnn_stream_t stream);
+/* chunks: DEVICE array [n_chunks]; step counts from 1; max_norm <= 0 disables clipping;
+ * norm_out (optional, device) receives the norm of the averaged gradient. */
+int agnn_adamw_clip_step(const agnn_param_chunk_t* chunks /* device */, int n_chunks, const float* grad, float* m,
+                         float* v, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                         float grad_scale, float max_norm, const float* partials, int n_partials, float* norm_out,
+                         agnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

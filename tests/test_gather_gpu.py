@@ -1,0 +1,139 @@
+"""agnn_gather_reduce / agnn_rowscale_sum vs straight torch arithmetic on the CPU
+(the oracle's mean_into_copy / sum_into formulations, oracle/intree.py)."""
+import numpy as np
+import pytest
+import torch
+
+from analysisgnn_b200 import _lib, graph, ops
+from oracle import intree as oi
+from tests.util import DEV, BF16_REL, FP32_REL, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(n_rows, n_cols, e, seed, zipf=False):
+    rng = np.random.default_rng(seed)
+    if zipf:
+        row = np.minimum(rng.zipf(1.3, e) - 1, n_rows - 1)
+    else:
+        row = rng.integers(0, n_rows, e)
+    col = rng.integers(0, n_cols, e)
+    return torch.as_tensor(np.stack((row, col)), dtype=torch.long)
+
+
+@pytest.mark.parametrize("f", [4, 32, 64, 128, 256, 512])
+@pytest.mark.parametrize("mean", [False, True])
+def test_segment_reduce_forward_backward(f, mean):
+    n_rows, n_cols, e = 301, 257, 2000
+    ei = _graph(n_rows, n_cols, e, f)
+    torch.manual_seed(f)
+    src = torch.randn(n_cols, f)
+    self_add = torch.randn(n_rows, f)
+    g = torch.randn(n_rows, f)
+    s1 = src.clone().requires_grad_(True)
+    a1 = self_add.clone().requires_grad_(True)
+    if mean:
+        want = oi.mean_into_copy(s1[ei[1]], ei[0], a1)
+    else:
+        want = oi.sum_into(s1[ei[1]], ei[0], n_rows)
+    want.backward(g)
+    csr = graph.TypedCSR(ei.to(DEV), None, n_rows, n_cols=n_cols)
+    s2 = src.to(DEV).requires_grad_(True)
+    a2 = self_add.to(DEV).requires_grad_(True)
+    got = ops.segment_mean_self(s2, a2, csr) if mean else ops.segment_sum(s2, csr)
+    got.backward(g.to(DEV))
+    assert_close(got, want, FP32_REL, "forward")
+    assert_close(s2.grad, s1.grad, FP32_REL, "d src")
+    if mean:
+        assert_close(a2.grad, a1.grad, FP32_REL, "d self")
+
+
+def test_transposed_view_reduces_the_other_way():
+    n_rows, n_cols, e, f = 90, 140, 700, 64
+    ei = _graph(n_rows, n_cols, e, 3)
+    x = torch.randn(n_rows, f)
+    want = oi.sum_into(x[ei[0]], ei[1], n_cols)
+    csr = graph.TypedCSR(ei.to(DEV), None, n_rows, n_cols=n_cols)
+    got = ops.segment_sum(x.to(DEV), csr.t())
+    assert_close(got, want, FP32_REL)
+
+
+def test_skewed_degrees_and_empty_rows():
+    n, e, f = 5000, 60000, 256
+    ei = _graph(n, n, e, 5, zipf=True)
+    x = torch.randn(n, f)
+    want = oi.mean_into_copy(x[ei[1]], ei[0], x)
+    csr = graph.TypedCSR(ei.to(DEV), None, n)
+    got = ops.segment_mean_self(x.to(DEV), x.to(DEV), csr)
+    assert_close(got, want, FP32_REL)
+
+
+def test_no_edges_at_all():
+    n, f = 17, 32
+    ei = torch.zeros((2, 0), dtype=torch.long)
+    x = torch.randn(n, f)
+    csr = graph.TypedCSR(ei.to(DEV), None, n)
+    assert_close(ops.segment_sum(x.to(DEV), csr), torch.zeros(n, f) + 0 * x, FP32_REL)
+    got = ops.segment_mean_self(x.to(DEV), x.to(DEV), csr)
+    assert_close(got, x, FP32_REL)
+
+
+def test_bf16_mode():
+    n, e, f = 1000, 9000, 256
+    ei = _graph(n, n, e, 6)
+    x = torch.randn(n, f)
+    want = oi.mean_into_copy(x[ei[1]], ei[0], x)
+    csr = graph.TypedCSR(ei.to(DEV), None, n)
+    xb = x.to(DEV, torch.bfloat16)
+    got = ops.segment_mean_self(xb, xb, csr)
+    assert got.dtype == torch.bfloat16
+    assert_close(got.float(), want, BF16_REL)
+
+
+def test_multi_relation_concat_and_sum_modes():
+    """The relation-fused launch: every relation in its own output slice (concat) or summed."""
+    n, f, r = 400, 64, 5
+    rng = np.random.default_rng(11)
+    e = 3000
+    ei = torch.as_tensor(np.stack((rng.integers(0, n, e), rng.integers(0, n, e))), dtype=torch.long)
+    et = torch.as_tensor(rng.integers(0, r - 1, e))               # the last relation stays empty
+    h = torch.randn(n, r * f)
+    x = torch.randn(n, f)
+    csr = graph.TypedCSR(ei.to(DEV), et.to(DEV), n, n_rel=r)
+    hd, xd = h.to(DEV), x.to(DEV)
+    out = torch.empty((n, (r + 1) * f), device=DEV)
+    rels = [ops.Rel(csr.fwd.rowptr[k], csr.fwd.col, hd[:, k * f:(k + 1) * f], out_col=(k + 1) * f,
+                    flags=_lib.REL_IDENTITY_IF_EMPTY) for k in range(r)]
+    ops.gather_reduce(rels, out, f, mean=True, concat=True, self_add=xd, copy=xd, copy_col=0)
+    assert_close(out[:, :f], x, 0.0, "copy slice")
+    for k in range(r):
+        pick = et == k
+        hk = h[:, k * f:(k + 1) * f]
+        want = oi.mean_into_copy(hk[ei[1][pick]], ei[0][pick], x) if pick.any() else hk   # gnn.py:67-69
+        assert_close(out[:, (k + 1) * f:(k + 2) * f], want, FP32_REL, f"relation {k}")
+    tot = torch.empty((n, f), device=DEV)
+    rels = [ops.Rel(csr.fwd.rowptr[k], csr.fwd.col, hd[:, k * f:(k + 1) * f]) for k in range(r)]
+    ops.gather_reduce(rels, tot, f, mean=True, concat=False, self_add=xd)
+    want = x.clone()
+    for k in range(r):
+        pick = et == k
+        hk = h[:, k * f:(k + 1) * f]
+        want = want + oi.mean_into_copy(hk[ei[1][pick]], ei[0][pick], torch.zeros(n, f))
+    assert_close(tot, want, FP32_REL, "sum mode")
+
+
+def test_linearity_at_full_size():
+    """BASELINE config 1 size: gather(a + b) == gather(a) + gather(b), and the column sums of an
+    un-normalised gather equal the degree-weighted column sums of the input."""
+    from analysisgnn_b200 import synth
+    b = synth.intree_batch(100, 500, 1, in_features=8, metrical=False)
+    n, f = b["x"].shape[0], 256
+    ei = b["edge_index"].to(DEV)
+    csr = graph.TypedCSR(ei, None, n)
+    torch.manual_seed(0)
+    a, c = torch.randn(n, f, device=DEV), torch.randn(n, f, device=DEV)
+    ga, gc, gac = ops.segment_sum(a, csr), ops.segment_sum(c, csr), ops.segment_sum(a + c, csr)
+    assert_close(gac, ga + gc, FP32_REL)
+    outdeg = torch.bincount(b["edge_index"][1], minlength=n).double().to(DEV)
+    want = (a.double() * outdeg[:, None]).sum(0)
+    assert_close(ga.double().sum(0), want, FP32_REL)

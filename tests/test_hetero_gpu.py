@@ -1,0 +1,251 @@
+"""CUDA PyG-style encoders (analysisgnn_b200/nn/hetero.py, shell.py) vs this repo's
+restatement of the PyG / graphmuse operators (oracle/pyg.py -- parity UNPINNED against
+upstream PyG, see oracle/__init__.py).  fp32 1e-5 relative; bf16 2e-2."""
+import pytest
+import torch
+
+from analysisgnn_b200 import graph, ops, synth
+from analysisgnn_b200 import nn as ann
+from oracle import pyg as op
+from tests.util import DEV, BF16_REL, FP32_REL, assert_close, grads_of
+
+pytestmark = pytest.mark.gpu
+
+
+def _mv(d, dev=DEV):
+    return {k: v.to(dev) for k, v in d.items()}
+
+
+def _stack_pair(cls_ref, cls_net, b, f_in, hidden, layers, **kw):
+    torch.manual_seed(0)
+    ref = cls_ref(b["metadata"][1] if cls_ref is op.HeteroSAGEStack else b["metadata"], f_in, hidden, layers, **kw)
+    net = cls_net(b["metadata"][1] if cls_net is ann.HeteroSAGEStack else b["metadata"], f_in, hidden, layers, **kw)
+    net.load_state_dict(ref.state_dict())
+    return ref, net.to(DEV)
+
+
+def _features(b, f, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return {k: torch.randn(v.shape[0], f, generator=g) for k, v in b["x_dict"].items()}
+
+
+def _compare_dict_outputs(ref, net, x_cpu, ei_cpu, tol, extra=()):
+    x1 = {k: v.clone().requires_grad_(True) for k, v in x_cpu.items()}
+    o1 = ref(x1, ei_cpu, *extra)
+    x2 = {k: v.to(DEV).requires_grad_(True) for k, v in x_cpu.items()}
+    o2 = net(x2, _mv(ei_cpu), *extra)
+    assert set(o1) == set(o2)
+    cat1 = torch.cat([o1[k] for k in sorted(o1)], dim=0)
+    cat2 = torch.cat([o2[k] for k in sorted(o1)], dim=0)
+    for k in o1:
+        assert_close(o2[k], o1[k], tol, f"forward {k}")
+    keys = sorted(x1)
+    pg1, ig1 = grads_of(ref, cat1, [x1[k] for k in keys])
+    pg2, ig2 = grads_of(net, cat2, [x2[k] for k in keys])
+    assert set(pg1) == set(pg2)
+    for k in pg1:
+        assert_close(pg2[k], pg1[k], tol, f"grad {k}")
+    for k, a, c in zip(keys, ig2, ig1):
+        if c is None:
+            assert a is None or float(a.abs().max()) == 0.0
+        else:
+            assert_close(a, c, tol, f"grad x[{k}]")
+
+
+@pytest.mark.parametrize("aggr", ["sum", "mean"])
+def test_sage_layer(aggr):
+    b = synth.hetero_batch(3, 90, 30)
+    torch.manual_seed(0)
+    ref = op.HeteroSAGELayer(b["metadata"][1], 32, 48, aggr)
+    net = ann.HeteroSAGELayer(b["metadata"][1], 32, 48, aggr)
+    net.load_state_dict(ref.state_dict())
+    _compare_dict_outputs(ref, net.to(DEV), _features(b, 32), b["edge_index_dict"], FP32_REL)
+
+
+def test_sage_layer_with_missing_relations_and_types():
+    """Edge types absent from the batch are skipped; a node type that receives nothing is
+    absent from the output (PyG HeteroConv)."""
+    b = synth.hetero_batch(2, 80, 31)
+    ei = {k: v for k, v in b["edge_index_dict"].items() if k[2] != "measure" and k[1] != "rest"}
+    torch.manual_seed(0)
+    ref = op.HeteroSAGELayer(b["metadata"][1], 16, 16)
+    net = ann.HeteroSAGELayer(b["metadata"][1], 16, 16)
+    net.load_state_dict(ref.state_dict())
+    _compare_dict_outputs(ref, net.to(DEV), _features(b, 16), ei, FP32_REL)
+
+
+def test_single_sageconv_module():
+    b = synth.hetero_batch(2, 60, 32, add_beats=False, add_measures=False)
+    ei = b["edge_index_dict"][("note", "during", "note")]
+    torch.manual_seed(0)
+    ref, net = op.SAGEConv(24, 40), ann.SAGEConv(24, 40)
+    net.load_state_dict(ref.state_dict())
+    net.to(DEV)
+    x = torch.randn(b["batch_size"], 24)
+    x1 = x.clone().requires_grad_(True)
+    o1 = ref(x1, x1, ei)
+    x2 = x.to(DEV).requires_grad_(True)
+    o2 = net(x2, x2, ei.to(DEV))
+    assert_close(o2, o1, FP32_REL)
+    pg1, ig1 = grads_of(ref, o1, [x1])
+    pg2, ig2 = grads_of(net, o2, [x2])
+    for k in pg1:
+        assert_close(pg2[k], pg1[k], FP32_REL, k)
+    assert_close(ig2[0], ig1[0], FP32_REL, "x")
+
+
+def test_sage_stack_3x256():
+    b = synth.hetero_batch(3, 150, 33)
+    ref, net = _stack_pair(op.HeteroSAGEStack, ann.HeteroSAGEStack, b, 256, 256, 3)
+    _compare_dict_outputs(ref, net, _features(b, 256), b["edge_index_dict"], FP32_REL)
+
+
+def test_sage_stack_trim_to_layer():
+    """Sampled-batch layout: per-hop node / edge counts, trim_to_layer before every layer."""
+    from oracle import graph as og
+    import numpy as np
+    na = synth.synth_note_array(400, 34, 4)
+    e = synth.score_graph_edges(na)
+    rowptr, col, perm = og.csr_build(e[1], e[0], 400, e[2], 4)
+    s = og.neighbor_sample(rowptr, col, 400, np.arange(150, 200), [4, 4], seed=1, n_rel=4)
+    names = ["onset", "consecutive", "during", "rest"]
+    ets = [("note", r, "note") for r in names]
+    ei = {et: torch.as_tensor(np.stack((s["src"][k], s["dst"][k]))) for k, et in enumerate(ets)}
+    nodes_per_hop = {"note": s["num_sampled_nodes"]}
+    edges_per_hop = {et: s["num_sampled_edges"][k] for k, et in enumerate(ets)}
+    n = len(s["node"])
+    torch.manual_seed(0)
+    ref = op.HeteroSAGEStack(ets, 32, 32, 3)
+    net = ann.HeteroSAGEStack(ets, 32, 32, 3)
+    net.load_state_dict(ref.state_dict())
+    x = {"note": torch.randn(n, 32)}
+    _compare_dict_outputs(ref, net.to(DEV), x, ei, FP32_REL, extra=(nodes_per_hop, edges_per_hop))
+
+
+@pytest.mark.parametrize("joint", [True, False])
+@pytest.mark.parametrize("heads,hidden", [(4, 256), (2, 64), (8, 128)])
+def test_hgt_conv(joint, heads, hidden):
+    b = synth.hetero_batch(2, 70, 35)
+    torch.manual_seed(0)
+    ref = op.HGTConv(hidden, hidden, b["metadata"], heads, joint_softmax=joint)
+    net = ann.HGTConv(hidden, hidden, b["metadata"], heads, joint_softmax=joint)
+    with torch.no_grad():                                   # make p_rel / skip non-trivial
+        for p in ref.p_rel.values():
+            p.uniform_(0.5, 1.5)
+        for p in ref.skip.values():
+            p.uniform_(-1.0, 1.0)
+    net.load_state_dict(ref.state_dict())
+    _compare_dict_outputs(ref, net.to(DEV), _features(b, hidden), b["edge_index_dict"], 2 * FP32_REL)
+
+
+def test_hgt_isolated_targets_get_zero_attention():
+    b = synth.hetero_batch(1, 40, 36, add_beats=False, add_measures=False)
+    ei = {k: v[:, v[1] % 3 != 0] for k, v in b["edge_index_dict"].items()}      # targets 0,3,6,.. isolated
+    torch.manual_seed(0)
+    ref = op.HGTConv(32, 32, b["metadata"], 4)
+    net = ann.HGTConv(32, 32, b["metadata"], 4)
+    net.load_state_dict(ref.state_dict())
+    _compare_dict_outputs(ref, net.to(DEV), _features(b, 32), ei, 2 * FP32_REL)
+
+
+@pytest.mark.parametrize("encoder_type", ["hybridgnn", "hgt", "metricalgnn"])
+def test_analysis_encoder_shell(encoder_type):
+    """BASELINE configs 2 / 3 architecture (3 layers, hidden 256, beat + measure nodes, three task
+    heads) on a small batch: logits, loss and every gradient."""
+    tasks = {"cadence": 4, "localkey": 50, "romanNumeral": 185}
+    b = synth.hetero_batch(3, 130, 37, in_features=25, task_dict=tasks)
+    torch.manual_seed(0)
+    if encoder_type == "metricalgnn":
+        pytest.skip("oracle shell has no metricalgnn wiring; covered by test_graphmuse_metricalgnn")
+    ref = op.AnalysisEncoderShell(b["metadata"], 25, 256, 128, tasks, 3, dropout=0.0, encoder_type=encoder_type)
+    net = ann.AnalysisEncoder(b["metadata"], 25, 256, 128, tasks, 3, dropout=0.0, encoder_type=encoder_type)
+    net.load_state_dict(ref.state_dict())
+    net.to(DEV)
+    args = lambda d: (b["pitch_spelling"].to(d), b["key_signature"].to(d), _mv(b["x_dict"], d),
+                      _mv(b["edge_index_dict"], d), _mv(b["batch_dict"], d), b["batch_size"], None, None)
+    l1 = ref(*args("cpu"))
+    loss1 = op.multitask_ce(l1, b["labels"])
+    loss1.backward()
+    l2 = net(*args(DEV))
+    loss2 = ann.multitask_ce(l2, _mv(b["labels"]))
+    loss2.backward()
+    tol = 3 * FP32_REL
+    for t in tasks:
+        assert_close(l2[t], l1[t], tol, f"logits {t}")
+    assert_close(loss2, loss1, tol, "loss")
+    g1 = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    g2 = {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
+    assert set(g1) <= set(g2)
+    for k in g1:
+        assert_close(g2[k], g1[k], 10 * FP32_REL, f"grad {k}")
+
+
+def test_graphmuse_metricalgnn():
+    b = synth.hetero_batch(2, 100, 38)
+    torch.manual_seed(0)
+    ref = op.MetricalGNN(b["metadata"], 64, 64, 32, 3, dropout=0.0)
+    net = ann.hetero.MetricalGNN(b["metadata"], 64, 64, 32, 3, dropout=0.0)
+    net.load_state_dict(ref.state_dict())
+    net.to(DEV)
+    x = _features(b, 64)
+    o1 = ref(x, b["edge_index_dict"])
+    o2 = net(_mv(x), _mv(b["edge_index_dict"]))
+    assert_close(o2, o1, FP32_REL)
+
+
+def test_overlapped_sequence_branch_matches_serial():
+    """The GRU branch on a side stream must give the same numbers as running it in line."""
+    b = synth.hetero_batch(3, 110, 39)
+    torch.manual_seed(0)
+    net = ann.HybridGNN(b["metadata"], 64, 64, 3, dropout=0.0).to(DEV)
+    x = _mv(_features(b, 64))
+    ei = _mv(b["edge_index_dict"])
+    bd = _mv(b["batch_dict"])
+    outs = []
+    for overlap in (False, True):
+        net.overlap_sequence_branch = overlap
+        net.zero_grad()
+        o = net(x, ei, bd, b["batch_size"])
+        o.square().sum().backward()
+        torch.cuda.synchronize()
+        outs.append((o.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()}))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for k in outs[0][1]:
+        assert torch.equal(outs[0][1][k], outs[1][1][k]), k
+
+
+def test_bf16_mode_hybridgnn():
+    """Stated bf16 mode: features / weights in bf16, accumulation in fp32, 2e-2 relative."""
+    b = synth.hetero_batch(3, 120, 40)
+    ref, net = _stack_pair(op.HeteroSAGEStack, ann.HeteroSAGEStack, b, 64, 64, 3)
+    x = _features(b, 64)
+    o1 = ref({k: v.clone() for k, v in x.items()}, b["edge_index_dict"])
+    net = net.to(torch.bfloat16)
+    o2 = net({k: v.to(DEV, torch.bfloat16) for k, v in x.items()}, _mv(b["edge_index_dict"]))
+    for k in o1:
+        assert o2[k].dtype == torch.bfloat16
+        assert_close(o2[k].float(), o1[k], BF16_REL, k)
+
+
+def test_bf16_mode_hgt_attention():
+    b = synth.hetero_batch(2, 80, 41, add_beats=False, add_measures=False)
+    torch.manual_seed(0)
+    ref = op.HGTConv(64, 64, b["metadata"], 4)
+    net = ann.HGTConv(64, 64, b["metadata"], 4)
+    net.load_state_dict(ref.state_dict())
+    net = net.to(DEV, torch.bfloat16)
+    x = _features(b, 64)
+    o1 = ref(x, b["edge_index_dict"])
+    o2 = net({k: v.to(DEV, torch.bfloat16) for k, v in x.items()}, _mv(b["edge_index_dict"]))
+    assert_close(o2["note"].float(), o1["note"], BF16_REL)
+
+
+def test_onset_pool_filter_matches_reference_recipe():
+    from oracle import intree as oi
+    b = synth.hetero_batch(2, 90, 42, add_beats=False, add_measures=False)
+    x = torch.randn(b["batch_size"], 32)
+    onset = b["edge_index_dict"][("note", "onset", "note")]
+    bs = 120                                              # only the first 120 notes are targets
+    want = oi.onset_pool(x[:bs], onset, bs)
+    got = ann.shell.onset_pool(x[:bs].to(DEV), onset.to(DEV), bs)
+    assert_close(got, want, FP32_REL)

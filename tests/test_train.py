@@ -1,0 +1,140 @@
+"""Data-parallel step: gradient arena + allreduce (host logic, gloo world_size 2 on CPU) and the
+fused clip + AdamW kernels vs torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW (GPU)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+from analysisgnn_b200 import _lib
+from analysisgnn_b200.train import DataParallelTrainer, GradArena, shard_indices
+from tests.util import DEV, assert_close
+
+
+def _toy(seed=0):
+    torch.manual_seed(seed)
+    return nn.Sequential(nn.Linear(7, 13), nn.ReLU(), nn.Linear(13, 5), nn.LayerNorm(5), nn.Linear(5, 3, bias=False))
+
+
+def test_arena_views_and_zero_filled_unused_parameters():
+    net = _toy()
+    extra = nn.Linear(4, 4)                                  # never used in the loss
+    params = list(net.parameters()) + list(extra.parameters())
+    arena = GradArena(params, 4096)
+    assert arena.numel % 4 == 0 and all(o % 4 == 0 for o in arena.offsets)
+    net(torch.randn(9, 7)).sum().backward()
+    arena.check_views()
+    ref = _toy()
+    ref(torch.randn(9, 7))                                    # different input: just shapes
+    for p, o in zip(arena.params, arena.offsets):
+        assert torch.equal(arena.grad[o:o + p.numel()].view_as(p), p.grad)
+    assert float(extra.weight.grad.abs().sum()) == 0.0        # zeros, not None
+    arena.zero_()
+    assert float(arena.grad.abs().sum()) == 0.0 and float(net[0].weight.grad.abs().sum()) == 0.0
+    net.zero_grad(set_to_none=True)
+    with pytest.raises(RuntimeError):
+        arena.check_views()
+
+
+def test_shard_indices_partition_the_batch():
+    for world in (1, 2, 4, 8):
+        parts = [shard_indices(100, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(100))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_step_refuses_cpu_parameters():
+    net = _toy()
+    tr = DataParallelTrainer(net, world_size=1)
+    net(torch.randn(3, 7)).sum().backward()
+    with pytest.raises(_lib.AgnnError):
+        tr.step()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    net = _toy(0)                                            # same weights on every rank
+    tr = DataParallelTrainer(net)
+    assert tr.world_size == world
+    torch.manual_seed(100)
+    data = torch.randn(12, 7)
+    tr.zero_grad()
+    net(data[shard_indices(12, rank, world)]).sum().backward()
+    tr.allreduce()
+    out[rank] = tr.arena.grad.clone()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_allreduce_equals_full_batch_gradient():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        g0, g1 = out[0], out[1]
+    assert torch.equal(g0, g1)
+    net = _toy(0)
+    tr = DataParallelTrainer(net, world_size=1)
+    torch.manual_seed(100)
+    net(torch.randn(12, 7)).sum().backward()
+    assert_close(g0, tr.arena.grad, 1e-6, "sum of shard gradients")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_norm", [1.0, 0.0, 1e6])
+def test_fused_clip_adamw_matches_torch(max_norm):
+    torch.manual_seed(0)
+    mk = lambda: nn.Sequential(nn.Linear(33, 257), nn.ReLU(), nn.Linear(257, 129), nn.LayerNorm(129),
+                               nn.Linear(129, 5001, bias=False), nn.GRU(3, 9, num_layers=2, bidirectional=True))
+    a = mk().to(DEV)
+    b = mk().to(DEV)
+    b.load_state_dict(a.state_dict())
+    tr = DataParallelTrainer(a, lr=5e-3, weight_decay=5e-3, max_norm=max_norm, world_size=1)
+    opt = torch.optim.AdamW(b.parameters(), lr=5e-3, weight_decay=5e-3)
+    for it in range(4):
+        x = torch.randn(64, 33, device=DEV) * (10.0 if it % 2 else 0.1)
+
+        def loss_of(net):
+            h = net[4](net[3](net[2](net[1](net[0](x)))))
+            return h.square().mean() + net[5](h[:, :3].unsqueeze(0))[0].sum()
+        tr.zero_grad()
+        loss_of(a).backward()
+        tr.step()
+        opt.zero_grad(set_to_none=True)
+        loss_of(b).backward()
+        if max_norm:
+            norm = torch.nn.utils.clip_grad_norm_(b.parameters(), max_norm)
+            assert_close(tr.grad_norm[0], norm, 1e-5, "gradient norm")
+        opt.step()
+        for (n, p), q in zip(a.named_parameters(), b.parameters()):
+            assert_close(p, q, 2e-6, f"step {it} {n}")
+
+
+@pytest.mark.gpu
+def test_grad_scale_is_the_world_average():
+    torch.manual_seed(1)
+    a = nn.Linear(16, 16).to(DEV)
+    b = nn.Linear(16, 16).to(DEV)
+    b.load_state_dict(a.state_dict())
+    tr = DataParallelTrainer(a, max_norm=0.0, world_size=1)
+    tr.world_size = 4                                        # pretend the arena holds a 4-rank sum
+    opt = torch.optim.AdamW(b.parameters(), lr=5e-3, weight_decay=5e-3)
+    x = torch.randn(8, 16, device=DEV)
+    tr.zero_grad()
+    (a(x).sum() * 4).backward()
+    tr.allreduce = lambda: None
+    tr.step()
+    b(x).sum().backward()
+    opt.step()
+    assert_close(a.weight, b.weight, 2e-6)
