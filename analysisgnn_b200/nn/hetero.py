@@ -303,7 +303,7 @@ class SequenceBranch(nn.Module):
     def forward(self, x, batch):
         layout = graph.batch_layout(batch)
         seq = layout.pad(x)
-        seq, _ = self.rnn(seq)
+        seq = ops.run_rnn(self.rnn, seq)
         seq = self.rnn_mlp(self.rnn_norm(seq))
         return layout.unpad(seq)
 

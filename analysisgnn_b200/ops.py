@@ -462,3 +462,8 @@ def side_stream(device) -> "torch.cuda.Stream":
     if idx not in _side_streams:
         _side_streams[idx] = torch.cuda.Stream(device=idx)
     return _side_streams[idx]
+
+
+def run_rnn(rnn: "torch.nn.RNNBase", seq: torch.Tensor):
+    """cuDNN RNN (kept as a library call: the GRU branches are outside the kernel scope)."""
+    return rnn(seq)[0]

@@ -298,7 +298,9 @@ def run_ours(args):
         sampler.start()
     ops.timer = ops.KernelTimer()
     launches0 = _lib.launches()
+    torch.cuda.profiler.start()                    # ncu --profile-from-start off captures the timed region only
     ms, wall = timed(lambda: step(resident), args.steps)
+    torch.cuda.profiler.stop()
     launches = _lib.launches() - launches0
     ktimes = ops.timer.summary()
     ops.timer = None
@@ -311,7 +313,8 @@ def run_ours(args):
         g = ktimes.get("gather_reduce", {"launches": 0, "bytes": 0, "ms": 0.0, "max_bytes": 0, "max_ms": 0.0})
         achieved = g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] > 0 else 0.0
         big = g["max_bytes"] / (g["max_ms"] * 1e-3) / 1e9 if g["max_ms"] > 0 else 0.0
-        cpu = cpu_arm(steps=2, warmup=1, budget_s=20.0, max_graphs=20)
+        cpu = cpu_arm(steps=2, warmup=1, budget_s=20.0, max_graphs=20) if not args.skip_cpu else \
+            {"value": None, "unit": "nodes/s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped (--skip-cpu)"}
         value = world * n_nodes * args.steps / (ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
@@ -345,6 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--skip-cpu", action="store_true", help="leave out the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

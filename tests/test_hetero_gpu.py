@@ -7,7 +7,8 @@ import torch
 from analysisgnn_b200 import graph, ops, synth
 from analysisgnn_b200 import nn as ann
 from oracle import pyg as op
-from tests.util import DEV, BF16_REL, FP32_REL, assert_close, grads_of
+from tests.util import (DEV, BF16_REL, FP32_REL, ActivationPatterns, assert_close, feeds_relu,
+                        first_seed_with_equal_patterns, grads_of)
 
 pytestmark = pytest.mark.gpu
 
@@ -29,27 +30,62 @@ def _features(b, f, seed=0):
     return {k: torch.randn(v.shape[0], f, generator=g) for k, v in b["x_dict"].items()}
 
 
-def _compare_dict_outputs(ref, net, x_cpu, ei_cpu, tol, extra=()):
+def _fp64_floor(ref, x_cpu, ei_cpu, extra, pg1, ig1, keys):
+    """Per-tensor error of the fp32 CPU oracle against the same oracle in fp64: where the quantity
+    itself is ill-conditioned in fp32 (softmax-gradient cancellation), the CUDA path is held to a
+    small multiple of what the fp32 oracle achieves rather than to a number neither can reach."""
+    import copy
+    ref64 = copy.deepcopy(ref).double()
+    x3 = {k: v.double().requires_grad_(True) for k, v in x_cpu.items()}
+    o3 = ref64(x3, ei_cpu, *extra)
+    cat3 = torch.cat([o3[k] for k in sorted(o3)], dim=0)
+    w = torch.linspace(0.25, 1.25, cat3.numel(), dtype=torch.float64).view_as(cat3)
+    named = list(ref64.named_parameters())
+    got = torch.autograd.grad((cat3 * w).sum(), [p for _, p in named] + [x3[k] for k in keys], allow_unused=True)
+    from tests.util import rel_err
+    floor = {n: rel_err(pg1[n], g) for (n, _), g in zip(named, got[:len(named)]) if g is not None and n in pg1}
+    xfloor = [rel_err(a, g) if g is not None and a is not None else 0.0 for a, g in zip(ig1, got[len(named):])]
+    return floor, xfloor
+
+
+def _compare_dict_outputs(ref, net, x_cpu, ei_cpu, tol, extra=(), deep=False, fp64_floor=False):
+    """Forward + every gradient.  ``deep``: the model applies ReLUs, so gradients are compared
+    only if both sides produced the same activation pattern (tests/util.py); returns the number
+    of pattern mismatches (0 = everything was compared)."""
+    pr = ActivationPatterns(ref, feeds_relu) if deep else None
+    pn = ActivationPatterns(net, feeds_relu) if deep else None
     x1 = {k: v.clone().requires_grad_(True) for k, v in x_cpu.items()}
     o1 = ref(x1, ei_cpu, *extra)
     x2 = {k: v.to(DEV).requires_grad_(True) for k, v in x_cpu.items()}
     o2 = net(x2, _mv(ei_cpu), *extra)
     assert set(o1) == set(o2)
-    cat1 = torch.cat([o1[k] for k in sorted(o1)], dim=0)
-    cat2 = torch.cat([o2[k] for k in sorted(o1)], dim=0)
     for k in o1:
         assert_close(o2[k], o1[k], tol, f"forward {k}")
+    if deep:
+        mism = pr.mismatches(pn)
+        pr.close(), pn.close()
+        if mism:
+            return mism
+    cat1 = torch.cat([o1[k] for k in sorted(o1)], dim=0)
+    cat2 = torch.cat([o2[k] for k in sorted(o1)], dim=0)
     keys = sorted(x1)
     pg1, ig1 = grads_of(ref, cat1, [x1[k] for k in keys])
     pg2, ig2 = grads_of(net, cat2, [x2[k] for k in keys])
     assert set(pg1) == set(pg2)
+    floor, xfloor = _fp64_floor(ref, x_cpu, ei_cpu, extra, pg1, ig1, keys) if fp64_floor else ({}, [0.0] * len(keys))
     for k in pg1:
-        assert_close(pg2[k], pg1[k], tol, f"grad {k}")
-    for k, a, c in zip(keys, ig2, ig1):
+        assert_close(pg2[k], pg1[k], max(tol, 4 * floor.get(k, 0.0)), f"grad {k}")
+    for k, a, c, fl in zip(keys, ig2, ig1, xfloor):
         if c is None:
             assert a is None or float(a.abs().max()) == 0.0
         else:
-            assert_close(a, c, tol, f"grad x[{k}]")
+            assert_close(a, c, max(tol, 4 * fl), f"grad x[{k}]")
+    return 0
+
+
+def _deep(ref, net, b, f, ei, tol, extra=()):
+    first_seed_with_equal_patterns(
+        lambda seed: (_compare_dict_outputs(ref, net, _features(b, f, seed), ei, tol, extra, deep=True), None))
 
 
 @pytest.mark.parametrize("aggr", ["sum", "mean"])
@@ -97,7 +133,7 @@ def test_single_sageconv_module():
 def test_sage_stack_3x256():
     b = synth.hetero_batch(3, 150, 33)
     ref, net = _stack_pair(op.HeteroSAGEStack, ann.HeteroSAGEStack, b, 256, 256, 3)
-    _compare_dict_outputs(ref, net, _features(b, 256), b["edge_index_dict"], FP32_REL)
+    _deep(ref, net, b, 256, b["edge_index_dict"], FP32_REL)
 
 
 def test_sage_stack_trim_to_layer():
@@ -118,8 +154,8 @@ def test_sage_stack_trim_to_layer():
     ref = op.HeteroSAGEStack(ets, 32, 32, 3)
     net = ann.HeteroSAGEStack(ets, 32, 32, 3)
     net.load_state_dict(ref.state_dict())
-    x = {"note": torch.randn(n, 32)}
-    _compare_dict_outputs(ref, net.to(DEV), x, ei, FP32_REL, extra=(nodes_per_hop, edges_per_hop))
+    fake = {"x_dict": {"note": torch.empty(n, 1)}}
+    _deep(ref, net.to(DEV), fake, 32, ei, FP32_REL, extra=(nodes_per_hop, edges_per_hop))
 
 
 @pytest.mark.parametrize("joint", [True, False])
@@ -135,7 +171,8 @@ def test_hgt_conv(joint, heads, hidden):
         for p in ref.skip.values():
             p.uniform_(-1.0, 1.0)
     net.load_state_dict(ref.state_dict())
-    _compare_dict_outputs(ref, net.to(DEV), _features(b, hidden), b["edge_index_dict"], 2 * FP32_REL)
+    _compare_dict_outputs(ref, net.to(DEV), _features(b, hidden), b["edge_index_dict"], 2 * FP32_REL,
+                          fp64_floor=True)
 
 
 def test_hgt_isolated_targets_get_zero_attention():
@@ -161,23 +198,38 @@ def test_analysis_encoder_shell(encoder_type):
     net = ann.AnalysisEncoder(b["metadata"], 25, 256, 128, tasks, 3, dropout=0.0, encoder_type=encoder_type)
     net.load_state_dict(ref.state_dict())
     net.to(DEV)
-    args = lambda d: (b["pitch_spelling"].to(d), b["key_signature"].to(d), _mv(b["x_dict"], d),
-                      _mv(b["edge_index_dict"], d), _mv(b["batch_dict"], d), b["batch_size"], None, None)
-    l1 = ref(*args("cpu"))
-    loss1 = op.multitask_ce(l1, b["labels"])
-    loss1.backward()
-    l2 = net(*args(DEV))
-    loss2 = ann.multitask_ce(l2, _mv(b["labels"]))
-    loss2.backward()
-    tol = 3 * FP32_REL
-    for t in tasks:
-        assert_close(l2[t], l1[t], tol, f"logits {t}")
-    assert_close(loss2, loss1, tol, "loss")
-    g1 = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
-    g2 = {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
-    assert set(g1) <= set(g2)
-    for k in g1:
-        assert_close(g2[k], g1[k], 10 * FP32_REL, f"grad {k}")
+
+    def run(seed):
+        bb = synth.hetero_batch(3, 130, 37 + 100 * seed, in_features=25, task_dict=tasks)
+        args = lambda d: (bb["pitch_spelling"].to(d), bb["key_signature"].to(d), _mv(bb["x_dict"], d),
+                          _mv(bb["edge_index_dict"], d), _mv(bb["batch_dict"], d), bb["batch_size"], None, None)
+        pr, pn = ActivationPatterns(ref, feeds_relu), ActivationPatterns(net, feeds_relu)
+        ref.zero_grad(), net.zero_grad()
+        l1 = ref(*args("cpu"))
+        loss1 = op.multitask_ce(l1, bb["labels"])
+        l2 = net(*args(DEV))
+        loss2 = ann.multitask_ce(l2, _mv(bb["labels"]))
+        mism = pr.mismatches(pn)
+        pr.close(), pn.close()
+        tol = 3 * FP32_REL
+        for t in tasks:
+            assert_close(l2[t], l1[t], tol, f"logits {t}")
+        assert_close(loss2, loss1, tol, "loss")
+        if mism:
+            return mism, None
+        loss1.backward()
+        loss2.backward()
+        g1 = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+        g2 = {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
+        assert set(g1) <= set(g2)
+        for k in g2:
+            if k in g1:
+                assert_close(g2[k], g1[k], 10 * FP32_REL, f"grad {k}")
+            else:                                              # unused in the oracle (None there)
+                assert float(g2[k].abs().max()) == 0.0, k
+        return 0, None
+
+    first_seed_with_equal_patterns(run)
 
 
 def test_graphmuse_metricalgnn():
@@ -208,7 +260,7 @@ def test_overlapped_sequence_branch_matches_serial():
         o = net(x, ei, bd, b["batch_size"])
         o.square().sum().backward()
         torch.cuda.synchronize()
-        outs.append((o.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()}))
+        outs.append((o.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}))
     assert torch.equal(outs[0][0], outs[1][0])
     for k in outs[0][1]:
         assert torch.equal(outs[0][1][k], outs[1][1][k]), k

@@ -52,3 +52,64 @@ def grads_of(module, out, inputs):
     got = torch.autograd.grad(loss, [p for _, p in named] + list(inputs), allow_unused=True)
     pg = {n: g for (n, _), g in zip(named, got[:len(named)]) if g is not None}
     return pg, list(got[len(named):])
+
+
+# ---------------------------------------------------------------------------------------------
+# ReLU-pattern bookkeeping.  A gradient is a discontinuous function of the inputs wherever a
+# pre-activation crosses zero: two correct fp32 implementations that sum in a different order can
+# put a |z| ~ 1e-7 pre-activation on opposite sides, and on a few-hundred-node test graph that one
+# flipped unit moves a weight gradient by ~1e-3 of its scale.  The parity claim "gradients within
+# 1e-5" is therefore stated -- and tested -- on inputs where both implementations produce the same
+# activation pattern; the helpers below record the patterns so a test can tell the two cases apart
+# and move to the next seed instead of asserting on a flipped unit.
+# ---------------------------------------------------------------------------------------------
+
+class ActivationPatterns:
+    """Records ``output > 0`` of every module selected by ``pick(name, module)`` (tensor or dict
+    of tensors), keyed by module name (the two implementations may run branches in a different
+    order) and call count."""
+
+    def __init__(self, model, pick):
+        self.masks = {}
+        self.handles = [m.register_forward_hook(self._hook(n)) for n, m in model.named_modules() if pick(n, m)]
+
+    def _hook(self, name):
+        def hook(module, args, out):
+            outs = out if isinstance(out, dict) else {"": out[0] if isinstance(out, tuple) else out}
+            self.masks.setdefault(name, []).append({k: (o.detach() > 0).cpu() for k, o in outs.items()})
+        return hook
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
+
+    def mismatches(self, other: "ActivationPatterns") -> int:
+        assert set(self.masks) == set(other.masks), set(self.masks) ^ set(other.masks)
+        total = 0
+        for name, calls in self.masks.items():
+            assert len(calls) == len(other.masks[name]), name
+            for a, b in zip(calls, other.masks[name]):
+                # dict outputs: a destination type one side skipped as unused (last layer) is not compared
+                total += sum(int((a[k] != b[k]).sum()) for k in a if k in b)
+        return total
+
+
+def feeds_relu(name, module):
+    """Modules whose output goes straight into a ReLU in the encoders under test."""
+    cls = type(module).__name__
+    if cls in ("ReLU", "HeteroSAGELayer", "HGTConv", "HeteroConv"):
+        return True
+    return cls == "Linear" and (name.endswith("conv_out") or ".project_metrical." in name
+                                or name.startswith("project_metrical."))
+
+
+def first_seed_with_equal_patterns(run, seeds=(0, 1, 2, 3, 4, 5)):
+    """``run(seed)`` -> (mismatches, payload).  Returns the payload of the first seed on which
+    the CPU oracle and the CUDA path agree on every activation sign; fails if none does."""
+    seen = []
+    for seed in seeds:
+        mism, payload = run(seed)
+        seen.append(mism)
+        if mism == 0:
+            return payload
+    raise AssertionError(f"activation patterns differed on every seed: {seen}")
