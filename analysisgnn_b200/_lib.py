@@ -22,6 +22,9 @@ F32, BF16 = 0, 1
 SCALE_NONE, SCALE_MEAN = 0, 1
 COMBINE_CONCAT, COMBINE_SUM = 0, 1
 REL_IDENTITY_IF_EMPTY = 1
+GEMM_TF32X3, GEMM_TF32, GEMM_BF16 = 0, 1, 2
+K_MAJOR, MN_MAJOR = 0, 1
+GEMM_RELU, GEMM_ACCUMULATE, GEMM_OUT_BF16 = 1, 2, 4
 
 
 class AgnnError(RuntimeError):
@@ -78,6 +81,13 @@ _PROTOTYPES = {
     "agnn_adamw_clip_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                        C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p,
                                        C.c_int, C.c_void_p, C.c_void_p]),
+    "agnn_split_tf32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p]),
+    "agnn_gemm_split_k": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64]),
+    "agnn_gemm_workspace": (C.c_size_t, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "agnn_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                            C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
+                            C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,596 @@
+// Dense projections on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators,
+// TMA-fed shared-memory operands, mbarrier pipelines, one persistent CTA per SM.
+//
+// Replaces the nn.Linear calls of the hot path -- SageConvScatter's neigh_linear / linear
+// (analysisgnn/models/core/gnn.py:65, 75), PyG SAGEConv's lin_l / lin_r and HGT's kqv / out
+// projections (third party), project_dict (analysisgnn/models/analysis.py:429-443) -- and the two
+// GEMMs of their backward (grad-input, grad-weight).  See include/agnn.h (agnn_gemm).
+//
+// Precision modes
+//   AGNN_GEMM_TF32X3  fp32 parity mode.  tcgen05 has no fp32-input MMA, so every fp32 operand is
+//                     given as two TF32-exact matrices (hi = rna_tf32(x), lo = rna_tf32(x - hi),
+//                     agnn_split_tf32) and D = Ahi*Bhi + Ahi*Blo + Alo*Bhi accumulates in fp32 TMEM.
+//   AGNN_GEMM_TF32    one product (hi only): 1e-3 relative, for experiments.
+//   AGNN_GEMM_BF16    bf16 operands, fp32 accumulation, bf16 or fp32 output: the stated bf16 mode.
+//
+// Operand layouts (both handled by the UMMA descriptors, no transposition pass):
+//   K-major  : matrix stored [MN, K] row-major (activations as A, nn.Linear weights as B)
+//   MN-major : matrix stored [K, MN] row-major (weights as B in grad-input; both operands in grad-weight)
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
+// lane), warps 2-5 = epilogue (TMEM -> registers -> global, each warp its own 32 TMEM lanes).
+// The accumulator is double buffered in TMEM (2 x 128 columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.  Tile 128 x 128, K block = 128 bytes per row (32 tf32 / 64 bf16),
+// 128-byte swizzle everywhere.
+#include <cuda.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace agnn {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 128;
+constexpr int kRowBytes = 128;              // one swizzle row = the K (or MN) extent of a tile row
+constexpr int kTileBytes = kBlockM * kRowBytes;  // 16 KB per operand tile
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 2 * kBlockN;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct GemmParams {
+  CUtensorMap map_a[2];  // hi, lo
+  CUtensorMap map_b[2];
+  int M, N, K;
+  int k_blocks;          // K blocks in total
+  int k_blocks_per_split;
+  int chain_blocks;      // K blocks accumulated in TMEM before the sum is promoted to fp32 registers
+  int split_k;
+  int tiles_m, tiles_n;
+  void* out;             // [split_k][M][ldc] when split_k > 1 (workspace), else C
+  int64_t ldc;
+  int64_t split_stride;  // elements between split partials
+  const float* bias;
+  int flags;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
+// version 1 << 46 | layout SWIZZLE_128B (2) << 61
+// layout: 2 = SWIZZLE_128B (16-byte swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only
+// layout tcgen05 accepts for MN-major 32-bit operands -- TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor), D = fp32
+__host__ __device__ constexpr uint32_t instr_desc(bool bf16, bool a_mn, bool b_mn, int m, int n) {
+  return (1u << 4) | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <bool BF16, bool A_MN, bool B_MN, int TERMS>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int kElem = BF16 ? 2 : 4;
+  constexpr int kBlockK = kRowBytes / kElem;   // 32 tf32 / 64 bf16
+  constexpr int kUmmaK = 32 / kElem;           // 8 tf32 / 16 bf16
+  constexpr int kParts = TERMS == 3 ? 2 : 1;   // hi (+ lo)
+  constexpr int kStageBytes = 2 * kParts * kTileBytes;
+  constexpr int kStages = kSmemBudget / kStageBytes;
+  constexpr int kChunk = kRowBytes / kElem;    // MN elements per 128-byte row of an MN-major tile
+  constexpr int kChunks = kBlockM / kChunk;    // TMA boxes per MN-major tile
+  constexpr uint32_t kIdesc = instr_desc(BF16, A_MN, B_MN, kBlockM, kBlockN);
+  constexpr uint32_t kMnSbo = BF16 ? 1024 : 512;
+  constexpr uint64_t kMnLayout = BF16 ? 2 : 1;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* acc_full = empty + kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.tiles_m * p.tiles_n * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kParts; ++i) {
+      prefetch_tmap(&p.map_a[i]);
+      prefetch_tmap(&p.map_b[i]);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int split = tile / (p.tiles_m * p.tiles_n);
+        const int mn = tile - split * p.tiles_m * p.tiles_n;
+        const int m0 = (mn / p.tiles_n) * kBlockM, n0 = (mn % p.tiles_n) * kBlockN;
+        const int kb0 = split * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * kStageBytes;
+          mbar_expect_tx(&full[stage], kStageBytes);
+          const int k0 = kb * kBlockK;
+#pragma unroll
+          for (int part = 0; part < kParts; ++part) {
+            uint8_t* a_dst = st + part * kTileBytes;
+            uint8_t* b_dst = st + (kParts + part) * kTileBytes;
+            if constexpr (A_MN) {
+#pragma unroll
+              for (int c = 0; c < kChunks; ++c)
+                tma_load_2d(a_dst + c * (kBlockK * kRowBytes), &p.map_a[part], &full[stage], m0 + c * kChunk, k0);
+            } else {
+              tma_load_2d(a_dst, &p.map_a[part], &full[stage], k0, m0);
+            }
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int c = 0; c < kChunks; ++c)
+                tma_load_2d(b_dst + c * (kBlockK * kRowBytes), &p.map_b[part], &full[stage], n0 + c * kChunk, k0);
+            } else {
+              tma_load_2d(b_dst, &p.map_b[part], &full[stage], k0, n0);
+            }
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    // The tensor core adds into the fp32 TMEM accumulator with truncation (measured: -0.5 ulp per MMA,
+    // i.e. a bias that grows linearly with the chain).  A chain is therefore limited to
+    // p.chain_blocks K blocks; the epilogue warps sum the chains in registers with round-to-nearest.
+    int stage = 0;
+    uint32_t phase = 0;
+    int cc = 0;                                      // chains issued so far (TMEM buffer = cc & 1)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int split = tile / (p.tiles_m * p.tiles_n);
+      const int kb0 = split * p.k_blocks_per_split;
+      const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+      for (int c0 = kb0; c0 < kb1; c0 += p.chain_blocks, ++cc) {
+        const int c1 = min(c0 + p.chain_blocks, kb1);
+        const int buf = cc & 1;
+        mbar_wait(&acc_empty[buf], ((cc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * kBlockN;
+        for (int kb = c0; kb < c1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t st = smem_u32(smem + stage * kStageBytes);
+#pragma unroll
+            for (int term = 0; term < TERMS; ++term) {
+              // term 0: hi*hi, 1: hi*lo, 2: lo*hi
+              const uint32_t a_base = st + (term == 2 ? 1 : 0) * kTileBytes;
+              const uint32_t b_base = st + (kParts + (term == 1 ? 1 : 0)) * kTileBytes;
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // K-major: advance 32 bytes inside the 128-byte swizzle row; 8-row groups are 1024 B apart.
+                // MN-major: one K step = kUmmaK rows of 128 bytes; MN chunks are kBlockK rows apart;
+                // 32-bit operands use the 32-byte-atom swizzle (groups of 4 K rows, 512 B).
+                const uint64_t da = A_MN ? smem_desc(a_base + k * kUmmaK * kRowBytes, kBlockK * kRowBytes, kMnSbo, kMnLayout)
+                                         : smem_desc(a_base + k * 32, 16, 1024, 2);
+                const uint64_t db = B_MN ? smem_desc(b_base + k * kUmmaK * kRowBytes, kBlockK * kRowBytes, kMnSbo, kMnLayout)
+                                         : smem_desc(b_base + k * 32, 16, 1024, 2);
+                umma<BF16>(tmem_d, da, db, kIdesc, (kb > c0 || term > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty[stage]);              // frees the smem stage when these MMAs retire
+            if (kb == c1 - 1) umma_commit(&acc_full[buf]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) belong to this warp
+    int cc = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int split = tile / (p.tiles_m * p.tiles_n);
+      const int mn = tile - split * p.tiles_m * p.tiles_n;
+      const int m0 = (mn / p.tiles_n) * kBlockM, n0 = (mn % p.tiles_n) * kBlockN;
+      const int kb0 = split * p.k_blocks_per_split;
+      const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+      const int row = m0 + quarter * 32 + lane;
+      float acc[kBlockN];
+#pragma unroll
+      for (int j = 0; j < kBlockN; ++j) acc[j] = 0.f;
+      for (int c0 = kb0; c0 < kb1; c0 += p.chain_blocks, ++cc) {
+        const int buf = cc & 1;
+        mbar_wait(&acc_full[buf], (cc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * kBlockN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < kBlockN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      if (row < p.M) {
+        const bool direct = p.split_k == 1;
+#pragma unroll
+        for (int c = 0; c < kBlockN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;
+          float* v = acc + c * 32;
+          if (direct && p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+          const int64_t off = (int64_t)split * p.split_stride + (int64_t)row * p.ldc + col0;
+          if (!direct || !(p.flags & AGNN_GEMM_OUT_BF16)) {
+            float* o = static_cast<float*>(p.out) + off;
+            if (direct && (p.flags & AGNN_GEMM_ACCUMULATE)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] += o[j];
+            }
+            if (direct && (p.flags & AGNN_GEMM_RELU)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + off;
+            if (p.flags & AGNN_GEMM_ACCUMULATE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] += __bfloat162float(o[j]);
+            }
+            if (p.flags & AGNN_GEMM_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------- split / reduce helpers
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t rows, int cols4,
+                                                          int64_t ld_x, float* __restrict__ hi, float* __restrict__ lo,
+                                                          int64_t ld_o) {
+  const int64_t total = rows * cols4;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + c));
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    float h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[k]));
+      h[k] = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(in[k] - h[k]));
+      l[k] = __uint_as_float(lb);
+    }
+    *reinterpret_cast<float4*>(hi + r * ld_o + c) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo + r * ld_o + c) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// out[m, n] (+)= bias[n] + sum_s partial[s][m][n]   (fixed order => deterministic), optional ReLU
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int split_k,
+                                                             int64_t split_stride, int64_t M, int N, int64_t ld_p,
+                                                             void* __restrict__ out, int64_t ldc,
+                                                             const float* __restrict__ bias, int flags) {
+  const int64_t total = M * N;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t m = i / N;
+    const int n = (int)(i - m * N);
+    float acc = bias ? __ldg(bias + n) : 0.f;
+    for (int s = 0; s < split_k; ++s) acc += part[s * split_stride + m * ld_p + n];
+    if (flags & AGNN_GEMM_OUT_BF16) {
+      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + m * ldc + n;
+      if (flags & AGNN_GEMM_ACCUMULATE) acc += __bfloat162float(*o);
+      if (flags & AGNN_GEMM_RELU) acc = fmaxf(acc, 0.f);
+      *o = __float2bfloat16_rn(acc);
+    } else {
+      float* o = static_cast<float*>(out) + m * ldc + n;
+      if (flags & AGNN_GEMM_ACCUMULATE) acc += *o;
+      if (flags & AGNN_GEMM_RELU) acc = fmaxf(acc, 0.f);
+      *o = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D map over a row-major matrix [rows, cols] (cols contiguous), box = box_cols x box_rows, 128B swizzle
+int make_map(CUtensorMap* map, const void* ptr, bool bf16, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+             int box_rows, bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(AGNN_ERR_CUDA, "gemm: cuTensorMapEncodeTiled is not available from this driver");
+  const int eb = bf16 ? 2 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * eb};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   (mn_major && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(AGNN_ERR_CUDA, "gemm: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+  return AGNN_OK;
+}
+
+template <bool BF16, bool A_MN, bool B_MN, int TERMS>
+int launch(const GemmParams& p, int grid, cudaStream_t st) {
+  constexpr int kElem = BF16 ? 2 : 4;
+  constexpr int kParts = TERMS == 3 ? 2 : 1;
+  constexpr int kStageBytes = 2 * kParts * kTileBytes;
+  constexpr int kStages = kSmemBudget / kStageBytes;
+  constexpr int smem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  (void)kElem;
+  auto kern = gemm_kernel<BF16, A_MN, B_MN, TERMS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return check_launch("gemm: cudaFuncSetAttribute");
+    configured = true;
+  }
+  kern<<<grid, kThreads, smem, st>>>(p);
+  return check_launch("gemm");
+}
+
+template <bool BF16, int TERMS>
+int dispatch_layout(bool a_mn, bool b_mn, const GemmParams& p, int grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BF16, false, false, TERMS>(p, grid, st);
+  if (!a_mn && b_mn) return launch<BF16, false, true, TERMS>(p, grid, st);
+  if (a_mn && b_mn) return launch<BF16, true, true, TERMS>(p, grid, st);
+  return launch<BF16, true, false, TERMS>(p, grid, st);
+}
+
+}  // namespace
+}  // namespace agnn
+
+using namespace agnn;
+
+extern "C" int agnn_split_tf32(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* hi, float* lo,
+                               int64_t ld_out, agnn_stream_t stream) {
+  if (rows < 0 || cols < 0 || (cols % 4) || (ld_x % 4) || (ld_out % 4) || !aligned16(x) || !aligned16(hi) || !aligned16(lo))
+    return fail(AGNN_ERR_ARG, "split_tf32: needs 16-byte aligned rows and a column count multiple of 4");
+  if (rows == 0 || cols == 0) return AGNN_OK;
+  int64_t blocks = ceil_div(rows * (cols / 4), 256);
+  if (blocks > kNumSM * 16) blocks = kNumSM * 16;
+  split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, (int)(cols / 4), ld_x, hi, lo, ld_out);
+  return check_launch("split_tf32");
+}
+
+extern "C" int agnn_gemm_split_k(int precision, int64_t M, int64_t N, int64_t K) {
+  const int block_k = precision == AGNN_GEMM_BF16 ? 64 : 32;
+  const int64_t tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN);
+  const int64_t kb = ceil_div(K, block_k);
+  if (tiles >= kNumSM || kb < 16) return 1;
+  int64_t s = (2 * kNumSM) / tiles;          // aim at ~2 waves of work items
+  if (s > kb / 8) s = kb / 8;                // at least 8 K blocks per split
+  if (s > 32) s = 32;
+  return s < 1 ? 1 : (int)s;
+}
+
+extern "C" size_t agnn_gemm_workspace(int precision, int64_t M, int64_t N, int64_t K, int split_k) {
+  (void)precision; (void)K;
+  if (split_k <= 1) return 0;
+  return (size_t)split_k * (size_t)M * (size_t)((N + 3) / 4 * 4) * sizeof(float);
+}
+
+extern "C" int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, int64_t N, int64_t K, const void* a_hi,
+                         const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb, void* c,
+                         int64_t ldc, const float* bias, int flags, int split_k, void* workspace,
+                         size_t workspace_bytes, agnn_stream_t stream) {
+  if (precision != AGNN_GEMM_TF32X3 && precision != AGNN_GEMM_TF32 && precision != AGNN_GEMM_BF16)
+    return fail(AGNN_ERR_ARG, "gemm: unknown precision mode %d", precision);
+  if (M < 0 || N < 0 || K < 0 || !c || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31))
+    return fail(AGNN_ERR_ARG, "gemm: bad sizes");
+  if (M == 0 || N == 0) return AGNN_OK;
+  const bool bf16 = precision == AGNN_GEMM_BF16;
+  const int eb = bf16 ? 2 : 4, block_k = kRowBytes / eb, chunk = kRowBytes / eb;
+  const bool a_mn = a_layout == AGNN_LAYOUT_MN_MAJOR, b_mn = b_layout == AGNN_LAYOUT_MN_MAJOR;
+  if (!a_hi || !b_hi || (precision == AGNN_GEMM_TF32X3 && (!a_lo || !b_lo)))
+    return fail(AGNN_ERR_ARG, "gemm: null operand (TF32X3 needs the hi and lo parts of both operands)");
+  if ((lda * eb) % 16 || (ldb * eb) % 16 || !aligned16(a_hi) || !aligned16(b_hi) || (a_lo && !aligned16(a_lo)) ||
+      (b_lo && !aligned16(b_lo)))
+    return fail(AGNN_ERR_UNSUPPORTED, "gemm: operands must be 16-byte aligned with 16-byte multiple row strides");
+  if ((flags & AGNN_GEMM_OUT_BF16) && !bf16) return fail(AGNN_ERR_ARG, "gemm: bf16 output needs the bf16 mode");
+  if (split_k < 1) split_k = 1;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.k_blocks = (int)ceil_div(K, block_k);
+  if (p.k_blocks == 0) return fail(AGNN_ERR_ARG, "gemm: K == 0");
+  if (split_k > p.k_blocks) split_k = p.k_blocks;
+  p.k_blocks_per_split = (int)ceil_div(p.k_blocks, split_k);
+  split_k = (int)ceil_div(p.k_blocks, p.k_blocks_per_split);
+  p.split_k = split_k;
+  p.chain_blocks = precision == AGNN_GEMM_TF32X3 ? 2 : (1 << 30);
+  p.tiles_m = (int)ceil_div(M, kBlockM);
+  p.tiles_n = (int)ceil_div(N, kBlockN);
+  p.bias = bias;
+  p.flags = flags;
+  const int64_t ld_part = (N + 3) / 4 * 4;
+  if (split_k > 1) {
+    const size_t need = (size_t)split_k * (size_t)M * (size_t)ld_part * sizeof(float);
+    if (!workspace || workspace_bytes < need || !aligned16(workspace))
+      return fail(AGNN_ERR_WORKSPACE, "gemm: split-K workspace %zu < %zu bytes", workspace_bytes, need);
+    p.out = workspace; p.ldc = ld_part; p.split_stride = M * ld_part;
+  } else {
+    p.out = c; p.ldc = ldc; p.split_stride = 0;
+  }
+  int rc;
+  const void* a_parts[2] = {a_hi, a_lo};
+  const void* b_parts[2] = {b_hi, b_lo};
+  const int parts = precision == AGNN_GEMM_TF32X3 ? 2 : 1;
+  for (int i = 0; i < parts; ++i) {
+    // K-major: [MN, K] row-major, box = block_k x 128 rows.  MN-major: [K, MN] row-major, box = chunk x block_k rows.
+    rc = a_mn ? make_map(&p.map_a[i], a_parts[i], bf16, K, M, lda, chunk, block_k, true)
+              : make_map(&p.map_a[i], a_parts[i], bf16, M, K, lda, block_k, kBlockM, false);
+    if (rc) return rc;
+    rc = b_mn ? make_map(&p.map_b[i], b_parts[i], bf16, K, N, ldb, chunk, block_k, true)
+              : make_map(&p.map_b[i], b_parts[i], bf16, N, K, ldb, block_k, kBlockN, false);
+    if (rc) return rc;
+  }
+  const int64_t work = (int64_t)p.tiles_m * p.tiles_n * split_k;
+  const int grid = (int)(work < kNumSM ? work : kNumSM);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bf16) rc = dispatch_layout<true, 1>(a_mn, b_mn, p, grid, st);
+  else if (precision == AGNN_GEMM_TF32X3) rc = dispatch_layout<false, 3>(a_mn, b_mn, p, grid, st);
+  else rc = dispatch_layout<false, 1>(a_mn, b_mn, p, grid, st);
+  if (rc) return rc;
+  if (split_k > 1) {
+    int64_t blocks = ceil_div(M * N, 256);
+    if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(workspace), split_k,
+                                                            p.split_stride, M, (int)N, ld_part, c, ldc, bias, flags);
+    return check_launch("gemm split-K reduce");
+  }
+  return AGNN_OK;
+}

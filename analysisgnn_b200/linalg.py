@@ -1,20 +1,25 @@
 """Dense contractions used by the fused layers.
 
-The per-relation / per-node-type projections are the only GEMM-shaped work on
-the hot path.  ``backend()`` selects who runs them:
+The per-relation / per-node-type projections are the only GEMM-shaped work on the hot path.
+``backend()`` selects who runs them:
 
-* ``"cublas"``  -- ``torch.addmm`` / ``torch.mm`` (library GEMM, fp32 without TF32).
-* ``"tcgen05"`` -- this repo's sm_100a tcgen05/TMEM grouped GEMM (csrc/gemm.cu).
+* ``"tcgen05"`` -- this repo's sm_100a tensor-core GEMM (csrc/gemm.cu, ``agnn_gemm``): fp32 tensors
+  run in the 3xTF32 split mode (fp32 parity), bf16 tensors in the bf16 mode.
+* ``"cublas"``  -- ``torch.addmm`` / ``torch.mm`` (library GEMM, fp32 SIMT with TF32 off).  Also the
+  route for shapes ``agnn_gemm`` does not take (row strides that are not 16-byte multiples).
 
 There is no CPU path in either case: inputs must be CUDA tensors.
 """
 from __future__ import annotations
 
 import os
+from typing import Optional, Union
 
 import torch
 
-_BACKEND = os.environ.get("AGNN_GEMM", "cublas")
+from . import _lib
+
+_BACKEND = os.environ.get("AGNN_GEMM", "tcgen05")
 
 
 def backend() -> str:
@@ -30,34 +35,164 @@ def set_backend(name: str) -> None:
 
 def _need_cuda(t):
     if not t.is_cuda:
-        from ._lib import AgnnError
-        raise AgnnError("analysisgnn_b200 has no CPU path: tensors must live on a CUDA device")
+        raise _lib.AgnnError("analysisgnn_b200 has no CPU path: tensors must live on a CUDA device")
 
 
-def linear(x, weight, bias=None, relu: bool = False):
-    """``x @ weight.T + bias`` (optionally ReLU'd), ``weight`` [out, in]."""
+class Split:
+    """An fp32 matrix as TF32-exact ``hi`` + ``lo`` parts (``agnn_split_tf32``): the operand form of the
+    3xTF32 mode.  Keeping the pair lets one split feed several GEMMs (forward, grad-weight)."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def dtype(self):
+        return self.hi.dtype
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def merged(self):
+        return self.hi + self.lo
+
+
+Operand = Union[torch.Tensor, Split]
+
+
+def _rows_ok(t: torch.Tensor) -> bool:
+    return (t.dim() == 2 and t.stride(1) == 1 and (t.stride(0) * t.element_size()) % 16 == 0
+            and t.data_ptr() % 16 == 0 and t.shape[0] > 0 and t.shape[1] > 0)
+
+
+def split(x: torch.Tensor) -> Split:
+    """hi = rna_tf32(x), lo = rna_tf32(x - hi) (contiguous copies)."""
     _need_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 4 or x.stride(0) % 4 \
+            or x.data_ptr() % 16:
+        raise ValueError("split needs an fp32 matrix with unit column stride and 16-byte aligned rows")
+    rows, cols = x.shape
+    buf = torch.empty((2, rows, cols), dtype=torch.float32, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(_lib.lib().agnn_split_tf32(x.data_ptr(), rows, cols, x.stride(0), buf[0].data_ptr(), buf[1].data_ptr(),
+                                          cols, stream), "agnn_split_tf32")
+    _lib.count_launches(1)
+    return Split(buf[0], buf[1])
+
+
+def prepare(x: torch.Tensor) -> Operand:
+    """Pre-split an fp32 operand that several GEMMs will read (no-op for other backends / dtypes)."""
+    if (_BACKEND == "tcgen05" and isinstance(x, torch.Tensor) and x.dtype == torch.float32 and _rows_ok(x)
+            and x.shape[1] % 4 == 0):
+        return split(x)
+    return x
+
+
+def pack(x: Operand):
+    """(tensor, tensor-or-None) for ``save_for_backward``; ``unpack`` restores the operand."""
+    return (x.hi, x.lo) if isinstance(x, Split) else (x, None)
+
+
+def unpack(first, second) -> Operand:
+    return first if second is None else Split(first, second)
+
+
+def _as_operand(x: Operand):
+    """(hi, lo, precision) for agnn_gemm, or None when the tensor cannot take the tcgen05 route."""
+    if isinstance(x, Split):
+        return x.hi, x.lo, _lib.GEMM_TF32X3
+    if x.dtype == torch.bfloat16:
+        return (x, None, _lib.GEMM_BF16) if _rows_ok(x) else None
+    if x.dtype == torch.float32 and _rows_ok(x) and x.shape[1] % 4 == 0:
+        s = split(x)
+        return s.hi, s.lo, _lib.GEMM_TF32X3
+    return None
+
+
+def plain(x: Operand) -> torch.Tensor:
+    return x.merged() if isinstance(x, Split) else x
+
+
+_plain = plain
+
+
+def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, k: int, bias, flags: int,
+          out: Optional[torch.Tensor], split_k: Optional[int] = None) -> Optional[torch.Tensor]:
+    """agnn_gemm wrapper; returns None if the operands are not eligible (caller falls back)."""
+    if _BACKEND != "tcgen05":
+        return None
+    oa, ob = _as_operand(a), _as_operand(b)
+    if oa is None or ob is None or oa[2] != ob[2]:
+        return None
+    prec = oa[2]
+    dev = oa[0].device
+    out_dtype = torch.bfloat16 if prec == _lib.GEMM_BF16 else torch.float32
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype, device=dev)
+    elif out.dtype != out_dtype or out.stride(1) != 1:
+        return None
+    if prec == _lib.GEMM_BF16:
+        flags |= _lib.GEMM_OUT_BF16
     if bias is not None:
-        y = torch.addmm(bias, x, weight.t())
-    else:
-        y = torch.mm(x, weight.t())
+        bias = bias.float().contiguous()
+    lib = _lib.lib()
+    if split_k is None:
+        split_k = lib.agnn_gemm_split_k(prec, m, n, k)
+    ws_bytes = lib.agnn_gemm_workspace(prec, m, n, k, split_k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.agnn_gemm(prec, a_layout, b_layout, m, n, k, oa[0].data_ptr(),
+                             oa[1].data_ptr() if oa[1] is not None else None, oa[0].stride(0), ob[0].data_ptr(),
+                             ob[1].data_ptr() if ob[1] is not None else None, ob[0].stride(0), out.data_ptr(),
+                             out.stride(0), bias.data_ptr() if bias is not None else None, flags, split_k,
+                             ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gemm")
+    _lib.count_launches(2 if split_k > 1 else 1)
+    return out
+
+
+def linear(x: Operand, weight: Operand, bias=None, relu: bool = False):
+    """``x @ weight.T + bias`` (optionally ReLU'd), ``weight`` [out, in]."""
+    _need_cuda(x if isinstance(x, torch.Tensor) else x.hi)
+    m, k = x.shape
+    n = weight.shape[0]
+    y = _gemm(x, _lib.K_MAJOR, weight, _lib.K_MAJOR, m, n, k, bias, _lib.GEMM_RELU if relu else 0, None)
+    if y is not None:
+        return y
+    xp, wp = _plain(x), _plain(weight)
+    y = torch.addmm(bias, xp, wp.t()) if bias is not None else torch.mm(xp, wp.t())
     return y.relu_() if relu else y
 
 
-def mm(a, b, out=None, accumulate: bool = False):
-    """``a @ b``; with ``out`` and ``accumulate`` adds into ``out`` in place."""
-    _need_cuda(a)
+def mm(a: Operand, b: Operand, out=None, accumulate: bool = False):
+    """``a @ b`` with ``b`` stored [K, N]; with ``out`` and ``accumulate`` adds into ``out`` in place."""
+    _need_cuda(a if isinstance(a, torch.Tensor) else a.hi)
+    m, k = a.shape
+    n = b.shape[1]
+    y = _gemm(a, _lib.K_MAJOR, b, _lib.MN_MAJOR, m, n, k, None, _lib.GEMM_ACCUMULATE if accumulate else 0, out)
+    if y is not None:
+        return y
+    ap, bp = _plain(a), _plain(b)
     if out is None:
-        return torch.mm(a, b)
+        return torch.mm(ap, bp)
     if accumulate:
-        return out.addmm_(a, b)
-    return torch.mm(a, b, out=out)
+        return out.addmm_(ap, bp)
+    return torch.mm(ap, bp, out=out)
 
 
-def mm_tn(a, b):
-    """``a.T @ b`` (weight gradients)."""
-    _need_cuda(a)
-    return torch.mm(a.t(), b)
+def mm_tn(a: Operand, b: Operand):
+    """``a.T @ b`` (weight gradients): ``a`` [R, M], ``b`` [R, N], reduction over the R rows (split-K)."""
+    _need_cuda(a if isinstance(a, torch.Tensor) else a.hi)
+    r, m = a.shape
+    n = b.shape[1]
+    y = _gemm(a, _lib.MN_MAJOR, b, _lib.MN_MAJOR, m, n, r, None, 0, None)
+    if y is not None:
+        return y
+    return torch.mm(_plain(a).t(), _plain(b))
 
 
 def relu_backward(grad, out):

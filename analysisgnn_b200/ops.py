@@ -230,20 +230,23 @@ class _IntreeSageLayer(torch.autograd.Function):
         rels = [Rel(csr.fwd.rowptr[k], csr.fwd.col, h[:, k * f:(k + 1) * f], out_col=(k + 1) * f,
                     flags=_lib.REL_IDENTITY_IF_EMPTY, n_edges=csr.n_edges if k == 0 else 0) for k in range(r)]
         gather_reduce(rels, a, f, mean=True, concat=True, self_add=x, copy=x, copy_col=0)
+        a = linalg.prepare(a)                      # one TF32 split feeds the forward and the grad-weight GEMM
         z = linalg.linear(a, wc, bc)
-        ctx.save_for_backward(x, a, wn_cat, wc)
+        ctx.save_for_backward(x, *linalg.pack(a), wn_cat, wc)
         ctx.csr = csr
         ctx.has_bias = (bn_cat is not None, bc is not None)
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        x, a, wn_cat, wc = ctx.saved_tensors
+        x, a_first, a_second, wn_cat, wc = ctx.saved_tensors
+        a = linalg.unpack(a_first, a_second)
         csr, (n, f), r = ctx.csr, x.shape, ctx.csr.n_rel
-        dz = dz.contiguous()
+        dz_plain = dz.contiguous()
+        dz = linalg.prepare(dz_plain)
         da = linalg.mm(dz, wc)                                                   # [N, (R+1)F]
         dwc = linalg.mm_tn(dz, a) if ctx.needs_input_grad[3] else None
-        dbc = dz.sum(0) if ctx.has_bias[1] and ctx.needs_input_grad[4] else None
+        dbc = dz_plain.sum(0) if ctx.has_bias[1] and ctx.needs_input_grad[4] else None
         dh = torch.empty((n, r * f), dtype=x.dtype, device=x.device)
         rels_t = [Rel(csr.bwd.rowptr[k], csr.bwd.col, da[:, (k + 1) * f:(k + 2) * f], out_col=k * f,
                       nbr_deg_rowptr=csr.fwd.rowptr[k], flags=_lib.REL_IDENTITY_IF_EMPTY,
@@ -255,8 +258,11 @@ class _IntreeSageLayer(torch.autograd.Function):
             rels_s = [Rel(csr.fwd.rowptr[k], csr.fwd.col, da, out_col=(k + 1) * f,
                           flags=_lib.REL_IDENTITY_IF_EMPTY) for k in range(r)]
             rowscale_sum(rels_s, da, dx, f, base=da[:, :f])
-            linalg.mm(dh, wn_cat, out=dx, accumulate=True)
-        dwn = linalg.mm_tn(dh, x) if ctx.needs_input_grad[1] else None
+            dh_op = linalg.prepare(dh)
+            linalg.mm(dh_op, wn_cat, out=dx, accumulate=True)
+        else:
+            dh_op = dh
+        dwn = linalg.mm_tn(dh_op, x) if ctx.needs_input_grad[1] else None
         dbn = dh.sum(0) if ctx.has_bias[0] and ctx.needs_input_grad[2] else None
         return dx, dwn, dbn, dwc, dbc, None
 
@@ -294,9 +300,10 @@ class _HeteroSageLayer(torch.autograd.Function):
             rels = [Rel(csr.fwd[et].rowptr[0], csr.fwd[et].col, xs[et[0]], out_col=(k + 1) * f,
                         n_edges=csr.n_edges[et]) for k, et in enumerate(rel_list)]
             gather_reduce(rels, a, f, mean=True, concat=True, copy=x_t, copy_col=0)
+            a = linalg.prepare(a)
             o = linalg.linear(a, wcat, bias, relu=relu)
             outs.append(o)
-            saved += [a, wcat, o]
+            saved += [*linalg.pack(a), wcat, o]
         ctx.save_for_backward(*saved)
         ctx.set_materialize_grads(False)        # an unused destination type costs nothing in backward
         ctx.plan, ctx.csr, ctx.relu = plan, csr, relu
@@ -311,16 +318,18 @@ class _HeteroSageLayer(torch.autograd.Function):
         grads = [None] * (nt + 2 * len(plan.dst_types))
         da = {}
         for j, t in enumerate(plan.dst_types):
-            a, wcat, o = ctx.saved_tensors[3 * j:3 * j + 3]
+            a_first, a_second, wcat, o = ctx.saved_tensors[4 * j:4 * j + 4]
+            a = linalg.unpack(a_first, a_second)
             g = douts[j]
             if g is None:
                 continue
             g = linalg.relu_backward(g, o) if ctx.relu else g.contiguous()
+            if ctx.needs_input_grad[3 + nt + 2 * j + 1]:
+                grads[nt + 2 * j + 1] = g.sum(0)
+            g = linalg.prepare(g)
             da[t] = linalg.mm(g, wcat)
             if ctx.needs_input_grad[3 + nt + 2 * j]:
                 grads[nt + 2 * j] = linalg.mm_tn(g, a)
-            if ctx.needs_input_grad[3 + nt + 2 * j + 1]:
-                grads[nt + 2 * j + 1] = g.sum(0)
         for i, s in enumerate(plan.node_types):
             if not ctx.needs_input_grad[3 + i]:
                 continue

@@ -215,6 +215,45 @@ int agnn_adamw_clip_step(const agnn_param_chunk_t* chunks /* device */, int n_ch
                          float grad_scale, float max_norm, const float* partials, int n_partials, float* norm_out,
                          agnn_stream_t stream);
 
+/* ------------------------------------------------------------ dense projections
+ * Replaces the nn.Linear calls of the path and the GEMMs of their backward:
+ * SageConvScatter.neigh_linear / .linear (analysisgnn/models/core/gnn.py:65, 75), project_dict
+ * (analysisgnn/models/analysis.py:429-443, 575), PyG SAGEConv lin_l / lin_r and HGTConv kqv / out
+ * projections (third party).  tcgen05.mma, TMEM accumulators, TMA operands (gemm.cu).
+ *
+ *   C[M,N] (+)= A[M,K] * B[K,N] + bias[N]   (optional ReLU)
+ *
+ * Layouts: AGNN_LAYOUT_K_MAJOR  = the operand is stored [M or N, K] row-major (K contiguous);
+ *          AGNN_LAYOUT_MN_MAJOR = the operand is stored [K, M or N] row-major.
+ *   forward      Y = X W^T          A = X  K-major,  B = W [out,in]  K-major
+ *   grad input   dX = dY W          A = dY K-major,  B = W [out,in]  MN-major
+ *   grad weight  dW = dY^T X        A = dY MN-major, B = X           MN-major  (use split_k)
+ * Precision: AGNN_GEMM_TF32X3 = fp32 parity mode, operands given as TF32-exact hi / lo parts
+ * (agnn_split_tf32), three tensor-core products accumulated in fp32; AGNN_GEMM_TF32 = hi only;
+ * AGNN_GEMM_BF16 = bf16 operands (lo ignored), fp32 accumulation, fp32 or bf16 (AGNN_GEMM_OUT_BF16) output.
+ * Row strides (lda, ldb, in elements) must be multiples of 16 bytes.  split_k > 1 needs
+ * agnn_gemm_workspace() bytes; partial sums are reduced in a fixed order (deterministic).
+ */
+#define AGNN_GEMM_TF32X3 0
+#define AGNN_GEMM_TF32 1
+#define AGNN_GEMM_BF16 2
+#define AGNN_LAYOUT_K_MAJOR 0
+#define AGNN_LAYOUT_MN_MAJOR 1
+#define AGNN_GEMM_RELU 1
+#define AGNN_GEMM_ACCUMULATE 2
+#define AGNN_GEMM_OUT_BF16 4
+
+/* hi = rna_tf32(x), lo = rna_tf32(x - hi), both stored as fp32 bit patterns */
+int agnn_split_tf32(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* hi, float* lo, int64_t ld_out,
+                    agnn_stream_t stream);
+/* suggested split_k for a problem (host arithmetic) and the workspace a given split_k needs */
+int agnn_gemm_split_k(int precision, int64_t M, int64_t N, int64_t K);
+size_t agnn_gemm_workspace(int precision, int64_t M, int64_t N, int64_t K, int split_k);
+int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, int64_t N, int64_t K, const void* a_hi,
+              const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb, void* c, int64_t ldc,
+              const float* bias, int flags, int split_k, void* workspace, size_t workspace_bytes,
+              agnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
