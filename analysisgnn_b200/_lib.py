@@ -88,6 +88,16 @@ _PROTOTYPES = {
     "agnn_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                             C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
                             C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "agnn_row_blocks": (C.c_int, [C.c_int64]),
+    "agnn_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+    "agnn_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "agnn_l2norm_relu_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                                       C.c_int, C.c_float, C.c_void_p]),
+    "agnn_l2norm_relu_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "agnn_colsum_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
 }
 
 _lib = None

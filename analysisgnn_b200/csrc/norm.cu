@@ -1,0 +1,369 @@
+// Row-wise normalisation kernels of the hot path and the column sums of its backward.
+//
+//   agnn_layernorm_fwd / _bwd   nn.LayerNorm inside project_dict / project_enc / the sequence branch
+//                               (analysisgnn/models/analysis.py:429-443, 474-485; models/cadence.py:249-260)
+//   agnn_l2norm_relu_fwd / _bwd F.normalize(p=2) + ReLU between the MetricalGNN layers
+//                               (analysisgnn/models/core/hgnn.py:415, 421-422, 431)
+//   agnn_colsum_partials        bias gradients (column sums of dY)
+//
+// One warp per row (rows are 64..1024 wide), 128-bit loads, fp32 statistics, two-pass variance as in
+// ATen.  Column reductions (d gamma, d beta, bias gradients) are accumulated per lane over a
+// grid-stride loop, combined across the warps of a block through shared memory and written as
+// per-block partials that the caller sums -- fixed order, no atomics.
+// Roofline: HBM.  fwd 2 rows moved per row (x in, y out); bwd 3 (dy, x in; dx out).
+#include <initializer_list>
+
+#include "common.cuh"
+
+namespace agnn {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxV = 8;  // float4 vectors per lane: up to 1024 columns
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+template <int V>
+__device__ __forceinline__ void load_row(const float* p, int cols, int lane, float (&v)[V][4]) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < cols) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p + c));
+      v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+    } else {
+      v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
+    }
+  }
+}
+
+template <int V>
+__device__ __forceinline__ void store_row(float* p, int cols, int lane, const float (&v)[V][4]) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < cols) *reinterpret_cast<float4*>(p + c) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kThreads) layernorm_fwd_kernel(const float* __restrict__ x, int64_t ld_x,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float* __restrict__ y,
+                                                                  int64_t ld_y, float* __restrict__ mean,
+                                                                  float* __restrict__ rstd, int64_t rows, int cols,
+                                                                  float eps) {
+  const int lane = threadIdx.x & 31;
+  float g[V][4], b[V][4];
+  load_row<V>(gamma, cols, lane, g);
+  load_row<V>(beta, cols, lane, b);
+  const float inv = 1.f / (float)cols;
+  for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarps) {
+    float v[V][4];
+    load_row<V>(x + row * ld_x, cols, lane, v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    const float mu = warp_sum(s) * inv;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = ((i * 32 + lane) * 4 + e < cols) ? v[i][e] - mu : 0.f;
+        q = fmaf(d, d, q);
+      }
+    const float rs = rsqrtf(warp_sum(q) * inv + eps);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[i][e] = fmaf((v[i][e] - mu) * rs, g[i][e], b[i][e]);
+    store_row<V>(y + row * ld_y, cols, lane, v);
+    if (lane == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
+  }
+}
+
+// dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)); partials: d gamma = sum dy*xhat, d beta = sum dy
+template <int V>
+__global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy,
+                                                                  const float* __restrict__ x, int64_t ld_x,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd, float* __restrict__ dx,
+                                                                  int64_t ld_dx, float* __restrict__ dgamma_part,
+                                                                  float* __restrict__ dbeta_part, int64_t rows,
+                                                                  int cols) {
+  __shared__ float red[kWarps][32 * 4 + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float g[V][4], ag[V][4], ab[V][4];
+  load_row<V>(gamma, cols, lane, g);
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ag[i][e] = ab[i][e] = 0.f;
+  const float inv = 1.f / (float)cols;
+  for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < rows; row += (int64_t)gridDim.x * kWarps) {
+    float d[V][4], v[V][4];
+    load_row<V>(dy + row * ld_dy, cols, lane, d);
+    load_row<V>(x + row * ld_x, cols, lane, v);
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool on = (i * 32 + lane) * 4 + e < cols;
+        const float xh = on ? (v[i][e] - mu) * rs : 0.f;
+        const float dg = d[i][e] * g[i][e];
+        s1 += dg;
+        s2 = fmaf(dg, xh, s2);
+        ag[i][e] = fmaf(d[i][e], xh, ag[i][e]);
+        ab[i][e] += d[i][e];
+        v[i][e] = xh;
+        d[i][e] = dg;
+      }
+    s1 = warp_sum(s1) * inv;
+    s2 = warp_sum(s2) * inv;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[i][e] = rs * (d[i][e] - s1 - v[i][e] * s2);
+    store_row<V>(dx + row * ld_dx, cols, lane, d);
+  }
+  // combine the warps of the block, one 128-column slab at a time
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[warp][lane * 4 + e] = pass == 0 ? ag[i][e] : ab[i][e];
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        const int c = i * 128 + threadIdx.x;
+        if (c < cols) {
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) t += red[w][threadIdx.x];
+          (pass == 0 ? dgamma_part : dbeta_part)[(int64_t)blockIdx.x * cols + c] = t;
+        }
+      }
+    }
+  }
+}
+
+// y = relu?(x) / max(||relu?(x)||, eps) (relu_first)   or   relu(x / max(||x||, eps))
+template <int V>
+__global__ void __launch_bounds__(kThreads) l2norm_relu_fwd_kernel(const float* __restrict__ x, int64_t ld_x,
+                                                                    float* __restrict__ y, int64_t ld_y,
+                                                                    float* __restrict__ inv_norm, int64_t rows, int cols,
+                                                                    int relu_first, float eps) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarps) {
+    float v[V][4];
+    load_row<V>(x + row * ld_x, cols, lane, v);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (relu_first) v[i][e] = fmaxf(v[i][e], 0.f);
+        q = fmaf(v[i][e], v[i][e], q);
+      }
+    const float inv = 1.f / fmaxf(sqrtf(warp_sum(q)), eps);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[i][e] = relu_first ? v[i][e] * inv : fmaxf(v[i][e] * inv, 0.f);
+    store_row<V>(y + row * ld_y, cols, lane, v);
+    if (lane == 0) inv_norm[row] = inv;
+  }
+}
+
+// with u = relu?(x), n = u * inv:  d u = inv * (g' - n * (g' . n)),  g' = dy masked by the outer relu;
+// relu_first additionally masks d u by x > 0.  y (= saved output) provides n and both masks.
+template <int V>
+__global__ void __launch_bounds__(kThreads) l2norm_relu_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy,
+                                                                    const float* __restrict__ x, int64_t ld_x,
+                                                                    const float* __restrict__ inv_norm,
+                                                                    float* __restrict__ dx, int64_t ld_dx, int64_t rows,
+                                                                    int cols, int relu_first) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarps) {
+    float d[V][4], v[V][4];
+    load_row<V>(dy + row * ld_dy, cols, lane, d);
+    load_row<V>(x + row * ld_x, cols, lane, v);
+    const float inv = __ldg(inv_norm + row);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (relu_first) v[i][e] = fmaxf(v[i][e], 0.f);
+        const float n = v[i][e] * inv;                     // normalised value before the outer relu
+        if (!relu_first && n <= 0.f) d[i][e] = 0.f;        // relu(normalize(x)) backward mask
+        dot = fmaf(d[i][e], n, dot);
+        v[i][e] = n;
+      }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float t = inv * (d[i][e] - v[i][e] * dot);
+        if (relu_first && v[i][e] <= 0.f) t = 0.f;         // normalize(relu(x)): x <= 0 gets no gradient
+        d[i][e] = t;
+      }
+    store_row<V>(dx + row * ld_dx, cols, lane, d);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restrict__ x, int64_t ld_x,
+                                                           float* __restrict__ part, int64_t rows, int cols) {
+  __shared__ float red[kWarps][32 * 4 + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[V][4];
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < rows; row += (int64_t)gridDim.x * kWarps) {
+    float v[V][4];
+    load_row<V>(x + row * ld_x, cols, lane, v);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][e] += v[i][e];
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[warp][lane * 4 + e] = acc[i][e];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int c = i * 128 + threadIdx.x;
+      if (c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += red[w][threadIdx.x];
+        part[(int64_t)blockIdx.x * cols + c] = t;
+      }
+    }
+  }
+}
+
+int row_blocks(int64_t rows) {
+  int64_t b = ceil_div(rows, kWarps * 4);   // >= 4 rows per warp so the column partials amortise
+  if (b > kNumSM * 4) b = kNumSM * 4;
+  return b < 1 ? 1 : (int)b;
+}
+
+int check(const char* what, int64_t rows, int cols, std::initializer_list<const void*> ptrs,
+          std::initializer_list<int64_t> lds) {
+  if (rows < 0 || cols < 4 || (cols % 4) || cols > kMaxV * 128)
+    return fail(AGNN_ERR_UNSUPPORTED, "%s: columns must be a multiple of 4 in [4, %d] (got %d)", what, kMaxV * 128, cols);
+  for (const void* p : ptrs)
+    if (!p || !aligned16(p)) return fail(AGNN_ERR_ARG, "%s: null or unaligned pointer", what);
+  for (int64_t ld : lds)
+    if (ld % 4) return fail(AGNN_ERR_ARG, "%s: row strides must be multiples of 4 elements", what);
+  return AGNN_OK;
+}
+
+#define AGNN_DISPATCH_V(cols, CALL)                 \
+  do {                                              \
+    const int v_ = (int)ceil_div((cols), 128);      \
+    if (v_ <= 1) { CALL(1); }                       \
+    else if (v_ <= 2) { CALL(2); }                  \
+    else if (v_ <= 4) { CALL(4); }                  \
+    else { CALL(8); }                               \
+  } while (0)
+
+}  // namespace
+}  // namespace agnn
+
+using namespace agnn;
+
+extern "C" int agnn_row_blocks(int64_t rows) { return row_blocks(rows); }
+
+extern "C" int agnn_layernorm_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, float* y,
+                                  int64_t ld_y, float* mean, float* rstd, int64_t rows, int cols, float eps,
+                                  agnn_stream_t stream) {
+  int rc = check("layernorm_fwd", rows, cols, {x, gamma, beta, y}, {ld_x, ld_y});
+  if (rc) return rc;
+  if (!mean || !rstd) return fail(AGNN_ERR_ARG, "layernorm_fwd: null statistics pointer");
+  if (rows == 0) return AGNN_OK;
+  int64_t blocks = ceil_div(rows, kWarps);
+  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(V) layernorm_fwd_kernel<V><<<(unsigned)blocks, kThreads, 0, st>>>(x, ld_x, gamma, beta, y, ld_y, mean, rstd, rows, cols, eps)
+  AGNN_DISPATCH_V(cols, CALL);
+#undef CALL
+  return check_launch("layernorm_fwd");
+}
+
+extern "C" int agnn_layernorm_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* gamma,
+                                  const float* mean, const float* rstd, float* dx, int64_t ld_dx, float* dgamma_part,
+                                  float* dbeta_part, int64_t rows, int cols, agnn_stream_t stream) {
+  int rc = check("layernorm_bwd", rows, cols, {dy, x, gamma, dx}, {ld_dy, ld_x, ld_dx});
+  if (rc) return rc;
+  if (!mean || !rstd || !dgamma_part || !dbeta_part) return fail(AGNN_ERR_ARG, "layernorm_bwd: null pointer");
+  const int blocks = row_blocks(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(V) layernorm_bwd_kernel<V><<<blocks, kThreads, 0, st>>>(dy, ld_dy, x, ld_x, gamma, mean, rstd, dx, ld_dx, dgamma_part, dbeta_part, rows, cols)
+  AGNN_DISPATCH_V(cols, CALL);
+#undef CALL
+  return check_launch("layernorm_bwd");
+}
+
+extern "C" int agnn_l2norm_relu_fwd(const float* x, int64_t ld_x, float* y, int64_t ld_y, float* inv_norm, int64_t rows,
+                                    int cols, int relu_first, float eps, agnn_stream_t stream) {
+  int rc = check("l2norm_relu_fwd", rows, cols, {x, y}, {ld_x, ld_y});
+  if (rc) return rc;
+  if (!inv_norm) return fail(AGNN_ERR_ARG, "l2norm_relu_fwd: null inv_norm");
+  if (rows == 0) return AGNN_OK;
+  int64_t blocks = ceil_div(rows, kWarps);
+  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(V) l2norm_relu_fwd_kernel<V><<<(unsigned)blocks, kThreads, 0, st>>>(x, ld_x, y, ld_y, inv_norm, rows, cols, relu_first, eps)
+  AGNN_DISPATCH_V(cols, CALL);
+#undef CALL
+  return check_launch("l2norm_relu_fwd");
+}
+
+extern "C" int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* inv_norm,
+                                    float* dx, int64_t ld_dx, int64_t rows, int cols, int relu_first,
+                                    agnn_stream_t stream) {
+  int rc = check("l2norm_relu_bwd", rows, cols, {dy, x, dx}, {ld_dy, ld_x, ld_dx});
+  if (rc) return rc;
+  if (!inv_norm) return fail(AGNN_ERR_ARG, "l2norm_relu_bwd: null inv_norm");
+  if (rows == 0) return AGNN_OK;
+  int64_t blocks = ceil_div(rows, kWarps);
+  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(V) l2norm_relu_bwd_kernel<V><<<(unsigned)blocks, kThreads, 0, st>>>(dy, ld_dy, x, ld_x, inv_norm, dx, ld_dx, rows, cols, relu_first)
+  AGNN_DISPATCH_V(cols, CALL);
+#undef CALL
+  return check_launch("l2norm_relu_bwd");
+}
+
+extern "C" int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, int64_t rows, int cols,
+                                    agnn_stream_t stream) {
+  int rc = check("colsum_partials", rows, cols, {x, partials}, {ld_x});
+  if (rc) return rc;
+  const int blocks = row_blocks(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(V) colsum_kernel<V><<<blocks, kThreads, 0, st>>>(x, ld_x, partials, rows, cols)
+  AGNN_DISPATCH_V(cols, CALL);
+#undef CALL
+  return check_launch("colsum_partials");
+}

@@ -22,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import graph, ops
+from .layers import LayerNorm, Linear
 
 EdgeType = Tuple[str, str, str]
 
@@ -39,8 +40,8 @@ class SAGEConv(nn.Module):
     def __init__(self, in_channels, out_channels):
         super().__init__()
         self.in_channels, self.out_channels = in_channels, out_channels
-        self.lin_l = nn.Linear(in_channels, out_channels, bias=True)
-        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+        self.lin_l = Linear(in_channels, out_channels, bias=True)
+        self.lin_r = Linear(in_channels, out_channels, bias=False)
 
     def reset_parameters(self):
         self.lin_l.reset_parameters()
@@ -204,8 +205,8 @@ class HGTConv(nn.Module):
         self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
         self.joint_softmax = joint_softmax
         d = out_channels // heads
-        self.kqv_lin = nn.ModuleDict({t: nn.Linear(in_channels, 3 * out_channels) for t in self.node_types})
-        self.out_lin = nn.ModuleDict({t: nn.Linear(out_channels, out_channels) for t in self.node_types})
+        self.kqv_lin = nn.ModuleDict({t: Linear(in_channels, 3 * out_channels) for t in self.node_types})
+        self.out_lin = nn.ModuleDict({t: Linear(out_channels, out_channels) for t in self.node_types})
         n_rel = len(self.edge_types)
         self.k_rel = nn.Parameter(torch.empty(heads * n_rel, d, d))   # index = head * n_rel + relation
         self.v_rel = nn.Parameter(torch.empty(heads * n_rel, d, d))
@@ -295,10 +296,10 @@ class SequenceBranch(nn.Module):
         super().__init__()
         self.rnn = nn.GRU(input_size=in_channels, hidden_size=hidden_channels // 2, num_layers=2,
                           batch_first=True, bidirectional=True, dropout=dropout)
-        self.rnn_norm = nn.LayerNorm(hidden_channels)
+        self.rnn_norm = LayerNorm(hidden_channels)
         self.rnn_mlp = nn.Sequential(
-            nn.Linear(hidden_channels, hidden_channels), nn.ReLU(), nn.LayerNorm(hidden_channels),
-            nn.Dropout(dropout), nn.Linear(hidden_channels, hidden_channels))
+            Linear(hidden_channels, hidden_channels), nn.ReLU(), LayerNorm(hidden_channels),
+            nn.Dropout(dropout), Linear(hidden_channels, hidden_channels))
 
     def forward(self, x, batch):
         layout = graph.batch_layout(batch)
@@ -314,7 +315,7 @@ class JumpingKnowledge(nn.Module):
     def __init__(self, n_hidden, n_layers):
         super().__init__()
         self.lstm = nn.LSTM(n_hidden, (n_layers * n_hidden) // 2, bidirectional=True, batch_first=True)
-        self.att = nn.Linear(2 * ((n_layers * n_hidden) // 2), 1)
+        self.att = Linear(2 * ((n_layers * n_hidden) // 2), 1)
 
     def forward(self, xs):
         x = torch.stack(xs, dim=1)
@@ -362,7 +363,7 @@ class HybridGNN(_HybridBase):
         self.use_jk = use_jk
         self.gnn = HeteroSAGEStack(metadata[1], input_channels, hidden_channels, num_layers)
         self.seq = SequenceBranch(input_channels, hidden_channels, dropout)
-        self.cat_proj = nn.Linear(2 * hidden_channels, hidden_channels)
+        self.cat_proj = Linear(2 * hidden_channels, hidden_channels)
         if use_jk:
             self.jk = JumpingKnowledge(hidden_channels, num_layers)
 
@@ -376,7 +377,7 @@ class HybridHGT(_HybridBase):
         self.use_jk = use_jk
         self.gnn = HeteroHGTStack(metadata, input_channels, hidden_channels, num_layers, heads, dropout, joint_softmax)
         self.seq = SequenceBranch(input_channels, hidden_channels, dropout)
-        self.cat_proj = nn.Linear(2 * hidden_channels, hidden_channels)
+        self.cat_proj = Linear(2 * hidden_channels, hidden_channels)
         if use_jk:
             self.jk = JumpingKnowledge(hidden_channels, num_layers)
 
@@ -392,8 +393,8 @@ class MetricalGNN(nn.Module):
         super().__init__()
         self.gnn = HeteroSAGEStack(metadata[1], input_channels, hidden_channels, num_layers)
         self.mlp = nn.Sequential(
-            nn.Linear(hidden_channels, hidden_channels), nn.ReLU(), nn.LayerNorm(hidden_channels),
-            nn.Dropout(dropout), nn.Linear(hidden_channels, output_channels))
+            Linear(hidden_channels, hidden_channels), nn.ReLU(), LayerNorm(hidden_channels),
+            nn.Dropout(dropout), Linear(hidden_channels, output_channels))
 
     def forward(self, x_dict, edge_index_dict, neighbor_mask_node=None, neighbor_mask_edge=None, **kwargs):
         out = self.gnn(x_dict, edge_index_dict, neighbor_mask_node, neighbor_mask_edge, None, ("note",))

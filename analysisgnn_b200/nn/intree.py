@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import graph, ops
+from .layers import LayerNorm, Linear
 
 
 def _xavier_relu_(linear: nn.Linear):
@@ -34,11 +35,11 @@ class SageConvScatter(nn.Module):
 
     def __init__(self, in_features, out_features, bias=True, in_edge_features=None):
         super().__init__()
-        self.neigh_linear = nn.Linear(in_features, in_features, bias=bias)
-        self.linear = nn.Linear(in_features * 2, out_features, bias=bias)
+        self.neigh_linear = Linear(in_features, in_features, bias=bias)
+        self.linear = Linear(in_features * 2, out_features, bias=bias)
         self.in_edge_features = in_edge_features
         if in_edge_features is not None:
-            self.edge_linear = nn.Linear(in_edge_features, in_features, bias=bias)
+            self.edge_linear = Linear(in_edge_features, in_features, bias=bias)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -160,8 +161,8 @@ class MetricalConvLayer(nn.Module):
         self.activation = nn.Identity() if activation is None else activation
         self.dropout = nn.Dropout(dropout)
         self.normalize = nn.BatchNorm1d(out_dim)
-        self.neigh = nn.Linear(in_dim, in_dim, bias=bias)
-        self.conv_out = nn.Linear(4 * in_dim, out_dim, bias=bias)
+        self.neigh = Linear(in_dim, in_dim, bias=bias)
+        self.conv_out = Linear(4 * in_dim, out_dim, bias=bias)
         self.seq = nn.GRU(in_dim, in_dim, batch_first=True, bias=bias, bidirectional=True)
 
     def reset_parameters(self):
@@ -200,8 +201,8 @@ class MetricalGNN(nn.Module):
         self.use_metrical = metrical
         self.use_knowledge = False
         self.convs = nn.ModuleList()
-        self.emb_beats = nn.Linear(input_features, hidden_features)
-        self.emb_measures = nn.Linear(input_features, hidden_features)
+        self.emb_beats = Linear(input_features, hidden_features)
+        self.emb_measures = Linear(input_features, hidden_features)
         self.beat_convs = nn.ModuleList()
         self.measure_convs = nn.ModuleList()
         self.project_metrical = nn.ModuleList()
@@ -218,7 +219,7 @@ class MetricalGNN(nn.Module):
     def _add_metrical(self, h_in, h_out, dropout):
         self.beat_convs.append(MetricalConvLayer(h_in, h_out, activation=F.relu, dropout=dropout))
         self.measure_convs.append(MetricalConvLayer(h_in, h_out, activation=F.relu, dropout=dropout))
-        self.project_metrical.append(nn.Linear(h_out * 3, h_out))
+        self.project_metrical.append(Linear(h_out * 3, h_out))
 
     def reset_parameters(self):
         for group in (self.convs, self.beat_convs, self.measure_convs, self.project_metrical):

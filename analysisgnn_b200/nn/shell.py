@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import graph, ops
+from .layers import LayerNorm, Linear
 from .hetero import HybridGNN, HybridHGT, MetricalGNN
 
 ONSET = ("note", "onset", "note")
@@ -52,8 +53,8 @@ class AnalysisEncoder(nn.Module):
         self.hidden_channels = hidden_channels
 
         def mlp(cin):
-            return nn.Sequential(nn.Linear(cin, hidden_channels), nn.ReLU(), nn.LayerNorm(hidden_channels),
-                                 nn.Dropout(dropout), nn.Linear(hidden_channels, hidden_channels))
+            return nn.Sequential(Linear(cin, hidden_channels), nn.ReLU(), LayerNorm(hidden_channels),
+                                 nn.Dropout(dropout), Linear(hidden_channels, hidden_channels))
 
         self.project_dict = nn.ModuleDict({k: mlp(in_channels + 128 if k == "note" else in_channels)
                                            for k in metadata[0]})
@@ -73,12 +74,12 @@ class AnalysisEncoder(nn.Module):
             raise ValueError(f"unknown encoder_type {encoder_type!r}")
         self.encoder_type = encoder_type
         self.project_enc = nn.Sequential(
-            nn.LayerNorm(2 * hidden_channels), nn.Linear(2 * hidden_channels, hidden_channels), nn.ReLU(),
-            nn.LayerNorm(hidden_channels), nn.Dropout(dropout), nn.Linear(hidden_channels, out_channels), nn.ReLU(),
-            nn.LayerNorm(out_channels), nn.Dropout(dropout), nn.Linear(out_channels, out_channels))
+            LayerNorm(2 * hidden_channels), Linear(2 * hidden_channels, hidden_channels), nn.ReLU(),
+            LayerNorm(hidden_channels), nn.Dropout(dropout), Linear(hidden_channels, out_channels), nn.ReLU(),
+            LayerNorm(out_channels), nn.Dropout(dropout), Linear(out_channels, out_channels))
         self.clf_dict = nn.ModuleDict({
-            task: nn.Sequential(nn.Linear(out_channels, out_channels // 2), nn.ReLU(),
-                                nn.LayerNorm(out_channels // 2), nn.Linear(out_channels // 2, n_cls))
+            task: nn.Sequential(Linear(out_channels, out_channels // 2), nn.ReLU(),
+                                LayerNorm(out_channels // 2), Linear(out_channels // 2, n_cls))
             for task, n_cls in task_dict.items()})
 
     def encode(self, pitch_spelling, key_signature, x_dict, edge_index_dict, batch_dict, batch_size,

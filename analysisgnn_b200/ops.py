@@ -454,9 +454,145 @@ def hgt_attention(q, ks, vs, pscale, fwd_csrs, bwd_csrs, heads: int, joint_softm
 # row-wise L2 normalisation + ReLU (hgnn.py:415, 421-422) and stream helper
 # ------------------------------------------------------------------------------
 
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of a 2-D fp32 matrix (bias gradients): per-block partials + a fixed-order final sum."""
+    if (x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 4 or x.shape[1] > 1024
+            or x.stride(0) % 4 or x.data_ptr() % 16 or x.shape[0] == 0):
+        return x.sum(0)
+    lib = _lib.lib()
+    rows, cols = x.shape
+    part = torch.empty((lib.agnn_row_blocks(rows), cols), dtype=torch.float32, device=x.device)
+    _lib.check(lib.agnn_colsum_partials(x.data_ptr(), x.stride(0), part.data_ptr(), rows, cols, _stream(x)),
+               "agnn_colsum_partials")
+    _lib.count_launches(1)
+    return part.sum(0)
+
+
+class _Linear(torch.autograd.Function):
+    """``y = x W^T + b`` on agnn_gemm (forward, grad-input, grad-weight) with one TF32 split per operand."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xs = linalg.prepare(x)
+        y = linalg.linear(xs, weight, bias)
+        ctx.save_for_backward(*linalg.pack(xs), weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x_first, x_second, weight = ctx.saved_tensors
+        xs = linalg.unpack(x_first, x_second)
+        g = g.contiguous()
+        db = colsum(g) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        gs = linalg.prepare(g)
+        dx = linalg.mm(gs, weight) if ctx.needs_input_grad[0] else None
+        dw = linalg.mm_tn(gs, xs) if ctx.needs_input_grad[1] else None
+        return dx, dw, db
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``nn.Linear`` arithmetic for any leading shape.  Inputs whose feature count is not a multiple
+    of 4 (e.g. the 25 + 128 note features, analysisgnn/models/analysis.py:574) are zero-padded so the
+    TMA row-stride rule (16 bytes) holds."""
+    if not x.is_cuda:
+        raise _lib.AgnnError("analysisgnn_b200 has no CPU path: tensors must live on a CUDA device")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    k = x2.shape[1]
+    if x2.dtype == torch.float32 and k % 4 and linalg.backend() == "tcgen05":
+        pad = 4 - k % 4
+        x2 = torch.nn.functional.pad(x2, (0, pad))
+        weight = torch.nn.functional.pad(weight, (0, pad))
+    elif not x2.is_contiguous():
+        x2 = x2.contiguous()
+    y = _Linear.apply(x2, weight, bias)
+    return y.reshape(*lead, weight.shape[0])
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        rows, cols = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().agnn_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                                 y.data_ptr(), y.stride(0), mean.data_ptr(), rstd.data_ptr(), rows,
+                                                 cols, eps, _stream(x)), "agnn_layernorm_fwd")
+        _lib.count_launches(1)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        rows, cols = x.shape
+        dy = dy.contiguous()
+        lib = _lib.lib()
+        dx = torch.empty_like(x)
+        blocks = lib.agnn_row_blocks(rows)
+        part = torch.empty((2, blocks, cols), dtype=torch.float32, device=x.device)
+        _lib.check(lib.agnn_layernorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gamma.data_ptr(),
+                                          mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), dx.stride(0),
+                                          part[0].data_ptr(), part[1].data_ptr(), rows, cols, _stream(x)),
+                   "agnn_layernorm_bwd")
+        _lib.count_launches(1)
+        sums = part.sum(1)
+        return dx, sums[0], sums[1], None
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """``nn.LayerNorm`` over the last dimension (fp32, width a multiple of 4 up to 1024; other cases go
+    to the library kernel)."""
+    if not x.is_cuda:
+        raise _lib.AgnnError("analysisgnn_b200 has no CPU path: tensors must live on a CUDA device")
+    cols = x.shape[-1]
+    if x.dtype != torch.float32 or cols % 4 or cols > 1024 or gamma is None or beta is None or x.numel() == 0:
+        return torch.nn.functional.layer_norm(x, (cols,), gamma, beta, eps)
+    x2 = x.reshape(-1, cols)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    return _LayerNorm.apply(x2, gamma.contiguous(), beta.contiguous(), eps).reshape(x.shape)
+
+
+class _L2NormRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, relu_first):
+        rows, cols = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().agnn_l2norm_relu_fwd(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0),
+                                                   inv.data_ptr(), rows, cols, int(relu_first), 1e-12, _stream(x)),
+                   "agnn_l2norm_relu_fwd")
+        _lib.count_launches(1)
+        ctx.save_for_backward(x, inv)
+        ctx.relu_first = relu_first
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, inv = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        rows, cols = x.shape
+        _lib.check(_lib.lib().agnn_l2norm_relu_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0),
+                                                   inv.data_ptr(), dx.data_ptr(), dx.stride(0), rows, cols,
+                                                   int(ctx.relu_first), _stream(x)), "agnn_l2norm_relu_bwd")
+        _lib.count_launches(1)
+        return dx, None
+
+
 def l2norm_relu(h, relu_first: bool):
     """``relu_first``: ``normalize(relu(h))`` (hgnn.py:415, 431); else ``relu(normalize(h))``
     (hgnn.py:421-422).  ``normalize`` = ``h / max(||h||_2, 1e-12)`` per row."""
+    if (h.is_cuda and h.dtype == torch.float32 and h.dim() == 2 and h.shape[1] % 4 == 0 and h.shape[1] <= 1024
+            and h.shape[0] > 0):
+        return _L2NormRelu.apply(h.contiguous(), bool(relu_first))
     if relu_first:
         return torch.nn.functional.normalize(torch.relu(h), p=2.0, dim=-1)
     return torch.relu(torch.nn.functional.normalize(h, p=2.0, dim=-1))

@@ -254,6 +254,27 @@ int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, int64_t N, i
               const float* bias, int flags, int split_k, void* workspace, size_t workspace_bytes,
               agnn_stream_t stream);
 
+/* ------------------------------------------------------------ row-wise normalisation
+ * agnn_layernorm_*: nn.LayerNorm of project_dict / project_enc (analysisgnn/models/analysis.py:429-443,
+ * 474-485) and of the sequence branch (analysisgnn/models/cadence.py:249-260).  fp32, warp per row,
+ * cols a multiple of 4 up to 1024.  Backward writes dx and per-block partial sums of d gamma / d beta,
+ * [agnn_row_blocks(rows)][cols] each, which the caller adds up (fixed order).
+ * agnn_l2norm_relu_*: F.normalize(p=2, eps) combined with the ReLU around it in MetricalGNN
+ * (analysisgnn/models/core/hgnn.py:415, 421-422, 431): relu_first = normalize(relu(x)), else relu(normalize(x)).
+ * agnn_colsum_partials: bias gradients, partials[agnn_row_blocks(rows)][cols].
+ */
+int agnn_row_blocks(int64_t rows);
+int agnn_layernorm_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, float* y, int64_t ld_y,
+                       float* mean, float* rstd, int64_t rows, int cols, float eps, agnn_stream_t stream);
+int agnn_layernorm_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* gamma,
+                       const float* mean, const float* rstd, float* dx, int64_t ld_dx, float* dgamma_partials,
+                       float* dbeta_partials, int64_t rows, int cols, agnn_stream_t stream);
+int agnn_l2norm_relu_fwd(const float* x, int64_t ld_x, float* y, int64_t ld_y, float* inv_norm, int64_t rows, int cols,
+                         int relu_first, float eps, agnn_stream_t stream);
+int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* inv_norm, float* dx,
+                         int64_t ld_dx, int64_t rows, int cols, int relu_first, agnn_stream_t stream);
+int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, int64_t rows, int cols, agnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
