@@ -77,10 +77,10 @@ _PROTOTYPES = {
                                         C.c_void_p]),
     "agnn_optim_chunk_elems": (C.c_int, []),
     "agnn_sumsq_blocks": (C.c_int, [C.c_int64]),
-    "agnn_sumsq_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "agnn_sumsq_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnn_adamw_clip_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
-                                       C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p,
-                                       C.c_int, C.c_void_p, C.c_void_p]),
+                                       C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_float, C.c_float,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "agnn_split_tf32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p]),
     "agnn_gemm_split_k": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64]),

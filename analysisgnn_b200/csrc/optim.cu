@@ -36,7 +36,9 @@ __device__ __forceinline__ float block_sum(float v, float* smem) {
 }
 
 __global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ g, int64_t n4,
-                                                          float* __restrict__ partials) {
+                                                          float* __restrict__ partials, int* __restrict__ step_counter) {
+  // the step counter lives on the device so that a CUDA-graph replay advances it (bias correction)
+  if (step_counter && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1;
   __shared__ float smem[kThreads / 32];
   float acc = 0.f;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -59,6 +61,7 @@ struct AdamParams {
   const float* partials;
   int n_partials;
   float lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm, bias1, bias2_sqrt;
+  const int* step_dev;               // optional: step number on the device (overrides bias1 / bias2_sqrt)
   float* norm_out;
 };
 
@@ -80,7 +83,13 @@ __global__ void __launch_bounds__(kThreads) adamw_kernel(const __grid_constant__
   const agnn_param_chunk_t c = p.chunks[blockIdx.x];
   float* const w = static_cast<float*>(c.param);
   const float decay = 1.f - p.lr * p.weight_decay;
-  const float step_size = p.lr / p.bias1;
+  float bias1 = p.bias1, bias2_sqrt = p.bias2_sqrt;
+  if (p.step_dev) {
+    const float t = (float)__ldg(p.step_dev);
+    bias1 = 1.f - powf(p.beta1, t);
+    bias2_sqrt = sqrtf(1.f - powf(p.beta2, t));
+  }
+  const float step_size = p.lr / bias1;
   for (int i = threadIdx.x * 4; i < c.count; i += kThreads * 4) {
     const int64_t a = c.arena_off + i;
     float gv[4], mv[4], vv[4], wv[4];
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(kThreads) adamw_kernel(const __grid_constant__
       wv[k] *= decay;                                       // param.mul_(1 - lr * wd)
       mv[k] = mv[k] + (g - mv[k]) * (1.f - p.beta1);        // exp_avg.lerp_(grad, 1 - beta1)
       vv[k] = vv[k] * p.beta2 + (1.f - p.beta2) * g * g;    // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-      const float denom = sqrtf(vv[k]) / p.bias2_sqrt + p.eps;
+      const float denom = sqrtf(vv[k]) / bias2_sqrt + p.eps;
       wv[k] -= step_size * (mv[k] / denom);                 // param.addcdiv_(exp_avg, denom, -step_size)
     }
     if (rem >= 4) {
@@ -142,18 +151,19 @@ extern "C" int agnn_sumsq_blocks(int64_t n) {
   return b < 1 ? 1 : (int)b;
 }
 
-extern "C" int agnn_sumsq_partials(const float* grad, int64_t n, float* partials, agnn_stream_t stream) {
+extern "C" int agnn_sumsq_partials(const float* grad, int64_t n, float* partials, int* step_counter,
+                                   agnn_stream_t stream) {
   if (n < 0 || (n % 4) || !partials || (n > 0 && !grad) || !aligned16(grad))
     return fail(AGNN_ERR_ARG, "sumsq_partials: the arena must be 16-byte aligned and a multiple of 4 elements");
-  sumsq_kernel<<<agnn_sumsq_blocks(n), kThreads, 0, (cudaStream_t)stream>>>(grad, n / 4, partials);
+  sumsq_kernel<<<agnn_sumsq_blocks(n), kThreads, 0, (cudaStream_t)stream>>>(grad, n / 4, partials, step_counter);
   return check_launch("sumsq_partials");
 }
 
 extern "C" int agnn_adamw_clip_step(const agnn_param_chunk_t* chunks, int n_chunks, const float* grad, float* m,
                                     float* v, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                    int step, float grad_scale, float max_norm, const float* partials,
-                                    int n_partials, float* norm_out, agnn_stream_t stream) {
-  if (n_chunks < 0 || step < 1 || !chunks || !grad || !m || !v || !partials || n_partials < 1)
+                                    int step, const int* step_dev, float grad_scale, float max_norm,
+                                    const float* partials, int n_partials, float* norm_out, agnn_stream_t stream) {
+  if (n_chunks < 0 || (step < 1 && !step_dev) || !chunks || !grad || !m || !v || !partials || n_partials < 1)
     return fail(AGNN_ERR_ARG, "adamw_clip_step: bad arguments (n_chunks=%d step=%d)", n_chunks, step);
   if (!aligned16(grad) || !aligned16(m) || !aligned16(v))
     return fail(AGNN_ERR_ARG, "adamw_clip_step: arenas must be 16-byte aligned");
@@ -162,8 +172,9 @@ extern "C" int agnn_adamw_clip_step(const agnn_param_chunk_t* chunks, int n_chun
   p.chunks = chunks; p.grad = grad; p.m = m; p.v = v; p.partials = partials; p.n_partials = n_partials;
   p.lr = lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.weight_decay = weight_decay;
   p.grad_scale = grad_scale; p.max_norm = max_norm;
-  p.bias1 = 1.f - powf(beta1, (float)step);
-  p.bias2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  p.bias1 = 1.f - powf(beta1, (float)(step < 1 ? 1 : step));
+  p.bias2_sqrt = sqrtf(1.f - powf(beta2, (float)(step < 1 ? 1 : step)));
+  p.step_dev = step_dev;
   p.norm_out = norm_out;
   adamw_kernel<<<n_chunks, kThreads, 0, (cudaStream_t)stream>>>(p);
   return check_launch("adamw_clip_step");

@@ -154,21 +154,26 @@ class HeteroCSR:
 # ---------------------------------------------------------------------- cache
 
 class _StructureCache:
-    """Small LRU keyed on tensor identity + version.  Entries hold the index
-    tensors, so an address can never be recycled under a live key."""
+    """Small LRU keyed on tensor identity; an entry is stale when a tensor's version counter moved
+    (in-place update = new batch).  Entries hold the index tensors, so an address can never be
+    recycled under a live key.  ``frozen`` (set while a CUDA graph is captured) accepts entries whose
+    tensors were overwritten in place: a captured step promises static layouts."""
 
     def __init__(self, capacity=8):
         self.capacity = capacity
+        self.frozen = False
         self.entries: "OrderedDict[tuple, tuple]" = OrderedDict()
 
     def get(self, tensors: Sequence[torch.Tensor], extra: tuple, make):
-        key = tuple((id(t), t._version, tuple(t.shape)) for t in tensors) + extra
+        key = tuple((id(t), tuple(t.shape)) for t in tensors) + extra
+        versions = tuple(t._version for t in tensors)
         hit = self.entries.get(key)
-        if hit is not None:
+        if hit is not None and (self.frozen or hit[1] == versions):
             self.entries.move_to_end(key)
-            return hit[1]
+            return hit[2]
         value = make()
-        self.entries[key] = (list(tensors), value)
+        self.entries[key] = (list(tensors), versions, value)
+        self.entries.move_to_end(key)
         while len(self.entries) > self.capacity:
             self.entries.popitem(last=False)
         return value
@@ -177,11 +182,22 @@ class _StructureCache:
         self.entries.clear()
 
 
-_cache = _StructureCache(capacity=64)
+_cache = _StructureCache(capacity=64)        # device structures (CSR, derived index tensors)
+_host_cache = _StructureCache(capacity=64)   # layouts that needed a device -> host read
 
 
-def clear_cache():
+def freeze_host_layouts(frozen: bool) -> None:
+    """While True, sequence layouts cached from earlier (eager) steps are reused even if their index
+    tensors were overwritten in place -- required inside a CUDA-graph capture, where the device ->
+    host read a fresh layout needs is illegal."""
+    _host_cache.frozen = bool(frozen)
+
+
+def clear_cache(host_layouts: bool = False):
+    """Forget the per-batch device structures (and, on request, the host-side sequence layouts)."""
     _cache.clear()
+    if host_layouts:
+        _host_cache.clear()
 
 
 def typed_csr(edge_index, edge_type, n_rows, n_rel, reduce_row=0, n_cols=None) -> TypedCSR:
@@ -256,7 +272,7 @@ class SequenceLayout:
 def sequence_layout(lengths: Optional[torch.Tensor], n: int) -> SequenceLayout:
     if lengths is None:
         return SequenceLayout.from_lengths(None, n)
-    return _cache.get([lengths], ("seq", int(n)), lambda: SequenceLayout.from_lengths(lengths, n))
+    return _host_cache.get([lengths], ("seq", int(n)), lambda: SequenceLayout.from_lengths(lengths, n))
 
 
 def batch_layout(batch: torch.Tensor) -> SequenceLayout:
@@ -266,7 +282,7 @@ def batch_layout(batch: torch.Tensor) -> SequenceLayout:
         counts = torch.bincount(batch).cpu().tolist() if batch.numel() else []
         return SequenceLayout([c for c in counts], batch.device)
     base = batch._base if batch._base is not None else batch
-    return _cache.get([base], ("batch", int(batch.numel()), int(batch.storage_offset())), make)
+    return _host_cache.get([base], ("batch", int(batch.numel()), int(batch.storage_offset())), make)
 
 
 def hetero_csr_trimmed(edge_index_dict, n_edges: Dict[Tuple[str, str, str], int], num_nodes: Dict[str, int]) -> "HeteroCSR":

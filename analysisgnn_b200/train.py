@@ -103,6 +103,7 @@ class DataParallelTrainer:
             self.arena = GradArena(model.parameters(), 4096)
             self.n_partials, self.partials = 0, None
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=first.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=first.device)   # device-side step number
 
     def zero_grad(self):
         self.arena.zero_()
@@ -118,14 +119,53 @@ class DataParallelTrainer:
             raise _lib.AgnnError("DataParallelTrainer.step needs CUDA parameters: there is no CPU optimizer path")
         a.check_views()
         self.allreduce()
-        self.step_count += 1
+        self.step_count += 1                    # host mirror; the kernels use the device counter
         lib = _lib.lib()
         stream = torch.cuda.current_stream(a.grad.device).cuda_stream
-        _lib.check(lib.agnn_sumsq_partials(a.grad.data_ptr(), a.numel, self.partials.data_ptr(), stream),
-                   "agnn_sumsq_partials")
+        _lib.check(lib.agnn_sumsq_partials(a.grad.data_ptr(), a.numel, self.partials.data_ptr(),
+                                           self.step_dev.data_ptr(), stream), "agnn_sumsq_partials")
         _lib.check(lib.agnn_adamw_clip_step(
             a.table.data_ptr(), a.n_chunks, a.grad.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(),
-            self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
+            self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 0, self.step_dev.data_ptr(),
             1.0 / self.world_size, self.max_norm if self.max_norm else 0.0, self.partials.data_ptr(),
             self.n_partials, self.grad_norm.data_ptr(), stream), "agnn_adamw_clip_step")
         _lib.count_launches(2)
+
+
+class GraphedStep:
+    """A whole training step (CSR build, forward, backward, allreduce, clip + AdamW) captured once in
+    a CUDA graph and replayed: the step is ~2 500 short launches, and launching them one by one from
+    Python costs more than the GPU needs to run them.  Everything the step enqueues is capturable
+    (libagnn never allocates or synchronises; the optimizer's step number lives on the device).
+
+    ``fn(inputs) -> loss`` must read its data from the tensors in ``inputs`` (static buffers: write the
+    next batch into them with ``copy_`` -- shapes are fixed by the capture, so batches are padded to
+    the captured capacity with relation id -1 edges and ``ignore_index`` labels) and must not read
+    device data on the host.  Host-side layouts that need such a read (sequence lengths) are taken
+    from the warm-up steps, which run eagerly before the capture."""
+
+    def __init__(self, fn, inputs, warmup: int = 3):
+        self.fn, self.inputs = fn, inputs
+        dev = torch.cuda.current_device()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import graph as _graph
+        before = _lib.launches()
+        self.graph = torch.cuda.CUDAGraph()
+        _graph.freeze_host_layouts(True)
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = fn(inputs)
+        finally:
+            _graph.freeze_host_layouts(False)
+        self.launches_per_replay = _lib.launches() - before
+
+    def __call__(self):
+        self.graph.replay()
+        _lib.count_launches(self.launches_per_replay)
+        return self.loss

@@ -210,7 +210,7 @@ def run_ours(args):
     import torch.distributed as dist
     from analysisgnn_b200 import _lib, graph, ops
     from analysisgnn_b200 import nn as ann
-    from analysisgnn_b200.train import DataParallelTrainer
+    from analysisgnn_b200.train import DataParallelTrainer, GraphedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,9 +256,14 @@ def run_ours(args):
         trainer.step()
         return loss
 
+    not_pinned = [k for k, v in host.items() if v.numel() and not v.is_pinned()]
+    if not_pinned or not loss_host.is_pinned():
+        raise SystemExit(f"bench.py: host buffers are not pinned: {not_pinned}")
+
     def e2e_step():
         for k, v in host.items():
-            staging[k].copy_(v, non_blocking=True)
+            if v.numel():
+                staging[k].copy_(v, non_blocking=True)
         loss = step(staging)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
@@ -273,13 +278,17 @@ def run_ours(args):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         t0 = time.perf_counter()
+        enqueue = 0.0
         for a, z in ev:
             flush.fill_(1.0)                       # L2 flush, outside the event pair
             a.record()
+            t1 = time.perf_counter()
             fn()
+            enqueue += time.perf_counter() - t1
             z.record()
         barrier()
         wall = time.perf_counter() - t0
+        timed.enqueue_ms = 1e3 * enqueue / steps   # host time spent launching one step
         ms = sum(a.elapsed_time(z) for a, z in ev)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -287,26 +296,45 @@ def run_ours(args):
             ms = float(t.item())
         return ms, wall
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step(resident)
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
 
+    use_graph = not args.no_graph
+    if use_graph:
+        # the step is launch-bound from Python (host enqueue ~ step time in eager mode): capture it once
+        run_resident = GraphedStep(lambda t: step(t), resident, warmup=1)
+        run_e2e = GraphedStep(lambda _: e2e_step(), None, warmup=1)
+    else:
+        run_resident, run_e2e = (lambda: step(resident)), e2e_step
+    for _ in range(warm):
+        run_resident()
+    torch.cuda.synchronize()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.timer = ops.KernelTimer()
     launches0 = _lib.launches()
     torch.cuda.profiler.start()                    # ncu --profile-from-start off captures the timed region only
-    ms, wall = timed(lambda: step(resident), args.steps)
+    ms, wall = timed(run_resident, args.steps)
     torch.cuda.profiler.stop()
     launches = _lib.launches() - launches0
-    ktimes = ops.timer.summary()
-    ops.timer = None
-    e2e_ms, _ = timed(e2e_step, args.steps)
+    enqueue_ms = timed.enqueue_ms
+    for _ in range(2):
+        run_e2e()
+    e2e_ms, _ = timed(run_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss_host.item())
+    # per-kernel timing of the aggregation kernels: CUDA events cannot be read inside a graph, so the same
+    # K steps run once more eagerly with an event pair around every agnn_gather_reduce launch
+    ops.timer = ops.KernelTimer()
+    eager_ms, _ = timed(lambda: step(resident), args.steps)
+    eager_enqueue_ms = timed.enqueue_ms
+    ktimes = ops.timer.summary()
+    ops.timer = None
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -324,13 +352,17 @@ def run_ours(args):
             "edges_per_s": world * n_edges * CFG["layers"] * args.steps / (ms * 1e-3),
             "e2e": {"value": world * n_nodes * args.steps / (e2e_ms * 1e-3), "unit": "nodes/s",
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": enqueue_ms,
+            "execution": ("one CUDA graph per step (CSR build + fwd + bwd + clip + AdamW captured once, replayed)"
+                          if use_graph else "eager launches"),
+            "eager": {"ms_per_step": eager_ms / args.steps, "host_enqueue_ms_per_step": eager_enqueue_ms},
             "roofline": {"bound": "hbm", "kernel": "agnn gather_reduce_kernel (all launches of the timed region)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "launches": g["launches"],
                          "algorithmic_bytes_per_step": g["bytes"] / max(args.steps, 1),
                          "kernel_ms_per_step": g["ms"] / max(args.steps, 1),
-                         "share_of_step": g["ms"] / ms if ms else None,
+                         "share_of_step": g["ms"] / eager_ms if eager_ms else None,
+                         "timed_in": "eager re-run of the same K steps (events around each launch)",
                          "largest_launch": {"bytes": g["max_bytes"], "ms": g["max_ms"], "achieved": big,
                                             "frac": big / peak}},
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -349,6 +381,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--skip-cpu", action="store_true", help="leave out the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -206,14 +206,16 @@ typedef struct agnn_param_chunk {
 
 int agnn_optim_chunk_elems(void);
 int agnn_sumsq_blocks(int64_t n);
-/* partials[agnn_sumsq_blocks(n)] = per-block sums of grad^2 (n multiple of 4, arena 16-byte aligned) */
-int agnn_sumsq_partials(const float* grad, int64_t n, float* partials, agnn_stream_t stream);
-/* chunks: DEVICE array [n_chunks]; step counts from 1; max_norm <= 0 disables clipping;
- * norm_out (optional, device) receives the norm of the averaged gradient. */
+/* partials[agnn_sumsq_blocks(n)] = per-block sums of grad^2 (n multiple of 4, arena 16-byte aligned);
+ * step_counter (optional, device int) is incremented by one -- the device-side step number that makes
+ * the optimizer step replayable inside a CUDA graph. */
+int agnn_sumsq_partials(const float* grad, int64_t n, float* partials, int* step_counter, agnn_stream_t stream);
+/* chunks: DEVICE array [n_chunks]; the step number (from 1) is *step_dev if step_dev is given, else `step`;
+ * max_norm <= 0 disables clipping; norm_out (optional, device) receives the norm of the averaged gradient. */
 int agnn_adamw_clip_step(const agnn_param_chunk_t* chunks /* device */, int n_chunks, const float* grad, float* m,
                          float* v, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                         float grad_scale, float max_norm, const float* partials, int n_partials, float* norm_out,
-                         agnn_stream_t stream);
+                         const int* step_dev, float grad_scale, float max_norm, const float* partials, int n_partials,
+                         float* norm_out, agnn_stream_t stream);
 
 /* ------------------------------------------------------------ dense projections
  * Replaces the nn.Linear calls of the path and the GEMMs of their backward:
