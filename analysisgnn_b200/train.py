@@ -133,10 +133,11 @@ class DataParallelTrainer:
 
 
 class GraphedStep:
-    """A whole training step (CSR build, forward, backward, allreduce, clip + AdamW) captured once in
-    a CUDA graph and replayed: the step is ~2 500 short launches, and launching them one by one from
-    Python costs more than the GPU needs to run them.  Everything the step enqueues is capturable
-    (libagnn never allocates or synchronises; the optimizer's step number lives on the device).
+    """The device work of a training step (CSR build, forward, backward; optionally the optimizer)
+    captured once in a CUDA graph and replayed: the step is ~2 500 short launches, and launching them
+    one by one from Python costs more than the GPU needs to run them.  Everything libagnn enqueues is
+    capturable (it never allocates or synchronises; the optimizer's step number lives on the device).
+    With several ranks keep ``trainer.step()`` (the NCCL allreduce) outside the captured function.
 
     ``fn(inputs) -> loss`` must read its data from the tensors in ``inputs`` (static buffers: write the
     next batch into them with ``copy_`` -- shapes are fixed by the capture, so batches are padded to
