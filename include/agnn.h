@@ -277,6 +277,21 @@ int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t
                          int64_t ld_dx, int64_t rows, int cols, int relu_first, agnn_stream_t stream);
 int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, int64_t rows, int cols, agnn_stream_t stream);
 
+/* ------------------------------------------------------------ score-graph construction
+ * Replaces hetero_graph_from_note_array (analysisgnn/utils/hgraph.py:214-300; rest_array=None,
+ * pot_edge_dist=0) for a batch of scores: onset (0) / consecutive (1) / during (2) / rest (3) edges in
+ * the reference's emission order, node ids offset by the score's first note.  Notes of a score must be
+ * sorted by onset.  score_ptr [S+1]: first note of every score; key_base [S+1]: prefix sum of
+ * (max_end - first_onset + 1) per score (host arithmetic on the note arrays), key_slots = key_base[S].
+ * edges: int64 [3][capacity] (src, dst, type rows); *n_edges receives the number of edges the scores
+ * have -- if it exceeds `capacity` the surplus was not written and the call must be repeated.
+ */
+size_t agnn_score_graph_workspace(int32_t n_notes, int32_t n_scores, int64_t key_slots);
+int agnn_score_graph_build(int32_t n_scores, const int32_t* score_ptr, const int32_t* key_base, const int32_t* onset,
+                           const int32_t* duration, int32_t n_notes, int64_t key_slots, int64_t* edges,
+                           int64_t capacity, int32_t* n_edges, void* workspace, size_t workspace_bytes,
+                           agnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
