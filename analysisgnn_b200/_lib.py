@@ -102,6 +102,16 @@ _PROTOTYPES = {
     "agnn_score_graph_build": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t,
                                          C.c_void_p]),
+    "agnn_window_workspace": (C.c_size_t, [C.c_int64]),
+    "agnn_window_subgraph": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 10 + [C.c_int64, C.c_void_p, C.c_void_p,
+                                                                                    C.c_size_t, C.c_void_p]),
+    "agnn_sample_init": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agnn_sample_hop_workspace": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "agnn_sample_hop_count": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "agnn_sample_hop_draw": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_int32] +
+                             [C.c_void_p] * 8 + [C.c_size_t, C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,236 @@
+"""Subgraph sampling and batch collation on the GPU (agnn_window_subgraph, agnn_sample_hop_*).
+
+Replaces the CPU loaders of the reference (analysisgnn/data/datamodules/analysis.py:270-323: graphmuse
+``MuseNeighborLoader`` -> PyG ``NeighborSampler`` -> pyg-lib, in DataLoader worker processes) for
+corpora that live on the device: a ``Corpus`` holds every score's notes and typed edges (global node
+ids, as ``scoregraph.score_graph_edges`` builds them); a batch is ``batch_size`` scores, one contiguous
+``subgraph_size``-note window each (analysisgnn/data/datasets/chord.py:217-229), optionally grown by
+``num_neighbors`` sampled hops, collated with PyG's target-first node order and per-hop counts.
+
+Random choices are functions of ``(seed, ...)`` only (splitmix64 counter RNG, oracle/graph.py), so a
+batch is reproducible bit for bit on any device count.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, graph
+
+MASK64 = (1 << 64) - 1
+
+
+def _mix64(x: int) -> int:
+    x &= MASK64
+    x ^= x >> 30
+    x = (x * 0xBF58476D1CE4E5B9) & MASK64
+    x ^= x >> 27
+    x = (x * 0x94D049BB133111EB) & MASK64
+    x ^= x >> 31
+    return x
+
+
+def rng_u64(seed: int, a: int, b: int, c: int, d: int) -> int:
+    """The counter RNG shared with the kernels: one 64-bit draw keyed on (seed, a, b, c, d)."""
+    h = _mix64(seed + 0x9E3779B97F4A7C15)
+    for v in (a, b, c, d):
+        h = _mix64(h ^ ((v + 0x9E3779B97F4A7C15) & MASK64))
+    return h
+
+
+def window_start(seed: int, graph_id: int, n_nodes: int, size: int) -> int:
+    """``start = randint(0, n - size)`` (chord.py:219) with the counter RNG."""
+    if n_nodes <= size:
+        return 0
+    return rng_u64(seed, 0x57494E, graph_id, 0, 0) % (n_nodes - size + 1)
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def window_subgraphs(src, dst, etype, node_ptr: Sequence[int], edge_ptr: Sequence[int], graph_ids: Sequence[int],
+                     starts: Sequence[int], size: int):
+    """Node-induced subgraphs of contiguous windows of several scores, collated.
+
+    ``src/dst/etype``: corpus COO with global node ids (device int64); ``node_ptr/edge_ptr`` host lists.
+    Returns ``(edges int64 [3, E], edge_id int64 [E], node_index int64 [N_batch], slot_ptr list)``:
+    ``node_index`` = corpus node of every batch node, ``slot_ptr`` = first batch node of every slot."""
+    dev = src.device
+    if dev.type != "cuda":
+        raise _lib.AgnnError("analysisgnn_b200 has no CPU path: the sampler needs CUDA tensors")
+    lib = _lib.lib()
+    cand_ptr, edge_lo, node_lo, win, out_off = [0], [], [], [], []
+    off = 0
+    for g, st in zip(graph_ids, starts):
+        n = node_ptr[g + 1] - node_ptr[g]
+        w = min(size, n - st)
+        edge_lo.append(edge_ptr[g])
+        cand_ptr.append(cand_ptr[-1] + edge_ptr[g + 1] - edge_ptr[g])
+        node_lo.append(node_ptr[g] + st)
+        win.append(w)
+        out_off.append(off)
+        off += w
+    n_cand = cand_ptr[-1]
+    t64 = lambda a: torch.tensor(a, dtype=torch.int64, device=dev)
+    d_cand, d_elo, d_nlo, d_off = t64(cand_ptr), t64(edge_lo), t64(node_lo), t64(out_off)
+    d_win = torch.tensor(win, dtype=torch.int32, device=dev)
+    ws_bytes = lib.agnn_window_workspace(n_cand)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    capacity = max(n_cand, 1)
+    edges = torch.empty((3, capacity), dtype=torch.int64, device=dev)
+    eid = torch.empty(capacity, dtype=torch.int64, device=dev)
+    _lib.check(lib.agnn_window_subgraph(len(win), n_cand, d_cand.data_ptr(), d_elo.data_ptr(), d_nlo.data_ptr(),
+                                        d_win.data_ptr(), d_off.data_ptr(), src.data_ptr(), dst.data_ptr(),
+                                        etype.data_ptr() if etype is not None else None, edges.data_ptr(),
+                                        eid.data_ptr(), capacity, n_out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                        _stream(dev)), "agnn_window_subgraph")
+    _lib.count_launches(5)
+    total = int(n_out.item())
+    node_index = torch.cat([torch.arange(lo, lo + w, device=dev) for lo, w in zip(node_lo, win)]) if win else \
+        torch.zeros(0, dtype=torch.int64, device=dev)
+    return edges[:, :total], eid[:total], node_index, out_off + [off]
+
+
+def neighbor_sample(csr: graph.CSR, n_nodes: int, seeds: torch.Tensor, fanouts: Sequence[int], seed: int):
+    """k-hop sampling on a destination-keyed relation-major CSR (``graph.build_csr`` of (dst, src, etype)).
+
+    Returns a dict like oracle/graph.py::neighbor_sample: ``node`` (global ids, discovery order),
+    per relation ``src`` / ``dst`` (batch-local) and ``edge`` (CSR slot), ``num_sampled_nodes``,
+    ``num_sampled_edges[r]`` per hop."""
+    dev = csr.rowptr.device
+    lib = _lib.lib()
+    r = csr.n_rel
+    rowptr = csr.rowptr.reshape(-1)
+    seeds32 = seeds.to(torch.int32).contiguous()
+    n_seeds = int(seeds32.numel())
+    local = torch.empty(max(n_nodes, 1), dtype=torch.int32, device=dev)
+    first_pos = torch.empty(max(n_nodes, 1), dtype=torch.int32, device=dev)
+    nodes = torch.empty(max(n_nodes, 1), dtype=torch.int32, device=dev)
+    st = _stream(dev)
+    _lib.check(lib.agnn_sample_init(n_nodes, seeds32.data_ptr(), n_seeds, local.data_ptr(), nodes.data_ptr(), st),
+               "agnn_sample_init")
+    n_known, lo = n_seeds, 0
+    nodes_per_hop = [n_seeds]
+    per_rel = {k: [[] for _ in range(r)] for k in ("src", "dst", "edge")}
+    edges_per_hop = [[] for _ in range(r)]
+    base = int(rowptr[0].item()) if rowptr.numel() else 0      # slots are relative to the segment's col block
+    for hop, k in enumerate(fanouts):
+        f = n_known - lo
+        counts = torch.empty(r * f + 1, dtype=torch.int32, device=dev)
+        ws_bytes = lib.agnn_sample_hop_workspace(r, f)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.agnn_sample_hop_count(r, n_nodes, rowptr.data_ptr(), nodes.data_ptr(), lo, f, int(k),
+                                             counts.data_ptr(), ws.data_ptr(), ws_bytes, st), "agnn_sample_hop_count")
+        offs = counts.cpu()
+        n_cand = int(offs[-1])
+        cand = torch.empty((4, max(n_cand, 1)), dtype=torch.int32, device=dev)
+        flag = torch.empty(n_cand + 1, dtype=torch.int32, device=dev)
+        ws2 = torch.empty(max((n_cand // 4096 + 2) * 4, 16), dtype=torch.uint8, device=dev)
+        _lib.check(lib.agnn_sample_hop_draw(r, n_nodes, rowptr.data_ptr(), csr.col.data_ptr(), nodes.data_ptr(), lo, f,
+                                            n_known, hop, int(k), int(seed) & MASK64, counts.data_ptr(), n_cand,
+                                            cand[0].data_ptr(), cand[1].data_ptr(), cand[2].data_ptr(),
+                                            cand[3].data_ptr(), local.data_ptr(), first_pos.data_ptr(),
+                                            flag.data_ptr(), ws2.data_ptr(), ws2.numel(), st), "agnn_sample_hop_draw")
+        _lib.count_launches(12)
+        n_new = int(flag[-1].item())
+        for rel in range(r):
+            a, b = int(offs[rel * f]), int(offs[(rel + 1) * f])
+            per_rel["src"][rel].append(cand[3, a:b].long())
+            per_rel["dst"][rel].append(cand[2, a:b].long())
+            per_rel["edge"][rel].append(cand[0, a:b].long() - base)
+            edges_per_hop[rel].append(b - a)
+        lo, n_known = n_known, n_known + n_new
+        nodes_per_hop.append(n_new)
+    cat = lambda parts: torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64, device=dev)
+    return {"node": nodes[:n_known].long(), "src": [cat(v) for v in per_rel["src"]],
+            "dst": [cat(v) for v in per_rel["dst"]], "edge": [cat(v) for v in per_rel["edge"]],
+            "num_sampled_nodes": nodes_per_hop, "num_sampled_edges": edges_per_hop}
+
+
+class Corpus:
+    """Scores resident on the device: note features, typed edges with global node ids, per-score ranges."""
+
+    def __init__(self, x: torch.Tensor, edges: torch.Tensor, node_ptr: Sequence[int], n_rel: int = 4,
+                 extras: Optional[Dict[str, torch.Tensor]] = None):
+        self.x, self.edges, self.n_rel = x, edges, n_rel
+        self.node_ptr = [int(v) for v in node_ptr]
+        self.extras = extras or {}
+        score_of_edge = torch.bucketize(edges[0], torch.tensor(self.node_ptr[1:], device=edges.device), right=True)
+        counts = torch.bincount(score_of_edge, minlength=len(self.node_ptr) - 1).cpu().tolist()
+        self.edge_ptr = [0]
+        for c in counts:
+            self.edge_ptr.append(self.edge_ptr[-1] + c)
+        self._csr = None
+
+    @property
+    def n_scores(self):
+        return len(self.node_ptr) - 1
+
+    def csr_by_destination(self) -> graph.CSR:
+        if self._csr is None:
+            n = self.node_ptr[-1]
+            self._csr = graph.build_csr([graph.Segment(self.edges[1], self.edges[0], n, n, self.edges[2], self.n_rel)])[0]
+        return self._csr
+
+
+class ScoreGraphLoader:
+    """Batches of ``batch_size`` score windows (``subgraph_size`` notes each), optionally extended by
+    ``num_neighbors`` sampled hops, in the dict layout ``TorchAnalysisGNN.encode`` consumes
+    (analysisgnn/models/analysis.py:948-961): ``x_dict, edge_index_dict, batch_dict, batch_size,
+    num_sampled_nodes_dict, num_sampled_edges_dict`` plus gathered ``extras`` (labels, spellings)."""
+
+    REL_NAMES = ("onset", "consecutive", "during", "rest")
+
+    def __init__(self, corpus: Corpus, subgraph_size: int, batch_size: int, num_neighbors: Sequence[int] = (),
+                 seed: int = 0, shuffle: bool = True, rank: int = 0, world_size: int = 1):
+        self.corpus, self.subgraph_size, self.batch_size = corpus, subgraph_size, batch_size
+        self.num_neighbors, self.seed, self.shuffle = list(num_neighbors), seed, shuffle
+        self.rank, self.world_size = rank, world_size
+
+    def __len__(self):
+        return (self.corpus.n_scores + self.batch_size - 1) // self.batch_size
+
+    def order(self, epoch: int) -> List[int]:
+        ids = list(range(self.corpus.n_scores))
+        if self.shuffle:
+            ids.sort(key=lambda g: rng_u64(self.seed, 0x5348, epoch, g, 0))
+        return ids
+
+    def batch(self, epoch: int, index: int):
+        c = self.corpus
+        ids = self.order(epoch)[index * self.batch_size:(index + 1) * self.batch_size]
+        ids = ids[self.rank::self.world_size]                     # data parallel: subgraphs g mod W == rank
+        step_seed = rng_u64(self.seed, 0x424154, epoch, index, 0)
+        starts = [window_start(step_seed, g, c.node_ptr[g + 1] - c.node_ptr[g], self.subgraph_size) for g in ids]
+        edges, _, node_index, slot_ptr = window_subgraphs(c.edges[0], c.edges[1], c.edges[2], c.node_ptr, c.edge_ptr,
+                                                          ids, starts, self.subgraph_size)
+        n_target = slot_ptr[-1]
+        dev = edges.device
+        batch_vec = torch.repeat_interleave(torch.arange(len(ids), device=dev),
+                                            torch.tensor(np.diff(slot_ptr), device=dev))
+        out = {"batch_size": n_target, "graph_ids": ids}
+        if not self.num_neighbors:
+            ei = {("note", name, "note"): edges[:2, edges[2] == k] for k, name in enumerate(self.REL_NAMES[:c.n_rel])}
+            out.update(node_index=node_index, edge_index_dict=ei, num_sampled_nodes_dict=None,
+                       num_sampled_edges_dict=None)
+        else:
+            s = neighbor_sample(c.csr_by_destination(), c.node_ptr[-1], node_index, self.num_neighbors, step_seed)
+            node_index = s["node"]
+            ei = {("note", name, "note"): torch.stack((s["src"][k], s["dst"][k]))
+                  for k, name in enumerate(self.REL_NAMES[:c.n_rel])}
+            score_of = torch.bucketize(node_index, torch.tensor(c.node_ptr[1:], device=dev), right=True)
+            remap = torch.full((c.n_scores,), -1, dtype=torch.long, device=dev)
+            remap[torch.tensor(ids, device=dev)] = torch.arange(len(ids), device=dev)
+            batch_vec = remap[score_of]
+            out.update(node_index=node_index, edge_index_dict=ei,
+                       num_sampled_nodes_dict={"note": s["num_sampled_nodes"]},
+                       num_sampled_edges_dict={("note", name, "note"): s["num_sampled_edges"][k]
+                                               for k, name in enumerate(self.REL_NAMES[:c.n_rel])})
+        out["x_dict"] = {"note": c.x.index_select(0, node_index)}
+        out["batch_dict"] = {"note": batch_vec}
+        out["extras"] = {k: v.index_select(0, node_index) for k, v in c.extras.items()}
+        return out

@@ -292,6 +292,46 @@ int agnn_score_graph_build(int32_t n_scores, const int32_t* score_ptr, const int
                            int64_t capacity, int32_t* n_edges, void* workspace, size_t workspace_bytes,
                            agnn_stream_t stream);
 
+/* ------------------------------------------------------------ subgraph sampling
+ * Replaces the CPU sampling / collation behind the reference's loaders (analysisgnn/data/datamodules/
+ * analysis.py:270-323 -> graphmuse MuseNeighborLoader -> PyG NeighborSampler -> pyg-lib, third party) and the
+ * in-tree window step (analysisgnn/data/datasets/chord.py:217-229, analysisgnn/utils/hgraph.py:404-452).
+ * Semantics = oracle/graph.py (window_subgraph, neighbor_sample); bit-identical for a given seed.
+ *
+ * agnn_window_subgraph: for batch slot b, the node-induced subgraph of the contiguous window
+ * [node_lo[b], node_lo[b] + win_size[b]) of one score: its candidate edges are the corpus edges
+ * [edge_lo[b], edge_lo[b] + cand_ptr[b+1] - cand_ptr[b]); kept edges (both ends inside) come out in corpus
+ * order, re-indexed to out_off[b] + (id - node_lo[b]) -- the collated batch.  edges: int64 [3][capacity].
+ */
+size_t agnn_window_workspace(int64_t n_cand);
+int agnn_window_subgraph(int32_t n_slots, int64_t n_cand, const int64_t* cand_ptr, const int64_t* edge_lo,
+                         const int64_t* node_lo, const int32_t* win_size, const int64_t* out_off, const int64_t* src,
+                         const int64_t* dst, const int64_t* type /* optional */, int64_t* edges,
+                         int64_t* edge_id /* optional [capacity] */, int64_t capacity, int32_t* n_out, void* workspace,
+                         size_t workspace_bytes, agnn_stream_t stream);
+
+/* k-hop uniform neighbour sampling on a relation-major CSR keyed on the destination (agnn_csr_build),
+ * one node type.  local[n_nodes] / nodes[] hold the batch-local id of every node (or -1) and the
+ * discovered nodes in discovery order.  Per hop: _count (edges per relation x frontier node, scanned),
+ * the caller reads counts[n_rel * frontier_n] = n_cand, then _draw (sampling without replacement by
+ * partial Fisher-Yates with draw t = rng(seed, hop, relation, destination, t); all neighbours when
+ * degree <= fanout or fanout < 0; new sources are appended to `nodes` in the order the sequential
+ * algorithm meets them).  Candidates are ordered (relation, frontier node, draw): cand_slot = CSR slot,
+ * cand_src = global source, cand_dst = local destination, src_local = local source.  After _draw,
+ * flag[n_cand] holds the number of newly discovered nodes.  fanout <= 32.
+ */
+int agnn_sample_init(int32_t n_nodes, const int32_t* seeds, int32_t n_seeds, int32_t* local, int32_t* nodes,
+                     agnn_stream_t stream);
+size_t agnn_sample_hop_workspace(int32_t n_rel, int32_t frontier_n);
+int agnn_sample_hop_count(int32_t n_rel, int32_t n_nodes, const int32_t* rowptr, const int32_t* nodes,
+                          int32_t frontier_lo, int32_t frontier_n, int32_t fanout, int32_t* counts, void* workspace,
+                          size_t workspace_bytes, agnn_stream_t stream);
+int agnn_sample_hop_draw(int32_t n_rel, int32_t n_nodes, const int32_t* rowptr, const int32_t* col, int32_t* nodes,
+                         int32_t frontier_lo, int32_t frontier_n, int32_t n_known, int32_t hop, int32_t fanout,
+                         uint64_t seed, const int32_t* counts, int32_t n_cand, int32_t* cand_slot, int32_t* cand_src,
+                         int32_t* cand_dst, int32_t* src_local, int32_t* local, int32_t* first_pos, int32_t* flag,
+                         void* workspace, size_t workspace_bytes, agnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
