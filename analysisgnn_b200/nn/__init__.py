@@ -13,7 +13,8 @@ keys as the modules they replace, so reference checkpoints load unchanged:
 
 Every forward runs on libagnn.so's CUDA kernels; there is no CPU path.
 """
-from .intree import HeteroConv, MetricalConvLayer, MetricalGNN, SageConvScatter  # noqa: F401
+from .intree import (HeteroConv, MetricalConvLayer, MetricalGNN, RelEdgeConv, ResGatedGraphConv,  # noqa: F401
+                     SageConvScatter)
 from .hetero import (HeteroSAGELayer, HeteroSAGEStack, HGTConv, HeteroHGTStack, HybridGNN, HybridHGT,  # noqa: F401
                      SAGEConv, SequenceBranch)
 from .shell import AnalysisEncoder, multitask_ce  # noqa: F401

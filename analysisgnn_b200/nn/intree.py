@@ -69,6 +69,66 @@ class SageConvScatter(nn.Module):
         return self.linear(torch.cat((features, s), dim=-1))
 
 
+class ResGatedGraphConv(nn.Module):
+    """analysisgnn/models/core/gnn.py:212-258: ``h1 + (h1 + sum_j sigmoid(W3 x_i + W4 x_j [+ W5 e]) * W2 x_j)``
+    (``h1`` enters twice in the reference, :256-257).  Projections on the tensor-core GEMM, the per-edge
+    gate as elementwise ops, the reduction on the atomics-free segmented kernel."""
+
+    def __init__(self, in_features, out_features, bias=True, in_edge_features=None):
+        super().__init__()
+        self.W1 = Linear(in_features, out_features, bias=bias)
+        self.W2 = Linear(in_features, out_features, bias=bias)
+        self.W3 = Linear(in_features, out_features, bias=bias)
+        self.W4 = Linear(in_features, out_features, bias=bias)
+        self.in_edge_features = in_edge_features
+        if in_edge_features is not None:
+            self.W5 = Linear(in_edge_features, out_features, bias=bias)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for name in ("W1", "W2", "W3", "W4", "W5"):
+            if hasattr(self, name):
+                _xavier_relu_(getattr(self, name))
+
+    def forward(self, features, edge_index, edge_features=None, neigh_feats=None):
+        h1 = self.W1(features)
+        h2 = self.W2(features if neigh_feats is None else neigh_feats)
+        if edge_index is None or edge_index.shape[1] == 0:
+            return h1 + h1
+        gate = self.W3(features).index_select(0, edge_index[0]) + self.W4(features).index_select(0, edge_index[1])
+        if edge_features is not None and self.in_edge_features is not None:
+            gate = gate + self.W5(edge_features)
+        msg = torch.sigmoid(gate) * h2.index_select(0, edge_index[1])
+        s = ops.segment_sum_self(msg, h1, graph.edge_csr(edge_index[0], features.shape[0]))
+        return h1 + s
+
+
+class RelEdgeConv(nn.Module):
+    """analysisgnn/models/core/gnn.py:79-106: messages ``edge_linear([h_j || |h_i - h_j|])`` (or given edge
+    features), mean into ``h.clone()``, then ``linear([x || s])``."""
+
+    def __init__(self, in_node_features, out_features, bias=True, in_edge_features=None):
+        super().__init__()
+        self.neigh_linear = Linear(in_node_features, in_node_features, bias=bias)
+        self.edge_linear = Linear(in_node_features * 2 if in_edge_features is None
+                                  else in_node_features + in_edge_features, in_node_features, bias=bias)
+        self.linear = Linear(in_node_features * 2, out_features, bias=bias)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for lin in (self.linear, self.neigh_linear, self.edge_linear):
+            _xavier_relu_(lin)
+
+    def forward(self, features, edge_index, edge_features=None):
+        h = self.neigh_linear(features)
+        hi, hj = h.index_select(0, edge_index[0]), h.index_select(0, edge_index[1])
+        if edge_features is None:
+            edge_features = torch.abs(hi - hj)
+        msg = self.edge_linear(torch.cat((hj, edge_features), dim=-1))
+        s = ops.segment_mean_self(msg, h, graph.edge_csr(edge_index[0], features.shape[0]))
+        return self.linear(torch.cat((features, s), dim=-1))
+
+
 _FOLDABLE = ("mean", "sum")
 
 

@@ -200,6 +200,11 @@ def segment_sum(src, csr: TypedCSR):
     return _SegmentReduce.apply(src, None, csr, False)
 
 
+def segment_sum_self(src, self_add, csr: TypedCSR):
+    """``scatter(src[e_gather], e_reduce, out=self.clone(), reduce='sum')`` (gnn.py:256)."""
+    return _SegmentReduce.apply(src, self_add, csr, False)
+
+
 def segment_mean_self(src, self_add, csr: TypedCSR):
     """``scatter(src[e_gather], e_reduce, out=self.clone(), reduce='mean')`` (gnn.py:74; analysis.py:586)."""
     return _SegmentReduce.apply(src, self_add, csr, True)

@@ -97,6 +97,27 @@ class ResGatedGraphConv(nn.Module):
         return h1 + s
 
 
+class RelEdgeConv(nn.Module):
+    """analysisgnn/models/core/gnn.py:79-106."""
+
+    def __init__(self, in_node_features, out_features, bias=True, in_edge_features=None):
+        super().__init__()
+        self.neigh_linear = nn.Linear(in_node_features, in_node_features, bias=bias)
+        self.edge_linear = nn.Linear(in_node_features * 2 if in_edge_features is None
+                                     else in_node_features + in_edge_features, in_node_features, bias=bias)
+        self.linear = nn.Linear(in_node_features * 2, out_features, bias=bias)
+        for lin in (self.linear, self.neigh_linear, self.edge_linear):
+            _xavier_relu_(lin)
+
+    def forward(self, features, edge_index, edge_features=None):
+        h = self.neigh_linear(features)
+        if edge_features is None:
+            edge_features = torch.abs(h[edge_index[0]] - h[edge_index[1]])
+        new_h = self.edge_linear(torch.cat((h[edge_index[1]], edge_features), dim=-1))
+        s = mean_into_copy(new_h, edge_index[0], h)
+        return self.linear(torch.cat((features, s), dim=-1))
+
+
 _REDUCTIONS = {
     "mean": lambda t: t.mean(dim=0),
     "sum": lambda t: t.sum(dim=0),

@@ -132,6 +132,30 @@ def test_sage_edge_features_and_neigh_feats():
     _compare(net, o1, pg, ig[0], o2, x2)
 
 
+@pytest.mark.parametrize("name", ["ResGatedGraphConv", "RelEdgeConv"])
+def test_alternative_conv_blocks(name):
+    """The other ``conv_block``s of the reference (gnn.py:79-106, 212-258), alone and inside HeteroConv."""
+    b = synth.intree_batch(2, 110, 25, in_features=32, metrical=False)
+    ei = b["edge_index"][:, b["edge_type"] == 2]
+    torch.manual_seed(6)
+    ref = getattr(oi, name)(32, 48)
+    net = getattr(ann, name)(32, 48).to(DEV)
+    net.load_state_dict(ref.state_dict())
+    x1 = b["x"].clone().requires_grad_(True)
+    o1 = ref(x1, ei)
+    pg, ig = grads_of(ref, o1, [x1])
+    x2 = b["x"].to(DEV).requires_grad_(True)
+    _compare(net, o1, pg, ig[0], net(x2, ei.to(DEV)), x2)
+    ref_h = oi.HeteroConv(32, 48, b["etypes"], module=getattr(oi, name))
+    net_h = ann.HeteroConv(32, 48, b["etypes"], module=getattr(ann, name)).to(DEV)
+    net_h.load_state_dict(ref_h.state_dict())
+    x1 = b["x"].clone().requires_grad_(True)
+    o1 = ref_h(x1, b["edge_index"], b["edge_type"])
+    pg, ig = grads_of(ref_h, o1, [x1])
+    x2 = b["x"].to(DEV).requires_grad_(True)
+    _compare(net_h, o1, pg, ig[0], net_h(x2, b["edge_index"].to(DEV), b["edge_type"].to(DEV)), x2)
+
+
 @pytest.mark.parametrize("uniform", [True, False])
 def test_metrical_conv_layer_uniform_and_ragged(uniform):
     torch.manual_seed(4)

@@ -92,3 +92,25 @@ def test_oracle_matches_live_reference():
     # state_dict keys and shapes are the reference's
     assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == \
            {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name", ["ResGatedGraphConv", "RelEdgeConv"])
+def test_alternative_conv_blocks_match_live_reference(name):
+    from analysisgnn_b200 import synth
+    gnn, _ = ref_loader.load_core()
+    b = synth.intree_batch(2, 60, 3, in_features=12, metrical=False)
+    ei = b["edge_index"][:, b["edge_type"] == 2]
+    torch.manual_seed(1)
+    ref = getattr(gnn, name)(12, 20)
+    mine = getattr(intree, name)(12, 20)
+    mine.load_state_dict(ref.state_dict())
+    x1 = b["x"].clone().requires_grad_(True)
+    x2 = b["x"].clone().requires_grad_(True)
+    o1, o2 = ref(x1, ei), mine(x2, ei)
+    assert_close(o2, o1, TOL, "forward")
+    g1, i1 = grads_of(ref, o1, [x1])
+    g2, i2 = grads_of(mine, o2, [x2])
+    for k in g1:
+        assert_close(g2[k], g1[k], 5e-6, k)
+    assert_close(i2[0], i1[0], 5e-6, "x grad")
