@@ -112,10 +112,23 @@ _PROTOTYPES = {
     "agnn_sample_hop_draw": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_int32] +
                              [C.c_void_p] * 8 + [C.c_size_t, C.c_void_p]),
+    "agnn_gru_supported": (C.c_int, [C.c_int]),
+    "agnn_gru_fwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agnn_gru_bwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
 _launches = 0
+
+
+def ptr_array(tensors):
+    """A host array of device pointers (``const float* const*`` arguments)."""
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
 
 
 def count_launches(n: int) -> None:

@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import graph, ops
-from .layers import LayerNorm, Linear
+from .layers import GRU, LayerNorm, Linear
 
 EdgeType = Tuple[str, str, str]
 
@@ -294,7 +294,7 @@ class SequenceBranch(nn.Module):
 
     def __init__(self, in_channels, hidden_channels, dropout):
         super().__init__()
-        self.rnn = nn.GRU(input_size=in_channels, hidden_size=hidden_channels // 2, num_layers=2,
+        self.rnn = GRU(input_size=in_channels, hidden_size=hidden_channels // 2, num_layers=2,
                           batch_first=True, bidirectional=True, dropout=dropout)
         self.rnn_norm = LayerNorm(hidden_channels)
         self.rnn_mlp = nn.Sequential(

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import graph, ops
-from .layers import LayerNorm, Linear
+from .layers import GRU, LayerNorm, Linear
 
 
 def _xavier_relu_(linear: nn.Linear):
@@ -223,7 +223,7 @@ class MetricalConvLayer(nn.Module):
         self.normalize = nn.BatchNorm1d(out_dim)
         self.neigh = Linear(in_dim, in_dim, bias=bias)
         self.conv_out = Linear(4 * in_dim, out_dim, bias=bias)
-        self.seq = nn.GRU(in_dim, in_dim, batch_first=True, bias=bias, bidirectional=True)
+        self.seq = GRU(in_dim, in_dim, batch_first=True, bias=bias, bidirectional=True)
 
     def reset_parameters(self):
         self.neigh.reset_parameters()

@@ -614,6 +614,84 @@ def side_stream(device) -> "torch.cuda.Stream":
     return _side_streams[idx]
 
 
+class _GRULayer(torch.autograd.Function):
+    """One (bi)directional GRU layer, batch first, h0 = 0.  Arguments: x [B, T, C], then per direction
+    (w_ih [3H, C], w_hh [3H, H], b_ih [3H], b_hh [3H]).  Input projections and all weight / input
+    gradients are tensor-core GEMMs; agnn_gru_fwd / _bwd run only the time recurrence."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        n_dir = len(params) // 4
+        b, t, c = x.shape
+        h = params[1].shape[1]
+        x2 = x.reshape(b * t, c)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        xs = linalg.prepare(x2)
+        gis, whh, bhh = [], [], []
+        for d in range(n_dir):
+            w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
+            gis.append(linalg.linear(xs, w_ih, b_ih))
+            whh.append(w_hh.contiguous())
+            bhh.append(b_hh.contiguous())
+        out = torch.empty((b, t, n_dir * h), dtype=x.dtype, device=x.device)
+        gates = [torch.empty((b, t, 4 * h), dtype=x.dtype, device=x.device) for _ in range(n_dir)]
+        _lib.check(_lib.lib().agnn_gru_fwd(b, t, h, n_dir, _lib.ptr_array(gis), _lib.ptr_array(whh),
+                                           _lib.ptr_array(bhh), out.data_ptr(), _lib.ptr_array(gates), _stream(x)),
+                   "agnn_gru_fwd")
+        _lib.count_launches(1)
+        ctx.save_for_backward(*linalg.pack(xs), out, *gates, *[params[4 * d] for d in range(n_dir)], *whh)
+        ctx.n_dir, ctx.dims = n_dir, (b, t, c, h)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n_dir = ctx.n_dir
+        b, t, c, h = ctx.dims
+        saved = ctx.saved_tensors
+        xs = linalg.unpack(saved[0], saved[1])
+        out = saved[2]
+        gates = list(saved[3:3 + n_dir])
+        w_ih = list(saved[3 + n_dir:3 + 2 * n_dir])
+        whh = list(saved[3 + 2 * n_dir:3 + 3 * n_dir])
+        dout = dout.contiguous()
+        dgi = [torch.empty((b * t, 3 * h), dtype=out.dtype, device=out.device) for _ in range(n_dir)]
+        dgh = [torch.empty((b * t, 3 * h), dtype=out.dtype, device=out.device) for _ in range(n_dir)]
+        _lib.check(_lib.lib().agnn_gru_bwd(b, t, h, n_dir, _lib.ptr_array(whh), out.data_ptr(), _lib.ptr_array(gates),
+                                           dout.data_ptr(), _lib.ptr_array(dgi), _lib.ptr_array(dgh), _stream(out)),
+                   "agnn_gru_bwd")
+        _lib.count_launches(1)
+        grads = []
+        dx = None
+        for d in range(n_dir):
+            hd = out[:, :, d * h:(d + 1) * h]
+            h_prev = torch.zeros((b, t, h), dtype=out.dtype, device=out.device)
+            if t > 1:
+                if d == 0:
+                    h_prev[:, 1:] = hd[:, :-1]
+                else:
+                    h_prev[:, :-1] = hd[:, 1:]
+            gi_s, gh_s = linalg.prepare(dgi[d]), linalg.prepare(dgh[d])
+            dw_ih = linalg.mm_tn(gi_s, xs)
+            dw_hh = linalg.mm_tn(gh_s, h_prev.reshape(b * t, h))
+            if ctx.needs_input_grad[0]:
+                if dx is None:
+                    dx = linalg.mm(gi_s, w_ih[d])
+                else:
+                    dx = linalg.mm(gi_s, w_ih[d], out=dx, accumulate=True)
+            grads += [dw_ih, dw_hh, colsum(dgi[d]), colsum(dgh[d])]
+        return (dx.reshape(b, t, c) if dx is not None else None, *grads)
+
+
+def gru_layer(x: torch.Tensor, params) -> torch.Tensor:
+    """``params``: flat list of (w_ih, w_hh, b_ih, b_hh) per direction."""
+    return _GRULayer.apply(x, *params)
+
+
+def gru_supported(x: torch.Tensor, hidden: int) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[0] > 0 and x.shape[1] > 0
+            and bool(_lib.lib().agnn_gru_supported(int(hidden))))
+
+
 def run_rnn(rnn: "torch.nn.RNNBase", seq: torch.Tensor):
     """cuDNN RNN (kept as a library call: the GRU branches are outside the kernel scope)."""
     return rnn(seq)[0]

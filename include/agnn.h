@@ -332,6 +332,26 @@ int agnn_sample_hop_draw(int32_t n_rel, int32_t n_nodes, const int32_t* rowptr, 
                          int32_t* cand_dst, int32_t* src_local, int32_t* local, int32_t* first_pos, int32_t* flag,
                          void* workspace, size_t workspace_bytes, agnn_stream_t stream);
 
+/* ------------------------------------------------------------ GRU recurrence
+ * Replaces the sequential part of nn.GRU in the sequence branches (analysisgnn/models/cadence.py:249-260,
+ * 276-285; analysisgnn/models/analysis.py:527-537; MetricalConvLayer.seq, analysisgnn/models/core/gnn.py:498,
+ * 523).  The input projections gi = X W_ih^T + b_ih of all time steps and every weight / input gradient are
+ * agnn_gemm calls made by the caller; these two kernels run the time loop with W_hh resident in registers
+ * (hidden size 32, 64 or 128; one layer, n_dir = 1 or 2 directions, h0 = 0, batch-first [B, T, .]).
+ * Pointer-array arguments are HOST arrays of n_dir device pointers.
+ *   fwd:  out [B, T, n_dir*H]; gates[d] [B, T, 4H] (r, z, n, W_hn h + b_hn) kept for the backward (may be NULL
+ *         arrays for inference).
+ *   bwd:  from dout, out, gates: dgi[d] = dL/d(gi_d) [B, T, 3H] and dgh[d] = dL/d(W_hh h + b_hh) [B, T, 3H];
+ *         then db_ih = colsum(dgi), db_hh = colsum(dgh), dW_ih = dgi^T X, dW_hh = dgh^T H_prev, dX = sum_d dgi_d W_ih_d.
+ */
+int agnn_gru_supported(int hidden);
+int agnn_gru_fwd(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* gi /* host */,
+                 const float* const* w_hh /* host */, const float* const* b_hh /* host */, float* out,
+                 float* const* gates /* host, optional */, agnn_stream_t stream);
+int agnn_gru_bwd(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* w_hh /* host */,
+                 const float* out, const float* const* gates /* host */, const float* dout,
+                 float* const* dgi /* host */, float* const* dgh /* host */, agnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
