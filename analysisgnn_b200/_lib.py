@@ -61,7 +61,7 @@ _PROTOTYPES = {
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "agnn_gather_reduce": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Rel),
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
-                                     C.c_int64, C.c_void_p]),
+                                     C.c_int64, C.c_void_p, C.c_void_p]),
     "agnn_rowscale_sum": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.POINTER(Rel), C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "agnn_hgt_attn_fwd": (C.c_int, [C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HgtRel), C.c_void_p,
@@ -92,12 +92,13 @@ _PROTOTYPES = {
     "agnn_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
     "agnn_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_int, C.c_void_p]),
     "agnn_l2norm_relu_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
                                        C.c_int, C.c_float, C.c_void_p]),
     "agnn_l2norm_relu_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_int64, C.c_int, C.c_int, C.c_void_p]),
-    "agnn_colsum_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "agnn_colsum_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "agnn_score_graph_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
     "agnn_score_graph_build": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t,

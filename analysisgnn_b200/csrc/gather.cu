@@ -31,7 +31,30 @@ struct GatherParams {
   int64_t ld_copy;
   void* out;
   int64_t ld_out;
+  void* out_lo;  // optional (fp32 only): out receives rna_tf32(y), out_lo rna_tf32(y - out) -- agnn_gemm operands
 };
+
+// store one 16-byte vector, optionally as the TF32 hi / lo pair the tensor-core GEMM consumes
+template <typename T>
+__device__ __forceinline__ void store_split(T* hi_ptr, T* lo_ptr, const float (&v)[Vec16<T>::E]) {
+  if constexpr (sizeof(T) == 4) {
+    if (lo_ptr) {
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        uint32_t hb, lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[e]));
+        h[e] = __uint_as_float(hb);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v[e] - h[e]));
+        l[e] = __uint_as_float(lb);
+      }
+      Vec16<T>::store(hi_ptr, h);
+      Vec16<T>::store(lo_ptr, l);
+      return;
+    }
+  }
+  Vec16<T>::store(hi_ptr, v);
+}
 
 template <typename T, int LANES, int V>
 __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_constant__ GatherParams p) {
@@ -41,6 +64,7 @@ __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_co
   const int lane = threadIdx.x % LANES;
   const int F = p.n_feat;
   T* const out = static_cast<T*>(p.out);
+  T* const out_lo = static_cast<T*>(p.out_lo);
 
   for (int row = blockIdx.x * kRowsPerBlock + threadIdx.x / LANES; row < p.n_rows;
        row += gridDim.x * kRowsPerBlock) {
@@ -124,7 +148,7 @@ __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_co
       }
 
       if (p.combine == AGNN_COMBINE_CONCAT) {
-        T* op = out + (int64_t)row * p.ld_out + R.out_col;
+        const int64_t off = (int64_t)row * p.ld_out + R.out_col;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           const int c = (v * LANES + lane) * E;
@@ -132,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_co
             float o[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) o[e] = acc[v][e] * s;
-            VT::store(op + c, o);
+            store_split<T>(out + off + c, out_lo ? out_lo + off + c : nullptr, o);
           }
         }
       } else {
@@ -144,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_co
     }
 
     if (p.combine == AGNN_COMBINE_SUM) {
-      T* op = out + (int64_t)row * p.ld_out + p.rel[0].out_col;
+      const int64_t off = (int64_t)row * p.ld_out + p.rel[0].out_col;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int c = (v * LANES + lane) * E;
@@ -152,20 +176,20 @@ __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_co
           float o[E];
 #pragma unroll
           for (int e = 0; e < E; ++e) o[e] = tot[v][e] + (p.self_add ? selfv[v][e] : 0.f);
-          VT::store(op + c, o);
+          store_split<T>(out + off + c, out_lo ? out_lo + off + c : nullptr, o);
         }
       }
     }
     if (p.copy) {
       const T* cp = static_cast<const T*>(p.copy) + (int64_t)row * p.ld_copy;
-      T* op = out + (int64_t)row * p.ld_out + p.copy_col;
+      const int64_t off = (int64_t)row * p.ld_out + p.copy_col;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int c = (v * LANES + lane) * E;
         if (c < F) {
           float t[E];
           VT::load_nc(cp + c, t);
-          VT::store(op + c, t);
+          store_split<T>(out + off + c, out_lo ? out_lo + off + c : nullptr, t);
         }
       }
     }
@@ -247,7 +271,7 @@ using namespace agnn;
 
 extern "C" int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
                                   const agnn_rel_t* rels, const void* self_add, int64_t ld_self, const void* copy,
-                                  int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out,
+                                  int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out, void* out_lo,
                                   agnn_stream_t stream) {
   if (n_rows < 0 || n_feat <= 0 || n_rel < 1 || n_rel > AGNN_MAX_REL || !rels || !out)
     return fail(AGNN_ERR_ARG, "gather_reduce: bad sizes (n_rows=%d n_feat=%d n_rel=%d)", n_rows, n_feat, n_rel);
@@ -262,6 +286,9 @@ extern "C" int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int
   p.n_rows = n_rows; p.n_feat = n_feat; p.n_rel = n_rel; p.scale = scale; p.combine = combine;
   p.copy_col = copy_col;
   p.self_add = self_add; p.ld_self = ld_self; p.copy = copy; p.ld_copy = ld_copy; p.out = out; p.ld_out = ld_out;
+  p.out_lo = out_lo;
+  if (out_lo && (dtype != AGNN_F32 || !aligned16(out_lo)))
+    return fail(AGNN_ERR_ARG, "gather_reduce: the TF32 hi/lo output needs fp32 and a 16-byte aligned out_lo");
   int rc;
   if ((rc = check_matrix("gather_reduce: out", out, ld_out, eb))) return rc;
   if (self_add && (rc = check_matrix("gather_reduce: self_add", self_add, ld_self, eb))) return rc;

@@ -262,9 +262,40 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restric
   }
 }
 
+// out[c] = sum_b part[b][c] (fixed order => deterministic).  One CTA per 32 columns: lane = column (128-byte
+// coalesced rows), the 8 warps stride over the partial rows with 4 loads in flight each, then combine in
+// shared memory -- a single-thread-per-column loop over ~600 rows is a 100 us latency chain.
+__global__ void __launch_bounds__(kThreads) reduce_partials_kernel(const float* __restrict__ part, int blocks, int cols,
+                                                                    float* __restrict__ out, int64_t set_stride_part,
+                                                                    int64_t set_stride_out) {
+  __shared__ float red[kWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const float* p = part + blockIdx.y * set_stride_part;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < cols) {
+    int b = warp;
+    for (; b + 3 * kWarps < blocks; b += 4 * kWarps) {
+      a0 += p[(int64_t)b * cols + c];
+      a1 += p[(int64_t)(b + kWarps) * cols + c];
+      a2 += p[(int64_t)(b + 2 * kWarps) * cols + c];
+      a3 += p[(int64_t)(b + 3 * kWarps) * cols + c];
+    }
+    for (; b < blocks; b += kWarps) a0 += p[(int64_t)b * cols + c];
+  }
+  red[warp][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (warp == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += red[w][lane];
+    out[blockIdx.y * set_stride_out + c] = t;
+  }
+}
+
 int row_blocks(int64_t rows) {
   int64_t b = ceil_div(rows, kWarps * 4);   // >= 4 rows per warp so the column partials amortise
-  if (b > kNumSM * 4) b = kNumSM * 4;
+  if (b > kNumSM * 2) b = kNumSM * 2;
   return b < 1 ? 1 : (int)b;
 }
 
@@ -313,7 +344,8 @@ extern "C" int agnn_layernorm_fwd(const float* x, int64_t ld_x, const float* gam
 
 extern "C" int agnn_layernorm_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* gamma,
                                   const float* mean, const float* rstd, float* dx, int64_t ld_dx, float* dgamma_part,
-                                  float* dbeta_part, int64_t rows, int cols, agnn_stream_t stream) {
+                                  float* dbeta_part, float* dgamma, float* dbeta, int64_t rows, int cols,
+                                  agnn_stream_t stream) {
   int rc = check("layernorm_bwd", rows, cols, {dy, x, gamma, dx}, {ld_dy, ld_x, ld_dx});
   if (rc) return rc;
   if (!mean || !rstd || !dgamma_part || !dbeta_part) return fail(AGNN_ERR_ARG, "layernorm_bwd: null pointer");
@@ -322,6 +354,13 @@ extern "C" int agnn_layernorm_bwd(const float* dy, int64_t ld_dy, const float* x
 #define CALL(V) layernorm_bwd_kernel<V><<<blocks, kThreads, 0, st>>>(dy, ld_dy, x, ld_x, gamma, mean, rstd, dx, ld_dx, dgamma_part, dbeta_part, rows, cols)
   AGNN_DISPATCH_V(cols, CALL);
 #undef CALL
+  if (dgamma && dbeta) {
+    if (dbeta_part != dgamma_part + (int64_t)blocks * cols || dbeta != dgamma + cols)
+      return fail(AGNN_ERR_ARG, "layernorm_bwd: the fused final reduction needs dbeta directly behind dgamma "
+                                "(partials [2][blocks][cols], outputs [2][cols])");
+    reduce_partials_kernel<<<dim3((unsigned)ceil_div(cols, 32), 2), kThreads, 0, st>>>(dgamma_part, blocks, cols, dgamma,
+                                                                                        (int64_t)blocks * cols, cols);
+  }
   return check_launch("layernorm_bwd");
 }
 
@@ -356,7 +395,7 @@ extern "C" int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float*
   return check_launch("l2norm_relu_bwd");
 }
 
-extern "C" int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, int64_t rows, int cols,
+extern "C" int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, float* out, int64_t rows, int cols,
                                     agnn_stream_t stream) {
   int rc = check("colsum_partials", rows, cols, {x, partials}, {ld_x});
   if (rc) return rc;
@@ -365,5 +404,6 @@ extern "C" int agnn_colsum_partials(const float* x, int64_t ld_x, float* partial
 #define CALL(V) colsum_kernel<V><<<blocks, kThreads, 0, st>>>(x, ld_x, partials, rows, cols)
   AGNN_DISPATCH_V(cols, CALL);
 #undef CALL
+  if (out) reduce_partials_kernel<<<dim3((unsigned)ceil_div(cols, 32), 1), kThreads, 0, st>>>(partials, blocks, cols, out, 0, 0);
   return check_launch("colsum_partials");
 }

@@ -113,9 +113,12 @@ def gather_bytes(rels: Sequence[Rel], n_rows: int, n_feat: int, elem: int, conca
 
 def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: bool, concat: bool,
                   self_add: Optional[torch.Tensor] = None, copy: Optional[torch.Tensor] = None,
-                  copy_col: int = 0) -> torch.Tensor:
-    """agnn_gather_reduce on ``out`` ([n_rows, >= n_feat] view).  See include/agnn.h."""
+                  copy_col: int = 0, out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """agnn_gather_reduce on ``out`` ([n_rows, >= n_feat] view).  See include/agnn.h.  With ``out_lo``
+    the result is written as the TF32 hi / lo pair (``out``, ``out_lo``) that ``agnn_gemm`` consumes."""
     out = _rows2d(out, "out")
+    if out_lo is not None and (out_lo.shape != out.shape or out_lo.stride() != out.stride()):
+        raise ValueError("out_lo must match out in shape and strides")
     n_rows = out.shape[0]
     arr = _pack(rels, n_feat, out.dtype)
     sa = _rows2d(self_add, "self_add") if self_add is not None else None
@@ -128,10 +131,13 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
             _lib.COMBINE_CONCAT if concat else _lib.COMBINE_SUM, len(rels), arr,
             sa.data_ptr() if sa is not None else None, sa.stride(0) if sa is not None else 0,
             cp.data_ptr() if cp is not None else None, cp.stride(0) if cp is not None else 0, int(copy_col),
-            out.data_ptr(), out.stride(0), stream), "agnn_gather_reduce")
+            out.data_ptr(), out.stride(0), out_lo.data_ptr() if out_lo is not None else None, stream),
+            "agnn_gather_reduce")
 
     if timer is not None and all(r.n_edges is not None for r in rels):
         nbytes = gather_bytes(rels, n_rows, n_feat, out.element_size(), concat, sa is not None, cp is not None)
+        if out_lo is not None:      # every written row goes out twice (hi and lo)
+            nbytes += n_rows * n_feat * out.element_size() * ((len(rels) if concat else 1) + int(cp is not None))
         timer.launch("gather_reduce", nbytes, out.device, run)
     else:
         run()
@@ -214,6 +220,19 @@ def segment_mean_self(src, self_add, csr: TypedCSR):
 # in-tree HeteroConv{SageConvScatter}: one fused layer
 # ------------------------------------------------------------------------------
 
+def _operand_buffers(rows: int, cols: int, like: torch.Tensor):
+    """(hi, lo) buffers for a GEMM operand the gather kernel writes: a TF32 pair on the tcgen05 fp32 route
+    (lo is None otherwise, and hi then holds the plain values)."""
+    if linalg.backend() == "tcgen05" and like.dtype == torch.float32 and cols % 4 == 0:
+        buf = torch.empty((2, rows, cols), dtype=like.dtype, device=like.device)
+        return buf[0], buf[1]
+    return torch.empty((rows, cols), dtype=like.dtype, device=like.device), None
+
+
+def _as_operand_pair(hi, lo):
+    return linalg.Split(hi, lo) if lo is not None else hi
+
+
 class _IntreeSageLayer(torch.autograd.Function):
     """All relations of a reference ``HeteroConv(module=SageConvScatter)`` layer
     (analysisgnn/models/core/hgnn.py:479-484 over gnn.py:62-76) in 2 GEMMs + 1 gather:
@@ -231,11 +250,12 @@ class _IntreeSageLayer(torch.autograd.Function):
         n, f = x.shape
         r = csr.n_rel
         h = linalg.linear(x, wn_cat, bn_cat)                                     # [N, R*F]
-        a = torch.empty((n, (r + 1) * f), dtype=x.dtype, device=x.device)
+        a_hi, a_lo = _operand_buffers(n, (r + 1) * f, x)
         rels = [Rel(csr.fwd.rowptr[k], csr.fwd.col, h[:, k * f:(k + 1) * f], out_col=(k + 1) * f,
                     flags=_lib.REL_IDENTITY_IF_EMPTY, n_edges=csr.n_edges if k == 0 else 0) for k in range(r)]
-        gather_reduce(rels, a, f, mean=True, concat=True, self_add=x, copy=x, copy_col=0)
-        a = linalg.prepare(a)                      # one TF32 split feeds the forward and the grad-weight GEMM
+        # the gather writes the GEMM operand directly as a TF32 pair: it feeds the forward and the grad-weight GEMM
+        gather_reduce(rels, a_hi, f, mean=True, concat=True, self_add=x, copy=x, copy_col=0, out_lo=a_lo)
+        a = _as_operand_pair(a_hi, a_lo)
         z = linalg.linear(a, wc, bc)
         ctx.save_for_backward(x, *linalg.pack(a), wn_cat, wc)
         ctx.csr = csr
@@ -251,7 +271,7 @@ class _IntreeSageLayer(torch.autograd.Function):
         dz = linalg.prepare(dz_plain)
         da = linalg.mm(dz, wc)                                                   # [N, (R+1)F]
         dwc = linalg.mm_tn(dz, a) if ctx.needs_input_grad[3] else None
-        dbc = dz_plain.sum(0) if ctx.has_bias[1] and ctx.needs_input_grad[4] else None
+        dbc = colsum(dz_plain) if ctx.has_bias[1] and ctx.needs_input_grad[4] else None
         dh = torch.empty((n, r * f), dtype=x.dtype, device=x.device)
         rels_t = [Rel(csr.bwd.rowptr[k], csr.bwd.col, da[:, (k + 1) * f:(k + 2) * f], out_col=k * f,
                       nbr_deg_rowptr=csr.fwd.rowptr[k], flags=_lib.REL_IDENTITY_IF_EMPTY,
@@ -268,7 +288,7 @@ class _IntreeSageLayer(torch.autograd.Function):
         else:
             dh_op = dh
         dwn = linalg.mm_tn(dh_op, x) if ctx.needs_input_grad[1] else None
-        dbn = dh.sum(0) if ctx.has_bias[0] and ctx.needs_input_grad[2] else None
+        dbn = colsum(dh) if ctx.has_bias[0] and ctx.needs_input_grad[2] else None
         return dx, dwn, dbn, dwc, dbc, None
 
 
@@ -301,11 +321,11 @@ class _HeteroSageLayer(torch.autograd.Function):
             x_t = xs[t]
             f = x_t.shape[1]
             rel_list = plan.incoming[t]
-            a = torch.empty((x_t.shape[0], (len(rel_list) + 1) * f), dtype=x_t.dtype, device=x_t.device)
+            a_hi, a_lo = _operand_buffers(x_t.shape[0], (len(rel_list) + 1) * f, x_t)
             rels = [Rel(csr.fwd[et].rowptr[0], csr.fwd[et].col, xs[et[0]], out_col=(k + 1) * f,
                         n_edges=csr.n_edges[et]) for k, et in enumerate(rel_list)]
-            gather_reduce(rels, a, f, mean=True, concat=True, copy=x_t, copy_col=0)
-            a = linalg.prepare(a)
+            gather_reduce(rels, a_hi, f, mean=True, concat=True, copy=x_t, copy_col=0, out_lo=a_lo)
+            a = _as_operand_pair(a_hi, a_lo)
             o = linalg.linear(a, wcat, bias, relu=relu)
             outs.append(o)
             saved += [*linalg.pack(a), wcat, o]
@@ -330,7 +350,7 @@ class _HeteroSageLayer(torch.autograd.Function):
                 continue
             g = linalg.relu_backward(g, o) if ctx.relu else g.contiguous()
             if ctx.needs_input_grad[3 + nt + 2 * j + 1]:
-                grads[nt + 2 * j + 1] = g.sum(0)
+                grads[nt + 2 * j + 1] = colsum(g)
             g = linalg.prepare(g)
             da[t] = linalg.mm(g, wcat)
             if ctx.needs_input_grad[3 + nt + 2 * j]:
@@ -471,10 +491,11 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     lib = _lib.lib()
     rows, cols = x.shape
     part = torch.empty((lib.agnn_row_blocks(rows), cols), dtype=torch.float32, device=x.device)
-    _lib.check(lib.agnn_colsum_partials(x.data_ptr(), x.stride(0), part.data_ptr(), rows, cols, _stream(x)),
-               "agnn_colsum_partials")
-    _lib.count_launches(1)
-    return part.sum(0)
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    _lib.check(lib.agnn_colsum_partials(x.data_ptr(), x.stride(0), part.data_ptr(), out.data_ptr(), rows, cols,
+                                        _stream(x)), "agnn_colsum_partials")
+    _lib.count_launches(2)
+    return out
 
 
 class _Linear(torch.autograd.Function):
@@ -542,12 +563,12 @@ class _LayerNorm(torch.autograd.Function):
         dx = torch.empty_like(x)
         blocks = lib.agnn_row_blocks(rows)
         part = torch.empty((2, blocks, cols), dtype=torch.float32, device=x.device)
+        sums = torch.empty((2, cols), dtype=torch.float32, device=x.device)
         _lib.check(lib.agnn_layernorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gamma.data_ptr(),
                                           mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), dx.stride(0),
-                                          part[0].data_ptr(), part[1].data_ptr(), rows, cols, _stream(x)),
-                   "agnn_layernorm_bwd")
-        _lib.count_launches(1)
-        sums = part.sum(1)
+                                          part[0].data_ptr(), part[1].data_ptr(), sums[0].data_ptr(),
+                                          sums[1].data_ptr(), rows, cols, _stream(x)), "agnn_layernorm_bwd")
+        _lib.count_launches(2)
         return dx, sums[0], sums[1], None
 
 

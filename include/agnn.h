@@ -105,6 +105,9 @@ int agnn_csr_build(int n_seg, const agnn_coo_t* segs /* host */, int32_t* rowptr
  * contributes src_r[i, :] itself, unscaled, without the self term: the reference's
  * E == 0 branch, z = W [x || h] (gnn.py:67-69).
  * If `copy` is given, out[i, copy_col : +F] = copy[i, :] (builds [x || S] rows).
+ * If `out_lo` is given (fp32 only; same shape and stride as `out`), every value y is stored as the TF32
+ * pair out = rna_tf32(y), out_lo = rna_tf32(y - out): the operand form of agnn_gemm's 3xTF32 mode,
+ * produced here for free instead of by a separate agnn_split_tf32 pass over the matrix.
  */
 typedef struct agnn_rel {
   const int32_t* rowptr; /* [n_rows + 1]                                        */
@@ -126,7 +129,7 @@ typedef struct agnn_rel {
 int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
                        const agnn_rel_t* rels /* host */, const void* self_add, int64_t ld_self,
                        const void* copy, int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out,
-                       agnn_stream_t stream);
+                       void* out_lo /* optional */, agnn_stream_t stream);
 
 /* out[i, :] = base[i, :] (if given) + sum_r in[i, in_col_r : +F] / max(deg_r(i), 1)
  * -- the gradient of the self term of the mean_self reduction (gnn.py:74 backward).
@@ -264,18 +267,22 @@ int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, int64_t N, i
  * agnn_l2norm_relu_*: F.normalize(p=2, eps) combined with the ReLU around it in MetricalGNN
  * (analysisgnn/models/core/hgnn.py:415, 421-422, 431): relu_first = normalize(relu(x)), else relu(normalize(x)).
  * agnn_colsum_partials: bias gradients, partials[agnn_row_blocks(rows)][cols].
+ * When the optional final outputs are given (dgamma / dbeta / out) the partials are also summed, in block
+ * order, by a second launch inside the call (dbeta_partials must directly follow dgamma_partials).
  */
 int agnn_row_blocks(int64_t rows);
 int agnn_layernorm_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, float* y, int64_t ld_y,
                        float* mean, float* rstd, int64_t rows, int cols, float eps, agnn_stream_t stream);
 int agnn_layernorm_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* gamma,
                        const float* mean, const float* rstd, float* dx, int64_t ld_dx, float* dgamma_partials,
-                       float* dbeta_partials, int64_t rows, int cols, agnn_stream_t stream);
+                       float* dbeta_partials, float* dgamma /* optional [cols] */, float* dbeta /* = dgamma + cols */,
+                       int64_t rows, int cols, agnn_stream_t stream);
 int agnn_l2norm_relu_fwd(const float* x, int64_t ld_x, float* y, int64_t ld_y, float* inv_norm, int64_t rows, int cols,
                          int relu_first, float eps, agnn_stream_t stream);
 int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* inv_norm, float* dx,
                          int64_t ld_dx, int64_t rows, int cols, int relu_first, agnn_stream_t stream);
-int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, int64_t rows, int cols, agnn_stream_t stream);
+int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, float* out /* optional [cols] */, int64_t rows,
+                         int cols, agnn_stream_t stream);
 
 /* ------------------------------------------------------------ score-graph construction
  * Replaces hetero_graph_from_note_array (analysisgnn/utils/hgraph.py:214-300; rest_array=None,

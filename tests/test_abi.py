@@ -38,7 +38,7 @@ def test_python_binding_covers_every_declared_symbol():
 
 def test_version_and_error_text(lib):
     assert lib.agnn_version() >= 100
-    rc = lib.agnn_gather_reduce(4, 0, 0, 0, 0, 1, None, None, 0, None, 0, 0, None, 0, None)
+    rc = lib.agnn_gather_reduce(4, 0, 0, 0, 0, 1, None, None, 0, None, 0, 0, None, 0, None, None)
     assert rc == -1
     assert b"gather_reduce" in lib.agnn_last_error()
 

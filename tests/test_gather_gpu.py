@@ -137,3 +137,19 @@ def test_linearity_at_full_size():
     outdeg = torch.bincount(b["edge_index"][1], minlength=n).double().to(DEV)
     want = (a.double() * outdeg[:, None]).sum(0)
     assert_close(ga.double().sum(0), want, FP32_REL)
+
+
+def test_tf32_pair_output_is_what_the_gemm_consumes():
+    """out_lo: the gather writes rna_tf32(y) and rna_tf32(y - hi) -- bit-identical to agnn_split_tf32 of the plain result."""
+    from analysisgnn_b200 import linalg
+    n, e, f = 700, 5000, 256
+    ei = _graph(n, n, e, 12)
+    x = torch.randn(n, f, device=DEV)
+    csr = graph.TypedCSR(ei.to(DEV), None, n)
+    rel = [ops.Rel(csr.fwd.rowptr[0], csr.fwd.col, x, out_col=f)]
+    plain = torch.empty((n, 2 * f), device=DEV)
+    ops.gather_reduce(rel, plain, f, mean=True, concat=True, copy=x, copy_col=0)
+    pair = torch.empty((2, n, 2 * f), device=DEV)
+    ops.gather_reduce(rel, pair[0], f, mean=True, concat=True, copy=x, copy_col=0, out_lo=pair[1])
+    want = linalg.split(plain)
+    assert torch.equal(pair[0], want.hi) and torch.equal(pair[1], want.lo)
