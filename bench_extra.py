@@ -1,0 +1,178 @@
+#!/usr/bin/env python
+"""Secondary measurements for the other BASELINE.json configs (not the driver's bench contract; see bench.py).
+
+    python bench_extra.py [--out profiles/extra.json]
+
+* degree sweep (config 5): agnn_gather_reduce on E = 2^22 edges, F = 256 fp32, mean in-degree 1..128,
+  uniform and Zipf(1.2) destination distributions, random sources over a matrix larger than L2 --
+  achieved algorithmic GB/s vs the measured HBM copy peak;
+* HGT attention kernels (config 3): forward / bwd_dst / bwd_src on the config-1 graph, fp32 and bf16;
+* full-score inference (config 5): 200 000-note score: GPU graph build -> CSR -> HybridGNN forward;
+* in-tree MetricalGNN 4L/512, 64 x 500 notes (config 4): forward + backward step time.
+Every timing: CUDA events on the launching stream, 3 warm-up + 10 timed runs, L2 flushed between runs.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from analysisgnn_b200 import graph, ops, scoregraph, synth  # noqa: E402
+from analysisgnn_b200 import nn as ann  # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.isfile(p) else 6650.0
+
+
+_flush = None
+
+
+def timeit(fn, n=10, warm=3):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=DEV)
+    for _ in range(warm):
+        fn()
+    ms = []
+    for _ in range(n):
+        _flush.fill_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return float(np.median(ms))
+
+
+def degree_sweep():
+    out, pk = [], peak()
+    e, f = 1 << 22, 256
+    rng = np.random.default_rng(0)
+    for dist in ("uniform", "zipf1.2"):
+        for deg in (1, 2, 4, 8, 16, 32, 64, 128):
+            n = e // deg
+            n_src = max(n, 1 << 18)                                   # >= 256 MB of source rows: not L2-resident
+            if dist == "uniform":
+                dst = rng.integers(0, n, e)
+            else:
+                dst = np.minimum(rng.zipf(1.2, e) - 1, n - 1)
+            src = rng.integers(0, n_src, e)
+            ei = torch.as_tensor(np.stack((dst, src)), dtype=torch.long, device=DEV)
+            csr = graph.TypedCSR(ei, None, n, n_cols=n_src)
+            x = torch.randn(n_src, f, device=DEV)
+            y = torch.empty(n, f, device=DEV)
+            rel = [ops.Rel(csr.fwd.rowptr[0], csr.fwd.col, x, n_edges=e)]
+            ms = timeit(lambda: ops.gather_reduce(rel, y, f, mean=True, concat=True))
+            nbytes = ops.gather_bytes(rel, n, f, 4, True, False, False)
+            out.append({"dist": dist, "mean_in_degree": deg, "rows": n, "ms": ms, "algorithmic_bytes": nbytes,
+                        "achieved_gbs": nbytes / ms / 1e6, "frac_of_measured_peak": nbytes / ms / 1e6 / pk})
+            del csr, x, y, ei
+    return out
+
+
+def hgt_kernels():
+    b = synth.hetero_batch(100, 500, 0, add_beats=False, add_measures=False)
+    res, pk = [], peak()
+    heads, d = 4, 64
+    n = b["batch_size"]
+    ei = {k: v.to(DEV) for k, v in b["edge_index_dict"].items()}
+    csr = graph.hetero_csr(ei, {"note": n})
+    ets = list(ei.keys())
+    e_tot = sum(v.shape[1] for v in ei.values())
+    for dtype in (torch.float32, torch.bfloat16):
+        eb = 4 if dtype == torch.float32 else 2
+        q = torch.randn(n, heads * d, device=DEV).to(dtype).requires_grad_(True)
+        ks = [torch.randn(n, heads * d, device=DEV).to(dtype).requires_grad_(True) for _ in ets]
+        vs = [torch.randn(n, heads * d, device=DEV).to(dtype).requires_grad_(True) for _ in ets]
+        ps = torch.ones(len(ets), heads, device=DEV) / 8.0
+        fw = [csr.fwd[et] for et in ets]
+        bw = [csr.bwd[et] for et in ets]
+        f_ms = timeit(lambda: ops.hgt_attention(q.detach(), [k.detach() for k in ks], [v.detach() for v in vs], ps, fw, bw, heads))
+        out = ops.hgt_attention(q, ks, vs, ps, fw, bw, heads)
+        g = torch.randn_like(out)
+        b_ms = timeit(lambda: torch.autograd.grad(out, [q] + ks + vs, g, retain_graph=True))
+        row = heads * d * eb
+        f_bytes = e_tot * (2 * row + 4) + n * (2 * row + 8 * heads)
+        b_bytes = e_tot * (2 * row + 4) + n * (4 * row + 12 * heads) + e_tot * (2 * row + 4 + 12 * heads) + \
+            len(ets) * n * 4 * row
+        res.append({"dtype": str(dtype).split(".")[1], "nodes": n, "edges": e_tot, "relations": len(ets),
+                    "fwd_ms": f_ms, "fwd_gbs": f_bytes / f_ms / 1e6, "fwd_frac": f_bytes / f_ms / 1e6 / pk,
+                    "bwd_ms": b_ms, "bwd_gbs": b_bytes / b_ms / 1e6, "bwd_frac": b_bytes / b_ms / 1e6 / pk})
+    return res
+
+
+def full_score_inference():
+    na = synth.synth_note_array(200_000, 5, 4)
+    build_ms = timeit(lambda: scoregraph.score_graph_edges(na, DEV), n=5, warm=1)
+    edges, _ = scoregraph.score_graph_edges(na, DEV)
+    names = ["onset", "consecutive", "during", "rest"]
+    ei = {("note", nm, "note"): edges[:2, edges[2] == k].contiguous() for k, nm in enumerate(names)}
+    for k, nm in enumerate(names[1:], 1):
+        ei[("note", nm + "_rev", "note")] = ei[("note", nm, "note")].flip(0).contiguous()
+    torch.manual_seed(0)
+    meta = (["note"], list(ei.keys()))
+    net = ann.HybridGNN(meta, 256, 256, 3, dropout=0.0).to(DEV).eval()
+    x = {"note": torch.randn(200_000, 256, device=DEV)}
+    batch = {"note": torch.zeros(200_000, dtype=torch.long, device=DEV)}
+
+    def fwd():
+        graph.clear_cache()
+        with torch.no_grad():
+            return net.gnn(x, ei)
+
+    gnn_ms = timeit(fwd, n=5, warm=2)
+    return {"notes": 200_000, "edges_fwd": int(edges.shape[1]), "edges_with_rev": int(sum(v.shape[1] for v in ei.values())),
+            "graph_build_ms_incl_h2d": build_ms, "csr_plus_sage_stack_3x256_fwd_ms": gnn_ms,
+            "nodes_per_s_message_passing": 200_000 / gnn_ms * 1e3}
+
+
+def metrical_gnn_step():
+    b = synth.intree_batch(64, 500, 0, in_features=64, metrical=True)
+    torch.manual_seed(0)
+    net = ann.MetricalGNN(64, 512, 512, b["etypes"], num_layers=4, dropout=0.3, metrical=True).to(DEV)
+    net.train()
+    args = [b[k].to(DEV) for k in ("edge_index", "edge_type", "beat_nodes", "measure_nodes", "beat_edges", "measure_edges")]
+    kw = {k: b[k].to(DEV) for k in ("beat_lengths", "measure_lengths")}
+    x = b["x"].to(DEV)
+
+    def step():
+        graph.clear_cache()
+        net.zero_grad(set_to_none=True)
+        net(x, *args, **kw).square().mean().backward()
+
+    ms = timeit(step, n=5, warm=2)
+    n = x.shape[0]
+    return {"nodes": n, "edges": int(b["edge_index"].shape[1]), "params": sum(p.numel() for p in net.parameters()),
+            "fwd_bwd_ms": ms, "nodes_per_s": n / ms * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "extra.json"))
+    args = ap.parse_args()
+    res = {"hbm_peak_gbs": peak(), "degree_sweep": degree_sweep(), "hgt_attention": hgt_kernels(),
+           "full_score_inference": full_score_inference(), "metrical_gnn_4L512": metrical_gnn_step()}
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as fh:
+        json.dump(res, fh, indent=1)
+    for r in res["degree_sweep"]:
+        print(f"sweep {r['dist']:8s} deg {r['mean_in_degree']:4d}: {r['ms']:.3f} ms {r['achieved_gbs']:.0f} GB/s "
+              f"({r['frac_of_measured_peak']:.2f})")
+    for r in res["hgt_attention"]:
+        print("hgt", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()})
+    print("full-score", res["full_score_inference"])
+    print("metricalgnn", res["metrical_gnn_4L512"])
+
+
+if __name__ == "__main__":
+    main()
