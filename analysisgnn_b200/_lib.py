@@ -22,6 +22,7 @@ F32, BF16 = 0, 1
 SCALE_NONE, SCALE_MEAN = 0, 1
 COMBINE_CONCAT, COMBINE_SUM = 0, 1
 REL_IDENTITY_IF_EMPTY = 1
+HEAVY_ROW, HEAVY_CHUNK = 4096, 2048
 GEMM_TF32X3, GEMM_TF32, GEMM_BF16 = 0, 1, 2
 K_MAJOR, MN_MAJOR = 0, 1
 GEMM_RELU, GEMM_ACCUMULATE, GEMM_OUT_BF16 = 1, 2, 4
@@ -34,12 +35,14 @@ class AgnnError(RuntimeError):
 class Coo(C.Structure):
     _fields_ = [("row", C.c_void_p), ("col", C.c_void_p), ("etype", C.c_void_p), ("n_edges", C.c_int64),
                 ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("n_rel", C.c_int32), ("reserved", C.c_int32),
-                ("rowptr_off", C.c_int64), ("edge_off", C.c_int64)]
+                ("rowptr_off", C.c_int64), ("edge_off", C.c_int64), ("heavy_off", C.c_int64), ("count_off", C.c_int64),
+                ("heavy_cap", C.c_int64)]
 
 
 class Rel(C.Structure):
     _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("src", C.c_void_p), ("ld_src", C.c_int64),
-                ("nbr_deg_rowptr", C.c_void_p), ("out_col", C.c_int32), ("flags", C.c_int32)]
+                ("nbr_deg_rowptr", C.c_void_p), ("out_col", C.c_int32), ("flags", C.c_int32),
+                ("heavy_rows", C.c_void_p), ("n_heavy", C.c_void_p), ("heavy_cap", C.c_int64)]
 
 
 class HgtRel(C.Structure):
@@ -58,10 +61,11 @@ _PROTOTYPES = {
     "agnn_last_error": (C.c_char_p, []),
     "agnn_csr_build_workspace": (C.c_size_t, [C.c_int, C.POINTER(Coo)]),
     "agnn_csr_build": (C.c_int, [C.c_int, C.POINTER(Coo), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "agnn_gather_reduce": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Rel),
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
-                                     C.c_int64, C.c_void_p, C.c_void_p]),
+                                     C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "agnn_gather_heavy_workspace": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "agnn_rowscale_sum": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.POINTER(Rel), C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "agnn_hgt_attn_fwd": (C.c_int, [C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HgtRel), C.c_void_p,

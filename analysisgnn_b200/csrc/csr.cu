@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(kThreads) scan_add_kernel(const __grid_constan
 // thread per key: restore input order inside the row, emit col
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constant__ SegTable tab,
                                                              const int32_t* rowptr, int32_t* col, int32_t* perm,
-                                                             int32_t* long_count, int64_t* long_list) {
+                                                             int32_t* long_count, int64_t* long_list,
+                                                             int32_t* heavy, int32_t* n_heavy) {
   const int s = find_seg(tab.key_tile_start, tab.n_seg, blockIdx.x);
   const agnn_coo_t& g = tab.seg[s];
   const int64_t base = (int64_t)(blockIdx.x - tab.key_tile_start[s]) * kKeysPerTile;
@@ -178,6 +179,11 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constan
     const int beg = rowptr[g.rowptr_off + k], end = rowptr[g.rowptr_off + k + 1];
     const int deg = end - beg;
     if (deg == 0) continue;
+    if (deg >= AGNN_HEAVY_ROW && heavy && n_heavy && g.heavy_cap > 0) {
+      const int r = (int)(k / (g.n_rows + 1)), row = (int)(k % (g.n_rows + 1));
+      const int slot = atomicAdd(&n_heavy[g.count_off + r], 1);
+      if (slot < g.heavy_cap) heavy[g.heavy_off + (int64_t)r * g.heavy_cap + slot] = row;
+    }
     if (deg > kShortRow) {
       const int slot = atomicAdd(long_count, 1);
       long_list[slot] = ((int64_t)s << 40) | k;
@@ -307,7 +313,8 @@ extern "C" size_t agnn_csr_build_workspace(int n_seg, const agnn_coo_t* segs) {
 }
 
 extern "C" int agnn_csr_build(int n_seg, const agnn_coo_t* segs, int32_t* rowptr, int32_t* col, int32_t* perm,
-                              int32_t* status, void* workspace, size_t workspace_bytes, agnn_stream_t stream_) {
+                              int32_t* status, int32_t* heavy, int32_t* n_heavy, void* workspace,
+                              size_t workspace_bytes, agnn_stream_t stream_) {
   SegTable tab;
   Layout lay;
   int rc = make_tables(n_seg, segs, tab, lay, true);
@@ -325,6 +332,12 @@ extern "C" int agnn_csr_build(int n_seg, const agnn_coo_t* segs, int32_t* rowptr
   const int key_tiles = tab.key_tile_start[n_seg], edge_blks = tab.edge_blk_start[n_seg];
 
   if (cudaMemsetAsync(long_count, 0, 4, stream) != cudaSuccess) return check_launch("csr_build memset");
+  if (heavy && n_heavy) {
+    for (int s = 0; s < n_seg; ++s)
+      if (segs[s].heavy_cap > 0 &&
+          cudaMemsetAsync(n_heavy + segs[s].count_off, 0, (size_t)segs[s].n_rel * 4, stream) != cudaSuccess)
+        return check_launch("csr_build memset");
+  }
   zero_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, cursor);
   if (edge_blks > 0) edge_kernel<false><<<edge_blks, kThreads, 0, stream>>>(tab, rowptr, cursor, perm, status);
   scan_tile_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, tile_sums);
@@ -333,7 +346,7 @@ extern "C" int agnn_csr_build(int n_seg, const agnn_coo_t* segs, int32_t* rowptr
   if (edge_blks > 0) {
     if (!col || !perm) return fail(AGNN_ERR_ARG, "csr_build: null col/perm with edges present");
     edge_kernel<true><<<edge_blks, kThreads, 0, stream>>>(tab, rowptr, cursor, perm, status);
-    finalize_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list);
+    finalize_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list, heavy, n_heavy);
     long_rows_kernel<<<kNumSM * 2, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list);
   }
   return check_launch("csr_build");

@@ -32,7 +32,17 @@ struct GatherParams {
   void* out;
   int64_t ld_out;
   void* out_lo;  // optional (fp32 only): out receives rna_tf32(y), out_lo rna_tf32(y - out) -- agnn_gemm operands
+  float* heavy_ws;      // optional: partial rows of the heavy-row path, [max_chunks][n_feat]
+  int64_t max_chunks;
 };
+
+constexpr int kHeavyRow = AGNN_HEAVY_ROW;
+constexpr int kHeavyChunk = AGNN_HEAVY_CHUNK;
+
+// is (relation, row) handled by the heavy-row kernels instead of the row's own warp?
+__device__ __forceinline__ bool is_heavy(const GatherParams& p, const agnn_rel_t& R, int deg) {
+  return p.heavy_ws && R.heavy_rows && deg >= kHeavyRow;
+}
 
 // store one 16-byte vector, optionally as the TF32 hi / lo pair the tensor-core GEMM consumes
 template <typename T>
@@ -102,6 +112,7 @@ __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_co
         }
       } else {
         const int beg = __ldg(R.rowptr + row), end = __ldg(R.rowptr + row + 1);
+        if (is_heavy(p, R, end - beg)) continue;   // this slice / contribution comes from the heavy-row kernels
         for (int k = beg; k < end; k += kUnroll) {
           int idx[kUnroll];
           float w[kUnroll];
@@ -196,6 +207,180 @@ __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_co
   }
 }
 
+// ---- heavy rows: split across warps -------------------------------------------------------------
+// Chunk numbering: relations in order, their heavy entries in list order, kHeavyChunk edges per chunk.
+// Every warp walks the (short) heavy lists to find the chunks it owns; partial sums go to heavy_ws and
+// are combined per row in chunk order by the second kernel (deterministic, no atomics).
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads) gather_heavy_partial_kernel(const __grid_constant__ GatherParams p) {
+  using VT = Vec16<T>;
+  constexpr int E = VT::E;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
+  const int F = p.n_feat;
+  int64_t g = 0;
+  for (int r = 0; r < p.n_rel; ++r) {
+    const agnn_rel_t& R = p.rel[r];
+    if (!R.heavy_rows) continue;
+    const int nh = (int)min((int64_t)__ldg(R.n_heavy), R.heavy_cap);
+    const T* src = static_cast<const T*>(R.src);
+    for (int h = 0; h < nh; ++h) {
+      const int row = __ldg(R.heavy_rows + h);
+      const int beg = __ldg(R.rowptr + row), end = __ldg(R.rowptr + row + 1);
+      const int chunks = (end - beg + kHeavyChunk - 1) / kHeavyChunk;
+      for (int c = 0; c < chunks; ++c, ++g) {
+        if (g % n_warps != warp_id || g >= p.max_chunks) continue;
+        float acc[V][E];
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[v][e] = 0.f;
+        const int k0 = beg + c * kHeavyChunk, k1 = min(k0 + kHeavyChunk, end);
+        for (int k = k0; k < k1; k += kUnroll) {
+          int idx[kUnroll];
+          float w[kUnroll];
+          float x[kUnroll][V][E];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            idx[u] = (k + u < k1) ? __ldg(R.col + k + u) : -1;
+            w[u] = 1.f;
+            if (idx[u] >= 0 && R.nbr_deg_rowptr) {
+              const int d = __ldg(R.nbr_deg_rowptr + idx[u] + 1) - __ldg(R.nbr_deg_rowptr + idx[u]);
+              w[u] = 1.f / (float)max(d, 1);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (idx[u] >= 0) {
+              const T* rp = src + (int64_t)idx[u] * R.ld_src;
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                const int cc = (v * 32 + lane) * E;
+                if (cc < F) VT::load_nc(rp + cc, x[u][v]);
+              }
+            }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (idx[u] >= 0) {
+#pragma unroll
+              for (int v = 0; v < V; ++v)
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[v][e] = fmaf(w[u], x[u][v][e], acc[v][e]);
+            }
+        }
+        float* wp = p.heavy_ws + g * F;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int cc = (v * 32 + lane) * E;
+          if (cc < F) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) wp[cc + e] = acc[v][e];
+          }
+        }
+      }
+    }
+  }
+}
+
+// one warp per heavy (relation, row): sum the chunk partials in order and finish the row like the main kernel
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __grid_constant__ GatherParams p) {
+  using VT = Vec16<T>;
+  constexpr int E = VT::E;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
+  const int F = p.n_feat;
+  T* const out = static_cast<T*>(p.out);
+  T* const out_lo = static_cast<T*>(p.out_lo);
+  int64_t g = 0, item = 0;
+  for (int r = 0; r < p.n_rel; ++r) {
+    const agnn_rel_t& R = p.rel[r];
+    if (!R.heavy_rows) continue;
+    const int nh = (int)min((int64_t)__ldg(R.n_heavy), R.heavy_cap);
+    for (int h = 0; h < nh; ++h, ++item) {
+      const int row = __ldg(R.heavy_rows + h);
+      const int beg = __ldg(R.rowptr + row), end = __ldg(R.rowptr + row + 1);
+      const int chunks = (end - beg + kHeavyChunk - 1) / kHeavyChunk;
+      const int64_t g0 = g;
+      g += chunks;
+      if (item % n_warps != warp_id || g > p.max_chunks) continue;
+      float acc[V][E];
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[v][e] = 0.f;
+      for (int c = 0; c < chunks; ++c) {
+        const float* wp = p.heavy_ws + (g0 + c) * F;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int cc = (v * 32 + lane) * E;
+          if (cc < F) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[v][e] += wp[cc + e];
+          }
+        }
+      }
+      const float s = p.scale == AGNN_SCALE_MEAN ? 1.f / (float)max(end - beg, 1) : 1.f;
+      if (p.combine == AGNN_COMBINE_CONCAT) {
+        const int64_t off = (int64_t)row * p.ld_out + R.out_col;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int cc = (v * 32 + lane) * E;
+          if (cc < F) {
+            float o[E];
+            if (p.self_add) {
+              float sv[E];
+              VT::load_nc(static_cast<const T*>(p.self_add) + (int64_t)row * p.ld_self + cc, sv);
+#pragma unroll
+              for (int e = 0; e < E; ++e) acc[v][e] += sv[e];
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) o[e] = acc[v][e] * s;
+            store_split<T>(out + off + cc, out_lo ? out_lo + off + cc : nullptr, o);
+          }
+        }
+      } else {
+        // COMBINE_SUM: the main kernel wrote self + the light relations; add this relation's share.  Several
+        // heavy relations may hit the same row: entries of one row are handled by different warps, so each adds
+        // with its own read-modify-write only when it is the row's single heavy relation; otherwise atomics.
+        const int64_t off = (int64_t)row * p.ld_out + p.rel[0].out_col;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int cc = (v * 32 + lane) * E;
+          if (cc < F) {
+            if constexpr (sizeof(T) == 4) {
+              if (!out_lo) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) atomicAdd(reinterpret_cast<float*>(out) + off + cc + e, acc[v][e] * s);
+                continue;
+              }
+            }
+            float cur[E], lo[E];
+            VT::load_nc(out + off + cc, cur);
+            if (out_lo) {
+              VT::load_nc(out_lo + off + cc, lo);
+#pragma unroll
+              for (int e = 0; e < E; ++e) cur[e] += lo[e];
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) cur[e] = fmaf(acc[v][e], s, cur[e]);
+            store_split<T>(out + off + cc, out_lo ? out_lo + off + cc : nullptr, cur);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int V>
+int launch_heavy(const GatherParams& p, cudaStream_t stream) {
+  gather_heavy_partial_kernel<T, V><<<kNumSM * 4, kThreads, 0, stream>>>(p);
+  gather_heavy_combine_kernel<T, V><<<kNumSM, kThreads, 0, stream>>>(p);
+  return check_launch("gather_reduce (heavy rows)");
+}
+
 template <typename T, int LANES, int V>
 int launch(const GatherParams& p, cudaStream_t stream) {
   constexpr int kRowsPerBlock = kThreads / LANES;
@@ -203,6 +388,7 @@ int launch(const GatherParams& p, cudaStream_t stream) {
   const int64_t cap = (int64_t)kNumSM * 8;  // 8 resident CTAs/SM; grid-stride beyond that
   if (blocks > cap) blocks = cap;
   gather_reduce_kernel<T, LANES, V><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  if (p.heavy_ws) return launch_heavy<T, V>(p, stream);
   return check_launch("gather_reduce");
 }
 
@@ -272,7 +458,7 @@ using namespace agnn;
 extern "C" int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
                                   const agnn_rel_t* rels, const void* self_add, int64_t ld_self, const void* copy,
                                   int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out, void* out_lo,
-                                  agnn_stream_t stream) {
+                                  void* heavy_workspace, size_t heavy_workspace_bytes, agnn_stream_t stream) {
   if (n_rows < 0 || n_feat <= 0 || n_rel < 1 || n_rel > AGNN_MAX_REL || !rels || !out)
     return fail(AGNN_ERR_ARG, "gather_reduce: bad sizes (n_rows=%d n_feat=%d n_rel=%d)", n_rows, n_feat, n_rel);
   if (dtype != AGNN_F32 && dtype != AGNN_BF16) return fail(AGNN_ERR_ARG, "gather_reduce: dtype %d", dtype);
@@ -287,6 +473,15 @@ extern "C" int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int
   p.copy_col = copy_col;
   p.self_add = self_add; p.ld_self = ld_self; p.copy = copy; p.ld_copy = ld_copy; p.out = out; p.ld_out = ld_out;
   p.out_lo = out_lo;
+  p.heavy_ws = nullptr;
+  p.max_chunks = 0;
+  bool any_heavy = false;
+  for (int r = 0; r < n_rel; ++r) any_heavy = any_heavy || (rels[r].heavy_rows && rels[r].n_heavy && rels[r].heavy_cap > 0);
+  if (any_heavy && heavy_workspace && heavy_workspace_bytes >= (size_t)n_feat * 4) {
+    if (!aligned16(heavy_workspace)) return fail(AGNN_ERR_ARG, "gather_reduce: heavy workspace must be 16-byte aligned");
+    p.heavy_ws = static_cast<float*>(heavy_workspace);
+    p.max_chunks = (int64_t)(heavy_workspace_bytes / ((size_t)n_feat * 4));
+  }
   if (out_lo && (dtype != AGNN_F32 || !aligned16(out_lo)))
     return fail(AGNN_ERR_ARG, "gather_reduce: the TF32 hi/lo output needs fp32 and a 16-byte aligned out_lo");
   int rc;
@@ -302,6 +497,11 @@ extern "C" int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int
   }
   cudaStream_t st = (cudaStream_t)stream;
   return dtype == AGNN_F32 ? dispatch<float>(p, st) : dispatch<__nv_bfloat16>(p, st);
+}
+
+extern "C" size_t agnn_gather_heavy_workspace(int64_t total_edges, int64_t total_heavy_cap, int32_t n_feat) {
+  if (total_edges < 0 || total_heavy_cap < 0 || n_feat <= 0) return 0;
+  return (size_t)(total_edges / kHeavyChunk + total_heavy_cap + 1) * (size_t)n_feat * sizeof(float);
 }
 
 extern "C" int agnn_rowscale_sum(int32_t n_rows, int32_t n_feat, int dtype, int n_rel, const agnn_rel_t* rels,

@@ -240,7 +240,7 @@ extern "C" int agnn_score_graph_build(int32_t n_scores, const int32_t* score_ptr
   memset(&seg, 0, sizeof(seg));
   seg.row = p.key; seg.col = p.idx; seg.etype = nullptr;
   seg.n_edges = n_notes; seg.n_rows = (int32_t)key_slots; seg.n_cols = n_notes; seg.n_rel = 1;
-  int rc = agnn_csr_build(1, &seg, rowptr, col, perm, status, ws + l.off_csr, l.csr_bytes, stream_);
+  int rc = agnn_csr_build(1, &seg, rowptr, col, perm, status, nullptr, nullptr, ws + l.off_csr, l.csr_bytes, stream_);
   if (rc) return rc;
   const int64_t emitters = (int64_t)n_notes + key_slots + 1;
   const int blocks = (int)ceil_div(emitters, kThreads);

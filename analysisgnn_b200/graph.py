@@ -56,11 +56,13 @@ class CSR:
     """Result for one segment: ``rowptr`` [n_rel, n_rows+1] (absolute positions in
     ``col`` / ``perm``), ``col`` [E] gathered-side ids, ``perm`` [E] input positions."""
 
-    __slots__ = ("rowptr", "col", "perm", "n_rows", "n_cols", "n_rel", "n_edges")
+    __slots__ = ("rowptr", "col", "perm", "n_rows", "n_cols", "n_rel", "n_edges", "heavy", "n_heavy", "heavy_cap")
 
-    def __init__(self, rowptr, col, perm, seg: Segment):
+    def __init__(self, rowptr, col, perm, seg: Segment, heavy=None, n_heavy=None, heavy_cap=0):
         self.rowptr, self.col, self.perm = rowptr, col, perm
         self.n_rows, self.n_cols, self.n_rel, self.n_edges = seg.n_rows, seg.n_cols, seg.n_rel, seg.n_edges
+        # rows with >= HEAVY_ROW entries, per relation: [n_rel, heavy_cap] row ids + [n_rel] counts (device)
+        self.heavy, self.n_heavy, self.heavy_cap = heavy, n_heavy, heavy_cap
 
 
 def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) -> List[CSR]:
@@ -77,8 +79,11 @@ def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) 
     col = torch.empty(max(edge_total, 1), dtype=torch.int32, device=device)
     perm = torch.empty(max(edge_total, 1), dtype=torch.int32, device=device)
     status = torch.zeros(1, dtype=torch.int32, device=device)
+    caps = [s.n_edges // _lib.HEAVY_ROW + 1 for s in segments]
+    heavy = torch.empty(sum(s.n_rel * c for s, c in zip(segments, caps)), dtype=torch.int32, device=device)
+    n_heavy = torch.empty(sum(s.n_rel for s in segments), dtype=torch.int32, device=device)
     stream = torch.cuda.current_stream(device).cuda_stream
-    out, k_off, e_off = [], 0, 0
+    out, k_off, e_off, h_off, c_off = [], 0, 0, 0, 0
     for lo in range(0, len(segments), _lib.MAX_SEG):
         chunk = segments[lo:lo + _lib.MAX_SEG]
         arr = (_lib.Coo * len(chunk))()
@@ -88,17 +93,23 @@ def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) 
             arr[i].etype = s.etype.data_ptr() if (s.etype is not None and s.n_edges) else None
             arr[i].n_edges, arr[i].n_rows, arr[i].n_cols, arr[i].n_rel = s.n_edges, s.n_rows, s.n_cols, s.n_rel
             arr[i].rowptr_off, arr[i].edge_off = k_off, e_off
+            cap = caps[lo + i]
+            arr[i].heavy_off, arr[i].count_off, arr[i].heavy_cap = h_off, c_off, cap
             keys = s.n_rel * (s.n_rows + 1)
             out.append(CSR(rowptr[k_off:k_off + keys].view(s.n_rel, s.n_rows + 1), col[e_off:e_off + s.n_edges],
-                           perm[e_off:e_off + s.n_edges], s))
+                           perm[e_off:e_off + s.n_edges], s, heavy[h_off:h_off + s.n_rel * cap].view(s.n_rel, cap),
+                           n_heavy[c_off:c_off + s.n_rel], cap))
             k_off += keys
             e_off += s.n_edges
+            h_off += s.n_rel * cap
+            c_off += s.n_rel
         ws_bytes = lib.agnn_csr_build_workspace(len(chunk), arr)
         if ws_bytes == 0:
             raise _lib.AgnnError("agnn_csr_build_workspace: " + lib.agnn_last_error().decode())
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
         _lib.check(lib.agnn_csr_build(len(chunk), arr, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
-                                      status.data_ptr(), ws.data_ptr(), ws_bytes, stream), "agnn_csr_build")
+                                      status.data_ptr(), heavy.data_ptr(), n_heavy.data_ptr(), ws.data_ptr(), ws_bytes,
+                                      stream), "agnn_csr_build")
         _lib.count_launches(8 if any(s.n_edges for s in chunk) else 4)
     if validate and int(status.item()) != 0:
         raise ValueError("edge_index contains node ids outside [0, num_nodes)")

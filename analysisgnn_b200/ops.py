@@ -41,7 +41,9 @@ class Rel:
     out_col: int = 0
     nbr_deg_rowptr: Optional[torch.Tensor] = None
     flags: int = 0
-    n_edges: Optional[int] = None            # edges of this relation (bench accounting only)
+    n_edges: Optional[int] = None            # edges of this relation (accounting, heavy-row workspace size)
+    heavy_rows: Optional[torch.Tensor] = None    # rows with >= HEAVY_ROW entries (CSR.heavy[k]) ...
+    n_heavy: Optional[torch.Tensor] = None       # ... and their device-side count (CSR.n_heavy[k:k+1])
 
 
 def _pack(rels: Sequence[Rel], n_feat: int, dtype) -> "ctypes.Array":
@@ -59,7 +61,16 @@ def _pack(rels: Sequence[Rel], n_feat: int, dtype) -> "ctypes.Array":
         arr[i].nbr_deg_rowptr = r.nbr_deg_rowptr.data_ptr() if r.nbr_deg_rowptr is not None else None
         arr[i].out_col = int(r.out_col)
         arr[i].flags = int(r.flags)
+        if r.heavy_rows is not None and r.n_heavy is not None:
+            arr[i].heavy_rows, arr[i].n_heavy = r.heavy_rows.data_ptr(), r.n_heavy.data_ptr()
+            arr[i].heavy_cap = int(r.heavy_rows.numel())
     return arr
+
+
+def rel_of(csr: CSR, k: int, src: torch.Tensor, **kw) -> "Rel":
+    """Relation ``k`` of a CSR as a gather operand, heavy-row list included."""
+    return Rel(csr.rowptr[k], csr.col, src, heavy_rows=csr.heavy[k] if csr.heavy is not None else None,
+               n_heavy=csr.n_heavy[k:k + 1] if csr.n_heavy is not None else None, **kw)
 
 
 class KernelTimer:
@@ -124,6 +135,14 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
     sa = _rows2d(self_add, "self_add") if self_add is not None else None
     cp = _rows2d(copy, "copy") if copy is not None else None
     stream = torch.cuda.current_stream(out.device).cuda_stream
+    ws, ws_bytes = None, 0
+    if any(r.heavy_rows is not None for r in rels) and all(r.n_edges is not None for r in rels):
+        # rows of >= HEAVY_ROW entries (hubs) are split across warps; a relation below that size cannot have one
+        if max(int(r.n_edges) for r in rels) >= _lib.HEAVY_ROW:
+            ws_bytes = _lib.lib().agnn_gather_heavy_workspace(
+                sum(int(r.n_edges) for r in rels),
+                sum(int(r.heavy_rows.numel()) for r in rels if r.heavy_rows is not None), n_feat)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
 
     def run():
         _lib.check(_lib.lib().agnn_gather_reduce(
@@ -131,8 +150,8 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
             _lib.COMBINE_CONCAT if concat else _lib.COMBINE_SUM, len(rels), arr,
             sa.data_ptr() if sa is not None else None, sa.stride(0) if sa is not None else 0,
             cp.data_ptr() if cp is not None else None, cp.stride(0) if cp is not None else 0, int(copy_col),
-            out.data_ptr(), out.stride(0), out_lo.data_ptr() if out_lo is not None else None, stream),
-            "agnn_gather_reduce")
+            out.data_ptr(), out.stride(0), out_lo.data_ptr() if out_lo is not None else None,
+            ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gather_reduce")
 
     if timer is not None and all(r.n_edges is not None for r in rels):
         nbytes = gather_bytes(rels, n_rows, n_feat, out.element_size(), concat, sa is not None, cp is not None)
@@ -141,7 +160,7 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
         timer.launch("gather_reduce", nbytes, out.device, run)
     else:
         run()
-    _lib.count_launches(1)
+    _lib.count_launches(3 if ws is not None else 1)
     return out
 
 
@@ -178,7 +197,7 @@ class _SegmentReduce(torch.autograd.Function):
         f = src.shape[1]
         out = torch.empty((csr.n_rows, f), dtype=src.dtype, device=src.device)
         sa = self_add.contiguous() if self_add is not None else None
-        gather_reduce([Rel(csr.fwd.rowptr[0], csr.fwd.col, src, n_edges=csr.n_edges)], out, f, mean=mean, concat=True,
+        gather_reduce([rel_of(csr.fwd, 0, src, n_edges=csr.n_edges)], out, f, mean=mean, concat=True,
                       self_add=sa)
         ctx.csr, ctx.mean, ctx.has_self = csr, mean, self_add is not None
         return out
@@ -189,7 +208,7 @@ class _SegmentReduce(torch.autograd.Function):
         g = g.contiguous()
         d_src = torch.empty((csr.n_cols, f), dtype=g.dtype, device=g.device)
         deg = csr.fwd.rowptr[0] if ctx.mean else None
-        gather_reduce([Rel(csr.bwd.rowptr[0], csr.bwd.col, g, nbr_deg_rowptr=deg, n_edges=csr.n_edges)], d_src, f, mean=False,
+        gather_reduce([rel_of(csr.bwd, 0, g, nbr_deg_rowptr=deg, n_edges=csr.n_edges)], d_src, f, mean=False,
                       concat=True)
         d_self = None
         if ctx.has_self:
@@ -251,8 +270,8 @@ class _IntreeSageLayer(torch.autograd.Function):
         r = csr.n_rel
         h = linalg.linear(x, wn_cat, bn_cat)                                     # [N, R*F]
         a_hi, a_lo = _operand_buffers(n, (r + 1) * f, x)
-        rels = [Rel(csr.fwd.rowptr[k], csr.fwd.col, h[:, k * f:(k + 1) * f], out_col=(k + 1) * f,
-                    flags=_lib.REL_IDENTITY_IF_EMPTY, n_edges=csr.n_edges if k == 0 else 0) for k in range(r)]
+        rels = [rel_of(csr.fwd, k, h[:, k * f:(k + 1) * f], out_col=(k + 1) * f,
+                       flags=_lib.REL_IDENTITY_IF_EMPTY, n_edges=csr.n_edges if k == 0 else 0) for k in range(r)]
         # the gather writes the GEMM operand directly as a TF32 pair: it feeds the forward and the grad-weight GEMM
         gather_reduce(rels, a_hi, f, mean=True, concat=True, self_add=x, copy=x, copy_col=0, out_lo=a_lo)
         a = _as_operand_pair(a_hi, a_lo)
@@ -273,9 +292,9 @@ class _IntreeSageLayer(torch.autograd.Function):
         dwc = linalg.mm_tn(dz, a) if ctx.needs_input_grad[3] else None
         dbc = colsum(dz_plain) if ctx.has_bias[1] and ctx.needs_input_grad[4] else None
         dh = torch.empty((n, r * f), dtype=x.dtype, device=x.device)
-        rels_t = [Rel(csr.bwd.rowptr[k], csr.bwd.col, da[:, (k + 1) * f:(k + 2) * f], out_col=k * f,
-                      nbr_deg_rowptr=csr.fwd.rowptr[k], flags=_lib.REL_IDENTITY_IF_EMPTY,
-                      n_edges=csr.n_edges if k == 0 else 0) for k in range(r)]
+        rels_t = [rel_of(csr.bwd, k, da[:, (k + 1) * f:(k + 2) * f], out_col=k * f,
+                         nbr_deg_rowptr=csr.fwd.rowptr[k], flags=_lib.REL_IDENTITY_IF_EMPTY,
+                         n_edges=csr.n_edges if k == 0 else 0) for k in range(r)]
         gather_reduce(rels_t, dh, f, mean=False, concat=True)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -322,8 +341,8 @@ class _HeteroSageLayer(torch.autograd.Function):
             f = x_t.shape[1]
             rel_list = plan.incoming[t]
             a_hi, a_lo = _operand_buffers(x_t.shape[0], (len(rel_list) + 1) * f, x_t)
-            rels = [Rel(csr.fwd[et].rowptr[0], csr.fwd[et].col, xs[et[0]], out_col=(k + 1) * f,
-                        n_edges=csr.n_edges[et]) for k, et in enumerate(rel_list)]
+            rels = [rel_of(csr.fwd[et], 0, xs[et[0]], out_col=(k + 1) * f, n_edges=csr.n_edges[et])
+                    for k, et in enumerate(rel_list)]
             gather_reduce(rels, a_hi, f, mean=True, concat=True, copy=x_t, copy_col=0, out_lo=a_lo)
             a = _as_operand_pair(a_hi, a_lo)
             o = linalg.linear(a, wcat, bias, relu=relu)
@@ -365,8 +384,8 @@ class _HeteroSageLayer(torch.autograd.Function):
                 if dst not in da:
                     continue
                 k = plan.incoming[dst].index(et)
-                rels.append(Rel(csr.bwd[et].rowptr[0], csr.bwd[et].col, da[dst][:, (k + 1) * f:(k + 2) * f],
-                                nbr_deg_rowptr=csr.fwd[et].rowptr[0], n_edges=csr.n_edges[et]))
+                rels.append(rel_of(csr.bwd[et], 0, da[dst][:, (k + 1) * f:(k + 2) * f],
+                                   nbr_deg_rowptr=csr.fwd[et].rowptr[0], n_edges=csr.n_edges[et]))
             root = da[s][:, :f] if s in da else None
             if not rels:
                 grads[i] = root.contiguous() if root is not None else None

@@ -76,14 +76,22 @@ typedef struct agnn_coo {
   int32_t reserved;
   int64_t rowptr_off; /* element offset of this segment's [n_rel*(n_rows+1)] block in rowptr */
   int64_t edge_off;   /* element offset of this segment's [n_edges] block in col / perm       */
+  int64_t heavy_off;  /* element offset of this segment's [n_rel][heavy_cap] block in `heavy`  */
+  int64_t count_off;  /* element offset of this segment's [n_rel] counters in `n_heavy`        */
+  int64_t heavy_cap;  /* capacity per relation; n_edges / AGNN_HEAVY_ROW + 1 always suffices   */
 } agnn_coo_t;
+
+/* Rows with at least AGNN_HEAVY_ROW entries are also listed per (segment, relation) in `heavy` (row ids, in no
+ * particular order) with their count in `n_heavy`, when those arrays are given: agnn_gather_reduce splits such
+ * rows across many warps instead of letting one warp walk them alone (hub nodes, Zipf-like degree tails). */
+#define AGNN_HEAVY_ROW 4096
 
 /* bytes of scratch agnn_csr_build needs for these segments (host arithmetic only) */
 size_t agnn_csr_build_workspace(int n_seg, const agnn_coo_t* segs /* host */);
 
 int agnn_csr_build(int n_seg, const agnn_coo_t* segs /* host */, int32_t* rowptr, int32_t* col,
-                   int32_t* perm, int32_t* status, void* workspace, size_t workspace_bytes,
-                   agnn_stream_t stream);
+                   int32_t* perm, int32_t* status, int32_t* heavy /* optional */, int32_t* n_heavy /* optional */,
+                   void* workspace, size_t workspace_bytes, agnn_stream_t stream);
 
 /* ------------------------------------------------------------ gather-reduce
  * Replaces: h[edge_index[1]] + torch_scatter.scatter(..., out=x.clone(),
@@ -117,6 +125,9 @@ typedef struct agnn_rel {
   const int32_t* nbr_deg_rowptr; /* optional [n_src + 1]: neighbour weights     */
   int32_t out_col;
   int32_t flags;
+  const int32_t* heavy_rows; /* optional: rows with >= AGNN_HEAVY_ROW entries (agnn_csr_build) */
+  const int32_t* n_heavy;    /* device counter that goes with heavy_rows                        */
+  int64_t heavy_cap;         /* entries heavy_rows can hold                                     */
 } agnn_rel_t;
 
 #define AGNN_REL_IDENTITY_IF_EMPTY 1
@@ -129,7 +140,13 @@ typedef struct agnn_rel {
 int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
                        const agnn_rel_t* rels /* host */, const void* self_add, int64_t ld_self,
                        const void* copy, int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out,
-                       void* out_lo /* optional */, agnn_stream_t stream);
+                       void* out_lo /* optional */, void* heavy_workspace /* optional */, size_t heavy_workspace_bytes,
+                       agnn_stream_t stream);
+/* Scratch for the heavy-row path of a launch whose relations hold `total_edges` edges and `total_heavy_cap` heavy
+ * slots in all: (total_edges / AGNN_HEAVY_CHUNK + total_heavy_cap) partial rows of n_feat floats.  Relations are
+ * only split when heavy_rows is set AND a workspace is given; otherwise every row is walked by its own warp. */
+#define AGNN_HEAVY_CHUNK 2048
+size_t agnn_gather_heavy_workspace(int64_t total_edges, int64_t total_heavy_cap, int32_t n_feat);
 
 /* out[i, :] = base[i, :] (if given) + sum_r in[i, in_col_r : +F] / max(deg_r(i), 1)
  * -- the gradient of the self term of the mean_self reduction (gnn.py:74 backward).

@@ -38,15 +38,15 @@ def test_python_binding_covers_every_declared_symbol():
 
 def test_version_and_error_text(lib):
     assert lib.agnn_version() >= 100
-    rc = lib.agnn_gather_reduce(4, 0, 0, 0, 0, 1, None, None, 0, None, 0, 0, None, 0, None, None)
+    rc = lib.agnn_gather_reduce(4, 0, 0, 0, 0, 1, None, None, 0, None, 0, 0, None, 0, None, None, 0, None)
     assert rc == -1
     assert b"gather_reduce" in lib.agnn_last_error()
 
 
 def test_struct_layouts_match_the_header():
     # agnn_coo_t: 3 pointers + int64 + 4 int32 + 2 int64; agnn_rel_t: 3 pointers + int64 + pointer + 2 int32
-    assert C.sizeof(_lib.Coo) == 3 * 8 + 8 + 4 * 4 + 2 * 8
-    assert C.sizeof(_lib.Rel) == 3 * 8 + 8 + 8 + 2 * 4
+    assert C.sizeof(_lib.Coo) == 3 * 8 + 8 + 4 * 4 + 5 * 8
+    assert C.sizeof(_lib.Rel) == 3 * 8 + 8 + 8 + 2 * 4 + 3 * 8
     assert C.sizeof(_lib.HgtRel) == 6 * 8 + 8 + 2 * 8 + 8 + 2 * 4
 
 

@@ -153,3 +153,32 @@ def test_tf32_pair_output_is_what_the_gemm_consumes():
     ops.gather_reduce(rel, pair[0], f, mean=True, concat=True, copy=x, copy_col=0, out_lo=pair[1])
     want = linalg.split(plain)
     assert torch.equal(pair[0], want.hi) and torch.equal(pair[1], want.lo)
+
+
+@pytest.mark.parametrize("mean", [False, True])
+def test_heavy_rows_are_split_across_warps(mean):
+    """Hub rows (>= 4096 entries) take the multi-warp path: chunk partials + ordered combine.  Same numbers as the
+    plain formulation, deterministic from run to run, forward and backward."""
+    rng = np.random.default_rng(3)
+    n_rows, n_cols, f = 300, 5000, 64
+    row = np.concatenate([np.full(20000, 7), np.full(4096, 11), np.full(4095, 13), rng.integers(0, n_rows, 6000)])
+    rng.shuffle(row)
+    col = rng.integers(0, n_cols, len(row))
+    ei = torch.as_tensor(np.stack((row, col)), dtype=torch.long)
+    src = torch.randn(n_cols, f)
+    base = torch.randn(n_rows, f)
+    g = torch.randn(n_rows, f)
+    s1 = src.clone().requires_grad_(True)
+    want = oi.mean_into_copy(s1[ei[1]], ei[0], base) if mean else oi.sum_into(s1[ei[1]], ei[0], n_rows)
+    want.backward(g)
+    csr = graph.TypedCSR(ei.to(DEV), None, n_rows, n_cols=n_cols)
+    want_heavy = np.flatnonzero(np.bincount(row, minlength=n_rows) >= 4096).tolist()
+    assert 7 in want_heavy and 11 in want_heavy
+    assert sorted(csr.fwd.heavy[0, :int(csr.fwd.n_heavy[0])].tolist()) == want_heavy
+    s2 = src.to(DEV).requires_grad_(True)
+    got = ops.segment_mean_self(s2, base.to(DEV), csr) if mean else ops.segment_sum(s2, csr)
+    got.backward(g.to(DEV))
+    assert_close(got, want, 2 * FP32_REL, "forward")        # 20 000-term sums: order differs from index_add_
+    assert_close(s2.grad, s1.grad, FP32_REL, "d src")
+    again = ops.segment_mean_self(s2, base.to(DEV), csr) if mean else ops.segment_sum(s2, csr)
+    assert torch.equal(got, again)
