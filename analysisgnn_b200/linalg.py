@@ -20,6 +20,7 @@ import torch
 from . import _lib
 
 _BACKEND = os.environ.get("AGNN_GEMM", "tcgen05")
+timer = None      # set to an ops.KernelTimer by bench.py to time every agnn_gemm launch
 
 
 def backend() -> str:
@@ -146,11 +147,18 @@ def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, 
     ws_bytes = lib.agnn_gemm_workspace(prec, m, n, k, split_k)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(lib.agnn_gemm(prec, a_layout, b_layout, m, n, k, oa[0].data_ptr(),
-                             oa[1].data_ptr() if oa[1] is not None else None, oa[0].stride(0), ob[0].data_ptr(),
-                             ob[1].data_ptr() if ob[1] is not None else None, ob[0].stride(0), out.data_ptr(),
-                             out.stride(0), bias.data_ptr() if bias is not None else None, flags, split_k,
-                             ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gemm")
+
+    def run():
+        _lib.check(lib.agnn_gemm(prec, a_layout, b_layout, m, n, k, oa[0].data_ptr(),
+                                 oa[1].data_ptr() if oa[1] is not None else None, oa[0].stride(0), ob[0].data_ptr(),
+                                 ob[1].data_ptr() if ob[1] is not None else None, ob[0].stride(0), out.data_ptr(),
+                                 out.stride(0), bias.data_ptr() if bias is not None else None, flags, split_k,
+                                 ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gemm")
+
+    if timer is not None:                       # bench.py: per-launch CUDA events, algorithmic flops = 2 M N K
+        timer.launch("gemm", 2 * m * n * k, dev, run)
+    else:
+        run()
     _lib.count_launches(2 if split_k > 1 else 1)
     return out
 
