@@ -207,6 +207,124 @@ __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_co
   }
 }
 
+// ---- COMBINE_SUM fast path ------------------------------------------------------------------------
+// The backward gathers (d x_src = self + sum over all outgoing relations) see 1-2 edges in each of ~9
+// relations per row: walking the relations one after another is a chain of ~4 dependent global loads per
+// relation (rowptr, col, neighbour degree, row).  Here the index work is lane-parallel: lane r reads
+// relation r's row extent, a warp scan flattens all (relation, edge) items of the row, lane t resolves item
+// t (column id, neighbour-degree weight, source row address) -- three dependent round trips for up to 32
+// items -- and then the whole warp streams the source rows, four in flight.
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads) gather_sum_kernel(const __grid_constant__ GatherParams p) {
+  using VT = Vec16<T>;
+  constexpr int E = VT::E;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int F = p.n_feat;
+  T* const out = static_cast<T*>(p.out);
+  T* const out_lo = static_cast<T*>(p.out_lo);
+  for (int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < p.n_rows; row += gridDim.x * (kThreads / 32)) {
+    float tot[V][E];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = (v * 32 + lane) * E;
+      if (p.self_add && c < F) {
+        VT::load_nc(static_cast<const T*>(p.self_add) + (int64_t)row * p.ld_self + c, tot[v]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) tot[v][e] = 0.f;
+      }
+    }
+    // lane r < n_rel: extent of relation r's row
+    int beg = 0, deg = 0;
+    if (lane < p.n_rel) {
+      const agnn_rel_t& R = p.rel[lane];
+      beg = __ldg(R.rowptr + row);
+      deg = __ldg(R.rowptr + row + 1) - beg;
+      if (is_heavy(p, R, deg)) deg = 0;              // handled by the heavy-row kernels
+    }
+    const float rel_scale = (p.scale == AGNN_SCALE_MEAN) ? 1.f / (float)max(deg, 1) : 1.f;
+    int incl = deg;                                  // inclusive scan of the degrees over the lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int excl = incl - deg;
+    const int total = __shfl_sync(kFull, incl, 31);
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      // item t = t0 + lane: which relation, which edge
+      const int t = t0 + lane;
+      int r = 0;
+      for (int q = 0; q < p.n_rel; ++q) r += (__shfl_sync(kFull, incl, q) <= t) ? 1 : 0;
+      r = min(r, p.n_rel - 1);
+      const int k = __shfl_sync(kFull, beg, r) + (t - __shfl_sync(kFull, excl, r));
+      const float sc = __shfl_sync(kFull, rel_scale, r);
+      const T* rowp = nullptr;
+      float w = 0.f;
+      if (t < total) {
+        const agnn_rel_t& R = p.rel[r];
+        const int idx = __ldg(R.col + k);
+        w = sc;
+        if (R.nbr_deg_rowptr) {
+          const int d = __ldg(R.nbr_deg_rowptr + idx + 1) - __ldg(R.nbr_deg_rowptr + idx);
+          w = sc / (float)max(d, 1);
+        }
+        rowp = static_cast<const T*>(R.src) + (int64_t)idx * R.ld_src;
+      }
+      const int n_items = min(32, total - t0);
+      for (int i0 = 0; i0 < n_items; i0 += kUnroll) {
+        const T* ptr[kUnroll];
+        float wi[kUnroll];
+        float x[kUnroll][V][E];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int src_lane = min(i0 + u, 31);
+          const unsigned long long a = __shfl_sync(kFull, (unsigned long long)rowp, src_lane);
+          ptr[u] = (i0 + u < n_items) ? reinterpret_cast<const T*>(a) : nullptr;
+          wi[u] = __shfl_sync(kFull, w, src_lane);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (ptr[u]) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const int c = (v * 32 + lane) * E;
+              if (c < F) VT::load_nc(ptr[u] + c, x[u][v]);
+            }
+          }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (ptr[u]) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+#pragma unroll
+              for (int e = 0; e < E; ++e) tot[v][e] = fmaf(wi[u], x[u][v][e], tot[v][e]);
+          }
+      }
+    }
+    const int64_t off = (int64_t)row * p.ld_out + p.rel[0].out_col;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = (v * 32 + lane) * E;
+      if (c < F) store_split<T>(out + off + c, out_lo ? out_lo + off + c : nullptr, tot[v]);
+    }
+    if (p.copy) {
+      const T* cp = static_cast<const T*>(p.copy) + (int64_t)row * p.ld_copy;
+      const int64_t coff = (int64_t)row * p.ld_out + p.copy_col;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = (v * 32 + lane) * E;
+        if (c < F) {
+          float tmp[E];
+          VT::load_nc(cp + c, tmp);
+          store_split<T>(out + coff + c, out_lo ? out_lo + coff + c : nullptr, tmp);
+        }
+      }
+    }
+  }
+}
+
 // ---- heavy rows: split across warps -------------------------------------------------------------
 // Chunk numbering: relations in order, their heavy entries in list order, kHeavyChunk edges per chunk.
 // Every warp walks the (short) heavy lists to find the chunks it owns; partial sums go to heavy_ws and
@@ -387,7 +505,13 @@ int launch(const GatherParams& p, cudaStream_t stream) {
   int64_t blocks = ceil_div(p.n_rows, kRowsPerBlock);
   const int64_t cap = (int64_t)kNumSM * 8;  // 8 resident CTAs/SM; grid-stride beyond that
   if (blocks > cap) blocks = cap;
-  gather_reduce_kernel<T, LANES, V><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  bool flags_set = false;
+  for (int r = 0; r < p.n_rel; ++r) flags_set = flags_set || (p.rel[r].flags & AGNN_REL_IDENTITY_IF_EMPTY);
+  if (LANES == 32 && p.combine == AGNN_COMBINE_SUM && !flags_set && p.n_rel > 1) {
+    gather_sum_kernel<T, V><<<(unsigned)blocks, kThreads, 0, stream>>>(p);      // lane-parallel index phase
+  } else {
+    gather_reduce_kernel<T, LANES, V><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  }
   if (p.heavy_ws) return launch_heavy<T, V>(p, stream);
   return check_launch("gather_reduce");
 }
