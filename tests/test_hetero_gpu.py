@@ -301,3 +301,4 @@ def test_onset_pool_filter_matches_reference_recipe():
     want = oi.onset_pool(x[:bs], onset, bs)
     got = ann.shell.onset_pool(x[:bs].to(DEV), onset.to(DEV), bs)
     assert_close(got, want, FP32_REL)
+
