@@ -67,7 +67,7 @@ __device__ __forceinline__ void store_split(T* hi_ptr, T* lo_ptr, const float (&
 }
 
 template <typename T, int LANES, int V>
-__global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_constant__ GatherParams p) {
+__global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel(const __grid_constant__ GatherParams p) {
   using VT = Vec16<T>;
   constexpr int E = VT::E;
   constexpr int kRowsPerBlock = kThreads / LANES;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) gather_reduce_kernel(const __grid_co
 // t (column id, neighbour-degree weight, source row address) -- three dependent round trips for up to 32
 // items -- and then the whole warp streams the source rows, four in flight.
 template <typename T, int V>
-__global__ void __launch_bounds__(kThreads) gather_sum_kernel(const __grid_constant__ GatherParams p) {
+__global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_sum_kernel(const __grid_constant__ GatherParams p) {
   using VT = Vec16<T>;
   constexpr int E = VT::E;
   constexpr unsigned kFull = 0xffffffffu;
