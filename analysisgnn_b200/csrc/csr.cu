@@ -199,8 +199,22 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constan
       }
       pp[b + 1] = v;
     }
-    int32_t* cc = col + g.edge_off + beg;
-    for (int a = 0; a < deg; ++a) cc[a] = (int32_t)g.col[pp[a]];
+  }
+}
+
+// col[k] = col_in[perm[k]] for the short rows, edge-parallel (the long rows write theirs after their block sort)
+__global__ void __launch_bounds__(kThreads) gather_col_kernel(const __grid_constant__ SegTable tab, int32_t* col,
+                                                               const int32_t* perm) {
+  const int s = find_seg(tab.edge_blk_start, tab.n_seg, blockIdx.x);
+  const agnn_coo_t& g = tab.seg[s];
+  const int64_t base = (int64_t)(blockIdx.x - tab.edge_blk_start[s]) * kEdgesPerBlock;
+#pragma unroll
+  for (int i = 0; i < kEdgesPerBlock / kThreads; ++i) {
+    const int64_t e = base + i * kThreads + threadIdx.x;
+    if (e >= g.n_edges) continue;
+    const int32_t src = perm[g.edge_off + e];
+    // slots past the kept edges (dropped relation codes) hold stale values: guard the read
+    if (src >= 0 && src < g.n_edges) col[g.edge_off + e] = (int32_t)g.col[src];
   }
 }
 
@@ -347,6 +361,7 @@ extern "C" int agnn_csr_build(int n_seg, const agnn_coo_t* segs, int32_t* rowptr
     if (!col || !perm) return fail(AGNN_ERR_ARG, "csr_build: null col/perm with edges present");
     edge_kernel<true><<<edge_blks, kThreads, 0, stream>>>(tab, rowptr, cursor, perm, status);
     finalize_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list, heavy, n_heavy);
+    gather_col_kernel<<<edge_blks, kThreads, 0, stream>>>(tab, col, perm);
     long_rows_kernel<<<kNumSM * 2, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list);
   }
   return check_launch("csr_build");

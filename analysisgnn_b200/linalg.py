@@ -103,6 +103,28 @@ def unpack(first, second) -> Operand:
     return first if second is None else Split(first, second)
 
 
+# Splits of small operands (weights) made inside a step: a weight is read by the forward GEMM and again by the
+# grad-input GEMM.  Entries keep the source tensor alive (its address cannot be recycled under a live key) and are
+# dropped by begin_step(), which every optimizer step / captured step function calls.
+_split_cache = {}
+_SPLIT_CACHE_MAX_ELEMS = 4 * 1024 * 1024
+
+
+def begin_step() -> None:
+    """Forget cached weight splits (call once per training step, before the forward)."""
+    _split_cache.clear()
+
+
+def _cached_split(x: torch.Tensor) -> Split:
+    if x.numel() > _SPLIT_CACHE_MAX_ELEMS:
+        return split(x)
+    key = (x.data_ptr(), tuple(x.shape), x.stride(0), x._version)
+    hit = _split_cache.get(key)
+    if hit is None:
+        hit = _split_cache[key] = (x, split(x))
+    return hit[1]
+
+
 def _as_operand(x: Operand):
     """(hi, lo, precision) for agnn_gemm, or None when the tensor cannot take the tcgen05 route."""
     if isinstance(x, Split):
@@ -110,7 +132,7 @@ def _as_operand(x: Operand):
     if x.dtype == torch.bfloat16:
         return (x, None, _lib.GEMM_BF16) if _rows_ok(x) else None
     if x.dtype == torch.float32 and _rows_ok(x) and x.shape[1] % 4 == 0:
-        s = split(x)
+        s = _cached_split(x)
         return s.hi, s.lo, _lib.GEMM_TF32X3
     return None
 

@@ -130,6 +130,8 @@ class DataParallelTrainer:
             1.0 / self.world_size, self.max_norm if self.max_norm else 0.0, self.partials.data_ptr(),
             self.n_partials, self.grad_norm.data_ptr(), stream), "agnn_adamw_clip_step")
         _lib.count_launches(2)
+        from . import linalg
+        linalg.begin_step()                     # the weights changed: cached TF32 splits are stale
 
 
 class GraphedStep:

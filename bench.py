@@ -250,7 +250,10 @@ def run_ours(args):
     trainer = DataParallelTrainer(model, lr=CFG["lr"], weight_decay=CFG["weight_decay"], max_norm=CFG["max_norm"],
                                   world_size=world)
 
+    from analysisgnn_b200 import linalg as _lin
+
     def fwd_bwd(tensors):
+        _lin.begin_step()                          # weight splits are per step (a captured step re-splits on replay)
         graph.clear_cache()                        # a new batch every step: the CSR build is part of the step
         d = unflatten(tensors, b)
         trainer.zero_grad()
