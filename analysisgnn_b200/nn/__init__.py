@@ -9,7 +9,8 @@ keys as the modules they replace, so reference checkpoints load unchanged:
   ``analysisgnn/models/analysis.py:444-473`` (``HybridGNN``, ``HybridHGT``,
   ``MetricalGNN``) and their layers;
 * ``shell``   -- the hot-path part of ``TorchAnalysisGNN``
-  (``analysisgnn/models/analysis.py:421-591``).
+  (``analysisgnn/models/analysis.py:421-591``);
+* ``layers``  -- ``Linear`` / ``LayerNorm`` / ``GRU`` with ``torch.nn``'s parameters on libagnn's kernels.
 
 Every forward runs on libagnn.so's CUDA kernels; there is no CPU path.
 """
@@ -17,4 +18,5 @@ from .intree import (HeteroConv, MetricalConvLayer, MetricalGNN, RelEdgeConv, Re
                      SageConvScatter)
 from .hetero import (HeteroSAGELayer, HeteroSAGEStack, HGTConv, HeteroHGTStack, HybridGNN, HybridHGT,  # noqa: F401
                      SAGEConv, SequenceBranch)
-from .shell import AnalysisEncoder, multitask_ce  # noqa: F401
+from .layers import GRU, LayerNorm, Linear  # noqa: F401
+from .shell import AnalysisEncoder, multitask_ce, onset_pool  # noqa: F401

@@ -129,12 +129,6 @@ class HeteroSAGELayer(nn.Module):
         return dict(zip(plan.dst_types, outs))
 
 
-def trim_counts(layer: int, counts: List[int]) -> int:
-    """How many trailing entries ``trim_to_layer`` has dropped in total by ``layer``
-    (applied cumulatively to already-trimmed tensors, cadence.py:165-174)."""
-    return sum(counts[-k] for k in range(1, layer + 1)) if layer > 0 else 0
-
-
 def trim_inputs(layer, nodes_per_hop, edges_per_hop, x_dict, ei_dict):
     """``torch_geometric.utils.trim_to_layer`` for dict inputs, one step (as called in
     cadence.py:166-173): drop the outermost remaining hop's nodes and edges."""
@@ -145,11 +139,12 @@ def trim_inputs(layer, nodes_per_hop, edges_per_hop, x_dict, ei_dict):
     return x_dict, ei_dict
 
 
-def _layer_structures(conv_layers, x_dict, ei_dict, nodes_per_hop, edges_per_hop, plan_of):
+def _layer_structures(conv_layers, x_dict, ei_dict, nodes_per_hop, edges_per_hop):
     """One ``HeteroCSR`` per layer (trimmed edge lists differ per layer), built in a
     single batched agnn_csr_build pass and cached per batch."""
-    ets = list(ei_dict.keys())
     sizes = {t: v.shape[0] for t, v in x_dict.items()}
+    ei_dict = {et: v for et, v in ei_dict.items() if et[0] in sizes and et[2] in sizes}
+    ets = list(ei_dict.keys())
     if edges_per_hop is None:
         csr = graph.hetero_csr(ei_dict, sizes)
         return [csr] * len(conv_layers)
@@ -177,7 +172,7 @@ class HeteroSAGEStack(nn.Module):
     def forward(self, x_dict, ei_dict, nodes_per_hop=None, edges_per_hop=None, collect=None, final_types=None):
         """``final_types``: node types the caller reads from the result; the last layer skips the rest
         (PyG computes and discards them)."""
-        structures = _layer_structures(self.convs, x_dict, ei_dict, nodes_per_hop, edges_per_hop, None)
+        structures = _layer_structures(self.convs, x_dict, ei_dict, nodes_per_hop, edges_per_hop)
         last = len(self.convs) - 1
         for i, conv in enumerate(self.convs):
             x_dict, ei_dict = trim_inputs(i, nodes_per_hop, edges_per_hop, x_dict, ei_dict)
@@ -274,7 +269,7 @@ class HeteroHGTStack(nn.Module):
             for i in range(num_layers))
 
     def forward(self, x_dict, ei_dict, nodes_per_hop=None, edges_per_hop=None, collect=None, final_types=None):
-        structures = _layer_structures(self.convs, x_dict, ei_dict, nodes_per_hop, edges_per_hop, None)
+        structures = _layer_structures(self.convs, x_dict, ei_dict, nodes_per_hop, edges_per_hop)
         last = len(self.convs) - 1
         for i, conv in enumerate(self.convs):
             x_dict, ei_dict = trim_inputs(i, nodes_per_hop, edges_per_hop, x_dict, ei_dict)
@@ -304,7 +299,7 @@ class SequenceBranch(nn.Module):
     def forward(self, x, batch):
         layout = graph.batch_layout(batch)
         seq = layout.pad(x)
-        seq = ops.run_rnn(self.rnn, seq)
+        seq = self.rnn(seq)[0]
         seq = self.rnn_mlp(self.rnn_norm(seq))
         return layout.unpad(seq)
 

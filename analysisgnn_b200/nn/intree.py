@@ -237,7 +237,7 @@ class MetricalConvLayer(nn.Module):
         gathered = ops.segment_sum(self.neigh(x), csr)                            # gnn.py:510-511
         both = torch.cat((gathered, x_metrical), dim=-1)
         gath_seq, both_seq = layout.pad(gathered), layout.pad(both)
-        rec = ops.run_rnn(self.seq, gath_seq)
+        rec = self.seq(gath_seq)[0]
         h = self.activation(self.conv_out(torch.cat((both_seq, rec), dim=-1)))
         h = self.dropout(self.normalize(h.transpose(1, 2))).transpose(1, 2)
         h = layout.unpad(h)

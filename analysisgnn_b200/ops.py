@@ -730,8 +730,3 @@ def gru_layer(x: torch.Tensor, params) -> torch.Tensor:
 def gru_supported(x: torch.Tensor, hidden: int) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[0] > 0 and x.shape[1] > 0
             and bool(_lib.lib().agnn_gru_supported(int(hidden))))
-
-
-def run_rnn(rnn: "torch.nn.RNNBase", seq: torch.Tensor):
-    """cuDNN RNN (kept as a library call: the GRU branches are outside the kernel scope)."""
-    return rnn(seq)[0]
