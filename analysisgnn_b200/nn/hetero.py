@@ -222,36 +222,60 @@ class HGTConv(nn.Module):
 
     def forward(self, x_dict, ei_dict, csr: Optional[graph.HeteroCSR] = None, only_dst=None):
         H, D = self.heads, self.out_channels // self.heads
+        hd = H * D
         n_rel = len(self.edge_types)
         present = [et for et in self.edge_types if et in ei_dict and et[0] in x_dict and et[2] in x_dict]
         if csr is None:
             csr = graph.hetero_csr({et: ei_dict[et] for et in present}, {t: v.shape[0] for t, v in x_dict.items()})
-        kqv = {t: self.kqv_lin[t](x) for t, x in x_dict.items()}                # [N_t, 3*H*D] = k | q | v
-        hd = H * D
-        wk_all = self.k_rel.view(H, n_rel, D, D)
-        wv_all = self.v_rel.view(H, n_rel, D, D)
-        scale = 1.0 / math.sqrt(D)
         by_dst: Dict[str, List[EdgeType]] = {}
         for et in present:
-            by_dst.setdefault(et[2], []).append(et)
-        out_dict = {}
-        for dst, ets in by_dst.items():
-            if only_dst is not None and dst not in only_dst:
+            if only_dst is None or et[2] in only_dst:
+                by_dst.setdefault(et[2], []).append(et)
+        # One wide projection per node type: q (if the type is a target) and, for every relation leaving
+        # the type, k and v with the relation's per-head k_rel / v_rel folded into the weight,
+        #   (x Wk^T + bk) blockdiag(k_rel[:, r]) = x (blockdiag^T Wk)^T + bk blockdiag,
+        # so all per-node-type and per-relation projections of the layer are one tensor-core GEMM per type.
+        wk_all = self.k_rel.view(H, n_rel, D, D)
+        wv_all = self.v_rel.view(H, n_rel, D, D)
+        ys, slot, q_off, kv_off = [], {}, {}, {}
+        for t, x in x_dict.items():
+            out_rels = [et for ets in by_dst.values() for et in ets if et[0] == t]
+            if t not in by_dst and not out_rels:
                 continue
-            q = kqv[dst][:, hd:2 * hd]
-            ks, vs, ps = [], [], []
-            for et in ets:
-                r = self.edge_types.index(et)
-                src = kqv[et[0]]
-                n_src = src.shape[0]
-                # relation-specific key / value of the source type: per head [N, D] @ [D, D]
-                k_r = torch.bmm(src[:, :hd].reshape(n_src, H, D).transpose(0, 1), wk_all[:, r]).transpose(0, 1)
-                v_r = torch.bmm(src[:, 2 * hd:].reshape(n_src, H, D).transpose(0, 1), wv_all[:, r]).transpose(0, 1)
-                ks.append(k_r.reshape(n_src, hd))
-                vs.append(v_r.reshape(n_src, hd))
-                ps.append(self.p_rel[rel_key(et)].reshape(H) * scale)
-            agg = ops.hgt_attention(q, ks, vs, torch.stack(ps, dim=0), [csr.fwd[et] for et in ets],
-                                    [csr.bwd[et] for et in ets], H, self.joint_softmax)
+            w, b = self.kqv_lin[t].weight, self.kqv_lin[t].bias
+            parts_w, parts_b, width = [], [], 0
+            if t in by_dst:
+                parts_w.append(w[hd:2 * hd])
+                parts_b.append(b[hd:2 * hd])
+                q_off[t], width = 0, hd
+            if out_rels:
+                ids = [self.edge_types.index(et) for et in out_rels]
+                n_out = len(ids)
+                for which, rel_w, rows in ((0, wk_all, slice(0, hd)), (1, wv_all, slice(2 * hd, 3 * hd))):
+                    sel = rel_w[:, ids]                                                   # [H, R_t, D, D]
+                    parts_w.append(torch.einsum("hrde,hdi->rhei", sel, w[rows].view(H, D, -1)).reshape(n_out * hd, -1))
+                    parts_b.append(torch.einsum("hrde,hd->rhe", sel, b[rows].view(H, D)).reshape(n_out * hd))
+                    for i, et in enumerate(out_rels):
+                        kv_off[(et, which)] = width + i * hd
+                    width += n_out * hd
+            slot[t] = len(ys)
+            ys.append(ops.linear(x, torch.cat(parts_w, dim=0), torch.cat(parts_b, dim=0)))
+        scale = 1.0 / math.sqrt(D)
+        targets, pscales, order = [], [], []
+        for dst, ets in by_dst.items():
+            rels = [(slot[et[0]], kv_off[(et, 0)], kv_off[(et, 1)], csr.fwd[et], csr.bwd[et]) for et in ets]
+            ps = torch.stack([self.p_rel[rel_key(et)].reshape(H) * scale for et in ets], dim=0)
+            if self.joint_softmax:
+                groups = [ops.HgtGroup(rels)]
+                pscales.append(ps)
+            else:
+                groups = [ops.HgtGroup([r]) for r in rels]
+                pscales += [ps[i:i + 1] for i in range(len(rels))]
+            targets.append(ops.HgtTarget(slot[dst], q_off[dst], groups))
+            order.append(dst)
+        aggs = ops.hgt_layer_attention(ys, targets, pscales, H, hd) if targets else ()
+        out_dict = {}
+        for dst, agg in zip(order, aggs):
             o = self.out_lin[dst](F.gelu(agg))
             if o.size(-1) == x_dict[dst].size(-1):
                 a = self.skip[dst].sigmoid()

@@ -494,6 +494,144 @@ def hgt_attention(q, ks, vs, pscale, fwd_csrs, bwd_csrs, heads: int, joint_softm
     return out
 
 
+
+
+class HgtGroup:
+    """Relations of one destination type that share a softmax: (src slot, k column, v column, fwd CSR, bwd CSR)."""
+
+    __slots__ = ("rels",)
+
+    def __init__(self, rels):
+        self.rels = list(rels)
+
+
+class HgtTarget:
+    """One destination type of a layer: slot of its wide projection, column of q, softmax groups."""
+
+    __slots__ = ("slot", "q_off", "groups")
+
+    def __init__(self, slot, q_off, groups):
+        self.slot, self.q_off, self.groups = slot, q_off, list(groups)
+
+
+def _hgt_pack_wide(group: HgtGroup, ys, hd, dys=None):
+    arr = (_lib.HgtRel * len(group.rels))()
+    esz = ys[0].element_size()
+    for i, (slot, k_off, v_off, cf, cb) in enumerate(group.rels):
+        y = ys[slot]
+        arr[i].rowptr, arr[i].col = cf.rowptr.data_ptr(), cf.col.data_ptr()
+        arr[i].t_rowptr, arr[i].t_col = cb.rowptr.data_ptr(), cb.col.data_ptr()
+        arr[i].k, arr[i].v, arr[i].ld_kv = y.data_ptr() + k_off * esz, y.data_ptr() + v_off * esz, y.stride(0)
+        arr[i].n_src = y.shape[0]
+        if dys is not None:
+            dy = dys[slot]
+            arr[i].dk, arr[i].dv, arr[i].ld_dkv = dy.data_ptr() + k_off * esz, dy.data_ptr() + v_off * esz, dy.stride(0)
+    return arr
+
+
+class _HGTLayerAttention(torch.autograd.Function):
+    """Edge-softmax attention of every destination type of one HGT layer, reading q / k_r / v_r as column
+    slices of the node types' wide projections ``ys`` and writing dq / dk_r / dv_r straight into the
+    matching slices of one gradient buffer per type (no per-relation tensors on either pass).
+    Arguments: (heads, hd, targets, *pscales (one [R_g, H] per group, in target/group order), *ys)."""
+
+    @staticmethod
+    def forward(ctx, heads, hd, targets, *tensors):
+        n_groups = sum(len(t.groups) for t in targets)
+        pscales, ys = tensors[:n_groups], tensors[n_groups:]
+        for y in ys:
+            if y.dim() != 2 or y.stride(1) != 1:
+                raise ValueError("wide projections must be row-major 2-D tensors")
+        d = hd // heads
+        lib = _lib.lib()
+        stream = _stream(ys[0])
+        esz = ys[0].element_size()
+        outs, saved, ps_saved = [], [], []
+        gi = 0
+        for t in targets:
+            yq = ys[t.slot]
+            n = yq.shape[0]
+            total = None
+            for g in t.groups:
+                ps = pscales[gi].detach().to(torch.float32).contiguous()
+                gi += 1
+                out = torch.empty((n, hd), dtype=yq.dtype, device=yq.device)
+                row_max = torch.empty((n, heads), dtype=torch.float32, device=yq.device)
+                row_den = torch.empty((n, heads), dtype=torch.float32, device=yq.device)
+                arr = _hgt_pack_wide(g, ys, hd)
+                _lib.check(lib.agnn_hgt_attn_fwd(n, heads, d, _dtype_code(yq), len(g.rels), arr,
+                                                 yq.data_ptr() + t.q_off * esz, yq.stride(0), ps.data_ptr(),
+                                                 out.data_ptr(), out.stride(0), row_max.data_ptr(),
+                                                 row_den.data_ptr(), stream), "agnn_hgt_attn_fwd")
+                _lib.count_launches(1)
+                saved += [out, row_max, row_den]
+                ps_saved.append(ps)
+                total = out if total is None else total + out
+            outs.append(total)
+        ctx.save_for_backward(*ys, *ps_saved, *saved)
+        ctx.meta = (heads, hd, targets, len(ys), n_groups, [p.dtype for p in pscales])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        heads, hd, targets, n_y, n_groups, ps_dtypes = ctx.meta
+        ys = ctx.saved_tensors[:n_y]
+        pss = ctx.saved_tensors[n_y:n_y + n_groups]
+        saved = ctx.saved_tensors[n_y + n_groups:]
+        d = hd // heads
+        lib = _lib.lib()
+        stream = _stream(ys[0])
+        esz = ys[0].element_size()
+        covered = [0] * n_y
+        for t in targets:
+            covered[t.slot] += hd
+            for g in t.groups:
+                for slot, *_ in g.rels:
+                    covered[slot] += 2 * hd
+        dys = [torch.empty_like(y) if c == y.shape[1] else torch.zeros_like(y) for y, c in zip(ys, covered)]
+        dpss = []
+        gi = 0
+        for t, dout in zip(targets, douts):
+            yq, dyq = ys[t.slot], dys[t.slot]
+            n = yq.shape[0]
+            dout = dout.contiguous()
+            q_ptr = yq.data_ptr() + t.q_off * esz
+            dq_view = dyq[:, t.q_off:t.q_off + hd]
+            for j, g in enumerate(t.groups):
+                out, row_max, row_den = saved[3 * gi:3 * gi + 3]
+                ps = pss[gi]
+                r = len(g.rels)
+                arr = _hgt_pack_wide(g, ys, hd, dys)
+                delta = torch.empty((n, heads), dtype=torch.float32, device=yq.device)
+                dq = dq_view if j == 0 else torch.empty((n, hd), dtype=yq.dtype, device=yq.device)
+                if n > 0:
+                    blocks = lib.agnn_hgt_attn_bwd_dst_blocks(n)
+                    partial = torch.empty((blocks, r * heads), dtype=torch.float32, device=yq.device)
+                    _lib.check(lib.agnn_hgt_attn_bwd_dst(n, heads, d, _dtype_code(yq), r, arr, q_ptr, yq.stride(0),
+                                                         ps.data_ptr(), out.data_ptr(), out.stride(0),
+                                                         dout.data_ptr(), dout.stride(0), row_max.data_ptr(),
+                                                         row_den.data_ptr(), delta.data_ptr(), dq.data_ptr(),
+                                                         dq.stride(0), partial.data_ptr(), stream),
+                               "agnn_hgt_attn_bwd_dst")
+                    dpss.append(partial.sum(0).view(r, heads).to(ps_dtypes[gi]))
+                else:
+                    dpss.append(torch.zeros((r, heads), dtype=ps_dtypes[gi], device=yq.device))
+                _lib.check(lib.agnn_hgt_attn_bwd_src(heads, d, _dtype_code(yq), r, arr, q_ptr, yq.stride(0),
+                                                     ps.data_ptr(), dout.data_ptr(), dout.stride(0),
+                                                     row_max.data_ptr(), row_den.data_ptr(), delta.data_ptr(),
+                                                     stream), "agnn_hgt_attn_bwd_src")
+                _lib.count_launches(2)
+                if j > 0:
+                    dq_view += dq
+                gi += 1
+        return (None, None, None, *dpss, *dys)
+
+
+def hgt_layer_attention(ys, targets, pscales, heads: int, hd: int):
+    """See _HGTLayerAttention; returns one [N_dst, hd] tensor per target."""
+    return _HGTLayerAttention.apply(heads, hd, list(targets), *pscales, *ys)
+
+
 # ------------------------------------------------------------------------------
 # row-wise L2 normalisation + ReLU (hgnn.py:415, 421-422) and stream helper
 # ------------------------------------------------------------------------------

@@ -156,17 +156,46 @@ def metrical_gnn_step():
             "fwd_bwd_ms": ms, "nodes_per_s": n / ms * 1e3}
 
 
+def hgt_encoder_step():
+    """BASELINE.json configs[3]: the config[1] batch through the HGT encoder (3 layers, 256, 4 heads)."""
+    import bench
+    b = bench.make_batch(0, bench.CFG["graphs"])
+    torch.manual_seed(0)
+    net = ann.AnalysisEncoder(b["metadata"], bench.CFG["in_features"], bench.CFG["hidden"], bench.CFG["out"],
+                              bench.TASKS, bench.CFG["layers"], dropout=bench.CFG["dropout"],
+                              encoder_type="hgt").to(DEV)
+    net.train()
+    t = {k: v.to(DEV) for k, v in bench.batch_tensors(b).items()}
+    d = bench.unflatten(t, b)
+
+    def step():
+        graph.clear_cache()
+        net.zero_grad(set_to_none=True)
+        logits = net(d["pitch_spelling"], d["key_signature"], d["x_dict"], d["edge_index_dict"], d["batch_dict"],
+                     d["batch_size"], None, None)
+        ann.multitask_ce(logits, d["labels"]).backward()
+
+    ms = timeit(step, n=5, warm=3)
+    n = b["batch_size"]
+    return {"nodes": n, "edges": sum(v.shape[1] for v in b["edge_index_dict"].values()), "fwd_bwd_ms_eager": ms,
+            "nodes_per_s": n / ms * 1e3}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "extra.json"))
     ap.add_argument("--only-sweep", action="store_true")
+    ap.add_argument("--only-hgt", action="store_true")
     args = ap.parse_args()
+    if args.only_hgt:
+        print("hgt-encoder", hgt_encoder_step())
+        return
     res = {"hbm_peak_gbs": peak(), "degree_sweep": degree_sweep()}
     if args.only_sweep:
         res.update(hgt_attention=[], full_score_inference={}, metrical_gnn_4L512={})
     else:
         res.update(hgt_attention=hgt_kernels(), full_score_inference=full_score_inference(),
-                   metrical_gnn_4L512=metrical_gnn_step())
+                   metrical_gnn_4L512=metrical_gnn_step(), hgt_encoder=hgt_encoder_step())
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as fh:
         json.dump(res, fh, indent=1)
@@ -177,6 +206,7 @@ def main():
         print("hgt", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()})
     print("full-score", res["full_score_inference"])
     print("metricalgnn", res["metrical_gnn_4L512"])
+    print("hgt-encoder", res.get("hgt_encoder"))
 
 
 if __name__ == "__main__":
