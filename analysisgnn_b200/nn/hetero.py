@@ -220,6 +220,14 @@ class HGTConv(nn.Module):
         for p in self.p_rel.values():
             nn.init.ones_(p)
 
+    def _rel_ids(self, ids, device):
+        """Device copy of a relation-id list (made once: a host->device copy cannot be graph-captured)."""
+        key = (tuple(ids), device)
+        cache = self.__dict__.setdefault("_rel_id_cache", {})
+        if key not in cache:
+            cache[key] = torch.tensor(ids, dtype=torch.long, device=device)
+        return cache[key]
+
     def forward(self, x_dict, ei_dict, csr: Optional[graph.HeteroCSR] = None, only_dst=None):
         H, D = self.heads, self.out_channels // self.heads
         hd = H * D
@@ -252,7 +260,7 @@ class HGTConv(nn.Module):
                 ids = [self.edge_types.index(et) for et in out_rels]
                 n_out = len(ids)
                 for which, rel_w, rows in ((0, wk_all, slice(0, hd)), (1, wv_all, slice(2 * hd, 3 * hd))):
-                    sel = rel_w[:, ids]                                                   # [H, R_t, D, D]
+                    sel = rel_w.index_select(1, self._rel_ids(ids, x.device))             # [H, R_t, D, D]
                     parts_w.append(torch.einsum("hrde,hdi->rhei", sel, w[rows].view(H, D, -1)).reshape(n_out * hd, -1))
                     parts_b.append(torch.einsum("hrde,hd->rhe", sel, b[rows].view(H, D)).reshape(n_out * hd))
                     for i, et in enumerate(out_rels):

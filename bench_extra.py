@@ -168,17 +168,42 @@ def hgt_encoder_step():
     t = {k: v.to(DEV) for k, v in bench.batch_tensors(b).items()}
     d = bench.unflatten(t, b)
 
-    def step():
+    from analysisgnn_b200 import linalg
+    from analysisgnn_b200.train import DataParallelTrainer, GraphedStep
+    trainer = DataParallelTrainer(net, lr=bench.CFG["lr"], weight_decay=bench.CFG["weight_decay"],
+                                  max_norm=bench.CFG["max_norm"], world_size=1)
+
+    def fwd_bwd(_=None):
+        linalg.begin_step()
         graph.clear_cache()
-        net.zero_grad(set_to_none=True)
+        trainer.zero_grad()
         logits = net(d["pitch_spelling"], d["key_signature"], d["x_dict"], d["edge_index_dict"], d["batch_dict"],
                      d["batch_size"], None, None)
-        ann.multitask_ce(logits, d["labels"]).backward()
+        loss = ann.multitask_ce(logits, d["labels"])
+        loss.backward()
+        return loss
+
+    def step():
+        fwd_bwd()
+        trainer.step()
 
     ms = timeit(step, n=5, warm=3)
+    if os.environ.get("AGNN_PROFILE"):
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+    graphed = GraphedStep(fwd_bwd, None)
+
+    def graphed_step():
+        graphed()
+        trainer.step()
+
+    ms_graph = timeit(graphed_step, n=10, warm=3)
     n = b["batch_size"]
-    return {"nodes": n, "edges": sum(v.shape[1] for v in b["edge_index_dict"].values()), "fwd_bwd_ms_eager": ms,
-            "nodes_per_s": n / ms * 1e3}
+    return {"nodes": n, "edges": sum(v.shape[1] for v in b["edge_index_dict"].values()), "step_ms_eager": ms,
+            "step_ms_graph": ms_graph, "nodes_per_s": n / ms_graph * 1e3}
 
 
 def main():
