@@ -37,11 +37,16 @@ constexpr int kRowBytes = 128;              // one swizzle row = the K (or MN) e
 constexpr int kTileBytes = kBlockM * kRowBytes;  // 16 KB per operand tile
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 2 * kBlockN;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 200 * 1024;      // operand stages
+constexpr int kStoreBox = 32;                // epilogue staging: one warp's 32 rows x 32 fp32 columns ...
+constexpr int kStoreBufBytes = kStoreBox * 128;          // ... = 4 KB, 128-byte swizzled, stored by TMA
+constexpr int kStoreBytes = 4 * 2 * kStoreBufBytes;      // 4 epilogue warps x 2 buffers
 
 struct GemmParams {
   CUtensorMap map_a[2];  // hi, lo
   CUtensorMap map_b[2];
+  CUtensorMap map_c;     // fp32 C, box 32 x 32 (valid when tma_store)
+  int tma_store;         // epilogue: registers -> swizzled smem -> TMA store / reduce-add
   int M, N, K;
   int k_blocks;          // K blocks in total
   int k_blocks_per_split;
@@ -85,6 +90,22 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// C tile out of shared memory: plain store, or element-wise fp32 add into global memory (one writer per element)
+template <bool REDUCE>
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  if constexpr (REDUCE) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -168,7 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* store_base = smem + kStages * kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(store_base + kStoreBytes);
   uint64_t* empty = full + kStages;
   uint64_t* acc_full = empty + kStages;
   uint64_t* acc_empty = acc_full + 2;
@@ -182,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       prefetch_tmap(&p.map_a[i]);
       prefetch_tmap(&p.map_b[i]);
     }
+    if (p.tma_store) prefetch_tmap(&p.map_c);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -292,7 +315,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) belong to this warp
+    uint8_t* sbuf = store_base + quarter * 2 * kStoreBufBytes;
+    const bool direct = p.split_k == 1;
     int cc = 0;
+    int sc = 0;                                    // staged chunks so far (buffer = sc & 1)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int split = tile / (p.tiles_m * p.tiles_n);
       const int mn = tile - split * p.tiles_m * p.tiles_n;
@@ -300,9 +326,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       const int kb0 = split * p.k_blocks_per_split;
       const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
       const int row = m0 + quarter * 32 + lane;
+      // The bias is the first addend: its loads are in flight while the first chain is computed.
       float acc[kBlockN];
+      if (direct && p.bias) {
 #pragma unroll
-      for (int j = 0; j < kBlockN; ++j) acc[j] = 0.f;
+        for (int j = 0; j < kBlockN; ++j) acc[j] = n0 + j < p.N ? __ldg(p.bias + n0 + j) : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < kBlockN; ++j) acc[j] = 0.f;
+      }
       for (int c0 = kb0; c0 < kb1; c0 += p.chain_blocks, ++cc) {
         const int buf = cc & 1;
         mbar_wait(&acc_full[buf], (cc >> 1) & 1);
@@ -319,18 +351,41 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
-      if (row < p.M) {
-        const bool direct = p.split_k == 1;
+      if (p.tma_store) {
+        // registers -> 128-byte-swizzled shared memory (this warp's 32 rows x 32 columns) -> one TMA store
+        // (or fp32 reduce-add for AGNN_GEMM_ACCUMULATE); the map clips rows >= M and columns >= N.
 #pragma unroll
         for (int c = 0; c < kBlockN / 32; ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;
           float* v = acc + c * 32;
-          if (direct && p.bias) {
+          if (p.flags & AGNN_GEMM_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
+          uint8_t* buf = sbuf + (sc & 1) * kStoreBufBytes;
+          ++sc;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          const uint32_t row_addr = smem_u32(buf) + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((j ^ (lane & 7)) << 4)),
+                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                         : "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (p.flags & AGNN_GEMM_ACCUMULATE) tma_store_2d<true>(&p.map_c, buf, col0, m0 + quarter * 32);
+            else tma_store_2d<false>(&p.map_c, buf, col0, m0 + quarter * 32);
+          }
+        }
+      } else if (row < p.M) {
+#pragma unroll
+        for (int c = 0; c < kBlockN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;
+          float* v = acc + c * 32;
           const int64_t off = (int64_t)split * p.split_stride + (int64_t)row * p.ldc + col0;
           if (!direct || !(p.flags & AGNN_GEMM_OUT_BF16)) {
             float* o = static_cast<float*>(p.out) + off;
@@ -369,6 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
       }
     }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -469,7 +525,7 @@ int launch(const GemmParams& p, int grid, cudaStream_t st) {
   constexpr int kParts = TERMS == 3 ? 2 : 1;
   constexpr int kStageBytes = 2 * kParts * kTileBytes;
   constexpr int kStages = kSmemBudget / kStageBytes;
-  constexpr int smem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr int smem = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
   (void)kElem;
   auto kern = gemm_kernel<BF16, A_MN, B_MN, TERMS>;
   static bool configured = false;
@@ -577,6 +633,12 @@ extern "C" int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, i
     rc = b_mn ? make_map(&p.map_b[i], b_parts[i], bf16, K, N, ldb, chunk, block_k, true)
               : make_map(&p.map_b[i], b_parts[i], bf16, N, K, ldb, block_k, kBlockN, false);
     if (rc) return rc;
+  }
+  const bool acc_relu = (flags & AGNN_GEMM_ACCUMULATE) && (flags & AGNN_GEMM_RELU);
+  if (split_k == 1 && !(flags & AGNN_GEMM_OUT_BF16) && !acc_relu && (ldc * 4) % 16 == 0 && aligned16(c)) {
+    rc = make_map(&p.map_c, c, false, M, N, ldc, kStoreBox, kStoreBox, false);
+    if (rc) return rc;
+    p.tma_store = 1;
   }
   const int64_t work = (int64_t)p.tiles_m * p.tiles_n * split_k;
   const int grid = (int)(work < kNumSM ? work : kNumSM);
