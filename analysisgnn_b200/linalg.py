@@ -178,7 +178,7 @@ def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, 
                                  ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gemm")
 
     if timer is not None:                       # bench.py: per-launch CUDA events, algorithmic flops = 2 M N K
-        timer.launch("gemm", 2 * m * n * k, dev, run)
+        timer.launch("gemm", 2 * m * n * k, dev, run, tag=(a_layout, b_layout, m, n, k, split_k))
     else:
         run()
     _lib.count_launches(2 if split_k > 1 else 1)

@@ -80,14 +80,26 @@ class KernelTimer:
 
     def __init__(self):
         self.records = []
+        self.tags = []
 
-    def launch(self, name: str, nbytes: int, device, fn):
+    def launch(self, name: str, nbytes: int, device, fn, tag=None):
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st = torch.cuda.current_stream(device)
         start.record(st)
         fn()
         stop.record(st)
         self.records.append((name, nbytes, start, stop))
+        self.tags.append(tag)
+
+    def by_tag(self, name: str):
+        """{tag: (launches, total ms)} of the launches recorded under ``name``."""
+        torch.cuda.synchronize()
+        out = {}
+        for (n, _, a, b), tag in zip(self.records, self.tags):
+            if n == name:
+                c, ms = out.get(tag, (0, 0.0))
+                out[tag] = (c + 1, ms + a.elapsed_time(b))
+        return out
 
     def summary(self):
         torch.cuda.synchronize()
