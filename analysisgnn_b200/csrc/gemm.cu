@@ -567,9 +567,17 @@ extern "C" int agnn_gemm_split_k(int precision, int64_t M, int64_t N, int64_t K)
   const int64_t tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN);
   const int64_t kb = ceil_div(K, block_k);
   if (tiles >= kNumSM || kb < 16) return 1;
-  int64_t s = (2 * kNumSM) / tiles;          // aim at ~2 waves of work items
-  if (s > kb / 8) s = kb / 8;                // at least 8 K blocks per split
-  if (s > 32) s = 32;
+  // Work items = tiles x splits run in waves of kNumSM persistent CTAs.  Pick the split count with the best
+  // (wave occupancy) x (useful share of an item: K blocks against ~6 K-block-times of fill + partial store).
+  int64_t s = 1;
+  double best = 0.0;
+  const int64_t s_max = kb / 8 < kNumSM ? kb / 8 : kNumSM;      // at least 8 K blocks per split
+  for (int64_t c = 1; c <= s_max; ++c) {
+    const int64_t items = tiles * c, waves = ceil_div(items, (int64_t)kNumSM);
+    const double kbs = (double)ceil_div(kb, c);
+    const double score = (double)items / (double)(waves * kNumSM) * kbs / (kbs + 6.0);
+    if (score > best * 1.02) { best = score; s = c; }            // prefer fewer splits unless clearly better
+  }
   return s < 1 ? 1 : (int)s;
 }
 

@@ -156,7 +156,9 @@ def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, 
     dev = oa[0].device
     out_dtype = torch.bfloat16 if prec == _lib.GEMM_BF16 else torch.float32
     if out is None:
-        out = torch.empty((m, n), dtype=out_dtype, device=dev)
+        # rows padded to 16 bytes so that the TMA-store epilogue applies (e.g. the 185-class head)
+        pad = (-n) % (8 if out_dtype == torch.bfloat16 else 4)
+        out = torch.empty((m, n + pad), dtype=out_dtype, device=dev)[:, :n]
     elif out.dtype != out_dtype or out.stride(1) != 1:
         return None
     if prec == _lib.GEMM_BF16:
