@@ -684,9 +684,15 @@ class _Linear(torch.autograd.Function):
         xs = linalg.unpack(x_first, x_second)
         g = g.contiguous()
         db = colsum(g) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        n = g.shape[1]
+        if g.dtype == torch.float32 and n % 4 and linalg.backend() == "tcgen05":
+            # e.g. the 185- and 50-class heads: zero columns / weight rows up to the 16-byte row rule of TMA
+            pad = 4 - n % 4
+            g = torch.nn.functional.pad(g, (0, pad))
+            weight = torch.nn.functional.pad(weight, (0, 0, 0, pad))
         gs = linalg.prepare(g)
         dx = linalg.mm(gs, weight) if ctx.needs_input_grad[0] else None
-        dw = linalg.mm_tn(gs, xs) if ctx.needs_input_grad[1] else None
+        dw = linalg.mm_tn(gs, xs)[:n] if ctx.needs_input_grad[1] else None
         return dx, dw, db
 
 

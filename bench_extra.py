@@ -156,14 +156,14 @@ def metrical_gnn_step():
             "fwd_bwd_ms": ms, "nodes_per_s": n / ms * 1e3}
 
 
-def hgt_encoder_step():
+def hgt_encoder_step(encoder_type="hgt"):
     """BASELINE.json configs[3]: the config[1] batch through the HGT encoder (3 layers, 256, 4 heads)."""
     import bench
     b = bench.make_batch(0, bench.CFG["graphs"])
     torch.manual_seed(0)
     net = ann.AnalysisEncoder(b["metadata"], bench.CFG["in_features"], bench.CFG["hidden"], bench.CFG["out"],
                               bench.TASKS, bench.CFG["layers"], dropout=bench.CFG["dropout"],
-                              encoder_type="hgt").to(DEV)
+                              encoder_type=encoder_type).to(DEV)
     net.train()
     t = {k: v.to(DEV) for k, v in bench.batch_tensors(b).items()}
     d = bench.unflatten(t, b)
@@ -193,7 +193,7 @@ def hgt_encoder_step():
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             step()
             torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     graphed = GraphedStep(fwd_bwd, None)
 
     def graphed_step():
@@ -211,7 +211,11 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "extra.json"))
     ap.add_argument("--only-sweep", action="store_true")
     ap.add_argument("--only-hgt", action="store_true")
+    ap.add_argument("--only-hybrid", action="store_true", help="config[1] step through the same harness (profiling)")
     args = ap.parse_args()
+    if args.only_hybrid:
+        print("hybridgnn-encoder", hgt_encoder_step("hybridgnn"))
+        return
     if args.only_hgt:
         print("hgt-encoder", hgt_encoder_step())
         return
