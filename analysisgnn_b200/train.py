@@ -69,6 +69,32 @@ class GradArena:
     def zero_(self):
         self.grad.zero_()
 
+    def views(self):
+        return [self.grad[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
+
+    def detach_views(self):
+        """``p.grad = None``: autograd then hands over each gradient tensor as produced (no in-place add per
+        parameter); ``collect`` brings them into the arena."""
+        for p in self.params:
+            p.grad = None
+
+    def collect(self):
+        """Copy the parameters' gradient tensors into the arena with one multi-tensor copy, zero the slices of
+        parameters that received none (task-dependent heads), and point every ``p.grad`` at its slice again."""
+        views = self.views()
+        src, dst = [], []
+        for p, v in zip(self.params, views):
+            g = p.grad
+            if g is None:
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g if g.dtype == v.dtype else g.to(v.dtype))
+                dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(self.params, views):
+            p.grad = v
+
     def check_views(self):
         """Autograd accumulates in place into an existing ``.grad``; anything that replaced
         it (``zero_grad(set_to_none=True)``) would silently detach the arena."""
@@ -84,7 +110,8 @@ class DataParallelTrainer:
     """``zero_grad() -> loss.backward() -> step()``; ``step`` = allreduce + clip + AdamW."""
 
     def __init__(self, model: torch.nn.Module, lr=5e-3, weight_decay=5e-3, betas=(0.9, 0.999), eps=1e-8,
-                 max_norm: float = 1.0, process_group=None, world_size: Optional[int] = None):
+                 max_norm: float = 1.0, process_group=None, world_size: Optional[int] = None,
+                 collect_grads: bool = False):
         import torch.distributed as dist
         self.model = model
         self.lr, self.weight_decay, self.betas, self.eps, self.max_norm = lr, weight_decay, betas, eps, max_norm
@@ -93,6 +120,10 @@ class DataParallelTrainer:
             world_size = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.world_size = world_size
         self.step_count = 0
+        # collect_grads: ``zero_grad`` detaches the views and ``collect`` (called by ``allreduce`` / ``step``, or
+        # explicitly inside a captured step) copies the finished gradients in -- ~180 in-place adds per step less
+        self.collect_grads = collect_grads
+        self._collected = True
         first = next(p for p in model.parameters() if p.requires_grad)
         if first.is_cuda:
             lib = _lib.lib()
@@ -106,9 +137,19 @@ class DataParallelTrainer:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=first.device)   # device-side step number
 
     def zero_grad(self):
-        self.arena.zero_()
+        if self.collect_grads:
+            self.arena.detach_views()
+            self._collected = False
+        else:
+            self.arena.zero_()
+
+    def collect(self):
+        if self.collect_grads and not self._collected:
+            self.arena.collect()
+            self._collected = True
 
     def allreduce(self):
+        self.collect()
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.arena.grad, op=dist.ReduceOp.SUM, group=self.group)
@@ -117,6 +158,7 @@ class DataParallelTrainer:
         a = self.arena
         if not a.grad.is_cuda:
             raise _lib.AgnnError("DataParallelTrainer.step needs CUDA parameters: there is no CPU optimizer path")
+        self.collect()
         a.check_views()
         self.allreduce()
         self.step_count += 1                    # host mirror; the kernels use the device counter

@@ -248,7 +248,7 @@ def run_ours(args):
                                 dropout=CFG["dropout"]).to(dev)
     model.train()
     trainer = DataParallelTrainer(model, lr=CFG["lr"], weight_decay=CFG["weight_decay"], max_norm=CFG["max_norm"],
-                                  world_size=world)
+                                  world_size=world, collect_grads=True)
 
     from analysisgnn_b200 import linalg as _lin
 
@@ -261,6 +261,7 @@ def run_ours(args):
                        d["batch_dict"], d["batch_size"], None, None)
         loss = ann.multitask_ce(logits, d["labels"])
         loss.backward()
+        trainer.collect()                          # gradients -> flat arena (inside the captured region)
         return loss
 
     def step(tensors):

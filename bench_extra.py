@@ -171,7 +171,7 @@ def hgt_encoder_step(encoder_type="hgt"):
     from analysisgnn_b200 import linalg
     from analysisgnn_b200.train import DataParallelTrainer, GraphedStep
     trainer = DataParallelTrainer(net, lr=bench.CFG["lr"], weight_decay=bench.CFG["weight_decay"],
-                                  max_norm=bench.CFG["max_norm"], world_size=1)
+                                  max_norm=bench.CFG["max_norm"], world_size=1, collect_grads=True)
 
     def fwd_bwd(_=None):
         linalg.begin_step()
@@ -181,6 +181,7 @@ def hgt_encoder_step(encoder_type="hgt"):
                      d["batch_size"], None, None)
         loss = ann.multitask_ce(logits, d["labels"])
         loss.backward()
+        trainer.collect()
         return loss
 
     def step():

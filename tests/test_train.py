@@ -53,6 +53,29 @@ def test_step_refuses_cpu_parameters():
         tr.step()
 
 
+def test_collect_mode_fills_the_same_arena():
+    """collect_grads: detached .grad, one multi-tensor copy after backward, zeros for unused parameters."""
+    a, b = _toy(3), _toy(3)
+    ta = DataParallelTrainer(a, world_size=1)
+    tb = DataParallelTrainer(b, world_size=1, collect_grads=True)
+    torch.manual_seed(5)
+    x = torch.randn(9, 7)
+    for it in range(2):
+        ta.zero_grad(), tb.zero_grad()
+        assert all(p.grad is None for p in b.parameters())
+        if it == 0:
+            a(x).sum().backward(), b(x).sum().backward()
+        else:                                                # only the first layer gets a gradient
+            a[0](x).sum().backward(), b[0](x).sum().backward()
+        tb.collect()
+        assert torch.equal(ta.arena.grad, tb.arena.grad)
+        tb.arena.check_views()
+    tb.collect()                                             # idempotent
+    b[0](x).sum().backward()                                 # accumulating on top of collected views still works
+    a[0](x).sum().backward()
+    assert torch.equal(ta.arena.grad, tb.arena.grad)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -135,3 +158,21 @@ def test_grad_scale_is_the_world_average():
     b(x).sum().backward()
     opt.step()
     assert_close(a.weight, b.weight, 2e-6)
+
+
+@pytest.mark.gpu
+def test_collect_mode_trains_identically():
+    torch.manual_seed(2)
+    mk = lambda: nn.Sequential(nn.Linear(20, 64), nn.ReLU(), nn.Linear(64, 9))
+    a, b = mk().to(DEV), mk().to(DEV)
+    b.load_state_dict(a.state_dict())
+    ta = DataParallelTrainer(a, world_size=1)
+    tb = DataParallelTrainer(b, world_size=1, collect_grads=True)
+    for it in range(3):
+        x = torch.randn(32, 20, device=DEV)
+        for net, tr in ((a, ta), (b, tb)):
+            tr.zero_grad()
+            net(x).square().mean().backward()
+            tr.step()
+        for p, q in zip(a.parameters(), b.parameters()):
+            assert torch.equal(p, q)
