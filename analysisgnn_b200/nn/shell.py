@@ -85,8 +85,8 @@ class AnalysisEncoder(nn.Module):
     def encode(self, pitch_spelling, key_signature, x_dict, edge_index_dict, batch_dict, batch_size,
                neighbor_mask_node=None, neighbor_mask_edge=None):
         z = dict(x_dict)
-        z["note"] = torch.cat((x_dict["note"], self.pitch_embedding(pitch_spelling),
-                               self.key_embedding(key_signature)), dim=-1)
+        z["note"] = torch.cat((x_dict["note"], ops.embedding(pitch_spelling, self.pitch_embedding.weight),
+                               ops.embedding(key_signature, self.key_embedding.weight)), dim=-1)
         h = {k: self.project_dict[k](z[k]) for k in self.project_dict.keys()}
         x = self.encoder(x_dict=h, edge_index_dict=edge_index_dict, batch_dict=batch_dict, batch_size=batch_size,
                          neighbor_mask_node=neighbor_mask_node, neighbor_mask_edge=neighbor_mask_edge,
@@ -114,5 +114,5 @@ def multitask_ce(logits, labels):
     """Default multi-task objective of ``ContinualAnalysisGNN`` (analysisgnn/models/analysis.py:
     881-908, 1035-1037): ``MultiTaskLoss(requires_grad=False)`` = plain sum of per-task
     ``CrossEntropyLoss(ignore_index=-1, label_smoothing=0.1)`` divided by the number of tasks."""
-    total = sum(F.cross_entropy(logits[t], labels[t], ignore_index=-1, label_smoothing=0.1) for t in labels)
+    total = sum(ops.cross_entropy(logits[t], labels[t], ignore_index=-1, label_smoothing=0.1) for t in labels)
     return total / len(labels)

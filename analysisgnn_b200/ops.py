@@ -715,6 +715,86 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return y.reshape(*lead, weight.shape[0])
 
 
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index, smoothing):
+        rows, cols = logits.shape
+        dev = logits.device
+        lib = _lib.lib()
+        lse = torch.empty(rows, dtype=torch.float32, device=dev)
+        partials = torch.empty((lib.agnn_ce_blocks(rows), 2), dtype=torch.float32, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        _lib.check(lib.agnn_softmax_ce_fwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), rows, cols,
+                                           smoothing, ignore_index, lse.data_ptr(), partials.data_ptr(),
+                                           out.data_ptr(), _stream(logits)), "agnn_softmax_ce_fwd")
+        _lib.count_launches(2)
+        ctx.save_for_backward(logits, labels, lse, out)
+        ctx.args = (ignore_index, smoothing)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse, out = ctx.saved_tensors
+        ignore_index, smoothing = ctx.args
+        rows, cols = logits.shape
+        g = g.to(torch.float32).contiguous()
+        dx = torch.empty((rows, cols), dtype=torch.float32, device=logits.device)
+        _lib.check(_lib.lib().agnn_softmax_ce_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(),
+                                                  lse.data_ptr(), rows, cols, smoothing, ignore_index, out.data_ptr(),
+                                                  g.data_ptr(), dx.data_ptr(), dx.stride(0), _stream(logits)),
+                   "agnn_softmax_ce_bwd")
+        _lib.count_launches(1)
+        return dx, None, None, None
+
+
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100,
+                  label_smoothing: float = 0.0) -> torch.Tensor:
+    """``F.cross_entropy(logits, labels, ignore_index=..., label_smoothing=...)`` (mean over the rows that count)
+    for 2-D fp32 logits (any row stride) and int64 labels."""
+    if not logits.is_cuda:
+        raise _lib.AgnnError("analysisgnn_b200 has no CPU path: tensors must live on a CUDA device")
+    if logits.dim() != 2 or labels.dim() != 1 or labels.shape[0] != logits.shape[0]:
+        raise ValueError("cross_entropy expects logits [N, C] and labels [N]")
+    if logits.dtype != torch.float32:
+        logits = logits.float()
+    if logits.stride(1) != 1:
+        logits = logits.contiguous()
+    return _CrossEntropy.apply(logits, labels.to(torch.int64).contiguous(), int(ignore_index), float(label_smoothing))
+
+
+class _SmallEmbedding(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, weight):
+        ctx.save_for_backward(idx)
+        ctx.shape = weight.shape
+        return weight.index_select(0, idx.reshape(-1)).view(*idx.shape, weight.shape[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        n_emb, dim = ctx.shape
+        g = g.reshape(-1, dim)
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        rows = g.shape[0]
+        lib = _lib.lib()
+        partials = torch.empty((lib.agnn_embedding_bwd_blocks(rows), n_emb * dim), dtype=torch.float32, device=g.device)
+        dw = torch.empty((n_emb, dim), dtype=torch.float32, device=g.device)
+        _lib.check(lib.agnn_embedding_bwd(g.data_ptr(), g.stride(0), idx.reshape(-1).contiguous().data_ptr(), rows, dim,
+                                          n_emb, partials.data_ptr(), dw.data_ptr(), _stream(g)), "agnn_embedding_bwd")
+        _lib.count_launches(2)
+        return None, dw
+
+
+def embedding(idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``F.embedding`` for the small fp32 tables of the encoder input (no padding_idx / max_norm); larger
+    tables and other dtypes go to ATen."""
+    if (not weight.is_cuda or weight.dtype != torch.float32 or weight.numel() > 3072 or idx.dtype != torch.int64
+            or not weight.is_contiguous()):
+        return torch.nn.functional.embedding(idx, weight)
+    return _SmallEmbedding.apply(idx, weight)
+
+
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps):

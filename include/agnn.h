@@ -301,6 +301,27 @@ int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t
 int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, float* out /* optional [cols] */, int64_t rows,
                          int cols, agnn_stream_t stream);
 
+/* ------------------------------------------------------------ objective and lookup-table gradients
+ * agnn_softmax_ce_*: nn.CrossEntropyLoss(ignore_index, label_smoothing) with mean reduction over the rows
+ * that are not ignored -- one call per task head; MultiTaskLoss sums them (analysisgnn/models/analysis.py:
+ * 881-908, 1035-1037; label_smoothing = 0.1 at :893).  Labels are int64 in [0, cols) or ignore_index.
+ * fwd writes lse[rows] (log-sum-exp per row, kept for the backward), partials[agnn_ce_blocks(rows)][2] and
+ * out[2] = {mean loss, number of rows that count}; bwd writes
+ *   dlogits = grad_out / rows_that_count * (softmax - (1 - smoothing) onehot - smoothing / cols)   (0 for ignored rows).
+ * agnn_embedding_bwd: d weight of a small nn.Embedding (pitch spelling 35 x 64, key signature 15 x 64,
+ * analysisgnn/models/analysis.py:427-428, 572-574): dweight[e] = sum over rows with idx == e of g[row], summed
+ * in a fixed order; n_emb * dim <= 3072; partials[agnn_embedding_bwd_blocks(rows)][n_emb * dim].
+ */
+int agnn_ce_blocks(int64_t rows);
+int agnn_softmax_ce_fwd(const float* logits, int64_t ld, const int64_t* labels, int64_t rows, int cols, float smoothing,
+                        int64_t ignore_index, float* lse, float* partials, float* out, agnn_stream_t stream);
+int agnn_softmax_ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse, int64_t rows, int cols,
+                        float smoothing, int64_t ignore_index, const float* out, const float* grad_out /* device scalar */,
+                        float* dlogits, int64_t ld_d, agnn_stream_t stream);
+int agnn_embedding_bwd_blocks(int64_t rows);
+int agnn_embedding_bwd(const float* g, int64_t ld_g, const int64_t* idx, int64_t rows, int dim, int n_emb,
+                       float* partials, float* dweight, agnn_stream_t stream);
+
 /* ------------------------------------------------------------ score-graph construction
  * Replaces hetero_graph_from_note_array (analysisgnn/utils/hgraph.py:214-300; rest_array=None,
  * pot_edge_dist=0) for a batch of scores: onset (0) / consecutive (1) / during (2) / rest (3) edges in
