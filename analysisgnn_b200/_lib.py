@@ -103,6 +103,8 @@ _PROTOTYPES = {
     "agnn_l2norm_relu_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "agnn_colsum_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "agnn_grad_prepare": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "agnn_ce_blocks": (C.c_int, [C.c_int64]),
     "agnn_softmax_ce_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -379,10 +379,8 @@ class _HeteroSageLayer(torch.autograd.Function):
             g = douts[j]
             if g is None:
                 continue
-            g = linalg.relu_backward(g, o) if ctx.relu else g.contiguous()
-            if ctx.needs_input_grad[3 + nt + 2 * j + 1]:
-                grads[nt + 2 * j + 1] = colsum(g)
-            g = linalg.prepare(g)
+            g, db = prepare_grad(g, o if ctx.relu else None, ctx.needs_input_grad[3 + nt + 2 * j + 1])
+            grads[nt + 2 * j + 1] = db
             da[t] = linalg.mm(g, wcat)
             if ctx.needs_input_grad[3 + nt + 2 * j]:
                 grads[nt + 2 * j] = linalg.mm_tn(g, a)
@@ -667,6 +665,36 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_colsum: bool = False):
+    """What a projection's backward needs from its incoming gradient, in one pass (agnn_grad_prepare):
+    ``g' = g * [relu_out > 0]`` as a GEMM operand and, optionally, the column sums of ``g'``.
+    Returns ``(operand, colsum or None)``."""
+    rows, cols = g.shape
+    ok = (linalg.backend() == "tcgen05" and g.dtype == torch.float32 and g.is_cuda and rows > 0 and cols % 4 == 0
+          and cols <= 1024 and g.stride(1) == 1 and g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0)
+    if ok and relu_out is not None:
+        ok = (relu_out.dtype == torch.float32 and relu_out.shape == g.shape and relu_out.stride(1) == 1
+              and relu_out.stride(0) % 4 == 0 and relu_out.data_ptr() % 16 == 0)
+    if not ok:
+        if relu_out is not None:
+            g = linalg.relu_backward(g, relu_out)
+        g = g.contiguous()
+        return linalg.prepare(g), (colsum(g) if want_colsum else None)
+    lib = _lib.lib()
+    buf = torch.empty((2, rows, cols), dtype=torch.float32, device=g.device)
+    part = out = None
+    if want_colsum:
+        part = torch.empty((lib.agnn_row_blocks(rows), cols), dtype=torch.float32, device=g.device)
+        out = torch.empty(cols, dtype=torch.float32, device=g.device)
+    _lib.check(lib.agnn_grad_prepare(g.data_ptr(), g.stride(0), relu_out.data_ptr() if relu_out is not None else None,
+                                     relu_out.stride(0) if relu_out is not None else 0, buf[0].data_ptr(),
+                                     buf[1].data_ptr(), cols, part.data_ptr() if part is not None else None,
+                                     out.data_ptr() if out is not None else None, rows, cols, _stream(g)),
+               "agnn_grad_prepare")
+    _lib.count_launches(2 if want_colsum else 1)
+    return linalg.Split(buf[0], buf[1]), out
+
+
 class _Linear(torch.autograd.Function):
     """``y = x W^T + b`` on agnn_gemm (forward, grad-input, grad-weight) with one TF32 split per operand."""
 
@@ -682,15 +710,16 @@ class _Linear(torch.autograd.Function):
     def backward(ctx, g):
         x_first, x_second, weight = ctx.saved_tensors
         xs = linalg.unpack(x_first, x_second)
-        g = g.contiguous()
-        db = colsum(g) if ctx.has_bias and ctx.needs_input_grad[2] else None
         n = g.shape[1]
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if g.dtype == torch.float32 and n % 4 and linalg.backend() == "tcgen05":
             # e.g. the 185- and 50-class heads: zero columns / weight rows up to the 16-byte row rule of TMA
             pad = 4 - n % 4
             g = torch.nn.functional.pad(g, (0, pad))
             weight = torch.nn.functional.pad(weight, (0, 0, 0, pad))
-        gs = linalg.prepare(g)
+        gs, db = prepare_grad(g, None, want_db)
+        if db is not None:
+            db = db[:n]
         dx = linalg.mm(gs, weight) if ctx.needs_input_grad[0] else None
         dw = linalg.mm_tn(gs, xs)[:n] if ctx.needs_input_grad[1] else None
         return dx, dw, db

@@ -300,6 +300,13 @@ int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t
                          int64_t ld_dx, int64_t rows, int cols, int relu_first, agnn_stream_t stream);
 int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, float* out /* optional [cols] */, int64_t rows,
                          int cols, agnn_stream_t stream);
+/* One pass over the gradient g [rows, cols] entering the backward of a projection (nn.Linear backward; the ReLU
+ * in front of it when relu_out, the saved ReLU output, is given): g' = g * [relu_out > 0]; hi / lo = the TF32 operand
+ * pair of g' (as agnn_split_tf32); partials[agnn_row_blocks(rows)][cols] and colsum[cols] = column sums of g' (the
+ * bias gradient) when the two optional buffers are given. */
+int agnn_grad_prepare(const float* g, int64_t ld_g, const float* relu_out /* optional */, int64_t ld_o, float* hi,
+                      float* lo, int64_t ld_s, float* partials /* optional */, float* colsum /* optional */,
+                      int64_t rows, int cols, agnn_stream_t stream);
 
 /* ------------------------------------------------------------ objective and lookup-table gradients
  * agnn_softmax_ce_*: nn.CrossEntropyLoss(ignore_index, label_smoothing) with mean reduction over the rows

@@ -82,3 +82,21 @@ def test_layernorm_module_state_dict_and_fallbacks():
     assert_close(mine(x.to(DEV)), ref(x), FP32_REL)
     odd = LayerNorm(30).to(DEV)                             # width not a multiple of 4: library kernel
     assert_close(odd(torch.ones(4, 30, device=DEV)), torch.zeros(4, 30), 1.0)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 64), (50001, 256), (333, 1024), (77, 36)])
+@pytest.mark.parametrize("with_relu", [False, True])
+def test_grad_prepare_matches_where_colsum_split(rows, cols, with_relu):
+    """agnn_grad_prepare = relu mask + TF32 hi/lo pair + column sums of one gradient matrix in one pass."""
+    from analysisgnn_b200 import linalg
+    torch.manual_seed(rows + cols)
+    g = torch.randn(rows, cols, device=DEV)
+    o = torch.relu(torch.randn(rows, cols, device=DEV)) if with_relu else None
+    op, cs = ops.prepare_grad(g, o, want_colsum=True)
+    ref = torch.where(o > 0, g, torch.zeros((), device=DEV)) if with_relu else g
+    want = linalg.split(ref.contiguous())
+    assert isinstance(op, linalg.Split)
+    assert torch.equal(op.hi, want.hi) and torch.equal(op.lo, want.lo)
+    assert_close(cs, ref.double().sum(0).float(), FP32_REL, "column sums")
+    op2, none = ops.prepare_grad(g, o, want_colsum=False)
+    assert none is None and torch.equal(op2.hi, want.hi)
