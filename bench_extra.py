@@ -194,7 +194,7 @@ def hgt_encoder_step(encoder_type="hgt"):
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             step()
             torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=160, max_name_column_width=90))
     graphed = GraphedStep(fwd_bwd, None)
 
     def graphed_step():

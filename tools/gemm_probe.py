@@ -21,17 +21,20 @@ SHAPES = [  # name, kind, M, N, K
     ("wgrad_256", "mm_tn", 256, 256, 50000),
     ("wgrad_2560", "mm_tn", 256, 2560, 50000),
 ]
+# exactly r persistent rounds of 148 tiles (N = 256 -> 2 column tiles): per-round time and fixed cost
+ROUNDS = [(f"rounds_{r}_k{k}", "linear", 9472 * r, 256, k) for k in (256, 2560) for r in (1, 2, 3, 6)]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--one", default=None)
+    ap.add_argument("--rounds", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     torch.manual_seed(0)
-    for name, kind, m, n, k in SHAPES:
+    for name, kind, m, n, k in (ROUNDS if args.rounds else SHAPES):
         if args.one and name != args.one:
             continue
         if kind == "linear":
