@@ -391,7 +391,11 @@ def run_ours(args):
         roofline_gemm = {
             "bound": "tensor", "kernel": "agnn gemm_kernel (tcgen05 3xTF32, all launches of the step)",
             "achieved": mm_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": mm_tflops / tf32_peak,
-            "traffic": None, "peak_source": peak_src + ": bf16 burst / 2 (TF32 rate)", "launches": mm["launches"],
+            # DRAM bytes of the largest launch (50 000 x 256 x 2560) from the committed ncu --set full capture:
+            # 1.0545 GB read + 46 MB written, against 1.080 GB of operand + result bytes -- nothing is re-read
+            "traffic": 1.1005e9, "traffic_source": "profiles/r1_t_gemm_fwd2560_full_raw.csv (largest launch; "
+                                                   "sm__pipe_tensor_cycles_active 72 %)",
+            "peak_source": peak_src + ": bf16 burst / 2 (TF32 rate)", "launches": mm["launches"],
             "algorithmic_flops_per_step": mm["bytes"] / max(args.steps, 1),
             "kernel_ms_per_step": mm["ms"] / max(args.steps, 1),
             "share_of_step": mm["ms"] / serial_ms if serial_ms else None, "timed_in": timed_in,
@@ -402,7 +406,10 @@ def run_ours(args):
         roofline_gather = {
             "bound": "hbm", "kernel": "agnn gather_reduce_kernel (all launches of the step)",
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": None, "peak_source": peak_src, "launches": g["launches"],
+            # DRAM bytes of the largest launch from the ncu capture: 70 MB read + 966 MB written against 1.62 GB
+            # algorithmic (the 51 MB source matrix and the column ids stay in the 126 MB L2)
+            "traffic": 1.036e9, "traffic_source": "profiles/r1_i_gemm_gather_full_raw.csv (largest launch)",
+            "peak_source": peak_src, "launches": g["launches"],
             "algorithmic_bytes_per_step": g["bytes"] / max(args.steps, 1),
             "kernel_ms_per_step": g["ms"] / max(args.steps, 1),
             "share_of_step": g["ms"] / serial_ms if serial_ms else None, "timed_in": timed_in,
