@@ -202,6 +202,13 @@ def hgt_encoder_step(encoder_type="hgt"):
         trainer.step()
 
     ms_graph = timeit(graphed_step, n=10, warm=3)
+    if os.environ.get("AGNN_TRACE"):                      # kernel timeline of two replayed steps (chrome trace)
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            graphed_step()
+            graphed_step()
+            torch.cuda.synchronize()
+        prof.export_chrome_trace(os.environ["AGNN_TRACE"])
     n = b["batch_size"]
     return {"nodes": n, "edges": sum(v.shape[1] for v in b["edge_index_dict"].values()), "step_ms_eager": ms,
             "step_ms_graph": ms_graph, "nodes_per_s": n / ms_graph * 1e3}
