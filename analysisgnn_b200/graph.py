@@ -17,7 +17,6 @@ of the index tensors, so a stack of L layers builds them once.
 """
 from __future__ import annotations
 
-import ctypes as C
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import graph, ops
-from .layers import GRU, LayerNorm, Linear
+from .layers import GRU, Linear
 
 
 def _xavier_relu_(linear: nn.Linear):

@@ -7,7 +7,7 @@ Dense contractions go through ``linalg`` (this repo's GEMM entry points).
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence
 
 import torch
 

@@ -7,7 +7,7 @@ score or a whole batch of scores at once (node ids offset per score, as ``batch_
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple, Union
+from typing import Sequence, Tuple, Union
 
 import numpy as np
 import torch

@@ -17,7 +17,6 @@ subgraphs, so message passing needs no exchange).
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Iterable, Optional
 
 import torch
