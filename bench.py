@@ -391,6 +391,10 @@ def run_ours(args):
         roofline_gemm = {
             "bound": "tensor", "kernel": "agnn gemm_kernel (tcgen05 3xTF32, all launches of the step)",
             "achieved": mm_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": mm_tflops / tf32_peak,
+            # what the tensor pipe actually executes in the fp32-parity mode: 3 TF32 MMAs per algorithmic product
+            "mma_achieved": mm_tflops * (3 if dtype == torch.float32 else 1),
+            "mma_frac": mm_tflops * (3 if dtype == torch.float32 else 1) / (tf32_peak if dtype == torch.float32
+                                                                              else bf16_peak),
             # DRAM bytes of the largest launch (50 000 x 256 x 2560) from the committed ncu --set full capture:
             # 1.0545 GB read + 46 MB written, against 1.080 GB of operand + result bytes -- nothing is re-read
             "traffic": 1.1005e9, "traffic_source": "profiles/r1_t_gemm_fwd2560_full_raw.csv (largest launch; "
