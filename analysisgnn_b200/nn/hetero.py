@@ -351,6 +351,11 @@ class JumpingKnowledge(nn.Module):
         return (x * alpha.unsqueeze(-1)).sum(dim=1)
 
 
+def _head(x, n):
+    """``x[:n]`` without an autograd slice (zeros + copy in the backward) when it keeps every row."""
+    return x if x.shape[0] == n else x[:n]
+
+
 class _HybridBase(nn.Module):
     overlap_sequence_branch = True
 
@@ -365,18 +370,18 @@ class _HybridBase(nn.Module):
         if side is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                x_seq = self.seq(x_in[:batch_size], batch)
+                x_seq = self.seq(_head(x_in, batch_size), batch)
         collect = [] if self.use_jk else None
         out = self.gnn(x_dict, edge_index_dict, neighbor_mask_node, neighbor_mask_edge, collect, ("note",))
         if self.use_jk:
-            x_gnn = self.jk([c["note"][:batch_size] for c in collect])
+            x_gnn = self.jk([_head(c["note"], batch_size) for c in collect])
         else:
-            x_gnn = out["note"][:batch_size]
+            x_gnn = _head(out["note"], batch_size)
         if side is not None:
             main.wait_stream(side)
             x_seq.record_stream(main)
         else:
-            x_seq = self.seq(x_in[:batch_size], batch)
+            x_seq = self.seq(_head(x_in, batch_size), batch)
         return self.cat_proj(torch.cat((x_gnn, x_seq), dim=-1))
 
 

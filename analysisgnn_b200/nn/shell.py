@@ -91,7 +91,7 @@ class AnalysisEncoder(nn.Module):
                          neighbor_mask_node=neighbor_mask_node, neighbor_mask_edge=neighbor_mask_edge,
                          return_edge_index=False, edge_attr_dict=None)
         if self.encoder_type == "metricalgnn":
-            x = x[:batch_size]
+            x = x if x.shape[0] == batch_size else x[:batch_size]
         pooled = onset_pool(x, edge_index_dict[ONSET], batch_size)
         return self.project_enc(torch.cat((x, pooled), dim=-1))
 

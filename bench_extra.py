@@ -191,10 +191,12 @@ def hgt_encoder_step(encoder_type="hgt"):
     ms = timeit(step, n=5, warm=3)
     if os.environ.get("AGNN_PROFILE"):
         from torch.profiler import profile, ProfilerActivity
-        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        shapes = bool(os.environ.get("AGNN_PROFILE_SHAPES"))
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=shapes) as prof:
             step()
             torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=160, max_name_column_width=90))
+        print(prof.key_averages(group_by_input_shape=shapes).table(sort_by="cuda_time_total", row_limit=160,
+                                                                   max_name_column_width=60))
     graphed = GraphedStep(fwd_bwd, None)
 
     def graphed_step():
