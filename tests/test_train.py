@@ -176,3 +176,70 @@ def test_collect_mode_trains_identically():
             tr.step()
         for p, q in zip(a.parameters(), b.parameters()):
             assert torch.equal(p, q)
+
+
+@pytest.mark.gpu
+def test_graphed_step_replays_the_eager_step():
+    """train.GraphedStep: CSR build + forward + backward (+ gradient collection) captured once and replayed
+    must train exactly like the same step launched eagerly -- also after new data is written into the static
+    input buffers (the CSR is rebuilt inside the graph)."""
+    import bench
+    from analysisgnn_b200 import graph, linalg, synth
+    from analysisgnn_b200 import nn as ann
+    from analysisgnn_b200.train import GraphedStep
+    tasks = {"cadence": 4, "localkey": 50}
+    b = synth.hetero_batch(3, 60, 11, task_dict=tasks)
+    first = bench.batch_tensors(b)
+    gen = torch.Generator().manual_seed(5)
+    second = {}
+    for k, v in first.items():                               # same shapes: other features / labels, edges reordered
+        if k.startswith("x."):
+            second[k] = torch.randn(v.shape, generator=gen)
+        elif k.startswith("ei."):
+            second[k] = v[:, torch.randperm(v.shape[1], generator=gen)]
+        elif k.startswith("label."):
+            second[k] = v[torch.randperm(v.shape[0], generator=gen)]
+        else:
+            second[k] = v.clone()
+
+    def make():
+        torch.manual_seed(0)
+        net = ann.AnalysisEncoder(b["metadata"], 25, 32, 16, tasks, 2, dropout=0.0).to(DEV)
+        net.train()
+        return net, DataParallelTrainer(net, lr=1e-3, weight_decay=1e-2, max_norm=1.0, world_size=1, collect_grads=True)
+
+    def step_fn(net, tr):
+        def fwd_bwd(t):
+            linalg.begin_step()
+            graph.clear_cache()
+            d = bench.unflatten(t, b)
+            tr.zero_grad()
+            logits = net(d["pitch_spelling"], d["key_signature"], d["x_dict"], d["edge_index_dict"], d["batch_dict"],
+                         d["batch_size"], None, None)
+            loss = ann.multitask_ce(logits, d["labels"])
+            loss.backward()
+            tr.collect()
+            return loss
+        return fwd_bwd
+
+    data = [{k: v.to(DEV) for k, v in x.items()} for x in (first, second)]
+    net_e, tr_e = make()
+    eager = step_fn(net_e, tr_e)
+    net_g, tr_g = make()
+    static = {k: v.clone() for k, v in data[0].items()}
+    start = {k: v.detach().clone() for k, v in net_g.state_dict().items()}
+    graphed = GraphedStep(step_fn(net_g, tr_g), static, warmup=2)      # warm-up steps do not call the optimizer
+    net_g.load_state_dict(start)
+    losses_e, losses_g = [], []
+    for it in range(4):
+        batch = data[it % 2]
+        losses_e.append(float(eager(batch).detach()))
+        tr_e.step()
+        for k, v in batch.items():
+            static[k].copy_(v)
+        losses_g.append(float(graphed().detach()))
+        tr_g.step()
+    assert losses_e == losses_g, (losses_e, losses_g)
+    for (n, p), q in zip(net_e.named_parameters(), net_g.parameters()):
+        assert torch.equal(p, q), n
+    assert graphed.launches_per_replay > 50
