@@ -312,3 +312,51 @@ def hetero_batch(n_graphs: int, notes_per_graph: int, seed: int, voices: int = 4
     task_dict = task_dict if task_dict is not None else {"cadence": 4, "localkey": 50, "romanNumeral": 185}
     out["labels"] = {t: torch.from_numpy(rng.integers(0, c, n_note)) for t, c in task_dict.items()}
     return out
+
+
+DECODE_TASKS = {"quality": 15, "inversion": 4, "degree1": 22, "degree2": 22, "localkey": 50}
+
+
+def decode_case(n_notes: int, seed: int, n_scores: int = 1, extra_nodes: int = 0, with_tpc: bool = False,
+                valid_fraction: float = 1.0, smooth: int = 6):
+    """Inputs of the reference's ``onsetwise_logit_aggregation`` (analysisgnn/models/analysis.py:44-101) for a
+    synthetic prediction: softmaxed logits per task, notes sorted by onset with chords (equal onsets), the
+    ``("note", "onset", "note")`` edges between chord members (both directions, plus some that touch the
+    ``extra_nodes`` sampled beyond ``batch_size``), graph ids and an optional valid-label mask.  ``smooth``
+    makes neighbouring onsets share their arg-max so that change points are sparse, as in real predictions."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    n_total = n_notes + extra_nodes
+    steps = torch.randint(0, 3, (n_total,), generator=g)          # 0 = same onset as the previous note (chord)
+    steps[0] = 0
+    onset = torch.cumsum(steps, 0).to(torch.int64) + 7
+    batch = torch.sort(torch.randint(0, n_scores, (n_total,), generator=g)).values if n_scores > 1 else \
+        torch.zeros(n_total, dtype=torch.int64)
+    src, dst = [], []
+    start = 0
+    onset_list = onset.tolist()
+    for i in range(1, n_total + 1):
+        if i == n_total or onset_list[i] != onset_list[start]:
+            for a in range(start, i):
+                for b in range(start, i):
+                    if a != b:
+                        src.append(a)
+                        dst.append(b)
+            start = i
+    loops = torch.randint(0, n_total, (max(n_total // 50, 1),), generator=g)    # self loops the reference drops
+    e = torch.tensor([src + loops.tolist(), dst + loops.tolist()], dtype=torch.int64).reshape(2, -1)
+    e = e[:, torch.randperm(e.shape[1], generator=g)]
+    logits = {}
+    for k, c in DECODE_TASKS.items():
+        base = torch.randn(n_total // smooth + 2, c, generator=g) * 3.0
+        rows = base[torch.arange(n_total) // smooth] + 0.5 * torch.randn(n_total, c, generator=g)
+        logits[k] = torch.softmax(rows[:n_notes], dim=-1)
+    if with_tpc:
+        logits["tpc_in_label"] = torch.softmax(torch.randn(n_notes, 2, generator=g) + torch.tensor([0.0, 1.5]), dim=-1)
+    valid = None
+    if valid_fraction < 1.0:
+        valid = torch.rand(n_notes, generator=g) < valid_fraction
+        valid[0] = True
+    return dict(logits=logits, onset_div=onset, batch=batch, x=torch.zeros(n_total, 1),
+                edge_index_dict={("note", "onset", "note"): e}, batch_size=n_notes, valid_label_mask=valid)

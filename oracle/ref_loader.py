@@ -13,7 +13,9 @@ partitura / torch_geometric / graphmuse, none of which exist here.  Instead
   ``torch_scatter``;
 * the body of ``hetero_graph_from_note_array`` (``analysisgnn/utils/hgraph.py:214``)
   and of ``HeteroScoreGraph.add_beat_nodes / add_measure_nodes`` (``:41-73``) are
-  cut out of the file with ``ast`` and exec'd with numpy only.
+  cut out of the file with ``ast`` and exec'd with numpy only;
+* ``onsetwise_logit_aggregation`` (``analysisgnn/models/analysis.py:44-101``) is cut
+  out the same way and exec'd with torch + the ``torch_scatter`` shim.
 """
 import ast
 import importlib.util
@@ -113,3 +115,25 @@ def load_metrical_edge_builders():
                         found[item.name] = _exec_function(item)
         _cache["metrical"] = (found["add_beat_nodes"], found["add_measure_nodes"])
     return _cache["metrical"]
+
+
+def load_onsetwise_decode():
+    """The reference's ``onsetwise_logit_aggregation`` (models/analysis.py:44-101), unmodified."""
+    if "decode" not in _cache:
+        import torch
+        from . import scatter_shim
+        path = os.path.join(REFERENCE_ROOT, "analysisgnn/models/analysis.py")
+        with open(path) as fh:
+            tree = ast.parse(fh.read(), filename=path)
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef) and node.name == "onsetwise_logit_aggregation":
+                node.decorator_list = []
+                module = ast.Module(body=[node], type_ignores=[])
+                ast.fix_missing_locations(module)
+                scope = {"torch": torch, "torch_scatter": scatter_shim}
+                exec(compile(module, "<reference models/analysis.py>", "exec"), scope)
+                _cache["decode"] = scope[node.name]
+                break
+        else:
+            raise LookupError("onsetwise_logit_aggregation not found in the reference")
+    return _cache["decode"]

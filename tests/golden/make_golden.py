@@ -7,6 +7,8 @@ Run in the build container only (needs /root/reference):
 * ``edges_*.npz``   -- edge lists produced by the reference's
   ``hetero_graph_from_note_array`` (analysisgnn/utils/hgraph.py:214-300) and its
   ``add_beat_nodes`` / ``add_measure_nodes`` (:41-73) on small note arrays.
+* ``decode_*.pt``   -- outputs of the reference's ``onsetwise_logit_aggregation``
+  (analysisgnn/models/analysis.py:44-101, torch_scatter shim) on ``synth.decode_case`` inputs.
 * ``intree_*.pt``   -- inputs, state_dict, forward output and all gradients of the
   reference's ``SageConvScatter`` / ``HeteroConv`` / ``MetricalConvLayer`` /
   ``MetricalGNN`` (analysisgnn/models/core/{gnn,hgnn}.py) executed through
@@ -117,6 +119,32 @@ def intree_goldens():
         print("intree seed", seed, "nodes", x.shape[0], "edges", ei.shape[1])
 
 
+DECODE_CASES = {   # name -> synth.decode_case kwargs
+    "single": dict(n_notes=240, seed=0),
+    "single_extra_nodes": dict(n_notes=200, seed=1, extra_nodes=40),
+    "single_valid_mask": dict(n_notes=220, seed=2, valid_fraction=0.8),
+    "single_tpc": dict(n_notes=260, seed=3, with_tpc=True),
+    "two_scores": dict(n_notes=180, seed=4, n_scores=2),
+    "one_note": dict(n_notes=1, seed=5),
+}
+
+
+def decode_goldens():
+    from oracle import decode as odecode
+    fn = ref_loader.load_onsetwise_decode()
+    for name, kw in DECODE_CASES.items():
+        case = synth.decode_case(**kw)
+        logits = {k: v.clone() for k, v in case["logits"].items()}
+        originals = dict(logits)                                  # the reference also mutates these tensors in place
+        graph = odecode.note_store(case["x"], case["batch"], case["onset_div"], case["edge_index_dict"])
+        out = fn(logits, graph, batch_size=case["batch_size"], valid_label_mask=case["valid_label_mask"])
+        torch.save({"kwargs": kw, "out": {k: v.clone() for k, v in out.items()},
+                    "mutated_inputs": {k: v.clone() for k, v in originals.items()}},
+                   os.path.join(HERE, f"decode_{name}.pt"))
+        print("decode", name, {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     edge_goldens()
     intree_goldens()
+    decode_goldens()
