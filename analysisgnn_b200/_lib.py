@@ -113,6 +113,15 @@ _PROTOTYPES = {
     "agnn_embedding_bwd_blocks": (C.c_int, [C.c_int64]),
     "agnn_embedding_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "agnn_softmax2_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
+                                     C.c_void_p]),
+    "agnn_run_heads_workspace": (C.c_size_t, [C.c_int64]),
+    "agnn_run_heads": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_size_t, C.c_void_p]),
+    "agnn_row_argmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
+    "agnn_decode_assign": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnn_score_graph_workspace": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
     "agnn_score_graph_build": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t,

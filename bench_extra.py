@@ -8,7 +8,8 @@
   achieved algorithmic GB/s vs the measured HBM copy peak;
 * HGT attention kernels (config 3): forward / bwd_dst / bwd_src on the config-1 graph, fp32 and bf16;
 * full-score inference (config 5): 200 000-note score: GPU graph build -> CSR -> HybridGNN forward;
-* in-tree MetricalGNN 4L/512, 64 x 500 notes (config 4): forward + backward step time.
+* in-tree MetricalGNN 4L/512, 64 x 500 notes (config 4): forward + backward step time;
+* onset-wise logit aggregation + decode of a 200 000-note score.
 Every timing: CUDA events on the launching stream, 3 warm-up + 10 timed runs, L2 flushed between runs.
 """
 import argparse
@@ -216,13 +217,62 @@ def hgt_encoder_step(encoder_type="hgt"):
             "step_ms_graph": ms_graph, "nodes_per_s": n / ms_graph * 1e3}
 
 
+def decode_full_score(n_notes=200_000, cpu_notes=20_000):
+    """Onset-wise logit aggregation + decode (analysisgnn/models/analysis.py:44-101) of one 200 k-note score: the call
+    as ``predict`` makes it (device tensors in, device tensors out; its own host synchronisations included), timed
+    with CUDA events; beside it the CPU restatement (oracle/decode.py, pinned to the reference's function) on a
+    bounded sample -- its loop over change points is O(segments x notes), so the sample is smaller and the
+    per-note figure FAVOURS the CPU."""
+    import time
+    from analysisgnn_b200 import decode
+    from oracle import decode as odecode
+
+    def prep(case, dev):
+        mv = lambda t: None if t is None else t.to(dev)
+        g = odecode.note_store(mv(case["x"]), mv(case["batch"]), mv(case["onset_div"]),
+                               {k: mv(v) for k, v in case["edge_index_dict"].items()})
+        return {k: v.to(dev) for k, v in case["logits"].items()}, g
+
+    case = synth.decode_case(n_notes, 21, smooth=12)
+    logits0, g = prep(case, DEV)
+
+    def run():
+        graph.clear_cache()
+        decode.onsetwise_logit_aggregation({k: v.clone() for k, v in logits0.items()}, g, batch_size=n_notes)
+
+    ms = timeit(run, n=10, warm=3)
+    small = synth.decode_case(cpu_notes, 21, smooth=12)
+    lc, gc = prep(small, "cpu")
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.perf_counter()
+    odecode.onsetwise_logit_aggregation(lc, gc, batch_size=cpu_notes)
+    cpu_s = time.perf_counter() - t0
+    cols = sum(synth.DECODE_TASKS[k] for k in odecode.RNA_KEYS)
+    e_kept = int(case["edge_index_dict"][("note", "onset", "note")].shape[1])
+    # algorithmic bytes of one call: the packed logits read (edges + self) and written by the mean, read and written
+    # by the two softmaxes, read by the arg-max of one row per onset, rows copied by the assignment (read + write)
+    alg = 4 * cols * (e_kept + 2 * n_notes) + 2 * 4 * cols * n_notes + 2 * 4 * cols * n_notes
+    return {"notes": n_notes, "onset_edges": e_kept, "task_columns": cols, "gpu_ms": ms,
+            "gpu_notes_per_s": n_notes / ms * 1e3, "algorithmic_gb": alg / 1e9,
+            "achieved_gbs_whole_call": alg / ms / 1e6,
+            "cpu_port": {"notes": cpu_notes, "seconds": cpu_s, "notes_per_s": cpu_notes / cpu_s,
+                         "cores": os.cpu_count(), "kind": "port"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--only-decode", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "extra.json"))
     ap.add_argument("--only-sweep", action="store_true")
     ap.add_argument("--only-hgt", action="store_true")
     ap.add_argument("--only-hybrid", action="store_true", help="config[1] step through the same harness (profiling)")
     args = ap.parse_args()
+    if args.only_decode:
+        r = decode_full_score()
+        print("decode", r)
+        with open(args.out, "w") as fh:
+            json.dump({"decode_full_score": r}, fh, indent=1)
+        return
     if args.only_hybrid:
         print("hybridgnn-encoder", hgt_encoder_step("hybridgnn"))
         return
@@ -234,7 +284,8 @@ def main():
         res.update(hgt_attention=[], full_score_inference={}, metrical_gnn_4L512={})
     else:
         res.update(hgt_attention=hgt_kernels(), full_score_inference=full_score_inference(),
-                   metrical_gnn_4L512=metrical_gnn_step(), hgt_encoder=hgt_encoder_step())
+                   metrical_gnn_4L512=metrical_gnn_step(), hgt_encoder=hgt_encoder_step(),
+                   decode_full_score=decode_full_score())
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as fh:
         json.dump(res, fh, indent=1)
@@ -246,6 +297,7 @@ def main():
     print("full-score", res["full_score_inference"])
     print("metricalgnn", res["metrical_gnn_4L512"])
     print("hgt-encoder", res.get("hgt_encoder"))
+    print("decode", res.get("decode_full_score"))
 
 
 if __name__ == "__main__":

@@ -329,6 +329,32 @@ int agnn_embedding_bwd_blocks(int64_t rows);
 int agnn_embedding_bwd(const float* g, int64_t ld_g, const int64_t* idx, int64_t rows, int dim, int n_emb,
                        float* partials, float* dweight, agnn_stream_t stream);
 
+/* ------------------------------------------------------------ onset-wise decode
+ * Replaces onsetwise_logit_aggregation (analysisgnn/models/analysis.py:44-101, called from predict at :1588); the
+ * onset mean itself (:66) is agnn_gather_reduce with the self term.  All buffers are device memory.
+ *
+ * agnn_softmax2_rows   y[i] = softmax(softmax(x[rows ? rows[i] : i])): the softmax after the onset mean (:66) and the
+ *                      one after the valid-label selection (:68) in one pass; cols <= 256.
+ * agnn_run_heads       heads[u] = first position of the u-th run of equal consecutive keys, *n_runs = number of runs
+ *                      (torch.unique + the run starts of its inverse, :79-81, for keys that do not decrease;
+ *                      *unsorted is set to 1 if they do).  With n_dev only the first min(n, *n_dev) keys count.
+ * agnn_row_argmax      out[u] = first arg-max of row rowmap[heads[u]] (either map may be null), u < min(n_max, *n_dev).
+ * agnn_decode_assign   the loop over change points (:85-99): with ov(i) = onsets_f[onset_heads[cp_heads[i]]], every row j
+ *                      whose onsets[j] lies in [ov(i), ov(i+1)) for some i < *n_cp - 1 is overwritten by row
+ *                      rowmap[onset_heads[cp_heads[i]]] of the same matrix (the last segment stays as it is).
+ */
+int agnn_softmax2_rows(const float* x, int64_t ld_x, const int32_t* rows /* optional */, int64_t n_out, int cols,
+                       float* y, int64_t ld_y, agnn_stream_t stream);
+size_t agnn_run_heads_workspace(int64_t n);
+int agnn_run_heads(const int64_t* keys, int64_t n, const int32_t* n_dev /* optional */, int32_t* heads /* [n] */,
+                   int32_t* n_runs /* device */, int32_t* unsorted /* optional, device, pre-zeroed */, void* workspace,
+                   size_t workspace_bytes, agnn_stream_t stream);
+int agnn_row_argmax(const float* x, int64_t ld, const int32_t* heads /* optional */, const int32_t* rowmap /* optional */,
+                    const int32_t* n_dev /* optional */, int64_t n_max, int cols, int64_t* out, agnn_stream_t stream);
+int agnn_decode_assign(float* y, int64_t ld, int cols, const int64_t* onsets, int64_t n_rows, const int64_t* onsets_f,
+                       const int32_t* onset_heads, const int32_t* rowmap /* optional */, const int32_t* cp_heads,
+                       const int32_t* n_cp /* device */, agnn_stream_t stream);
+
 /* ------------------------------------------------------------ score-graph construction
  * Replaces hetero_graph_from_note_array (analysisgnn/utils/hgraph.py:214-300; rest_array=None,
  * pot_edge_dist=0) for a batch of scores: onset (0) / consecutive (1) / during (2) / rest (3) edges in
