@@ -63,14 +63,40 @@ def row_pattern(t):
     return first[inv]
 
 
+def run_starts(t, tol=1e-6):
+    """Start index of the run of (nearly) equal consecutive rows each row belongs to.  Notes are in onset order, so a
+    decoded segment is one run; so is a chord in the part that keeps per-note rows (the onset mean gives chord mates
+    the same distribution up to the order of the fp32 sum, which is why the comparison is not bit-wise: WHICH chord
+    mates come out bit-identical depends on that order).  Rows of different chords / segments differ by >= 1e-4."""
+    t = t.detach().cpu()
+    new = torch.ones(t.shape[0], dtype=torch.bool)
+    if t.shape[0] > 1:
+        new[1:] = (t[1:] - t[:-1]).abs().amax(-1) > tol
+    idx = torch.arange(t.shape[0])
+    return torch.cummax(torch.where(new, idx, torch.zeros_like(idx)), 0).values
+
+
+def check_segments(got, want, onsets=None):
+    """Same segmentation as the reference, and the rows of a decoded segment (a run spanning several onsets) are
+    bit-for-bit copies of its first row."""
+    for k in odecode.RNA_KEYS:
+        g = got[k].detach().cpu()
+        starts = run_starts(g)
+        assert torch.equal(starts, run_starts(want[k])), f"{k}: segments differ from the reference's"
+        if onsets is not None and g.shape[0] == onsets.numel():
+            spans = onsets != onsets[starts]              # rows whose run began at another onset: decoded rows
+            assert torch.equal(g[spans], g[starts[spans]]), f"{k}: a decoded row is not a copy of its segment's row"
+
+
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[7:-3] for p in GOLDEN])
 def test_matches_reference_golden(path):
     rec = torch.load(path)
     out, originals = run_gpu(synth.decode_case(**rec["kwargs"]))
     same(out, rec["out"], "returned dict")
     same(originals, rec["mutated_inputs"], "caller's tensors after the in-place onset mean")
-    for k in odecode.RNA_KEYS:
-        assert torch.equal(row_pattern(out[k]), row_pattern(rec["out"][k])), f"{k}: rows held by other segments"
+    kw = rec["kwargs"]
+    full = kw.get("valid_fraction", 1.0) >= 1.0
+    check_segments(out, rec["out"], synth.decode_case(**kw)["onset_div"][:kw["n_notes"]] if full else None)
 
 
 @pytest.mark.parametrize("seed", range(10))
@@ -81,8 +107,8 @@ def test_matches_oracle_seeded(seed):
     got, got_in = run_gpu(synth.decode_case(**kw))
     same(got, want, "returned dict")
     same(got_in, want_in, "mutated inputs")
-    for k in odecode.RNA_KEYS:
-        assert torch.equal(row_pattern(got[k]), row_pattern(want[k])), k
+    full = kw["valid_fraction"] >= 1.0
+    check_segments(got, want, synth.decode_case(**kw)["onset_div"][:kw["n_notes"]] if full else None)
 
 
 def test_valid_mask_together_with_several_scores_returns_before_the_decode():
@@ -98,8 +124,7 @@ def test_20k_note_score_against_the_oracle():
     got, got_in = run_gpu(synth.decode_case(**kw))
     same(got, want, "returned dict")
     same(got_in, want_in, "mutated inputs")
-    for k in odecode.RNA_KEYS:
-        assert torch.equal(row_pattern(got[k]), row_pattern(want[k])), k
+    check_segments(got, want, synth.decode_case(**kw)["onset_div"][:kw["n_notes"]])
 
 
 def test_missing_rna_key_returns_the_dict_untouched():
