@@ -66,23 +66,32 @@ def onsetwise_logit_aggregation(logits_softmax_dict, graph, edge_index_dict=None
     batch_id = note.batch[:batch_size][valid_label_mask]
     if torch.all(batch_id == batch_id[0]):                                          # :71
         onsets = note.onset_div[:batch_size][valid_label_mask]
-        onsets = onsets - onsets.min()
-        if tpc is not None:
-            onsets_f = onsets[tpc]
-            agg = {k: v[tpc] for k, v in agg.items()}
-        else:
-            onsets_f = onsets
-        uniq, inv = torch.unique(onsets_f, return_inverse=True)                     # :79
-        heads = (inv[1:] != inv[:-1]).nonzero(as_tuple=True)[0] + 1
-        heads = torch.cat([torch.zeros(1, dtype=heads.dtype), heads])
-        onsetwise = {k: v[heads] for k, v in agg.items()}
-        for k in rna_keys:                                                          # :85-99
-            pred = onsetwise[k].argmax(-1)
-            cp = (pred[1:] != pred[:-1]).nonzero(as_tuple=True)[0] + 1
-            cp = torch.cat([torch.zeros(1, dtype=cp.dtype), cp])
-            onset_at = uniq[cp]
-            rows = onsetwise[k][cp]
-            for i in range(len(cp) - 1):
-                m = (onset_at[i] <= onsets) & (onsets < onset_at[i + 1])
-                logits_softmax_dict[k][m] = rows[i]
+        hold_between_change_points(logits_softmax_dict, onsets, tpc, rna_keys)
     return logits_softmax_dict
+
+
+def hold_between_change_points(dists, onsets, tpc=None, rna_keys=RNA_KEYS):
+    """The single-score stage (:72-99) on its own: ``dists[k]`` are the per-note distributions after the two
+    softmaxes; rows are overwritten in place.  Only comparisons, arg-max and row copies happen here, so given the
+    same ``dists`` every implementation must agree bit for bit."""
+    onsets = onsets - onsets.min()
+    agg = {k: dists[k] for k in rna_keys}
+    if tpc is not None:
+        onsets_f = onsets[tpc]
+        agg = {k: v[tpc] for k, v in agg.items()}
+    else:
+        onsets_f = onsets
+    uniq, inv = torch.unique(onsets_f, return_inverse=True)                         # :79
+    heads = (inv[1:] != inv[:-1]).nonzero(as_tuple=True)[0] + 1
+    heads = torch.cat([torch.zeros(1, dtype=heads.dtype), heads])
+    onsetwise = {k: v[heads] for k, v in agg.items()}
+    for k in rna_keys:                                                              # :85-99
+        pred = onsetwise[k].argmax(-1)
+        cp = (pred[1:] != pred[:-1]).nonzero(as_tuple=True)[0] + 1
+        cp = torch.cat([torch.zeros(1, dtype=cp.dtype), cp])
+        onset_at = uniq[cp]
+        rows = onsetwise[k][cp]
+        for i in range(len(cp) - 1):
+            m = (onset_at[i] <= onsets) & (onsets < onset_at[i + 1])
+            dists[k][m] = rows[i]
+    return dists

@@ -95,3 +95,26 @@ def test_loader_batches_feed_the_encoder_and_shard_across_ranks():
     out = stack(hop["x_dict"], hop["edge_index_dict"], hop["num_sampled_nodes_dict"], hop["num_sampled_edges_dict"])
     assert out["note"].shape[0] == hop["batch_size"] + 0 * n_all or out["note"].shape[0] <= n_all
     assert torch.isfinite(out["note"]).all()
+
+
+def test_corpus_file_round_trip_feeds_the_same_batches(tmp_path):
+    """corpusfile: device corpus -> file -> pinned staging -> device; the loader's batches (plain windows and sampled
+    hops) from the reloaded corpus are bit-identical to those from the original."""
+    from analysisgnn_b200 import corpusfile
+    sizes = [300, 420, 260, 510, 333]
+    arrays, corpus = _corpus(sizes, seed=8)
+    corpus.extras["onset_div"] = torch.cat([torch.as_tensor(a["onset_div"].astype(np.int64)) for a in arrays]).to(DEV)
+    path = str(tmp_path / "corpus.agc")
+    corpusfile.save_corpus(path, corpus)
+    loaded = corpusfile.load_corpus(path, device=DEV)
+    assert loaded.x.is_cuda and loaded.edges.dtype == torch.int64 and loaded.node_ptr == corpus.node_ptr
+    assert torch.equal(loaded.x, corpus.x) and torch.equal(loaded.edges, corpus.edges)
+    for kwargs in (dict(), dict(num_neighbors=[3, 2])):
+        a = sampler.ScoreGraphLoader(corpus, subgraph_size=200, batch_size=3, seed=5, **kwargs).batch(1, 0)
+        b = sampler.ScoreGraphLoader(loaded, subgraph_size=200, batch_size=3, seed=5, **kwargs).batch(1, 0)
+        assert a["graph_ids"] == b["graph_ids"] and a["batch_size"] == b["batch_size"]
+        assert torch.equal(a["node_index"], b["node_index"])
+        assert torch.equal(a["x_dict"]["note"], b["x_dict"]["note"])
+        assert torch.equal(a["extras"]["onset_div"], b["extras"]["onset_div"])
+        for et in a["edge_index_dict"]:
+            assert torch.equal(a["edge_index_dict"][et], b["edge_index_dict"][et]), et
