@@ -23,7 +23,7 @@ SCALE_NONE, SCALE_MEAN = 0, 1
 COMBINE_CONCAT, COMBINE_SUM = 0, 1
 REL_IDENTITY_IF_EMPTY = 1
 HEAVY_ROW, HEAVY_CHUNK = 4096, 2048
-GEMM_TF32X3, GEMM_TF32, GEMM_BF16 = 0, 1, 2
+GEMM_TF32X3, GEMM_TF32, GEMM_BF16, GEMM_F16X3 = 0, 1, 2, 3
 K_MAJOR, MN_MAJOR = 0, 1
 GEMM_RELU, GEMM_ACCUMULATE, GEMM_OUT_BF16 = 1, 2, 4
 
@@ -65,6 +65,9 @@ _PROTOTYPES = {
     "agnn_gather_reduce": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Rel),
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "agnn_gather_reduce_f16": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Rel),
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "agnn_gather_heavy_workspace": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "agnn_rowscale_sum": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.POINTER(Rel), C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -92,6 +95,12 @@ _PROTOTYPES = {
     "agnn_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                             C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
                             C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "agnn_amax": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "agnn_split_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_void_p]),
+    "agnn_gemm_scaled": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "agnn_row_blocks": (C.c_int, [C.c_int64]),
     "agnn_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
@@ -105,6 +114,8 @@ _PROTOTYPES = {
     "agnn_colsum_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "agnn_grad_prepare": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "agnn_grad_prepare_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "agnn_ce_blocks": (C.c_int, [C.c_int64]),
     "agnn_softmax_ce_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

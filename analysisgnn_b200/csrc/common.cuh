@@ -2,11 +2,13 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 
 #include "agnn.h"
 
@@ -66,5 +68,45 @@ struct Vec16<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 };
+
+// ---- fp16 hi / lo operand pairs of agnn_gemm's F16X3 mode ---------------------------------------------
+// One power-of-two scale per tensor, derived from its amax so that max |s x| lies in [2^13, 2^14) -- two
+// binades below the fp16 maximum, which leaves room for producers that can exceed the amax they were given by
+// up to 4x (a mean with a self term: 2x).  amax == 0, denormal, inf or nan: s = 1.  |log2 s| <= 100.
+__host__ __device__ inline float f16_scale_of(float amax) {
+#ifdef __CUDA_ARCH__
+  const uint32_t bits = __float_as_uint(amax) & 0x7fffffffu;
+#else
+  uint32_t bits;
+  memcpy(&bits, &amax, 4);
+  bits &= 0x7fffffffu;
+#endif
+  const int e = (int)(bits >> 23);            // biased exponent: floor(log2 amax) + 127
+  if (e == 0 || e == 255) return 1.f;
+  int k = 13 - (e - 127);
+  k = k > 100 ? 100 : (k < -100 ? -100 : k);
+  const uint32_t sb = (uint32_t)(k + 127) << 23;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(sb);
+#else
+  float s;
+  memcpy(&s, &sb, 4);
+  return s;
+#endif
+}
+// 4 values -> 4 fp16 hi + 4 fp16 lo (8 bytes each) of s * v
+__device__ __forceinline__ void f16_pair4(const float (&v)[4], float s, uint2& hi, uint2& lo) {
+  __half h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float x = v[e] * s;
+    h[e] = __float2half_rn(x);
+    l[e] = __float2half_rn(x - __half2float(h[e]));
+  }
+  __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+  __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+  hi = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+  lo = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+}
 
 }  // namespace agnn

@@ -32,6 +32,8 @@ struct GatherParams {
   void* out;
   int64_t ld_out;
   void* out_lo;  // optional (fp32 only): out receives rna_tf32(y), out_lo rna_tf32(y - out) -- agnn_gemm operands
+  const float* pair_amax;  // optional (fp32, CONCAT, with out_lo): out / out_lo are fp16 matrices receiving the F16X3
+                           // operand pair of s y, s = f16_scale_of(*pair_amax); ld_out counts fp16 elements
   float* heavy_ws;      // optional: partial rows of the heavy-row path, [max_chunks][n_feat]
   int64_t max_chunks;
 };
@@ -44,11 +46,20 @@ __device__ __forceinline__ bool is_heavy(const GatherParams& p, const agnn_rel_t
   return p.heavy_ws && R.heavy_rows && deg >= kHeavyRow;
 }
 
-// store one 16-byte vector, optionally as the TF32 hi / lo pair the tensor-core GEMM consumes
+// store one 16-byte vector at element `idx` of the output, optionally as the TF32 hi / lo pair the tensor-core GEMM
+// consumes, or (f16s != 0) as the fp16 hi / lo pair of f16s * v
 template <typename T>
-__device__ __forceinline__ void store_split(T* hi_ptr, T* lo_ptr, const float (&v)[Vec16<T>::E]) {
+__device__ __forceinline__ void store_split(T* out, T* out_lo, int64_t idx, const float (&v)[Vec16<T>::E],
+                                            float f16s = 0.f) {
   if constexpr (sizeof(T) == 4) {
-    if (lo_ptr) {
+    if (f16s != 0.f) {
+      uint2 h, l;
+      f16_pair4(v, f16s, h, l);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + idx) = h;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out_lo) + idx) = l;
+      return;
+    }
+    if (out_lo) {
       float h[4], l[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -58,12 +69,12 @@ __device__ __forceinline__ void store_split(T* hi_ptr, T* lo_ptr, const float (&
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v[e] - h[e]));
         l[e] = __uint_as_float(lb);
       }
-      Vec16<T>::store(hi_ptr, h);
-      Vec16<T>::store(lo_ptr, l);
+      Vec16<T>::store(out + idx, h);
+      Vec16<T>::store(out_lo + idx, l);
       return;
     }
   }
-  Vec16<T>::store(hi_ptr, v);
+  Vec16<T>::store(out + idx, v);
 }
 
 template <typename T, int LANES, int V>
@@ -75,6 +86,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel
   const int F = p.n_feat;
   T* const out = static_cast<T*>(p.out);
   T* const out_lo = static_cast<T*>(p.out_lo);
+  const float f16s = p.pair_amax ? f16_scale_of(__ldg(p.pair_amax)) : 0.f;
 
   for (int row = blockIdx.x * kRowsPerBlock + threadIdx.x / LANES; row < p.n_rows;
        row += gridDim.x * kRowsPerBlock) {
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel
             float o[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) o[e] = acc[v][e] * s;
-            store_split<T>(out + off + c, out_lo ? out_lo + off + c : nullptr, o);
+            store_split<T>(out, out_lo, off + c, o, f16s);
           }
         }
       } else {
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel
           float o[E];
 #pragma unroll
           for (int e = 0; e < E; ++e) o[e] = tot[v][e] + (p.self_add ? selfv[v][e] : 0.f);
-          store_split<T>(out + off + c, out_lo ? out_lo + off + c : nullptr, o);
+          store_split<T>(out, out_lo, off + c, o, f16s);
         }
       }
     }
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel
         if (c < F) {
           float t[E];
           VT::load_nc(cp + c, t);
-          store_split<T>(out + off + c, out_lo ? out_lo + off + c : nullptr, t);
+          store_split<T>(out, out_lo, off + c, t, f16s);
         }
       }
     }
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_sum_kernel(co
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const int c = (v * 32 + lane) * E;
-      if (c < F) store_split<T>(out + off + c, out_lo ? out_lo + off + c : nullptr, tot[v]);
+      if (c < F) store_split<T>(out, out_lo, off + c, tot[v]);
     }
     if (p.copy) {
       const T* cp = static_cast<const T*>(p.copy) + (int64_t)row * p.ld_copy;
@@ -318,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_sum_kernel(co
         if (c < F) {
           float tmp[E];
           VT::load_nc(cp + c, tmp);
-          store_split<T>(out + coff + c, out_lo ? out_lo + coff + c : nullptr, tmp);
+          store_split<T>(out, out_lo, coff + c, tmp);
         }
       }
     }
@@ -412,6 +424,7 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
   const int F = p.n_feat;
   T* const out = static_cast<T*>(p.out);
   T* const out_lo = static_cast<T*>(p.out_lo);
+  const float f16s = p.pair_amax ? f16_scale_of(__ldg(p.pair_amax)) : 0.f;
   int64_t g = 0, item = 0;
   for (int r = 0; r < p.n_rel; ++r) {
     const agnn_rel_t& R = p.rel[r];
@@ -456,7 +469,7 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
             }
 #pragma unroll
             for (int e = 0; e < E; ++e) o[e] = acc[v][e] * s;
-            store_split<T>(out + off + cc, out_lo ? out_lo + off + cc : nullptr, o);
+            store_split<T>(out, out_lo, off + cc, o, f16s);
           }
         }
       } else {
@@ -484,7 +497,7 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
             }
 #pragma unroll
             for (int e = 0; e < E; ++e) cur[e] = fmaf(acc[v][e], s, cur[e]);
-            store_split<T>(out + off + cc, out_lo ? out_lo + off + cc : nullptr, cur);
+            store_split<T>(out, out_lo, off + cc, cur);
           }
         }
       }
@@ -583,6 +596,15 @@ extern "C" int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int
                                   const agnn_rel_t* rels, const void* self_add, int64_t ld_self, const void* copy,
                                   int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out, void* out_lo,
                                   void* heavy_workspace, size_t heavy_workspace_bytes, agnn_stream_t stream) {
+  return agnn_gather_reduce_f16(n_rows, n_feat, dtype, scale, combine, n_rel, rels, self_add, ld_self, copy, ld_copy,
+                                copy_col, out, ld_out, out_lo, nullptr, heavy_workspace, heavy_workspace_bytes, stream);
+}
+
+extern "C" int agnn_gather_reduce_f16(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
+                                      const agnn_rel_t* rels, const void* self_add, int64_t ld_self, const void* copy,
+                                      int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out, void* out_lo,
+                                      const float* pair_amax, void* heavy_workspace, size_t heavy_workspace_bytes,
+                                      agnn_stream_t stream) {
   if (n_rows < 0 || n_feat <= 0 || n_rel < 1 || n_rel > AGNN_MAX_REL || !rels || !out)
     return fail(AGNN_ERR_ARG, "gather_reduce: bad sizes (n_rows=%d n_feat=%d n_rel=%d)", n_rows, n_feat, n_rel);
   if (dtype != AGNN_F32 && dtype != AGNN_BF16) return fail(AGNN_ERR_ARG, "gather_reduce: dtype %d", dtype);
@@ -597,6 +619,10 @@ extern "C" int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int
   p.copy_col = copy_col;
   p.self_add = self_add; p.ld_self = ld_self; p.copy = copy; p.ld_copy = ld_copy; p.out = out; p.ld_out = ld_out;
   p.out_lo = out_lo;
+  p.pair_amax = pair_amax;
+  if (pair_amax && (dtype != AGNN_F32 || combine != AGNN_COMBINE_CONCAT || !out_lo || (ld_out * 2) % 16))
+    return fail(AGNN_ERR_ARG, "gather_reduce: the fp16 hi/lo output needs fp32 inputs, the concatenated layout, out_lo "
+                              "and a row stride that is a multiple of 8 fp16 elements");
   p.heavy_ws = nullptr;
   p.max_chunks = 0;
   bool any_heavy = false;
@@ -609,7 +635,7 @@ extern "C" int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int
   if (out_lo && (dtype != AGNN_F32 || !aligned16(out_lo)))
     return fail(AGNN_ERR_ARG, "gather_reduce: the TF32 hi/lo output needs fp32 and a 16-byte aligned out_lo");
   int rc;
-  if ((rc = check_matrix("gather_reduce: out", out, ld_out, eb))) return rc;
+  if ((rc = check_matrix("gather_reduce: out", out, ld_out, pair_amax ? 2 : eb))) return rc;
   if (self_add && (rc = check_matrix("gather_reduce: self_add", self_add, ld_self, eb))) return rc;
   if (copy && ((rc = check_matrix("gather_reduce: copy", copy, ld_copy, eb)) || copy_col % ev))
     return rc ? rc : fail(AGNN_ERR_ARG, "gather_reduce: copy_col must be a multiple of %d", ev);

@@ -12,6 +12,11 @@
 //                     agnn_split_tf32) and D = Ahi*Bhi + Ahi*Blo + Alo*Bhi accumulates in fp32 TMEM.
 //   AGNN_GEMM_TF32    one product (hi only): 1e-3 relative, for experiments.
 //   AGNN_GEMM_BF16    bf16 operands, fp32 accumulation, bf16 or fp32 output: the stated bf16 mode.
+//   AGNN_GEMM_F16X3   fp32 parity mode on the f16 MMA (twice the TF32 rate, half the operand bytes): every operand is
+//                     hi = fp16(s x), lo = fp16(s x - hi) with one power-of-two scale s per tensor derived from its
+//                     amax (agnn_amax, agnn_split_f16; max |s x| in [2^13, 2^14)).  fp16 has TF32's 11-bit significand,
+//                     so the three products carry the same 22 bits as TF32X3 for elements down to 2^-17 of the
+//                     tensor's amax (fixed point 2^-25 of the scaled range below); the epilogue undoes s_a s_b exactly.
 //
 // Operand layouts (both handled by the UMMA descriptors, no transposition pass):
 //   K-major  : matrix stored [MN, K] row-major (activations as A, nn.Linear weights as B)
@@ -58,7 +63,11 @@ struct GemmParams {
   int64_t split_stride;  // elements between split partials
   const float* bias;
   int flags;
+  const float* amax_a;   // F16X3: device scalars the operand scales derive from (null = unscaled operands)
+  const float* amax_b;
 };
+
+enum { kFmtTF32 = 0, kFmtBF16 = 1, kFmtF16 = 2 };
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,9 +133,9 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-template <bool BF16>
+template <int FMT>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (BF16) {
+  if constexpr (FMT != kFmtTF32) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
@@ -165,13 +174,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // (assembled in the MMA issue loop: constant high word, low word = address >> 4 | LBO >> 4 << 16)
 
 // instruction descriptor (cute::UMMA::InstrDescriptor), D = fp32
-__host__ __device__ constexpr uint32_t instr_desc(bool bf16, bool a_mn, bool b_mn, int m, int n) {
-  return (1u << 4) | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+// operand format codes (cute::UMMA::F16F32Format): F16 = 0, BF16 = 1, TF32 = 2
+__host__ __device__ constexpr uint32_t instr_desc(int fmt, bool a_mn, bool b_mn, int m, int n) {
+  return (1u << 4) | ((fmt == kFmtTF32 ? 2u : fmt == kFmtBF16 ? 1u : 0u) << 7) |
+         ((fmt == kFmtTF32 ? 2u : fmt == kFmtBF16 ? 1u : 0u) << 10) | ((a_mn ? 1u : 0u) << 15) |
          ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <bool BF16, bool A_MN, bool B_MN, int TERMS>
+template <int FMT, bool A_MN, bool B_MN, int TERMS>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr bool BF16 = FMT != kFmtTF32;       // 2-byte operands (bf16 or fp16): same tiles and descriptors
   constexpr int kElem = BF16 ? 2 : 4;
   constexpr int kBlockK = kRowBytes / kElem;   // 32 tf32 / 64 bf16
   constexpr int kUmmaK = 32 / kElem;           // 8 tf32 / 16 bf16
@@ -180,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   constexpr int kStages = kSmemBudget / kStageBytes;
   constexpr int kChunk = kRowBytes / kElem;    // MN elements per 128-byte row of an MN-major tile
   constexpr int kChunks = kBlockM / kChunk;    // TMA boxes per MN-major tile
-  constexpr uint32_t kIdesc = instr_desc(BF16, A_MN, B_MN, kBlockM, kBlockN);
+  constexpr uint32_t kIdesc = instr_desc(FMT, A_MN, B_MN, kBlockM, kBlockN);
   constexpr uint32_t kMnSbo = BF16 ? 1024 : 512;
   constexpr uint64_t kMnLayout = BF16 ? 2 : 1;
 
@@ -308,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 // 32-bit operands use the 32-byte-atom swizzle (groups of 4 K rows, 512 B).
                 const uint64_t da = ((uint64_t)(A_MN ? kHiMn : kHiK) << 32) | (a_lo + k * kStepA);
                 const uint64_t db = ((uint64_t)(B_MN ? kHiMn : kHiK) << 32) | (b_lo + k * kStepB);
-                umma<BF16>(tmem_d, da, db, kIdesc, accumulate);
+                umma<FMT>(tmem_d, da, db, kIdesc, accumulate);
                 accumulate = 1;
               }
             }
@@ -325,6 +337,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) belong to this warp
     uint8_t* sbuf = store_base + quarter * 2 * kStoreBufBytes;
     const bool direct = p.split_k == 1;
+    // F16X3: the operands were scaled by powers of two; dividing by them (exactly) comes before the bias
+    const bool scaled = p.amax_a != nullptr;
+    const float inv_a = scaled ? 1.f / f16_scale_of(__ldg(p.amax_a)) : 1.f;
+    const float inv_b = scaled ? 1.f / f16_scale_of(__ldg(p.amax_b)) : 1.f;
     int cc = 0;
     int sc = 0;                                    // staged chunks so far (buffer = sc & 1)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -336,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       const int row = m0 + quarter * 32 + lane;
       // The bias is the first addend: its loads are in flight while the first chain is computed.
       float acc[kBlockN];
-      if (direct && p.bias) {
+      if (direct && p.bias && !scaled) {
 #pragma unroll
         for (int j = 0; j < kBlockN; ++j) acc[j] = n0 + j < p.N ? __ldg(p.bias + n0 + j) : 0.f;
       } else {
@@ -358,6 +374,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      if (scaled) {
+        if (direct && p.bias) {
+#pragma unroll
+          for (int j = 0; j < kBlockN; ++j)
+            acc[j] = (acc[j] * inv_a) * inv_b + (n0 + j < p.N ? __ldg(p.bias + n0 + j) : 0.f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kBlockN; ++j) acc[j] = (acc[j] * inv_a) * inv_b;
+        }
       }
       if (p.tma_store) {
         // registers -> 128-byte-swizzled shared memory (this warp's 32 rows x 32 columns) -> one TMA store
@@ -510,16 +536,18 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D map over a row-major matrix [rows, cols] (cols contiguous), box = box_cols x box_rows, 128B swizzle
-int make_map(CUtensorMap* map, const void* ptr, bool bf16, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+int make_map(CUtensorMap* map, const void* ptr, int fmt, int64_t rows, int64_t cols, int64_t ld, int box_cols,
              int box_rows, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(AGNN_ERR_CUDA, "gemm: cuTensorMapEncodeTiled is not available from this driver");
+  const bool bf16 = fmt != kFmtTF32;   // 2-byte elements
   const int eb = bf16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * eb};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult rc = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult rc = fn(map, fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : fmt == kFmtF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    (mn_major && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -527,15 +555,15 @@ int make_map(CUtensorMap* map, const void* ptr, bool bf16, int64_t rows, int64_t
   return AGNN_OK;
 }
 
-template <bool BF16, bool A_MN, bool B_MN, int TERMS>
+template <int FMT, bool A_MN, bool B_MN, int TERMS>
 int launch(const GemmParams& p, int grid, cudaStream_t st) {
-  constexpr int kElem = BF16 ? 2 : 4;
+  constexpr int kElem = FMT != kFmtTF32 ? 2 : 4;
   constexpr int kParts = TERMS == 3 ? 2 : 1;
   constexpr int kStageBytes = 2 * kParts * kTileBytes;
   constexpr int kStages = kSmemBudget / kStageBytes;
   constexpr int smem = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
   (void)kElem;
-  auto kern = gemm_kernel<BF16, A_MN, B_MN, TERMS>;
+  auto kern = gemm_kernel<FMT, A_MN, B_MN, TERMS>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -546,12 +574,12 @@ int launch(const GemmParams& p, int grid, cudaStream_t st) {
   return check_launch("gemm");
 }
 
-template <bool BF16, int TERMS>
+template <int FMT, int TERMS>
 int dispatch_layout(bool a_mn, bool b_mn, const GemmParams& p, int grid, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BF16, false, false, TERMS>(p, grid, st);
-  if (!a_mn && b_mn) return launch<BF16, false, true, TERMS>(p, grid, st);
-  if (a_mn && b_mn) return launch<BF16, true, true, TERMS>(p, grid, st);
-  return launch<BF16, true, false, TERMS>(p, grid, st);
+  if (!a_mn && !b_mn) return launch<FMT, false, false, TERMS>(p, grid, st);
+  if (!a_mn && b_mn) return launch<FMT, false, true, TERMS>(p, grid, st);
+  if (a_mn && b_mn) return launch<FMT, true, true, TERMS>(p, grid, st);
+  return launch<FMT, true, false, TERMS>(p, grid, st);
 }
 
 }  // namespace
@@ -570,8 +598,74 @@ extern "C" int agnn_split_tf32(const float* x, int64_t rows, int64_t cols, int64
   return check_launch("split_tf32");
 }
 
+// *amax = max(*amax, max |x|): non-negative floats order like their bit patterns, so one integer atomicMax per block
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, int64_t rows, int cols4, int64_t ld_x,
+                                                    float* __restrict__ amax) {
+  __shared__ uint32_t red[8];
+  const int64_t total = rows * cols4;
+  uint32_t m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + c));
+    m = max(max(m, __float_as_uint(v.x) & 0x7fffffffu), __float_as_uint(v.y) & 0x7fffffffu);
+    m = max(max(m, __float_as_uint(v.z) & 0x7fffffffu), __float_as_uint(v.w) & 0x7fffffffu);
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = max(m, red[w]);
+    if (m) atomicMax(reinterpret_cast<unsigned int*>(amax), m);
+  }
+}
+
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, int64_t rows, int cols4,
+                                                         int64_t ld_x, const float* __restrict__ amax,
+                                                         __half* __restrict__ hi, __half* __restrict__ lo, int64_t ld_o) {
+  const float s = f16_scale_of(__ldg(amax));
+  const int64_t total = rows * cols4;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + c));
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    uint2 h, l;
+    f16_pair4(in, s, h, l);
+    *reinterpret_cast<uint2*>(hi + r * ld_o + c) = h;
+    *reinterpret_cast<uint2*>(lo + r * ld_o + c) = l;
+  }
+}
+
+extern "C" int agnn_amax(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* amax, agnn_stream_t stream) {
+  if (rows < 0 || cols < 0 || !amax) return fail(AGNN_ERR_ARG, "amax: bad arguments");
+  if (rows == 0 || cols == 0) return AGNN_OK;
+  if (cols % 4 || (ld_x * 4) % 16 || !aligned16(x))
+    return fail(AGNN_ERR_ARG, "amax: needs 16-byte aligned rows and a column count multiple of 4");
+  int64_t blocks = ceil_div(rows * (cols / 4), 256 * 4);
+  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  amax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, (int)(cols / 4), ld_x, amax);
+  return check_launch("amax");
+}
+
+extern "C" int agnn_split_f16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax, void* hi,
+                              void* lo, int64_t ld_out, agnn_stream_t stream) {
+  if (rows < 0 || cols < 0 || !amax || !hi || !lo) return fail(AGNN_ERR_ARG, "split_f16: bad arguments");
+  if (rows == 0 || cols == 0) return AGNN_OK;
+  if (cols % 4 || (ld_x * 4) % 16 || (ld_out * 2) % 16 || !aligned16(x) || !aligned16(hi) || !aligned16(lo))
+    return fail(AGNN_ERR_ARG, "split_f16: needs 16-byte aligned rows and a column count multiple of 4");
+  int64_t blocks = ceil_div(rows * (cols / 4), 256);
+  if (blocks > kNumSM * 16) blocks = kNumSM * 16;
+  split_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, (int)(cols / 4), ld_x, amax,
+                                                                        static_cast<__half*>(hi), static_cast<__half*>(lo),
+                                                                        ld_out);
+  return check_launch("split_f16");
+}
+
 extern "C" int agnn_gemm_split_k(int precision, int64_t M, int64_t N, int64_t K) {
-  const int block_k = precision == AGNN_GEMM_BF16 ? 64 : 32;
+  const int block_k = (precision == AGNN_GEMM_BF16 || precision == AGNN_GEMM_F16X3) ? 64 : 32;
   const int64_t tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN);
   const int64_t kb = ceil_div(K, block_k);
   if (tiles >= kNumSM || kb < 16) return 1;
@@ -599,16 +693,30 @@ extern "C" int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, i
                          const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb, void* c,
                          int64_t ldc, const float* bias, int flags, int split_k, void* workspace,
                          size_t workspace_bytes, agnn_stream_t stream) {
-  if (precision != AGNN_GEMM_TF32X3 && precision != AGNN_GEMM_TF32 && precision != AGNN_GEMM_BF16)
+  return agnn_gemm_scaled(precision, a_layout, b_layout, M, N, K, a_hi, a_lo, lda, nullptr, b_hi, b_lo, ldb, nullptr, c,
+                          ldc, bias, flags, split_k, workspace, workspace_bytes, stream);
+}
+
+extern "C" int agnn_gemm_scaled(int precision, int a_layout, int b_layout, int64_t M, int64_t N, int64_t K,
+                                const void* a_hi, const void* a_lo, int64_t lda, const float* amax_a, const void* b_hi,
+                                const void* b_lo, int64_t ldb, const float* amax_b, void* c, int64_t ldc,
+                                const float* bias, int flags, int split_k, void* workspace, size_t workspace_bytes,
+                                agnn_stream_t stream) {
+  if (precision != AGNN_GEMM_TF32X3 && precision != AGNN_GEMM_TF32 && precision != AGNN_GEMM_BF16 &&
+      precision != AGNN_GEMM_F16X3)
     return fail(AGNN_ERR_ARG, "gemm: unknown precision mode %d", precision);
+  if ((amax_a || amax_b) && (precision != AGNN_GEMM_F16X3 || !amax_a || !amax_b))
+    return fail(AGNN_ERR_ARG, "gemm: operand scales belong to the F16X3 mode and come in pairs");
   if (M < 0 || N < 0 || K < 0 || !c || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31))
     return fail(AGNN_ERR_ARG, "gemm: bad sizes");
   if (M == 0 || N == 0) return AGNN_OK;
   const bool bf16 = precision == AGNN_GEMM_BF16;
-  const int eb = bf16 ? 2 : 4, block_k = kRowBytes / eb, chunk = kRowBytes / eb;
+  const bool three = precision == AGNN_GEMM_TF32X3 || precision == AGNN_GEMM_F16X3;
+  const int fmt = bf16 ? kFmtBF16 : precision == AGNN_GEMM_F16X3 ? kFmtF16 : kFmtTF32;
+  const int eb = fmt == kFmtTF32 ? 4 : 2, block_k = kRowBytes / eb, chunk = kRowBytes / eb;
   const bool a_mn = a_layout == AGNN_LAYOUT_MN_MAJOR, b_mn = b_layout == AGNN_LAYOUT_MN_MAJOR;
-  if (!a_hi || !b_hi || (precision == AGNN_GEMM_TF32X3 && (!a_lo || !b_lo)))
-    return fail(AGNN_ERR_ARG, "gemm: null operand (TF32X3 needs the hi and lo parts of both operands)");
+  if (!a_hi || !b_hi || (three && (!a_lo || !b_lo)))
+    return fail(AGNN_ERR_ARG, "gemm: null operand (the three-product modes need the hi and lo parts of both operands)");
   if ((lda * eb) % 16 || (ldb * eb) % 16 || !aligned16(a_hi) || !aligned16(b_hi) || (a_lo && !aligned16(a_lo)) ||
       (b_lo && !aligned16(b_lo)))
     return fail(AGNN_ERR_UNSUPPORTED, "gemm: operands must be 16-byte aligned with 16-byte multiple row strides");
@@ -623,7 +731,9 @@ extern "C" int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, i
   p.k_blocks_per_split = (int)ceil_div(p.k_blocks, split_k);
   split_k = (int)ceil_div(p.k_blocks, p.k_blocks_per_split);
   p.split_k = split_k;
-  p.chain_blocks = precision == AGNN_GEMM_TF32X3 ? 2 : (1 << 30);
+  p.chain_blocks = three ? 2 : (1 << 30);      // 24 MMAs per TMEM chain in both three-product modes
+  p.amax_a = amax_a;
+  p.amax_b = amax_b;
   p.tiles_m = (int)ceil_div(M, kBlockM);
   p.tiles_n = (int)ceil_div(N, kBlockN);
   p.bias = bias;
@@ -640,28 +750,29 @@ extern "C" int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, i
   int rc;
   const void* a_parts[2] = {a_hi, a_lo};
   const void* b_parts[2] = {b_hi, b_lo};
-  const int parts = precision == AGNN_GEMM_TF32X3 ? 2 : 1;
+  const int parts = three ? 2 : 1;
   for (int i = 0; i < parts; ++i) {
     // K-major: [MN, K] row-major, box = block_k x 128 rows.  MN-major: [K, MN] row-major, box = chunk x block_k rows.
-    rc = a_mn ? make_map(&p.map_a[i], a_parts[i], bf16, K, M, lda, chunk, block_k, true)
-              : make_map(&p.map_a[i], a_parts[i], bf16, M, K, lda, block_k, kBlockM, false);
+    rc = a_mn ? make_map(&p.map_a[i], a_parts[i], fmt, K, M, lda, chunk, block_k, true)
+              : make_map(&p.map_a[i], a_parts[i], fmt, M, K, lda, block_k, kBlockM, false);
     if (rc) return rc;
-    rc = b_mn ? make_map(&p.map_b[i], b_parts[i], bf16, K, N, ldb, chunk, block_k, true)
-              : make_map(&p.map_b[i], b_parts[i], bf16, N, K, ldb, block_k, kBlockN, false);
+    rc = b_mn ? make_map(&p.map_b[i], b_parts[i], fmt, K, N, ldb, chunk, block_k, true)
+              : make_map(&p.map_b[i], b_parts[i], fmt, N, K, ldb, block_k, kBlockN, false);
     if (rc) return rc;
   }
   const bool acc_relu = (flags & AGNN_GEMM_ACCUMULATE) && (flags & AGNN_GEMM_RELU);
   if (split_k == 1 && !(flags & AGNN_GEMM_OUT_BF16) && !acc_relu && (ldc * 4) % 16 == 0 && aligned16(c)) {
-    rc = make_map(&p.map_c, c, false, M, N, ldc, kStoreBox, kStoreBox, false);
+    rc = make_map(&p.map_c, c, kFmtTF32, M, N, ldc, kStoreBox, kStoreBox, false);
     if (rc) return rc;
     p.tma_store = 1;
   }
   const int64_t work = (int64_t)p.tiles_m * p.tiles_n * split_k;
   const int grid = (int)(work < kNumSM ? work : kNumSM);
   cudaStream_t st = (cudaStream_t)stream;
-  if (bf16) rc = dispatch_layout<true, 1>(a_mn, b_mn, p, grid, st);
-  else if (precision == AGNN_GEMM_TF32X3) rc = dispatch_layout<false, 3>(a_mn, b_mn, p, grid, st);
-  else rc = dispatch_layout<false, 1>(a_mn, b_mn, p, grid, st);
+  if (bf16) rc = dispatch_layout<kFmtBF16, 1>(a_mn, b_mn, p, grid, st);
+  else if (precision == AGNN_GEMM_F16X3) rc = dispatch_layout<kFmtF16, 3>(a_mn, b_mn, p, grid, st);
+  else if (precision == AGNN_GEMM_TF32X3) rc = dispatch_layout<kFmtTF32, 3>(a_mn, b_mn, p, grid, st);
+  else rc = dispatch_layout<kFmtTF32, 1>(a_mn, b_mn, p, grid, st);
   if (rc) return rc;
   if (split_k > 1) {
     int64_t blocks = ceil_div(M * N, 256);

@@ -271,9 +271,11 @@ __global__ void __launch_bounds__(kThreads) grad_prepare_kernel(const float* __r
                                                                  const float* __restrict__ relu_out, int64_t ld_o,
                                                                  float* __restrict__ hi, float* __restrict__ lo,
                                                                  int64_t ld_s, float* __restrict__ part, int64_t rows,
-                                                                 int cols) {
+                                                                 int cols, const float* __restrict__ amax) {
   __shared__ float red[kWarps][32 * 4 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // amax given: hi / lo are fp16 matrices (ld_s in fp16 elements) receiving the F16X3 operand pair of s g'
+  const float f16s = amax ? f16_scale_of(__ldg(amax)) : 0.f;
   float acc[V][4];
 #pragma unroll
   for (int i = 0; i < V; ++i)
@@ -289,6 +291,23 @@ __global__ void __launch_bounds__(kThreads) grad_prepare_kernel(const float* __r
       for (int i = 0; i < V; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[i][e] = o[i][e] > 0.f ? v[i][e] : 0.f;
+    }
+    if (f16s != 0.f) {
+      __half* hh = reinterpret_cast<__half*>(hi) + row * ld_s;
+      __half* ll = reinterpret_cast<__half*>(lo) + row * ld_s;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][e] += v[i][e];
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+          uint2 a, b;
+          f16_pair4(v[i], f16s, a, b);
+          *reinterpret_cast<uint2*>(hh + c) = a;
+          *reinterpret_cast<uint2*>(ll + c) = b;
+        }
+      }
+      continue;
     }
 #pragma unroll
     for (int i = 0; i < V; ++i)
@@ -459,7 +478,17 @@ extern "C" int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float*
 extern "C" int agnn_grad_prepare(const float* g, int64_t ld_g, const float* relu_out, int64_t ld_o, float* hi, float* lo,
                                  int64_t ld_s, float* partials, float* colsum, int64_t rows, int cols,
                                  agnn_stream_t stream) {
-  int rc = check("grad_prepare", rows, cols, {g, hi, lo}, {ld_g, ld_s, relu_out ? ld_o : 0});
+  return agnn_grad_prepare_f16(g, ld_g, relu_out, ld_o, nullptr, hi, lo, ld_s, partials, colsum, rows, cols, stream);
+}
+
+extern "C" int agnn_grad_prepare_f16(const float* g, int64_t ld_g, const float* relu_out, int64_t ld_o, const float* amax,
+                                     void* hi_v, void* lo_v, int64_t ld_s, float* partials, float* colsum, int64_t rows,
+                                     int cols, agnn_stream_t stream) {
+  float* hi = static_cast<float*>(hi_v);
+  float* lo = static_cast<float*>(lo_v);
+  // fp16 outputs: a row stride of ld_s halves must be a 16-byte multiple, i.e. ld_s / 2 floats a multiple of 4
+  if (amax && ld_s % 8) return fail(AGNN_ERR_ARG, "grad_prepare: fp16 row stride must be a multiple of 8 elements");
+  int rc = check("grad_prepare", rows, cols, {g, hi, lo}, {ld_g, amax ? ld_s / 2 : ld_s, relu_out ? ld_o : 0});
   if (rc) return rc;
   if (relu_out && !aligned16(relu_out)) return fail(AGNN_ERR_ARG, "grad_prepare: unaligned relu_out");
   if (colsum && !partials) return fail(AGNN_ERR_ARG, "grad_prepare: colsum needs the partials buffer");
@@ -469,7 +498,7 @@ extern "C" int agnn_grad_prepare(const float* g, int64_t ld_g, const float* relu
   }
   const int blocks = row_blocks(rows);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(V) grad_prepare_kernel<V><<<blocks, kThreads, 0, st>>>(g, ld_g, relu_out, ld_o, hi, lo, ld_s, partials, rows, cols)
+#define CALL(V) grad_prepare_kernel<V><<<blocks, kThreads, 0, st>>>(g, ld_g, relu_out, ld_o, hi, lo, ld_s, partials, rows, cols, amax)
   AGNN_DISPATCH_V(cols, CALL);
 #undef CALL
   if (colsum) reduce_partials_kernel<<<dim3((unsigned)ceil_div(cols, 32), 1), kThreads, 0, st>>>(partials, blocks, cols, colsum, 0, 0);

@@ -63,7 +63,96 @@ class Split:
         return self.hi + self.lo
 
 
-Operand = Union[torch.Tensor, Split]
+class SplitH:
+    """An fp32 matrix as the fp16 ``hi`` + ``lo`` pair of ``s * x`` (``agnn_split_f16``; ``s`` = the power of two
+    derived from the device scalar ``amax``): the operand form of the F16X3 mode -- fp32-grade like ``Split``, at
+    twice the tensor-core rate and half the bytes."""
+    __slots__ = ("hi", "lo", "amax")
+
+    def __init__(self, hi, lo, amax):
+        self.hi, self.lo, self.amax = hi, lo, amax
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def merged(self):
+        return (self.hi.float() + self.lo.float()) / f16_scale(self.amax)
+
+
+def f16_scale(amax: torch.Tensor) -> torch.Tensor:
+    """The scale the kernels derive from an amax scalar (csrc/common.cuh::f16_scale_of), as a device tensor."""
+    e = torch.frexp(amax)[1].to(torch.float32) - 1       # floor(log2 amax), exact (amax = m 2^e', m in [0.5, 1))
+    k = (13 - e).clamp(-100, 100)
+    ok = (amax > 1.1754944e-38) & torch.isfinite(amax)
+    return torch.where(ok, torch.exp2(k), torch.ones_like(amax))
+
+
+Operand = Union[torch.Tensor, Split, SplitH]
+
+_PARITY_OPERANDS = os.environ.get("AGNN_PARITY_OPERANDS", "tf32")
+
+
+def parity_operands() -> str:
+    return _PARITY_OPERANDS
+
+
+def set_parity_operands(name: str) -> None:
+    """Operand form of the fp32 parity mode in the fused message-passing layers: ``"tf32"`` (3xTF32) or ``"f16"``
+    (3 x fp16 with per-tensor power-of-two scales; same accuracy, twice the MMA rate)."""
+    global _PARITY_OPERANDS
+    if name not in ("tf32", "f16"):
+        raise ValueError(name)
+    _PARITY_OPERANDS = name
+
+
+def new_amax(device) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.float32, device=device)
+
+
+def amax_into(amax: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """``amax = max(amax, max |x|)`` on the device (agnn_amax); several tensors may share one scalar."""
+    _need_cuda(x)
+    if x.numel() == 0:
+        return amax
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 4 or x.stride(0) % 4 \
+            or x.data_ptr() % 16:
+        return torch.maximum(amax, x.detach().abs().max().float().reshape(1), out=amax)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(_lib.lib().agnn_amax(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), amax.data_ptr(), stream),
+               "agnn_amax")
+    _lib.count_launches(1)
+    return amax
+
+
+def f16_ok(x: torch.Tensor) -> bool:
+    return (x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 8 == 0
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.shape[0] > 0)
+
+
+def split_f16(x: torch.Tensor, amax: Optional[torch.Tensor] = None) -> SplitH:
+    """hi = fp16(s x), lo = fp16(s x - hi); ``amax`` (device scalar >= max |x| / 4) is measured when not given."""
+    _need_cuda(x)
+    if not f16_ok(x):
+        raise ValueError("split_f16 needs an fp32 matrix with unit column stride, 16-byte aligned rows and a column "
+                         "count that is a multiple of 8")
+    if amax is None:
+        amax = amax_into(new_amax(x.device), x)
+    rows, cols = x.shape
+    buf = torch.empty((2, rows, cols), dtype=torch.float16, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(_lib.lib().agnn_split_f16(x.data_ptr(), rows, cols, x.stride(0), amax.data_ptr(), buf[0].data_ptr(),
+                                         buf[1].data_ptr(), cols, stream), "agnn_split_f16")
+    _lib.count_launches(1)
+    return SplitH(buf[0], buf[1], amax)
 
 
 def _rows_ok(t: torch.Tensor) -> bool:
@@ -95,12 +184,15 @@ def prepare(x: torch.Tensor) -> Operand:
 
 
 def pack(x: Operand):
-    """(tensor, tensor-or-None) for ``save_for_backward``; ``unpack`` restores the operand."""
-    return (x.hi, x.lo) if isinstance(x, Split) else (x, None)
+    """(tensor, tensor-or-None) for ``save_for_backward``; ``unpack`` restores the operand (a ``SplitH`` also needs
+    its ``amax``, which the caller keeps)."""
+    return (x.hi, x.lo) if isinstance(x, (Split, SplitH)) else (x, None)
 
 
-def unpack(first, second) -> Operand:
-    return first if second is None else Split(first, second)
+def unpack(first, second, amax=None) -> Operand:
+    if second is None:
+        return first
+    return SplitH(first, second, amax) if first.dtype == torch.float16 else Split(first, second)
 
 
 # Splits of small operands (weights) made inside a step: a weight is read by the forward GEMM and again by the
@@ -125,20 +217,38 @@ def _cached_split(x: torch.Tensor) -> Split:
     return hit[1]
 
 
-def _as_operand(x: Operand):
-    """(hi, lo, precision) for agnn_gemm, or None when the tensor cannot take the tcgen05 route."""
+def _cached_split_f16(x: torch.Tensor) -> SplitH:
+    if x.numel() > _SPLIT_CACHE_MAX_ELEMS:
+        return split_f16(x)
+    key = ("f16", x.data_ptr(), tuple(x.shape), x.stride(0), x._version)
+    hit = _split_cache.get(key)
+    if hit is None:
+        hit = _split_cache[key] = (x, split_f16(x))
+    return hit[1]
+
+
+def _as_operand(x: Operand, f16: bool = False):
+    """(hi, lo, precision, amax) for agnn_gemm, or None when the tensor cannot take the tcgen05 route.  ``f16``: the
+    other operand is an fp16 pair, so a plain fp32 tensor is split the same way."""
+    if isinstance(x, SplitH):
+        return x.hi, x.lo, _lib.GEMM_F16X3, x.amax
     if isinstance(x, Split):
-        return x.hi, x.lo, _lib.GEMM_TF32X3
+        return x.hi, x.lo, _lib.GEMM_TF32X3, None
     if x.dtype == torch.bfloat16:
-        return (x, None, _lib.GEMM_BF16) if _rows_ok(x) else None
+        return (x, None, _lib.GEMM_BF16, None) if _rows_ok(x) else None
+    if f16:
+        if not f16_ok(x):
+            return None
+        s = _cached_split_f16(x)
+        return s.hi, s.lo, _lib.GEMM_F16X3, s.amax
     if x.dtype == torch.float32 and _rows_ok(x) and x.shape[1] % 4 == 0:
         s = _cached_split(x)
-        return s.hi, s.lo, _lib.GEMM_TF32X3
+        return s.hi, s.lo, _lib.GEMM_TF32X3, None
     return None
 
 
 def plain(x: Operand) -> torch.Tensor:
-    return x.merged() if isinstance(x, Split) else x
+    return x.merged() if isinstance(x, (Split, SplitH)) else x
 
 
 _plain = plain
@@ -149,7 +259,8 @@ def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, 
     """agnn_gemm wrapper; returns None if the operands are not eligible (caller falls back)."""
     if _BACKEND != "tcgen05":
         return None
-    oa, ob = _as_operand(a), _as_operand(b)
+    f16 = isinstance(a, SplitH) or isinstance(b, SplitH)
+    oa, ob = _as_operand(a, f16), _as_operand(b, f16)
     if oa is None or ob is None or oa[2] != ob[2]:
         return None
     prec = oa[2]
@@ -173,6 +284,14 @@ def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, 
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def run():
+        if prec == _lib.GEMM_F16X3:
+            _lib.check(lib.agnn_gemm_scaled(prec, a_layout, b_layout, m, n, k, oa[0].data_ptr(), oa[1].data_ptr(),
+                                            oa[0].stride(0), oa[3].data_ptr(), ob[0].data_ptr(), ob[1].data_ptr(),
+                                            ob[0].stride(0), ob[3].data_ptr(), out.data_ptr(), out.stride(0),
+                                            bias.data_ptr() if bias is not None else None, flags, split_k,
+                                            ws.data_ptr() if ws is not None else None, ws_bytes, stream),
+                       "agnn_gemm_scaled")
+            return
         _lib.check(lib.agnn_gemm(prec, a_layout, b_layout, m, n, k, oa[0].data_ptr(),
                                  oa[1].data_ptr() if oa[1] is not None else None, oa[0].stride(0), ob[0].data_ptr(),
                                  ob[1].data_ptr() if ob[1] is not None else None, ob[0].stride(0), out.data_ptr(),

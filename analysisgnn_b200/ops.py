@@ -136,14 +136,19 @@ def gather_bytes(rels: Sequence[Rel], n_rows: int, n_feat: int, elem: int, conca
 
 def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: bool, concat: bool,
                   self_add: Optional[torch.Tensor] = None, copy: Optional[torch.Tensor] = None,
-                  copy_col: int = 0, out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  copy_col: int = 0, out_lo: Optional[torch.Tensor] = None,
+                  pair_amax: Optional[torch.Tensor] = None) -> torch.Tensor:
     """agnn_gather_reduce on ``out`` ([n_rows, >= n_feat] view).  See include/agnn.h.  With ``out_lo``
-    the result is written as the TF32 hi / lo pair (``out``, ``out_lo``) that ``agnn_gemm`` consumes."""
+    the result is written as the TF32 hi / lo pair (``out``, ``out_lo``) that ``agnn_gemm`` consumes; with
+    ``pair_amax`` too, ``out`` / ``out_lo`` are fp16 and receive the F16X3 pair (agnn_gather_reduce_f16)."""
     out = _rows2d(out, "out")
+    if pair_amax is not None and (out.dtype != torch.float16 or out_lo is None or not concat):
+        raise ValueError("the fp16 operand pair needs fp16 out / out_lo buffers and the concatenated layout")
     if out_lo is not None and (out_lo.shape != out.shape or out_lo.stride() != out.stride()):
         raise ValueError("out_lo must match out in shape and strides")
     n_rows = out.shape[0]
-    arr = _pack(rels, n_feat, out.dtype)
+    in_dtype = torch.float32 if pair_amax is not None else out.dtype
+    arr = _pack(rels, n_feat, in_dtype)
     sa = _rows2d(self_add, "self_add") if self_add is not None else None
     cp = _rows2d(copy, "copy") if copy is not None else None
     stream = torch.cuda.current_stream(out.device).cuda_stream
@@ -157,6 +162,14 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
 
     def run():
+        if pair_amax is not None:
+            _lib.check(_lib.lib().agnn_gather_reduce_f16(
+                n_rows, n_feat, _lib.F32, _lib.SCALE_MEAN if mean else _lib.SCALE_NONE, _lib.COMBINE_CONCAT, len(rels),
+                arr, sa.data_ptr() if sa is not None else None, sa.stride(0) if sa is not None else 0,
+                cp.data_ptr() if cp is not None else None, cp.stride(0) if cp is not None else 0, int(copy_col),
+                out.data_ptr(), out.stride(0), out_lo.data_ptr(), pair_amax.data_ptr(),
+                ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gather_reduce_f16")
+            return
         _lib.check(_lib.lib().agnn_gather_reduce(
             n_rows, n_feat, _dtype_code(out), _lib.SCALE_MEAN if mean else _lib.SCALE_NONE,
             _lib.COMBINE_CONCAT if concat else _lib.COMBINE_SUM, len(rels), arr,
@@ -166,9 +179,11 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
             ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gather_reduce")
 
     if timer is not None and all(r.n_edges is not None for r in rels):
-        nbytes = gather_bytes(rels, n_rows, n_feat, out.element_size(), concat, sa is not None, cp is not None)
-        if out_lo is not None:      # every written row goes out twice (hi and lo)
-            nbytes += n_rows * n_feat * out.element_size() * ((len(rels) if concat else 1) + int(cp is not None))
+        nbytes = gather_bytes(rels, n_rows, n_feat, 4 if pair_amax is not None else out.element_size(), concat,
+                              sa is not None, cp is not None)
+        written = n_rows * n_feat * ((len(rels) if concat else 1) + int(cp is not None))
+        if pair_amax is None and out_lo is not None:   # every written row goes out twice (hi and lo); the fp16 pair
+            nbytes += written * out.element_size()     # is 2 + 2 bytes per element = one fp32 row, already counted
         timer.launch("gather_reduce", nbytes, out.device, run)
     else:
         run()
@@ -347,20 +362,36 @@ class _HeteroSageLayer(torch.autograd.Function):
         nt = len(plan.node_types)
         xs = {t: tensors[i].contiguous() for i, t in enumerate(plan.node_types)}
         outs, saved = [], []
+        # F16X3 operands: every aggregated row is a copy or a mean of input rows, so the amax over the layer's inputs
+        # bounds every operand the gather writes -- one scalar for all destination types
+        f16 = (linalg.parity_operands() == "f16" and linalg.backend() == "tcgen05"
+               and all(v.dtype == torch.float32 and v.shape[1] % 8 == 0 for v in xs.values()))
+        x_amax = None
+        if f16:
+            x_amax = linalg.new_amax(tensors[0].device)
+            for v in xs.values():
+                linalg.amax_into(x_amax, v)
         for j, t in enumerate(plan.dst_types):
             wcat, bias = tensors[nt + 2 * j], tensors[nt + 2 * j + 1]
             x_t = xs[t]
             f = x_t.shape[1]
             rel_list = plan.incoming[t]
-            a_hi, a_lo = _operand_buffers(x_t.shape[0], (len(rel_list) + 1) * f, x_t)
             rels = [rel_of(csr.fwd[et], 0, xs[et[0]], out_col=(k + 1) * f, n_edges=csr.n_edges[et])
                     for k, et in enumerate(rel_list)]
-            gather_reduce(rels, a_hi, f, mean=True, concat=True, copy=x_t, copy_col=0, out_lo=a_lo)
-            a = _as_operand_pair(a_hi, a_lo)
+            if f16 and x_t.shape[0] > 0:
+                buf = torch.empty((2, x_t.shape[0], (len(rel_list) + 1) * f), dtype=torch.float16, device=x_t.device)
+                gather_reduce(rels, buf[0], f, mean=True, concat=True, copy=x_t, copy_col=0, out_lo=buf[1],
+                              pair_amax=x_amax)
+                a = linalg.SplitH(buf[0], buf[1], x_amax)
+            else:
+                a_hi, a_lo = _operand_buffers(x_t.shape[0], (len(rel_list) + 1) * f, x_t)
+                gather_reduce(rels, a_hi, f, mean=True, concat=True, copy=x_t, copy_col=0, out_lo=a_lo)
+                a = _as_operand_pair(a_hi, a_lo)
             o = linalg.linear(a, wcat, bias, relu=relu)
             outs.append(o)
             saved += [*linalg.pack(a), wcat, o]
         ctx.save_for_backward(*saved)
+        ctx.x_amax = x_amax
         ctx.set_materialize_grads(False)        # an unused destination type costs nothing in backward
         ctx.plan, ctx.csr, ctx.relu = plan, csr, relu
         ctx.feat = {t: xs[t].shape[1] for t in plan.node_types}
@@ -375,11 +406,12 @@ class _HeteroSageLayer(torch.autograd.Function):
         da = {}
         for j, t in enumerate(plan.dst_types):
             a_first, a_second, wcat, o = ctx.saved_tensors[4 * j:4 * j + 4]
-            a = linalg.unpack(a_first, a_second)
+            a = linalg.unpack(a_first, a_second, ctx.x_amax)
             g = douts[j]
             if g is None:
                 continue
-            g, db = prepare_grad(g, o if ctx.relu else None, ctx.needs_input_grad[3 + nt + 2 * j + 1])
+            g, db = prepare_grad(g, o if ctx.relu else None, ctx.needs_input_grad[3 + nt + 2 * j + 1],
+                                 f16=isinstance(a, linalg.SplitH))
             grads[nt + 2 * j + 1] = db
             da[t] = linalg.mm(g, wcat)
             if ctx.needs_input_grad[3 + nt + 2 * j]:
@@ -665,10 +697,12 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_colsum: bool = False):
+def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_colsum: bool = False,
+                 f16: bool = False):
     """What a projection's backward needs from its incoming gradient, in one pass (agnn_grad_prepare):
     ``g' = g * [relu_out > 0]`` as a GEMM operand and, optionally, the column sums of ``g'``.
-    Returns ``(operand, colsum or None)``."""
+    Returns ``(operand, colsum or None)``.  ``f16``: the operand is the fp16 pair of the F16X3 mode (one extra
+    pass measures the amax of ``g`` first)."""
     rows, cols = g.shape
     ok = (linalg.backend() == "tcgen05" and g.dtype == torch.float32 and g.is_cuda and rows > 0 and cols % 4 == 0
           and cols <= 1024 and g.stride(1) == 1 and g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0)
@@ -681,11 +715,23 @@ def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_
         g = g.contiguous()
         return linalg.prepare(g), (colsum(g) if want_colsum else None)
     lib = _lib.lib()
-    buf = torch.empty((2, rows, cols), dtype=torch.float32, device=g.device)
+    f16 = f16 and cols % 8 == 0
+    buf = torch.empty((2, rows, cols), dtype=torch.float16 if f16 else torch.float32, device=g.device)
     part = out = None
     if want_colsum:
         part = torch.empty((lib.agnn_row_blocks(rows), cols), dtype=torch.float32, device=g.device)
         out = torch.empty(cols, dtype=torch.float32, device=g.device)
+    if f16:
+        amax = linalg.amax_into(linalg.new_amax(g.device), g)
+        _lib.check(lib.agnn_grad_prepare_f16(g.data_ptr(), g.stride(0),
+                                             relu_out.data_ptr() if relu_out is not None else None,
+                                             relu_out.stride(0) if relu_out is not None else 0, amax.data_ptr(),
+                                             buf[0].data_ptr(), buf[1].data_ptr(), cols,
+                                             part.data_ptr() if part is not None else None,
+                                             out.data_ptr() if out is not None else None, rows, cols, _stream(g)),
+                   "agnn_grad_prepare_f16")
+        _lib.count_launches(2 if want_colsum else 1)
+        return linalg.SplitH(buf[0], buf[1], amax), out
     _lib.check(lib.agnn_grad_prepare(g.data_ptr(), g.stride(0), relu_out.data_ptr() if relu_out is not None else None,
                                      relu_out.stride(0) if relu_out is not None else 0, buf[0].data_ptr(),
                                      buf[1].data_ptr(), cols, part.data_ptr() if part is not None else None,

@@ -201,6 +201,7 @@ def workload_config(args, cpu=False):
                         "step = CSR build + fwd + bwd + clip(1.0) + AdamW, train mode dropout 0.3",
             "subgraphs_per_gpu": CFG["graphs"], "notes_per_subgraph": CFG["notes"], "hidden": CFG["hidden"],
             "layers": CFG["layers"], "parallelism": f"dp{args.gpus}",
+            "parity_gemm_operands": "n/a (CPU)" if cpu else getattr(args, "operands", "tf32"),
             "l2": "n/a (CPU)" if cpu else "L2 flushed between timed steps (256 MiB write); per-step activations "
                                            "(~2 GB) also exceed the 126 MB L2"}
 
@@ -252,6 +253,7 @@ def run_ours(args):
                                   world_size=world, collect_grads=True)
 
     from analysisgnn_b200 import linalg as _lin
+    _lin.set_parity_operands(args.operands)
 
     def fwd_bwd(tensors):
         _lin.begin_step()                          # weight splits are per step (a captured step re-splits on replay)
@@ -508,6 +510,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--operands", default=os.environ.get("AGNN_PARITY_OPERANDS", "tf32"), choices=["tf32", "f16"],
+                    help="operand form of the fp32 parity GEMMs in the message-passing layers: 3xTF32 or 3 x fp16 with "
+                         "per-tensor power-of-two scales (same accuracy, twice the MMA rate)")
     ap.add_argument("--skip-cpu", action="store_true", help="leave out the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -142,6 +142,15 @@ int agnn_gather_reduce(int32_t n_rows, int32_t n_feat, int dtype, int scale, int
                        const void* copy, int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out,
                        void* out_lo /* optional */, void* heavy_workspace /* optional */, size_t heavy_workspace_bytes,
                        agnn_stream_t stream);
+/* Same launch with the concatenated output written as the fp16 hi / lo operand pair of agnn_gemm's F16X3 mode: out and
+ * out_lo are fp16 matrices (ld_out in fp16 elements, a multiple of 8), every value is scaled by the power of two
+ * derived from *pair_amax (a device scalar >= max |y| / 4 -- e.g. the amax of the gathered features: a mean of rows
+ * cannot exceed it).  fp32 inputs, AGNN_COMBINE_CONCAT only; pair_amax == NULL is agnn_gather_reduce. */
+int agnn_gather_reduce_f16(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
+                           const agnn_rel_t* rels /* host */, const void* self_add, int64_t ld_self, const void* copy,
+                           int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out, void* out_lo,
+                           const float* pair_amax, void* heavy_workspace /* optional */, size_t heavy_workspace_bytes,
+                           agnn_stream_t stream);
 /* Scratch for the heavy-row path of a launch whose relations hold `total_edges` edges and `total_heavy_cap` heavy
  * slots in all: (total_edges / AGNN_HEAVY_CHUNK + total_heavy_cap) partial rows of n_feat floats.  Relations are
  * only split when heavy_rows is set AND a workspace is given; otherwise every row is walked by its own warp. */
@@ -259,6 +268,7 @@ int agnn_adamw_clip_step(const agnn_param_chunk_t* chunks /* device */, int n_ch
 #define AGNN_GEMM_TF32X3 0
 #define AGNN_GEMM_TF32 1
 #define AGNN_GEMM_BF16 2
+#define AGNN_GEMM_F16X3 3 /* fp32 parity on the f16 MMA: fp16 hi / lo operands with one power-of-two scale per tensor */
 #define AGNN_LAYOUT_K_MAJOR 0
 #define AGNN_LAYOUT_MN_MAJOR 1
 #define AGNN_GEMM_RELU 1
@@ -275,6 +285,21 @@ int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, int64_t N, i
               const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb, void* c, int64_t ldc,
               const float* bias, int flags, int split_k, void* workspace, size_t workspace_bytes,
               agnn_stream_t stream);
+/* AGNN_GEMM_F16X3 (same nn.Linear sites as agnn_gemm; twice the MMA rate of TF32X3, half the operand bytes):
+ * operands are fp16 hi / lo pairs of s_a A and s_b B (lda / ldb in fp16 elements), where s = 2^k is derived from the
+ * tensor's amax so that max |s x| lies in [2^13, 2^14); amax_a / amax_b point at those device scalars and the
+ * epilogue divides by s_a s_b (exact) before the bias.  fp16 carries TF32's 11-bit significand, so
+ * hi*hi + hi*lo + lo*hi has TF32X3's accuracy for elements down to 2^-17 of the tensor's amax (absolute error
+ * 2^-25 of the scaled range below that).
+ *   agnn_amax       *amax = max(*amax, max |x|)  (zero it first; several tensors may share one scalar)
+ *   agnn_split_f16  hi = fp16(s x), lo = fp16(s x - hi), s from *amax */
+int agnn_amax(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* amax, agnn_stream_t stream);
+int agnn_split_f16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax, void* hi, void* lo,
+                   int64_t ld_out, agnn_stream_t stream);
+int agnn_gemm_scaled(int precision, int a_layout, int b_layout, int64_t M, int64_t N, int64_t K, const void* a_hi,
+                     const void* a_lo, int64_t lda, const float* amax_a, const void* b_hi, const void* b_lo, int64_t ldb,
+                     const float* amax_b, void* c, int64_t ldc, const float* bias, int flags, int split_k, void* workspace,
+                     size_t workspace_bytes, agnn_stream_t stream);
 
 /* ------------------------------------------------------------ row-wise normalisation
  * agnn_layernorm_*: nn.LayerNorm of project_dict / project_enc (analysisgnn/models/analysis.py:429-443,
@@ -307,6 +332,12 @@ int agnn_colsum_partials(const float* x, int64_t ld_x, float* partials, float* o
 int agnn_grad_prepare(const float* g, int64_t ld_g, const float* relu_out /* optional */, int64_t ld_o, float* hi,
                       float* lo, int64_t ld_s, float* partials /* optional */, float* colsum /* optional */,
                       int64_t rows, int cols, agnn_stream_t stream);
+
+/* agnn_grad_prepare with the operand pair in the F16X3 form: hi / lo are fp16 matrices (ld_s in fp16 elements), scaled
+ * by the power of two derived from *amax (agnn_amax of g; the ReLU mask only removes entries). */
+int agnn_grad_prepare_f16(const float* g, int64_t ld_g, const float* relu_out /* optional */, int64_t ld_o,
+                          const float* amax, void* hi, void* lo, int64_t ld_s, float* partials /* optional */,
+                          float* colsum /* optional */, int64_t rows, int cols, agnn_stream_t stream);
 
 /* ------------------------------------------------------------ objective and lookup-table gradients
  * agnn_softmax_ce_*: nn.CrossEntropyLoss(ignore_index, label_smoothing) with mean reduction over the rows
