@@ -440,29 +440,35 @@ def run_ours(args):
         big = g["max_bytes"] / (g["max_ms"] * 1e-3) / 1e9 if g["max_ms"] > 0 else 0.0
         # TF32 runs at half the bf16 tensor rate: the measured bf16 cuBLAS burst / 2 is the denominator
         tf32_peak = bf16_peak / 2.0
+        f16_ops = args.operands == "f16"
+        # f16 operand mode: the big layer GEMMs run on the f16 MMA (the bf16 burst rate), the small ones stay 3xTF32;
+        # the denominator is the faster pipe's rate
+        mma_peak = bf16_peak if f16_ops else tf32_peak
         mm_tflops = mm["bytes"] / (mm["ms"] * 1e-3) / 1e12 if mm["ms"] > 0 else 0.0
         mm_big = mm["max_bytes"] / (mm["max_ms"] * 1e-3) / 1e12 if mm["max_ms"] > 0 else 0.0
         timed_in = ("eager, single-stream re-run of the same K steps (CUDA events around each launch; events cannot "
                     "be read inside the replayed graph)")
         roofline_gemm = {
-            "bound": "tensor", "kernel": "agnn gemm_kernel (tcgen05 3xTF32, all launches of the step)",
-            "achieved": mm_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": mm_tflops / tf32_peak,
+            "bound": "tensor", "kernel": "agnn gemm_kernel (tcgen05 " + ("3xF16 message-passing layers + 3xTF32 rest" if f16_ops
+                                                                          else "3xTF32") + ", all launches of the step)",
+            "achieved": mm_tflops, "peak": mma_peak, "unit": "TFLOP/s", "frac": mm_tflops / mma_peak,
             # what the tensor pipe actually executes in the fp32-parity mode: 3 TF32 MMAs per algorithmic product
             "mma_achieved": mm_tflops * (3 if dtype == torch.float32 else 1),
-            "mma_frac": mm_tflops * (3 if dtype == torch.float32 else 1) / (tf32_peak if dtype == torch.float32
+            "mma_frac": mm_tflops * (3 if dtype == torch.float32 else 1) / (mma_peak if dtype == torch.float32
                                                                               else bf16_peak),
             # DRAM bytes of the largest launch (50 000 x 256 x 2560) from the committed ncu --set full capture:
             # 1.0545 GB read + 46 MB written, against 1.080 GB of operand + result bytes -- nothing is re-read
             "traffic": 1.1005e9, "traffic_source": "profiles/r1_t_gemm_fwd2560_full_raw.csv (largest launch; "
                                                    "sm__pipe_tensor_cycles_active 72 %)",
-            "peak_source": peak_src + ": bf16 burst / 2 (TF32 rate)", "launches": mm["launches"],
+            "peak_source": peak_src + (": bf16 burst (f16 MMA rate)" if f16_ops else ": bf16 burst / 2 (TF32 rate)"),
+            "launches": mm["launches"],
             "algorithmic_flops_per_step": mm["bytes"] / max(args.steps, 1),
             "kernel_ms_per_step": mm["ms"] / max(args.steps, 1),
             "share_of_step": mm["ms"] / serial_ms if serial_ms else None, "timed_in": timed_in,
-            "note": "algorithmic flops = 2*M*N*K per GEMM; the fp32-parity mode spends 3 TF32 MMAs per product, so "
+            "note": "algorithmic flops = 2*M*N*K per GEMM; the fp32-parity modes spend 3 MMAs per product, so "
                     "frac <= 0.33 by construction (tensor-pipe active cycles are in profiles/)",
             "largest_launch": {"flops": mm["max_bytes"], "ms": mm["max_ms"], "achieved": mm_big,
-                               "frac": mm_big / tf32_peak}}
+                               "frac": mm_big / mma_peak}}
         roofline_gather = {
             "bound": "hbm", "kernel": "agnn gather_reduce_kernel (all launches of the step)",
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
