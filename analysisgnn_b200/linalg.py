@@ -4,7 +4,9 @@ The per-relation / per-node-type projections are the only GEMM-shaped work on th
 ``backend()`` selects who runs them:
 
 * ``"tcgen05"`` -- this repo's sm_100a tensor-core GEMM (csrc/gemm.cu, ``agnn_gemm``): fp32 tensors
-  run in the 3xTF32 split mode (fp32 parity), bf16 tensors in the bf16 mode.
+  run in a three-product split mode (fp32 parity) -- 3xTF32 (``Split``), or 3 x fp16 with one power-of-two scale per
+  tensor (``SplitH``, ``parity_operands() == "f16"``: the fused message-passing layers and the large projections;
+  same accuracy at twice the MMA rate) -- bf16 tensors in the bf16 mode.
 * ``"cublas"``  -- ``torch.addmm`` / ``torch.mm`` (library GEMM, fp32 SIMT with TF32 off).  Also the
   route for shapes ``agnn_gemm`` does not take (row strides that are not 16-byte multiples).
 
@@ -98,7 +100,7 @@ def f16_scale(amax: torch.Tensor) -> torch.Tensor:
 
 Operand = Union[torch.Tensor, Split, SplitH]
 
-_PARITY_OPERANDS = os.environ.get("AGNN_PARITY_OPERANDS", "tf32")
+_PARITY_OPERANDS = os.environ.get("AGNN_PARITY_OPERANDS", "f16")
 
 
 def parity_operands() -> str:
@@ -114,8 +116,21 @@ def set_parity_operands(name: str) -> None:
     _PARITY_OPERANDS = name
 
 
+_amax_pool = None        # zeroed scalars handed out one by one: one fill launch per 256 of them
+_amax_next = 0
+
+
 def new_amax(device) -> torch.Tensor:
-    return torch.zeros(1, dtype=torch.float32, device=device)
+    """A zeroed device scalar for ``amax_into``.  Slots come from a pool that ``begin_step`` renews, so a (captured)
+    training step zeroes all of its scalars with one fill."""
+    global _amax_pool, _amax_next
+    device = torch.device(device)
+    if _amax_pool is None or _amax_next >= _amax_pool.numel() or _amax_pool.device != device:
+        _amax_pool = torch.zeros(256, dtype=torch.float32, device=device)
+        _amax_next = 0
+    slot = _amax_pool[_amax_next:_amax_next + 1]
+    _amax_next += 1
+    return slot
 
 
 def amax_into(amax: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -203,8 +218,11 @@ _SPLIT_CACHE_MAX_ELEMS = 4 * 1024 * 1024
 
 
 def begin_step() -> None:
-    """Forget cached weight splits (call once per training step, before the forward)."""
+    """Forget cached weight splits and the amax scalars of the last step (call once per training step, before the
+    forward)."""
+    global _amax_pool
     _split_cache.clear()
+    _amax_pool = None
 
 
 def _cached_split(x: torch.Tensor) -> Split:

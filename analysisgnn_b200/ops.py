@@ -744,26 +744,36 @@ def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_
 class _Linear(torch.autograd.Function):
     """``y = x W^T + b`` on agnn_gemm (forward, grad-input, grad-weight) with one TF32 split per operand."""
 
+    # rows from which the fp16 operand form pays for its amax pass (two short launches per projection and direction)
+    F16_MIN_ROWS = 16384
+    F16_MIN_WEIGHT = 128 * 128
+
     @staticmethod
     def forward(ctx, x, weight, bias):
-        xs = linalg.prepare(x)
+        f16 = (linalg.parity_operands() == "f16" and linalg.backend() == "tcgen05" and x.shape[0] >= _Linear.F16_MIN_ROWS
+               and weight.shape[0] * weight.shape[1] >= _Linear.F16_MIN_WEIGHT and linalg.f16_ok(x)
+               and linalg.f16_ok(weight))
+        xs = linalg.split_f16(x) if f16 else linalg.prepare(x)
         y = linalg.linear(xs, weight, bias)
         ctx.save_for_backward(*linalg.pack(xs), weight)
+        ctx.x_amax = xs.amax if f16 else None
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, g):
         x_first, x_second, weight = ctx.saved_tensors
-        xs = linalg.unpack(x_first, x_second)
+        xs = linalg.unpack(x_first, x_second, ctx.x_amax)
+        f16 = isinstance(xs, linalg.SplitH)
         n = g.shape[1]
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
-        if g.dtype == torch.float32 and n % 4 and linalg.backend() == "tcgen05":
+        mult = 8 if f16 else 4
+        if g.dtype == torch.float32 and n % mult and linalg.backend() == "tcgen05":
             # e.g. the 185- and 50-class heads: zero columns / weight rows up to the 16-byte row rule of TMA
-            pad = 4 - n % 4
+            pad = mult - n % mult
             g = torch.nn.functional.pad(g, (0, pad))
             weight = torch.nn.functional.pad(weight, (0, 0, 0, pad))
-        gs, db = prepare_grad(g, None, want_db)
+        gs, db = prepare_grad(g, None, want_db, f16=f16)
         if db is not None:
             db = db[:n]
         dx = linalg.mm(gs, weight) if ctx.needs_input_grad[0] else None
@@ -780,8 +790,9 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     lead = x.shape[:-1]
     x2 = x.reshape(-1, x.shape[-1])
     k = x2.shape[1]
-    if x2.dtype == torch.float32 and k % 4 and linalg.backend() == "tcgen05":
-        pad = 4 - k % 4
+    mult = 8 if linalg.parity_operands() == "f16" else 4      # 16-byte rows in the operand's element type
+    if x2.dtype == torch.float32 and k % mult and linalg.backend() == "tcgen05":
+        pad = mult - k % mult
         x2 = torch.nn.functional.pad(x2, (0, pad))
         weight = torch.nn.functional.pad(weight, (0, pad))
     elif not x2.is_contiguous():

@@ -516,7 +516,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
-    ap.add_argument("--operands", default=os.environ.get("AGNN_PARITY_OPERANDS", "tf32"), choices=["tf32", "f16"],
+    ap.add_argument("--operands", default=os.environ.get("AGNN_PARITY_OPERANDS", "f16"), choices=["tf32", "f16"],
                     help="operand form of the fp32 parity GEMMs in the message-passing layers: 3xTF32 or 3 x fp16 with "
                          "per-tensor power-of-two scales (same accuracy, twice the MMA rate)")
     ap.add_argument("--skip-cpu", action="store_true", help="leave out the cpu_baseline leg (profiling runs)")

@@ -21,12 +21,13 @@ SHAPES = [(128, 128, 64), (256, 256, 256), (300, 200, 104), (1000, 256, 2560), (
           (130, 56, 64)]
 
 
-@pytest.fixture()
-def f16_mode():
+@pytest.fixture(params=["f16", "tf32"])
+def f16_mode(request):
+    """Both operand forms of the parity mode, whichever is the library default."""
     old_b, old_p = linalg.backend(), linalg.parity_operands()
     linalg.set_backend("tcgen05")
-    linalg.set_parity_operands("f16")
-    yield
+    linalg.set_parity_operands(request.param)
+    yield request.param
     linalg.set_backend(old_b)
     linalg.set_parity_operands(old_p)
 
@@ -126,8 +127,33 @@ def test_analysis_encoder_shell_in_f16_mode(f16_mode):
     th.test_analysis_encoder_shell("hybridgnn")
 
 
+@pytest.mark.parametrize("rows,k,n", [(20000, 153, 256), (16384, 128, 185), (30000, 512, 128)])
+def test_linear_module_fwd_bwd(f16_mode, rows, k, n):
+    """nn.Linear drop-in (ops._Linear): odd widths are padded to the 16-byte row rule of the operand type; from
+    16 384 rows on the f16 mode runs all three GEMMs on fp16 pairs."""
+    from analysisgnn_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x, w, b = torch.randn(rows, k, generator=g), torch.randn(n, k, generator=g) * 0.05, torch.randn(n, generator=g)
+    gy = torch.randn(rows, n, generator=g) * 1e-3
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    (xd @ wd.t() + bd).backward(gy.double())
+    xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    y = ops.linear(xg, wg, bg)
+    y.backward(gy.to(DEV))
+    assert rel_err(y, x.double() @ w.double().t() + b.double()) <= 4e-6
+    for got, want, what in ((xg.grad, xd.grad, "dx"), (wg.grad, wd.grad, "dw"), (bg.grad, bd.grad, "db")):
+        assert rel_err(got, want) <= 4e-6, what
+    fn = y.grad_fn
+    while fn is not None and not hasattr(fn, "saved_tensors"):      # through the reshape node
+        fn = fn.next_functions[0][0] if fn.next_functions else None
+    assert fn is not None
+    assert any(t is not None and t.dtype == torch.float16 for t in fn.saved_tensors) == (f16_mode == "f16")
+
+
 def test_f16_mode_uses_the_f16_kernels(f16_mode):
     """The mode is not a silent no-op: the layer's saved operands are fp16 pairs."""
+    if f16_mode != "f16":
+        pytest.skip("checks the f16 form")
     from analysisgnn_b200 import nn as ann, synth
     b = synth.hetero_batch(2, 60, 3)
     net = ann.HeteroSAGELayer(b["metadata"][1], 32, 32).to(DEV)
