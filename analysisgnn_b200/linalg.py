@@ -116,20 +116,22 @@ def set_parity_operands(name: str) -> None:
     _PARITY_OPERANDS = name
 
 
-_amax_pool = None        # zeroed scalars handed out one by one: one fill launch per 256 of them
-_amax_next = 0
+_amax_pools = {}         # (device, stream) -> [zeroed scalars, next free]: one fill launch per 256 scalars
+F16_MIN_ROWS = 16384     # rows from which the fp16 operand form pays for its amax pass
 
 
 def new_amax(device) -> torch.Tensor:
-    """A zeroed device scalar for ``amax_into``.  Slots come from a pool that ``begin_step`` renews, so a (captured)
-    training step zeroes all of its scalars with one fill."""
-    global _amax_pool, _amax_next
+    """A zeroed device scalar for ``amax_into``.  Slots come from a per-stream pool that ``begin_step`` renews, so a
+    (captured) training step zeroes all of its scalars with one fill per stream."""
     device = torch.device(device)
-    if _amax_pool is None or _amax_next >= _amax_pool.numel() or _amax_pool.device != device:
-        _amax_pool = torch.zeros(256, dtype=torch.float32, device=device)
-        _amax_next = 0
-    slot = _amax_pool[_amax_next:_amax_next + 1]
-    _amax_next += 1
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    pool = _amax_pools.get(key)
+    if pool is None or pool[1] >= pool[0].numel():
+        pool = _amax_pools[key] = [torch.zeros(256, dtype=torch.float32, device=device), 0]
+    slot = pool[0][pool[1]:pool[1] + 1]
+    pool[1] += 1
     return slot
 
 
@@ -198,6 +200,15 @@ def prepare(x: torch.Tensor) -> Operand:
     return x
 
 
+def prepare_auto(x: torch.Tensor) -> Operand:
+    """``prepare`` in the operand form of the current parity mode: the fp16 pair for large matrices when
+    ``parity_operands() == "f16"`` (every GEMM that reads it then runs in F16X3), the TF32 pair otherwise."""
+    if (_BACKEND == "tcgen05" and _PARITY_OPERANDS == "f16" and isinstance(x, torch.Tensor) and x.is_cuda
+            and x.shape[0] >= F16_MIN_ROWS and f16_ok(x)):
+        return split_f16(x)
+    return prepare(x)
+
+
 def pack(x: Operand):
     """(tensor, tensor-or-None) for ``save_for_backward``; ``unpack`` restores the operand (a ``SplitH`` also needs
     its ``amax``, which the caller keeps)."""
@@ -220,9 +231,8 @@ _SPLIT_CACHE_MAX_ELEMS = 4 * 1024 * 1024
 def begin_step() -> None:
     """Forget cached weight splits and the amax scalars of the last step (call once per training step, before the
     forward)."""
-    global _amax_pool
     _split_cache.clear()
-    _amax_pool = None
+    _amax_pools.clear()
 
 
 def _cached_split(x: torch.Tensor) -> Split:

@@ -745,7 +745,7 @@ class _Linear(torch.autograd.Function):
     """``y = x W^T + b`` on agnn_gemm (forward, grad-input, grad-weight) with one TF32 split per operand."""
 
     # rows from which the fp16 operand form pays for its amax pass (two short launches per projection and direction)
-    F16_MIN_ROWS = 16384
+    F16_MIN_ROWS = linalg.F16_MIN_ROWS
     F16_MIN_WEIGHT = 128 * 128
 
     @staticmethod
@@ -988,7 +988,7 @@ class _GRULayer(torch.autograd.Function):
         h = params[1].shape[1]
         x2 = x.reshape(b * t, c)
         x2 = x2 if x2.is_contiguous() else x2.contiguous()
-        xs = linalg.prepare(x2)
+        xs = linalg.prepare_auto(x2)
         gis, whh, bhh = [], [], []
         for d in range(n_dir):
             w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
@@ -1003,6 +1003,7 @@ class _GRULayer(torch.autograd.Function):
         _lib.count_launches(1)
         ctx.save_for_backward(*linalg.pack(xs), out, *gates, *[params[4 * d] for d in range(n_dir)], *whh)
         ctx.n_dir, ctx.dims = n_dir, (b, t, c, h)
+        ctx.x_amax = getattr(xs, "amax", None)
         return out
 
     @staticmethod
@@ -1010,7 +1011,7 @@ class _GRULayer(torch.autograd.Function):
         n_dir = ctx.n_dir
         b, t, c, h = ctx.dims
         saved = ctx.saved_tensors
-        xs = linalg.unpack(saved[0], saved[1])
+        xs = linalg.unpack(saved[0], saved[1], ctx.x_amax)
         out = saved[2]
         gates = list(saved[3:3 + n_dir])
         w_ih = list(saved[3 + n_dir:3 + 2 * n_dir])
@@ -1032,7 +1033,9 @@ class _GRULayer(torch.autograd.Function):
                     h_prev[:, 1:] = hd[:, :-1]
                 else:
                     h_prev[:, :-1] = hd[:, 1:]
-            gi_s, gh_s = linalg.prepare(dgi[d]), linalg.prepare(dgh[d])
+            # dgi meets xs in the grad-weight GEMM: same operand form
+            gi_s = (linalg.prepare_auto if isinstance(xs, linalg.SplitH) else linalg.prepare)(dgi[d])
+            gh_s = linalg.prepare_auto(dgh[d])
             dw_ih = linalg.mm_tn(gi_s, xs)
             dw_hh = linalg.mm_tn(gh_s, h_prev.reshape(b * t, h))
             if ctx.needs_input_grad[0]:

@@ -139,15 +139,15 @@ def test_linear_module_fwd_bwd(f16_mode, rows, k, n):
     (xd @ wd.t() + bd).backward(gy.double())
     xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
     y = ops.linear(xg, wg, bg)
-    y.backward(gy.to(DEV))
-    assert rel_err(y, x.double() @ w.double().t() + b.double()) <= 4e-6
-    for got, want, what in ((xg.grad, xd.grad, "dx"), (wg.grad, wd.grad, "dw"), (bg.grad, bd.grad, "db")):
-        assert rel_err(got, want) <= 4e-6, what
     fn = y.grad_fn
     while fn is not None and not hasattr(fn, "saved_tensors"):      # through the reshape node
         fn = fn.next_functions[0][0] if fn.next_functions else None
     assert fn is not None
     assert any(t is not None and t.dtype == torch.float16 for t in fn.saved_tensors) == (f16_mode == "f16")
+    y.backward(gy.to(DEV))
+    assert rel_err(y, x.double() @ w.double().t() + b.double()) <= 4e-6
+    for got, want, what in ((xg.grad, xd.grad, "dx"), (wg.grad, wd.grad, "dw"), (bg.grad, bd.grad, "db")):
+        assert rel_err(got, want) <= 4e-6, what
 
 
 def test_f16_mode_uses_the_f16_kernels(f16_mode):

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("hidden,cin,layers,bidir,b,t", [
     (128, 256, 2, True, 5, 40), (64, 32, 1, True, 3, 17), (32, 48, 1, False, 4, 9), (128, 128, 1, True, 1, 1),
-    (128, 256, 2, True, 100, 64), (64, 64, 2, False, 7, 130)])
+    (128, 256, 2, True, 100, 64), (64, 64, 2, False, 7, 130),
+    (128, 256, 2, True, 130, 128)])     # 16 640 rows: the projections take the fp16 operand form (linalg.prepare_auto)
 def test_matches_torch_gru(hidden, cin, layers, bidir, b, t):
     torch.manual_seed(hidden + t)
     ref = nn.GRU(cin, hidden, num_layers=layers, batch_first=True, bidirectional=bidir)
