@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Standalone timing of agnn_gemm on the shapes of the training step (used with ncu for kernel work).
 
-    python tools/gemm_probe.py [--reps 20] [--one NAME]
+    python tools/gemm_probe.py [--reps 20] [--one NAME] [--operands f16|tf32]
 """
 import argparse
 import os
@@ -30,7 +30,10 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--one", default=None)
     ap.add_argument("--rounds", action="store_true")
+    ap.add_argument("--operands", default="f16", choices=["f16", "tf32"],
+                    help="operand form of the parity mode: fp16 pairs (AGNN_GEMM_F16X3) or TF32 pairs (AGNN_GEMM_TF32X3)")
     args = ap.parse_args()
+    split = linalg.split_f16 if args.operands == "f16" else linalg.split
     dev = torch.device("cuda:0")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     torch.manual_seed(0)
@@ -38,16 +41,16 @@ def main():
         if args.one and name != args.one:
             continue
         if kind == "linear":
-            a = linalg.split(torch.randn(m, k, device=dev))
-            b = linalg.split(torch.randn(n, k, device=dev))
+            a = split(torch.randn(m, k, device=dev))
+            b = split(torch.randn(n, k, device=dev))
             fn = lambda: linalg.linear(a, b, None)
         elif kind == "mm":
-            a = linalg.split(torch.randn(m, k, device=dev))
-            b = linalg.split(torch.randn(k, n, device=dev))
+            a = split(torch.randn(m, k, device=dev))
+            b = split(torch.randn(k, n, device=dev))
             fn = lambda: linalg.mm(a, b)
         else:
-            a = linalg.split(torch.randn(k, m, device=dev))
-            b = linalg.split(torch.randn(k, n, device=dev))
+            a = split(torch.randn(k, m, device=dev))
+            b = split(torch.randn(k, n, device=dev))
             fn = lambda: linalg.mm_tn(a, b)
         for _ in range(3):
             fn()
