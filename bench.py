@@ -456,10 +456,14 @@ def run_ours(args):
             "mma_achieved": mm_tflops * (3 if dtype == torch.float32 else 1),
             "mma_frac": mm_tflops * (3 if dtype == torch.float32 else 1) / (mma_peak if dtype == torch.float32
                                                                               else bf16_peak),
-            # DRAM bytes of the largest launch (50 000 x 256 x 2560) from the committed ncu --set full capture:
-            # 1.0545 GB read + 46 MB written, against 1.080 GB of operand + result bytes -- nothing is re-read
-            "traffic": 1.1005e9, "traffic_source": "profiles/r1_t_gemm_fwd2560_full_raw.csv (largest launch; "
-                                                   "sm__pipe_tensor_cycles_active 72 %)",
+            # DRAM bytes of the largest launch (50 000 x 256 x 2560) from the committed ncu --set full captures:
+            # fp16 pairs 524 MB read + 45 MB written against 0.57 GB of operand + result bytes; TF32 pairs 1.0545 GB +
+            # 46 MB against 1.08 GB -- nothing is re-read in either form
+            "traffic": 5.690e8 if f16_ops else 1.1005e9,
+            "traffic_source": ("profiles/r1_w_gemm_f16_fwd2560_full_raw.csv (largest launch; "
+                               "sm__pipe_tensor_cycles_active 70.6 %)") if f16_ops else
+                              ("profiles/r1_t_gemm_fwd2560_full_raw.csv (largest launch; "
+                               "sm__pipe_tensor_cycles_active 72 %)"),
             "peak_source": peak_src + (": bf16 burst (f16 MMA rate)" if f16_ops else ": bf16 burst / 2 (TF32 rate)"),
             "launches": mm["launches"],
             "algorithmic_flops_per_step": mm["bytes"] / max(args.steps, 1),
