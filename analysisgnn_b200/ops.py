@@ -295,26 +295,42 @@ class _IntreeSageLayer(torch.autograd.Function):
         x = x.contiguous()
         n, f = x.shape
         r = csr.n_rel
-        h = linalg.linear(x, wn_cat, bn_cat)                                     # [N, R*F]
-        a_hi, a_lo = _operand_buffers(n, (r + 1) * f, x)
+        # fp16 operand form: |S_r| <= amax(x) + amax(H), inside the 4x headroom of a scale taken from
+        # max(amax(x), amax(H))
+        f16 = (linalg.parity_operands() == "f16" and linalg.backend() == "tcgen05" and x.dtype == torch.float32
+               and f % 8 == 0 and n > 0 and linalg.f16_ok(wn_cat) and linalg.f16_ok(wc))
+        xs = linalg.split_f16(x) if f16 else x
+        h = linalg.linear(xs, wn_cat, bn_cat)                                    # [N, R*F]
         rels = [rel_of(csr.fwd, k, h[:, k * f:(k + 1) * f], out_col=(k + 1) * f,
                        flags=_lib.REL_IDENTITY_IF_EMPTY, n_edges=csr.n_edges if k == 0 else 0) for k in range(r)]
-        # the gather writes the GEMM operand directly as a TF32 pair: it feeds the forward and the grad-weight GEMM
-        gather_reduce(rels, a_hi, f, mean=True, concat=True, self_add=x, copy=x, copy_col=0, out_lo=a_lo)
-        a = _as_operand_pair(a_hi, a_lo)
+        a_amax = None
+        if f16:
+            a_amax = linalg.amax_into(linalg.amax_into(linalg.new_amax(x.device), x), h)
+            buf = torch.empty((2, n, (r + 1) * f), dtype=torch.float16, device=x.device)
+            gather_reduce(rels, buf[0], f, mean=True, concat=True, self_add=x, copy=x, copy_col=0, out_lo=buf[1],
+                          pair_amax=a_amax)
+            a = linalg.SplitH(buf[0], buf[1], a_amax)
+        else:
+            a_hi, a_lo = _operand_buffers(n, (r + 1) * f, x)
+            # the gather writes the GEMM operand directly as a TF32 pair: it feeds the forward and the grad-weight GEMM
+            gather_reduce(rels, a_hi, f, mean=True, concat=True, self_add=x, copy=x, copy_col=0, out_lo=a_lo)
+            a = _as_operand_pair(a_hi, a_lo)
         z = linalg.linear(a, wc, bc)
         ctx.save_for_backward(x, *linalg.pack(a), wn_cat, wc)
         ctx.csr = csr
+        ctx.a_amax = a_amax
         ctx.has_bias = (bn_cat is not None, bc is not None)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         x, a_first, a_second, wn_cat, wc = ctx.saved_tensors
-        a = linalg.unpack(a_first, a_second)
+        a = linalg.unpack(a_first, a_second, ctx.a_amax)
+        f16 = isinstance(a, linalg.SplitH)
+        prep = (lambda t: linalg.split_f16(t) if linalg.f16_ok(t) else linalg.prepare(t)) if f16 else linalg.prepare
         csr, (n, f), r = ctx.csr, x.shape, ctx.csr.n_rel
         dz_plain = dz.contiguous()
-        dz = linalg.prepare(dz_plain)
+        dz = prep(dz_plain)
         da = linalg.mm(dz, wc)                                                   # [N, (R+1)F]
         dwc = linalg.mm_tn(dz, a) if ctx.needs_input_grad[3] else None
         dbc = colsum(dz_plain) if ctx.has_bias[1] and ctx.needs_input_grad[4] else None
@@ -329,7 +345,7 @@ class _IntreeSageLayer(torch.autograd.Function):
             rels_s = [Rel(csr.fwd.rowptr[k], csr.fwd.col, da, out_col=(k + 1) * f,
                           flags=_lib.REL_IDENTITY_IF_EMPTY) for k in range(r)]
             rowscale_sum(rels_s, da, dx, f, base=da[:, :f])
-            dh_op = linalg.prepare(dh)
+            dh_op = prep(dh)
             linalg.mm(dh_op, wn_cat, out=dx, accumulate=True)
         else:
             dh_op = dh

@@ -150,6 +150,17 @@ def test_linear_module_fwd_bwd(f16_mode, rows, k, n):
         assert rel_err(got, want) <= 4e-6, what
 
 
+def test_intree_layers_in_both_operand_forms(f16_mode):
+    """In-tree HeteroConv{SageConvScatter} / MetricalGNN (ops._IntreeSageLayer): reference goldens and the oracle."""
+    from tests import test_intree_gpu as ti
+    ti.test_golden_heteroconv(0)
+    ti.test_golden_sage_and_empty_branch(1)
+    ti.test_golden_metricalgnn(2, "eval")
+    ti.test_heteroconv_vs_oracle("mean", 128, 512)
+    ti.test_heteroconv_vs_oracle("sum", 256, 256)
+    ti.test_metricalgnn_config4_shape_small_batch()
+
+
 def test_f16_mode_uses_the_f16_kernels(f16_mode):
     """The mode is not a silent no-op: the layer's saved operands are fp16 pairs."""
     if f16_mode != "f16":
