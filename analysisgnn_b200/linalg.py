@@ -23,6 +23,9 @@ from . import _lib
 
 _BACKEND = os.environ.get("AGNN_GEMM", "tcgen05")
 timer = None      # set to an ops.KernelTimer by bench.py to time every agnn_gemm launch
+# how many contractions went to the library route (torch.mm / addmm) because agnn_gemm does not take their operands:
+# misaligned rows, or a TF32 pair meeting an fp16 pair.  bench.py reports it; a hot path should show 0.
+stats = {"library_gemms": 0}
 
 
 def backend() -> str:
@@ -342,6 +345,7 @@ def linear(x: Operand, weight: Operand, bias=None, relu: bool = False):
     y = _gemm(x, _lib.K_MAJOR, weight, _lib.K_MAJOR, m, n, k, bias, _lib.GEMM_RELU if relu else 0, None)
     if y is not None:
         return y
+    stats["library_gemms"] += 1
     xp, wp = _plain(x), _plain(weight)
     y = torch.addmm(bias, xp, wp.t()) if bias is not None else torch.mm(xp, wp.t())
     return y.relu_() if relu else y
@@ -355,6 +359,7 @@ def mm(a: Operand, b: Operand, out=None, accumulate: bool = False):
     y = _gemm(a, _lib.K_MAJOR, b, _lib.MN_MAJOR, m, n, k, None, _lib.GEMM_ACCUMULATE if accumulate else 0, out)
     if y is not None:
         return y
+    stats["library_gemms"] += 1
     ap, bp = _plain(a), _plain(b)
     if out is None:
         return torch.mm(ap, bp)
@@ -371,6 +376,7 @@ def mm_tn(a: Operand, b: Operand):
     y = _gemm(a, _lib.MN_MAJOR, b, _lib.MN_MAJOR, m, n, r, None, 0, None)
     if y is not None:
         return y
+    stats["library_gemms"] += 1
     return torch.mm(_plain(a).t(), _plain(b))
 
 

@@ -729,7 +729,9 @@ def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_
         if relu_out is not None:
             g = linalg.relu_backward(g, relu_out)
         g = g.contiguous()
-        return linalg.prepare(g), (colsum(g) if want_colsum else None)
+        # wide gradients (e.g. HGT's folded 4864-column projection) miss the one-pass kernel but keep the operand form
+        op = linalg.split_f16(g) if f16 and g.is_cuda and linalg.f16_ok(g) else linalg.prepare(g)
+        return op, (colsum(g) if want_colsum else None)
     lib = _lib.lib()
     f16 = f16 and cols % 8 == 0
     buf = torch.empty((2, rows, cols), dtype=torch.float16 if f16 else torch.float32, device=g.device)

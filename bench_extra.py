@@ -262,11 +262,23 @@ def decode_full_score(n_notes=200_000, cpu_notes=20_000):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only-decode", action="store_true")
+    ap.add_argument("--only-encoders", action="store_true",
+                    help="in-tree MetricalGNN 4L/512 and the HGT encoder step (AGNN_PARITY_OPERANDS=tf32|f16 selects "
+                         "the operand form)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "extra.json"))
     ap.add_argument("--only-sweep", action="store_true")
     ap.add_argument("--only-hgt", action="store_true")
     ap.add_argument("--only-hybrid", action="store_true", help="config[1] step through the same harness (profiling)")
     args = ap.parse_args()
+    if args.only_encoders:
+        from analysisgnn_b200 import linalg
+        r = {"parity_operands": linalg.parity_operands(), "metrical_gnn_4L512": metrical_gnn_step(),
+             "hgt_encoder": hgt_encoder_step()}
+        r["library_gemms"] = linalg.stats["library_gemms"]
+        print("encoders", r)
+        with open(args.out, "w") as fh:
+            json.dump(r, fh, indent=1)
+        return
     if args.only_decode:
         r = decode_full_score()
         print("decode", r)
