@@ -1,0 +1,66 @@
+"""Host-side arithmetic of the fp16 operand form (no GPU): the Python mirror of csrc/common.cuh::f16_scale_of and the
+precision the hi / lo pair keeps, checked on a bit-level model of what agnn_split_f16 computes."""
+import struct
+
+import pytest
+import torch
+
+from analysisgnn_b200 import linalg
+
+
+def scale_of(amax: float) -> float:
+    """csrc/common.cuh::f16_scale_of, restated on the bit pattern."""
+    bits = struct.unpack("<I", struct.pack("<f", amax))[0] & 0x7FFFFFFF
+    e = bits >> 23
+    if e == 0 or e == 255:
+        return 1.0
+    k = max(-100, min(100, 13 - (e - 127)))
+    return 2.0 ** k
+
+
+@pytest.mark.parametrize("amax", [1.0, 2.0, 3.999, 4.0, 0.5, 1e-30, 1e30, 8192.0, 16383.9, 0.0, float("inf"), 1e-39,
+                                  1.17e-38, 65504.0, 3e-6, 7e4])
+def test_python_scale_matches_the_kernel_rule(amax):
+    got = float(linalg.f16_scale(torch.tensor([amax], dtype=torch.float32)))
+    assert got == scale_of(amax)
+    if 1e-25 < amax < 1e25:
+        assert 2.0 ** 13 <= amax * got < 2.0 ** 14
+
+
+@pytest.mark.parametrize("magnitude", [1.0, 3e-6, 7e4])
+def test_pair_keeps_22_bits_down_to_2_pow_minus_17_of_the_amax(magnitude):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(300, 200, generator=g) * magnitude
+    x[::3] *= 2.0 ** -16                                # rows far below the amax
+    s = scale_of(float(x.abs().max()))
+    xs = x * s
+    hi = xs.half()
+    lo = (xs - hi.float()).half()
+    back = (hi.double() + lo.double()) / s
+    err = (back - x.double()).abs()
+    rel = err / x.double().abs().clamp_min(1e-300)
+    big = x.abs() >= float(x.abs().max()) * 2.0 ** -17
+    assert float(rel[big].max()) <= 2.0 ** -21          # two 11-bit significands
+    assert float(err.max()) <= max(float((x.double().abs() * 2.0 ** -21).max()), 2.0 ** -24 / s)
+    assert not torch.isinf(hi).any() and float(hi.abs().max()) < 2.0 ** 14
+
+
+def test_parity_operand_switch():
+    old = linalg.parity_operands()
+    try:
+        linalg.set_parity_operands("tf32")
+        assert linalg.parity_operands() == "tf32"
+        linalg.set_parity_operands("f16")
+        assert linalg.parity_operands() == "f16"
+        with pytest.raises(ValueError):
+            linalg.set_parity_operands("fp8")
+    finally:
+        linalg.set_parity_operands(old)
+
+
+def test_no_cpu_path_for_the_operand_producers():
+    from analysisgnn_b200 import _lib
+    with pytest.raises(_lib.AgnnError):
+        linalg.split_f16(torch.randn(8, 8))
+    with pytest.raises(_lib.AgnnError):
+        linalg.amax_into(torch.zeros(1), torch.randn(8, 8))
