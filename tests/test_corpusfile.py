@@ -148,3 +148,21 @@ def test_loader_reads_a_loaded_corpus_like_the_original(tmp_path):
     la = sampler.ScoreGraphLoader(c, 32, 3, seed=7)
     lb = sampler.ScoreGraphLoader(d, 32, 3, seed=7)
     assert la.order(2) == lb.order(2) and len(la) == len(lb)
+
+
+def test_convert_cli(tmp_path):
+    """tools/convert_corpus.py on a file laid out like the reference's processed/data.pt (plain dicts pickle without PyG)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    xs, edges, extras = make_scores(3, seed=9)
+    data, slices = collate_like_pyg(xs, edges, extras, cf.REL_NAMES)
+    src, dst = str(tmp_path / "data.pt"), str(tmp_path / "c.agc")
+    torch.save((data, slices, dict), src)
+    run = subprocess.run([sys.executable, os.path.join(root, "tools", "convert_corpus.py"), src, dst],
+                         capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    same_corpus(cf.from_pyg_collated(data, slices), cf.load_corpus(dst, device="cpu"))
+    info = subprocess.run([sys.executable, os.path.join(root, "tools", "convert_corpus.py"), "--info", dst],
+                          capture_output=True, text=True)
+    assert info.returncode == 0 and "checksums ok" in info.stdout and "extra.onset_div" in info.stdout
