@@ -4,7 +4,7 @@ upstream PyG, see oracle/__init__.py).  fp32 1e-5 relative; bf16 2e-2."""
 import pytest
 import torch
 
-from analysisgnn_b200 import graph, ops, synth
+from analysisgnn_b200 import synth
 from analysisgnn_b200 import nn as ann
 from oracle import pyg as op
 from tests.util import (DEV, BF16_REL, FP32_REL, ActivationPatterns, assert_close, feeds_relu,

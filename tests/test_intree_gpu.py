@@ -4,7 +4,7 @@ modules (tests/golden/intree_seed*.pt).  fp32, tolerance 1e-5 relative."""
 import pytest
 import torch
 
-from analysisgnn_b200 import graph, synth
+from analysisgnn_b200 import synth
 from analysisgnn_b200 import nn as ann
 from oracle import intree as oi
 from tests.util import (DEV, FP32_REL, ActivationPatterns, assert_close, feeds_relu,

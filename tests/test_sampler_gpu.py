@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from analysisgnn_b200 import graph, sampler, scoregraph, synth
+from analysisgnn_b200 import sampler, scoregraph, synth
 from oracle import graph as og
 from tests.util import DEV
 
