@@ -14,8 +14,8 @@ keys as the modules they replace, so reference checkpoints load unchanged:
 
 Every forward runs on libagnn.so's CUDA kernels; there is no CPU path.
 """
-from .intree import (HeteroConv, MetricalConvLayer, MetricalGNN, RelEdgeConv, ResGatedGraphConv,  # noqa: F401
-                     SageConvScatter)
+from .intree import (GATConvLayer, HeteroConv, MetricalConvLayer, MetricalGNN, OnsetEmbedding,  # noqa: F401
+                     RelEdgeConv, ResGatedGraphConv, SageConvScatter)
 from .hetero import (HeteroSAGELayer, HeteroSAGEStack, HGTConv, HeteroHGTStack, HybridGNN, HybridHGT,  # noqa: F401
                      SAGEConv, SequenceBranch)
 from .layers import GRU, LayerNorm, Linear  # noqa: F401

@@ -6,6 +6,7 @@ Replaces (same names / ctor / forward / state_dict keys):
 * ``HeteroConv``         analysisgnn/models/core/hgnn.py:435-484
 * ``MetricalConvLayer``  analysisgnn/models/core/gnn.py:488-540
 * ``MetricalGNN``        analysisgnn/models/core/hgnn.py:323-433
+* ``ResGatedGraphConv`` / ``RelEdgeConv`` / ``GATConvLayer`` / ``OnsetEmbedding``  gnn.py:212-258, 79-106, 154-209, 294-311
 
 Convention of these layers: reduce at ``edge_index[0]`` reading ``edge_index[1]``.
 A ``HeteroConv`` layer is ONE fused launch chain for all relations -- a grouped
@@ -127,6 +128,66 @@ class RelEdgeConv(nn.Module):
         msg = self.edge_linear(torch.cat((hj, edge_features), dim=-1))
         s = ops.segment_mean_self(msg, h, graph.edge_csr(edge_index[0], features.shape[0]))
         return self.linear(torch.cat((features, s), dim=-1))
+
+
+class GATConvLayer(nn.Module):
+    """analysisgnn/models/core/gnn.py:154-209.  The reference normalises the attention scores over the HEADS
+    (``Softmax(dim=1)``) and then averages over the heads (:206): the weight of every edge is the constant
+    ``1 / num_heads`` whatever the scores and the attention dropout are, so the layer is
+    ``h_i + (1 / num_heads) sum_{e: ei[0,e]=i} h_{ei[1,e]}`` with ``h = linear(x)`` -- one projection and one segmented
+    sum with the self term.  ``el`` / ``er`` / ``attnl`` / ``attnr`` (``attne`` / ``fc_fij``) are kept for the
+    reference's ``state_dict`` layout; the reference's gradients for them are the rounding residue of
+    ``1 - sum(softmax)`` (1e-8 of the ``linear`` gradients), here they stay ``None``."""
+
+    def __init__(self, in_features, out_features, num_heads=3, bias=True, dropout=0.3, negative_slope=0.2,
+                 in_edge_features=None):
+        super().__init__()
+        self.num_heads, self.in_features, self.out_features = num_heads, in_features, out_features
+        self.linear = Linear(in_features, out_features, bias=bias)
+        self.el = nn.Linear(in_features, in_features * num_heads, bias=bias)
+        self.er = nn.Linear(in_features, in_features * num_heads, bias=bias)
+        self.attnl = nn.Parameter(torch.empty(1, num_heads, in_features))
+        self.attnr = nn.Parameter(torch.empty(1, num_heads, in_features))
+        if in_edge_features is not None:
+            self.attne = nn.Parameter(torch.empty(1, num_heads, in_features))
+            self.fc_fij = nn.Linear(in_edge_features, in_features * num_heads, bias=bias)
+        self.in_edge_feats = in_edge_features
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        for lin in (self.linear, self.el, self.er) + ((self.fc_fij,) if self.in_edge_feats is not None else ()):
+            nn.init.xavier_normal_(lin.weight, gain=gain)
+            if lin.bias is not None:
+                nn.init.constant_(lin.bias, 0.0)
+        nn.init.xavier_normal_(self.attnl, gain=gain)
+        nn.init.xavier_normal_(self.attnr, gain=gain)
+        if self.in_edge_feats is not None:
+            nn.init.xavier_normal_(self.attne, gain=gain)
+
+    def forward(self, features, edge_index, edge_features=None):
+        h = self.linear(features)
+        if edge_index is None or edge_index.shape[1] == 0:
+            return h
+        csr = graph.typed_csr(edge_index, None, features.shape[0], 1)
+        return ops.segment_sum_self(h * (1.0 / self.num_heads), h, csr)
+
+
+class OnsetEmbedding(nn.Module):
+    """analysisgnn/models/core/gnn.py:294-311: ``W((x_i + sum_{e: ei[0,e]=i} |x_i - x_{ei[1,e]}|) / max(deg_i, 1))``;
+    the self loops the reference appends add nothing to the sum and one to every divisor."""
+
+    def __init__(self, in_feats, out_feats, bias=True, add_self_loops=True):
+        super().__init__()
+        self.W = Linear(in_feats, out_feats, bias=bias)
+        self.add_self_loops = add_self_loops
+
+    def forward(self, x, edge_index):
+        if self.add_self_loops:
+            loops = torch.arange(0, x.size(0), dtype=torch.long, device=x.device).unsqueeze(0).repeat(2, 1)
+            edge_index = torch.cat([edge_index, loops], dim=1)
+        msg = torch.abs(x.index_select(0, edge_index[0]) - x.index_select(0, edge_index[1]))
+        return self.W(ops.segment_mean_self(msg, x, graph.edge_csr(edge_index[0], x.shape[0])))
 
 
 _FOLDABLE = ("mean", "sum")

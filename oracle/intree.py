@@ -118,6 +118,73 @@ class RelEdgeConv(nn.Module):
         return self.linear(torch.cat((features, s), dim=-1))
 
 
+class GATConvLayer(nn.Module):
+    """analysisgnn/models/core/gnn.py:154-209.  The attention weight is ``softmax`` over the HEADS (dim=1) followed by
+    the mean over the heads (:206) -- a constant 1 / num_heads for every edge, whatever the scores and the attention
+    dropout are -- so the layer computes ``h_i + (1/H) sum_j h_j`` with ``h = linear(x)`` and ``el`` / ``er`` /
+    ``attnl`` / ``attnr`` receive (numerically almost) zero gradients.  Restated literally."""
+
+    def __init__(self, in_features, out_features, num_heads=3, bias=True, dropout=0.3, negative_slope=0.2,
+                 in_edge_features=None):
+        super().__init__()
+        self.num_heads, self.in_features, self.out_features = num_heads, in_features, out_features
+        self.linear = nn.Linear(in_features, out_features, bias=bias)
+        self.el = nn.Linear(in_features, in_features * num_heads, bias=bias)
+        self.er = nn.Linear(in_features, in_features * num_heads, bias=bias)
+        self.attnl = nn.Parameter(torch.empty(1, num_heads, in_features))
+        self.attnr = nn.Parameter(torch.empty(1, num_heads, in_features))
+        if in_edge_features is not None:
+            self.attne = nn.Parameter(torch.empty(1, num_heads, in_features))
+            self.fc_fij = nn.Linear(in_edge_features, in_features * num_heads, bias=bias)
+        self.in_edge_feats = in_edge_features
+        self.leaky_relu = nn.LeakyReLU(negative_slope)
+        self.attndrop = nn.Dropout(dropout)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        for lin in (self.linear, self.el, self.er) + ((self.fc_fij,) if self.in_edge_feats is not None else ()):
+            nn.init.xavier_normal_(lin.weight, gain=gain)
+            if lin.bias is not None:
+                nn.init.constant_(lin.bias, 0.0)
+        nn.init.xavier_normal_(self.attnl, gain=gain)
+        nn.init.xavier_normal_(self.attnr, gain=gain)
+        if self.in_edge_feats is not None:       # the reference leaves attne uninitialised (gnn.py:168); any value works
+            nn.init.xavier_normal_(self.attne, gain=gain)
+
+    def forward(self, features, edge_index, edge_features=None):
+        prefix = features.shape[:-1]
+        fc_src = self.el(features).view(*prefix, self.num_heads, self.in_features)
+        fc_dst = self.er(features).view(*prefix, self.num_heads, self.in_features)
+        el = (fc_src[edge_index[0]] * self.attnl).sum(dim=-1).unsqueeze(-1)
+        er = (fc_dst[edge_index[1]] * self.attnr).sum(dim=-1).unsqueeze(-1)
+        if edge_features is not None and self.in_edge_feats is not None:
+            fc_eij = self.fc_fij(edge_features).view(*edge_features.shape[:-1], self.num_heads, self.in_features)
+            e = self.leaky_relu(el + er + (fc_eij * self.attne).sum(dim=-1).unsqueeze(-1))
+        else:
+            e = self.leaky_relu(el + er)
+        a = torch.softmax(self.attndrop(e), dim=1).mean(dim=1)
+        h = self.linear(features)
+        return h.clone().index_add_(0, edge_index[0], a * h[edge_index[1]])
+
+
+class OnsetEmbedding(nn.Module):
+    """analysisgnn/models/core/gnn.py:294-311: ``W((x_i + sum_j |x_i - x_j|) / max(deg_i, 1))`` with self loops
+    appended first (they add nothing to the sum and one to the divisor)."""
+
+    def __init__(self, in_feats, out_feats, bias=True, add_self_loops=True):
+        super().__init__()
+        self.W = nn.Linear(in_feats, out_feats, bias=bias)
+        self.add_self_loops = add_self_loops
+
+    def forward(self, x, edge_index):
+        if self.add_self_loops:
+            loops = torch.arange(0, x.size(0), dtype=torch.long, device=x.device).unsqueeze(0).repeat(2, 1)
+            edge_index = torch.cat([edge_index, loops], dim=1)
+        msg = torch.abs(x[edge_index[0]] - x[edge_index[1]])
+        return self.W(mean_into_copy(msg, edge_index[0], x))
+
+
 _REDUCTIONS = {
     "mean": lambda t: t.mean(dim=0),
     "sum": lambda t: t.sum(dim=0),

@@ -14,6 +14,8 @@ Run in the build container only (needs /root/reference):
   ``MetricalGNN`` (analysisgnn/models/core/{gnn,hgnn}.py) executed through
   ``oracle/ref_loader.py`` (torch_scatter shim), seeds 0-2.
 
+* ``convblocks.pt`` -- the same for the reference's ``GATConvLayer`` and ``OnsetEmbedding`` (gnn.py:154-209, 294-311).
+
 The files are small on purpose; tests compare the oracle restatement and the
 CUDA path with them.
 """
@@ -119,6 +121,33 @@ def intree_goldens():
         print("intree seed", seed, "nodes", x.shape[0], "edges", ei.shape[1])
 
 
+def convblock_goldens():
+    """GATConvLayer (gnn.py:154-209) and OnsetEmbedding (:294-311) of the reference, alone, on the 'during' relation."""
+    gnn, _ = ref_loader.load_core()
+    record = {}
+    for seed in (0, 1):
+        torch.manual_seed(40 + seed)
+        b = synth.intree_batch(2, 50 + 13 * seed, 30 + seed, voices=4, in_features=12, metrical=False)
+        ei = b["edge_index"][:, b["edge_type"] == 2]
+        x = b["x"].clone().requires_grad_(True)
+        gat = gnn.GATConvLayer(12, 20, num_heads=3, dropout=0.0)
+        out = gat(x, ei)
+        pg, ig = _grads(gat, out, [x])
+        record[f"gat{seed}"] = {"x": b["x"], "edge_index": ei, "state": gat.state_dict(), "out": out.detach(),
+                                "param_grads": pg, "x_grad": ig[0]}
+        gat.train()                                  # attention dropout on: the output must not change (see oracle)
+        gat.attndrop.p = 0.5
+        record[f"gat{seed}"]["out_train_dropout"] = gat(x, ei).detach()
+        for loops in (True, False):
+            emb = gnn.OnsetEmbedding(12, 20, add_self_loops=loops)
+            out = emb(x, ei)
+            pg, ig = _grads(emb, out, [x])
+            record[f"onset{seed}_{int(loops)}"] = {"x": b["x"], "edge_index": ei, "state": emb.state_dict(),
+                                                   "out": out.detach(), "param_grads": pg, "x_grad": ig[0]}
+    torch.save(record, os.path.join(HERE, "convblocks.pt"))
+    print("convblocks", sorted(record))
+
+
 DECODE_CASES = {   # name -> synth.decode_case kwargs
     "single": dict(n_notes=240, seed=0),
     "single_extra_nodes": dict(n_notes=200, seed=1, extra_nodes=40),
@@ -147,4 +176,5 @@ def decode_goldens():
 if __name__ == "__main__":
     edge_goldens()
     intree_goldens()
+    convblock_goldens()
     decode_goldens()
