@@ -200,10 +200,15 @@ class ScoreGraphLoader:
             ids.sort(key=lambda g: rng_u64(self.seed, 0x5348, epoch, g, 0))
         return ids
 
+    def batch_ids(self, epoch: int, index: int) -> List[int]:
+        """Scores of global batch ``index`` that this rank takes (data parallel: positions ``g mod W == rank`` of the
+        batch, so the ranks' shares are disjoint and together are the global batch).  Host arithmetic only."""
+        ids = self.order(epoch)[index * self.batch_size:(index + 1) * self.batch_size]
+        return ids[self.rank::self.world_size]
+
     def batch(self, epoch: int, index: int):
         c = self.corpus
-        ids = self.order(epoch)[index * self.batch_size:(index + 1) * self.batch_size]
-        ids = ids[self.rank::self.world_size]                     # data parallel: subgraphs g mod W == rank
+        ids = self.batch_ids(epoch, index)
         step_seed = rng_u64(self.seed, 0x424154, epoch, index, 0)
         starts = [window_start(step_seed, g, c.node_ptr[g + 1] - c.node_ptr[g], self.subgraph_size) for g in ids]
         edges, _, node_index, slot_ptr = window_subgraphs(c.edges[0], c.edges[1], c.edges[2], c.node_ptr, c.edge_ptr,

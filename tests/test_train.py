@@ -243,3 +243,34 @@ def test_graphed_step_replays_the_eager_step():
     for (n, p), q in zip(net_e.named_parameters(), net_g.parameters()):
         assert torch.equal(p, q), n
     assert graphed.launches_per_replay > 50
+
+
+def test_loader_shards_a_global_batch_across_ranks():
+    """Host side of the data-parallel loader (sampler.ScoreGraphLoader.batch_ids): for every world size the ranks'
+    shares of a global batch are disjoint, together they are the batch, an epoch visits every score once, and the
+    order depends on (seed, epoch) only."""
+    import torch
+    from analysisgnn_b200 import sampler
+    n_scores = 37
+    node_ptr = [0]
+    for s in range(n_scores):
+        node_ptr.append(node_ptr[-1] + 5 + s % 4)
+    corpus = sampler.Corpus(torch.zeros(node_ptr[-1], 2), torch.zeros((3, 0), dtype=torch.long), node_ptr)
+    single = sampler.ScoreGraphLoader(corpus, subgraph_size=4, batch_size=8, seed=11)
+    assert len(single) == 5
+    for epoch in (0, 1):
+        seen = []
+        for index in range(len(single)):
+            whole = single.batch_ids(epoch, index)
+            seen += whole
+            for world in (2, 3, 8):
+                parts = [sampler.ScoreGraphLoader(corpus, 4, 8, seed=11, rank=r, world_size=world).batch_ids(epoch, index)
+                         for r in range(world)]
+                flat = [g for p in parts for g in p]
+                assert sorted(flat) == sorted(whole) and len(set(flat)) == len(flat)
+                assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+        assert sorted(seen) == list(range(n_scores))
+    assert single.order(0) != single.order(1)
+    assert single.order(0) == sampler.ScoreGraphLoader(corpus, 4, 8, seed=11).order(0)
+    assert single.order(0) != sampler.ScoreGraphLoader(corpus, 4, 8, seed=12).order(0)
+    assert sampler.ScoreGraphLoader(corpus, 4, 8, seed=11, shuffle=False).order(3) == list(range(n_scores))
