@@ -238,13 +238,24 @@ def begin_step() -> None:
     _amax_pools.clear()
 
 
+_SPLIT_CACHE_MAX_ENTRIES = 512     # a step makes a few dozen; the cap only matters to callers that never call begin_step
+
+
+def _remember(key, value):
+    _split_cache[key] = value
+    if len(_split_cache) > _SPLIT_CACHE_MAX_ENTRIES:
+        for old in list(_split_cache)[:_SPLIT_CACHE_MAX_ENTRIES // 2]:      # oldest first (insertion order)
+            del _split_cache[old]
+    return value
+
+
 def _cached_split(x: torch.Tensor) -> Split:
     if x.numel() > _SPLIT_CACHE_MAX_ELEMS:
         return split(x)
     key = (x.data_ptr(), tuple(x.shape), x.stride(0), x._version)
     hit = _split_cache.get(key)
     if hit is None:
-        hit = _split_cache[key] = (x, split(x))
+        hit = _remember(key, (x, split(x)))
     return hit[1]
 
 
@@ -254,7 +265,7 @@ def _cached_split_f16(x: torch.Tensor) -> SplitH:
     key = ("f16", x.data_ptr(), tuple(x.shape), x.stride(0), x._version)
     hit = _split_cache.get(key)
     if hit is None:
-        hit = _split_cache[key] = (x, split_f16(x))
+        hit = _remember(key, (x, split_f16(x)))
     return hit[1]
 
 

@@ -64,3 +64,15 @@ def test_no_cpu_path_for_the_operand_producers():
         linalg.split_f16(torch.randn(8, 8))
     with pytest.raises(_lib.AgnnError):
         linalg.amax_into(torch.zeros(1), torch.randn(8, 8))
+
+
+def test_split_cache_is_bounded_without_begin_step():
+    """Callers that never call ``begin_step`` (a plain torch optimizer loop) must not grow the weight-split cache
+    without bound: the oldest half goes when the cap is passed."""
+    linalg.begin_step()
+    for i in range(linalg._SPLIT_CACHE_MAX_ENTRIES + 10):
+        linalg._remember(("k", i), i)
+    assert len(linalg._split_cache) <= linalg._SPLIT_CACHE_MAX_ENTRIES
+    assert ("k", linalg._SPLIT_CACHE_MAX_ENTRIES + 9) in linalg._split_cache and ("k", 0) not in linalg._split_cache
+    linalg.begin_step()
+    assert not linalg._split_cache
