@@ -155,6 +155,41 @@ def test_tf32_pair_output_is_what_the_gemm_consumes():
     assert torch.equal(pair[0], want.hi) and torch.equal(pair[1], want.lo)
 
 
+@pytest.mark.parametrize("hubs", [False, True])
+def test_f16_pair_output_is_what_the_gemm_consumes(hubs):
+    """agnn_gather_reduce_f16: out / out_lo receive fp16(s y) and fp16(s y - hi), s from the amax scalar --
+    bit-identical to agnn_split_f16 of the plain result under the same scalar; also for hub rows (>= 4096 entries),
+    which the multi-warp kernels write."""
+    from analysisgnn_b200 import linalg
+    f = 256
+    if hubs:
+        rng = np.random.default_rng(5)
+        n = 400
+        row = np.concatenate([np.full(9000, 3), np.full(4096, 17), rng.integers(0, n, 5000)])
+        rng.shuffle(row)
+        ei = torch.as_tensor(np.stack((row, rng.integers(0, n, len(row)))), dtype=torch.long)
+    else:
+        n = 700
+        ei = _graph(n, n, 5000, 12)
+    torch.manual_seed(1)
+    x = torch.randn(n, f, device=DEV) * 0.03
+    csr = graph.TypedCSR(ei.to(DEV), None, n)
+    if hubs:
+        assert int(csr.fwd.n_heavy[0]) == 2
+    rel = [ops.rel_of(csr.fwd, 0, x, out_col=f, n_edges=ei.shape[1])]
+    plain = torch.empty((n, 2 * f), device=DEV)
+    ops.gather_reduce(rel, plain, f, mean=True, concat=True, self_add=x, copy=x, copy_col=0)
+    amax = linalg.amax_into(linalg.new_amax(DEV), x)       # |mean with the self term| <= 2 amax: inside the headroom
+    pair = torch.empty((2, n, 2 * f), dtype=torch.float16, device=DEV)
+    ops.gather_reduce(rel, pair[0], f, mean=True, concat=True, self_add=x, copy=x, copy_col=0, out_lo=pair[1],
+                      pair_amax=amax)
+    want = linalg.split_f16(plain, amax)
+    assert torch.equal(pair[0], want.hi) and torch.equal(pair[1], want.lo)
+    assert not torch.isinf(pair[0]).any()
+    back = (pair[0].double() + pair[1].double()) / float(linalg.f16_scale(amax))
+    assert_close(back, plain, 1e-6, "decoded pair")
+
+
 @pytest.mark.parametrize("mean", [False, True])
 def test_heavy_rows_are_split_across_warps(mean):
     """Hub rows (>= 4096 entries) take the multi-warp path: chunk partials + ordered combine.  Same numbers as the
