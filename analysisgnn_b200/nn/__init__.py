@@ -19,4 +19,4 @@ from .intree import (GATConvLayer, HeteroConv, MetricalConvLayer, MetricalGNN, O
 from .hetero import (HeteroSAGELayer, HeteroSAGEStack, HGTConv, HeteroHGTStack, HybridGNN, HybridHGT,  # noqa: F401
                      SAGEConv, SequenceBranch)
 from .layers import GRU, LayerNorm, Linear  # noqa: F401
-from .shell import AnalysisEncoder, multitask_ce, onset_pool  # noqa: F401
+from .shell import AnalysisEncoder, CrossEntropyLoss, MultiTaskLoss, multitask_ce, onset_pool  # noqa: F401

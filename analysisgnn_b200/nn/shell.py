@@ -115,3 +115,49 @@ def multitask_ce(logits, labels):
     ``CrossEntropyLoss(ignore_index=-1, label_smoothing=0.1)`` divided by the number of tasks."""
     total = sum(ops.cross_entropy(logits[t], labels[t], ignore_index=-1, label_smoothing=0.1) for t in labels)
     return total / len(labels)
+
+
+class CrossEntropyLoss(nn.Module):
+    """``nn.CrossEntropyLoss(ignore_index, label_smoothing)`` with mean reduction on ``agnn_softmax_ce_fwd/_bwd`` -- the
+    per-task criterion ``ContinualAnalysisGNN`` builds (analysisgnn/models/analysis.py:881-888)."""
+
+    def __init__(self, ignore_index: int = -100, label_smoothing: float = 0.0):
+        super().__init__()
+        self.ignore_index, self.label_smoothing = ignore_index, label_smoothing
+
+    def forward(self, logits, target):
+        return ops.cross_entropy(logits, target, ignore_index=self.ignore_index, label_smoothing=self.label_smoothing)
+
+
+class MultiTaskLoss(nn.Module):
+    """Drop-in for the reference's ``MultiTaskLoss(tasks, loss_ft, loss_weights=None, requires_grad=True)``
+    (analysisgnn/models/chord.py:16-49): per-task criteria from ``loss_ft``; with ``requires_grad`` the learned
+    weighting of Liebel & Koerner, ``sum_i 0.5 / p_i^2 * L_i + log(1 + p_i^2)`` with ``params`` initialised to one
+    (same ``state_dict`` key), else the plain sum.  Returns the per-task losses plus ``"total"``; ``p_i`` belongs to
+    the i-th task PRESENT in ``gt`` (the reference enumerates ``gt``'s keys, :41-44).  The caller divides ``total`` by
+    the number of tasks (analysis.py:1035-1037)."""
+
+    def __init__(self, tasks, loss_ft, loss_weights=None, requires_grad=True):
+        super().__init__()
+        if set(tasks) != set(loss_ft.keys()):
+            raise AssertionError("tasks and loss_ft must name the same tasks")
+        if loss_weights is not None and set(tasks) != set(loss_weights.keys()):
+            raise AssertionError("tasks and loss_weights must name the same tasks")
+        self.loss_weights = loss_weights if loss_weights is not None else {task: 1 for task in tasks}
+        self.tasks, self.loss_ft, self.requires_grad = tasks, loss_ft, requires_grad
+        if requires_grad:
+            self.params = nn.Parameter(torch.ones(len(tasks)))
+        else:
+            self.params = torch.ones(len(tasks), requires_grad=False)
+
+    def forward(self, pred, gt):
+        out = {task: self.loss_ft[task](pred[task], gt[task]) for task in gt.keys()}
+        total = 0
+        for i, loss in enumerate(list(out.values())):
+            if self.requires_grad:
+                total = total + (0.5 / (self.params[i] ** 2) * loss + torch.log(1 + self.params[i] ** 2))
+            else:
+                total = total + loss
+        out["total"] = total
+        return out
+

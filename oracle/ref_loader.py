@@ -137,3 +137,26 @@ def load_onsetwise_decode():
         else:
             raise LookupError("onsetwise_logit_aggregation not found in the reference")
     return _cache["decode"]
+
+
+def load_multitask_loss():
+    """The reference's ``MultiTaskLoss`` class (models/chord.py:16-49), unmodified (the module imports graphmuse /
+    partitura at the top, so only the class definition is taken)."""
+    if "mtl" not in _cache:
+        import torch
+        import torch.nn as nn
+        path = os.path.join(REFERENCE_ROOT, "analysisgnn/models/chord.py")
+        with open(path) as fh:
+            tree = ast.parse(fh.read(), filename=path)
+        for node in tree.body:
+            if isinstance(node, ast.ClassDef) and node.name == "MultiTaskLoss":
+                module = ast.Module(body=[node], type_ignores=[])
+                ast.fix_missing_locations(module)
+                scope = {"torch": torch, "nn": nn}
+                exec(compile(module, "<reference models/chord.py>", "exec"), scope)
+                _cache["mtl"] = scope[node.name]
+                break
+        else:
+            raise LookupError("MultiTaskLoss not found in the reference")
+    return _cache["mtl"]
+
