@@ -100,3 +100,9 @@ def test_with_the_cuda_criterion(requires_grad):
         assert_close(p2[t].grad, p1[t].grad, FP32_REL, f"d logits {t}")
     if requires_grad:
         assert_close(net.params.grad, ref.params.grad, FP32_REL, "d params")
+
+
+def test_cuda_criterion_has_no_cpu_path():
+    from analysisgnn_b200 import _lib
+    with pytest.raises(_lib.AgnnError):
+        ann.CrossEntropyLoss(ignore_index=-1, label_smoothing=0.1)(torch.randn(4, 3), torch.tensor([0, 1, 2, -1]))
