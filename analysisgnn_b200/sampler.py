@@ -177,6 +177,54 @@ class Corpus:
         return self._csr
 
 
+class NodeStore(dict):
+    """The part of a PyG node storage the reference's training step reads (analysisgnn/models/analysis.py:926-968):
+    ``batch["note"][key]``, ``.keys()``, attribute access (``.pitch_spelling``, ``.batch_size``)."""
+
+    def __init__(self, tensors: Dict[str, torch.Tensor], batch_size: int):
+        super().__init__(tensors)
+        self.batch_size = int(batch_size)
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+
+class HeteroBatch:
+    """What ``MuseNeighborLoader(..., transform=transform_to_pyg)`` yields, as far as ``ContinualAnalysisGNN.common_step``
+    uses it (analysis.py:947-961): ``.x_dict``, ``.edge_index_dict``, ``.batch_dict``, ``.num_sampled_nodes_dict``,
+    ``.num_sampled_edges_dict`` and ``batch["note"]`` with ``.batch_size``, the features, the graph ids and every
+    per-note array of the corpus (labels, spellings, onsets).  Built from ``ScoreGraphLoader.batch``'s dict."""
+
+    def __init__(self, out: dict):
+        self.x_dict = out["x_dict"]
+        self.edge_index_dict = out["edge_index_dict"]
+        self.batch_dict = out["batch_dict"]
+        self.num_sampled_nodes_dict = out.get("num_sampled_nodes_dict")
+        self.num_sampled_edges_dict = out.get("num_sampled_edges_dict")
+        self.graph_ids = out.get("graph_ids")
+        self.node_index = out.get("node_index")
+        self._stores = {}
+        for t, x in self.x_dict.items():
+            fields = {"x": x, "batch": self.batch_dict[t]}
+            if t == "note":
+                fields.update(out.get("extras", {}))
+            self._stores[t] = NodeStore(fields, out["batch_size"] if t == "note" else x.shape[0])
+
+    def __getitem__(self, node_type: str) -> NodeStore:
+        return self._stores[node_type]
+
+    @property
+    def node_types(self):
+        return list(self._stores)
+
+    @property
+    def edge_types(self):
+        return list(self.edge_index_dict)
+
+
 class ScoreGraphLoader:
     """Batches of ``batch_size`` score windows (``subgraph_size`` notes each), optionally extended by
     ``num_neighbors`` sampled hops, in the dict layout ``TorchAnalysisGNN.encode`` consumes
@@ -193,6 +241,15 @@ class ScoreGraphLoader:
 
     def __len__(self):
         return (self.corpus.n_scores + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        """One epoch of ``HeteroBatch``es (what the Lightning loop iterates over); every ``iter()`` starts the next
+        epoch, so shuffling differs from epoch to epoch and is the same on every rank."""
+        epoch = getattr(self, "_epoch", 0)
+        self._epoch = epoch + 1
+        for index in range(len(self)):
+            if self.batch_ids(epoch, index):               # a rank may have no share of a short last batch
+                yield HeteroBatch(self.batch(epoch, index))
 
     def order(self, epoch: int) -> List[int]:
         ids = list(range(self.corpus.n_scores))

@@ -118,3 +118,28 @@ def test_corpus_file_round_trip_feeds_the_same_batches(tmp_path):
         assert torch.equal(a["extras"]["onset_div"], b["extras"]["onset_div"])
         for et in a["edge_index_dict"]:
             assert torch.equal(a["edge_index_dict"][et], b["edge_index_dict"][et]), et
+
+
+def test_loader_iterates_hetero_batches():
+    """``for batch in loader`` yields what the reference's training step reads (sampler.HeteroBatch); a new ``iter()``
+    is a new epoch with another order."""
+    sizes = [300, 420, 260, 510, 333]
+    arrays, corpus = _corpus(sizes, seed=9)
+    corpus.extras["pitch_spelling"] = torch.randint(0, 35, (corpus.node_ptr[-1],), device=DEV)
+    loader = sampler.ScoreGraphLoader(corpus, subgraph_size=200, batch_size=2, seed=4)
+    first = list(loader)
+    assert len(first) == len(loader) == 3
+    seen = []
+    for b in first:
+        n = b["note"].batch_size
+        assert n == 200 * len(b.graph_ids) and b.x_dict["note"].shape == (n, 8)
+        assert b["note"].pitch_spelling.shape == (n,) and "pitch_spelling" in b["note"].keys()
+        assert torch.equal(b["note"].pitch_spelling, corpus.extras["pitch_spelling"][b.node_index])
+        assert b.batch_dict["note"].bincount().tolist() == [200] * len(b.graph_ids)
+        assert b.num_sampled_nodes_dict is None and set(b.edge_types) == set(b.edge_index_dict)
+        seen += b.graph_ids
+    assert sorted(seen) == list(range(5))
+    second = [b.graph_ids for b in loader]
+    assert sorted(g for ids in second for g in ids) == list(range(5))
+    assert second == [loader.batch_ids(1, i) for i in range(3)] and [b.graph_ids for b in first] == \
+        [loader.batch_ids(0, i) for i in range(3)]

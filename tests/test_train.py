@@ -274,3 +274,41 @@ def test_loader_shards_a_global_batch_across_ranks():
     assert single.order(0) == sampler.ScoreGraphLoader(corpus, 4, 8, seed=11).order(0)
     assert single.order(0) != sampler.ScoreGraphLoader(corpus, 4, 8, seed=12).order(0)
     assert sampler.ScoreGraphLoader(corpus, 4, 8, seed=11, shuffle=False).order(3) == list(range(n_scores))
+
+
+def test_hetero_batch_serves_the_reference_training_step():
+    """sampler.HeteroBatch: the accesses of ``ContinualAnalysisGNN.common_step`` / ``create_mask_dict``
+    (analysisgnn/models/analysis.py:926-968) on a batch dict of the shape ``ScoreGraphLoader.batch`` returns."""
+    import torch
+    from analysisgnn_b200 import sampler
+    n, extra = 12, 5
+    task_dict = {"cadence": 4, "localkey": 50}
+    out = {
+        "batch_size": n, "graph_ids": [3, 1],
+        "x_dict": {"note": torch.randn(n + extra, 6)},
+        "edge_index_dict": {("note", "onset", "note"): torch.zeros((2, 0), dtype=torch.long)},
+        "batch_dict": {"note": torch.cat((torch.zeros(8, dtype=torch.long), torch.ones(n + extra - 8, dtype=torch.long)))},
+        "num_sampled_nodes_dict": {"note": [n, extra]}, "num_sampled_edges_dict": {("note", "onset", "note"): [0]},
+        "extras": {"pitch_spelling": torch.randint(0, 35, (n + extra,)), "key_signature": torch.randint(0, 15, (n + extra,)),
+                   "cadence": torch.randint(0, 6, (n + extra,)), "localkey": torch.randint(0, 50, (n + extra,)),
+                   "valid_label": torch.ones(n + extra, dtype=torch.long)},
+    }
+    batch = sampler.HeteroBatch(out)
+    # analysis.py:948-961, verbatim access pattern
+    x_dict = batch.x_dict
+    batch_size = batch["note"].batch_size
+    labels_dict = {k: batch["note"][k][:batch_size] for k in task_dict.keys() if k in batch["note"].keys()}
+    pitch_spelling = batch["note"].pitch_spelling
+    key_signature = batch["note"].key_signature
+    labels_dict = {k: torch.where(labels_dict[k] < task_dict[k], labels_dict[k], torch.zeros_like(labels_dict[k]))
+                   for k in labels_dict.keys()}
+    assert batch.edge_index_dict is out["edge_index_dict"] and batch.batch_dict is out["batch_dict"]
+    assert batch.num_sampled_edges_dict is out["num_sampled_edges_dict"]
+    assert batch.num_sampled_nodes_dict is out["num_sampled_nodes_dict"]
+    assert "valid_label" in batch["note"].keys() and "has_cadence" not in batch["note"].keys()
+    valid = batch["note"]["valid_label"][:batch_size].bool()
+    assert batch_size == n and set(labels_dict) == set(task_dict) and int(labels_dict["cadence"].max()) < 4
+    assert x_dict["note"].shape[0] == n + extra and pitch_spelling.shape == key_signature.shape == (n + extra,)
+    assert valid.all() and batch.node_types == ["note"] and batch["note"].x is x_dict["note"]
+    with pytest.raises(AttributeError):
+        batch["note"].not_there
