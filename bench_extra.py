@@ -217,20 +217,30 @@ def hgt_encoder_step(encoder_type="hgt"):
             "step_ms_graph": ms_graph, "nodes_per_s": n / ms_graph * 1e3}
 
 
-def decode_full_score(n_notes=200_000, cpu_notes=20_000):
+def decode_full_score(n_notes=200_000, cpu_notes=20_000, cpu_port=False):
     """Onset-wise logit aggregation + decode (analysisgnn/models/analysis.py:44-101) of one 200 k-note score: the call
     as ``predict`` makes it (device tensors in, device tensors out; its own host synchronisations included), timed
-    with CUDA events; beside it the CPU restatement (oracle/decode.py, pinned to the reference's function) on a
-    bounded sample -- its loop over change points is O(segments x notes), so the sample is smaller and the
-    per-note figure FAVOURS the CPU."""
+    with CUDA events.  ``cpu_port`` (--with-cpu-port) adds the cpu_baseline leg: the CPU restatement (oracle/decode.py,
+    pinned to the reference's function; test infrastructure, used here only as the reported baseline) on a bounded
+    sample -- its loop over change points is O(segments x notes), so the sample is smaller and the per-note figure
+    FAVOURS the CPU."""
     import time
+    from types import SimpleNamespace
     from analysisgnn_b200 import decode
-    from oracle import decode as odecode
+
+    def note_store(x, batch, onset_div, edge_index_dict):
+        class Graph(dict):
+            pass
+        g = Graph(note=SimpleNamespace(x=x, batch=batch, onset_div=onset_div))
+        g.edge_index_dict = edge_index_dict
+        return g
+
+    rna_keys = decode.RNA_KEYS
 
     def prep(case, dev):
         mv = lambda t: None if t is None else t.to(dev)
-        g = odecode.note_store(mv(case["x"]), mv(case["batch"]), mv(case["onset_div"]),
-                               {k: mv(v) for k, v in case["edge_index_dict"].items()})
+        g = note_store(mv(case["x"]), mv(case["batch"]), mv(case["onset_div"]),
+                       {k: mv(v) for k, v in case["edge_index_dict"].items()})
         return {k: v.to(dev) for k, v in case["logits"].items()}, g
 
     case = synth.decode_case(n_notes, 21, smooth=12)
@@ -241,13 +251,18 @@ def decode_full_score(n_notes=200_000, cpu_notes=20_000):
         decode.onsetwise_logit_aggregation({k: v.clone() for k, v in logits0.items()}, g, batch_size=n_notes)
 
     ms = timeit(run, n=10, warm=3)
-    small = synth.decode_case(cpu_notes, 21, smooth=12)
-    lc, gc = prep(small, "cpu")
-    torch.set_num_threads(os.cpu_count())
-    t0 = time.perf_counter()
-    odecode.onsetwise_logit_aggregation(lc, gc, batch_size=cpu_notes)
-    cpu_s = time.perf_counter() - t0
-    cols = sum(synth.DECODE_TASKS[k] for k in odecode.RNA_KEYS)
+    cpu = None
+    if cpu_port:
+        from oracle import decode as odecode
+        small = synth.decode_case(cpu_notes, 21, smooth=12)
+        lc, gc = prep(small, "cpu")
+        torch.set_num_threads(os.cpu_count())
+        t0 = time.perf_counter()
+        odecode.onsetwise_logit_aggregation(lc, gc, batch_size=cpu_notes)
+        cpu_s = time.perf_counter() - t0
+        cpu = {"notes": cpu_notes, "seconds": cpu_s, "notes_per_s": cpu_notes / cpu_s, "cores": os.cpu_count(),
+               "kind": "port"}
+    cols = sum(synth.DECODE_TASKS[k] for k in rna_keys)
     e_kept = int(case["edge_index_dict"][("note", "onset", "note")].shape[1])
     # algorithmic bytes of one call: the packed logits read (edges + self) and written by the mean, read and written
     # by the two softmaxes, read by the arg-max of one row per onset, rows copied by the assignment (read + write)
@@ -255,13 +270,14 @@ def decode_full_score(n_notes=200_000, cpu_notes=20_000):
     return {"notes": n_notes, "onset_edges": e_kept, "task_columns": cols, "gpu_ms": ms,
             "gpu_notes_per_s": n_notes / ms * 1e3, "algorithmic_gb": alg / 1e9,
             "achieved_gbs_whole_call": alg / ms / 1e6,
-            "cpu_port": {"notes": cpu_notes, "seconds": cpu_s, "notes_per_s": cpu_notes / cpu_s,
-                         "cores": os.cpu_count(), "kind": "port"}}
+            "cpu_port": cpu}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only-decode", action="store_true")
+    ap.add_argument("--with-cpu-port", action="store_true",
+                    help="decode: also time the CPU restatement (oracle/decode.py) on a bounded sample")
     ap.add_argument("--only-encoders", action="store_true",
                     help="in-tree MetricalGNN 4L/512 and the HGT encoder step (AGNN_PARITY_OPERANDS=tf32|f16 selects "
                          "the operand form)")
@@ -280,7 +296,7 @@ def main():
             json.dump(r, fh, indent=1)
         return
     if args.only_decode:
-        r = decode_full_score()
+        r = decode_full_score(cpu_port=args.with_cpu_port)
         print("decode", r)
         with open(args.out, "w") as fh:
             json.dump({"decode_full_score": r}, fh, indent=1)
@@ -297,7 +313,7 @@ def main():
     else:
         res.update(hgt_attention=hgt_kernels(), full_score_inference=full_score_inference(),
                    metrical_gnn_4L512=metrical_gnn_step(), hgt_encoder=hgt_encoder_step(),
-                   decode_full_score=decode_full_score())
+                   decode_full_score=decode_full_score(cpu_port=args.with_cpu_port))
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as fh:
         json.dump(res, fh, indent=1)
