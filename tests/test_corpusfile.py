@@ -166,3 +166,32 @@ def test_convert_cli(tmp_path):
     info = subprocess.run([sys.executable, os.path.join(root, "tools", "convert_corpus.py"), "--info", dst],
                           capture_output=True, text=True)
     assert info.returncode == 0 and "checksums ok" in info.stdout and "extra.onset_div" in info.stdout
+
+
+def test_container_round_trips_arbitrary_arrays(tmp_path):
+    """The container itself (save_arrays / load_arrays): every storable dtype, empty and odd shapes, names with dots --
+    bytes come back exactly, every array on a page boundary (hypothesis-driven)."""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    dtypes = st.sampled_from([np.int32, np.int64, np.float32, np.float64, np.uint8])
+    arrays = st.dictionaries(
+        st.text(alphabet="abcxyz._0189", min_size=1, max_size=12),
+        dtypes.flatmap(lambda d: hnp.arrays(d, hnp.array_shapes(min_dims=1, max_dims=3, min_side=0, max_side=9))),
+        min_size=1, max_size=5)
+    counter = {"n": 0}
+
+    @settings(max_examples=40, deadline=None)
+    @given(arrays, st.integers(1, 9))
+    def check(arrs, n_rel):
+        counter["n"] += 1
+        path = str(tmp_path / f"h{counter['n']}.agc")
+        cf.save_arrays(path, arrs, n_rel)
+        back, rel = cf.load_arrays(path, verify=True)
+        assert rel == n_rel and set(back) == set(arrs)
+        for k, a in arrs.items():
+            assert back[k].dtype == a.dtype and back[k].shape == a.shape
+            assert np.asarray(back[k]).tobytes() == np.ascontiguousarray(a).tobytes()
+        assert all(e["offset"] % cf.ALIGN == 0 for e in cf.read_table(path)["arrays"])
+
+    check()
