@@ -32,6 +32,30 @@ class AgnnError(RuntimeError):
     pass
 
 
+# Routes off the hand-written kernels -- an operand repack before agnn_gemm, a library kernel for a shape the row
+# kernels do not take (odd widths, GRU sizes) -- are counted here; under ``set_strict(True)`` (bench.py, the full-size
+# parity tests) they raise instead, so a measured or parity-checked hot path provably has none.
+_strict = os.environ.get("AGNN_STRICT", "0") not in ("", "0")
+library_routes = {}
+
+
+def set_strict(on: bool) -> None:
+    global _strict
+    _strict = bool(on)
+
+
+def strict() -> bool:
+    return _strict
+
+
+def library_route(what: str, counter=None, key=None) -> None:
+    library_routes[what] = library_routes.get(what, 0) + 1
+    if counter is not None:
+        counter[key] = counter.get(key, 0) + 1
+    if _strict:
+        raise AgnnError(f"strict mode: {what}")
+
+
 class Coo(C.Structure):
     _fields_ = [("row", C.c_void_p), ("col", C.c_void_p), ("etype", C.c_void_p), ("n_edges", C.c_int64),
                 ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("n_rel", C.c_int32), ("reserved", C.c_int32),
@@ -86,8 +110,8 @@ _PROTOTYPES = {
     "agnn_sumsq_blocks": (C.c_int, [C.c_int64]),
     "agnn_sumsq_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnn_adamw_clip_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
-                                       C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_float, C.c_float,
-                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+                                       C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
+                                       C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "agnn_split_tf32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p]),
     "agnn_gemm_split_k": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64]),

@@ -413,7 +413,10 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_partial_kernel(const __
   }
 }
 
-// one warp per heavy (relation, row): sum the chunk partials in order and finish the row like the main kernel
+// CONCAT: one warp per heavy (relation, row) -- every (relation, row) owns its output slice.  SUM: one warp per heavy
+// ROW: the warp that owns the row's FIRST heavy relation adds the chunk partials of every heavy relation of that row
+// in relation order (chunks in order inside a relation) to what the main kernel wrote (self + light relations) and
+// stores once.  One writer per output element, fixed summation order: no atomics, bit-identical from run to run.
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __grid_constant__ GatherParams p) {
   using VT = Vec16<T>;
@@ -425,6 +428,7 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
   T* const out = static_cast<T*>(p.out);
   T* const out_lo = static_cast<T*>(p.out_lo);
   const float f16s = p.pair_amax ? f16_scale_of(__ldg(p.pair_amax)) : 0.f;
+  const bool sum_mode = p.combine == AGNN_COMBINE_SUM;
   int64_t g = 0, item = 0;
   for (int r = 0; r < p.n_rel; ++r) {
     const agnn_rel_t& R = p.rel[r];
@@ -437,6 +441,15 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
       const int64_t g0 = g;
       g += chunks;
       if (item % n_warps != warp_id || g > p.max_chunks) continue;
+      if (sum_mode) {
+        // the row belongs to the warp of its first heavy relation
+        bool first = true;
+        for (int q = 0; q < r && first; ++q) {
+          const agnn_rel_t& Q = p.rel[q];
+          if (is_heavy(p, Q, __ldg(Q.rowptr + row + 1) - __ldg(Q.rowptr + row))) first = false;
+        }
+        if (!first) continue;
+      }
       float acc[V][E];
 #pragma unroll
       for (int v = 0; v < V; ++v)
@@ -454,7 +467,7 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
         }
       }
       const float s = p.scale == AGNN_SCALE_MEAN ? 1.f / (float)max(end - beg, 1) : 1.f;
-      if (p.combine == AGNN_COMBINE_CONCAT) {
+      if (!sum_mode) {
         const int64_t off = (int64_t)row * p.ld_out + R.out_col;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -472,34 +485,70 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
             store_split<T>(out, out_lo, off + cc, o, f16s);
           }
         }
-      } else {
-        // COMBINE_SUM: the main kernel wrote self + the light relations; add this relation's share.  Several
-        // heavy relations may hit the same row: entries of one row are handled by different warps, so each adds
-        // with its own read-modify-write only when it is the row's single heavy relation; otherwise atomics.
-        const int64_t off = (int64_t)row * p.ld_out + p.rel[0].out_col;
+        continue;
+      }
+      // COMBINE_SUM: what the main kernel wrote (self + light relations), then relation r, then the later heavy
+      // relations of the same row in relation order
+      float tot[V][E];
+      const int64_t off = (int64_t)row * p.ld_out + p.rel[0].out_col;
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const int cc = (v * 32 + lane) * E;
-          if (cc < F) {
-            if constexpr (sizeof(T) == 4) {
-              if (!out_lo) {
+      for (int v = 0; v < V; ++v) {
+        const int cc = (v * 32 + lane) * E;
+        if (cc < F) {
+          VT::load(out + off + cc, tot[v]);
+          if (out_lo) {
+            float lo[E];
+            VT::load(out_lo + off + cc, lo);
 #pragma unroll
-                for (int e = 0; e < E; ++e) atomicAdd(reinterpret_cast<float*>(out) + off + cc + e, acc[v][e] * s);
-                continue;
+            for (int e = 0; e < E; ++e) tot[v][e] += lo[e];
+          }
+#pragma unroll
+          for (int e = 0; e < E; ++e) tot[v][e] = fmaf(acc[v][e], s, tot[v][e]);
+        }
+      }
+      int64_t g2 = g;                                   // chunk base of relation r's entries after (r, h) ...
+      for (int h2 = h + 1; h2 < nh; ++h2) {
+        const int row2 = __ldg(R.heavy_rows + h2);
+        g2 += (__ldg(R.rowptr + row2 + 1) - __ldg(R.rowptr + row2) + kHeavyChunk - 1) / kHeavyChunk;
+      }
+      for (int q = r + 1; q < p.n_rel; ++q) {           // ... then relation q's entries in list order
+        const agnn_rel_t& Q = p.rel[q];
+        if (!Q.heavy_rows) continue;
+        const int nq = (int)min((int64_t)__ldg(Q.n_heavy), Q.heavy_cap);
+        for (int h2 = 0; h2 < nq; ++h2) {
+          const int row2 = __ldg(Q.heavy_rows + h2);
+          const int b2 = __ldg(Q.rowptr + row2), e2 = __ldg(Q.rowptr + row2 + 1);
+          const int ch2 = (e2 - b2 + kHeavyChunk - 1) / kHeavyChunk;
+          if (row2 == row && g2 + ch2 <= p.max_chunks) {
+            const float s2 = p.scale == AGNN_SCALE_MEAN ? 1.f / (float)max(e2 - b2, 1) : 1.f;
+            float a2[V][E];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+#pragma unroll
+              for (int e = 0; e < E; ++e) a2[v][e] = 0.f;
+            for (int c = 0; c < ch2; ++c) {
+              const float* wp = p.heavy_ws + (g2 + c) * F;
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                const int cc = (v * 32 + lane) * E;
+                if (cc < F) {
+#pragma unroll
+                  for (int e = 0; e < E; ++e) a2[v][e] += wp[cc + e];
+                }
               }
             }
-            float cur[E], lo[E];
-            VT::load_nc(out + off + cc, cur);
-            if (out_lo) {
-              VT::load_nc(out_lo + off + cc, lo);
 #pragma unroll
-              for (int e = 0; e < E; ++e) cur[e] += lo[e];
-            }
+            for (int v = 0; v < V; ++v)
 #pragma unroll
-            for (int e = 0; e < E; ++e) cur[e] = fmaf(acc[v][e], s, cur[e]);
-            store_split<T>(out, out_lo, off + cc, cur);
+              for (int e = 0; e < E; ++e) tot[v][e] = fmaf(a2[v][e], s2, tot[v][e]);
           }
+          g2 += ch2;
         }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int cc = (v * 32 + lane) * E;
+        if (cc < F) store_split<T>(out, out_lo, off + cc, tot[v]);
       }
     }
   }

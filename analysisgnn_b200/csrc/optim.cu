@@ -62,6 +62,8 @@ struct AdamParams {
   int n_partials;
   float lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm, bias1, bias2_sqrt;
   const int* step_dev;               // optional: step number on the device (overrides bias1 / bias2_sqrt)
+  const float* lr_dev;               // optional: learning rate on the device (overrides lr) -- a scheduler keeps
+                                     // working when the launch is replayed from a CUDA graph
   float* norm_out;
 };
 
@@ -82,14 +84,15 @@ __global__ void __launch_bounds__(kThreads) adamw_kernel(const __grid_constant__
   const float gs = s_clip;
   const agnn_param_chunk_t c = p.chunks[blockIdx.x];
   float* const w = static_cast<float*>(c.param);
-  const float decay = 1.f - p.lr * p.weight_decay;
+  const float lr = p.lr_dev ? __ldg(p.lr_dev) : p.lr;
+  const float decay = 1.f - lr * p.weight_decay;
   float bias1 = p.bias1, bias2_sqrt = p.bias2_sqrt;
   if (p.step_dev) {
     const float t = (float)__ldg(p.step_dev);
     bias1 = 1.f - powf(p.beta1, t);
     bias2_sqrt = sqrtf(1.f - powf(p.beta2, t));
   }
-  const float step_size = p.lr / bias1;
+  const float step_size = lr / bias1;
   for (int i = threadIdx.x * 4; i < c.count; i += kThreads * 4) {
     const int64_t a = c.arena_off + i;
     float gv[4], mv[4], vv[4], wv[4];
@@ -161,8 +164,9 @@ extern "C" int agnn_sumsq_partials(const float* grad, int64_t n, float* partials
 
 extern "C" int agnn_adamw_clip_step(const agnn_param_chunk_t* chunks, int n_chunks, const float* grad, float* m,
                                     float* v, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                    int step, const int* step_dev, float grad_scale, float max_norm,
-                                    const float* partials, int n_partials, float* norm_out, agnn_stream_t stream) {
+                                    int step, const int* step_dev, const float* lr_dev, float grad_scale,
+                                    float max_norm, const float* partials, int n_partials, float* norm_out,
+                                    agnn_stream_t stream) {
   if (n_chunks < 0 || (step < 1 && !step_dev) || !chunks || !grad || !m || !v || !partials || n_partials < 1)
     return fail(AGNN_ERR_ARG, "adamw_clip_step: bad arguments (n_chunks=%d step=%d)", n_chunks, step);
   if (!aligned16(grad) || !aligned16(m) || !aligned16(v))
@@ -175,6 +179,7 @@ extern "C" int agnn_adamw_clip_step(const agnn_param_chunk_t* chunks, int n_chun
   p.bias1 = 1.f - powf(beta1, (float)(step < 1 ? 1 : step));
   p.bias2_sqrt = sqrtf(1.f - powf(beta2, (float)(step < 1 ? 1 : step)));
   p.step_dev = step_dev;
+  p.lr_dev = lr_dev;
   p.norm_out = norm_out;
   adamw_kernel<<<n_chunks, kThreads, 0, (cudaStream_t)stream>>>(p);
   return check_launch("adamw_clip_step");

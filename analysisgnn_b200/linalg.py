@@ -1,16 +1,13 @@
 """Dense contractions used by the fused layers.
 
-The per-relation / per-node-type projections are the only GEMM-shaped work on the hot path.
-``backend()`` selects who runs them:
+The per-relation / per-node-type projections are the only GEMM-shaped work on the hot path.  All of them run on
+this repo's sm_100a tensor-core GEMM (csrc/gemm.cu, ``agnn_gemm``): fp32 tensors in a three-product split mode
+(fp32 parity) -- 3xTF32 (``Split``), or 3 x fp16 with one power-of-two scale per tensor (``SplitH``,
+``parity_operands() == "f16"``: same accuracy at twice the MMA rate) -- bf16 tensors in the bf16 mode.
 
-* ``"tcgen05"`` -- this repo's sm_100a tensor-core GEMM (csrc/gemm.cu, ``agnn_gemm``): fp32 tensors
-  run in a three-product split mode (fp32 parity) -- 3xTF32 (``Split``), or 3 x fp16 with one power-of-two scale per
-  tensor (``SplitH``, ``parity_operands() == "f16"``: the fused message-passing layers and the large projections;
-  same accuracy at twice the MMA rate) -- bf16 tensors in the bf16 mode.
-* ``"cublas"``  -- ``torch.addmm`` / ``torch.mm`` (library GEMM, fp32 SIMT with TF32 off).  Also the
-  route for shapes ``agnn_gemm`` does not take (row strides that are not 16-byte multiples).
-
-There is no CPU path in either case: inputs must be CUDA tensors.
+There is no library GEMM and no CPU path: operands ``agnn_gemm`` cannot read as they are (rows that are not 16-byte
+multiples, mixed operand forms) are first copied into padded buffers (``stats["repacked_gemms"]``; an error under
+``_lib.set_strict(True)``, which bench.py sets -- a hot path must show 0), and CPU tensors raise.
 """
 from __future__ import annotations
 
@@ -21,22 +18,10 @@ import torch
 
 from . import _lib
 
-_BACKEND = os.environ.get("AGNN_GEMM", "tcgen05")
 timer = None      # set to an ops.KernelTimer by bench.py to time every agnn_gemm launch
-# how many contractions went to the library route (torch.mm / addmm) because agnn_gemm does not take their operands:
-# misaligned rows, or a TF32 pair meeting an fp16 pair.  bench.py reports it; a hot path should show 0.
-stats = {"library_gemms": 0}
-
-
-def backend() -> str:
-    return _BACKEND
-
-
-def set_backend(name: str) -> None:
-    global _BACKEND
-    if name not in ("cublas", "tcgen05"):
-        raise ValueError(name)
-    _BACKEND = name
+# how many contractions had to copy their operands into padded buffers first because agnn_gemm does not take them as
+# they are: misaligned rows, or a TF32 pair meeting an fp16 pair.  bench.py reports it; a hot path should show 0.
+stats = {"repacked_gemms": 0}
 
 
 def _need_cuda(t):
@@ -145,6 +130,7 @@ def amax_into(amax: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         return amax
     if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 4 or x.stride(0) % 4 \
             or x.data_ptr() % 16:
+        _lib.library_route("amax of a matrix agnn_amax does not take (width % 4, misaligned rows)")
         return torch.maximum(amax, x.detach().abs().max().float().reshape(1), out=amax)
     stream = torch.cuda.current_stream(x.device).cuda_stream
     _lib.check(_lib.lib().agnn_amax(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), amax.data_ptr(), stream),
@@ -196,9 +182,8 @@ def split(x: torch.Tensor) -> Split:
 
 
 def prepare(x: torch.Tensor) -> Operand:
-    """Pre-split an fp32 operand that several GEMMs will read (no-op for other backends / dtypes)."""
-    if (_BACKEND == "tcgen05" and isinstance(x, torch.Tensor) and x.dtype == torch.float32 and _rows_ok(x)
-            and x.shape[1] % 4 == 0):
+    """Pre-split an fp32 operand that several GEMMs will read (no-op for other dtypes / unaligned rows)."""
+    if isinstance(x, torch.Tensor) and x.dtype == torch.float32 and _rows_ok(x) and x.shape[1] % 4 == 0:
         return split(x)
     return x
 
@@ -206,8 +191,8 @@ def prepare(x: torch.Tensor) -> Operand:
 def prepare_auto(x: torch.Tensor) -> Operand:
     """``prepare`` in the operand form of the current parity mode: the fp16 pair for large matrices when
     ``parity_operands() == "f16"`` (every GEMM that reads it then runs in F16X3), the TF32 pair otherwise."""
-    if (_BACKEND == "tcgen05" and _PARITY_OPERANDS == "f16" and isinstance(x, torch.Tensor) and x.is_cuda
-            and x.shape[0] >= F16_MIN_ROWS and f16_ok(x)):
+    if (_PARITY_OPERANDS == "f16" and isinstance(x, torch.Tensor) and x.is_cuda and x.shape[0] >= F16_MIN_ROWS
+            and f16_ok(x)):
         return split_f16(x)
     return prepare(x)
 
@@ -298,9 +283,8 @@ _plain = plain
 
 def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, k: int, bias, flags: int,
           out: Optional[torch.Tensor], split_k: Optional[int] = None) -> Optional[torch.Tensor]:
-    """agnn_gemm wrapper; returns None if the operands are not eligible (caller falls back)."""
-    if _BACKEND != "tcgen05":
-        return None
+    """agnn_gemm wrapper; returns None if the operands are not eligible as they are (``_repacked`` then copies
+    them into padded buffers)."""
     f16 = isinstance(a, SplitH) or isinstance(b, SplitH)
     oa, ob = _as_operand(a, f16), _as_operand(b, f16)
     if oa is None or ob is None or oa[2] != ob[2]:
@@ -348,18 +332,53 @@ def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, 
     return out
 
 
+def _pad2(t: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """Contiguous zero-padded copy [rows, cols] of a 2-D tensor (elementwise copy kernels, not a GEMM)."""
+    if t.shape[0] == rows and t.shape[1] == cols and t.is_contiguous() and t.data_ptr() % 16 == 0:
+        return t
+    out = torch.zeros((rows, cols), dtype=t.dtype, device=t.device)
+    out[:t.shape[0], :t.shape[1]] = t
+    return out
+
+
+def _repacked(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, k: int, bias, flags: int,
+              out: Optional[torch.Tensor]) -> torch.Tensor:
+    """The same contraction for operands agnn_gemm cannot read in place: plain copies padded to 16-byte rows (zeros
+    do not change the result), the product on the tensor core as usual, the result copied / added into ``out``."""
+    from . import _lib as lib_mod
+    lib_mod.library_route("agnn_gemm operand repack (misaligned rows or mixed operand forms)", counter=stats,
+                          key="repacked_gemms")
+    ap, bp = plain(a), plain(b)
+    if ap.dtype != bp.dtype:
+        ap, bp = ap.float(), bp.float()
+    mult = 8 if ap.dtype == torch.bfloat16 else 4
+    up = lambda v: (v + mult - 1) // mult * mult
+    mp, np_, kp = up(m), up(n), up(k)
+    ap = _pad2(ap, *((kp, mp) if a_layout == _lib.MN_MAJOR else (m, kp)))
+    bp = _pad2(bp, *((kp, np_) if b_layout == _lib.MN_MAJOR else (n, kp)))
+    m2 = mp if a_layout == _lib.MN_MAJOR else m
+    n2 = np_ if b_layout == _lib.MN_MAJOR else n
+    if bias is not None and n2 != n:
+        bias = torch.nn.functional.pad(bias.float(), (0, n2 - n))
+    y = _gemm(ap, a_layout, bp, b_layout, m2, n2, kp, bias, flags & ~_lib.GEMM_ACCUMULATE, None)
+    if y is None:
+        raise _lib.AgnnError("agnn_gemm refused padded operands")
+    y = y[:m, :n]
+    if out is None:
+        return y
+    if flags & _lib.GEMM_ACCUMULATE:
+        return out.add_(y.to(out.dtype))
+    return out.copy_(y)
+
+
 def linear(x: Operand, weight: Operand, bias=None, relu: bool = False):
     """``x @ weight.T + bias`` (optionally ReLU'd), ``weight`` [out, in]."""
     _need_cuda(x if isinstance(x, torch.Tensor) else x.hi)
     m, k = x.shape
     n = weight.shape[0]
-    y = _gemm(x, _lib.K_MAJOR, weight, _lib.K_MAJOR, m, n, k, bias, _lib.GEMM_RELU if relu else 0, None)
-    if y is not None:
-        return y
-    stats["library_gemms"] += 1
-    xp, wp = _plain(x), _plain(weight)
-    y = torch.addmm(bias, xp, wp.t()) if bias is not None else torch.mm(xp, wp.t())
-    return y.relu_() if relu else y
+    flags = _lib.GEMM_RELU if relu else 0
+    y = _gemm(x, _lib.K_MAJOR, weight, _lib.K_MAJOR, m, n, k, bias, flags, None)
+    return y if y is not None else _repacked(x, _lib.K_MAJOR, weight, _lib.K_MAJOR, m, n, k, bias, flags, None)
 
 
 def mm(a: Operand, b: Operand, out=None, accumulate: bool = False):
@@ -367,16 +386,9 @@ def mm(a: Operand, b: Operand, out=None, accumulate: bool = False):
     _need_cuda(a if isinstance(a, torch.Tensor) else a.hi)
     m, k = a.shape
     n = b.shape[1]
-    y = _gemm(a, _lib.K_MAJOR, b, _lib.MN_MAJOR, m, n, k, None, _lib.GEMM_ACCUMULATE if accumulate else 0, out)
-    if y is not None:
-        return y
-    stats["library_gemms"] += 1
-    ap, bp = _plain(a), _plain(b)
-    if out is None:
-        return torch.mm(ap, bp)
-    if accumulate:
-        return out.addmm_(ap, bp)
-    return torch.mm(ap, bp, out=out)
+    flags = _lib.GEMM_ACCUMULATE if accumulate else 0
+    y = _gemm(a, _lib.K_MAJOR, b, _lib.MN_MAJOR, m, n, k, None, flags, out)
+    return y if y is not None else _repacked(a, _lib.K_MAJOR, b, _lib.MN_MAJOR, m, n, k, None, flags, out)
 
 
 def mm_tn(a: Operand, b: Operand):
@@ -385,10 +397,7 @@ def mm_tn(a: Operand, b: Operand):
     r, m = a.shape
     n = b.shape[1]
     y = _gemm(a, _lib.MN_MAJOR, b, _lib.MN_MAJOR, m, n, r, None, 0, None)
-    if y is not None:
-        return y
-    stats["library_gemms"] += 1
-    return torch.mm(_plain(a).t(), _plain(b))
+    return y if y is not None else _repacked(a, _lib.MN_MAJOR, b, _lib.MN_MAJOR, m, n, r, None, 0, None)
 
 
 def relu_backward(grad, out):

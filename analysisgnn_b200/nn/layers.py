@@ -29,6 +29,9 @@ class GRU(nn.GRU):
     def forward(self, x, hx=None):
         if (hx is not None or not isinstance(x, torch.Tensor) or not self.batch_first or self.proj_size != 0
                 or not ops.gru_supported(x, self.hidden_size)):
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                from .. import _lib
+                _lib.library_route("GRU outside agnn_gru's shapes (hidden size, given h0, packed input): cuDNN")
             return super().forward(x, hx)
         n_dir = 2 if self.bidirectional else 1
         h_n = []

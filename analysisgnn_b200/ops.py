@@ -268,8 +268,8 @@ def segment_mean_self(src, self_add, csr: TypedCSR):
 
 def _operand_buffers(rows: int, cols: int, like: torch.Tensor):
     """(hi, lo) buffers for a GEMM operand the gather kernel writes: a TF32 pair on the tcgen05 fp32 route
-    (lo is None otherwise, and hi then holds the plain values)."""
-    if linalg.backend() == "tcgen05" and like.dtype == torch.float32 and cols % 4 == 0:
+    (lo is None for other dtypes / widths, and hi then holds the plain values)."""
+    if like.dtype == torch.float32 and cols % 4 == 0:
         buf = torch.empty((2, rows, cols), dtype=like.dtype, device=like.device)
         return buf[0], buf[1]
     return torch.empty((rows, cols), dtype=like.dtype, device=like.device), None
@@ -297,7 +297,7 @@ class _IntreeSageLayer(torch.autograd.Function):
         r = csr.n_rel
         # fp16 operand form: |S_r| <= amax(x) + amax(H), inside the 4x headroom of a scale taken from
         # max(amax(x), amax(H))
-        f16 = (linalg.parity_operands() == "f16" and linalg.backend() == "tcgen05" and x.dtype == torch.float32
+        f16 = (linalg.parity_operands() == "f16" and x.dtype == torch.float32
                and f % 8 == 0 and n > 0 and linalg.f16_ok(wn_cat) and linalg.f16_ok(wc))
         xs = linalg.split_f16(x) if f16 else x
         h = linalg.linear(xs, wn_cat, bn_cat)                                    # [N, R*F]
@@ -380,7 +380,7 @@ class _HeteroSageLayer(torch.autograd.Function):
         outs, saved = [], []
         # F16X3 operands: every aggregated row is a copy or a mean of input rows, so the amax over the layer's inputs
         # bounds every operand the gather writes -- one scalar for all destination types
-        f16 = (linalg.parity_operands() == "f16" and linalg.backend() == "tcgen05"
+        f16 = (linalg.parity_operands() == "f16"
                and all(v.dtype == torch.float32 and v.shape[1] % 8 == 0 for v in xs.values()))
         x_amax = None
         if f16:
@@ -702,6 +702,7 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     """Column sums of a 2-D fp32 matrix (bias gradients): per-block partials + a fixed-order final sum."""
     if (x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 4 or x.shape[1] > 1024
             or x.stride(0) % 4 or x.data_ptr() % 16 or x.shape[0] == 0):
+        _lib.library_route("colsum of a matrix the row kernels do not take (width % 4, > 1024 columns, misaligned)")
         return x.sum(0)
     lib = _lib.lib()
     rows, cols = x.shape
@@ -720,7 +721,7 @@ def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_
     Returns ``(operand, colsum or None)``.  ``f16``: the operand is the fp16 pair of the F16X3 mode (one extra
     pass measures the amax of ``g`` first)."""
     rows, cols = g.shape
-    ok = (linalg.backend() == "tcgen05" and g.dtype == torch.float32 and g.is_cuda and rows > 0 and cols % 4 == 0
+    ok = (g.dtype == torch.float32 and g.is_cuda and rows > 0 and cols % 4 == 0
           and cols <= 1024 and g.stride(1) == 1 and g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0)
     if ok and relu_out is not None:
         ok = (relu_out.dtype == torch.float32 and relu_out.shape == g.shape and relu_out.stride(1) == 1
@@ -768,7 +769,7 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        f16 = (linalg.parity_operands() == "f16" and linalg.backend() == "tcgen05" and x.shape[0] >= _Linear.F16_MIN_ROWS
+        f16 = (linalg.parity_operands() == "f16" and x.shape[0] >= _Linear.F16_MIN_ROWS
                and weight.shape[0] * weight.shape[1] >= _Linear.F16_MIN_WEIGHT and linalg.f16_ok(x)
                and linalg.f16_ok(weight))
         xs = linalg.split_f16(x) if f16 else linalg.prepare(x)
@@ -786,7 +787,7 @@ class _Linear(torch.autograd.Function):
         n = g.shape[1]
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         mult = 8 if f16 else 4
-        if g.dtype == torch.float32 and n % mult and linalg.backend() == "tcgen05":
+        if g.dtype == torch.float32 and n % mult:
             # e.g. the 185- and 50-class heads: zero columns / weight rows up to the 16-byte row rule of TMA
             pad = mult - n % mult
             g = torch.nn.functional.pad(g, (0, pad))
@@ -809,7 +810,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     x2 = x.reshape(-1, x.shape[-1])
     k = x2.shape[1]
     mult = 8 if linalg.parity_operands() == "f16" else 4      # 16-byte rows in the operand's element type
-    if x2.dtype == torch.float32 and k % mult and linalg.backend() == "tcgen05":
+    if x2.dtype == torch.float32 and k % mult:
         pad = mult - k % mult
         x2 = torch.nn.functional.pad(x2, (0, pad))
         weight = torch.nn.functional.pad(weight, (0, pad))
@@ -938,6 +939,8 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
         raise _lib.AgnnError("analysisgnn_b200 has no CPU path: tensors must live on a CUDA device")
     cols = x.shape[-1]
     if x.dtype != torch.float32 or cols % 4 or cols > 1024 or gamma is None or beta is None or x.numel() == 0:
+        if x.numel():
+            _lib.library_route("layer_norm outside the row kernel's shapes (fp32, width % 4 == 0, <= 1024)")
         return torch.nn.functional.layer_norm(x, (cols,), gamma, beta, eps)
     x2 = x.reshape(-1, cols)
     if not x2.is_contiguous():
@@ -978,6 +981,8 @@ def l2norm_relu(h, relu_first: bool):
     if (h.is_cuda and h.dtype == torch.float32 and h.dim() == 2 and h.shape[1] % 4 == 0 and h.shape[1] <= 1024
             and h.shape[0] > 0):
         return _L2NormRelu.apply(h.contiguous(), bool(relu_first))
+    if h.numel():
+        _lib.library_route("l2norm_relu outside the row kernel's shapes (fp32, width % 4 == 0, <= 1024)")
     if relu_first:
         return torch.nn.functional.normalize(torch.relu(h), p=2.0, dim=-1)
     return torch.relu(torch.nn.functional.normalize(h, p=2.0, dim=-1))

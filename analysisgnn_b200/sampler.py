@@ -247,9 +247,8 @@ class ScoreGraphLoader:
         epoch, so shuffling differs from epoch to epoch and is the same on every rank."""
         epoch = getattr(self, "_epoch", 0)
         self._epoch = epoch + 1
-        for index in range(len(self)):
-            if self.batch_ids(epoch, index):               # a rank may have no share of a short last batch
-                yield HeteroBatch(self.batch(epoch, index))
+        for index in range(len(self)):                     # every rank yields len(self) batches (see batch_ids)
+            yield HeteroBatch(self.batch(epoch, index))
 
     def order(self, epoch: int) -> List[int]:
         ids = list(range(self.corpus.n_scores))
@@ -260,7 +259,13 @@ class ScoreGraphLoader:
     def batch_ids(self, epoch: int, index: int) -> List[int]:
         """Scores of global batch ``index`` that this rank takes (data parallel: positions ``g mod W == rank`` of the
         batch, so the ranks' shares are disjoint and together are the global batch).  Host arithmetic only."""
-        ids = self.order(epoch)[index * self.batch_size:(index + 1) * self.batch_size]
+        order = self.order(epoch)
+        ids = order[index * self.batch_size:(index + 1) * self.batch_size]
+        if 0 < len(ids) < self.world_size:
+            # a short last batch with fewer scores than ranks: wrap around the epoch order (DistributedSampler's
+            # padding) so that EVERY rank has a share -- ranks must run the same number of steps, or the others
+            # block in the gradient allreduce
+            ids = ids + [order[i % len(order)] for i in range(self.world_size - len(ids))]
         return ids[self.rank::self.world_size]
 
     def batch(self, epoch: int, index: int):

@@ -134,6 +134,27 @@ class DataParallelTrainer:
             self.n_partials, self.partials = 0, None
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=first.device)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=first.device)   # device-side step number
+        # the learning rate lives on the device: the optimizer launch reads it, so the host's scheduler
+        # (``set_lr``; the reference's warm-up + cosine schedule, analysis.py:1380-1400) keeps working when the launch
+        # is replayed from a CUDA graph
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=first.device)
+        if self.world_size > 1:
+            self.broadcast_state()
+
+    def set_lr(self, lr: float) -> None:
+        """Write a new learning rate (host scheduler) into the device scalar the optimizer kernel reads."""
+        self.lr = float(lr)
+        self.lr_dev.fill_(self.lr)
+
+    def broadcast_state(self, src: int = 0) -> None:
+        """What DDP does when it wraps a module (train_analysisgnn.py:138-145): every rank starts from rank ``src``'s
+        parameters AND buffers (BatchNorm running statistics of MetricalConvLayer, gnn.py:498-531).  Buffers are
+        rank-local afterwards, as under Lightning's DDP without SyncBatchNorm (``broadcast_buffers`` re-syncs them
+        from rank 0 before every forward there; call this again to do the same)."""
+        import torch.distributed as dist
+        with torch.no_grad():
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=src, group=self.group)
 
     def zero_grad(self):
         if self.collect_grads:
@@ -168,7 +189,7 @@ class DataParallelTrainer:
         _lib.check(lib.agnn_adamw_clip_step(
             a.table.data_ptr(), a.n_chunks, a.grad.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(),
             self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 0, self.step_dev.data_ptr(),
-            1.0 / self.world_size, self.max_norm if self.max_norm else 0.0, self.partials.data_ptr(),
+            self.lr_dev.data_ptr(), 1.0 / self.world_size, self.max_norm if self.max_norm else 0.0, self.partials.data_ptr(),
             self.n_partials, self.grad_norm.data_ptr(), stream), "agnn_adamw_clip_step")
         _lib.count_launches(2)
         from . import linalg
@@ -186,25 +207,38 @@ class GraphedStep:
     next batch into them with ``copy_`` -- shapes are fixed by the capture, so batches are padded to
     the captured capacity with relation id -1 edges and ``ignore_index`` labels) and must not read
     device data on the host.  Host-side layouts that need such a read (sequence lengths) are taken
-    from the warm-up steps, which run eagerly before the capture."""
+    from the warm-up steps, which run eagerly before the capture.
+
+    Per-batch device structures are part of the captured work: before every warm-up call and before the capture this
+    class itself drops the CSR cache (``graph.clear_cache``) and the per-step weight splits / amax scalars
+    (``linalg.begin_step``), so the ``agnn_csr_build`` launches and the scalar resets are IN the graph and every replay
+    rebuilds them from whatever the static inputs hold then -- ``fn`` does not have to remember to.  If the optimizer
+    launch is captured too, the learning rate it uses is the trainer's device scalar (``DataParallelTrainer.set_lr``),
+    not a constant baked into the graph."""
 
     def __init__(self, fn, inputs, warmup: int = 3):
-        self.fn, self.inputs = fn, inputs
+        from . import graph as _graph, linalg as _linalg
+
+        def step(x):
+            _graph.clear_cache()
+            _linalg.begin_step()
+            return fn(x)
+
+        self.fn, self.inputs = step, inputs
         dev = torch.cuda.current_device()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                fn(inputs)
+                step(inputs)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        from . import graph as _graph
         before = _lib.launches()
         self.graph = torch.cuda.CUDAGraph()
         _graph.freeze_host_layouts(True)
         try:
             with torch.cuda.graph(self.graph):
-                self.loss = fn(inputs)
+                self.loss = step(inputs)
         finally:
             _graph.freeze_host_layouts(False)
         self.launches_per_replay = _lib.launches() - before

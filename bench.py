@@ -498,7 +498,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                     "h2d": "pinned host -> one of two device staging sets on a copy stream, overlapped with the "
                            "previous step's compute; K copies for K timed steps, the first one exposed"},
-            "gpu_launches": launches, "library_gemm_fallbacks": _lin.stats["library_gemms"],
+            "gpu_launches": launches, "library_routes": dict(_lib.library_routes),
             "host_enqueue_ms_per_step": enqueue_ms,
             "execution": ("CSR build + fwd + bwd replayed as one CUDA graph per step, then allreduce + fused "
                           "clip/AdamW launched eagerly" if use_graph else "eager launches"),

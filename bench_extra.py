@@ -23,7 +23,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from analysisgnn_b200 import graph, ops, scoregraph, synth  # noqa: E402
+from analysisgnn_b200 import _lib, graph, ops, scoregraph, synth  # noqa: E402
 from analysisgnn_b200 import nn as ann  # noqa: E402
 
 DEV = torch.device("cuda:0")
@@ -290,7 +290,7 @@ def main():
         from analysisgnn_b200 import linalg
         r = {"parity_operands": linalg.parity_operands(), "metrical_gnn_4L512": metrical_gnn_step(),
              "hgt_encoder": hgt_encoder_step()}
-        r["library_gemms"] = linalg.stats["library_gemms"]
+        r["library_routes"] = dict(_lib.library_routes)
         print("encoders", r)
         with open(args.out, "w") as fh:
             json.dump(r, fh, indent=1)

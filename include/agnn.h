@@ -239,12 +239,14 @@ int agnn_sumsq_blocks(int64_t n);
  * step_counter (optional, device int) is incremented by one -- the device-side step number that makes
  * the optimizer step replayable inside a CUDA graph. */
 int agnn_sumsq_partials(const float* grad, int64_t n, float* partials, int* step_counter, agnn_stream_t stream);
-/* chunks: DEVICE array [n_chunks]; the step number (from 1) is *step_dev if step_dev is given, else `step`;
+/* chunks: DEVICE array [n_chunks]; the step number (from 1) is *step_dev if step_dev is given, else `step`; the
+ * learning rate is *lr_dev if lr_dev is given (a device scalar the host's LR scheduler writes: the reference's
+ * warm-up + cosine schedule, analysisgnn/models/analysis.py:1380-1400, keeps working under CUDA-graph replay), else `lr`;
  * max_norm <= 0 disables clipping; norm_out (optional, device) receives the norm of the averaged gradient. */
 int agnn_adamw_clip_step(const agnn_param_chunk_t* chunks /* device */, int n_chunks, const float* grad, float* m,
                          float* v, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                         const int* step_dev, float grad_scale, float max_norm, const float* partials, int n_partials,
-                         float* norm_out, agnn_stream_t stream);
+                         const int* step_dev, const float* lr_dev, float grad_scale, float max_norm,
+                         const float* partials, int n_partials, float* norm_out, agnn_stream_t stream);
 
 /* ------------------------------------------------------------ dense projections
  * Replaces the nn.Linear calls of the path and the GEMMs of their backward:

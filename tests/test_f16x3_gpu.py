@@ -24,11 +24,9 @@ SHAPES = [(128, 128, 64), (256, 256, 256), (300, 200, 104), (1000, 256, 2560), (
 @pytest.fixture(params=["f16", "tf32"])
 def f16_mode(request):
     """Both operand forms of the parity mode, whichever is the library default."""
-    old_b, old_p = linalg.backend(), linalg.parity_operands()
-    linalg.set_backend("tcgen05")
+    old_p = linalg.parity_operands()
     linalg.set_parity_operands(request.param)
     yield request.param
-    linalg.set_backend(old_b)
     linalg.set_parity_operands(old_p)
 
 

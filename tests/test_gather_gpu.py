@@ -217,3 +217,41 @@ def test_heavy_rows_are_split_across_warps(mean):
     assert_close(s2.grad, s1.grad, FP32_REL, "d src")
     again = ops.segment_mean_self(s2, base.to(DEV), csr) if mean else ops.segment_sum(s2, csr)
     assert torch.equal(got, again)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mean", [False, True])
+def test_two_heavy_relations_on_one_row_are_summed_in_order(dtype, mean):
+    """COMBINE_SUM with hub rows in SEVERAL relations (the backward of a hub source node, ops._HeteroSageLayer): the
+    row's heavy relations are added by ONE warp in relation order -- no atomics, no lost update, bit-identical from
+    run to run -- and agree with the plain formulation."""
+    rng = np.random.default_rng(11)
+    n_rows, n_cols, f = 200, 3000, 128
+    rows = [np.concatenate([np.full(9000, 5), np.full(5000, 9), rng.integers(0, n_rows, 3000)]),     # rel 0: 5, 9
+            np.concatenate([np.full(4096, 5), rng.integers(0, n_rows, 2000)]),                       # rel 1: 5
+            np.concatenate([np.full(6000, 9), np.full(4500, 5), rng.integers(0, n_rows, 1000)]),     # rel 2: 9, 5
+            rng.integers(0, n_rows, 1500)]                                                           # rel 3: light
+    eis = []
+    for r in rows:
+        rng.shuffle(r)
+        eis.append(torch.as_tensor(np.stack((r, rng.integers(0, n_cols, len(r)))), dtype=torch.long))
+    torch.manual_seed(2)
+    srcs = [torch.randn(n_cols, f) for _ in rows]
+    base = torch.randn(n_rows, f)
+    want = base.to(dtype).double()
+    for ei, s in zip(eis, srcs):
+        sd = s.to(dtype).double()
+        part = torch.zeros(n_rows, f, dtype=torch.float64).index_add_(0, ei[0], sd[ei[1]])
+        if mean:
+            part /= torch.bincount(ei[0], minlength=n_rows).clamp(min=1).double().unsqueeze(1)
+        want += part
+    csrs = [graph.TypedCSR(ei.to(DEV), None, n_rows, n_cols=n_cols) for ei in eis]
+    assert [int(c.fwd.n_heavy[0]) for c in csrs] == [2, 1, 2, 0]
+    rels = [ops.rel_of(c.fwd, 0, s.to(DEV, dtype), n_edges=ei.shape[1]) for c, s, ei in zip(csrs, srcs, eis)]
+    outs = []
+    for _ in range(3):
+        out = torch.empty((n_rows, f), dtype=dtype, device=DEV)
+        ops.gather_reduce(rels, out, f, mean=mean, concat=False, self_add=base.to(DEV, dtype))
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert_close(outs[0].double(), want, 2 * FP32_REL if dtype == torch.float32 else BF16_REL, "sum over relations")

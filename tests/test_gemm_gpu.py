@@ -20,14 +20,6 @@ def _ops(m, n, k, seed=0):
     return torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) * 0.1, torch.randn(n, generator=g)
 
 
-@pytest.fixture(autouse=True)
-def _backend():
-    old = linalg.backend()
-    linalg.set_backend("tcgen05")
-    yield
-    linalg.set_backend(old)
-
-
 def _check_fp32(got, want64, cpu32):
     err = rel_err(got, want64)
     floor = rel_err(cpu32, want64)

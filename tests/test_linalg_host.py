@@ -76,3 +76,24 @@ def test_split_cache_is_bounded_without_begin_step():
     assert ("k", linalg._SPLIT_CACHE_MAX_ENTRIES + 9) in linalg._split_cache and ("k", 0) not in linalg._split_cache
     linalg.begin_step()
     assert not linalg._split_cache
+
+
+def test_there_is_no_backend_switch_and_strict_mode_raises_on_library_routes():
+    """north_star: no multi-backend dispatch.  The GEMM has one implementation; routes off the hand-written kernels
+    are counted and, in strict mode (bench.py, full-size parity tests), refused."""
+    from analysisgnn_b200 import _lib
+    assert not hasattr(linalg, "set_backend") and not hasattr(linalg, "backend")
+    import inspect
+    src = inspect.getsource(linalg)
+    assert "torch.mm(" not in src and "addmm" not in src
+    old = _lib.strict()
+    try:
+        _lib.set_strict(False)
+        before = _lib.library_routes.get("probe", 0)
+        _lib.library_route("probe")
+        assert _lib.library_routes["probe"] == before + 1
+        _lib.set_strict(True)
+        with pytest.raises(_lib.AgnnError):
+            _lib.library_route("probe")
+    finally:
+        _lib.set_strict(old)

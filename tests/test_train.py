@@ -88,9 +88,17 @@ def _worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    net = _toy(0)                                            # same weights on every rank
-    tr = DataParallelTrainer(net)
+    net = _toy(rank)                                         # every rank seeds differently ...
+    net.add_module("bn", nn.BatchNorm1d(3))
+    with torch.no_grad():
+        net.bn.running_mean.fill_(float(rank + 1))
+    tr = DataParallelTrainer(net)                            # ... and starts from rank 0's parameters and buffers
     assert tr.world_size == world
+    ref = _toy(0)
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert torch.equal(p, q)
+    assert float(net.bn.running_mean[0]) == 1.0
+    del net.bn
     torch.manual_seed(100)
     data = torch.randn(12, 7)
     tr.zero_grad()
@@ -111,7 +119,8 @@ def test_gloo_world2_allreduce_equals_full_batch_gradient():
     tr = DataParallelTrainer(net, world_size=1)
     torch.manual_seed(100)
     net(torch.randn(12, 7)).sum().backward()
-    assert_close(g0, tr.arena.grad, 1e-6, "sum of shard gradients")
+    n = tr.arena.numel                                       # (the workers' arenas end with the BatchNorm probe)
+    assert_close(g0[:n], tr.arena.grad, 1e-6, "sum of shard gradients")
 
 
 @pytest.mark.gpu
@@ -209,9 +218,7 @@ def test_graphed_step_replays_the_eager_step():
         return net, DataParallelTrainer(net, lr=1e-3, weight_decay=1e-2, max_norm=1.0, world_size=1, collect_grads=True)
 
     def step_fn(net, tr):
-        def fwd_bwd(t):
-            linalg.begin_step()
-            graph.clear_cache()
+        def fwd_bwd(t):                                      # no clear_cache / begin_step here: GraphedStep's job
             d = bench.unflatten(t, b)
             tr.zero_grad()
             logits = net(d["pitch_spelling"], d["key_signature"], d["x_dict"], d["edge_index_dict"], d["batch_dict"],
@@ -243,6 +250,15 @@ def test_graphed_step_replays_the_eager_step():
     for (n, p), q in zip(net_e.named_parameters(), net_g.parameters()):
         assert torch.equal(p, q), n
     assert graphed.launches_per_replay > 50
+    # the learning rate is a device scalar: a scheduler's new value reaches the (replayable) optimizer launch
+    tr_g.set_lr(0.0)
+    before = [p.detach().clone() for p in net_g.parameters()]
+    graphed()
+    tr_g.weight_decay, keep = 0.0, tr_g.weight_decay
+    tr_g.step()
+    tr_g.weight_decay = keep
+    for p, q in zip(net_g.parameters(), before):
+        assert torch.equal(p, q)
 
 
 def test_loader_shards_a_global_batch_across_ranks():
@@ -267,9 +283,17 @@ def test_loader_shards_a_global_batch_across_ranks():
                 parts = [sampler.ScoreGraphLoader(corpus, 4, 8, seed=11, rank=r, world_size=world).batch_ids(epoch, index)
                          for r in range(world)]
                 flat = [g for p in parts for g in p]
-                assert sorted(flat) == sorted(whole) and len(set(flat)) == len(flat)
+                if len(whole) >= world:
+                    assert sorted(flat) == sorted(whole) and len(set(flat)) == len(flat)
+                else:       # short last batch: padded by wrapping around the epoch order, every rank gets one score
+                    assert set(whole) <= set(flat) and len(flat) == world and all(len(p) == 1 for p in parts)
+                    assert sorted(set(flat) - set(whole)) == sorted(single.order(epoch)[:world - len(whole)])
                 assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+                assert all(parts)                            # same number of steps on every rank (no allreduce hang)
         assert sorted(seen) == list(range(n_scores))
+    for world in (4, 8):                                     # corpus size not divisible by batch_size * world
+        lens = {len(sampler.ScoreGraphLoader(corpus, 4, 8, seed=11, rank=r, world_size=world)) for r in range(world)}
+        assert lens == {5}
     assert single.order(0) != single.order(1)
     assert single.order(0) == sampler.ScoreGraphLoader(corpus, 4, 8, seed=11).order(0)
     assert single.order(0) != sampler.ScoreGraphLoader(corpus, 4, 8, seed=12).order(0)

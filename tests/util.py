@@ -103,13 +103,23 @@ def feeds_relu(name, module):
                                 or name.startswith("project_metrical."))
 
 
+MAX_SKIPPED_SEEDS = 2
+
+
 def first_seed_with_equal_patterns(run, seeds=(0, 1, 2, 3, 4, 5)):
-    """``run(seed)`` -> (mismatches, payload).  Returns the payload of the first seed on which
-    the CPU oracle and the CUDA path agree on every activation sign; fails if none does."""
+    """``run(seed)`` -> (mismatches, payload).  Returns the payload of the first seed on which the CPU oracle and the
+    CUDA path agree on every activation sign (``run`` asserts the forward outputs on EVERY seed it sees, and the
+    gradients on that one).  Seeds skipped because a |z| ~ 1e-7 unit landed on the other side are counted, printed,
+    and more than ``MAX_SKIPPED_SEEDS`` of them fail the test: a real bug that flips activations on most seeds must
+    not pass because one seed happens to agree.  (The full-size tests, tests/test_fullsize_gpu.py, do not skip at
+    all: they evaluate the oracle's gradient with the CUDA side's sign choice at the flipped units.)"""
     seen = []
-    for seed in seeds:
+    for seed in seeds[:MAX_SKIPPED_SEEDS + 1]:
         mism, payload = run(seed)
         seen.append(mism)
         if mism == 0:
+            print(f"[relu patterns] gradients asserted on seed {seed}; skipped {len(seen) - 1} seed(s) with flipped "
+                  f"units: {seen[:-1]}")
             return payload
-    raise AssertionError(f"activation patterns differed on every seed: {seen}")
+    raise AssertionError(f"activation patterns differed on more than {MAX_SKIPPED_SEEDS} seeds in a row "
+                         f"(flipped units per seed: {seen})")
