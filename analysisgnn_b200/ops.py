@@ -699,18 +699,21 @@ def _stream(t):
 
 
 def colsum(x: torch.Tensor) -> torch.Tensor:
-    """Column sums of a 2-D fp32 matrix (bias gradients): per-block partials + a fixed-order final sum."""
-    if (x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 4 or x.shape[1] > 1024
-            or x.stride(0) % 4 or x.data_ptr() % 16 or x.shape[0] == 0):
-        _lib.library_route("colsum of a matrix the row kernels do not take (width % 4, > 1024 columns, misaligned)")
+    """Column sums of a 2-D fp32 matrix (bias gradients): per-block partials + a fixed-order final sum.  Matrices wider
+    than the row kernels' 1024 columns (HGT's folded 4864-column projection) are summed in 1024-column slices."""
+    if (x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 4 or x.stride(0) % 4
+            or x.data_ptr() % 16 or x.shape[0] == 0):
+        _lib.library_route("colsum of a matrix the row kernels do not take (width % 4, misaligned rows)")
         return x.sum(0)
     lib = _lib.lib()
     rows, cols = x.shape
-    part = torch.empty((lib.agnn_row_blocks(rows), cols), dtype=torch.float32, device=x.device)
     out = torch.empty(cols, dtype=torch.float32, device=x.device)
-    _lib.check(lib.agnn_colsum_partials(x.data_ptr(), x.stride(0), part.data_ptr(), out.data_ptr(), rows, cols,
-                                        _stream(x)), "agnn_colsum_partials")
-    _lib.count_launches(2)
+    part = torch.empty((lib.agnn_row_blocks(rows), min(cols, 1024)), dtype=torch.float32, device=x.device)
+    for c0 in range(0, cols, 1024):
+        w = min(1024, cols - c0)
+        _lib.check(lib.agnn_colsum_partials(x.data_ptr() + 4 * c0, x.stride(0), part.data_ptr(),
+                                            out.data_ptr() + 4 * c0, rows, w, _stream(x)), "agnn_colsum_partials")
+        _lib.count_launches(2)
     return out
 
 

@@ -47,6 +47,20 @@ def peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_of(kernel):
+    """{"traffic": DRAM bytes per launch or None, "traffic_source": ...} from profiles/traffic.json."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh).get(kernel)
+    except (OSError, ValueError):
+        t = None
+    if not t:
+        return {"traffic": None, "traffic_source": "no ncu --set full capture of this kernel committed for this round"}
+    return {"traffic": t["dram_bytes"], "traffic_source": t["source"],
+            "traffic_algorithmic_bytes_same_launch": t.get("algorithmic_bytes")}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -254,6 +268,8 @@ def run_ours(args):
 
     from analysisgnn_b200 import linalg as _lin
     _lin.set_parity_operands(args.operands)
+    # the measured path must stay on the hand-written kernels: an operand repack or a library kernel raises
+    _lib.set_strict(True)
 
     def fwd_bwd(tensors):
         _lin.begin_step()                          # weight splits are per step (a captured step re-splits on replay)
@@ -456,14 +472,10 @@ def run_ours(args):
             "mma_achieved": mm_tflops * (3 if dtype == torch.float32 else 1),
             "mma_frac": mm_tflops * (3 if dtype == torch.float32 else 1) / (mma_peak if dtype == torch.float32
                                                                               else bf16_peak),
-            # DRAM bytes of the largest launch (50 000 x 256 x 2560) from the committed ncu --set full captures:
-            # fp16 pairs 524 MB read + 45 MB written against 0.57 GB of operand + result bytes; TF32 pairs 1.0545 GB +
-            # 46 MB against 1.08 GB -- nothing is re-read in either form
-            "traffic": 5.690e8 if f16_ops else 1.1005e9,
-            "traffic_source": ("profiles/r1_w_gemm_f16_fwd2560_full_raw.csv (largest launch; "
-                               "sm__pipe_tensor_cycles_active 70.6 %)") if f16_ops else
-                              ("profiles/r1_t_gemm_fwd2560_full_raw.csv (largest launch; "
-                               "sm__pipe_tensor_cycles_active 72 %)"),
+            # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch from the ncu --set full capture of THIS
+            # round's kernel (profiles/traffic.json, written by tools/ncu_traffic.py from the committed raw page);
+            # null when no capture of the current kernel is committed
+            **traffic_of("gemm_f16" if f16_ops else "gemm_tf32"),
             "peak_source": peak_src + (": bf16 burst (f16 MMA rate)" if f16_ops else ": bf16 burst / 2 (TF32 rate)"),
             "launches": mm["launches"],
             "algorithmic_flops_per_step": mm["bytes"] / max(args.steps, 1),
@@ -476,9 +488,7 @@ def run_ours(args):
         roofline_gather = {
             "bound": "hbm", "kernel": "agnn gather_reduce_kernel (all launches of the step)",
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            # DRAM bytes of the largest launch from the ncu capture: 70 MB read + 966 MB written against 1.62 GB
-            # algorithmic (the 51 MB source matrix and the column ids stay in the 126 MB L2)
-            "traffic": 1.036e9, "traffic_source": "profiles/r1_i_gemm_gather_full_raw.csv (largest launch)",
+            **traffic_of("gather_f16" if f16_ops else "gather_tf32"),
             "peak_source": peak_src, "launches": g["launches"],
             "algorithmic_bytes_per_step": g["bytes"] / max(args.steps, 1),
             "kernel_ms_per_step": g["ms"] / max(args.steps, 1),
@@ -487,6 +497,26 @@ def run_ours(args):
         dominant_is_gemm = mm["ms"] >= g["ms"]
         cpu = cpu_arm(steps=2, warmup=1, budget_s=20.0, max_graphs=20) if not args.skip_cpu else \
             {"value": None, "unit": "nodes/s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped (--skip-cpu)"}
+    # ---- the other BASELINE configs, as sub-objects of the same line (bench_configs.py); collective ones on all ranks
+    extras = {}
+    if not args.no_extras:
+        import bench_configs as bc
+        _lib.set_strict(False)                     # the sub-configs report their library routes instead of refusing them
+        if use_graph:
+            del g_resident, g_e2e
+        torch.cuda.empty_cache()
+        ctx = bc.Ctx(dev, world, rank, peaks()[0])
+        extras["config4_dp"] = bc.guarded(bc.config4, ctx)
+        if world > 1:
+            extras["config1_strong"] = bc.guarded(bc.config1_strong, ctx, CFG, TASKS)
+        elif rank == 0:
+            extras["config1_strong"] = {"scaling": "strong", "n_gpus": 1, "ms_per_step": ms / args.steps,
+                                        "nodes_per_s": n_nodes * args.steps / (ms * 1e-3),
+                                        "workload": "= the main line at one GPU"}
+            extras["config3_hgt"] = bc.guarded(bc.config3, ctx, CFG, TASKS)
+            extras["config5_inference"] = bc.guarded(bc.config5, ctx)
+            extras["library_baseline"] = bc.guarded(bc.library_baseline, ctx, CFG, TASKS)
+    if rank == 0:
         value = world * n_nodes * args.steps / (ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
@@ -509,6 +539,7 @@ def run_ours(args):
             "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "clocks": clocks, "wall_s": wall, "loss": final_loss,
         }
+        line.update(extras)
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
@@ -526,6 +557,9 @@ def main():
                          "per-tensor power-of-two scales (same accuracy, twice the MMA rate)")
     ap.add_argument("--skip-cpu", action="store_true", help="leave out the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="main workload only: leave out the config 3 / 4 / 5, strong-scaling and library-baseline "
+                         "sub-objects (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,9 +12,10 @@ evaluated with the CUDA side's choice of subgradient at exactly those units (``o
 backward, (3) REQUIRES that the signs differ on at most 1e-6 of the units and only where |z| <= 1e-5 max|z| -- i.e.
 that every difference is a rounding-level tie, not a wrong activation -- and (4) compares all gradients.
 
-Tolerances (tensor-scale relative error, max|a-b| / max|b|, tests/util.py) are stated at each assertion.  north_star
-asks 1e-5; the multiples used here are set by what fp32 itself delivers through this depth: the same oracle run in
-fp64 is the yardstick, and the CUDA path must be no further from fp64 than 3x the CPU fp32 oracle is (floor 1e-5).
+Tolerances (tensor-scale relative error, max|a-b| / max|b|, tests/util.py) are stated at each assertion: north_star's
+1e-5 as it stands for configs 1 and 2 (forward, loss and every gradient); config 3 adds a stated multiple for the
+HGT k_rel / p_rel gradients, which are ill-conditioned in fp32 itself -- there the same oracle run in fp64 is the
+yardstick: the CUDA path must be no further from fp64 than 3x the CPU fp32 oracle is (floor 1e-5).
 The measured numbers are written to gpurun_out/fullsize_parity.json (committed under profiles/).
 """
 import copy
@@ -183,9 +184,9 @@ def test_config1_hybridgnn_3x256_on_100x500_notes(operands):
         out = model({"note": x0.to(dev, dtype)}, _mv(b["edge_index_dict"], dev), _mv(b["batch_dict"], dev), b["batch_size"])
         return {"out": out}, (out * w.to(dev, dtype)).sum() / out.shape[0]
 
-    # forward 3e-5: three message-passing layers + a 2-layer GRU (500 steps) + LayerNorms between the input and the
-    # output; gradients 1e-4: the same depth backwards, weight gradients are sums over 50 000 rows
-    _compare("config1_hybridgnn", ref, net, fn, operands, fwd_tol=3 * FP32_REL, grad_tol=10 * FP32_REL,
+    # north_star's 1e-5 as it stands, forward and every gradient (measured on a B200, profiles/r2_a_fullsize_parity.json:
+    # forward 2.4e-6, worst gradient 2.6e-6, 8 sign ties in 5.1e7 ReLU units)
+    _compare("config1_hybridgnn", ref, net, fn, operands, fwd_tol=FP32_REL, grad_tol=FP32_REL,
              with_fp64=operands == "f16")
 
 
@@ -198,7 +199,8 @@ def test_config2_shell_beats_measures_three_heads(operands):
     net = ann.AnalysisEncoder(b["metadata"], 25, HIDDEN, 128, TASKS, LAYERS, dropout=0.0)
     net.load_state_dict(ref.state_dict())
     net.to(DEV)
-    _compare("config2_shell", ref, net, _shell_fn(b), operands, fwd_tol=3 * FP32_REL, grad_tol=10 * FP32_REL,
+    # 1e-5 as it stands (measured: logits 4.4e-6, worst of 181 gradients 2.6e-6, 31 sign ties in 1.04e8 ReLU units)
+    _compare("config2_shell", ref, net, _shell_fn(b), operands, fwd_tol=FP32_REL, grad_tol=FP32_REL,
              with_fp64=operands == "f16")
 
 
