@@ -75,6 +75,19 @@ class HgtRel(C.Structure):
                 ("ld_dkv", C.c_int64), ("n_src", C.c_int32), ("reserved", C.c_int32)]
 
 
+class GemmProblem(C.Structure):
+    """agnn_gemm_problem_t"""
+    _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_int64), ("amax_a", C.c_void_p),
+                ("b_hi", C.c_void_p), ("b_lo", C.c_void_p), ("ldb", C.c_int64), ("amax_b", C.c_void_p),
+                ("c", C.c_void_p), ("ldc", C.c_int64), ("bias", C.c_void_p), ("flags", C.c_int32),
+                ("split_k", C.c_int32), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("amax_out", C.c_void_p)]
+
+
+GEMM_MAX_GROUP = 12
+
+
 class ParamChunk(C.Structure):
     _fields_ = [("param", C.c_void_p), ("param_off", C.c_int64), ("arena_off", C.c_int64), ("count", C.c_int32),
                 ("param_aligned", C.c_int32)]
@@ -125,6 +138,28 @@ _PROTOTYPES = {
     "agnn_gemm_scaled": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "agnn_gemm_tickets": (C.c_int64, [C.c_int64, C.c_int64, C.c_int]),
+    "agnn_gemm_grouped": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GemmProblem), C.c_void_p, C.c_int64,
+                                    C.c_void_p]),
+    "agnn_gather_reduce_amax": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Rel),
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.c_void_p]),
+    "agnn_softmax_ce_bwd_padded": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float,
+                                             C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                             C.c_void_p, C.c_void_p]),
+    "agnn_layernorm_fwd_pair": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                          C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "agnn_layernorm_bwd_dropout": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_uint32,
+                                             C.c_void_p, C.c_void_p]),
+    "agnn_dropout_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "agnn_dropout_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float,
+                                     C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "agnn_split_f16_dropout": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]),
     "agnn_row_blocks": (C.c_int, [C.c_int64]),
     "agnn_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),

@@ -122,4 +122,30 @@ __device__ __forceinline__ void f16_pair4(const float (&v)[4], float s, uint2& h
   lo = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
 }
 
+// ---- counter-based dropout mask --------------------------------------------------------------------
+// keep(element) is a pure function of (seed, step, stream id, element index): the backward recomputes the mask
+// instead of reading one, and a CUDA-graph replay draws new masks because `step` is read from device memory.
+// One splitmix64 draw decides four consecutive elements (16 bits each): keep iff bits >= p * 2^16.
+struct DropoutState {           // device memory: {seed, step}; agnn_dropout_advance increments step
+  uint64_t seed, step;
+};
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+__device__ __forceinline__ uint64_t dropout_key(const uint64_t* state, uint32_t stream_id) {
+  return mix64(mix64(state[0] + 0x9E3779B97F4A7C15ull) ^ (state[1] * 0xD1B54A32D192ED03ull + stream_id));
+}
+// bits for the 4 elements starting at linear index `idx4 * 4`
+__device__ __forceinline__ uint64_t dropout_bits(uint64_t key, uint64_t idx4) { return mix64(key ^ (idx4 * 0x9E3779B97F4A7C15ull)); }
+__device__ __forceinline__ bool dropout_keep(uint64_t bits, int e, uint32_t threshold) {
+  return ((uint32_t)(bits >> (16 * e)) & 0xffffu) >= threshold;
+}
+__host__ __device__ inline uint32_t dropout_threshold(float p) {
+  const float t = p * 65536.f;
+  return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)(t + 0.5f));
+}
+
 }  // namespace agnn

@@ -34,6 +34,7 @@ struct GatherParams {
   void* out_lo;  // optional (fp32 only): out receives rna_tf32(y), out_lo rna_tf32(y - out) -- agnn_gemm operands
   const float* pair_amax;  // optional (fp32, CONCAT, with out_lo): out / out_lo are fp16 matrices receiving the F16X3
                            // operand pair of s y, s = f16_scale_of(*pair_amax); ld_out counts fp16 elements
+  float* amax_out;      // optional (plain fp32 / bf16 output): *amax_out = max(*amax_out, max |out|) over what is written
   float* heavy_ws;      // optional: partial rows of the heavy-row path, [max_chunks][n_feat]
   int64_t max_chunks;
 };
@@ -77,6 +78,19 @@ __device__ __forceinline__ void store_split(T* out, T* out_lo, int64_t idx, cons
   Vec16<T>::store(out + idx, v);
 }
 
+template <int E>
+__device__ __forceinline__ uint32_t absmax_bits(uint32_t m, const float (&v)[E]) {
+#pragma unroll
+  for (int e = 0; e < E; ++e) m = max(m, __float_as_uint(v[e]) & 0x7fffffffu);
+  return m;
+}
+__device__ __forceinline__ void publish_amax(float* amax_out, uint32_t m) {
+  if (!amax_out) return;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(amax_out), m);
+}
+
 template <typename T, int LANES, int V>
 __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel(const __grid_constant__ GatherParams p) {
   using VT = Vec16<T>;
@@ -87,6 +101,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel
   T* const out = static_cast<T*>(p.out);
   T* const out_lo = static_cast<T*>(p.out_lo);
   const float f16s = p.pair_amax ? f16_scale_of(__ldg(p.pair_amax)) : 0.f;
+  uint32_t mx = 0;
 
   for (int row = blockIdx.x * kRowsPerBlock + threadIdx.x / LANES; row < p.n_rows;
        row += gridDim.x * kRowsPerBlock) {
@@ -179,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel
             float o[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) o[e] = acc[v][e] * s;
+            mx = absmax_bits<E>(mx, o);
             store_split<T>(out, out_lo, off + c, o, f16s);
           }
         }
@@ -199,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel
           float o[E];
 #pragma unroll
           for (int e = 0; e < E; ++e) o[e] = tot[v][e] + (p.self_add ? selfv[v][e] : 0.f);
+          mx = absmax_bits<E>(mx, o);
           store_split<T>(out, out_lo, off + c, o, f16s);
         }
       }
@@ -212,10 +229,15 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel
         if (c < F) {
           float t[E];
           VT::load_nc(cp + c, t);
+          mx = absmax_bits<E>(mx, t);
           store_split<T>(out, out_lo, off + c, t, f16s);
         }
       }
     }
+  }
+  if (p.amax_out) {
+    // groups narrower than a warp: every lane holds its own maximum, the warp publishes one
+    publish_amax(p.amax_out, mx);
   }
 }
 
@@ -235,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_sum_kernel(co
   const int F = p.n_feat;
   T* const out = static_cast<T*>(p.out);
   T* const out_lo = static_cast<T*>(p.out_lo);
+  uint32_t mx = 0;
   for (int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < p.n_rows; row += gridDim.x * (kThreads / 32)) {
     float tot[V][E];
 #pragma unroll
@@ -319,7 +342,10 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_sum_kernel(co
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const int c = (v * 32 + lane) * E;
-      if (c < F) store_split<T>(out, out_lo, off + c, tot[v]);
+      if (c < F) {
+        mx = absmax_bits<E>(mx, tot[v]);
+        store_split<T>(out, out_lo, off + c, tot[v]);
+      }
     }
     if (p.copy) {
       const T* cp = static_cast<const T*>(p.copy) + (int64_t)row * p.ld_copy;
@@ -330,11 +356,13 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_sum_kernel(co
         if (c < F) {
           float tmp[E];
           VT::load_nc(cp + c, tmp);
+          mx = absmax_bits<E>(mx, tmp);
           store_split<T>(out, out_lo, coff + c, tmp);
         }
       }
     }
   }
+  publish_amax(p.amax_out, mx);
 }
 
 // ---- heavy rows: split across warps -------------------------------------------------------------
@@ -429,6 +457,7 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
   T* const out_lo = static_cast<T*>(p.out_lo);
   const float f16s = p.pair_amax ? f16_scale_of(__ldg(p.pair_amax)) : 0.f;
   const bool sum_mode = p.combine == AGNN_COMBINE_SUM;
+  uint32_t hmx = 0;
   int64_t g = 0, item = 0;
   for (int r = 0; r < p.n_rel; ++r) {
     const agnn_rel_t& R = p.rel[r];
@@ -482,6 +511,7 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
             }
 #pragma unroll
             for (int e = 0; e < E; ++e) o[e] = acc[v][e] * s;
+            hmx = absmax_bits<E>(hmx, o);
             store_split<T>(out, out_lo, off + cc, o, f16s);
           }
         }
@@ -548,10 +578,14 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int cc = (v * 32 + lane) * E;
-        if (cc < F) store_split<T>(out, out_lo, off + cc, tot[v]);
+        if (cc < F) {
+          hmx = absmax_bits<E>(hmx, tot[v]);
+          store_split<T>(out, out_lo, off + cc, tot[v]);
+        }
       }
     }
   }
+  publish_amax(p.amax_out, hmx);
 }
 
 template <typename T, int V>
@@ -654,6 +688,16 @@ extern "C" int agnn_gather_reduce_f16(int32_t n_rows, int32_t n_feat, int dtype,
                                       int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out, void* out_lo,
                                       const float* pair_amax, void* heavy_workspace, size_t heavy_workspace_bytes,
                                       agnn_stream_t stream) {
+  return agnn_gather_reduce_amax(n_rows, n_feat, dtype, scale, combine, n_rel, rels, self_add, ld_self, copy, ld_copy,
+                                 copy_col, out, ld_out, out_lo, pair_amax, nullptr, heavy_workspace, heavy_workspace_bytes,
+                                 stream);
+}
+
+extern "C" int agnn_gather_reduce_amax(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
+                                       const agnn_rel_t* rels, const void* self_add, int64_t ld_self, const void* copy,
+                                       int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out, void* out_lo,
+                                       const float* pair_amax, float* amax_out, void* heavy_workspace,
+                                       size_t heavy_workspace_bytes, agnn_stream_t stream) {
   if (n_rows < 0 || n_feat <= 0 || n_rel < 1 || n_rel > AGNN_MAX_REL || !rels || !out)
     return fail(AGNN_ERR_ARG, "gather_reduce: bad sizes (n_rows=%d n_feat=%d n_rel=%d)", n_rows, n_feat, n_rel);
   if (dtype != AGNN_F32 && dtype != AGNN_BF16) return fail(AGNN_ERR_ARG, "gather_reduce: dtype %d", dtype);
@@ -669,6 +713,9 @@ extern "C" int agnn_gather_reduce_f16(int32_t n_rows, int32_t n_feat, int dtype,
   p.self_add = self_add; p.ld_self = ld_self; p.copy = copy; p.ld_copy = ld_copy; p.out = out; p.ld_out = ld_out;
   p.out_lo = out_lo;
   p.pair_amax = pair_amax;
+  p.amax_out = amax_out;
+  if (amax_out && (pair_amax || out_lo))
+    return fail(AGNN_ERR_ARG, "gather_reduce: amax_out reports the plain output (not available with an operand pair)");
   if (pair_amax && (dtype != AGNN_F32 || combine != AGNN_COMBINE_CONCAT || !out_lo || (ld_out * 2) % 16))
     return fail(AGNN_ERR_ARG, "gather_reduce: the fp16 hi/lo output needs fp32 inputs, the concatenated layout, out_lo "
                               "and a row stride that is a multiple of 8 fp16 elements");

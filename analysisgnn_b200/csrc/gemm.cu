@@ -22,6 +22,14 @@
 //   K-major  : matrix stored [MN, K] row-major (activations as A, nn.Linear weights as B)
 //   MN-major : matrix stored [K, MN] row-major (weights as B in grad-input; both operands in grad-weight)
 //
+// Grouped launches (agnn_gemm_grouped): up to AGNN_GEMM_MAX_GROUP independent problems of one precision / layout
+// combination share ONE persistent launch -- the per-node-type projections (project_dict), the task heads, the
+// destination types of a message-passing layer, the directions of a GRU layer; tiles of all problems are dealt round
+// robin to the CTAs.  Split-K partials are combined INSIDE the launch: the CTA that stores the last partial of an
+// output tile (a ticket counter per tile) adds the partials in split order -- deterministic, no second kernel.
+// The epilogue can also emit max |C| (amax_out) so that a consumer that needs the fp16 operand scale of C does not
+// re-read it.
+//
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
 // lane), warps 2-5 = epilogue (TMEM -> registers -> global, each warp its own 32 TMEM lanes).
 // The accumulator is double buffered in TMEM (2 x 128 columns) so the epilogue of tile i overlaps
@@ -55,16 +63,30 @@ struct GemmParams {
   int M, N, K;
   int k_blocks;          // K blocks in total
   int k_blocks_per_split;
-  int chain_blocks;      // K blocks accumulated in TMEM before the sum is promoted to fp32 registers
   int split_k;
   int tiles_m, tiles_n;
-  void* out;             // [split_k][M][ldc] when split_k > 1 (workspace), else C
+  void* out;             // [split_k][tiles_m * 128][ld_part] when split_k > 1 (workspace), else C
   int64_t ldc;
   int64_t split_stride;  // elements between split partials
+  void* c_final;         // C (the in-kernel split-K reduction writes it)
+  int64_t ldc_final;
   const float* bias;
   int flags;
   const float* amax_a;   // F16X3: device scalars the operand scales derive from (null = unscaled operands)
   const float* amax_b;
+  float* amax_out;       // optional: *amax_out = max(*amax_out, max |C|)
+  int* tickets;          // split_k > 1: one counter per output tile (zero before the launch, zero after it), or null =
+                         // the partials are reduced by splitk_reduce_kernel after the launch
+};
+
+constexpr int kMaxGroup = AGNN_GEMM_MAX_GROUP;
+
+struct GemmGroup {
+  int n_prob;
+  int chain_blocks;      // K blocks accumulated in TMEM before the sum is promoted to fp32 registers
+  int total_tiles;
+  int tile_start[kMaxGroup + 1];   // first work item (tile x split) of every problem
+  GemmParams prob[kMaxGroup];
 };
 
 enum { kFmtTF32 = 0, kFmtBF16 = 1, kFmtF16 = 2 };
@@ -181,8 +203,31 @@ __host__ __device__ constexpr uint32_t instr_desc(int fmt, bool a_mn, bool b_mn,
          ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// work item -> (problem, split, tile origin)
+struct Item {
+  int g, split, mn, m0, n0, kb0, kb1;
+};
+__device__ __forceinline__ Item decode_item(const GemmGroup& grp, int item) {
+  Item it;
+  int g = 0;
+  while (g + 1 < grp.n_prob && item >= grp.tile_start[g + 1]) ++g;
+  const GemmParams& p = grp.prob[g];
+  const int local = item - grp.tile_start[g];
+  const int per_split = p.tiles_m * p.tiles_n;
+  it.g = g;
+  it.split = local / per_split;
+  it.mn = local - it.split * per_split;
+  it.m0 = (it.mn / p.tiles_n) * kBlockM;
+  it.n0 = (it.mn % p.tiles_n) * kBlockN;
+  it.kb0 = it.split * p.k_blocks_per_split;
+  it.kb1 = min(it.kb0 + p.k_blocks_per_split, p.k_blocks);
+  return it;
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+
 template <int FMT, bool A_MN, bool B_MN, int TERMS>
-__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmGroup grp) {
   constexpr bool BF16 = FMT != kFmtTF32;       // 2-byte operands (bf16 or fp16): same tiles and descriptors
   constexpr int kElem = BF16 ? 2 : 4;
   constexpr int kBlockK = kRowBytes / kElem;   // 32 tf32 / 64 bf16
@@ -204,16 +249,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   uint64_t* acc_full = empty + kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = p.tiles_m * p.tiles_n * p.split_k;
+  const int n_items = grp.total_tiles;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kParts; ++i) {
-      prefetch_tmap(&p.map_a[i]);
-      prefetch_tmap(&p.map_b[i]);
+    for (int g = 0; g < grp.n_prob; ++g) {
+      for (int i = 0; i < kParts; ++i) {
+        prefetch_tmap(&grp.prob[g].map_a[i]);
+        prefetch_tmap(&grp.prob[g].map_b[i]);
+      }
+      if (grp.prob[g].tma_store) prefetch_tmap(&grp.prob[g].map_c);
     }
-    if (p.tma_store) prefetch_tmap(&p.map_c);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -239,13 +287,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int split = tile / (p.tiles_m * p.tiles_n);
-        const int mn = tile - split * p.tiles_m * p.tiles_n;
-        const int m0 = (mn / p.tiles_n) * kBlockM, n0 = (mn % p.tiles_n) * kBlockN;
-        const int kb0 = split * p.k_blocks_per_split;
-        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
-        for (int kb = kb0; kb < kb1; ++kb) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(grp, item);
+        const GemmParams& p = grp.prob[it.g];
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * kStageBytes;
           mbar_expect_tx(&full[stage], kStageBytes);
@@ -257,16 +302,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             if constexpr (A_MN) {
 #pragma unroll
               for (int c = 0; c < kChunks; ++c)
-                tma_load_2d(a_dst + c * (kBlockK * kRowBytes), &p.map_a[part], &full[stage], m0 + c * kChunk, k0);
+                tma_load_2d(a_dst + c * (kBlockK * kRowBytes), &p.map_a[part], &full[stage], it.m0 + c * kChunk, k0);
             } else {
-              tma_load_2d(a_dst, &p.map_a[part], &full[stage], k0, m0);
+              tma_load_2d(a_dst, &p.map_a[part], &full[stage], k0, it.m0);
             }
             if constexpr (B_MN) {
 #pragma unroll
               for (int c = 0; c < kChunks; ++c)
-                tma_load_2d(b_dst + c * (kBlockK * kRowBytes), &p.map_b[part], &full[stage], n0 + c * kChunk, k0);
+                tma_load_2d(b_dst + c * (kBlockK * kRowBytes), &p.map_b[part], &full[stage], it.n0 + c * kChunk, k0);
             } else {
-              tma_load_2d(b_dst, &p.map_b[part], &full[stage], k0, n0);
+              tma_load_2d(b_dst, &p.map_b[part], &full[stage], k0, it.n0);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -277,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     // ------------------------------------------------------------ MMA issuer
     // The tensor core adds into the fp32 TMEM accumulator with truncation (measured: -0.5 ulp per MMA,
     // i.e. a bias that grows linearly with the chain).  A chain is therefore limited to
-    // p.chain_blocks K blocks; the epilogue warps sum the chains in registers with round-to-nearest.
+    // grp.chain_blocks K blocks; the epilogue warps sum the chains in registers with round-to-nearest.
     // One elected thread runs the whole issue loop (waits included): the loop is ~40 instructions per K block,
     // against ~130 when every lane walked it and the descriptors were rebuilt in 64-bit arithmetic per MMA --
     // at 12 MMAs per K block the issue path, not the tensor pipe, was setting the pace.
@@ -293,12 +338,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int cc = 0;                                    // chains issued so far (TMEM buffer = cc & 1)
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int split = tile / (p.tiles_m * p.tiles_n);
-        const int kb0 = split * p.k_blocks_per_split;
-        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
-        for (int c0 = kb0; c0 < kb1; c0 += p.chain_blocks, ++cc) {
-          const int c1 = min(c0 + p.chain_blocks, kb1);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(grp, item);
+        for (int c0 = it.kb0; c0 < it.kb1; c0 += grp.chain_blocks, ++cc) {
+          const int c1 = min(c0 + grp.chain_blocks, it.kb1);
           const int buf = cc & 1;
           mbar_wait(&acc_empty[buf], ((cc >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -335,20 +378,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) belong to this warp
+    const int et = threadIdx.x - 64;               // 0..127 among the epilogue threads
     uint8_t* sbuf = store_base + quarter * 2 * kStoreBufBytes;
-    const bool direct = p.split_k == 1;
-    // F16X3: the operands were scaled by powers of two; dividing by them (exactly) comes before the bias
-    const bool scaled = p.amax_a != nullptr;
-    const float inv_a = scaled ? 1.f / f16_scale_of(__ldg(p.amax_a)) : 1.f;
-    const float inv_b = scaled ? 1.f / f16_scale_of(__ldg(p.amax_b)) : 1.f;
     int cc = 0;
     int sc = 0;                                    // staged chunks so far (buffer = sc & 1)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int split = tile / (p.tiles_m * p.tiles_n);
-      const int mn = tile - split * p.tiles_m * p.tiles_n;
-      const int m0 = (mn / p.tiles_n) * kBlockM, n0 = (mn % p.tiles_n) * kBlockN;
-      const int kb0 = split * p.k_blocks_per_split;
-      const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode_item(grp, item);
+      const GemmParams& p = grp.prob[it.g];
+      const int m0 = it.m0, n0 = it.n0;
+      const bool direct = p.split_k == 1;
+      // F16X3: the operands were scaled by powers of two; dividing by them (exactly) comes before the bias
+      const bool scaled = p.amax_a != nullptr;
+      const float inv_a = scaled ? 1.f / f16_scale_of(__ldg(p.amax_a)) : 1.f;
+      const float inv_b = scaled ? 1.f / f16_scale_of(__ldg(p.amax_b)) : 1.f;
       const int row = m0 + quarter * 32 + lane;
       // The bias is the first addend: its loads are in flight while the first chain is computed.
       float acc[kBlockN];
@@ -359,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 #pragma unroll
         for (int j = 0; j < kBlockN; ++j) acc[j] = 0.f;
       }
-      for (int c0 = kb0; c0 < kb1; c0 += p.chain_blocks, ++cc) {
+      for (int c0 = it.kb0; c0 < it.kb1; c0 += grp.chain_blocks, ++cc) {
         const int buf = cc & 1;
         mbar_wait(&acc_full[buf], (cc >> 1) & 1);
         tc_fence_after();
@@ -385,6 +427,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           for (int j = 0; j < kBlockN; ++j) acc[j] = (acc[j] * inv_a) * inv_b;
         }
       }
+      if (direct && (p.flags & AGNN_GEMM_RELU) && !(p.flags & AGNN_GEMM_ACCUMULATE)) {
+#pragma unroll
+        for (int j = 0; j < kBlockN; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      }
+      if (direct && p.amax_out && !(p.flags & AGNN_GEMM_ACCUMULATE)) {
+        // max |C| over the valid part of this thread's row (rows >= M hold the bias only: not part of C)
+        uint32_t mx = 0;
+        if (row < p.M) {
+#pragma unroll
+          for (int j = 0; j < kBlockN; ++j)
+            if (n0 + j < p.N) mx = max(mx, __float_as_uint(acc[j]) & 0x7fffffffu);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        if (lane == 0 && mx) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), mx);
+      }
       if (p.tma_store) {
         // registers -> 128-byte-swizzled shared memory (this warp's 32 rows x 32 columns) -> one TMA store
         // (or fp32 reduce-add for AGNN_GEMM_ACCUMULATE); the map clips rows >= M and columns >= N.
@@ -393,10 +451,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;
           float* v = acc + c * 32;
-          if (p.flags & AGNN_GEMM_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
           uint8_t* buf = sbuf + (sc & 1) * kStoreBufBytes;
           ++sc;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -414,51 +468,156 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             else tma_store_2d<false>(&p.map_c, buf, col0, m0 + quarter * 32);
           }
         }
-      } else if (row < p.M) {
+      } else if (direct) {
+        if (row < p.M) {
+#pragma unroll
+          for (int c = 0; c < kBlockN / 32; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= p.N) break;
+            float* v = acc + c * 32;
+            const int64_t off = (int64_t)row * p.ldc + col0;
+            if (!(p.flags & AGNN_GEMM_OUT_BF16)) {
+              float* o = static_cast<float*>(p.out) + off;
+              if (p.flags & AGNN_GEMM_ACCUMULATE) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) v[j] += o[j];
+                if (p.flags & AGNN_GEMM_RELU) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+              }
+              if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) o[j] = v[j];
+              }
+            } else {
+              __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + off;
+              if (p.flags & AGNN_GEMM_ACCUMULATE) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) v[j] += __bfloat162float(o[j]);
+                if (p.flags & AGNN_GEMM_RELU) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      } else {
+        // ---- split-K: this item's partial tile -> workspace [split][tiles_m * 128][ld_part] (rows padded to whole
+        // tiles, so every row of the tile has a slot).  Staged through this warp's shared-memory box so that 8 lanes
+        // write 128 contiguous bytes.
+        float* part = static_cast<float*>(p.out) + (int64_t)it.split * p.split_stride;
+        uint8_t* buf = sbuf;
 #pragma unroll
         for (int c = 0; c < kBlockN / 32; ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;
           float* v = acc + c * 32;
-          const int64_t off = (int64_t)split * p.split_stride + (int64_t)row * p.ldc + col0;
-          if (!direct || !(p.flags & AGNN_GEMM_OUT_BF16)) {
-            float* o = static_cast<float*>(p.out) + off;
-            if (direct && (p.flags & AGNN_GEMM_ACCUMULATE)) {
+          if (sc) {                                 // a TMA store of an earlier direct tile may still read the box
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            sc = 0;
+          }
+          __syncwarp();
+          const uint32_t row_addr = smem_u32(buf) + lane * 128;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) v[j] += o[j];
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((j ^ (lane & 7)) << 4)),
+                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                         : "memory");
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3), q = lane & 7;
+            float4 t;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                         : "r"(smem_u32(buf) + r * 128 + ((q ^ (r & 7)) << 4)));
+            if (m0 + quarter * 32 + r < p.M && col0 + q * 4 < p.N)
+              *reinterpret_cast<float4*>(part + (int64_t)(m0 + quarter * 32 + r) * p.ldc + col0 + q * 4) = t;
+          }
+          __syncwarp();
+        }
+        if (p.tickets) {
+          // the CTA that completes the tile adds the partials in split order (deterministic) and finishes C
+          __threadfence();
+          epi_barrier();
+          if (et == 0) {
+            const int old = atomicAdd(p.tickets + it.mn, 1);
+            *last_flag = (old == p.split_k - 1) ? 1 : 0;
+          }
+          epi_barrier();
+          const bool last = *last_flag != 0;
+          epi_barrier();                            // everyone has read the flag before the next item rewrites it
+          if (last) {
+            __threadfence();
+            const int qv = et & 31;                 // float4 column of the tile
+            uint32_t mx = 0;
+            for (int r = et >> 5; r < kBlockM; r += 4) {
+              const int grow = m0 + r, gcol = n0 + qv * 4;
+              if (grow >= p.M || gcol >= p.N) continue;
+              float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) {
+                sum.x = __ldg(p.bias + gcol);
+                if (gcol + 1 < p.N) sum.y = __ldg(p.bias + gcol + 1);
+                if (gcol + 2 < p.N) sum.z = __ldg(p.bias + gcol + 2);
+                if (gcol + 3 < p.N) sum.w = __ldg(p.bias + gcol + 3);
+              }
+              const float* src = static_cast<const float*>(p.out) + (int64_t)grow * p.ldc + gcol;
+              for (int sp = 0; sp < p.split_k; ++sp) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)sp * p.split_stride));
+                sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+              }
+              float v[4] = {sum.x, sum.y, sum.z, sum.w};
+              if (p.flags & AGNN_GEMM_OUT_BF16) {
+                __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.c_final) + (int64_t)grow * p.ldc_final + gcol;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (gcol + e < p.N) {
+                    float x = v[e];
+                    if (p.flags & AGNN_GEMM_ACCUMULATE) x += __bfloat162float(o[e]);
+                    if (p.flags & AGNN_GEMM_RELU) x = fmaxf(x, 0.f);
+                    mx = max(mx, __float_as_uint(x) & 0x7fffffffu);
+                    o[e] = __float2bfloat16_rn(x);
+                  }
+              } else {
+                float* o = static_cast<float*>(p.c_final) + (int64_t)grow * p.ldc_final + gcol;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (gcol + e < p.N) {
+                    if (p.flags & AGNN_GEMM_ACCUMULATE) v[e] += o[e];
+                    if (p.flags & AGNN_GEMM_RELU) v[e] = fmaxf(v[e], 0.f);
+                    mx = max(mx, __float_as_uint(v[e]) & 0x7fffffffu);
+                  }
+                if (gcol + 4 <= p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (gcol + e < p.N) o[e] = v[e];
+                }
+              }
             }
-            if (direct && (p.flags & AGNN_GEMM_RELU)) {
+            if (p.amax_out) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int d = 16; d >= 1; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+              if (lane == 0 && mx) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), mx);
             }
-            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + off;
-            if (p.flags & AGNN_GEMM_ACCUMULATE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) v[j] += __bfloat162float(o[j]);
-            }
-            if (p.flags & AGNN_GEMM_RELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+            if (et == 0) p.tickets[it.mn] = 0;      // self-cleaning: the counters are zero again after the launch
           }
         }
       }
     }
-    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -497,8 +656,10 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int split_k,
                                                              int64_t split_stride, int64_t M, int N, int64_t ld_p,
                                                              void* __restrict__ out, int64_t ldc,
-                                                             const float* __restrict__ bias, int flags) {
+                                                             const float* __restrict__ bias, int flags,
+                                                             float* __restrict__ amax_out) {
   const int64_t total = M * N;
+  uint32_t mx = 0;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     const int64_t m = i / N;
     const int n = (int)(i - m * N);
@@ -515,6 +676,12 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
       if (flags & AGNN_GEMM_RELU) acc = fmaxf(acc, 0.f);
       *o = acc;
     }
+    mx = max(mx, __float_as_uint(acc) & 0x7fffffffu);
+  }
+  if (amax_out) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(reinterpret_cast<unsigned int*>(amax_out), mx);
   }
 }
 
@@ -556,13 +723,11 @@ int make_map(CUtensorMap* map, const void* ptr, int fmt, int64_t rows, int64_t c
 }
 
 template <int FMT, bool A_MN, bool B_MN, int TERMS>
-int launch(const GemmParams& p, int grid, cudaStream_t st) {
-  constexpr int kElem = FMT != kFmtTF32 ? 2 : 4;
+int launch(const GemmGroup& grp, int grid, cudaStream_t st) {
   constexpr int kParts = TERMS == 3 ? 2 : 1;
   constexpr int kStageBytes = 2 * kParts * kTileBytes;
   constexpr int kStages = kSmemBudget / kStageBytes;
   constexpr int smem = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
-  (void)kElem;
   auto kern = gemm_kernel<FMT, A_MN, B_MN, TERMS>;
   static bool configured = false;
   if (!configured) {
@@ -570,16 +735,87 @@ int launch(const GemmParams& p, int grid, cudaStream_t st) {
       return check_launch("gemm: cudaFuncSetAttribute");
     configured = true;
   }
-  kern<<<grid, kThreads, smem, st>>>(p);
+  kern<<<grid, kThreads, smem, st>>>(grp);
   return check_launch("gemm");
 }
 
 template <int FMT, int TERMS>
-int dispatch_layout(bool a_mn, bool b_mn, const GemmParams& p, int grid, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<FMT, false, false, TERMS>(p, grid, st);
-  if (!a_mn && b_mn) return launch<FMT, false, true, TERMS>(p, grid, st);
-  if (a_mn && b_mn) return launch<FMT, true, true, TERMS>(p, grid, st);
-  return launch<FMT, true, false, TERMS>(p, grid, st);
+int dispatch_layout(bool a_mn, bool b_mn, const GemmGroup& grp, int grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<FMT, false, false, TERMS>(grp, grid, st);
+  if (!a_mn && b_mn) return launch<FMT, false, true, TERMS>(grp, grid, st);
+  if (a_mn && b_mn) return launch<FMT, true, true, TERMS>(grp, grid, st);
+  return launch<FMT, true, false, TERMS>(grp, grid, st);
+}
+
+inline int64_t part_ld(int64_t N) { return ceil_div(N, kBlockN) * kBlockN; }
+inline int64_t part_rows(int64_t M) { return ceil_div(M, kBlockM) * kBlockM; }
+
+// fills grp.prob[i] from a problem description (validation, tensor maps, split bookkeeping)
+int setup_problem(GemmParams& p, int precision, bool a_mn, bool b_mn, const agnn_gemm_problem_t& q, int* tickets) {
+  const int64_t M = q.M, N = q.N, K = q.K;
+  const bool bf16 = precision == AGNN_GEMM_BF16;
+  const bool three = precision == AGNN_GEMM_TF32X3 || precision == AGNN_GEMM_F16X3;
+  const int fmt = bf16 ? kFmtBF16 : precision == AGNN_GEMM_F16X3 ? kFmtF16 : kFmtTF32;
+  const int eb = fmt == kFmtTF32 ? 4 : 2, block_k = kRowBytes / eb, chunk = kRowBytes / eb;
+  if ((q.amax_a || q.amax_b) && (precision != AGNN_GEMM_F16X3 || !q.amax_a || !q.amax_b))
+    return fail(AGNN_ERR_ARG, "gemm: operand scales belong to the F16X3 mode and come in pairs");
+  if (M <= 0 || N <= 0 || K <= 0 || !q.c || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31))
+    return fail(AGNN_ERR_ARG, "gemm: bad sizes");
+  if (!q.a_hi || !q.b_hi || (three && (!q.a_lo || !q.b_lo)))
+    return fail(AGNN_ERR_ARG, "gemm: null operand (the three-product modes need the hi and lo parts of both operands)");
+  if ((q.lda * eb) % 16 || (q.ldb * eb) % 16 || !aligned16(q.a_hi) || !aligned16(q.b_hi) ||
+      (q.a_lo && !aligned16(q.a_lo)) || (q.b_lo && !aligned16(q.b_lo)))
+    return fail(AGNN_ERR_UNSUPPORTED, "gemm: operands must be 16-byte aligned with 16-byte multiple row strides");
+  if ((q.flags & AGNN_GEMM_OUT_BF16) && !bf16) return fail(AGNN_ERR_ARG, "gemm: bf16 output needs the bf16 mode");
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.k_blocks = (int)ceil_div(K, block_k);
+  int split_k = q.split_k < 1 ? 1 : q.split_k;
+  if (split_k > p.k_blocks) split_k = p.k_blocks;
+  p.k_blocks_per_split = (int)ceil_div(p.k_blocks, split_k);
+  split_k = (int)ceil_div(p.k_blocks, p.k_blocks_per_split);
+  p.split_k = split_k;
+  if (q.amax_out && (q.flags & AGNN_GEMM_ACCUMULATE) && split_k == 1)
+    return fail(AGNN_ERR_ARG, "gemm: amax_out is not available together with AGNN_GEMM_ACCUMULATE");
+  p.amax_a = q.amax_a;
+  p.amax_b = q.amax_b;
+  p.amax_out = q.amax_out;
+  p.tiles_m = (int)ceil_div(M, kBlockM);
+  p.tiles_n = (int)ceil_div(N, kBlockN);
+  p.bias = q.bias;
+  p.flags = q.flags;
+  p.c_final = q.c;
+  p.ldc_final = q.ldc;
+  if (split_k > 1) {
+    const int64_t ld_part = part_ld(N);
+    const size_t need = (size_t)split_k * (size_t)part_rows(M) * (size_t)ld_part * sizeof(float);
+    if (!q.workspace || q.workspace_bytes < need || !aligned16(q.workspace))
+      return fail(AGNN_ERR_WORKSPACE, "gemm: split-K workspace %zu < %zu bytes", q.workspace_bytes, need);
+    p.out = q.workspace; p.ldc = ld_part; p.split_stride = part_rows(M) * ld_part;
+    p.tickets = tickets;
+  } else {
+    p.out = q.c; p.ldc = q.ldc; p.split_stride = 0;
+  }
+  int rc;
+  const void* a_parts[2] = {q.a_hi, q.a_lo};
+  const void* b_parts[2] = {q.b_hi, q.b_lo};
+  const int parts = three ? 2 : 1;
+  for (int i = 0; i < parts; ++i) {
+    // K-major: [MN, K] row-major, box = block_k x 128 rows.  MN-major: [K, MN] row-major, box = chunk x block_k rows.
+    rc = a_mn ? make_map(&p.map_a[i], a_parts[i], fmt, K, M, q.lda, chunk, block_k, true)
+              : make_map(&p.map_a[i], a_parts[i], fmt, M, K, q.lda, block_k, kBlockM, false);
+    if (rc) return rc;
+    rc = b_mn ? make_map(&p.map_b[i], b_parts[i], fmt, K, N, q.ldb, chunk, block_k, true)
+              : make_map(&p.map_b[i], b_parts[i], fmt, N, K, q.ldb, block_k, kBlockN, false);
+    if (rc) return rc;
+  }
+  const bool acc_relu = (q.flags & AGNN_GEMM_ACCUMULATE) && (q.flags & AGNN_GEMM_RELU);
+  if (split_k == 1 && !(q.flags & AGNN_GEMM_OUT_BF16) && !acc_relu && (q.ldc * 4) % 16 == 0 && aligned16(q.c)) {
+    rc = make_map(&p.map_c, q.c, kFmtTF32, M, N, q.ldc, kStoreBox, kStoreBox, false);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
+  return AGNN_OK;
 }
 
 }  // namespace
@@ -624,14 +860,25 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, 
 
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, int64_t rows, int cols4,
                                                          int64_t ld_x, const float* __restrict__ amax,
-                                                         __half* __restrict__ hi, __half* __restrict__ lo, int64_t ld_o) {
+                                                         __half* __restrict__ hi, __half* __restrict__ lo, int64_t ld_o,
+                                                         float drop_p, const uint64_t* __restrict__ rng,
+                                                         uint32_t rng_stream) {
   const float s = f16_scale_of(__ldg(amax));
   const int64_t total = rows * cols4;
+  const bool drop = drop_p > 0.f && rng;
+  const float keep_scale = drop ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t thr = dropout_threshold(drop_p);
+  const uint64_t key = drop ? dropout_key(rng, rng_stream) : 0ull;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     const int64_t r = i / cols4;
     const int c = (int)(i - r * cols4) * 4;
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + c));
-    const float in[4] = {v.x, v.y, v.z, v.w};
+    float in[4] = {v.x, v.y, v.z, v.w};
+    if (drop) {                                   // same mask as agnn_dropout_apply on [rows, cols]
+      const uint64_t bits = dropout_bits(key, (uint64_t)i);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) in[e] = dropout_keep(bits, e, thr) ? in[e] * keep_scale : 0.f;
+    }
     uint2 h, l;
     f16_pair4(in, s, h, l);
     *reinterpret_cast<uint2*>(hi + r * ld_o + c) = h;
@@ -652,7 +899,14 @@ extern "C" int agnn_amax(const float* x, int64_t rows, int64_t cols, int64_t ld_
 
 extern "C" int agnn_split_f16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax, void* hi,
                               void* lo, int64_t ld_out, agnn_stream_t stream) {
+  return agnn_split_f16_dropout(x, rows, cols, ld_x, amax, hi, lo, ld_out, 0.f, nullptr, 0, stream);
+}
+
+extern "C" int agnn_split_f16_dropout(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax,
+                                      void* hi, void* lo, int64_t ld_out, float dropout_p, const uint64_t* rng_state,
+                                      uint32_t rng_stream, agnn_stream_t stream) {
   if (rows < 0 || cols < 0 || !amax || !hi || !lo) return fail(AGNN_ERR_ARG, "split_f16: bad arguments");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(AGNN_ERR_ARG, "split_f16: dropout needs 0 <= p < 1");
   if (rows == 0 || cols == 0) return AGNN_OK;
   if (cols % 4 || (ld_x * 4) % 16 || (ld_out * 2) % 16 || !aligned16(x) || !aligned16(hi) || !aligned16(lo))
     return fail(AGNN_ERR_ARG, "split_f16: needs 16-byte aligned rows and a column count multiple of 4");
@@ -660,7 +914,7 @@ extern "C" int agnn_split_f16(const float* x, int64_t rows, int64_t cols, int64_
   if (blocks > kNumSM * 16) blocks = kNumSM * 16;
   split_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, (int)(cols / 4), ld_x, amax,
                                                                         static_cast<__half*>(hi), static_cast<__half*>(lo),
-                                                                        ld_out);
+                                                                        ld_out, dropout_p, rng_state, rng_stream);
   return check_launch("split_f16");
 }
 
@@ -686,7 +940,12 @@ extern "C" int agnn_gemm_split_k(int precision, int64_t M, int64_t N, int64_t K)
 extern "C" size_t agnn_gemm_workspace(int precision, int64_t M, int64_t N, int64_t K, int split_k) {
   (void)precision; (void)K;
   if (split_k <= 1) return 0;
-  return (size_t)split_k * (size_t)M * (size_t)((N + 3) / 4 * 4) * sizeof(float);
+  // partial tiles are stored whole: rows and columns padded to the 128 x 128 tile grid
+  return (size_t)split_k * (size_t)part_rows(M) * (size_t)part_ld(N) * sizeof(float);
+}
+
+extern "C" int64_t agnn_gemm_tickets(int64_t M, int64_t N, int split_k) {
+  return split_k > 1 ? ceil_div(M, kBlockM) * ceil_div(N, kBlockN) : 0;
 }
 
 extern "C" int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, int64_t N, int64_t K, const void* a_hi,
@@ -702,84 +961,74 @@ extern "C" int agnn_gemm_scaled(int precision, int a_layout, int b_layout, int64
                                 const void* b_lo, int64_t ldb, const float* amax_b, void* c, int64_t ldc,
                                 const float* bias, int flags, int split_k, void* workspace, size_t workspace_bytes,
                                 agnn_stream_t stream) {
+  agnn_gemm_problem_t q;
+  memset(&q, 0, sizeof(q));
+  q.M = M; q.N = N; q.K = K;
+  q.a_hi = a_hi; q.a_lo = a_lo; q.lda = lda; q.amax_a = amax_a;
+  q.b_hi = b_hi; q.b_lo = b_lo; q.ldb = ldb; q.amax_b = amax_b;
+  q.c = c; q.ldc = ldc; q.bias = bias; q.flags = flags; q.split_k = split_k;
+  q.workspace = workspace; q.workspace_bytes = workspace_bytes;
+  return agnn_gemm_grouped(precision, a_layout, b_layout, 1, &q, nullptr, 0, stream);
+}
+
+extern "C" int agnn_gemm_grouped(int precision, int a_layout, int b_layout, int n_problems,
+                                 const agnn_gemm_problem_t* problems, int32_t* tickets, int64_t n_tickets,
+                                 agnn_stream_t stream) {
   if (precision != AGNN_GEMM_TF32X3 && precision != AGNN_GEMM_TF32 && precision != AGNN_GEMM_BF16 &&
       precision != AGNN_GEMM_F16X3)
     return fail(AGNN_ERR_ARG, "gemm: unknown precision mode %d", precision);
-  if ((amax_a || amax_b) && (precision != AGNN_GEMM_F16X3 || !amax_a || !amax_b))
-    return fail(AGNN_ERR_ARG, "gemm: operand scales belong to the F16X3 mode and come in pairs");
-  if (M < 0 || N < 0 || K < 0 || !c || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31))
-    return fail(AGNN_ERR_ARG, "gemm: bad sizes");
-  if (M == 0 || N == 0) return AGNN_OK;
-  const bool bf16 = precision == AGNN_GEMM_BF16;
-  const bool three = precision == AGNN_GEMM_TF32X3 || precision == AGNN_GEMM_F16X3;
-  const int fmt = bf16 ? kFmtBF16 : precision == AGNN_GEMM_F16X3 ? kFmtF16 : kFmtTF32;
-  const int eb = fmt == kFmtTF32 ? 4 : 2, block_k = kRowBytes / eb, chunk = kRowBytes / eb;
+  if (n_problems < 0 || n_problems > kMaxGroup || (n_problems && !problems))
+    return fail(AGNN_ERR_ARG, "gemm: 0..%d problems per launch, got %d", kMaxGroup, n_problems);
   const bool a_mn = a_layout == AGNN_LAYOUT_MN_MAJOR, b_mn = b_layout == AGNN_LAYOUT_MN_MAJOR;
-  if (!a_hi || !b_hi || (three && (!a_lo || !b_lo)))
-    return fail(AGNN_ERR_ARG, "gemm: null operand (the three-product modes need the hi and lo parts of both operands)");
-  if ((lda * eb) % 16 || (ldb * eb) % 16 || !aligned16(a_hi) || !aligned16(b_hi) || (a_lo && !aligned16(a_lo)) ||
-      (b_lo && !aligned16(b_lo)))
-    return fail(AGNN_ERR_UNSUPPORTED, "gemm: operands must be 16-byte aligned with 16-byte multiple row strides");
-  if ((flags & AGNN_GEMM_OUT_BF16) && !bf16) return fail(AGNN_ERR_ARG, "gemm: bf16 output needs the bf16 mode");
-  if (split_k < 1) split_k = 1;
-  GemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.k_blocks = (int)ceil_div(K, block_k);
-  if (p.k_blocks == 0) return fail(AGNN_ERR_ARG, "gemm: K == 0");
-  if (split_k > p.k_blocks) split_k = p.k_blocks;
-  p.k_blocks_per_split = (int)ceil_div(p.k_blocks, split_k);
-  split_k = (int)ceil_div(p.k_blocks, p.k_blocks_per_split);
-  p.split_k = split_k;
-  p.chain_blocks = three ? 2 : (1 << 30);      // 24 MMAs per TMEM chain in both three-product modes
-  p.amax_a = amax_a;
-  p.amax_b = amax_b;
-  p.tiles_m = (int)ceil_div(M, kBlockM);
-  p.tiles_n = (int)ceil_div(N, kBlockN);
-  p.bias = bias;
-  p.flags = flags;
-  const int64_t ld_part = (N + 3) / 4 * 4;
-  if (split_k > 1) {
-    const size_t need = (size_t)split_k * (size_t)M * (size_t)ld_part * sizeof(float);
-    if (!workspace || workspace_bytes < need || !aligned16(workspace))
-      return fail(AGNN_ERR_WORKSPACE, "gemm: split-K workspace %zu < %zu bytes", workspace_bytes, need);
-    p.out = workspace; p.ldc = ld_part; p.split_stride = M * ld_part;
-  } else {
-    p.out = c; p.ldc = ldc; p.split_stride = 0;
-  }
-  int rc;
-  const void* a_parts[2] = {a_hi, a_lo};
-  const void* b_parts[2] = {b_hi, b_lo};
-  const int parts = three ? 2 : 1;
-  for (int i = 0; i < parts; ++i) {
-    // K-major: [MN, K] row-major, box = block_k x 128 rows.  MN-major: [K, MN] row-major, box = chunk x block_k rows.
-    rc = a_mn ? make_map(&p.map_a[i], a_parts[i], fmt, K, M, lda, chunk, block_k, true)
-              : make_map(&p.map_a[i], a_parts[i], fmt, M, K, lda, block_k, kBlockM, false);
+  const bool three = precision == AGNN_GEMM_TF32X3 || precision == AGNN_GEMM_F16X3;
+  static thread_local GemmGroup grp;           // 9 KB: kept off the stack
+  grp.n_prob = 0;
+  grp.chain_blocks = three ? 2 : (1 << 30);    // 24 MMAs per TMEM chain in both three-product modes
+  int64_t items = 0, ticket_off = 0;
+  for (int i = 0; i < n_problems; ++i) {
+    const agnn_gemm_problem_t& q = problems[i];
+    if (q.M == 0 || q.N == 0) continue;        // empty problem: nothing to write
+    if (q.K == 0) return fail(AGNN_ERR_ARG, "gemm: K == 0");
+    GemmParams& p = grp.prob[grp.n_prob];
+    int* t = nullptr;
+    const int64_t need = agnn_gemm_tickets(q.M, q.N, q.split_k);
+    if (tickets && need) {
+      if (ticket_off + need > n_tickets)
+        return fail(AGNN_ERR_WORKSPACE, "gemm: %lld ticket counters needed, %lld given", (long long)(ticket_off + need),
+                    (long long)n_tickets);
+      t = tickets + ticket_off;
+    }
+    int rc = setup_problem(p, precision, a_mn, b_mn, q, t);
     if (rc) return rc;
-    rc = b_mn ? make_map(&p.map_b[i], b_parts[i], fmt, K, N, ldb, chunk, block_k, true)
-              : make_map(&p.map_b[i], b_parts[i], fmt, N, K, ldb, block_k, kBlockN, false);
-    if (rc) return rc;
+    if (p.split_k > 1 && t) ticket_off += need;
+    grp.tile_start[grp.n_prob] = (int)items;
+    items += (int64_t)p.tiles_m * p.tiles_n * p.split_k;
+    if (items >= (1ll << 31)) return fail(AGNN_ERR_ARG, "gemm: too many tiles");
+    ++grp.n_prob;
   }
-  const bool acc_relu = (flags & AGNN_GEMM_ACCUMULATE) && (flags & AGNN_GEMM_RELU);
-  if (split_k == 1 && !(flags & AGNN_GEMM_OUT_BF16) && !acc_relu && (ldc * 4) % 16 == 0 && aligned16(c)) {
-    rc = make_map(&p.map_c, c, kFmtTF32, M, N, ldc, kStoreBox, kStoreBox, false);
-    if (rc) return rc;
-    p.tma_store = 1;
-  }
-  const int64_t work = (int64_t)p.tiles_m * p.tiles_n * split_k;
-  const int grid = (int)(work < kNumSM ? work : kNumSM);
+  if (grp.n_prob == 0) return AGNN_OK;
+  grp.tile_start[grp.n_prob] = (int)items;
+  grp.total_tiles = (int)items;
+  const int grid = (int)(items < kNumSM ? items : kNumSM);
   cudaStream_t st = (cudaStream_t)stream;
-  if (bf16) rc = dispatch_layout<kFmtBF16, 1>(a_mn, b_mn, p, grid, st);
-  else if (precision == AGNN_GEMM_F16X3) rc = dispatch_layout<kFmtF16, 3>(a_mn, b_mn, p, grid, st);
-  else if (precision == AGNN_GEMM_TF32X3) rc = dispatch_layout<kFmtTF32, 3>(a_mn, b_mn, p, grid, st);
-  else rc = dispatch_layout<kFmtTF32, 1>(a_mn, b_mn, p, grid, st);
+  int rc;
+  if (precision == AGNN_GEMM_BF16) rc = dispatch_layout<kFmtBF16, 1>(a_mn, b_mn, grp, grid, st);
+  else if (precision == AGNN_GEMM_F16X3) rc = dispatch_layout<kFmtF16, 3>(a_mn, b_mn, grp, grid, st);
+  else if (precision == AGNN_GEMM_TF32X3) rc = dispatch_layout<kFmtTF32, 3>(a_mn, b_mn, grp, grid, st);
+  else rc = dispatch_layout<kFmtTF32, 1>(a_mn, b_mn, grp, grid, st);
   if (rc) return rc;
-  if (split_k > 1) {
-    int64_t blocks = ceil_div(M * N, 256);
-    if (blocks > kNumSM * 8) blocks = kNumSM * 8;
-    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(workspace), split_k,
-                                                            p.split_stride, M, (int)N, ld_part, c, ldc, bias, flags);
-    return check_launch("gemm split-K reduce");
+  // without ticket counters the partials are reduced by a second kernel (fixed order as well)
+  for (int i = 0; i < grp.n_prob; ++i) {
+    const GemmParams& p = grp.prob[i];
+    if (p.split_k > 1 && !p.tickets) {
+      int64_t blocks = ceil_div((int64_t)p.M * p.N, 256);
+      if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+      splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(p.out), p.split_k, p.split_stride,
+                                                              p.M, p.N, p.ldc, p.c_final, p.ldc_final, p.bias, p.flags,
+                                                              p.amax_out);
+      rc = check_launch("gemm split-K reduce");
+      if (rc) return rc;
+    }
   }
   return AGNN_OK;
 }

@@ -96,10 +96,14 @@ __global__ void __launch_bounds__(kThreads) ce_bwd_kernel(const float* __restric
                                                            const float* __restrict__ lse, int64_t rows, int cols,
                                                            float smoothing, int64_t ignore_index,
                                                            const float* __restrict__ out, const float* __restrict__ gout,
-                                                           float* __restrict__ dx, int64_t ld_d) {
+                                                           float* __restrict__ dx, int64_t ld_d, int cols_pad,
+                                                           float* __restrict__ amax_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float coef = __ldg(gout) / __ldg(out + 1);
   const float uniform = smoothing / (float)cols;
+  // |softmax - target| <= 1, so |coef| bounds every entry: the fp16 operand scale of dx for the head's backward GEMMs
+  if (amax_out && blockIdx.x == 0 && threadIdx.x == 0)
+    atomicMax(reinterpret_cast<unsigned int*>(amax_out), __float_as_uint(coef) & 0x7fffffffu);
   for (int64_t r = (int64_t)blockIdx.x * kWarps + warp; r < rows; r += (int64_t)gridDim.x * kWarps) {
     const int64_t y = labels[r];
     const bool valid = y != ignore_index && y >= 0 && y < cols;
@@ -111,6 +115,7 @@ __global__ void __launch_bounds__(kThreads) ce_bwd_kernel(const float* __restric
       if (valid) v = coef * (expf(__ldg(xr + c) - l) - (c == y ? 1.f - smoothing : 0.f) - uniform);
       dr[c] = v;
     }
+    for (int c = cols + lane; c < cols_pad; c += 32) dr[c] = 0.f;     // padding columns of a 16-byte aligned row
   }
 }
 
@@ -191,13 +196,23 @@ extern "C" int agnn_softmax_ce_fwd(const float* logits, int64_t ld, const int64_
 extern "C" int agnn_softmax_ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse,
                                    int64_t rows, int cols, float smoothing, int64_t ignore_index, const float* out,
                                    const float* grad_out, float* dlogits, int64_t ld_d, agnn_stream_t stream) {
-  if (rows < 0 || cols < 1 || ld < cols || ld_d < cols) return fail(AGNN_ERR_ARG, "softmax_ce_bwd: bad sizes");
+  return agnn_softmax_ce_bwd_padded(logits, ld, labels, lse, rows, cols, smoothing, ignore_index, out, grad_out, dlogits,
+                                    ld_d, cols, nullptr, stream);
+}
+
+extern "C" int agnn_softmax_ce_bwd_padded(const float* logits, int64_t ld, const int64_t* labels, const float* lse,
+                                          int64_t rows, int cols, float smoothing, int64_t ignore_index, const float* out,
+                                          const float* grad_out, float* dlogits, int64_t ld_d, int cols_padded,
+                                          float* amax_out, agnn_stream_t stream) {
+  if (rows < 0 || cols < 1 || ld < cols || cols_padded < cols || ld_d < cols_padded)
+    return fail(AGNN_ERR_ARG, "softmax_ce_bwd: bad sizes");
   if (rows == 0) return AGNN_OK;
   if (!logits || !labels || !lse || !out || !grad_out || !dlogits) return fail(AGNN_ERR_ARG, "softmax_ce_bwd: null pointer");
   int64_t blocks = ceil_div(rows, kWarps);
   if (blocks > kNumSM * 8) blocks = kNumSM * 8;
   ce_bwd_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(logits, ld, labels, lse, rows, cols, smoothing,
-                                                                        ignore_index, out, grad_out, dlogits, ld_d);
+                                                                        ignore_index, out, grad_out, dlogits, ld_d,
+                                                                        cols_padded, amax_out);
   return check_launch("softmax_ce_bwd");
 }
 

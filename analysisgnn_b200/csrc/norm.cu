@@ -57,12 +57,40 @@ __global__ void __launch_bounds__(kThreads) layernorm_fwd_kernel(const float* __
                                                                   const float* __restrict__ beta, float* __restrict__ y,
                                                                   int64_t ld_y, float* __restrict__ mean,
                                                                   float* __restrict__ rstd, int64_t rows, int cols,
-                                                                  float eps) {
+                                                                  float eps, __half* __restrict__ pair_hi,
+                                                                  __half* __restrict__ pair_lo, int64_t ld_pair,
+                                                                  float* __restrict__ pair_amax, float drop_p,
+                                                                  const uint64_t* __restrict__ rng, uint32_t rng_stream) {
   const int lane = threadIdx.x & 31;
   float g[V][4], b[V][4];
   load_row<V>(gamma, cols, lane, g);
   load_row<V>(beta, cols, lane, b);
   const float inv = 1.f / (float)cols;
+  // fp16 operand pair of the (dropped-out) output for the projection behind the norm.  Its scale must be known before
+  // the first element is written, so it comes from a BOUND instead of a measured amax: a row with zero mean and unit
+  // (biased) variance has |xhat| <= sqrt(cols - 1), hence |y| <= max|gamma| sqrt(cols - 1) + max|beta|, times 1/(1-p).
+  float f16s = 0.f;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t thr = dropout_threshold(drop_p);
+  const uint64_t key = (drop_p > 0.f && rng) ? dropout_key(rng, rng_stream) : 0ull;
+  if (pair_hi) {
+    float mg = 0.f, mb = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        mg = fmaxf(mg, fabsf(g[i][e]));
+        mb = fmaxf(mb, fabsf(b[i][e]));
+      }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, d));
+      mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, d));
+    }
+    const float bound = (mg * sqrtf((float)(cols - 1)) + mb) * keep_scale;
+    f16s = f16_scale_of(bound);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *pair_amax = bound;
+  }
   for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * kWarps) {
     float v[V][4];
     load_row<V>(x + row * ld_x, cols, lane, v);
@@ -83,7 +111,30 @@ __global__ void __launch_bounds__(kThreads) layernorm_fwd_kernel(const float* __
     for (int i = 0; i < V; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[i][e] = fmaf((v[i][e] - mu) * rs, g[i][e], b[i][e]);
-    store_row<V>(y + row * ld_y, cols, lane, v);
+    if (drop_p > 0.f) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+          const uint64_t bits = dropout_bits(key, ((uint64_t)row * cols + c) >> 2);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[i][e] = dropout_keep(bits, e, thr) ? v[i][e] * keep_scale : 0.f;
+        }
+      }
+    }
+    if (y) store_row<V>(y + row * ld_y, cols, lane, v);
+    if (pair_hi) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+          uint2 h, l;
+          f16_pair4(v[i], f16s, h, l);
+          *reinterpret_cast<uint2*>(pair_hi + row * ld_pair + c) = h;
+          *reinterpret_cast<uint2*>(pair_lo + row * ld_pair + c) = l;
+        }
+      }
+    }
     if (lane == 0) {
       mean[row] = mu;
       rstd[row] = rs;
@@ -100,9 +151,15 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const float* __
                                                                   const float* __restrict__ rstd, float* __restrict__ dx,
                                                                   int64_t ld_dx, float* __restrict__ dgamma_part,
                                                                   float* __restrict__ dbeta_part, int64_t rows,
-                                                                  int cols) {
+                                                                  int cols, float drop_p,
+                                                                  const uint64_t* __restrict__ rng, uint32_t rng_stream,
+                                                                  float* __restrict__ amax_out) {
   __shared__ float red[kWarps][32 * 4 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t thr = dropout_threshold(drop_p);
+  const uint64_t key = (drop_p > 0.f && rng) ? dropout_key(rng, rng_stream) : 0ull;
+  uint32_t mx = 0;
   float g[V][4], ag[V][4], ab[V][4];
   load_row<V>(gamma, cols, lane, g);
 #pragma unroll
@@ -114,6 +171,17 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const float* __
     float d[V][4], v[V][4];
     load_row<V>(dy + row * ld_dy, cols, lane, d);
     load_row<V>(x + row * ld_x, cols, lane, v);
+    if (drop_p > 0.f) {                                  // the forward's mask, recomputed: d(y') / d y = keep / (1 - p)
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+          const uint64_t bits = dropout_bits(key, ((uint64_t)row * cols + c) >> 2);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) d[i][e] = dropout_keep(bits, e, thr) ? d[i][e] * keep_scale : 0.f;
+        }
+      }
+    }
     const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -135,8 +203,16 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const float* __
 #pragma unroll
     for (int i = 0; i < V; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) d[i][e] = rs * (d[i][e] - s1 - v[i][e] * s2);
+      for (int e = 0; e < 4; ++e) {
+        d[i][e] = rs * (d[i][e] - s1 - v[i][e] * s2);
+        mx = max(mx, __float_as_uint(d[i][e]) & 0x7fffffffu);
+      }
     store_row<V>(dx + row * ld_dx, cols, lane, d);
+  }
+  if (amax_out) {
+#pragma unroll
+    for (int dd = 16; dd >= 1; dd >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, dd));
+    if (lane == 0 && mx) atomicMax(reinterpret_cast<unsigned int*>(amax_out), mx);
   }
   // combine the warps of the block, one 128-column slab at a time
 #pragma unroll
@@ -373,6 +449,39 @@ __global__ void __launch_bounds__(kThreads) reduce_partials_kernel(const float* 
   }
 }
 
+__global__ void dropout_advance_kernel(uint64_t* state) { state[1] += 1; }
+
+// y = keep ? x / (1 - p) : 0, mask of (rng, stream, row * cols + col); cols % 4 == 0
+__global__ void __launch_bounds__(kThreads) dropout_apply_kernel(const float* __restrict__ x, int64_t ld_x,
+                                                                  float* __restrict__ y, int64_t ld_y, int64_t rows,
+                                                                  int cols4, float drop_p,
+                                                                  const uint64_t* __restrict__ rng, uint32_t rng_stream,
+                                                                  float* __restrict__ amax_out) {
+  const float keep_scale = 1.f / (1.f - drop_p);
+  const uint32_t thr = dropout_threshold(drop_p);
+  const uint64_t key = dropout_key(rng, rng_stream);
+  const int64_t total = rows * cols4;
+  uint32_t mx = 0;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + c));
+    float v[4] = {t.x, t.y, t.z, t.w};
+    const uint64_t bits = dropout_bits(key, (uint64_t)i);          // (r * cols + c) / 4 == i
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e] = dropout_keep(bits, e, thr) ? v[e] * keep_scale : 0.f;
+      mx = max(mx, __float_as_uint(v[e]) & 0x7fffffffu);
+    }
+    *reinterpret_cast<float4*>(y + r * ld_y + c) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  if (amax_out) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(reinterpret_cast<unsigned int*>(amax_out), mx);
+  }
+}
+
 int row_blocks(int64_t rows) {
   int64_t b = ceil_div(rows, kWarps * 4);   // >= 4 rows per warp so the column partials amortise
   if (b > kNumSM * 2) b = kNumSM * 2;
@@ -409,14 +518,30 @@ extern "C" int agnn_row_blocks(int64_t rows) { return row_blocks(rows); }
 extern "C" int agnn_layernorm_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, float* y,
                                   int64_t ld_y, float* mean, float* rstd, int64_t rows, int cols, float eps,
                                   agnn_stream_t stream) {
-  int rc = check("layernorm_fwd", rows, cols, {x, gamma, beta, y}, {ld_x, ld_y});
+  if (!y) return fail(AGNN_ERR_ARG, "layernorm_fwd: null output");
+  return agnn_layernorm_fwd_pair(x, ld_x, gamma, beta, y, ld_y, mean, rstd, rows, cols, eps, nullptr, nullptr, 0, nullptr,
+                                 0.f, nullptr, 0, stream);
+}
+
+extern "C" int agnn_layernorm_fwd_pair(const float* x, int64_t ld_x, const float* gamma, const float* beta, float* y,
+                                       int64_t ld_y, float* mean, float* rstd, int64_t rows, int cols, float eps,
+                                       void* pair_hi, void* pair_lo, int64_t ld_pair, float* pair_amax, float dropout_p,
+                                       const uint64_t* rng_state, uint32_t rng_stream, agnn_stream_t stream) {
+  int rc = y ? check("layernorm_fwd", rows, cols, {x, gamma, beta, y}, {ld_x, ld_y})
+             : check("layernorm_fwd", rows, cols, {x, gamma, beta}, {ld_x});
   if (rc) return rc;
   if (!mean || !rstd) return fail(AGNN_ERR_ARG, "layernorm_fwd: null statistics pointer");
+  if (!y && !pair_hi) return fail(AGNN_ERR_ARG, "layernorm_fwd: no output requested");
+  if (pair_hi && (!pair_lo || !pair_amax || ld_pair % 8 || cols % 8 || !aligned16(pair_hi) || !aligned16(pair_lo)))
+    return fail(AGNN_ERR_ARG, "layernorm_fwd: the fp16 pair needs hi, lo, the amax scalar, 16-byte aligned rows and a "
+                              "column count that is a multiple of 8");
+  if (dropout_p < 0.f || dropout_p >= 1.f || (dropout_p > 0.f && !rng_state))
+    return fail(AGNN_ERR_ARG, "layernorm_fwd: dropout needs 0 <= p < 1 and the device RNG state");
   if (rows == 0) return AGNN_OK;
   int64_t blocks = ceil_div(rows, kWarps);
   if (blocks > kNumSM * 8) blocks = kNumSM * 8;
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(V) layernorm_fwd_kernel<V><<<(unsigned)blocks, kThreads, 0, st>>>(x, ld_x, gamma, beta, y, ld_y, mean, rstd, rows, cols, eps)
+#define CALL(V) layernorm_fwd_kernel<V><<<(unsigned)blocks, kThreads, 0, st>>>(x, ld_x, gamma, beta, y, ld_y, mean, rstd, rows, cols, eps, static_cast<__half*>(pair_hi), static_cast<__half*>(pair_lo), ld_pair, pair_amax, dropout_p, rng_state, rng_stream)
   AGNN_DISPATCH_V(cols, CALL);
 #undef CALL
   return check_launch("layernorm_fwd");
@@ -426,12 +551,24 @@ extern "C" int agnn_layernorm_bwd(const float* dy, int64_t ld_dy, const float* x
                                   const float* mean, const float* rstd, float* dx, int64_t ld_dx, float* dgamma_part,
                                   float* dbeta_part, float* dgamma, float* dbeta, int64_t rows, int cols,
                                   agnn_stream_t stream) {
+  return agnn_layernorm_bwd_dropout(dy, ld_dy, x, ld_x, gamma, mean, rstd, dx, ld_dx, dgamma_part, dbeta_part, dgamma,
+                                    dbeta, rows, cols, 0.f, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int agnn_layernorm_bwd_dropout(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x,
+                                          const float* gamma, const float* mean, const float* rstd, float* dx,
+                                          int64_t ld_dx, float* dgamma_part, float* dbeta_part, float* dgamma,
+                                          float* dbeta, int64_t rows, int cols, float dropout_p,
+                                          const uint64_t* rng_state, uint32_t rng_stream, float* amax_out,
+                                          agnn_stream_t stream) {
   int rc = check("layernorm_bwd", rows, cols, {dy, x, gamma, dx}, {ld_dy, ld_x, ld_dx});
   if (rc) return rc;
   if (!mean || !rstd || !dgamma_part || !dbeta_part) return fail(AGNN_ERR_ARG, "layernorm_bwd: null pointer");
+  if (dropout_p < 0.f || dropout_p >= 1.f || (dropout_p > 0.f && !rng_state))
+    return fail(AGNN_ERR_ARG, "layernorm_bwd: dropout needs 0 <= p < 1 and the device RNG state");
   const int blocks = row_blocks(rows);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(V) layernorm_bwd_kernel<V><<<blocks, kThreads, 0, st>>>(dy, ld_dy, x, ld_x, gamma, mean, rstd, dx, ld_dx, dgamma_part, dbeta_part, rows, cols)
+#define CALL(V) layernorm_bwd_kernel<V><<<blocks, kThreads, 0, st>>>(dy, ld_dy, x, ld_x, gamma, mean, rstd, dx, ld_dx, dgamma_part, dbeta_part, rows, cols, dropout_p, rng_state, rng_stream, amax_out)
   AGNN_DISPATCH_V(cols, CALL);
 #undef CALL
   if (dgamma && dbeta) {
@@ -442,6 +579,27 @@ extern "C" int agnn_layernorm_bwd(const float* dy, int64_t ld_dy, const float* x
                                                                                         (int64_t)blocks * cols, cols);
   }
   return check_launch("layernorm_bwd");
+}
+
+extern "C" int agnn_dropout_advance(uint64_t* rng_state, agnn_stream_t stream) {
+  if (!rng_state) return fail(AGNN_ERR_ARG, "dropout_advance: null state");
+  dropout_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng_state);
+  return check_launch("dropout_advance");
+}
+
+extern "C" int agnn_dropout_apply(const float* x, int64_t ld_x, float* y, int64_t ld_y, int64_t rows, int cols,
+                                  float dropout_p, const uint64_t* rng_state, uint32_t rng_stream, float* amax_out,
+                                  agnn_stream_t stream) {
+  if (rows < 0 || cols < 4 || cols % 4 || ld_x % 4 || ld_y % 4 || !x || !y || !aligned16(x) || !aligned16(y))
+    return fail(AGNN_ERR_ARG, "dropout_apply: needs 16-byte aligned rows and a column count multiple of 4");
+  if (dropout_p <= 0.f || dropout_p >= 1.f || !rng_state)
+    return fail(AGNN_ERR_ARG, "dropout_apply: needs 0 < p < 1 and the device RNG state");
+  if (rows == 0) return AGNN_OK;
+  int64_t blocks = ceil_div(rows * (cols / 4), kThreads);
+  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  dropout_apply_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, ld_x, y, ld_y, rows, cols / 4, dropout_p,
+                                                                                rng_state, rng_stream, amax_out);
+  return check_launch("dropout_apply");
 }
 
 extern "C" int agnn_l2norm_relu_fwd(const float* x, int64_t ld_x, float* y, int64_t ld_y, float* inv_norm, int64_t rows,

@@ -139,24 +139,91 @@ def amax_into(amax: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return amax
 
 
+def tag_amax(t: torch.Tensor, amax: Optional[torch.Tensor]) -> torch.Tensor:
+    """Remember that ``amax`` (device scalar) bounds ``max |t|`` -- written by the kernel that produced ``t`` (GEMM /
+    gather / LayerNorm-backward epilogues) -- so that a consumer needing the fp16 operand scale of ``t`` does not pass
+    over it again.  The tag dies with any in-place modification of ``t`` (version check in ``known_amax``)."""
+    if amax is not None:
+        t._agnn_amax = (amax, t._version)
+    return t
+
+
+def known_amax(t) -> Optional[torch.Tensor]:
+    rec = getattr(t, "_agnn_amax", None) if isinstance(t, torch.Tensor) else None
+    if rec is not None and rec[1] == t._version:
+        return rec[0]
+    return None
+
+
+_const_scalars = {}
+
+
+def const_amax(device, value: float) -> torch.Tensor:
+    """A device scalar holding a known bound (e.g. 1.0 for GRU states, |h| <= 1)."""
+    device = torch.device(device)
+    key = (torch.cuda.current_device() if device.index is None else device.index, float(value))
+    t = _const_scalars.get(key)
+    if t is None:
+        t = _const_scalars[key] = torch.full((1,), float(value), dtype=torch.float32, device=device)
+    return t
+
+
+def amax_of(t: torch.Tensor) -> torch.Tensor:
+    """The tagged amax of ``t`` if its producer left one, else one agnn_amax pass."""
+    am = known_amax(t)
+    if am is None:
+        stats["amax_passes"] = stats.get("amax_passes", 0) + 1
+        am = amax_into(new_amax(t.device), t)
+    return am
+
+
+# ---- counter-based dropout (csrc/common.cuh): device state {seed, step} per device, call-site ids per step
+_dropout_states = {}
+_dropout_calls = [0]
+
+
+def dropout_state(device) -> torch.Tensor:
+    device = torch.device(device)
+    idx = torch.cuda.current_device() if device.index is None else device.index
+    st = _dropout_states.get(idx)
+    if st is None:
+        seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        st = _dropout_states[idx] = torch.tensor([seed, 0], dtype=torch.int64, device=torch.device("cuda", idx))
+    return st
+
+
+def dropout_site() -> int:
+    """A fresh call-site id for a fused dropout (ids restart with every ``begin_step``, so a captured step and its
+    replays use the same ids while the device-side step counter changes the masks)."""
+    _dropout_calls[0] += 1
+    return _dropout_calls[0]
+
+
 def f16_ok(x: torch.Tensor) -> bool:
     return (x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 8 == 0
             and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.shape[0] > 0)
 
 
-def split_f16(x: torch.Tensor, amax: Optional[torch.Tensor] = None) -> SplitH:
-    """hi = fp16(s x), lo = fp16(s x - hi); ``amax`` (device scalar >= max |x| / 4) is measured when not given."""
+def split_f16(x: torch.Tensor, amax: Optional[torch.Tensor] = None, dropout=None) -> SplitH:
+    """hi = fp16(s x), lo = fp16(s x - hi); ``amax`` (device scalar >= max |x| / 4) is the producer's tag or measured
+    when not given.  ``dropout = (p, site)``: the pair of the dropped-out matrix (counter-based mask, 1 / (1 - p)
+    scaling; p < 0.75 keeps the result inside the scale's 4x headroom)."""
     _need_cuda(x)
     if not f16_ok(x):
         raise ValueError("split_f16 needs an fp32 matrix with unit column stride, 16-byte aligned rows and a column "
                          "count that is a multiple of 8")
     if amax is None:
-        amax = amax_into(new_amax(x.device), x)
+        amax = amax_of(x)
     rows, cols = x.shape
     buf = torch.empty((2, rows, cols), dtype=torch.float16, device=x.device)
     stream = torch.cuda.current_stream(x.device).cuda_stream
-    _lib.check(_lib.lib().agnn_split_f16(x.data_ptr(), rows, cols, x.stride(0), amax.data_ptr(), buf[0].data_ptr(),
-                                         buf[1].data_ptr(), cols, stream), "agnn_split_f16")
+    p, site = dropout if dropout is not None else (0.0, 0)
+    if p >= 0.75:
+        raise ValueError("fused dropout supports p < 0.75")
+    _lib.check(_lib.lib().agnn_split_f16_dropout(x.data_ptr(), rows, cols, x.stride(0), amax.data_ptr(),
+                                                 buf[0].data_ptr(), buf[1].data_ptr(), cols, float(p),
+                                                 dropout_state(x.device).data_ptr() if p > 0 else None, int(site),
+                                                 stream), "agnn_split_f16")
     _lib.count_launches(1)
     return SplitH(buf[0], buf[1], amax)
 
@@ -221,6 +288,12 @@ def begin_step() -> None:
     forward)."""
     _split_cache.clear()
     _amax_pools.clear()
+    _dropout_calls[0] = 0
+    for st in _dropout_states.values():        # new masks for the new step (inside a captured step: on every replay)
+        with torch.cuda.device(st.device):
+            _lib.check(_lib.lib().agnn_dropout_advance(st.data_ptr(), torch.cuda.current_stream(st.device).cuda_stream),
+                       "agnn_dropout_advance")
+        _lib.count_launches(1)
 
 
 _SPLIT_CACHE_MAX_ENTRIES = 512     # a step makes a few dozen; the cap only matters to callers that never call begin_step
@@ -281,10 +354,27 @@ def plain(x: Operand) -> torch.Tensor:
 _plain = plain
 
 
-def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, k: int, bias, flags: int,
-          out: Optional[torch.Tensor], split_k: Optional[int] = None) -> Optional[torch.Tensor]:
-    """agnn_gemm wrapper; returns None if the operands are not eligible as they are (``_repacked`` then copies
-    them into padded buffers)."""
+_ticket_pools = {}       # (device, stream) -> zeroed int32 counters for the in-kernel split-K reduction
+_TICKETS = 16384
+
+
+def _tickets(dev) -> torch.Tensor:
+    """Per-stream ticket counters (agnn_gemm_grouped): zero before every launch and zero again after it, so launches
+    that are ordered on one stream share one array."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    t = _ticket_pools.get(key)
+    if t is None:
+        t = _ticket_pools[key] = torch.zeros(_TICKETS, dtype=torch.int32, device=dev)
+    return t
+
+
+class _Problem:
+    """One contraction of a (possibly grouped) launch, operands already in the form agnn_gemm reads."""
+    __slots__ = ("oa", "ob", "m", "n", "k", "bias", "flags", "out", "split_k", "ws", "ws_bytes", "amax_out")
+
+
+def _resolve(a: Operand, b: Operand, m: int, n: int, k: int, bias, flags: int, out, split_k, amax_out):
+    """-> (precision, _Problem) or None if the operands cannot be read as they are."""
     f16 = isinstance(a, SplitH) or isinstance(b, SplitH)
     oa, ob = _as_operand(a, f16), _as_operand(b, f16)
     if oa is None or ob is None or oa[2] != ob[2]:
@@ -300,36 +390,115 @@ def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, 
         return None
     if prec == _lib.GEMM_BF16:
         flags |= _lib.GEMM_OUT_BF16
-    if bias is not None:
-        bias = bias.float().contiguous()
+    p = _Problem()
+    p.oa, p.ob, p.m, p.n, p.k, p.flags, p.out, p.amax_out = oa, ob, m, n, k, flags, out, amax_out
+    p.bias = bias.float().contiguous() if bias is not None else None
     lib = _lib.lib()
-    if split_k is None:
-        split_k = lib.agnn_gemm_split_k(prec, m, n, k)
-    ws_bytes = lib.agnn_gemm_workspace(prec, m, n, k, split_k)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    p.split_k = lib.agnn_gemm_split_k(prec, m, n, k) if split_k is None else split_k
+    p.ws_bytes = lib.agnn_gemm_workspace(prec, m, n, k, p.split_k)
+    p.ws = torch.empty(p.ws_bytes, dtype=torch.uint8, device=dev) if p.ws_bytes else None
+    return prec, p
 
-    def run():
-        if prec == _lib.GEMM_F16X3:
-            _lib.check(lib.agnn_gemm_scaled(prec, a_layout, b_layout, m, n, k, oa[0].data_ptr(), oa[1].data_ptr(),
-                                            oa[0].stride(0), oa[3].data_ptr(), ob[0].data_ptr(), ob[1].data_ptr(),
-                                            ob[0].stride(0), ob[3].data_ptr(), out.data_ptr(), out.stride(0),
-                                            bias.data_ptr() if bias is not None else None, flags, split_k,
-                                            ws.data_ptr() if ws is not None else None, ws_bytes, stream),
-                       "agnn_gemm_scaled")
-            return
-        _lib.check(lib.agnn_gemm(prec, a_layout, b_layout, m, n, k, oa[0].data_ptr(),
-                                 oa[1].data_ptr() if oa[1] is not None else None, oa[0].stride(0), ob[0].data_ptr(),
-                                 ob[1].data_ptr() if ob[1] is not None else None, ob[0].stride(0), out.data_ptr(),
-                                 out.stride(0), bias.data_ptr() if bias is not None else None, flags, split_k,
-                                 ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gemm")
 
-    if timer is not None:                       # bench.py: per-launch CUDA events, algorithmic flops = 2 M N K
-        timer.launch("gemm", 2 * m * n * k, dev, run, tag=(a_layout, b_layout, m, n, k, split_k))
-    else:
-        run()
-    _lib.count_launches(2 if split_k > 1 else 1)
-    return out
+def _launch(prec: int, a_layout: int, b_layout: int, problems) -> None:
+    """One agnn_gemm_grouped launch per AGNN_GEMM_MAX_GROUP problems of one precision / layout combination."""
+    lib = _lib.lib()
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    for lo in range(0, len(problems), _lib.GEMM_MAX_GROUP):
+        chunk = [p for p in problems[lo:lo + _lib.GEMM_MAX_GROUP] if p.m > 0 and p.n > 0]
+        if not chunk:
+            continue
+        dev = chunk[0].oa[0].device
+        arr = (_lib.GemmProblem * len(chunk))()
+        need = 0
+        for q, p in zip(arr, chunk):
+            q.M, q.N, q.K = p.m, p.n, p.k
+            q.a_hi, q.a_lo, q.lda, q.amax_a = ptr(p.oa[0]), ptr(p.oa[1]), p.oa[0].stride(0), ptr(p.oa[3])
+            q.b_hi, q.b_lo, q.ldb, q.amax_b = ptr(p.ob[0]), ptr(p.ob[1]), p.ob[0].stride(0), ptr(p.ob[3])
+            q.c, q.ldc, q.bias, q.flags, q.split_k = p.out.data_ptr(), p.out.stride(0), ptr(p.bias), p.flags, p.split_k
+            q.workspace, q.workspace_bytes, q.amax_out = ptr(p.ws), p.ws_bytes, ptr(p.amax_out)
+            need += lib.agnn_gemm_tickets(p.m, p.n, p.split_k)
+        tickets = _tickets(dev) if 0 < need <= _TICKETS else None      # None: the two-kernel split-K reduction
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def run():
+            _lib.check(lib.agnn_gemm_grouped(prec, a_layout, b_layout, len(chunk), arr, ptr(tickets),
+                                             tickets.numel() if tickets is not None else 0, stream), "agnn_gemm_grouped")
+
+        if timer is not None:                   # bench.py: per-launch CUDA events, algorithmic flops = 2 M N K
+            flops = sum(2 * p.m * p.n * p.k for p in chunk)
+            big = max(chunk, key=lambda p: p.m * p.n * p.k)
+            timer.launch("gemm", flops, dev, run, tag=(a_layout, b_layout, big.m, big.n, big.k, big.split_k, len(chunk)))
+        else:
+            run()
+        extra = 0 if tickets is not None or need == 0 else sum(1 for p in chunk if p.split_k > 1)
+        _lib.count_launches(1 + extra)
+        stats["gemm_launches"] = stats.get("gemm_launches", 0) + 1
+        stats["gemm_problems"] = stats.get("gemm_problems", 0) + len(chunk)
+
+
+def _gemm(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: int, k: int, bias, flags: int,
+          out: Optional[torch.Tensor], split_k: Optional[int] = None, amax_out=None) -> Optional[torch.Tensor]:
+    """One contraction on agnn_gemm_grouped; returns None if the operands are not eligible as they are
+    (``_repacked`` then copies them into padded buffers)."""
+    r = _resolve(a, b, m, n, k, bias, flags, out, split_k, amax_out)
+    if r is None:
+        return None
+    _launch(r[0], a_layout, b_layout, [r[1]])
+    return r[1].out
+
+
+def _group(a_layout: int, b_layout: int, specs):
+    """``specs``: list of dicts(a, b, m, n, k, bias, flags, out, amax_out).  Independent contractions of one layout
+    combination in as few launches as their precisions allow (one per precision, AGNN_GEMM_MAX_GROUP problems each);
+    problems whose operands need a repack run alone.  Returns the outputs in order."""
+    outs = [None] * len(specs)
+    by_prec = {}
+    for i, sp in enumerate(specs):
+        r = _resolve(sp["a"], sp["b"], sp["m"], sp["n"], sp["k"], sp.get("bias"), sp.get("flags", 0), sp.get("out"),
+                     None, sp.get("amax_out"))
+        if r is None:
+            outs[i] = _repacked(sp["a"], a_layout, sp["b"], b_layout, sp["m"], sp["n"], sp["k"], sp.get("bias"),
+                                sp.get("flags", 0), sp.get("out"))
+            if sp.get("amax_out") is not None:
+                amax_into(sp["amax_out"], outs[i])
+            continue
+        by_prec.setdefault(r[0], []).append((i, r[1]))
+    for prec, items in by_prec.items():
+        _launch(prec, a_layout, b_layout, [p for _, p in items])
+        for i, p in items:
+            outs[i] = p.out
+    return outs
+
+
+def linear_group(xs, weights, biases=None, relu: bool = False, amax_outs=None, outs=None):
+    """``[x_i @ w_i.T + b_i]`` for independent projections (per node type, per task head, per GRU direction) in one
+    grouped launch."""
+    biases = biases if biases is not None else [None] * len(xs)
+    amax_outs = amax_outs if amax_outs is not None else [None] * len(xs)
+    outs = outs if outs is not None else [None] * len(xs)
+    flags = _lib.GEMM_RELU if relu else 0
+    for x in xs:
+        _need_cuda(x if isinstance(x, torch.Tensor) else x.hi)
+    return _group(_lib.K_MAJOR, _lib.K_MAJOR,
+                  [dict(a=x, b=w, m=x.shape[0], n=w.shape[0], k=x.shape[1], bias=bb, flags=flags, out=o, amax_out=am)
+                   for x, w, bb, am, o in zip(xs, weights, biases, amax_outs, outs)])
+
+
+def mm_group(as_, bs, outs=None, accumulate: bool = False, amax_outs=None):
+    """``[a_i @ b_i]`` with ``b_i`` stored [K, N] (grad-input products of independent projections)."""
+    outs = outs if outs is not None else [None] * len(as_)
+    amax_outs = amax_outs if amax_outs is not None else [None] * len(as_)
+    flags = _lib.GEMM_ACCUMULATE if accumulate else 0
+    return _group(_lib.K_MAJOR, _lib.MN_MAJOR,
+                  [dict(a=a, b=b, m=a.shape[0], n=b.shape[1], k=a.shape[1], flags=flags, out=o, amax_out=am)
+                   for a, b, o, am in zip(as_, bs, outs, amax_outs)])
+
+
+def mm_tn_group(as_, bs):
+    """``[a_i.T @ b_i]`` (grad-weight products of independent projections; split-K inside the launch)."""
+    return _group(_lib.MN_MAJOR, _lib.MN_MAJOR,
+                  [dict(a=a, b=b, m=a.shape[1], n=b.shape[1], k=a.shape[0]) for a, b in zip(as_, bs)])
 
 
 def _pad2(t: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
@@ -371,33 +540,22 @@ def _repacked(a: Operand, a_layout: int, b: Operand, b_layout: int, m: int, n: i
     return out.copy_(y)
 
 
-def linear(x: Operand, weight: Operand, bias=None, relu: bool = False):
-    """``x @ weight.T + bias`` (optionally ReLU'd), ``weight`` [out, in]."""
-    _need_cuda(x if isinstance(x, torch.Tensor) else x.hi)
-    m, k = x.shape
-    n = weight.shape[0]
-    flags = _lib.GEMM_RELU if relu else 0
-    y = _gemm(x, _lib.K_MAJOR, weight, _lib.K_MAJOR, m, n, k, bias, flags, None)
-    return y if y is not None else _repacked(x, _lib.K_MAJOR, weight, _lib.K_MAJOR, m, n, k, bias, flags, None)
+def linear(x: Operand, weight: Operand, bias=None, relu: bool = False, amax_out=None, out=None):
+    """``x @ weight.T + bias`` (optionally ReLU'd), ``weight`` [out, in].  ``amax_out``: device scalar that receives
+    ``max(amax_out, max |y|)`` from the GEMM epilogue; ``out``: write into this view (e.g. a column slice)."""
+    return linear_group([x], [weight], [bias], relu, [amax_out], [out])[0]
 
 
-def mm(a: Operand, b: Operand, out=None, accumulate: bool = False):
+def mm(a: Operand, b: Operand, out=None, accumulate: bool = False, amax_out=None):
     """``a @ b`` with ``b`` stored [K, N]; with ``out`` and ``accumulate`` adds into ``out`` in place."""
     _need_cuda(a if isinstance(a, torch.Tensor) else a.hi)
-    m, k = a.shape
-    n = b.shape[1]
-    flags = _lib.GEMM_ACCUMULATE if accumulate else 0
-    y = _gemm(a, _lib.K_MAJOR, b, _lib.MN_MAJOR, m, n, k, None, flags, out)
-    return y if y is not None else _repacked(a, _lib.K_MAJOR, b, _lib.MN_MAJOR, m, n, k, None, flags, out)
+    return mm_group([a], [b], [out], accumulate, [amax_out])[0]
 
 
 def mm_tn(a: Operand, b: Operand):
     """``a.T @ b`` (weight gradients): ``a`` [R, M], ``b`` [R, N], reduction over the R rows (split-K)."""
     _need_cuda(a if isinstance(a, torch.Tensor) else a.hi)
-    r, m = a.shape
-    n = b.shape[1]
-    y = _gemm(a, _lib.MN_MAJOR, b, _lib.MN_MAJOR, m, n, r, None, 0, None)
-    return y if y is not None else _repacked(a, _lib.MN_MAJOR, b, _lib.MN_MAJOR, m, n, r, None, 0, None)
+    return mm_tn_group([a], [b])[0]
 
 
 def relu_backward(grad, out):

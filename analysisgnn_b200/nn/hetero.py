@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import graph, ops
-from .layers import GRU, LayerNorm, Linear
+from .layers import GRU, MLP, LayerNorm, Linear
 
 EdgeType = Tuple[str, str, str]
 
@@ -324,16 +324,17 @@ class SequenceBranch(nn.Module):
         self.rnn = GRU(input_size=in_channels, hidden_size=hidden_channels // 2, num_layers=2,
                           batch_first=True, bidirectional=True, dropout=dropout)
         self.rnn_norm = LayerNorm(hidden_channels)
-        self.rnn_mlp = nn.Sequential(
+        self.rnn_mlp = MLP(
             Linear(hidden_channels, hidden_channels), nn.ReLU(), LayerNorm(hidden_channels),
             nn.Dropout(dropout), Linear(hidden_channels, hidden_channels))
 
     def forward(self, x, batch):
+        from .. import linalg
         layout = graph.batch_layout(batch)
-        seq = layout.pad(x)
+        seq = linalg.tag_amax(layout.pad(x), linalg.known_amax(x))
         seq = self.rnn(seq)[0]
-        seq = self.rnn_mlp(self.rnn_norm(seq))
-        return layout.unpad(seq)
+        seq = self.rnn_mlp(seq, pre_norm=self.rnn_norm)          # LayerNorm fused into the first projection's operand
+        return linalg.tag_amax(layout.unpad(seq), linalg.known_amax(seq))
 
 
 class JumpingKnowledge(nn.Module):
@@ -424,7 +425,7 @@ class MetricalGNN(nn.Module):
                  use_jk=False, fast=True):
         super().__init__()
         self.gnn = HeteroSAGEStack(metadata[1], input_channels, hidden_channels, num_layers)
-        self.mlp = nn.Sequential(
+        self.mlp = MLP(
             Linear(hidden_channels, hidden_channels), nn.ReLU(), LayerNorm(hidden_channels),
             nn.Dropout(dropout), Linear(hidden_channels, output_channels))
 

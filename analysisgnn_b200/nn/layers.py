@@ -21,6 +21,64 @@ class LayerNorm(nn.LayerNorm):
         return ops.layer_norm(x, self.weight, self.bias, self.eps)
 
 
+class MLP(nn.Sequential):
+    """``nn.Sequential`` of Linear / ReLU / LayerNorm / Dropout modules (same children, same ``state_dict`` keys) whose
+    forward runs as fused projection stages ``[LayerNorm ->] [Dropout ->] Linear [-> ReLU]`` (fused.stage_group): the
+    reference's project_dict / project_enc / clf_dict / sequence-MLP blocks (analysisgnn/models/analysis.py:429-443,
+    474-496; models/cadence.py:252-260).  ``forward_group`` runs several structurally identical MLPs (one per node
+    type, one per task head) stage by stage with ONE grouped GEMM launch per stage and direction.  Sequences that are
+    not made of such stages run module by module."""
+
+    def stages(self, pre_norm=None):
+        """[(LayerNorm or None, dropout p, Linear, relu)] or None if the children do not parse into stages."""
+        out, norm, p = [], pre_norm, 0.0
+        mods = list(self.children())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.LayerNorm) and norm is None and p == 0.0 and len(m.normalized_shape) == 1 \
+                    and m.elementwise_affine and m.bias is not None:
+                norm = m
+            elif isinstance(m, nn.Dropout) and p == 0.0:
+                p = m.p
+            elif isinstance(m, nn.Linear):
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                out.append((norm, p, m, relu))
+                norm, p = None, 0.0
+                i += 1 if relu else 0
+            else:
+                return None
+            i += 1
+        return out if norm is None and p == 0.0 else None
+
+    def forward(self, x, pre_norm=None):
+        return MLP.forward_group([self], [x], pre_norms=[pre_norm])[0]
+
+    @staticmethod
+    def forward_group(mlps, xs, pre_norms=None, share_amax=False):
+        from .. import fused
+        pre_norms = pre_norms if pre_norms is not None else [None] * len(mlps)
+        plans = [m.stages(pn) for m, pn in zip(mlps, pre_norms)]
+        same = all(pl is not None and len(pl) == len(plans[0]) and
+                   [(s[0] is None, s[1], s[3]) for s in pl] == [(s[0] is None, s[1], s[3]) for s in plans[0]]
+                   for pl in plans) if plans and plans[0] is not None else False
+        if not same or not all(x.is_cuda for x in xs):
+            outs = []
+            for m, x, pn in zip(mlps, xs, pre_norms):
+                x = pn(x) if pn is not None else x
+                outs.append(nn.Sequential.forward(m, x))
+            return outs
+        xs = list(xs)
+        training = mlps[0].training
+        for k in range(len(plans[0])):
+            st = [pl[k] for pl in plans]
+            norms = [None if s[0] is None else (s[0].weight, s[0].bias, s[0].eps) for s in st]
+            xs = fused.stage_group(xs, [s[2].weight for s in st], [s[2].bias for s in st], norms, relu=st[0][3],
+                                   dropout=st[0][1], training=training,
+                                   share_amax=share_amax and k == len(plans[0]) - 1)
+        return xs
+
+
 class GRU(nn.GRU):
     """``nn.GRU`` (same parameters / ``state_dict``): batch-first fp32 CUDA inputs with hidden size 32, 64 or
     128 run on libagnn (tensor-core GEMMs for every projection + agnn_gru_fwd / _bwd for the recurrence);
@@ -45,10 +103,12 @@ class GRU(nn.GRU):
                 else:
                     b_ih = b_hh = torch.zeros(3 * self.hidden_size, dtype=x.dtype, device=x.device)
                 params += [w_ih, w_hh, b_ih, b_hh]
-            x = ops.gru_layer(x, params)
+            drop = None
+            if layer > 0 and self.dropout > 0 and self.training:
+                from .. import linalg
+                drop = (float(self.dropout), linalg.dropout_site())   # nn.GRU: dropout on the outputs of every layer
+            x = ops.gru_layer(x, params, dropout=drop)                # but the last = on the inputs of layers >= 1
             h_n.append(x[:, -1, :self.hidden_size])
             if n_dir == 2:
                 h_n.append(x[:, 0, self.hidden_size:])
-            if self.dropout > 0 and self.training and layer < self.num_layers - 1:
-                x = F.dropout(x, self.dropout, True)
         return x, torch.stack(h_n, dim=0)

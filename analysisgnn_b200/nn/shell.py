@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import graph, ops
-from .layers import LayerNorm, Linear
+from .layers import MLP, LayerNorm, Linear
 from .hetero import HybridGNN, HybridHGT, MetricalGNN
 
 ONSET = ("note", "onset", "note")
@@ -52,8 +52,8 @@ class AnalysisEncoder(nn.Module):
         self.hidden_channels = hidden_channels
 
         def mlp(cin):
-            return nn.Sequential(Linear(cin, hidden_channels), nn.ReLU(), LayerNorm(hidden_channels),
-                                 nn.Dropout(dropout), Linear(hidden_channels, hidden_channels))
+            return MLP(Linear(cin, hidden_channels), nn.ReLU(), LayerNorm(hidden_channels),
+                       nn.Dropout(dropout), Linear(hidden_channels, hidden_channels))
 
         self.project_dict = nn.ModuleDict({k: mlp(in_channels + 128 if k == "note" else in_channels)
                                            for k in metadata[0]})
@@ -72,13 +72,13 @@ class AnalysisEncoder(nn.Module):
         else:
             raise ValueError(f"unknown encoder_type {encoder_type!r}")
         self.encoder_type = encoder_type
-        self.project_enc = nn.Sequential(
+        self.project_enc = MLP(
             LayerNorm(2 * hidden_channels), Linear(2 * hidden_channels, hidden_channels), nn.ReLU(),
             LayerNorm(hidden_channels), nn.Dropout(dropout), Linear(hidden_channels, out_channels), nn.ReLU(),
             LayerNorm(out_channels), nn.Dropout(dropout), Linear(out_channels, out_channels))
         self.clf_dict = nn.ModuleDict({
-            task: nn.Sequential(Linear(out_channels, out_channels // 2), nn.ReLU(),
-                                LayerNorm(out_channels // 2), Linear(out_channels // 2, n_cls))
+            task: MLP(Linear(out_channels, out_channels // 2), nn.ReLU(),
+                      LayerNorm(out_channels // 2), Linear(out_channels // 2, n_cls))
             for task, n_cls in task_dict.items()})
 
     def encode(self, pitch_spelling, key_signature, x_dict, edge_index_dict, batch_dict, batch_size,
@@ -86,7 +86,11 @@ class AnalysisEncoder(nn.Module):
         z = dict(x_dict)
         z["note"] = torch.cat((x_dict["note"], ops.embedding(pitch_spelling, self.pitch_embedding.weight),
                                ops.embedding(key_signature, self.key_embedding.weight)), dim=-1)
-        h = {k: self.project_dict[k](z[k]) for k in self.project_dict.keys()}
+        # the per-node-type projections run stage by stage as ONE grouped launch each; their outputs share one
+        # operand scale (the inputs of the first message-passing layer)
+        keys = list(self.project_dict.keys())
+        h = dict(zip(keys, MLP.forward_group([self.project_dict[k] for k in keys], [z[k] for k in keys],
+                                             share_amax=True)))
         x = self.encoder(x_dict=h, edge_index_dict=edge_index_dict, batch_dict=batch_dict, batch_size=batch_size,
                          neighbor_mask_node=neighbor_mask_node, neighbor_mask_edge=neighbor_mask_edge,
                          return_edge_index=False, edge_attr_dict=None)
@@ -96,8 +100,9 @@ class AnalysisEncoder(nn.Module):
         return self.project_enc(torch.cat((x, pooled), dim=-1))
 
     def forward_clf(self, x, tasks=None):
-        tasks = self.clf_dict.keys() if tasks is None else tasks
-        return {t: self.clf_dict[t](x) for t in tasks}
+        tasks = list(self.clf_dict.keys() if tasks is None else tasks)
+        # all task heads stage by stage: one grouped launch per stage and direction instead of one chain per task
+        return dict(zip(tasks, MLP.forward_group([self.clf_dict[t] for t in tasks], [x] * len(tasks))))
 
     def clf_task(self, x, task_name):
         return self.clf_dict[task_name](x)

@@ -137,7 +137,7 @@ def gather_bytes(rels: Sequence[Rel], n_rows: int, n_feat: int, elem: int, conca
 def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: bool, concat: bool,
                   self_add: Optional[torch.Tensor] = None, copy: Optional[torch.Tensor] = None,
                   copy_col: int = 0, out_lo: Optional[torch.Tensor] = None,
-                  pair_amax: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  pair_amax: Optional[torch.Tensor] = None, amax_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """agnn_gather_reduce on ``out`` ([n_rows, >= n_feat] view).  See include/agnn.h.  With ``out_lo``
     the result is written as the TF32 hi / lo pair (``out``, ``out_lo``) that ``agnn_gemm`` consumes; with
     ``pair_amax`` too, ``out`` / ``out_lo`` are fp16 and receive the F16X3 pair (agnn_gather_reduce_f16)."""
@@ -170,12 +170,13 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
                 out.data_ptr(), out.stride(0), out_lo.data_ptr(), pair_amax.data_ptr(),
                 ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gather_reduce_f16")
             return
-        _lib.check(_lib.lib().agnn_gather_reduce(
+        _lib.check(_lib.lib().agnn_gather_reduce_amax(
             n_rows, n_feat, _dtype_code(out), _lib.SCALE_MEAN if mean else _lib.SCALE_NONE,
             _lib.COMBINE_CONCAT if concat else _lib.COMBINE_SUM, len(rels), arr,
             sa.data_ptr() if sa is not None else None, sa.stride(0) if sa is not None else 0,
             cp.data_ptr() if cp is not None else None, cp.stride(0) if cp is not None else 0, int(copy_col),
-            out.data_ptr(), out.stride(0), out_lo.data_ptr() if out_lo is not None else None,
+            out.data_ptr(), out.stride(0), out_lo.data_ptr() if out_lo is not None else None, None,
+            amax_out.data_ptr() if amax_out is not None else None,
             ws.data_ptr() if ws is not None else None, ws_bytes, stream), "agnn_gather_reduce")
 
     if timer is not None and all(r.n_edges is not None for r in rels):
@@ -369,24 +370,33 @@ class _HeteroSageLayer(torch.autograd.Function):
         A_t = [x_t || mean_{r_1}(x_src) || .. || mean_{r_k}(x_src)]    (one gather launch)
         out_t = A_t [sum_r Wr_r | Wl_1 | .. | Wl_k]^T + sum_r b_r      (one GEMM)
 
-    argument layout: (plan, csr, relu, *tensors) with tensors = x per node type
-    (plan.node_types order), then (Wcat_t, b_t) per destination type.
+    The GEMMs of all destination types (and, backwards, their grad-input and grad-weight products) are ONE grouped
+    launch each.  The forward GEMM epilogue reports max |out| over all types into ``box["out_amax"]`` -- the next
+    layer's operand scale -- and the backward gathers report max |d x|.
+
+    argument layout: (plan, csr, relu, box, *tensors) with tensors = x per node type
+    (plan.node_types order), then (Wcat_t, b_t) per destination type; ``box`` = {"x_amax": tagged scalar or None}.
     """
 
     @staticmethod
-    def forward(ctx, plan, csr: HeteroCSR, relu: bool, *tensors):
+    def forward(ctx, plan, csr: HeteroCSR, relu: bool, box: dict, *tensors):
         nt = len(plan.node_types)
         xs = {t: tensors[i].contiguous() for i, t in enumerate(plan.node_types)}
-        outs, saved = [], []
         # F16X3 operands: every aggregated row is a copy or a mean of input rows, so the amax over the layer's inputs
         # bounds every operand the gather writes -- one scalar for all destination types
         f16 = (linalg.parity_operands() == "f16"
                and all(v.dtype == torch.float32 and v.shape[1] % 8 == 0 for v in xs.values()))
         x_amax = None
         if f16:
-            x_amax = linalg.new_amax(tensors[0].device)
-            for v in xs.values():
-                linalg.amax_into(x_amax, v)
+            x_amax = box.get("x_amax")                     # the producer's epilogue already measured it
+            if x_amax is None:
+                x_amax = linalg.new_amax(tensors[0].device)
+                for v in xs.values():
+                    linalg.stats["amax_passes"] = linalg.stats.get("amax_passes", 0) + 1
+                    linalg.amax_into(x_amax, v)
+        out_amax = linalg.new_amax(tensors[0].device) if f16 else None
+        box["out_amax"] = out_amax
+        operands, specs, saved = [], [], []
         for j, t in enumerate(plan.dst_types):
             wcat, bias = tensors[nt + 2 * j], tensors[nt + 2 * j + 1]
             x_t = xs[t]
@@ -403,9 +413,13 @@ class _HeteroSageLayer(torch.autograd.Function):
                 a_hi, a_lo = _operand_buffers(x_t.shape[0], (len(rel_list) + 1) * f, x_t)
                 gather_reduce(rels, a_hi, f, mean=True, concat=True, copy=x_t, copy_col=0, out_lo=a_lo)
                 a = _as_operand_pair(a_hi, a_lo)
-            o = linalg.linear(a, wcat, bias, relu=relu)
-            outs.append(o)
-            saved += [*linalg.pack(a), wcat, o]
+            operands.append(a)
+            specs.append(dict(a=a, b=wcat, m=x_t.shape[0], n=wcat.shape[0], k=(len(rel_list) + 1) * f, bias=bias,
+                              flags=_lib.GEMM_RELU if relu else 0,
+                              amax_out=out_amax if isinstance(a, linalg.SplitH) else None))
+        outs = linalg._group(_lib.K_MAJOR, _lib.K_MAJOR, specs)
+        for a, sp, o in zip(operands, specs, outs):
+            saved += [*linalg.pack(a), sp["b"], o]
         ctx.save_for_backward(*saved)
         ctx.x_amax = x_amax
         ctx.set_materialize_grads(False)        # an unused destination type costs nothing in backward
@@ -418,22 +432,31 @@ class _HeteroSageLayer(torch.autograd.Function):
     def backward(ctx, *douts):
         plan, csr = ctx.plan, ctx.csr
         nt = len(plan.node_types)
+        base = 4                                 # plan, csr, relu, box precede the tensors
         grads = [None] * (nt + 2 * len(plan.dst_types))
-        da = {}
+        act, gs_list, a_list, w_list = [], [], [], []
         for j, t in enumerate(plan.dst_types):
             a_first, a_second, wcat, o = ctx.saved_tensors[4 * j:4 * j + 4]
-            a = linalg.unpack(a_first, a_second, ctx.x_amax)
             g = douts[j]
-            if g is None:
+            if g is None or g.shape[0] == 0:
                 continue
-            g, db = prepare_grad(g, o if ctx.relu else None, ctx.needs_input_grad[3 + nt + 2 * j + 1],
+            a = linalg.unpack(a_first, a_second, ctx.x_amax)
+            g, db = prepare_grad(g, o if ctx.relu else None, ctx.needs_input_grad[base + nt + 2 * j + 1],
                                  f16=isinstance(a, linalg.SplitH))
             grads[nt + 2 * j + 1] = db
-            da[t] = linalg.mm(g, wcat)
-            if ctx.needs_input_grad[3 + nt + 2 * j]:
-                grads[nt + 2 * j] = linalg.mm_tn(g, a)
+            act.append((j, t))
+            gs_list.append(g)
+            a_list.append(a)
+            w_list.append(wcat)
+        # grad-input and grad-weight products of all destination types: one grouped launch each
+        das = linalg.mm_group(gs_list, w_list) if act else []
+        da = {t: d for (j, t), d in zip(act, das)}
+        sel = [i for i, (j, t) in enumerate(act) if ctx.needs_input_grad[base + nt + 2 * j]]
+        dws = linalg.mm_tn_group([gs_list[i] for i in sel], [a_list[i] for i in sel]) if sel else []
+        for i, dw in zip(sel, dws):
+            grads[nt + 2 * act[i][0]] = dw
         for i, s in enumerate(plan.node_types):
-            if not ctx.needs_input_grad[3 + i]:
+            if not ctx.needs_input_grad[base + i]:
                 continue
             f = ctx.feat[s]
             rels = []
@@ -449,13 +472,21 @@ class _HeteroSageLayer(torch.autograd.Function):
                 grads[i] = root.contiguous() if root is not None else None
                 continue
             dx = torch.empty((ctx.rows[s], f), dtype=rels[0].src.dtype, device=rels[0].src.device)
-            gather_reduce(rels, dx, f, mean=False, concat=False, self_add=root)
-            grads[i] = dx
-        return (None, None, None, *grads)
+            am = linalg.new_amax(dx.device) if dx.dtype == torch.float32 else None
+            gather_reduce(rels, dx, f, mean=False, concat=False, self_add=root, amax_out=am)
+            grads[i] = linalg.tag_amax(dx, am)
+        return (None, None, None, None, *grads)
 
 
 def hetero_sage_layer(plan, csr: HeteroCSR, relu: bool, xs: Sequence[torch.Tensor], params: Sequence[torch.Tensor]):
-    return _HeteroSageLayer.apply(plan, csr, relu, *xs, *params)
+    """Outputs carry the amax tag of the layer (one scalar for all destination types); inputs that all carry ONE
+    common tag (the previous layer's outputs, the grouped per-node-type projections) need no amax pass."""
+    tags = [linalg.known_amax(x) for x in xs]
+    box = {"x_amax": tags[0] if tags and all(t is not None and t is tags[0] for t in tags) else None}
+    outs = _HeteroSageLayer.apply(plan, csr, relu, box, *xs, *params)
+    for o in outs:
+        linalg.tag_amax(o, box.get("out_amax"))
+    return outs
 
 
 # ------------------------------------------------------------------------------
@@ -718,11 +749,13 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
 
 
 def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_colsum: bool = False,
-                 f16: bool = False):
+                 f16: bool = False, amax: Optional[torch.Tensor] = None):
     """What a projection's backward needs from its incoming gradient, in one pass (agnn_grad_prepare):
     ``g' = g * [relu_out > 0]`` as a GEMM operand and, optionally, the column sums of ``g'``.
-    Returns ``(operand, colsum or None)``.  ``f16``: the operand is the fp16 pair of the F16X3 mode (one extra
-    pass measures the amax of ``g`` first)."""
+    Returns ``(operand, colsum or None)``.  ``f16``: the operand is the fp16 pair of the F16X3 mode; its scale comes
+    from ``amax`` (a bound of max |g| its producer reported), else from one extra pass over ``g``."""
+    if amax is None:
+        amax = linalg.known_amax(g)
     rows, cols = g.shape
     ok = (g.dtype == torch.float32 and g.is_cuda and rows > 0 and cols % 4 == 0
           and cols <= 1024 and g.stride(1) == 1 and g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0)
@@ -734,7 +767,7 @@ def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_
             g = linalg.relu_backward(g, relu_out)
         g = g.contiguous()
         # wide gradients (e.g. HGT's folded 4864-column projection) miss the one-pass kernel but keep the operand form
-        op = linalg.split_f16(g) if f16 and g.is_cuda and linalg.f16_ok(g) else linalg.prepare(g)
+        op = linalg.split_f16(g, amax) if f16 and g.is_cuda and linalg.f16_ok(g) else linalg.prepare(g)
         return op, (colsum(g) if want_colsum else None)
     lib = _lib.lib()
     f16 = f16 and cols % 8 == 0
@@ -744,7 +777,8 @@ def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_
         part = torch.empty((lib.agnn_row_blocks(rows), cols), dtype=torch.float32, device=g.device)
         out = torch.empty(cols, dtype=torch.float32, device=g.device)
     if f16:
-        amax = linalg.amax_into(linalg.new_amax(g.device), g)
+        if amax is None:
+            amax = linalg.amax_of(g)
         _lib.check(lib.agnn_grad_prepare_f16(g.data_ptr(), g.stride(0),
                                              relu_out.data_ptr() if relu_out is not None else None,
                                              relu_out.stride(0) if relu_out is not None else 0, amax.data_ptr(),
@@ -763,64 +797,12 @@ def prepare_grad(g: torch.Tensor, relu_out: Optional[torch.Tensor] = None, want_
     return linalg.Split(buf[0], buf[1]), out
 
 
-class _Linear(torch.autograd.Function):
-    """``y = x W^T + b`` on agnn_gemm (forward, grad-input, grad-weight) with one TF32 split per operand."""
-
-    # rows from which the fp16 operand form pays for its amax pass (two short launches per projection and direction)
-    F16_MIN_ROWS = linalg.F16_MIN_ROWS
-    F16_MIN_WEIGHT = 128 * 128
-
-    @staticmethod
-    def forward(ctx, x, weight, bias):
-        f16 = (linalg.parity_operands() == "f16" and x.shape[0] >= _Linear.F16_MIN_ROWS
-               and weight.shape[0] * weight.shape[1] >= _Linear.F16_MIN_WEIGHT and linalg.f16_ok(x)
-               and linalg.f16_ok(weight))
-        xs = linalg.split_f16(x) if f16 else linalg.prepare(x)
-        y = linalg.linear(xs, weight, bias)
-        ctx.save_for_backward(*linalg.pack(xs), weight)
-        ctx.x_amax = xs.amax if f16 else None
-        ctx.has_bias = bias is not None
-        return y
-
-    @staticmethod
-    def backward(ctx, g):
-        x_first, x_second, weight = ctx.saved_tensors
-        xs = linalg.unpack(x_first, x_second, ctx.x_amax)
-        f16 = isinstance(xs, linalg.SplitH)
-        n = g.shape[1]
-        want_db = ctx.has_bias and ctx.needs_input_grad[2]
-        mult = 8 if f16 else 4
-        if g.dtype == torch.float32 and n % mult:
-            # e.g. the 185- and 50-class heads: zero columns / weight rows up to the 16-byte row rule of TMA
-            pad = mult - n % mult
-            g = torch.nn.functional.pad(g, (0, pad))
-            weight = torch.nn.functional.pad(weight, (0, 0, 0, pad))
-        gs, db = prepare_grad(g, None, want_db, f16=f16)
-        if db is not None:
-            db = db[:n]
-        dx = linalg.mm(gs, weight) if ctx.needs_input_grad[0] else None
-        dw = linalg.mm_tn(gs, xs)[:n] if ctx.needs_input_grad[1] else None
-        return dx, dw, db
-
-
-def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``nn.Linear`` arithmetic for any leading shape.  Inputs whose feature count is not a multiple
-    of 4 (e.g. the 25 + 128 note features, analysisgnn/models/analysis.py:574) are zero-padded so the
-    TMA row-stride rule (16 bytes) holds."""
-    if not x.is_cuda:
-        raise _lib.AgnnError("analysisgnn_b200 has no CPU path: tensors must live on a CUDA device")
-    lead = x.shape[:-1]
-    x2 = x.reshape(-1, x.shape[-1])
-    k = x2.shape[1]
-    mult = 8 if linalg.parity_operands() == "f16" else 4      # 16-byte rows in the operand's element type
-    if x2.dtype == torch.float32 and k % mult:
-        pad = mult - k % mult
-        x2 = torch.nn.functional.pad(x2, (0, pad))
-        weight = torch.nn.functional.pad(weight, (0, pad))
-    elif not x2.is_contiguous():
-        x2 = x2.contiguous()
-    y = _Linear.apply(x2, weight, bias)
-    return y.reshape(*lead, weight.shape[0])
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """``nn.Linear`` arithmetic (optionally with the ReLU behind it in the GEMM epilogue) for any leading shape: one
+    member of a fused projection stage (fused.stage_group), which pads feature counts that are not multiples of 8
+    (e.g. the 25 + 128 note features, analysisgnn/models/analysis.py:574) to the TMA row rule."""
+    from . import fused
+    return fused.stage_group([x], [weight], [bias], relu=relu)[0]
 
 
 class _CrossEntropy(torch.autograd.Function):
@@ -846,12 +828,21 @@ class _CrossEntropy(torch.autograd.Function):
         ignore_index, smoothing = ctx.args
         rows, cols = logits.shape
         g = g.to(torch.float32).contiguous()
-        dx = torch.empty((rows, cols), dtype=torch.float32, device=logits.device)
-        _lib.check(_lib.lib().agnn_softmax_ce_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(),
-                                                  lse.data_ptr(), rows, cols, smoothing, ignore_index, out.data_ptr(),
-                                                  g.data_ptr(), dx.data_ptr(), dx.stride(0), _stream(logits)),
+        # rows padded to 16 bytes for the head's backward GEMMs (zeroed padding), |dx| <= |g / rows that count|
+        pad = (-cols) % 8
+        full = torch.empty((rows, cols + pad), dtype=torch.float32, device=logits.device)
+        amax = linalg.new_amax(logits.device)
+        _lib.check(_lib.lib().agnn_softmax_ce_bwd_padded(logits.data_ptr(), logits.stride(0), labels.data_ptr(),
+                                                         lse.data_ptr(), rows, cols, smoothing, ignore_index,
+                                                         out.data_ptr(), g.data_ptr(), full.data_ptr(), full.stride(0),
+                                                         cols + pad, amax.data_ptr(), _stream(logits)),
                    "agnn_softmax_ce_bwd")
         _lib.count_launches(1)
+        dx = full[:, :cols] if pad else full
+        linalg.tag_amax(full, amax)
+        linalg.tag_amax(dx, amax)
+        if pad:
+            dx._agnn_padded = full
         return dx, None, None, None
 
 
@@ -1008,19 +999,27 @@ class _GRULayer(torch.autograd.Function):
     gradients are tensor-core GEMMs; agnn_gru_fwd / _bwd run only the time recurrence."""
 
     @staticmethod
-    def forward(ctx, x, *params):
+    def forward(ctx, x, opts, *params):
         n_dir = len(params) // 4
         b, t, c = x.shape
         h = params[1].shape[1]
         x2 = x.reshape(b * t, c)
         x2 = x2 if x2.is_contiguous() else x2.contiguous()
-        xs = linalg.prepare_auto(x2)
-        gis, whh, bhh = [], [], []
-        for d in range(n_dir):
-            w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
-            gis.append(linalg.linear(xs, w_ih, b_ih))
-            whh.append(w_hh.contiguous())
-            bhh.append(b_hh.contiguous())
+        p, site = opts.get("dropout", (0.0, 0))          # nn.GRU's inter-layer dropout, applied to this layer's input
+        f16 = (linalg.parity_operands() == "f16" and x2.shape[0] >= linalg.F16_MIN_ROWS and linalg.f16_ok(x2))
+        if f16:
+            xs = linalg.split_f16(x2, opts.get("x_amax"), dropout=(p, site) if p > 0 else None)
+        else:
+            if p > 0:
+                from . import fused
+                x2 = fused.dropout_apply(x2, p, site)
+            xs = linalg.prepare(x2)
+        whh = [params[4 * d + 1].contiguous() for d in range(n_dir)]
+        bhh = [params[4 * d + 3].contiguous() for d in range(n_dir)]
+        # the input projections of all directions: one grouped launch
+        gis = linalg.linear_group([xs] * n_dir, [params[4 * d] for d in range(n_dir)],
+                                  [params[4 * d + 2] for d in range(n_dir)])
+        ctx.dropout = (p, site)
         out = torch.empty((b, t, n_dir * h), dtype=x.dtype, device=x.device)
         gates = [torch.empty((b, t, 4 * h), dtype=x.dtype, device=x.device) for _ in range(n_dir)]
         _lib.check(_lib.lib().agnn_gru_fwd(b, t, h, n_dir, _lib.ptr_array(gis), _lib.ptr_array(whh),
@@ -1051,6 +1050,7 @@ class _GRULayer(torch.autograd.Function):
         _lib.count_launches(1)
         grads = []
         dx = None
+        gi_ops, gh_ops, hp_ops = [], [], []
         for d in range(n_dir):
             hd = out[:, :, d * h:(d + 1) * h]
             h_prev = torch.zeros((b, t, h), dtype=out.dtype, device=out.device)
@@ -1060,22 +1060,35 @@ class _GRULayer(torch.autograd.Function):
                 else:
                     h_prev[:, :-1] = hd[:, 1:]
             # dgi meets xs in the grad-weight GEMM: same operand form
-            gi_s = (linalg.prepare_auto if isinstance(xs, linalg.SplitH) else linalg.prepare)(dgi[d])
-            gh_s = linalg.prepare_auto(dgh[d])
-            dw_ih = linalg.mm_tn(gi_s, xs)
-            dw_hh = linalg.mm_tn(gh_s, h_prev.reshape(b * t, h))
-            if ctx.needs_input_grad[0]:
-                if dx is None:
-                    dx = linalg.mm(gi_s, w_ih[d])
-                else:
-                    dx = linalg.mm(gi_s, w_ih[d], out=dx, accumulate=True)
-            grads += [dw_ih, dw_hh, colsum(dgi[d]), colsum(dgh[d])]
-        return (dx.reshape(b, t, c) if dx is not None else None, *grads)
+            gi_ops.append((linalg.prepare_auto if isinstance(xs, linalg.SplitH) else linalg.prepare)(dgi[d]))
+            gh_ops.append(linalg.prepare_auto(dgh[d]))
+            hp = h_prev.reshape(b * t, h)
+            hp_ops.append(linalg.split_f16(hp, linalg.const_amax(hp.device, 1.0))
+                          if isinstance(gh_ops[-1], linalg.SplitH) and linalg.f16_ok(hp) else hp)
+        # weight gradients of all directions (input and recurrent) in one grouped launch
+        dws = linalg.mm_tn_group(gi_ops + gh_ops, [xs] * n_dir + hp_ops)
+        if ctx.needs_input_grad[0]:
+            dx = linalg.mm(gi_ops[0], w_ih[0])
+            for d in range(1, n_dir):
+                dx = linalg.mm(gi_ops[d], w_ih[d], out=dx, accumulate=True)
+            p, site = ctx.dropout
+            if p > 0:
+                from . import fused
+                dx = fused.dropout_apply(dx, p, site)
+        for d in range(n_dir):
+            grads += [dws[d], dws[n_dir + d], colsum(dgi[d]), colsum(dgh[d])]
+        return (dx.reshape(b, t, c) if dx is not None else None, None, *grads)
 
 
-def gru_layer(x: torch.Tensor, params) -> torch.Tensor:
-    """``params``: flat list of (w_ih, w_hh, b_ih, b_hh) per direction."""
-    return _GRULayer.apply(x, *params)
+def gru_layer(x: torch.Tensor, params, dropout=None) -> torch.Tensor:
+    """``params``: flat list of (w_ih, w_hh, b_ih, b_hh) per direction.  ``dropout = (p, site)``: nn.GRU's
+    inter-layer dropout on this layer's INPUT (counter-based mask, fused into the operand split).  The output is tagged
+    with the bound |h| <= 1 (a GRU state is a convex combination of tanh values and earlier states)."""
+    opts = {"x_amax": linalg.known_amax(x)}
+    if dropout is not None and dropout[0] > 0:
+        opts["dropout"] = dropout
+    out = _GRULayer.apply(x, opts, *params)
+    return linalg.tag_amax(out, linalg.const_amax(out.device, 1.0))
 
 
 def gru_supported(x: torch.Tensor, hidden: int) -> bool:

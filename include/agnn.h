@@ -151,6 +151,14 @@ int agnn_gather_reduce_f16(int32_t n_rows, int32_t n_feat, int dtype, int scale,
                            int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out, void* out_lo,
                            const float* pair_amax, void* heavy_workspace /* optional */, size_t heavy_workspace_bytes,
                            agnn_stream_t stream);
+/* Same launch; amax_out (optional device scalar, zero it first) receives max(*amax_out, max |value written|) -- the
+ * fp16 operand scale of the result for a later agnn_gemm without another pass over it (the gradient a backward gather
+ * hands to the projection below it).  Plain fp32 / bf16 output only (out_lo == pair_amax == NULL). */
+int agnn_gather_reduce_amax(int32_t n_rows, int32_t n_feat, int dtype, int scale, int combine, int n_rel,
+                            const agnn_rel_t* rels /* host */, const void* self_add, int64_t ld_self, const void* copy,
+                            int64_t ld_copy, int32_t copy_col, void* out, int64_t ld_out, void* out_lo,
+                            const float* pair_amax, float* amax_out, void* heavy_workspace /* optional */,
+                            size_t heavy_workspace_bytes, agnn_stream_t stream);
 /* Scratch for the heavy-row path of a launch whose relations hold `total_edges` edges and `total_heavy_cap` heavy
  * slots in all: (total_edges / AGNN_HEAVY_CHUNK + total_heavy_cap) partial rows of n_feat floats.  Relations are
  * only split when heavy_rows is set AND a workspace is given; otherwise every row is walked by its own warp. */
@@ -303,6 +311,34 @@ int agnn_gemm_scaled(int precision, int a_layout, int b_layout, int64_t M, int64
                      const float* amax_b, void* c, int64_t ldc, const float* bias, int flags, int split_k, void* workspace,
                      size_t workspace_bytes, agnn_stream_t stream);
 
+/* Grouped launch: up to AGNN_GEMM_MAX_GROUP independent problems of ONE precision / layout combination in one
+ * persistent launch -- the per-node-type projections (project_dict, analysis.py:429-443; PyG HeteroDictLinear in
+ * HGTConv), the per-task heads (clf_dict, analysis.py:486-496, 546-569), the destination types of a message-passing
+ * layer, the directions of a GRU layer, and the matching grad-input / grad-weight products of their backward.  Every
+ * problem has its own sizes, operands, bias, flags and split_k.  Empty problems (M or N == 0) are skipped.
+ *   workspace   split_k > 1: agnn_gemm_workspace() bytes for the partial tiles;
+ *   tickets     optional device int32 array, ZERO on entry (and zero again on exit): with it the partials of a tile are
+ *               added in split order by the CTA that stores the tile's last partial -- inside the same launch,
+ *               deterministic; without it (NULL) a second kernel reduces them.  agnn_gemm_tickets() counters per
+ *               problem, handed out in problem order.  One array must not be used by two launches that may overlap.
+ *   amax_out    optional device scalar: *amax_out = max(*amax_out, max |C|) (zero it first) -- the F16X3 operand
+ *               scale of C for a later product, without another pass over C.  Not with AGNN_GEMM_ACCUMULATE. */
+#define AGNN_GEMM_MAX_GROUP 12
+typedef struct agnn_gemm_problem {
+  int64_t M, N, K;
+  const void* a_hi; const void* a_lo; int64_t lda; const float* amax_a; /* amax_*: F16X3 only, else NULL */
+  const void* b_hi; const void* b_lo; int64_t ldb; const float* amax_b;
+  void* c; int64_t ldc;
+  const float* bias;     /* optional [N] */
+  int32_t flags;         /* AGNN_GEMM_RELU | AGNN_GEMM_ACCUMULATE | AGNN_GEMM_OUT_BF16 */
+  int32_t split_k;       /* >= 1 */
+  void* workspace; size_t workspace_bytes;
+  float* amax_out;       /* optional */
+} agnn_gemm_problem_t;
+int64_t agnn_gemm_tickets(int64_t M, int64_t N, int split_k);
+int agnn_gemm_grouped(int precision, int a_layout, int b_layout, int n_problems, const agnn_gemm_problem_t* problems,
+                      int32_t* tickets, int64_t n_tickets, agnn_stream_t stream);
+
 /* ------------------------------------------------------------ row-wise normalisation
  * agnn_layernorm_*: nn.LayerNorm of project_dict / project_enc (analysisgnn/models/analysis.py:429-443,
  * 474-485) and of the sequence branch (analysisgnn/models/cadence.py:249-260).  fp32, warp per row,
@@ -321,6 +357,34 @@ int agnn_layernorm_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t l
                        const float* mean, const float* rstd, float* dx, int64_t ld_dx, float* dgamma_partials,
                        float* dbeta_partials, float* dgamma /* optional [cols] */, float* dbeta /* = dgamma + cols */,
                        int64_t rows, int cols, agnn_stream_t stream);
+/* LayerNorm feeding a projection (project_dict / project_enc / clf_dict / the sequence MLP are all
+ * Linear -> ReLU -> LayerNorm -> Dropout -> Linear chains, analysisgnn/models/analysis.py:429-443, 474-496): the
+ * (dropped-out) output is written directly as the fp16 hi / lo operand pair of the projection behind the norm
+ * (pair_hi / pair_lo, ld_pair in fp16 elements, cols % 8 == 0) -- no fp32 output (y may be NULL), no dropout kernel,
+ * no amax pass, no split pass.  The pair's scale comes from the bound |y| <= max|gamma| sqrt(cols - 1) + max|beta|
+ * (times 1 / (1 - p)), which the kernel writes to *pair_amax for agnn_gemm_scaled.
+ * Dropout (nn.Dropout in train mode; p = 0 or rng_state == NULL: none) is a counter-based mask: keep(element) is a
+ * function of rng_state = {seed, step} (DEVICE uint64[2]; agnn_dropout_advance increments step, so a CUDA-graph replay
+ * draws new masks), rng_stream (distinguishes call sites) and the element index; the backward recomputes it.
+ * agnn_layernorm_bwd_dropout: dy is first multiplied by the same mask / (1 - p); amax_out (optional) receives max |dx|.
+ * agnn_dropout_apply: y = keep ? x / (1 - p) : 0 for a plain matrix (both directions of the inter-layer dropout of
+ * the sequence GRU, analysisgnn/models/cadence.py:249-251), optional amax_out.
+ * agnn_split_f16_dropout: agnn_split_f16 of the dropped-out matrix in one pass (amax must bound |x| / (1 - p)). */
+int agnn_layernorm_fwd_pair(const float* x, int64_t ld_x, const float* gamma, const float* beta, float* y /* optional */,
+                            int64_t ld_y, float* mean, float* rstd, int64_t rows, int cols, float eps, void* pair_hi,
+                            void* pair_lo, int64_t ld_pair, float* pair_amax, float dropout_p, const uint64_t* rng_state,
+                            uint32_t rng_stream, agnn_stream_t stream);
+int agnn_layernorm_bwd_dropout(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* gamma,
+                               const float* mean, const float* rstd, float* dx, int64_t ld_dx, float* dgamma_partials,
+                               float* dbeta_partials, float* dgamma, float* dbeta, int64_t rows, int cols,
+                               float dropout_p, const uint64_t* rng_state, uint32_t rng_stream, float* amax_out,
+                               agnn_stream_t stream);
+int agnn_dropout_advance(uint64_t* rng_state, agnn_stream_t stream);
+int agnn_dropout_apply(const float* x, int64_t ld_x, float* y, int64_t ld_y, int64_t rows, int cols, float dropout_p,
+                       const uint64_t* rng_state, uint32_t rng_stream, float* amax_out, agnn_stream_t stream);
+int agnn_split_f16_dropout(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax, void* hi, void* lo,
+                           int64_t ld_out, float dropout_p, const uint64_t* rng_state, uint32_t rng_stream,
+                           agnn_stream_t stream);
 int agnn_l2norm_relu_fwd(const float* x, int64_t ld_x, float* y, int64_t ld_y, float* inv_norm, int64_t rows, int cols,
                          int relu_first, float eps, agnn_stream_t stream);
 int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* inv_norm, float* dx,
@@ -358,6 +422,12 @@ int agnn_softmax_ce_fwd(const float* logits, int64_t ld, const int64_t* labels, 
 int agnn_softmax_ce_bwd(const float* logits, int64_t ld, const int64_t* labels, const float* lse, int64_t rows, int cols,
                         float smoothing, int64_t ignore_index, const float* out, const float* grad_out /* device scalar */,
                         float* dlogits, int64_t ld_d, agnn_stream_t stream);
+/* Same backward writing rows of `cols_padded` >= cols columns (the extra columns are zeroed: a 16-byte aligned
+ * gradient for the head's backward GEMMs without a padding copy) and, optionally, *amax_out = max(*amax_out,
+ * |grad_out / rows_that_count|), an upper bound of every |dlogits| entry (|softmax - target| <= 1). */
+int agnn_softmax_ce_bwd_padded(const float* logits, int64_t ld, const int64_t* labels, const float* lse, int64_t rows,
+                               int cols, float smoothing, int64_t ignore_index, const float* out, const float* grad_out,
+                               float* dlogits, int64_t ld_d, int cols_padded, float* amax_out, agnn_stream_t stream);
 int agnn_embedding_bwd_blocks(int64_t rows);
 int agnn_embedding_bwd(const float* g, int64_t ld_g, const int64_t* idx, int64_t rows, int dim, int n_emb,
                        float* partials, float* dweight, agnn_stream_t stream);

@@ -105,11 +105,109 @@ def test_single_tf32_pass_is_not_the_parity_mode():
     assert 1e-5 < e1 < 5e-3 and e3 < 4e-6, (e1, e3)
 
 
-def test_unsupported_strides_fall_back_to_the_library():
-    x, w, b = _ops(100, 185, 153)                              # project_dict's 25+128 input: 612-byte rows
+def test_unaligned_operands_are_repacked_not_sent_to_a_library():
+    """Rows that are not 16-byte multiples (project_dict's 25 + 128 = 153 inputs: 612-byte rows) are copied into
+    padded buffers and still run on agnn_gemm (counted; refused in strict mode) -- there is no library GEMM."""
+    x, w, b = _ops(100, 185, 153)
     want = x.double() @ w.double().t() + b.double()
+    before = linalg.stats["repacked_gemms"]
     got = linalg.linear(x.to(DEV), w.to(DEV), b.to(DEV))
-    assert rel_err(got, want) < 4e-6
+    assert rel_err(got, want) < 4e-6 and got.shape == (100, 185)
+    assert linalg.stats["repacked_gemms"] == before + 1
+    wt = w.t().contiguous()                                    # [153, 185]: MN-major B with 740-byte rows
+    _check_fp32(linalg.mm(x.to(DEV), wt.to(DEV)), x.double() @ wt.double(), x @ wt)
+    a = torch.randn(100, 37)
+    _check_fp32(linalg.mm_tn(a.to(DEV), x.to(DEV)), a.double().t() @ x.double(), a.t() @ x)
+    base = torch.randn(100, 185)
+    out = base.to(DEV)
+    linalg.mm(x.to(DEV), wt.to(DEV), out=out, accumulate=True)
+    _check_fp32(out, x.double() @ wt.double() + base.double(), x @ wt + base)
+    old = _lib.strict()
+    _lib.set_strict(True)
+    try:
+        with pytest.raises(_lib.AgnnError):
+            linalg.linear(x.to(DEV), w.to(DEV), b.to(DEV))
+    finally:
+        _lib.set_strict(old)
+
+
+@pytest.mark.parametrize("operands", ["tf32", "f16"])
+def test_grouped_launch_matches_single_launches(operands):
+    """agnn_gemm_grouped: independent problems of different sizes (node types, task heads), one of them empty, in
+    ONE launch -- bit-identical to launching them one by one, in all three layout combinations."""
+    g = torch.Generator().manual_seed(3)
+    rows = [5000, 1133, 287, 0, 50000 if operands == "f16" else 640]
+    mk = (lambda t: linalg.split_f16(t.to(DEV)) if t.shape[0] else t.to(DEV)) if operands == "f16" else \
+        (lambda t: t.to(DEV))
+    xs = [torch.randn(r, 256, generator=g) for r in rows]
+    ws = [torch.randn(n, 256, generator=g) * 0.1 for n in (256, 128, 64, 32, 192)]
+    bs = [torch.randn(w.shape[0], generator=g) for w in ws]
+    xd = [mk(x) for x in xs]
+    wd = [mk(w) if operands == "f16" else w.to(DEV) for w in ws]
+    before = linalg.stats.get("gemm_launches", 0)
+    outs = linalg.linear_group(xd, wd, [b.to(DEV) for b in bs], relu=True)
+    assert linalg.stats["gemm_launches"] == before + 1
+    for x, w, b, xo, wo, o in zip(xs, ws, bs, xd, wd, outs):
+        assert o.shape == (x.shape[0], w.shape[0])
+        if x.shape[0] == 0:
+            continue
+        _check_fp32(o, (x.double() @ w.double().t() + b.double()).relu(), (x @ w.t() + b).relu())
+        assert torch.equal(o, linalg.linear(xo, wo, b.to(DEV), relu=True))
+    # grad-weight products (split-K inside the launch) and grad-input products of the same group
+    gs = [torch.randn(x.shape[0], w.shape[0], generator=g) for x, w in zip(xs, ws)]
+    gd = [mk(t) for t in gs]
+    dws = linalg.mm_tn_group(gd, xd)
+    dxs = linalg.mm_group(gd, wd)
+    for x, w, gg, go, xo, wo, dw, dx in zip(xs, ws, gs, gd, xd, wd, dws, dxs):
+        if x.shape[0] == 0:
+            continue
+        _check_fp32(dw, gg.double().t() @ x.double(), gg.t() @ x)
+        _check_fp32(dx, gg.double() @ w.double(), gg @ w)
+        assert torch.equal(dw, linalg.mm_tn(go, xo)) and torch.equal(dx, linalg.mm(go, wo))
+
+
+def test_split_k_is_reduced_inside_the_launch_deterministically():
+    """The CTA that stores a tile's last partial adds the partials in split order: no second kernel, bit-identical
+    from run to run, ticket counters back at zero, same numbers as the two-kernel reduction."""
+    g = torch.Generator().manual_seed(4)
+    a, b = torch.randn(50000, 384, generator=g).to(DEV), torch.randn(50000, 256, generator=g).to(DEV)
+    bias = torch.randn(256, generator=g).to(DEV)
+    launches = _lib.launches()
+    got = linalg.mm_tn(a, b)
+    assert _lib.launches() - launches <= 3                     # two operand splits + ONE gemm launch
+    for _ in range(3):
+        assert torch.equal(got, linalg.mm_tn(a, b))
+    dev = torch.device(DEV)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dev.index is None else dev
+    assert int(linalg._tickets(dev).abs().sum()) == 0
+    _check_fp32(got, a.double().cpu().t() @ b.double().cpu(), a.cpu().t() @ b.cpu())
+    # the legacy entry point (no ticket array: partials reduced by splitk_reduce_kernel) gives the same bits
+    lib = _lib.lib()
+    sa, sb = linalg.split(a), linalg.split(b)
+    m, n, k = 384, 256, 50000
+    sk = lib.agnn_gemm_split_k(_lib.GEMM_TF32X3, m, n, k)
+    assert sk > 1
+    ws = torch.empty(lib.agnn_gemm_workspace(_lib.GEMM_TF32X3, m, n, k, sk), dtype=torch.uint8, device=DEV)
+    out = torch.empty(m, n, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.agnn_gemm(_lib.GEMM_TF32X3, 1, 1, m, n, k, sa.hi.data_ptr(), sa.lo.data_ptr(), 384, sb.hi.data_ptr(),
+                             sb.lo.data_ptr(), 256, out.data_ptr(), 256, None, 0, sk, ws.data_ptr(), ws.numel(), st))
+    assert torch.equal(out, got)
+    del bias
+
+
+@pytest.mark.parametrize("m,n,k,relu", [(5000, 256, 256, True), (300, 200, 96, False), (77, 52, 640, False)])
+def test_epilogue_amax_out(m, n, k, relu):
+    """amax_out: max |C| from the GEMM epilogue (valid rows / columns only), also through split-K."""
+    x, w, b = _ops(m, n, k)
+    am = torch.zeros(1, device=DEV)
+    y = linalg.linear(x.to(DEV), w.to(DEV), b.to(DEV), relu=relu, amax_out=am)
+    assert float(am) == float(y.abs().max())
+    g = torch.Generator().manual_seed(9)
+    a, c = torch.randn(20000, 64, generator=g).to(DEV), torch.randn(20000, n if n % 4 == 0 else 56, generator=g).to(DEV)
+    am2 = torch.zeros(1, device=DEV)
+    dw = linalg._group(_lib.MN_MAJOR, _lib.MN_MAJOR, [dict(a=a, b=c, m=64, n=c.shape[1], k=20000, amax_out=am2)])[0]
+    assert float(am2) == float(dw.abs().max())
 
 
 def test_argument_errors():
