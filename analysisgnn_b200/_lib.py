@@ -139,6 +139,8 @@ _PROTOTYPES = {
                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "agnn_gemm_tickets": (C.c_int64, [C.c_int64, C.c_int64, C.c_int]),
+    "agnn_gemm_group_split_k": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "agnn_gemm_grouped": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GemmProblem), C.c_void_p, C.c_int64,
                                     C.c_void_p]),
     "agnn_gather_reduce_amax": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Rel),

@@ -84,8 +84,12 @@ constexpr int kMaxGroup = AGNN_GEMM_MAX_GROUP;
 struct GemmGroup {
   int n_prob;
   int chain_blocks;      // K blocks accumulated in TMEM before the sum is promoted to fp32 registers
-  int total_tiles;
+  int total_tiles;                 // GEMM work items (tile x split) of all problems
   int tile_start[kMaxGroup + 1];   // first work item (tile x split) of every problem
+  // split-K with ticket counters: the CTA that stores the LAST partial of an output tile adds the tile's partials in
+  // split order and finishes C.  Nobody ever waits for another CTA (two grids spinning on each other's unscheduled
+  // CTAs from two streams could deadlock), the adds keep 32 independent 16-byte loads in flight per thread, and the
+  // producer / MMA warps of that CTA go on with its next item meanwhile.
   GemmParams prob[kMaxGroup];
 };
 
@@ -548,8 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           __syncwarp();
         }
         if (p.tickets) {
-          // the CTA that completes the tile adds the partials in split order (deterministic) and finishes C
-          __threadfence();
+          __threadfence();                          // this CTA's partial is visible before its ticket
           epi_barrier();
           if (et == 0) {
             const int old = atomicAdd(p.tickets + it.mn, 1);
@@ -561,49 +564,74 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
           if (last) {
             __threadfence();
             const int qv = et & 31;                 // float4 column of the tile
+            const int gcol = n0 + qv * 4;
             uint32_t mx = 0;
-            for (int r = et >> 5; r < kBlockM; r += 4) {
-              const int grow = m0 + r, gcol = n0 + qv * 4;
-              if (grow >= p.M || gcol >= p.N) continue;
-              float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) {
-                sum.x = __ldg(p.bias + gcol);
-                if (gcol + 1 < p.N) sum.y = __ldg(p.bias + gcol + 1);
-                if (gcol + 2 < p.N) sum.z = __ldg(p.bias + gcol + 2);
-                if (gcol + 3 < p.N) sum.w = __ldg(p.bias + gcol + 3);
-              }
-              const float* src = static_cast<const float*>(p.out) + (int64_t)grow * p.ldc + gcol;
-              for (int sp = 0; sp < p.split_k; ++sp) {
-                const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)sp * p.split_stride));
-                sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
-              }
-              float v[4] = {sum.x, sum.y, sum.z, sum.w};
-              if (p.flags & AGNN_GEMM_OUT_BF16) {
-                __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.c_final) + (int64_t)grow * p.ldc_final + gcol;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && gcol < p.N) {
+              bias4.x = __ldg(p.bias + gcol);
+              if (gcol + 1 < p.N) bias4.y = __ldg(p.bias + gcol + 1);
+              if (gcol + 2 < p.N) bias4.z = __ldg(p.bias + gcol + 2);
+              if (gcol + 3 < p.N) bias4.w = __ldg(p.bias + gcol + 3);
+            }
+            const int rows_here = min(kBlockM, p.M - m0);
+            // thread (w, qv) owns rows w, w + 4, ...; four of its rows x eight splits = 32 loads in flight
+#pragma unroll 1
+            for (int r0 = et >> 5; r0 < rows_here && gcol < p.N; r0 += 16) {
+              float4 sum[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (gcol + e < p.N) {
-                    float x = v[e];
-                    if (p.flags & AGNN_GEMM_ACCUMULATE) x += __bfloat162float(o[e]);
-                    if (p.flags & AGNN_GEMM_RELU) x = fmaxf(x, 0.f);
-                    mx = max(mx, __float_as_uint(x) & 0x7fffffffu);
-                    o[e] = __float2bfloat16_rn(x);
-                  }
-              } else {
-                float* o = static_cast<float*>(p.c_final) + (int64_t)grow * p.ldc_final + gcol;
+              for (int j = 0; j < 4; ++j) sum[j] = bias4;
+              const float* src = static_cast<const float*>(p.out) + (int64_t)(m0 + r0) * p.ldc + gcol;
+#pragma unroll 1
+              for (int sp = 0; sp < p.split_k; sp += 8) {
+                float4 t[4][8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (gcol + e < p.N) {
-                    if (p.flags & AGNN_GEMM_ACCUMULATE) v[e] += o[e];
-                    if (p.flags & AGNN_GEMM_RELU) v[e] = fmaxf(v[e], 0.f);
-                    mx = max(mx, __float_as_uint(v[e]) & 0x7fffffffu);
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {
+                    const bool on = r0 + 4 * j < rows_here && sp + u < p.split_k;
+                    t[j][u] = on ? __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(4 * j) * p.ldc +
+                                                                           (int64_t)(sp + u) * p.split_stride))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                   }
-                if (gcol + 4 <= p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {       // split order: deterministic
+                    sum[j].x += t[j][u].x; sum[j].y += t[j][u].y; sum[j].z += t[j][u].z; sum[j].w += t[j][u].w;
+                  }
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int grow = m0 + r0 + 4 * j;
+                if (r0 + 4 * j >= rows_here) continue;
+                float v[4] = {sum[j].x, sum[j].y, sum[j].z, sum[j].w};
+                if (p.flags & AGNN_GEMM_OUT_BF16) {
+                  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.c_final) + (int64_t)grow * p.ldc_final + gcol;
 #pragma unroll
                   for (int e = 0; e < 4; ++e)
-                    if (gcol + e < p.N) o[e] = v[e];
+                    if (gcol + e < p.N) {
+                      float x = v[e];
+                      if (p.flags & AGNN_GEMM_ACCUMULATE) x += __bfloat162float(o[e]);
+                      if (p.flags & AGNN_GEMM_RELU) x = fmaxf(x, 0.f);
+                      mx = max(mx, __float_as_uint(x) & 0x7fffffffu);
+                      o[e] = __float2bfloat16_rn(x);
+                    }
+                } else {
+                  float* o = static_cast<float*>(p.c_final) + (int64_t)grow * p.ldc_final + gcol;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (gcol + e < p.N) {
+                      if (p.flags & AGNN_GEMM_ACCUMULATE) v[e] += o[e];
+                      if (p.flags & AGNN_GEMM_RELU) v[e] = fmaxf(v[e], 0.f);
+                      mx = max(mx, __float_as_uint(v[e]) & 0x7fffffffu);
+                    }
+                  if (gcol + 4 <= p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                      if (gcol + e < p.N) o[e] = v[e];
+                  }
                 }
               }
             }
@@ -935,6 +963,37 @@ extern "C" int agnn_gemm_split_k(int precision, int64_t M, int64_t N, int64_t K)
     if (score > best * 1.02) { best = score; s = c; }            // prefer fewer splits unless clearly better
   }
   return s < 1 ? 1 : (int)s;
+}
+
+// split counts for the problems of ONE grouped launch: the group as a whole should fill the machine for about two
+// waves, every problem getting work items in proportion to its share of the K blocks; at least 8 K blocks per item
+// (pipeline fill) and at most 32 splits (the partials of a tile are added by one CTA).
+extern "C" int agnn_gemm_group_split_k(int precision, int n_problems, const int64_t* M, const int64_t* N,
+                                       const int64_t* K, int32_t* split_out) {
+  if (n_problems < 0 || (n_problems && (!M || !N || !K || !split_out))) return fail(AGNN_ERR_ARG, "gemm_group_split_k: bad arguments");
+  const int block_k = (precision == AGNN_GEMM_BF16 || precision == AGNN_GEMM_F16X3) ? 64 : 32;
+  double total_work = 0.0;
+  int64_t total_tiles = 0;
+  for (int i = 0; i < n_problems; ++i) {
+    const int64_t tiles = ceil_div(M[i], kBlockM) * ceil_div(N[i], kBlockN), kb = ceil_div(K[i], block_k);
+    total_work += (double)tiles * (double)kb;
+    total_tiles += tiles;
+  }
+  const double target = total_work / kNumSM >= 32.0 ? 2.0 * kNumSM : 1.0 * kNumSM;
+  for (int i = 0; i < n_problems; ++i) {
+    const int64_t tiles = ceil_div(M[i], kBlockM) * ceil_div(N[i], kBlockN), kb = ceil_div(K[i], block_k);
+    int64_t s = 1;
+    if (tiles > 0 && kb >= 16 && total_tiles < 2 * kNumSM) {
+      const double share = total_work > 0.0 ? (double)tiles * (double)kb / total_work : 0.0;
+      const int64_t items = (int64_t)(share * target + 0.5);
+      s = ceil_div(items > tiles ? items : tiles, tiles);
+      const int64_t s_max = kb / 8 < 32 ? kb / 8 : 32;
+      if (s > s_max) s = s_max;
+      if (s < 1) s = 1;
+    }
+    split_out[i] = (int32_t)s;
+  }
+  return AGNN_OK;
 }
 
 extern "C" size_t agnn_gemm_workspace(int precision, int64_t M, int64_t N, int64_t K, int split_k) {

@@ -393,10 +393,7 @@ def _resolve(a: Operand, b: Operand, m: int, n: int, k: int, bias, flags: int, o
     p = _Problem()
     p.oa, p.ob, p.m, p.n, p.k, p.flags, p.out, p.amax_out = oa, ob, m, n, k, flags, out, amax_out
     p.bias = bias.float().contiguous() if bias is not None else None
-    lib = _lib.lib()
-    p.split_k = lib.agnn_gemm_split_k(prec, m, n, k) if split_k is None else split_k
-    p.ws_bytes = lib.agnn_gemm_workspace(prec, m, n, k, p.split_k)
-    p.ws = torch.empty(p.ws_bytes, dtype=torch.uint8, device=dev) if p.ws_bytes else None
+    p.split_k, p.ws, p.ws_bytes = split_k, None, 0      # chosen per launch group (_launch)
     return prec, p
 
 
@@ -411,6 +408,16 @@ def _launch(prec: int, a_layout: int, b_layout: int, problems) -> None:
         dev = chunk[0].oa[0].device
         arr = (_lib.GemmProblem * len(chunk))()
         need = 0
+        import ctypes as C
+        n = len(chunk)
+        ms, ns, ks = ((C.c_int64 * n)(*[getattr(p, f) for p in chunk]) for f in ("m", "n", "k"))
+        splits = (C.c_int32 * n)()
+        _lib.check(lib.agnn_gemm_group_split_k(prec, n, ms, ns, ks, splits), "agnn_gemm_group_split_k")
+        for p, sk in zip(chunk, splits):
+            if p.split_k is None:
+                p.split_k = int(sk)
+            p.ws_bytes = lib.agnn_gemm_workspace(prec, p.m, p.n, p.k, p.split_k)
+            p.ws = torch.empty(p.ws_bytes, dtype=torch.uint8, device=dev) if p.ws_bytes else None
         for q, p in zip(arr, chunk):
             q.M, q.N, q.K = p.m, p.n, p.k
             q.a_hi, q.a_lo, q.lda, q.amax_a = ptr(p.oa[0]), ptr(p.oa[1]), p.oa[0].stride(0), ptr(p.oa[3])

@@ -30,7 +30,8 @@ class MLP(nn.Sequential):
     not made of such stages run module by module."""
 
     def stages(self, pre_norm=None):
-        """[(LayerNorm or None, dropout p, Linear, relu)] or None if the children do not parse into stages."""
+        """[(LayerNorm or None, dropout p, Linear, ReLU module or None)] or None if the children do not parse into
+        stages."""
         out, norm, p = [], pre_norm, 0.0
         mods = list(self.children())
         i = 0
@@ -42,10 +43,10 @@ class MLP(nn.Sequential):
             elif isinstance(m, nn.Dropout) and p == 0.0:
                 p = m.p
             elif isinstance(m, nn.Linear):
-                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                relu = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU) else None
                 out.append((norm, p, m, relu))
                 norm, p = None, 0.0
-                i += 1 if relu else 0
+                i += 1 if relu is not None else 0
             else:
                 return None
             i += 1
@@ -60,7 +61,7 @@ class MLP(nn.Sequential):
         pre_norms = pre_norms if pre_norms is not None else [None] * len(mlps)
         plans = [m.stages(pn) for m, pn in zip(mlps, pre_norms)]
         same = all(pl is not None and len(pl) == len(plans[0]) and
-                   [(s[0] is None, s[1], s[3]) for s in pl] == [(s[0] is None, s[1], s[3]) for s in plans[0]]
+                   [(s[0] is None, s[1], s[3] is None) for s in pl] == [(s[0] is None, s[1], s[3] is None) for s in plans[0]]
                    for pl in plans) if plans and plans[0] is not None else False
         if not same or not all(x.is_cuda for x in xs):
             outs = []
@@ -73,9 +74,13 @@ class MLP(nn.Sequential):
         for k in range(len(plans[0])):
             st = [pl[k] for pl in plans]
             norms = [None if s[0] is None else (s[0].weight, s[0].bias, s[0].eps) for s in st]
-            xs = fused.stage_group(xs, [s[2].weight for s in st], [s[2].bias for s in st], norms, relu=st[0][3],
-                                   dropout=st[0][1], training=training,
+            xs = fused.stage_group(xs, [s[2].weight for s in st], [s[2].bias for s in st], norms,
+                                   relu=st[0][3] is not None, dropout=st[0][1], training=training,
                                    share_amax=share_amax and k == len(plans[0]) - 1)
+            for s, x in zip(st, xs):        # the ReLU ran in the GEMM epilogue: its module's forward hooks still see it
+                if s[3] is not None and s[3]._forward_hooks:
+                    for hook in list(s[3]._forward_hooks.values()):
+                        hook(s[3], (x,), x)
         return xs
 
 

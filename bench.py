@@ -440,10 +440,10 @@ def run_ours(args):
     if os.environ.get("AGNN_DUMP_GEMM") and rank == 0:      # per-shape GEMM time of one step, to stderr
         lay = {0: "K", 1: "MN"}
         rows = sorted(ops.timer.by_tag("gemm").items(), key=lambda kv: -kv[1][1])
-        for (la, lb, m_, n_, k_, sk), (cnt_, ms_) in rows:
-            print(f"gemm A:{lay.get(la, la)} B:{lay.get(lb, lb)} M={m_:6d} N={n_:5d} K={k_:6d} split={sk:2d}  "
-                  f"x{cnt_ / args.steps:5.1f}/step  {ms_ / args.steps * 1e3:8.1f} us/step  "
-                  f"{2.0 * m_ * n_ * k_ * cnt_ / ms_ / 1e9:6.1f} TF/s", file=sys.stderr)
+        for (la, lb, m_, n_, k_, sk, grp_), (cnt_, ms_) in rows:     # largest member of every (grouped) launch
+            print(f"gemm A:{lay.get(la, la)} B:{lay.get(lb, lb)} M={m_:6d} N={n_:5d} K={k_:6d} split={sk:2d} "
+                  f"group={grp_:2d}  x{cnt_ / args.steps:5.1f}/step  {ms_ / args.steps * 1e3:8.1f} us/step",
+                  file=sys.stderr)
     ops.timer = _linalg.timer = None
     _hetero._HybridBase.overlap_sequence_branch = True
 

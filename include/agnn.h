@@ -336,6 +336,9 @@ typedef struct agnn_gemm_problem {
   float* amax_out;       /* optional */
 } agnn_gemm_problem_t;
 int64_t agnn_gemm_tickets(int64_t M, int64_t N, int split_k);
+/* split counts for the problems of one grouped launch (host arithmetic): the group as a whole fills the machine */
+int agnn_gemm_group_split_k(int precision, int n_problems, const int64_t* M, const int64_t* N, const int64_t* K,
+                            int32_t* split_out);
 int agnn_gemm_grouped(int precision, int a_layout, int b_layout, int n_problems, const agnn_gemm_problem_t* problems,
                       int32_t* tickets, int64_t n_tickets, agnn_stream_t stream);
 

@@ -91,7 +91,7 @@ def _run_oracle(ref, masks, fn, dtype):
     return outs, loss.detach(), grads, ov
 
 
-def _compare(name, ref, net, fn, operands, fwd_tol, grad_tol, with_fp64=True):
+def _compare(name, ref, net, fn, operands, fwd_tol, grad_tol, with_fp64=True, ill_conditioned_ok=False):
     """``fn(model, device, dtype) -> (dict of outputs, scalar loss)``."""
     routes_before = dict(_lib.library_routes)
     repacked_before = linalg.stats["repacked_gemms"]
@@ -136,7 +136,10 @@ def _compare(name, ref, net, fn, operands, fwd_tol, grad_tol, with_fp64=True):
     assert worst_f <= fwd_tol, rep
     assert rep["loss_err_vs_cpu_fp32"] <= fwd_tol, rep
     for n, e in errs.items():
-        assert e <= grad_tol, (n, e, rep)
+        # ill_conditioned_ok: a tensor the fp32 oracle itself cannot reproduce to grad_tol is held to the fp64 yardstick
+        # below instead (needs the fp64 run)
+        tol = max(grad_tol, 3 * e_cpu[n]) if (ill_conditioned_ok and with_fp64) else grad_tol
+        assert e <= tol, (n, e, tol, rep)
     for n in g_cuda:
         if n not in g32:                                   # unused in the oracle (None there)
             assert float(g_cuda[n].abs().max()) == 0.0, n
@@ -212,10 +215,11 @@ def test_config3_hgt_shell_fp32(operands):
     net = ann.AnalysisEncoder(b["metadata"], 25, HIDDEN, 128, TASKS, LAYERS, dropout=0.0, encoder_type="hgt")
     net.load_state_dict(ref.state_dict())
     net.to(DEV)
-    # k_rel / p_rel gradients are softmax-gradient cancellations, ill-conditioned in fp32 itself: the fp64 yardstick
-    # inside _compare is the binding check for them; 3e-4 is the coarse bound against the fp32 oracle
-    _compare("config3_hgt_shell", ref, net, _shell_fn(b), operands, fwd_tol=3 * FP32_REL, grad_tol=30 * FP32_REL,
-             with_fp64=operands == "f16")
+    # forward / loss: 1e-5.  Gradients: 1e-5 wherever the CPU fp32 oracle itself is that close to its fp64 run; the
+    # k_rel / p_rel gradients are softmax-gradient cancellations (the fp32 oracle is 1e-2 away from fp64 on them, measured)
+    # and are held to 3x the fp32 oracle's own distance from fp64 -- per tensor, inside _compare
+    _compare("config3_hgt_shell", ref, net, _shell_fn(b), operands, fwd_tol=FP32_REL, grad_tol=FP32_REL,
+             with_fp64=True, ill_conditioned_ok=True)
 
 
 def test_config3_hgt_stack_bf16_mode():

@@ -185,7 +185,11 @@ def test_split_k_is_reduced_inside_the_launch_deterministically():
     lib = _lib.lib()
     sa, sb = linalg.split(a), linalg.split(b)
     m, n, k = 384, 256, 50000
-    sk = lib.agnn_gemm_split_k(_lib.GEMM_TF32X3, m, n, k)
+    import ctypes as C
+    one = lambda v: (C.c_int64 * 1)(v)
+    split = (C.c_int32 * 1)()
+    _lib.check(lib.agnn_gemm_group_split_k(_lib.GEMM_TF32X3, 1, one(m), one(n), one(k), split))
+    sk = int(split[0])                                         # the split count the grouped launch chose
     assert sk > 1
     ws = torch.empty(lib.agnn_gemm_workspace(_lib.GEMM_TF32X3, m, n, k, sk), dtype=torch.uint8, device=DEV)
     out = torch.empty(m, n, device=DEV)
