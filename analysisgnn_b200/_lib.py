@@ -85,7 +85,14 @@ class GemmProblem(C.Structure):
                 ("amax_out", C.c_void_p)]
 
 
+class SplitItem(C.Structure):
+    """agnn_split_item_t"""
+    _fields_ = [("x", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64), ("ld_x", C.c_int64), ("hi", C.c_void_p),
+                ("lo", C.c_void_p), ("ld_out", C.c_int64), ("amax", C.c_void_p)]
+
+
 GEMM_MAX_GROUP = 12
+SPLIT_MULTI_MAX = 24
 
 
 class ParamChunk(C.Structure):
@@ -138,6 +145,7 @@ _PROTOTYPES = {
     "agnn_gemm_scaled": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "agnn_split_f16_multi": (C.c_int, [C.c_int, C.POINTER(SplitItem), C.c_void_p]),
     "agnn_gemm_tickets": (C.c_int64, [C.c_int64, C.c_int64, C.c_int]),
     "agnn_gemm_group_split_k": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                           C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),

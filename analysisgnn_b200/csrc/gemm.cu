@@ -680,36 +680,83 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
-// out[m, n] (+)= bias[n] + sum_s partial[s][m][n]   (fixed order => deterministic), optional ReLU
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int split_k,
-                                                             int64_t split_stride, int64_t M, int N, int64_t ld_p,
-                                                             void* __restrict__ out, int64_t ldc,
-                                                             const float* __restrict__ bias, int flags,
-                                                             float* __restrict__ amax_out) {
-  const int64_t total = M * N;
+// C (+)= bias + sum_s partial[s] for every split-K problem of a grouped launch, in split order (deterministic),
+// optional ReLU / bf16 output / amax.  One launch for the whole group: blocks are dealt to the problems in proportion
+// to their output size; a thread owns one float4 of C and keeps 8 partial loads in flight.
+struct ReduceGroup {
+  int n_prob;
+  int blk_start[kMaxGroup + 1];
+  struct P {
+    const float* part; int split_k; int64_t split_stride, ld_p;
+    void* out; int64_t ldc; const float* bias; int flags; int M, N; float* amax_out;
+  } prob[kMaxGroup];
+};
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ ReduceGroup grp) {
+  int g = 0;
+  while (g + 1 < grp.n_prob && (int)blockIdx.x >= grp.blk_start[g + 1]) ++g;
+  const ReduceGroup::P& p = grp.prob[g];
+  const int n4 = (p.N + 3) / 4;
+  const int64_t total = (int64_t)p.M * n4;
+  const int64_t nblk = grp.blk_start[g + 1] - grp.blk_start[g];
   uint32_t mx = 0;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    const int64_t m = i / N;
-    const int n = (int)(i - m * N);
-    float acc = bias ? __ldg(bias + n) : 0.f;
-    for (int s = 0; s < split_k; ++s) acc += part[s * split_stride + m * ld_p + n];
-    if (flags & AGNN_GEMM_OUT_BF16) {
-      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + m * ldc + n;
-      if (flags & AGNN_GEMM_ACCUMULATE) acc += __bfloat162float(*o);
-      if (flags & AGNN_GEMM_RELU) acc = fmaxf(acc, 0.f);
-      *o = __float2bfloat16_rn(acc);
-    } else {
-      float* o = static_cast<float*>(out) + m * ldc + n;
-      if (flags & AGNN_GEMM_ACCUMULATE) acc += *o;
-      if (flags & AGNN_GEMM_RELU) acc = fmaxf(acc, 0.f);
-      *o = acc;
+  for (int64_t i = (int64_t)(blockIdx.x - grp.blk_start[g]) * 256 + threadIdx.x; i < total; i += nblk * 256) {
+    const int64_t m = i / n4;
+    const int n = (int)(i - m * n4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) {
+      acc.x = __ldg(p.bias + n);
+      if (n + 1 < p.N) acc.y = __ldg(p.bias + n + 1);
+      if (n + 2 < p.N) acc.z = __ldg(p.bias + n + 2);
+      if (n + 3 < p.N) acc.w = __ldg(p.bias + n + 3);
     }
-    mx = max(mx, __float_as_uint(acc) & 0x7fffffffu);
+    const float* src = p.part + m * p.ld_p + n;
+    int sp = 0;
+    for (; sp + 8 <= p.split_k; sp += 8) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(sp + u) * p.split_stride));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; }
+    }
+    for (; sp < p.split_k; ++sp) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src + (int64_t)sp * p.split_stride));
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (p.flags & AGNN_GEMM_OUT_BF16) {
+      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n + e < p.N) {
+          float x = v[e];
+          if (p.flags & AGNN_GEMM_ACCUMULATE) x += __bfloat162float(o[e]);
+          if (p.flags & AGNN_GEMM_RELU) x = fmaxf(x, 0.f);
+          mx = max(mx, __float_as_uint(x) & 0x7fffffffu);
+          o[e] = __float2bfloat16_rn(x);
+        }
+    } else {
+      float* o = static_cast<float*>(p.out) + m * p.ldc + n;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n + e < p.N) {
+          if (p.flags & AGNN_GEMM_ACCUMULATE) v[e] += o[e];
+          if (p.flags & AGNN_GEMM_RELU) v[e] = fmaxf(v[e], 0.f);
+          mx = max(mx, __float_as_uint(v[e]) & 0x7fffffffu);
+        }
+      if (n + 4 <= p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < p.N) o[e] = v[e];
+      }
+    }
   }
-  if (amax_out) {
+  if (p.amax_out) {
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if ((threadIdx.x & 31) == 0 && mx) atomicMax(reinterpret_cast<unsigned int*>(amax_out), mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(reinterpret_cast<unsigned int*>(p.amax_out), mx);
   }
 }
 
@@ -914,6 +961,92 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
   }
 }
 
+// ---- amax + fp16 pair of SEVERAL small matrices (the weights of a grouped launch) in one launch ----------------------
+// One cluster of 8 CTAs per matrix: every CTA takes the maximum over its share, the eight partial maxima meet through
+// distributed shared memory (one cluster barrier), every CTA then splits its share with the common scale.  Replaces
+// two launches per weight and step (agnn_amax + agnn_split_f16) by one launch per GEMM group.
+constexpr int kSplitCluster = 8;
+
+struct SplitMulti {
+  int n;
+  struct T {
+    const float* x; int64_t rows; int cols4; int64_t ld_x;
+    __half* hi; __half* lo; int64_t ld_o; float* amax;
+  } t[AGNN_SPLIT_MULTI_MAX];
+};
+
+__global__ void __cluster_dims__(kSplitCluster, 1, 1) __launch_bounds__(256)
+split_f16_multi_kernel(const __grid_constant__ SplitMulti p) {
+  __shared__ uint32_t red[8];
+  __shared__ uint32_t cta_max;
+  const SplitMulti::T& t = p.t[blockIdx.x / kSplitCluster];
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int64_t total = t.rows * t.cols4;
+  uint32_t m = 0;
+  for (int64_t i = (int64_t)rank * 256 + threadIdx.x; i < total; i += (int64_t)kSplitCluster * 256) {
+    const int64_t r = i / t.cols4;
+    const int c = (int)(i - r * t.cols4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(t.x + r * t.ld_x + c));
+    m = max(max(m, __float_as_uint(v.x) & 0x7fffffffu), __float_as_uint(v.y) & 0x7fffffffu);
+    m = max(max(m, __float_as_uint(v.z) & 0x7fffffffu), __float_as_uint(v.w) & 0x7fffffffu);
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = max(m, red[w]);
+    cta_max = m;
+  }
+  // all eight partial maxima are written ...
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  uint32_t all = 0;
+#pragma unroll
+  for (uint32_t r = 0; r < kSplitCluster; ++r) {
+    uint32_t remote, v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(&cta_max)), "r"(r));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+    all = max(all, v);
+  }
+  // ... and read: nobody leaves (or overwrites) before the others are done with its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const float amax = __uint_as_float(all);
+  if (rank == 0 && threadIdx.x == 0) *t.amax = amax;
+  const float s = f16_scale_of(amax);
+  for (int64_t i = (int64_t)rank * 256 + threadIdx.x; i < total; i += (int64_t)kSplitCluster * 256) {
+    const int64_t r = i / t.cols4;
+    const int c = (int)(i - r * t.cols4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(t.x + r * t.ld_x + c));
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    uint2 h, l;
+    f16_pair4(in, s, h, l);
+    *reinterpret_cast<uint2*>(t.hi + r * t.ld_o + c) = h;
+    *reinterpret_cast<uint2*>(t.lo + r * t.ld_o + c) = l;
+  }
+}
+
+extern "C" int agnn_split_f16_multi(int n, const agnn_split_item_t* items, agnn_stream_t stream) {
+  if (n < 0 || n > AGNN_SPLIT_MULTI_MAX || (n && !items))
+    return fail(AGNN_ERR_ARG, "split_f16_multi: 0..%d matrices per launch, got %d", AGNN_SPLIT_MULTI_MAX, n);
+  if (n == 0) return AGNN_OK;
+  SplitMulti p;
+  p.n = n;
+  for (int i = 0; i < n; ++i) {
+    const agnn_split_item_t& q = items[i];
+    if (q.rows <= 0 || q.cols <= 0 || q.cols % 4 || (q.ld_x * 4) % 16 || (q.ld_out * 2) % 16 || !q.x || !q.hi || !q.lo ||
+        !q.amax || !aligned16(q.x) || !aligned16(q.hi) || !aligned16(q.lo))
+      return fail(AGNN_ERR_ARG, "split_f16_multi: matrix %d needs 16-byte aligned rows, a column count multiple of 4 and "
+                                "non-null pointers", i);
+    p.t[i].x = q.x; p.t[i].rows = q.rows; p.t[i].cols4 = (int)(q.cols / 4); p.t[i].ld_x = q.ld_x;
+    p.t[i].hi = static_cast<__half*>(q.hi); p.t[i].lo = static_cast<__half*>(q.lo); p.t[i].ld_o = q.ld_out;
+    p.t[i].amax = q.amax;
+  }
+  split_f16_multi_kernel<<<n * kSplitCluster, 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("split_f16_multi");
+}
+
 extern "C" int agnn_amax(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* amax, agnn_stream_t stream) {
   if (rows < 0 || cols < 0 || !amax) return fail(AGNN_ERR_ARG, "amax: bad arguments");
   if (rows == 0 || cols == 0) return AGNN_OK;
@@ -1076,18 +1209,28 @@ extern "C" int agnn_gemm_grouped(int precision, int a_layout, int b_layout, int 
   else if (precision == AGNN_GEMM_TF32X3) rc = dispatch_layout<kFmtTF32, 3>(a_mn, b_mn, grp, grid, st);
   else rc = dispatch_layout<kFmtTF32, 1>(a_mn, b_mn, grp, grid, st);
   if (rc) return rc;
-  // without ticket counters the partials are reduced by a second kernel (fixed order as well)
+  // without ticket counters the partials of ALL split problems are reduced by one more launch (fixed order as well)
+  static thread_local ReduceGroup red;
+  red.n_prob = 0;
+  int64_t blocks = 0;
   for (int i = 0; i < grp.n_prob; ++i) {
     const GemmParams& p = grp.prob[i];
     if (p.split_k > 1 && !p.tickets) {
-      int64_t blocks = ceil_div((int64_t)p.M * p.N, 256);
-      if (blocks > kNumSM * 8) blocks = kNumSM * 8;
-      splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(p.out), p.split_k, p.split_stride,
-                                                              p.M, p.N, p.ldc, p.c_final, p.ldc_final, p.bias, p.flags,
-                                                              p.amax_out);
-      rc = check_launch("gemm split-K reduce");
-      if (rc) return rc;
+      ReduceGroup::P& r = red.prob[red.n_prob];
+      r.part = static_cast<const float*>(p.out); r.split_k = p.split_k; r.split_stride = p.split_stride; r.ld_p = p.ldc;
+      r.out = p.c_final; r.ldc = p.ldc_final; r.bias = p.bias; r.flags = p.flags; r.M = p.M; r.N = p.N;
+      r.amax_out = p.amax_out;
+      red.blk_start[red.n_prob++] = (int)blocks;
+      int64_t b = ceil_div((int64_t)p.M * ((p.N + 3) / 4), 256);
+      if (b > kNumSM * 4) b = kNumSM * 4;
+      blocks += b;
     }
+  }
+  if (red.n_prob) {
+    red.blk_start[red.n_prob] = (int)blocks;
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(red);
+    rc = check_launch("gemm split-K reduce");
+    if (rc) return rc;
   }
   return AGNN_OK;
 }

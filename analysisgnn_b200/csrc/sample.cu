@@ -46,6 +46,9 @@ struct WindowParams {
 };
 
 __device__ __forceinline__ bool window_edge(const WindowParams& p, int64_t t, int& b, int64_t& e) {
+  // n_cand may be an UPPER BOUND of the candidate count (a static-shape loader sizes its launch without reading the
+  // device): positions behind the real total, cand_ptr[n_slots], flag nothing
+  if (t >= __ldg(p.cand_ptr + p.n_slots)) return false;
   b = upper_bound64(p.cand_ptr, 0, p.n_slots + 1, t) - 1;
   e = __ldg(p.edge_lo + b) + (t - __ldg(p.cand_ptr + b));
   const int64_t lo = __ldg(p.node_lo + b), hi = lo + __ldg(p.win_size + b);

@@ -141,23 +141,102 @@ class TypedCSR:
         return self._t
 
 
+class TypedEdges:
+    """Several edge types between ONE pair of node types as a typed COO of fixed capacity: ``edge_index`` [2, cap]
+    (row 0 = source, row 1 = target), ``edge_type`` [cap] with codes ``0..len(names)-1`` and ``-1`` for unused slots
+    (dropped by agnn_csr_build).  This is what a static-shape (CUDA-graph replayable) loader emits: no per-type
+    compaction, so no shape depends on the data."""
+
+    def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, names: Sequence[Tuple[str, str, str]]):
+        self.edge_index, self.edge_type = edge_index, edge_type
+        self.names = [tuple(n) for n in names]
+        if len({(n[0], n[2]) for n in self.names}) != 1:
+            raise ValueError("TypedEdges: all edge types must connect the same pair of node types")
+
+
+class TypedEdgeDict(dict):
+    """An ``edge_index_dict`` backed by ``TypedEdges`` groups (plus ordinary ``[2, E]`` entries).  Looks like the PyG
+    dict to generic consumers -- ``d[edge_type]`` is a ``[2, cap]`` tensor whose slots of other types are -1 (made on
+    first use) -- while ``hetero_csr`` builds every group in one typed pass."""
+
+    def __init__(self, groups: Sequence[TypedEdges], plain: Optional[dict] = None):
+        super().__init__()
+        self.groups = list(groups)
+        self._where = {}
+        for gi, g in enumerate(self.groups):
+            for k, name in enumerate(g.names):
+                self._where[name] = (gi, k)
+                dict.__setitem__(self, name, None)
+        for k, v in (plain or {}).items():
+            dict.__setitem__(self, tuple(k), v)
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if v is None:
+            gi, k = self._where[key]
+            g = self.groups[gi]
+            v = torch.where((g.edge_type == k).unsqueeze(0), g.edge_index, torch.full_like(g.edge_index, -1))
+            dict.__setitem__(self, key, v)
+        return v
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def index_tensors(self):
+        """The tensors whose identity / version define the structure (cache key)."""
+        out = []
+        for g in self.groups:
+            out += [g.edge_index, g.edge_type]
+        return out + [dict.__getitem__(self, k) for k in self.keys() if k not in self._where]
+
+
+class _CSRView:
+    """Relation ``k`` of a typed CSR as a single-relation CSR (what ``ops.rel_of(csr, 0, ...)`` reads)."""
+
+    __slots__ = ("rowptr", "col", "perm", "n_rows", "n_cols", "n_rel", "n_edges", "heavy", "n_heavy", "heavy_cap")
+
+    def __init__(self, parent: CSR, k: int):
+        self.rowptr, self.col, self.perm = parent.rowptr[k:k + 1], parent.col, parent.perm
+        self.n_rows, self.n_cols, self.n_rel, self.n_edges = parent.n_rows, parent.n_cols, 1, parent.n_edges
+        self.heavy = parent.heavy[k:k + 1] if parent.heavy is not None else None
+        self.n_heavy = parent.n_heavy[k:k + 1] if parent.n_heavy is not None else None
+        self.heavy_cap = parent.heavy_cap
+
+
 class HeteroCSR:
     """PyG convention for an ``edge_index_dict``: per edge type ``(src, rel, dst)``
     ``fwd[et]`` has rows = dst nodes / cols = src ids, ``bwd[et]`` rows = src nodes /
-    cols = dst ids."""
+    cols = dst ids.  A ``TypedEdgeDict`` is built group by group (one typed segment pair per group)."""
 
     def __init__(self, edge_index_dict, num_nodes: Dict[str, int], validate=False):
         self.edge_types: List[Tuple[str, str, str]] = [tuple(et) for et in edge_index_dict.keys()]
         self.num_nodes = {k: int(v) for k, v in num_nodes.items()}
+        groups = edge_index_dict.groups if isinstance(edge_index_dict, TypedEdgeDict) else []
+        grouped = {n for g in groups for n in g.names}
+        plain = [et for et in self.edge_types if et not in grouped]
         segs = []
-        for et in self.edge_types:
+        for g in groups:
+            ns, nd = self.num_nodes[g.names[0][0]], self.num_nodes[g.names[0][2]]
+            ei, r = g.edge_index, len(g.names)
+            segs.append(Segment(ei[1], ei[0], nd, ns, g.edge_type, r))
+            segs.append(Segment(ei[0], ei[1], ns, nd, g.edge_type, r))
+        for et in plain:
             ei = edge_index_dict[et]
             ns, nd = self.num_nodes[et[0]], self.num_nodes[et[2]]
             segs.append(Segment(ei[1], ei[0], nd, ns))
             segs.append(Segment(ei[0], ei[1], ns, nd))
         built = build_csr(segs, validate=validate)
-        self.fwd = {et: built[2 * i] for i, et in enumerate(self.edge_types)}
-        self.bwd = {et: built[2 * i + 1] for i, et in enumerate(self.edge_types)}
+        self.fwd, self.bwd = {}, {}
+        for gi, g in enumerate(groups):
+            for k, name in enumerate(g.names):
+                if name in self.edge_types:
+                    self.fwd[name], self.bwd[name] = _CSRView(built[2 * gi], k), _CSRView(built[2 * gi + 1], k)
+        base = 2 * len(groups)
+        for i, et in enumerate(plain):
+            self.fwd[et], self.bwd[et] = built[base + 2 * i], built[base + 2 * i + 1]
         self.n_edges = {et: self.fwd[et].n_edges for et in self.edge_types}
 
 
@@ -220,7 +299,10 @@ def hetero_csr(edge_index_dict, num_nodes: Dict[str, int]) -> HeteroCSR:
     if isinstance(edge_index_dict, HeteroCSR):
         return edge_index_dict
     ets = list(edge_index_dict.keys())
-    tensors = [edge_index_dict[et] for et in ets]
+    if isinstance(edge_index_dict, TypedEdgeDict):
+        tensors = edge_index_dict.index_tensors()
+    else:
+        tensors = [edge_index_dict[et] for et in ets]
     extra = ("hetero", tuple(ets), tuple(sorted(num_nodes.items())))
     return _cache.get(tensors, extra, lambda: HeteroCSR(edge_index_dict, num_nodes))
 

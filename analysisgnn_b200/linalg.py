@@ -155,6 +155,7 @@ def known_amax(t) -> Optional[torch.Tensor]:
     return None
 
 
+trace_amax = None        # a dict when bench.py wants the amax passes attributed
 _const_scalars = {}
 
 
@@ -173,6 +174,12 @@ def amax_of(t: torch.Tensor) -> torch.Tensor:
     am = known_amax(t)
     if am is None:
         stats["amax_passes"] = stats.get("amax_passes", 0) + 1
+        if trace_amax is not None:                 # bench.py: which tensors still need a pass, by shape and caller
+            import sys
+            f = sys._getframe(1)
+            site = f"{f.f_code.co_name}<{f.f_back.f_code.co_name}" if f.f_back else f.f_code.co_name
+            key = f"{tuple(t.shape)} {site}"
+            trace_amax[key] = trace_amax.get(key, 0) + 1
         am = amax_into(new_amax(t.device), t)
     return am
 
@@ -327,6 +334,39 @@ def _cached_split_f16(x: torch.Tensor) -> SplitH:
     return hit[1]
 
 
+def presplit_f16(tensors) -> None:
+    """The fp16 operand pairs of several small fp32 matrices (the weights of a grouped launch) in ONE launch
+    (agnn_split_f16_multi), left in the per-step split cache where ``_as_operand`` finds them."""
+    todo, seen = [], set()
+    for x in tensors:
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and f16_ok(x) and x.numel() <= _SPLIT_CACHE_MAX_ELEMS):
+            continue
+        key = ("f16", x.data_ptr(), tuple(x.shape), x.stride(0), x._version)
+        if key in _split_cache or key in seen:
+            continue
+        seen.add(key)
+        todo.append((key, x))
+    if len(todo) < 2:
+        return                                     # a single matrix: the ordinary two-launch route
+    lib = _lib.lib()
+    for lo in range(0, len(todo), _lib.SPLIT_MULTI_MAX):
+        chunk = todo[lo:lo + _lib.SPLIT_MULTI_MAX]
+        dev = chunk[0][1].device
+        arr = (_lib.SplitItem * len(chunk))()
+        made = []
+        for q, (key, x) in zip(arr, chunk):
+            buf = torch.empty((2, x.shape[0], x.shape[1]), dtype=torch.float16, device=dev)
+            am = new_amax(dev)
+            q.x, q.rows, q.cols, q.ld_x = x.data_ptr(), x.shape[0], x.shape[1], x.stride(0)
+            q.hi, q.lo, q.ld_out, q.amax = buf[0].data_ptr(), buf[1].data_ptr(), x.shape[1], am.data_ptr()
+            made.append((key, x, SplitH(buf[0], buf[1], am)))
+        _lib.check(lib.agnn_split_f16_multi(len(chunk), arr, torch.cuda.current_stream(dev).cuda_stream),
+                   "agnn_split_f16_multi")
+        _lib.count_launches(1)
+        for key, x, sp in made:
+            _remember(key, (x, sp))
+
+
 def _as_operand(x: Operand, f16: bool = False):
     """(hi, lo, precision, amax) for agnn_gemm, or None when the tensor cannot take the tcgen05 route.  ``f16``: the
     other operand is an fp16 pair, so a plain fp32 tensor is split the same way."""
@@ -354,6 +394,7 @@ def plain(x: Operand) -> torch.Tensor:
 _plain = plain
 
 
+SPLITK_IN_KERNEL = os.environ.get("AGNN_SPLITK", "kernel") == "tickets"
 _ticket_pools = {}       # (device, stream) -> zeroed int32 counters for the in-kernel split-K reduction
 _TICKETS = 16384
 
@@ -425,7 +466,9 @@ def _launch(prec: int, a_layout: int, b_layout: int, problems) -> None:
             q.c, q.ldc, q.bias, q.flags, q.split_k = p.out.data_ptr(), p.out.stride(0), ptr(p.bias), p.flags, p.split_k
             q.workspace, q.workspace_bytes, q.amax_out = ptr(p.ws), p.ws_bytes, ptr(p.amax_out)
             need += lib.agnn_gemm_tickets(p.m, p.n, p.split_k)
-        tickets = _tickets(dev) if 0 < need <= _TICKETS else None      # None: the two-kernel split-K reduction
+        # split-K partials: added in split order either by ONE grouped reduce kernel behind the launch (default) or, with
+        # ticket counters, inside the launch by the CTA that stores a tile's last partial (AGNN_SPLITK=tickets)
+        tickets = _tickets(dev) if (SPLITK_IN_KERNEL and 0 < need <= _TICKETS) else None
         stream = torch.cuda.current_stream(dev).cuda_stream
 
         def run():
@@ -438,8 +481,7 @@ def _launch(prec: int, a_layout: int, b_layout: int, problems) -> None:
             timer.launch("gemm", flops, dev, run, tag=(a_layout, b_layout, big.m, big.n, big.k, big.split_k, len(chunk)))
         else:
             run()
-        extra = 0 if tickets is not None or need == 0 else sum(1 for p in chunk if p.split_k > 1)
-        _lib.count_launches(1 + extra)
+        _lib.count_launches(1 if tickets is not None or need == 0 else 2)
         stats["gemm_launches"] = stats.get("gemm_launches", 0) + 1
         stats["gemm_problems"] = stats.get("gemm_problems", 0) + len(chunk)
 
@@ -461,7 +503,18 @@ def _group(a_layout: int, b_layout: int, specs):
     problems whose operands need a repack run alone.  Returns the outputs in order."""
     outs = [None] * len(specs)
     by_prec = {}
+    # plain fp32 operands that will meet an fp16 pair (the weights): all their pairs in one launch
+    presplit_f16([sp["b"] if isinstance(sp["a"], SplitH) else sp["a"] for sp in specs
+                  if isinstance(sp["a"], SplitH) != isinstance(sp["b"], SplitH) and sp["m"] > 0 and sp["n"] > 0])
     for i, sp in enumerate(specs):
+        if sp["m"] == 0 or sp["n"] == 0:           # an empty member (a node type without nodes in this batch)
+            if sp.get("out") is not None:
+                outs[i] = sp["out"]
+            else:
+                a0 = sp["a"].hi if isinstance(sp["a"], (Split, SplitH)) else sp["a"]
+                dt = torch.bfloat16 if a0.dtype == torch.bfloat16 else torch.float32
+                outs[i] = torch.zeros((sp["m"], sp["n"]), dtype=dt, device=a0.device)
+            continue
         r = _resolve(sp["a"], sp["b"], sp["m"], sp["n"], sp["k"], sp.get("bias"), sp.get("flags", 0), sp.get("out"),
                      None, sp.get("amax_out"))
         if r is None:

@@ -143,7 +143,9 @@ def _layer_structures(conv_layers, x_dict, ei_dict, nodes_per_hop, edges_per_hop
     """One ``HeteroCSR`` per layer (trimmed edge lists differ per layer), built in a
     single batched agnn_csr_build pass and cached per batch."""
     sizes = {t: v.shape[0] for t, v in x_dict.items()}
-    ei_dict = {et: v for et, v in ei_dict.items() if et[0] in sizes and et[2] in sizes}
+    if not (isinstance(ei_dict, graph.TypedEdgeDict) and edges_per_hop is None
+            and all(et[0] in sizes and et[2] in sizes for et in ei_dict.keys())):
+        ei_dict = {et: ei_dict[et] for et in ei_dict.keys() if et[0] in sizes and et[2] in sizes}
     ets = list(ei_dict.keys())
     if edges_per_hop is None:
         csr = graph.hetero_csr(ei_dict, sizes)

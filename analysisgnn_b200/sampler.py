@@ -301,3 +301,147 @@ class ScoreGraphLoader:
         out["batch_dict"] = {"note": batch_vec}
         out["extras"] = {k: v.index_select(0, node_index) for k, v in c.extras.items()}
         return out
+
+
+class StaticBatcher:
+    """Batches of fixed SHAPE built entirely on the device from a resident ``Corpus`` -- the form a CUDA graph can
+    replay: the whole loader step (window selection, induced note -> note edges, beat / measure nodes and their
+    edges, feature and label gathers) is a fixed sequence of launches on static buffers, fed by ONE small host -> device
+    copy per step (``select``: the ``[2, batch_size]`` score ids and window starts, host arithmetic of the counter RNG).
+
+    What varies from batch to batch lives in padding: the typed note -> note COO has ``edge_cap`` slots (the maximum any
+    ``batch_size`` windows of this corpus can need), unused ones carry type / index -1 and are dropped by
+    agnn_csr_build; beat / measure node arrays have ``beat_cap`` / ``measure_cap`` rows, the unused ones are isolated
+    zero-feature nodes that no note ever sees.  Every score must have at least ``subgraph_size`` notes (each window
+    then has exactly that many: the sequence layout of the GRU branch is static too); shorter scores belong to the
+    eager ``ScoreGraphLoader``.
+
+    Replaces graphmuse ``MuseNeighborLoader`` + ``transform_to_pyg`` with ``add_beats / add_measures``
+    (analysisgnn/data/datamodules/analysis.py:217-225, 270-293; node and edge types per analysisgnn/utils/hgraph.py:
+    41-73 and data/data_utils.py:194) for full-window batches (``num_neighbors`` hops: ``ScoreGraphLoader``)."""
+
+    REL = ScoreGraphLoader.REL_NAMES
+
+    def __init__(self, corpus: Corpus, subgraph_size: int, batch_size: int, beat_of: Optional[torch.Tensor] = None,
+                 measure_of: Optional[torch.Tensor] = None, reverse: bool = True):
+        c, s, b = corpus, int(subgraph_size), int(batch_size)
+        dev = c.x.device
+        if dev.type != "cuda":
+            raise _lib.AgnnError("analysisgnn_b200 has no CPU path: the sampler needs CUDA tensors")
+        sizes = np.diff(np.asarray(c.node_ptr))
+        if sizes.min() < s:
+            raise ValueError(f"StaticBatcher: every score needs >= {s} notes (shortest has {int(sizes.min())})")
+        self.corpus, self.s, self.b, self.reverse = c, s, b, reverse
+        i64 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int64, device=dev)
+        self.node_ptr, self.edge_ptr = i64(c.node_ptr), i64(c.edge_ptr)
+        n = c.node_ptr[-1]
+        # ---- capacities (one pass over the corpus, once): the most edges any window holds, the widest beat span
+        src, dst = c.edges[0], c.edges[1]
+        lo, hi = torch.minimum(src, dst), torch.maximum(src, dst)
+        score = torch.bucketize(lo, self.node_ptr[1:], right=True)
+        inside = (hi - lo) < s
+        first = torch.maximum(hi - s + 1, self.node_ptr[score])[inside]     # first / last window start holding the edge
+        last = lo[inside]
+        diff = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+        diff.index_add_(0, first, torch.ones_like(first))
+        diff.index_add_(0, last + 1, -torch.ones_like(last))
+        per_window = int(torch.cumsum(diff, 0).max()) if first.numel() else 0
+        self.edge_cap = max(b * per_window, 1)
+        self.cand_cap = max(b * int(np.diff(np.asarray(c.edge_ptr)).max()), 1)
+        note_score = torch.bucketize(torch.arange(n, device=dev), self.node_ptr[1:], right=True)
+        idx = torch.arange(max(n - s + 1, 0), device=dev)
+        same = note_score[idx] == note_score[idx + s - 1]
+        self.virtual = {}
+        for name, of in (("beat", beat_of), ("measure", measure_of)):
+            if of is None:
+                continue
+            of = of.to(dev, torch.int64)
+            span = torch.where(same, of[idx + s - 1] - of[idx] + 1, torch.zeros_like(idx))
+            self.virtual[name] = (of, max(b * int(span.max()), 1))
+        # ---- constants of every batch
+        self.arange_s = torch.arange(s, device=dev)
+        self.win = torch.full((b,), s, dtype=torch.int32, device=dev)
+        self.out_off = torch.arange(b, device=dev) * s
+        self.note_batch = torch.arange(b, device=dev).repeat_interleave(s)
+        self.note_ids = torch.arange(b * s, device=dev)
+        names = [("note", r, "note") for r in self.REL[:c.n_rel]]
+        if reverse:
+            names += [("note", r + "_rev", "note") for r in self.REL[1:c.n_rel]]
+        self.names = names
+        self.zeros = {name: torch.zeros((cap, c.x.shape[1]), dtype=c.x.dtype, device=dev)
+                      for name, (_, cap) in self.virtual.items()}
+        self._host = torch.empty((2, b), dtype=torch.int64).pin_memory()
+
+    @property
+    def metadata(self):
+        node_types = ["note"] + list(self.virtual)
+        edge_types = list(self.names)
+        for v in self.virtual:
+            edge_types += [("note", "connects", v), (v, "connects_rev", "note"), (v, "next", v)]
+        return node_types, edge_types
+
+    def select(self, loader: ScoreGraphLoader, epoch: int, index: int) -> torch.Tensor:
+        """Host side of a step: the scores of global batch ``index`` this rank takes and their window starts (the
+        counter RNG of ``ScoreGraphLoader``), in a pinned ``[2, batch_size]`` tensor to be copied into the static
+        device selector (``non_blocking``)."""
+        c = self.corpus
+        ids = loader.batch_ids(epoch, index)
+        if len(ids) != self.b:
+            raise ValueError(f"StaticBatcher: batch {index} has {len(ids)} scores on this rank, the static shape is "
+                             f"{self.b} (use a corpus size that is a multiple of batch_size x world_size)")
+        step_seed = rng_u64(loader.seed, 0x424154, epoch, index, 0)
+        starts = [window_start(step_seed, g, c.node_ptr[g + 1] - c.node_ptr[g], self.s) for g in ids]
+        self._host[0] = torch.tensor(ids, dtype=torch.int64)
+        self._host[1] = torch.tensor(starts, dtype=torch.int64)
+        return self._host
+
+    def batch(self, sel: torch.Tensor) -> dict:
+        """``sel``: DEVICE int64 ``[2, batch_size]`` (score ids, window starts).  No host read, no data-dependent
+        shape: capturable.  Returns the dict layout of ``ScoreGraphLoader.batch``."""
+        c, s, b = self.corpus, self.s, self.b
+        dev = sel.device
+        ids, starts = sel[0], sel[1]
+        node_lo = self.node_ptr[ids] + starts
+        node_index = (node_lo.unsqueeze(1) + self.arange_s).reshape(-1)
+        # note -> note edges induced by the windows, in corpus order per slot
+        e_lo = self.edge_ptr[ids]
+        cand_ptr = torch.zeros(b + 1, dtype=torch.int64, device=dev)
+        cand_ptr[1:] = torch.cumsum(self.edge_ptr[ids + 1] - e_lo, 0)
+        lib = _lib.lib()
+        ws_bytes = lib.agnn_window_workspace(self.cand_cap)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        edges = torch.full((3, self.edge_cap), -1, dtype=torch.int64, device=dev)
+        _lib.check(lib.agnn_window_subgraph(b, self.cand_cap, cand_ptr.data_ptr(), e_lo.data_ptr(), node_lo.data_ptr(),
+                                            self.win.data_ptr(), self.out_off.data_ptr(), c.edges[0].data_ptr(),
+                                            c.edges[1].data_ptr(), c.edges[2].data_ptr(), edges.data_ptr(), None,
+                                            self.edge_cap, n_out.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev)),
+                   "agnn_window_subgraph")
+        _lib.count_launches(5)
+        ei, et = edges[:2], edges[2]
+        if self.reverse:
+            rev = torch.where(et > 0, et + (c.n_rel - 1), torch.full_like(et, -1))
+            ei, et = torch.cat((ei, ei.flip(0)), dim=1), torch.cat((et, rev))
+        plain, x_dict, batch_dict = {}, {"note": c.x.index_select(0, node_index)}, {"note": self.note_batch}
+        for name, (of, cap) in self.virtual.items():
+            first, last = of[node_lo], of[node_lo + (s - 1)]
+            count = last - first + 1
+            end = torch.cumsum(count, 0)
+            off = end - count
+            local = (of[node_index].view(b, s) - first.unsqueeze(1) + off.unsqueeze(1)).reshape(-1)
+            up = torch.stack((self.note_ids, local))
+            k = torch.arange(cap, device=dev)
+            slot = torch.bucketize(k, end, right=True)
+            slot_c = slot.clamp(max=b - 1)
+            ok = (slot < b) & (k + 1 < end[slot_c])
+            nxt = torch.where(ok.unsqueeze(0), torch.stack((k, k + 1)), torch.full((2, cap), -1, dtype=torch.int64,
+                                                                                    device=dev))
+            plain[("note", "connects", name)] = up
+            plain[(name, "connects_rev", "note")] = up.flip(0)
+            plain[(name, "next", name)] = nxt
+            x_dict[name] = self.zeros[name]
+            batch_dict[name] = slot_c
+        eid = graph.TypedEdgeDict([graph.TypedEdges(ei, et, self.names)], plain)
+        return {"batch_size": b * s, "node_index": node_index, "x_dict": x_dict, "edge_index_dict": eid,
+                "batch_dict": batch_dict, "num_sampled_nodes_dict": None, "num_sampled_edges_dict": None,
+                "extras": {k: v.index_select(0, node_index) for k, v in c.extras.items()}, "n_edges": n_out}

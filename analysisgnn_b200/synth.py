@@ -314,6 +314,45 @@ def hetero_batch(n_graphs: int, notes_per_graph: int, seed: int, voices: int = 4
     return out
 
 
+def corpus(n_scores: int, notes_per_score, seed: int, voices: int = 4, in_features: int = 25, task_dict=None):
+    """A synthetic corpus in the layout ``sampler.Corpus`` holds on the device: per-note features, typed note -> note
+    edges with GLOBAL node ids (the four forward types of analysisgnn/utils/hgraph.py:214-300), per-score node ranges,
+    per-note beat / measure ids (local to the score: ``floor(onset_beat)``, 4/4 measures -- hgraph.py:41-73) and the
+    per-note arrays the training step reads (spellings, key signatures, labels).  ``notes_per_score``: int or a
+    callable ``score -> int``."""
+    import torch
+
+    rng = np.random.default_rng(seed + 15485863)
+    task_dict = task_dict if task_dict is not None else {"cadence": 4, "localkey": 50, "romanNumeral": 185}
+    edges, beat_of, meas_of, node_ptr, n_beats, n_meas = [], [], [], [0], [], []
+    for g in range(n_scores):
+        n = notes_per_score(g) if callable(notes_per_score) else int(notes_per_score)
+        na = synth_note_array(n, seed * 100003 + g, voices)
+        e = score_graph_edges(na)
+        edges.append(np.stack((e[0] + node_ptr[-1], e[1] + node_ptr[-1], e[2])))
+        nb, be = beat_edges(na, reference_quirk=False)
+        nm, me = measure_edges(na, measure_bounds(na))
+        b = np.zeros(n, dtype=np.int64)
+        b[be[0]] = be[1]
+        m = np.zeros(n, dtype=np.int64)
+        m[me[0]] = me[1]
+        beat_of.append(b)
+        meas_of.append(m)
+        n_beats.append(nb)
+        n_meas.append(nm)
+        node_ptr.append(node_ptr[-1] + n)
+    total = node_ptr[-1]
+    extras = {"pitch_spelling": torch.from_numpy(rng.integers(0, 35, total)),
+              "key_signature": torch.from_numpy(rng.integers(0, 15, total))}
+    for t, c in task_dict.items():
+        extras[t] = torch.from_numpy(rng.integers(0, c, total))
+    return {"x": torch.from_numpy(rng.standard_normal((total, in_features), dtype=np.float32)),
+            "edges": torch.from_numpy(np.ascontiguousarray(np.concatenate(edges, axis=1))),
+            "node_ptr": node_ptr, "beat_of": torch.from_numpy(np.concatenate(beat_of)),
+            "measure_of": torch.from_numpy(np.concatenate(meas_of)), "n_beats": n_beats, "n_measures": n_meas,
+            "extras": extras, "tasks": dict(task_dict)}
+
+
 DECODE_TASKS = {"quality": 15, "inversion": 4, "degree1": 22, "degree2": 22, "localkey": 50}
 
 

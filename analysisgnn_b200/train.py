@@ -81,14 +81,16 @@ class GradArena:
         """Copy the parameters' gradient tensors into the arena with one multi-tensor copy, zero the slices of
         parameters that received none (task-dependent heads), and point every ``p.grad`` at its slice again."""
         views = self.views()
-        src, dst = [], []
+        src, dst, unused = [], [], []
         for p, v in zip(self.params, views):
             g = p.grad
             if g is None:
-                v.zero_()
+                unused.append(v)
             elif g.data_ptr() != v.data_ptr():
                 src.append(g if g.dtype == v.dtype else g.to(v.dtype))
                 dst.append(v)
+        if unused:
+            torch._foreach_zero_(unused)                  # one multi-tensor launch, not one fill per parameter
         if dst:
             torch._foreach_copy_(dst, src)
         for p, v in zip(self.params, views):

@@ -35,6 +35,7 @@ TASKS = {"cadence": 4, "localkey": 50, "romanNumeral": 185}   # analysisgnn/trai
 CFG = dict(graphs=100, notes=500, voices=4, in_features=25, hidden=256, out=128, layers=3, dropout=0.3,
            lr=5e-3, weight_decay=5e-3, max_norm=1.0)
 METRIC = "score-graph nodes/sec fwd+bwd (HybridGNN 3L/256)"
+N_HOST_BATCHES = 4        # distinct host batches the end-to-end arm rotates through (a different one every step)
 
 
 def peaks():
@@ -250,8 +251,29 @@ def run_ours(args):
                          "covered by the parity tests only")
     dtype = torch.float32
 
-    b = make_batch(seed=1000 + rank, graphs=CFG["graphs"])
-    host = {k: v.contiguous().pin_memory() for k, v in batch_tensors(b).items()}
+    # N_HOST_BATCHES different synthetic batches (different scores, features, labels, edge counts), padded to common
+    # shapes so that one captured graph serves them all: edge lists with -1 entries (dropped by agnn_csr_build), beat /
+    # measure node arrays with isolated zero-feature nodes.  The end-to-end arm copies a DIFFERENT one every step.
+    raw = [make_batch(seed=1000 + 17 * i + rank, graphs=CFG["graphs"]) for i in range(N_HOST_BATCHES)]
+    b = raw[0]
+    flats = [batch_tensors(x) for x in raw]
+    caps = {k: max(f[k].shape[-1] if k.startswith("ei.") else f[k].shape[0] for f in flats) for k in flats[0]}
+
+    def padded(f):
+        out = {}
+        for k, v in f.items():
+            if k.startswith("ei."):
+                out[k] = torch.nn.functional.pad(v, (0, caps[k] - v.shape[1]), value=-1)
+            elif k.startswith("batch.") and v.shape[0] < caps[k]:
+                out[k] = torch.cat((v, v[-1:].expand(caps[k] - v.shape[0])))
+            elif v.shape[0] < caps[k]:
+                out[k] = torch.cat((v, v.new_zeros((caps[k] - v.shape[0],) + tuple(v.shape[1:]))))
+            else:
+                out[k] = v
+        return out
+
+    hosts = [{k: v.contiguous().pin_memory() for k, v in padded(f).items()} for f in flats]
+    host = hosts[0]
     resident = {k: v.to(dev) for k, v in host.items()}
     staging = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
@@ -288,7 +310,7 @@ def run_ours(args):
         trainer.step()                             # NCCL allreduce (N > 1) + fused clip + AdamW
         return loss
 
-    not_pinned = [k for k, v in host.items() if v.numel() and not v.is_pinned()]
+    not_pinned = [k for h in hosts for k, v in h.items() if v.numel() and not v.is_pinned()]
     if not_pinned or not loss_host.is_pinned():
         raise SystemExit(f"bench.py: host buffers are not pinned: {not_pinned}")
 
@@ -321,7 +343,7 @@ def run_ours(args):
             else:
                 copy_stream.wait_stream(main)
             with torch.cuda.stream(copy_stream):
-                for k, v in host.items():
+                for k, v in hosts[cls.copies % N_HOST_BATCHES].items():     # a different batch every step
                     if v.numel():
                         staging2[s][k].copy_(v, non_blocking=True)
                 copied[s].record(copy_stream)
@@ -435,7 +457,13 @@ def run_ours(args):
     _hetero._HybridBase.overlap_sequence_branch = False
     from analysisgnn_b200 import linalg as _linalg
     ops.timer = _linalg.timer = ops.KernelTimer()
+    _linalg.trace_amax = {}
+    stats0 = dict(_linalg.stats)
     serial_ms, _ = timed(lambda: step(resident), args.steps)
+    amax_sites = {k: v / args.steps for k, v in sorted(_linalg.trace_amax.items(), key=lambda kv: -kv[1])}
+    _linalg.trace_amax = None
+    gemm_stats = {k: (_linalg.stats.get(k, 0) - stats0.get(k, 0)) / args.steps
+                  for k in ("gemm_launches", "gemm_problems", "amax_passes", "repacked_gemms")}
     ktimes = ops.timer.summary()
     if os.environ.get("AGNN_DUMP_GEMM") and rank == 0:      # per-shape GEMM time of one step, to stderr
         lay = {0: "K", 1: "MN"}
@@ -499,6 +527,7 @@ def run_ours(args):
             {"value": None, "unit": "nodes/s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped (--skip-cpu)"}
     # ---- the other BASELINE configs, as sub-objects of the same line (bench_configs.py); collective ones on all ranks
     extras = {}
+    main_routes = dict(_lib.library_routes)        # of the main arm alone (strict mode: must be empty)
     if not args.no_extras:
         import bench_configs as bc
         _lib.set_strict(False)                     # the sub-configs report their library routes instead of refusing them
@@ -513,6 +542,7 @@ def run_ours(args):
             extras["config1_strong"] = {"scaling": "strong", "n_gpus": 1, "ms_per_step": ms / args.steps,
                                         "nodes_per_s": n_nodes * args.steps / (ms * 1e-3),
                                         "workload": "= the main line at one GPU"}
+            extras["e2e_loader"] = bc.guarded(bc.loader_e2e, ctx, CFG, TASKS)
             extras["config3_hgt"] = bc.guarded(bc.config3, ctx, CFG, TASKS)
             extras["config5_inference"] = bc.guarded(bc.config5, ctx)
             extras["library_baseline"] = bc.guarded(bc.library_baseline, ctx, CFG, TASKS)
@@ -527,8 +557,11 @@ def run_ours(args):
             "e2e": {"value": world * n_nodes * args.steps / (e2e_ms * 1e-3), "unit": "nodes/s",
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                     "h2d": "pinned host -> one of two device staging sets on a copy stream, overlapped with the "
-                           "previous step's compute; K copies for K timed steps, the first one exposed"},
-            "gpu_launches": launches, "library_routes": dict(_lib.library_routes),
+                           "previous step's compute; K copies for K timed steps, the first one exposed; the copies "
+                           f"rotate through {N_HOST_BATCHES} DIFFERENT synthetic batches (padded to common shapes), so "
+                           "every timed step trains on other data than the step before"},
+            "gpu_launches": launches, "library_routes": main_routes,
+            "per_step": {**gemm_stats, "amax_passes_by_shape_and_site": amax_sites},
             "host_enqueue_ms_per_step": enqueue_ms,
             "execution": ("CSR build + fwd + bwd replayed as one CUDA graph per step, then allreduce + fused "
                           "clip/AdamW launched eagerly" if use_graph else "eager launches"),

@@ -383,3 +383,67 @@ def library_baseline(ctx, cfg, tasks, steps=5):
             "nodes_per_s": b["batch_size"] * steps / (ms * 1e-3), "steps": steps,
             "wall_s_incl_warmup": time.perf_counter() - t0,
             "workload": "same batch and step as the main line (oracle/pyg.py AnalysisEncoderShell, fp32, train mode)"}
+
+
+# ------------------------------------------------------------------------------------------ loader inside the step
+
+def loader_e2e(ctx, cfg, tasks, steps=10, n_scores=200):
+    """The headline step fed by the DEVICE loader: a corpus of synthetic scores (600-800 notes each) resident in HBM,
+    every step a different batch -- 100 scores drawn by the epoch order, one 500-note window each (counter RNG on the
+    host, 1.6 kB host -> device), window subgraph extraction + beat / measure nodes + feature / label gathers +
+    CSR build + forward + backward replayed as ONE CUDA graph (sampler.StaticBatcher: static shapes, -1 padding), then
+    allreduce / clip / AdamW, and the loss read back to pinned host memory.  Replaces graphmuse MuseNeighborLoader's
+    worker processes (analysisgnn/data/datamodules/analysis.py:270-293) for full-window batches."""
+    from analysisgnn_b200 import nn as ann, sampler, synth
+    from analysisgnn_b200.train import DataParallelTrainer, GraphedStep
+    t0 = time.perf_counter()
+    c = synth.corpus(n_scores, lambda g: 600 + 25 * (g % 9), 4242 + ctx.rank, voices=cfg["voices"],
+                     in_features=cfg["in_features"], task_dict=tasks)
+    corpus = sampler.Corpus(c["x"].to(ctx.dev), c["edges"].to(ctx.dev), c["node_ptr"],
+                            extras={k: v.to(ctx.dev) for k, v in c["extras"].items()})
+    sb = sampler.StaticBatcher(corpus, cfg["notes"], cfg["graphs"], beat_of=c["beat_of"].to(ctx.dev),
+                               measure_of=c["measure_of"].to(ctx.dev))
+    loader = sampler.ScoreGraphLoader(corpus, cfg["notes"], cfg["graphs"], seed=7)
+    build_s = time.perf_counter() - t0
+    torch.manual_seed(0)
+    net = ann.AnalysisEncoder(sb.metadata, cfg["in_features"], cfg["hidden"], cfg["out"], tasks, cfg["layers"],
+                              dropout=cfg["dropout"]).to(ctx.dev)
+    net.train()
+    trainer = DataParallelTrainer(net, lr=cfg["lr"], weight_decay=cfg["weight_decay"], max_norm=cfg["max_norm"],
+                                  world_size=ctx.world, collect_grads=True)
+    sel_dev = sb.select(loader, 0, 0).to(ctx.dev)
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def fwd_bwd(_=None):
+        b = sb.batch(sel_dev)
+        trainer.zero_grad()
+        logits = net(b["extras"]["pitch_spelling"], b["extras"]["key_signature"], b["x_dict"], b["edge_index_dict"],
+                     b["batch_dict"], b["batch_size"], None, None)
+        loss = ann.multitask_ce(logits, {t: b["extras"][t] for t in tasks})
+        loss.backward()
+        trainer.collect()
+        return loss
+
+    g = GraphedStep(fwd_bwd, None, warmup=2)
+    state = {"i": 0}
+    per_epoch = len(loader)
+
+    def step():
+        i = state["i"]
+        state["i"] += 1
+        sel_dev.copy_(sb.select(loader, i // per_epoch, i % per_epoch), non_blocking=True)
+        loss = g()
+        trainer.step()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    ms = ctx.time_steps(step, steps=steps, warm=3, collective=ctx.world > 1)
+    n = cfg["graphs"] * cfg["notes"]
+    return {"workload": "headline config fed by the device loader (StaticBatcher): a different 100 x 500-note batch "
+                        "every step, sampler + collation inside the replayed graph",
+            "value": ctx.world * n * steps / (ms * 1e-3), "unit": "nodes/s", "ms_per_step": ms / steps, "steps": steps,
+            "h2d_bytes_per_step": int(sel_dev.numel() * 8), "d2h_bytes_per_step": 4,
+            "corpus": {"scores": n_scores, "notes": int(c["node_ptr"][-1]), "edges": int(c["edges"].shape[1]),
+                       "host_build_s": build_s},
+            "static_capacity": {"note_note_edge_slots": int(sb.edge_cap) * 2,
+                                **{k: int(v[1]) for k, v in sb.virtual.items()}},
+            "loss": float(loss_host.item())}

@@ -306,6 +306,16 @@ int agnn_gemm(int precision, int a_layout, int b_layout, int64_t M, int64_t N, i
 int agnn_amax(const float* x, int64_t rows, int64_t cols, int64_t ld_x, float* amax, agnn_stream_t stream);
 int agnn_split_f16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax, void* hi, void* lo,
                    int64_t ld_out, agnn_stream_t stream);
+/* agnn_amax + agnn_split_f16 for up to AGNN_SPLIT_MULTI_MAX SMALL matrices (the weights of a grouped launch) in ONE
+ * launch: a cluster of 8 CTAs per matrix exchanges its partial maxima through distributed shared memory.  *amax is
+ * overwritten with max |x| of that matrix (it need not be zeroed). */
+#define AGNN_SPLIT_MULTI_MAX 24
+typedef struct agnn_split_item {
+  const float* x; int64_t rows, cols, ld_x;
+  void* hi; void* lo; int64_t ld_out; /* fp16 [rows, cols] each */
+  float* amax;
+} agnn_split_item_t;
+int agnn_split_f16_multi(int n, const agnn_split_item_t* items /* host */, agnn_stream_t stream);
 int agnn_gemm_scaled(int precision, int a_layout, int b_layout, int64_t M, int64_t N, int64_t K, const void* a_hi,
                      const void* a_lo, int64_t lda, const float* amax_a, const void* b_hi, const void* b_lo, int64_t ldb,
                      const float* amax_b, void* c, int64_t ldc, const float* bias, int flags, int split_k, void* workspace,

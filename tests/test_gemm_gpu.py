@@ -166,15 +166,19 @@ def test_grouped_launch_matches_single_launches(operands):
         assert torch.equal(dw, linalg.mm_tn(go, xo)) and torch.equal(dx, linalg.mm(go, wo))
 
 
-def test_split_k_is_reduced_inside_the_launch_deterministically():
-    """The CTA that stores a tile's last partial adds the partials in split order: no second kernel, bit-identical
-    from run to run, ticket counters back at zero, same numbers as the two-kernel reduction."""
+@pytest.mark.parametrize("in_kernel", [False, True])
+def test_split_k_reduction_is_deterministic(in_kernel, monkeypatch):
+    """Split-K partials are added in split order -- by one grouped reduce kernel behind the launch (default) or, with
+    ticket counters, inside the launch by the CTA that stores a tile's last partial (AGNN_SPLITK=tickets): bit-identical
+    from run to run and to each other, ticket counters back at zero."""
+    monkeypatch.setattr(linalg, "SPLITK_IN_KERNEL", in_kernel)
     g = torch.Generator().manual_seed(4)
     a, b = torch.randn(50000, 384, generator=g).to(DEV), torch.randn(50000, 256, generator=g).to(DEV)
     bias = torch.randn(256, generator=g).to(DEV)
     launches = _lib.launches()
     got = linalg.mm_tn(a, b)
-    assert _lib.launches() - launches <= 3                     # two operand splits + ONE gemm launch
+    # two operand splits + the gemm launch (+ ONE reduce launch in the two-kernel form)
+    assert _lib.launches() - launches <= (3 if in_kernel else 4)
     for _ in range(3):
         assert torch.equal(got, linalg.mm_tn(a, b))
     dev = torch.device(DEV)
@@ -218,3 +222,22 @@ def test_argument_errors():
     lib = _lib.lib()
     assert lib.agnn_gemm(7, 0, 0, 8, 8, 8, None, None, 8, None, None, 8, None, 8, None, 0, 1, None, 0, None) == -1
     assert b"gemm" in lib.agnn_last_error()
+
+
+def test_presplit_of_several_weights_in_one_launch():
+    """agnn_split_f16_multi (a cluster of 8 CTAs per matrix, partial maxima through distributed shared memory):
+    bit-identical to agnn_amax + agnn_split_f16 on each matrix, exact amax, one launch."""
+    g = torch.Generator().manual_seed(6)
+    shapes = [(256, 2560), (256, 768), (64, 128), (185, 64), (8, 8), (384, 256), (1000, 40)]
+    ws = [(torch.randn(r, c, generator=g) * (10.0 ** (i - 3))).to(DEV) for i, (r, c) in enumerate(shapes)]
+    ws[4].zero_()                                              # an all-zero matrix: amax 0, scale 1
+    linalg.begin_step()
+    before = _lib.launches()
+    linalg.presplit_f16(ws)
+    assert _lib.launches() - before == 1
+    for w in ws:
+        got = linalg._cached_split_f16(w)                      # served from the cache
+        want = linalg.split_f16(w)
+        assert float(got.amax) == float(w.abs().max()) == float(want.amax)
+        assert torch.equal(got.hi, want.hi) and torch.equal(got.lo, want.lo)
+    assert _lib.launches() - before == 1 + 2 * len(ws)         # only the reference splits launched anything more

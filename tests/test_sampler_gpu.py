@@ -143,3 +143,119 @@ def test_loader_iterates_hetero_batches():
     assert sorted(g for ids in second for g in ids) == list(range(5))
     assert second == [loader.batch_ids(1, i) for i in range(3)] and [b.graph_ids for b in first] == \
         [loader.batch_ids(0, i) for i in range(3)]
+
+
+# ------------------------------------------------------------------------------------------ static-shape batches
+
+def _static_setup(n_scores=12, batch=4, size=200, seed=3):
+    c = synth.corpus(n_scores, lambda g: size + 40 + 37 * (g % 5), seed, in_features=8)
+    corpus = sampler.Corpus(c["x"].to(DEV), c["edges"].to(DEV), c["node_ptr"], extras={k: v.to(DEV) for k, v in c["extras"].items()})
+    sb = sampler.StaticBatcher(corpus, size, batch, beat_of=c["beat_of"].to(DEV), measure_of=c["measure_of"].to(DEV))
+    loader = sampler.ScoreGraphLoader(corpus, size, batch, seed=5)
+    return c, corpus, sb, loader
+
+
+def _reference_batch(c, ids, starts, size):
+    """The same batch built on the host, score by score, the way synth.hetero_batch collates (compact, no padding)."""
+    e = c["edges"].numpy()
+    ptr = c["node_ptr"]
+    out = {"nn": [], "beat": [], "measure": []}
+    off = {"note": 0, "beat": 0, "measure": 0}
+    counts = {"beat": [], "measure": []}
+    for g, st in zip(ids, starts):
+        lo, hi = ptr[g] + st, ptr[g] + st + size
+        sel = (e[0] >= lo) & (e[0] < hi) & (e[1] >= lo) & (e[1] < hi)
+        # corpus edges are stored score by score: the selection keeps corpus order
+        out["nn"].append(np.stack((e[0][sel] - lo + off["note"], e[1][sel] - lo + off["note"], e[2][sel])))
+        for name, of in (("beat", c["beat_of"].numpy()), ("measure", c["measure_of"].numpy())):
+            ids_v = of[lo:hi]
+            first, n_v = ids_v[0], ids_v[-1] - ids_v[0] + 1
+            out[name].append(np.stack((np.arange(size) + off["note"], ids_v - first + off[name])))
+            counts[name].append(n_v)
+            off[name] += n_v
+        off["note"] += size
+    return {k: np.concatenate(v, axis=1) for k, v in out.items()}, counts
+
+
+def test_static_batches_match_the_host_collation():
+    """StaticBatcher: fixed shapes, -1 padding; after dropping the padding the edges are exactly (values AND order) the
+    induced window subgraphs collated score by score, beat / measure nodes are the windows' contiguous id ranges."""
+    size, batch = 200, 4
+    c, corpus, sb, loader = _static_setup(batch=batch, size=size)
+    shapes = None
+    for index in range(len(loader)):
+        sel_host = sb.select(loader, 0, index).clone()
+        out = sb.batch(sel_host.to(DEV))
+        ids, starts = sel_host[0].tolist(), sel_host[1].tolist()
+        assert ids == loader.batch_ids(0, index)
+        want, counts = _reference_batch(c, ids, starts, size)
+        eid = out["edge_index_dict"]
+        grp = eid.groups[0]
+        ei, et = grp.edge_index.cpu().numpy(), grp.edge_type.cpu().numpy()
+        cap = sb.edge_cap
+        fwd = et[:cap] >= 0
+        np.testing.assert_array_equal(np.stack((ei[0, :cap][fwd], ei[1, :cap][fwd], et[:cap][fwd])), want["nn"])
+        assert int(out["n_edges"]) == want["nn"].shape[1] and (ei[:, :cap][:, ~fwd] == -1).all()
+        # reversed copies of types 1..3 as types 4..6
+        rev = et[cap:] >= 0
+        keep = want["nn"][2] > 0
+        np.testing.assert_array_equal(np.stack((ei[0, cap:][rev], ei[1, cap:][rev], et[cap:][rev])),
+                                      np.stack((want["nn"][1][keep], want["nn"][0][keep], want["nn"][2][keep] + 3)))
+        for name in ("beat", "measure"):
+            up = eid[("note", "connects", name)].cpu().numpy()
+            np.testing.assert_array_equal(up, want[name])
+            np.testing.assert_array_equal(eid[(name, "connects_rev", "note")].cpu().numpy(), want[name][::-1])
+            nxt = eid[(name, "next", name)].cpu().numpy()
+            valid = nxt[0] >= 0
+            ends = np.cumsum(counts[name])
+            want_next = np.array([k for k in range(ends[-1]) if k + 1 not in ends and k + 1 < ends[-1]])
+            np.testing.assert_array_equal(nxt[0][valid], want_next)
+            np.testing.assert_array_equal(nxt[1][valid], want_next + 1)
+            assert out["x_dict"][name].shape[0] == sb.virtual[name][1] >= ends[-1]
+        # per-type views of the typed group: what generic consumers (onset pooling) index
+        onset = eid[("note", "onset", "note")].cpu().numpy()
+        np.testing.assert_array_equal(onset[:, onset[0] >= 0], want["nn"][:2][:, want["nn"][2] == 0])
+        # features / labels follow the windows
+        nodes = np.concatenate([np.arange(c["node_ptr"][g] + st, c["node_ptr"][g] + st + size) for g, st in zip(ids, starts)])
+        np.testing.assert_array_equal(out["node_index"].cpu().numpy(), nodes)
+        assert torch.equal(out["x_dict"]["note"].cpu(), c["x"][nodes])
+        assert torch.equal(out["extras"]["cadence"].cpu(), c["extras"]["cadence"][nodes])
+        sig = {k: tuple(v.shape) for k, v in out["x_dict"].items()}, grp.edge_index.shape
+        assert shapes is None or sig == shapes                 # the same shapes for every batch
+        shapes = sig
+
+
+def test_static_batch_gives_the_same_encoder_output_as_the_compact_batch():
+    """Padding is invisible to the model: the encoder shell on a static batch (typed COO with -1 slots, isolated padding
+    beats / measures) returns the note logits of the same batch in compact PyG form."""
+    from analysisgnn_b200 import nn as ann
+    size, batch = 200, 4
+    c, corpus, sb, loader = _static_setup(batch=batch, size=size)
+    sel = sb.select(loader, 1, 0).clone()
+    out = sb.batch(sel.to(DEV))
+    want, counts = _reference_batch(c, sel[0].tolist(), sel[1].tolist(), size)
+    tasks = c["tasks"]
+    torch.manual_seed(0)
+    net = ann.AnalysisEncoder(sb.metadata, 8, 32, 16, tasks, 2, dropout=0.0).to(DEV)
+    run = lambda x_dict, ei, bd: net(out["extras"]["pitch_spelling"], out["extras"]["key_signature"], x_dict, ei, bd,
+                                     out["batch_size"], None, None)
+    got = run(out["x_dict"], out["edge_index_dict"], out["batch_dict"])
+    names = ["onset", "consecutive", "during", "rest"]
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=DEV)
+    ei = {("note", nm, "note"): t(want["nn"][:2][:, want["nn"][2] == k]) for k, nm in enumerate(names)}
+    for k, nm in enumerate(names[1:], 1):
+        ei[("note", nm + "_rev", "note")] = ei[("note", nm, "note")].flip(0)
+    x_dict = {"note": out["x_dict"]["note"]}
+    bd = {"note": out["batch_dict"]["note"]}
+    for name in ("beat", "measure"):
+        n_v = int(sum(counts[name]))
+        ei[("note", "connects", name)] = t(want[name])
+        ei[(name, "connects_rev", "note")] = t(want[name][::-1])
+        ends = np.cumsum(counts[name])
+        nx = np.array([k for k in range(n_v) if k + 1 not in ends and k + 1 < n_v])
+        ei[(name, "next", name)] = t(np.stack((nx, nx + 1)))
+        x_dict[name] = out["x_dict"][name][:n_v]
+        bd[name] = out["batch_dict"][name][:n_v]
+    ref = run(x_dict, ei, bd)
+    for task in tasks:
+        assert torch.allclose(got[task], ref[task], rtol=0, atol=2e-6 * float(ref[task].abs().max())), task
