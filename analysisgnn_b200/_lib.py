@@ -22,7 +22,8 @@ F32, BF16 = 0, 1
 SCALE_NONE, SCALE_MEAN = 0, 1
 COMBINE_CONCAT, COMBINE_SUM = 0, 1
 REL_IDENTITY_IF_EMPTY = 1
-HEAVY_ROW, HEAVY_CHUNK = 4096, 2048
+REL_LOW_DEGREE = 2
+HEAVY_ROW, HEAVY_CHUNK = 512, 512
 GEMM_TF32X3, GEMM_TF32, GEMM_BF16, GEMM_F16X3 = 0, 1, 2, 3
 K_MAJOR, MN_MAJOR = 0, 1
 GEMM_RELU, GEMM_ACCUMULATE, GEMM_OUT_BF16 = 1, 2, 4
@@ -221,6 +222,8 @@ _PROTOTYPES = {
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnn_gru_bwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agnn_gru_bwd_amax": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

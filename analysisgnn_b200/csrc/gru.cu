@@ -38,6 +38,7 @@ struct GruParams {
   const float* dout;   // [B, T, n_dir * H]
   float* dgi[2];       // [B, T, 3H]
   float* dgh[2];       // [B, T, 3H]
+  float* amax[2];      // optional per direction: max |dgi| (>= max |dgh|: dgh = dgi with the n gate times r, |r| <= 1)
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(3 * H, 1) gru_bwd_kernel(const __grid_constant
   __shared__ float part_s[kSeq][3][H];
   __shared__ float in_s[kPrefetch][kSeq][6][H];  // dout, r, z, n, gh_n, h_prev of the next steps
   const int j = threadIdx.x;
+  float gmax = 0.f;
   const int gate = j / H, m = j - gate * H;
   const int rs = m & 3, cg = m >> 2;             // row slice, column group: columns 4cg .. 4cg+3 of the gate block
   const int dir = blockIdx.y;
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(3 * H, 1) gru_bwd_kernel(const __grid_constant
         const float dz_pre = dh * (hp - n) * z * (1.f - z);
         const float dr_pre = dn_pre * ghn * r * (1.f - r);
         keep = dh * z;
+        gmax = fmaxf(gmax, fmaxf(fabsf(dr_pre), fmaxf(fabsf(dz_pre), fabsf(dn_pre))));
         const int64_t row = ((int64_t)(b0 + sq) * T + t) * (3 * H);
         p.dgi[dir][row + u] = dr_pre; p.dgi[dir][row + H + u] = dz_pre; p.dgi[dir][row + 2 * H + u] = dn_pre;
         const float dghn = dn_pre * r;
@@ -278,6 +281,12 @@ __global__ void __launch_bounds__(3 * H, 1) gru_bwd_kernel(const __grid_constant
       // no third barrier: dgh_s is rewritten only after barrier (B), which every thread passes after its
       // mat-vec reads; part_s is rewritten only after the next barrier (A), which follows these reads
     }
+  }
+  if (p.amax[blockIdx.y]) {                      // operand scale of dgi / dgh for the weight-gradient GEMMs
+    uint32_t m = __float_as_uint(gmax);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(p.amax[blockIdx.y]), m);
   }
 }
 
@@ -333,6 +342,12 @@ extern "C" int agnn_gru_fwd(int32_t batch, int32_t steps, int32_t hidden, int32_
 extern "C" int agnn_gru_bwd(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* w_hh,
                             const float* out, const float* const* gates, const float* dout, float* const* dgi,
                             float* const* dgh, agnn_stream_t stream) {
+  return agnn_gru_bwd_amax(batch, steps, hidden, n_dir, w_hh, out, gates, dout, dgi, dgh, nullptr, stream);
+}
+
+extern "C" int agnn_gru_bwd_amax(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* w_hh,
+                                 const float* out, const float* const* gates, const float* dout, float* const* dgi,
+                                 float* const* dgh, float* const* amax, agnn_stream_t stream) {
   int rc = check_gru("gru_bwd", batch, steps, hidden, n_dir);
   if (rc) return rc;
   if (!w_hh || !out || !gates || !dout || !dgi || !dgh) return fail(AGNN_ERR_ARG, "gru_bwd: null pointer");
@@ -344,6 +359,7 @@ extern "C" int agnn_gru_bwd(int32_t batch, int32_t steps, int32_t hidden, int32_
   for (int d = 0; d < n_dir; ++d) {
     if (!w_hh[d] || !gates[d] || !dgi[d] || !dgh[d]) return fail(AGNN_ERR_ARG, "gru_bwd: null operand");
     p.w_hh[d] = w_hh[d]; p.gates[d] = const_cast<float*>(gates[d]); p.dgi[d] = dgi[d]; p.dgh[d] = dgh[d];
+    p.amax[d] = amax ? amax[d] : nullptr;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (hidden == 128) return launch_bwd<128>(p, st);

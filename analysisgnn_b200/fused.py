@@ -240,6 +240,29 @@ class _StageGroup(torch.autograd.Function):
         return tuple(grads)
 
 
+class _ConcatCols(torch.autograd.Function):
+    """``torch.cat(parts, dim=1)`` whose backward hands the column slices of the gradient on WITH the gradient's amax
+    tag (a bound of the whole matrix bounds every slice), so the projections below need no amax pass."""
+
+    @staticmethod
+    def forward(ctx, *parts):
+        ctx.widths = [p.shape[1] for p in parts]
+        return torch.cat(parts, dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        am = linalg.known_amax(g)
+        out, c0 = [], 0
+        for w in ctx.widths:
+            out.append(linalg.tag_amax(g[:, c0:c0 + w], am))
+            c0 += w
+        return tuple(out)
+
+
+def concat_cols(parts):
+    return _ConcatCols.apply(*parts)
+
+
 def stage_group(xs: Sequence[torch.Tensor], weights, biases, norms=None, relu=False, dropout: float = 0.0,
                 training: bool = False, share_amax: bool = False) -> List[torch.Tensor]:
     """``[Linear_i(Dropout(LayerNorm_i(x_i)))]`` (LayerNorm / Dropout / ReLU optional) for independent members.
@@ -259,7 +282,9 @@ def stage_group(xs: Sequence[torch.Tensor], weights, biases, norms=None, relu=Fa
         if not x.is_cuda:
             raise _lib.AgnnError("analysisgnn_b200 has no CPU path: tensors must live on a CUDA device")
         leads.append(x.shape[:-1])
-        x2 = x.reshape(-1, x.shape[-1])
+        # (no reshape node for matrices: a view node in the autograd graph hands the gradient on as a NEW tensor
+        # object, which loses the amax tag its producer attached)
+        x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
         am_in = linalg.known_amax(x) if nm is None else None
         k = x2.shape[1]
         if x2.dtype == torch.float32 and k % 8 and nm is None:

@@ -346,8 +346,8 @@ def presplit_f16(tensors) -> None:
             continue
         seen.add(key)
         todo.append((key, x))
-    if len(todo) < 2:
-        return                                     # a single matrix: the ordinary two-launch route
+    if not todo:
+        return
     lib = _lib.lib()
     for lo in range(0, len(todo), _lib.SPLIT_MULTI_MAX):
         chunk = todo[lo:lo + _lib.SPLIT_MULTI_MAX]
@@ -507,9 +507,9 @@ def _group(a_layout: int, b_layout: int, specs):
     presplit_f16([sp["b"] if isinstance(sp["a"], SplitH) else sp["a"] for sp in specs
                   if isinstance(sp["a"], SplitH) != isinstance(sp["b"], SplitH) and sp["m"] > 0 and sp["n"] > 0])
     for i, sp in enumerate(specs):
-        if sp["m"] == 0 or sp["n"] == 0:           # an empty member (a node type without nodes in this batch)
+        if sp["m"] == 0 or sp["n"] == 0 or sp["k"] == 0:       # an empty member (a node type without nodes in this batch)
             if sp.get("out") is not None:
-                outs[i] = sp["out"]
+                outs[i] = sp["out"] if sp.get("flags", 0) & _lib.GEMM_ACCUMULATE else sp["out"].zero_()
             else:
                 a0 = sp["a"].hi if isinstance(sp["a"], (Split, SplitH)) else sp["a"]
                 dt = torch.bfloat16 if a0.dtype == torch.bfloat16 else torch.float32

@@ -118,12 +118,8 @@ class HeteroSAGELayer(nn.Module):
         for t in plan.dst_types:
             convs = [self.convs[rel_key(et)] for et in plan.incoming[t]]
             scale = 1.0 / len(convs) if self.aggr == "mean" else 1.0
-            w_root = torch.stack([c.lin_r.weight for c in convs], dim=0).sum(0) if len(convs) > 1 \
-                else convs[0].lin_r.weight
-            wcat = torch.cat([w_root] + [c.lin_l.weight for c in convs], dim=1)
-            bias = torch.stack([c.lin_l.bias for c in convs], dim=0).sum(0) if len(convs) > 1 else convs[0].lin_l.bias
-            if scale != 1.0:
-                wcat, bias = wcat * scale, bias * scale
+            wcat, bias = ops.sage_weights([c.lin_r.weight for c in convs], [c.lin_l.weight for c in convs],
+                                          [c.lin_l.bias for c in convs], scale)
             params += [wcat, bias]
         outs = ops.hetero_sage_layer(plan, csr, relu, [x_dict[t] for t in plan.node_types], params)
         return dict(zip(plan.dst_types, outs))
@@ -385,7 +381,8 @@ class _HybridBase(nn.Module):
             x_seq.record_stream(main)
         else:
             x_seq = self.seq(_head(x_in, batch_size), batch)
-        return self.cat_proj(torch.cat((x_gnn, x_seq), dim=-1))
+        from .. import fused
+        return self.cat_proj(fused.concat_cols((x_gnn, x_seq)))
 
 
 class HybridGNN(_HybridBase):

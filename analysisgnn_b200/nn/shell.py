@@ -97,7 +97,8 @@ class AnalysisEncoder(nn.Module):
         if self.encoder_type == "metricalgnn":
             x = x if x.shape[0] == batch_size else x[:batch_size]
         pooled = onset_pool(x, edge_index_dict[ONSET], batch_size)
-        return self.project_enc(torch.cat((x, pooled), dim=-1))
+        from .. import fused
+        return self.project_enc(fused.concat_cols((x, pooled)))
 
     def forward_clf(self, x, tasks=None):
         tasks = list(self.clf_dict.keys() if tasks is None else tasks)

@@ -149,6 +149,10 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
     n_rows = out.shape[0]
     in_dtype = torch.float32 if pair_amax is not None else out.dtype
     arr = _pack(rels, n_feat, in_dtype)
+    if n_rows > 0 and all(r.n_edges is not None for r in rels) and \
+            sum(int(r.n_edges) for r in rels) <= 2.5 * n_rows:
+        for a in arr:                              # host hint: half-warp rows for very low degrees
+            a.flags |= _lib.REL_LOW_DEGREE
     sa = _rows2d(self_add, "self_add") if self_add is not None else None
     cp = _rows2d(copy, "copy") if copy is not None else None
     stream = torch.cuda.current_stream(out.device).cuda_stream
@@ -476,6 +480,74 @@ class _HeteroSageLayer(torch.autograd.Function):
             gather_reduce(rels, dx, f, mean=False, concat=False, self_add=root, amax_out=am)
             grads[i] = linalg.tag_amax(dx, am)
         return (None, None, None, None, *grads)
+
+
+class _SageWeights(torch.autograd.Function):
+    """The fused layer's weight for one destination type: ``[sum_r Wr_r | Wl_1 | .. | Wl_k] * scale`` and
+    ``sum_r b_r * scale`` from the k relations' ``lin_r.weight``, ``lin_l.weight``, ``lin_l.bias`` (PyG SAGEConv
+    parameters; HeteroConv's relation sum / mean folded in).
+
+    Backward: the gradient of every parameter is a column slice (or the root block / the bias) of the fused weight's
+    gradient.  Left to autograd those are 3k strided views, each of which AccumulateGrad clones with its own copy
+    kernel (~100 per step at config 2); here ONE multi-tensor copy writes them all -- straight into the trainer's flat
+    gradient arena when the parameter has a slot there and no gradient yet (``GradArena`` tags parameters with
+    ``_agnn_grad_view``), so that AccumulateGrad only takes the reference and ``collect`` finds it in place.
+
+    Arguments: (scale, k, *lin_r weights, *lin_l weights, *lin_l biases)."""
+
+    @staticmethod
+    def forward(ctx, scale, k, *tensors):
+        wr, wl, bl = tensors[:k], tensors[k:2 * k], tensors[2 * k:]
+        n, f = wl[0].shape
+        wcat = torch.empty((n, (k + 1) * f), dtype=wl[0].dtype, device=wl[0].device)
+        if k > 1:
+            torch.sum(torch.stack(wr, dim=0), dim=0, out=wcat[:, :f])
+            bias = torch.stack(bl, dim=0).sum(0)
+        else:
+            wcat[:, :f].copy_(wr[0])
+            bias = bl[0].clone()
+        torch._foreach_copy_([wcat[:, (r + 1) * f:(r + 2) * f] for r in range(k)], list(wl))
+        if scale != 1.0:
+            wcat.mul_(scale)
+            bias.mul_(scale)
+        ctx.scale, ctx.k, ctx.params = scale, k, tensors
+        return wcat, bias
+
+    @staticmethod
+    def backward(ctx, dwcat, dbias):
+        k, scale, params = ctx.k, ctx.scale, ctx.params
+        f = params[k].shape[1]
+
+        def target(p):
+            view = getattr(p, "_agnn_grad_view", None)
+            if view is not None and p.grad is None and view.shape == p.shape and view.device == p.device:
+                return view.view(p.shape)        # a fresh alias: AccumulateGrad takes a tensor nobody else holds
+            return torch.empty_like(p)
+
+        outs = [target(p) if need else None for p, need in zip(params, ctx.needs_input_grad[2:])]
+        dst, src = [], []
+        for r in range(k):
+            if dwcat is not None:
+                if outs[r] is not None:
+                    dst.append(outs[r]); src.append(dwcat[:, :f])
+                if outs[k + r] is not None:
+                    dst.append(outs[k + r]); src.append(dwcat[:, (r + 1) * f:(r + 2) * f])
+            if dbias is not None and outs[2 * k + r] is not None:
+                dst.append(outs[2 * k + r]); src.append(dbias)
+        if dwcat is None:
+            outs[:2 * k] = [None] * (2 * k)
+        if dbias is None:
+            outs[2 * k:] = [None] * k
+        if dst:
+            torch._foreach_copy_(dst, src)
+            if scale != 1.0:
+                torch._foreach_mul_(dst, scale)
+        return (None, None, *outs)
+
+
+def sage_weights(lin_r_weights, lin_l_weights, lin_l_biases, scale: float = 1.0):
+    k = len(lin_l_weights)
+    return _SageWeights.apply(float(scale), k, *lin_r_weights, *lin_l_weights, *lin_l_biases)
 
 
 def hetero_sage_layer(plan, csr: HeteroCSR, relu: bool, xs: Sequence[torch.Tensor], params: Sequence[torch.Tensor]):
@@ -1044,10 +1116,15 @@ class _GRULayer(torch.autograd.Function):
         dout = dout.contiguous()
         dgi = [torch.empty((b * t, 3 * h), dtype=out.dtype, device=out.device) for _ in range(n_dir)]
         dgh = [torch.empty((b * t, 3 * h), dtype=out.dtype, device=out.device) for _ in range(n_dir)]
-        _lib.check(_lib.lib().agnn_gru_bwd(b, t, h, n_dir, _lib.ptr_array(whh), out.data_ptr(), _lib.ptr_array(gates),
-                                           dout.data_ptr(), _lib.ptr_array(dgi), _lib.ptr_array(dgh), _stream(out)),
+        g_amax = [linalg.new_amax(out.device) for _ in range(n_dir)]
+        _lib.check(_lib.lib().agnn_gru_bwd_amax(b, t, h, n_dir, _lib.ptr_array(whh), out.data_ptr(),
+                                                _lib.ptr_array(gates), dout.data_ptr(), _lib.ptr_array(dgi),
+                                                _lib.ptr_array(dgh), _lib.ptr_array(g_amax), _stream(out)),
                    "agnn_gru_bwd")
         _lib.count_launches(1)
+        for d in range(n_dir):                               # max |dgi| bounds dgh as well
+            linalg.tag_amax(dgi[d], g_amax[d])
+            linalg.tag_amax(dgh[d], g_amax[d])
         grads = []
         dx = None
         gi_ops, gh_ops, hp_ops = [], [], []
@@ -1061,7 +1138,7 @@ class _GRULayer(torch.autograd.Function):
                     h_prev[:, :-1] = hd[:, 1:]
             # dgi meets xs in the grad-weight GEMM: same operand form
             gi_ops.append((linalg.prepare_auto if isinstance(xs, linalg.SplitH) else linalg.prepare)(dgi[d]))
-            gh_ops.append(linalg.prepare_auto(dgh[d]))
+            gh_ops.append(linalg.prepare_auto(dgh[d]))               # (split_f16 finds the tags: no amax pass)
             hp = h_prev.reshape(b * t, h)
             hp_ops.append(linalg.split_f16(hp, linalg.const_amax(hp.device, 1.0))
                           if isinstance(gh_ops[-1], linalg.SplitH) and linalg.f16_ok(hp) else hp)

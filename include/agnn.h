@@ -84,7 +84,7 @@ typedef struct agnn_coo {
 /* Rows with at least AGNN_HEAVY_ROW entries are also listed per (segment, relation) in `heavy` (row ids, in no
  * particular order) with their count in `n_heavy`, when those arrays are given: agnn_gather_reduce splits such
  * rows across many warps instead of letting one warp walk them alone (hub nodes, Zipf-like degree tails). */
-#define AGNN_HEAVY_ROW 4096
+#define AGNN_HEAVY_ROW 512
 
 /* bytes of scratch agnn_csr_build needs for these segments (host arithmetic only) */
 size_t agnn_csr_build_workspace(int n_seg, const agnn_coo_t* segs /* host */);
@@ -131,6 +131,10 @@ typedef struct agnn_rel {
 } agnn_rel_t;
 
 #define AGNN_REL_IDENTITY_IF_EMPTY 1
+/* host hint: the launch averages <= ~2 entries per row (leaf relations, degree-1 graphs).  When EVERY relation of a
+ * launch carries it, rows are mapped to half-warps (two rows in flight per warp): such launches are bound by the
+ * rowptr -> col -> row dependency chain per row, not by bytes per row. */
+#define AGNN_REL_LOW_DEGREE 2
 
 #define AGNN_SCALE_NONE 0
 #define AGNN_SCALE_MEAN 1
@@ -162,7 +166,7 @@ int agnn_gather_reduce_amax(int32_t n_rows, int32_t n_feat, int dtype, int scale
 /* Scratch for the heavy-row path of a launch whose relations hold `total_edges` edges and `total_heavy_cap` heavy
  * slots in all: (total_edges / AGNN_HEAVY_CHUNK + total_heavy_cap) partial rows of n_feat floats.  Relations are
  * only split when heavy_rows is set AND a workspace is given; otherwise every row is walked by its own warp. */
-#define AGNN_HEAVY_CHUNK 2048
+#define AGNN_HEAVY_CHUNK 512
 size_t agnn_gather_heavy_workspace(int64_t total_edges, int64_t total_heavy_cap, int32_t n_feat);
 
 /* out[i, :] = base[i, :] (if given) + sum_r in[i, in_col_r : +F] / max(deg_r(i), 1)
@@ -545,6 +549,12 @@ int agnn_gru_fwd(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, co
 int agnn_gru_bwd(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* w_hh /* host */,
                  const float* out, const float* const* gates /* host */, const float* dout,
                  float* const* dgi /* host */, float* const* dgh /* host */, agnn_stream_t stream);
+/* Same backward; amax[d] (optional host array of n_dir device scalars, zeroed by the caller) receives max |dgi[d]|,
+ * which also bounds dgh[d] (the n gate of dgh is the one of dgi times r, |r| <= 1): the fp16 operand scale of both for
+ * the weight-gradient products, without a pass over them. */
+int agnn_gru_bwd_amax(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* w_hh,
+                      const float* out, const float* const* gates, const float* dout, float* const* dgi,
+                      float* const* dgh, float* const* amax, agnn_stream_t stream);
 
 #ifdef __cplusplus
 }

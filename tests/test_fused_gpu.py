@@ -63,7 +63,13 @@ def test_stage_group_matches_torch(rows, with_norm, relu):
         assert rel_err(o, want) <= TOL
         assert float(linalg.known_amax(o)) == float(o.abs().max())      # the epilogue's amax tag is exact
         for a, r, what in zip(t_dev, t_ref, ("x", "w", "b", "gamma", "beta")):
-            assert rel_err(a.grad, r.grad) <= 2 * TOL, what
+            err = rel_err(a.grad, r.grad)
+            if err > 2 * TOL:                                     # where: which rows / columns are off
+                d = (a.grad.detach().double().cpu() - r.grad).abs()
+                bad = (d > 2 * TOL * float(r.grad.abs().max())).nonzero()
+                raise AssertionError(f"{what} of a member with {o.shape[0]} rows: err {err:.3e}, {bad.shape[0]} bad "
+                                     f"entries, rows {bad[:, 0].min().item()}..{bad[:, 0].max().item()}, cols "
+                                     f"{bad[:, -1].min().item()}..{bad[:, -1].max().item()}, first {bad[:5].tolist()}")
 
 
 def test_counter_dropout_masks():
