@@ -22,8 +22,7 @@ F32, BF16 = 0, 1
 SCALE_NONE, SCALE_MEAN = 0, 1
 COMBINE_CONCAT, COMBINE_SUM = 0, 1
 REL_IDENTITY_IF_EMPTY = 1
-REL_LOW_DEGREE = 2
-HEAVY_ROW, HEAVY_CHUNK = 512, 512
+HEAVY_ROW, HEAVY_CHUNK = 4096, 2048
 GEMM_TF32X3, GEMM_TF32, GEMM_BF16, GEMM_F16X3 = 0, 1, 2, 3
 K_MAJOR, MN_MAJOR = 0, 1
 GEMM_RELU, GEMM_ACCUMULATE, GEMM_OUT_BF16 = 1, 2, 4
@@ -147,6 +146,10 @@ _PROTOTYPES = {
                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "agnn_split_f16_multi": (C.c_int, [C.c_int, C.POINTER(SplitItem), C.c_void_p]),
+    "agnn_gemm_pair_supported": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "agnn_gemm_pair": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.c_int, C.c_void_p, C.c_void_p]),
     "agnn_gemm_tickets": (C.c_int64, [C.c_int64, C.c_int64, C.c_int]),
     "agnn_gemm_group_split_k": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                           C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),

@@ -615,15 +615,6 @@ int launch(const GatherParams& p, cudaStream_t stream) {
 template <typename T>
 int dispatch(const GatherParams& p, cudaStream_t stream) {
   const int vecs = p.n_feat / Vec16<T>::E;  // 16-byte vectors per row
-  bool low = !p.heavy_ws;
-  for (int r = 0; r < p.n_rel; ++r) low = low && (p.rel[r].flags & AGNN_REL_LOW_DEGREE);
-  if (low) {
-    // ~1-2 entries per row: the dependent loads of a row (extent -> column id -> source row) set the pace, so narrower
-    // groups put twice the rows in flight per warp
-    if (vecs > 8 && vecs <= 16) return launch<T, 8, 2>(p, stream);
-    if (vecs > 16 && vecs <= 32) return launch<T, 16, 2>(p, stream);
-    if (vecs > 32 && vecs <= 64) return launch<T, 16, 4>(p, stream);
-  }
   if (vecs <= 8) return launch<T, 8, 1>(p, stream);
   if (vecs <= 16) return launch<T, 16, 1>(p, stream);
   if (vecs <= 32) return launch<T, 32, 1>(p, stream);

@@ -975,16 +975,19 @@ struct SplitMulti {
   } t[AGNN_SPLIT_MULTI_MAX];
 };
 
-__global__ void __cluster_dims__(kSplitCluster, 1, 1) __launch_bounds__(256)
+constexpr int kSplitThreads = 1024;
+
+__global__ void __cluster_dims__(kSplitCluster, 1, 1) __launch_bounds__(kSplitThreads)
 split_f16_multi_kernel(const __grid_constant__ SplitMulti p) {
-  __shared__ uint32_t red[8];
+  __shared__ uint32_t red[kSplitThreads / 32];
   __shared__ uint32_t cta_max;
   const SplitMulti::T& t = p.t[blockIdx.x / kSplitCluster];
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int64_t total = t.rows * t.cols4;
   uint32_t m = 0;
-  for (int64_t i = (int64_t)rank * 256 + threadIdx.x; i < total; i += (int64_t)kSplitCluster * 256) {
+#pragma unroll 4
+  for (int64_t i = (int64_t)rank * kSplitThreads + threadIdx.x; i < total; i += (int64_t)kSplitCluster * kSplitThreads) {
     const int64_t r = i / t.cols4;
     const int c = (int)(i - r * t.cols4) * 4;
     const float4 v = __ldg(reinterpret_cast<const float4*>(t.x + r * t.ld_x + c));
@@ -996,8 +999,7 @@ split_f16_multi_kernel(const __grid_constant__ SplitMulti p) {
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int w = 1; w < 8; ++w) m = max(m, red[w]);
+    for (int w = 1; w < kSplitThreads / 32; ++w) m = max(m, red[w]);
     cta_max = m;
   }
   // all eight partial maxima are written ...
@@ -1015,7 +1017,8 @@ split_f16_multi_kernel(const __grid_constant__ SplitMulti p) {
   const float amax = __uint_as_float(all);
   if (rank == 0 && threadIdx.x == 0) *t.amax = amax;
   const float s = f16_scale_of(amax);
-  for (int64_t i = (int64_t)rank * 256 + threadIdx.x; i < total; i += (int64_t)kSplitCluster * 256) {
+#pragma unroll 4
+  for (int64_t i = (int64_t)rank * kSplitThreads + threadIdx.x; i < total; i += (int64_t)kSplitCluster * kSplitThreads) {
     const int64_t r = i / t.cols4;
     const int c = (int)(i - r * t.cols4) * 4;
     const float4 v = __ldg(reinterpret_cast<const float4*>(t.x + r * t.ld_x + c));
@@ -1043,7 +1046,7 @@ extern "C" int agnn_split_f16_multi(int n, const agnn_split_item_t* items, agnn_
     p.t[i].hi = static_cast<__half*>(q.hi); p.t[i].lo = static_cast<__half*>(q.lo); p.t[i].ld_o = q.ld_out;
     p.t[i].amax = q.amax;
   }
-  split_f16_multi_kernel<<<n * kSplitCluster, 256, 0, (cudaStream_t)stream>>>(p);
+  split_f16_multi_kernel<<<n * kSplitCluster, kSplitThreads, 0, (cudaStream_t)stream>>>(p);
   return check_launch("split_f16_multi");
 }
 

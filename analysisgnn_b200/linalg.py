@@ -395,6 +395,9 @@ _plain = plain
 
 
 SPLITK_IN_KERNEL = os.environ.get("AGNN_SPLITK", "kernel") == "tickets"
+# the large single products on CTA pairs (agnn_gemm_pair, csrc/gemm2.cu)
+GEMM_PAIR = os.environ.get("AGNN_GEMM_PAIR", "0") not in ("", "0")
+GEMM_PAIR_MIN_FLOPS = 2 * 16384 * 256 * 256
 _ticket_pools = {}       # (device, stream) -> zeroed int32 counters for the in-kernel split-K reduction
 _TICKETS = 16384
 
@@ -442,6 +445,32 @@ def _launch(prec: int, a_layout: int, b_layout: int, problems) -> None:
     """One agnn_gemm_grouped launch per AGNN_GEMM_MAX_GROUP problems of one precision / layout combination."""
     lib = _lib.lib()
     ptr = lambda t: t.data_ptr() if t is not None else None
+    if GEMM_PAIR and a_layout == _lib.K_MAJOR:
+        rest = []
+        for p in problems:
+            if (p.m > 0 and p.n > 0 and p.out.dtype == torch.float32 and (p.out.stride(0) * 4) % 16 == 0
+                    and p.out.data_ptr() % 16 == 0 and 2 * p.m * p.n * p.k >= GEMM_PAIR_MIN_FLOPS
+                    and lib.agnn_gemm_pair_supported(prec, a_layout, p.m, p.n, p.k, p.flags)):
+                dev = p.oa[0].device
+                stream = torch.cuda.current_stream(dev).cuda_stream
+
+                def run(p=p):
+                    _lib.check(lib.agnn_gemm_pair(b_layout, p.m, p.n, p.k, ptr(p.oa[0]), ptr(p.oa[1]), p.oa[0].stride(0),
+                                                  ptr(p.oa[3]), ptr(p.ob[0]), ptr(p.ob[1]), p.ob[0].stride(0),
+                                                  ptr(p.ob[3]), p.out.data_ptr(), p.out.stride(0), ptr(p.bias), p.flags,
+                                                  ptr(p.amax_out), stream), "agnn_gemm_pair")
+
+                if timer is not None:
+                    timer.launch("gemm", 2 * p.m * p.n * p.k, dev, run, tag=(a_layout, b_layout, p.m, p.n, p.k, 1, -2))
+                else:
+                    run()
+                _lib.count_launches(1)
+                stats["gemm_launches"] = stats.get("gemm_launches", 0) + 1
+                stats["gemm_problems"] = stats.get("gemm_problems", 0) + 1
+                stats["gemm_pair_launches"] = stats.get("gemm_pair_launches", 0) + 1
+            else:
+                rest.append(p)
+        problems = rest
     for lo in range(0, len(problems), _lib.GEMM_MAX_GROUP):
         chunk = [p for p in problems[lo:lo + _lib.GEMM_MAX_GROUP] if p.m > 0 and p.n > 0]
         if not chunk:

@@ -149,10 +149,6 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
     n_rows = out.shape[0]
     in_dtype = torch.float32 if pair_amax is not None else out.dtype
     arr = _pack(rels, n_feat, in_dtype)
-    if n_rows > 0 and all(r.n_edges is not None for r in rels) and \
-            sum(int(r.n_edges) for r in rels) <= 2.5 * n_rows:
-        for a in arr:                              # host hint: half-warp rows for very low degrees
-            a.flags |= _lib.REL_LOW_DEGREE
     sa = _rows2d(self_add, "self_add") if self_add is not None else None
     cp = _rows2d(copy, "copy") if copy is not None else None
     stream = torch.cuda.current_stream(out.device).cuda_stream
@@ -487,62 +483,58 @@ class _SageWeights(torch.autograd.Function):
     ``sum_r b_r * scale`` from the k relations' ``lin_r.weight``, ``lin_l.weight``, ``lin_l.bias`` (PyG SAGEConv
     parameters; HeteroConv's relation sum / mean folded in).
 
-    Backward: the gradient of every parameter is a column slice (or the root block / the bias) of the fused weight's
-    gradient.  Left to autograd those are 3k strided views, each of which AccumulateGrad clones with its own copy
-    kernel (~100 per step at config 2); here ONE multi-tensor copy writes them all -- straight into the trainer's flat
-    gradient arena when the parameter has a slot there and no gradient yet (``GradArena`` tags parameters with
-    ``_agnn_grad_view``), so that AccumulateGrad only takes the reference and ``collect`` finds it in place.
+    Backward: the gradient of every parameter is a column block (or the root block / the bias) of the fused weight's
+    gradient.  Left to autograd those are 3k strided or shared views, each of which AccumulateGrad clones with its own
+    copy kernel (~100 per step at config 2).  Here ONE gather writes all 2k weight gradients as the contiguous rows of a
+    ``[2k, N, F]`` buffer (and one broadcast the k bias gradients), which AccumulateGrad takes over as they are.
 
     Arguments: (scale, k, *lin_r weights, *lin_l weights, *lin_l biases)."""
 
     @staticmethod
     def forward(ctx, scale, k, *tensors):
         wr, wl, bl = tensors[:k], tensors[k:2 * k], tensors[2 * k:]
-        n, f = wl[0].shape
-        wcat = torch.empty((n, (k + 1) * f), dtype=wl[0].dtype, device=wl[0].device)
         if k > 1:
-            torch.sum(torch.stack(wr, dim=0), dim=0, out=wcat[:, :f])
+            root = torch.stack(wr, dim=0).sum(0)
             bias = torch.stack(bl, dim=0).sum(0)
         else:
-            wcat[:, :f].copy_(wr[0])
-            bias = bl[0].clone()
-        torch._foreach_copy_([wcat[:, (r + 1) * f:(r + 2) * f] for r in range(k)], list(wl))
+            root, bias = wr[0], bl[0].clone()
+        wcat = torch.cat([root] + list(wl), dim=1)
         if scale != 1.0:
             wcat.mul_(scale)
             bias.mul_(scale)
-        ctx.scale, ctx.k, ctx.params = scale, k, tensors
+        ctx.scale, ctx.k = scale, k
+        ctx.feat = wl[0].shape[1]
         return wcat, bias
 
     @staticmethod
     def backward(ctx, dwcat, dbias):
-        k, scale, params = ctx.k, ctx.scale, ctx.params
-        f = params[k].shape[1]
-
-        def target(p):
-            view = getattr(p, "_agnn_grad_view", None)
-            if view is not None and p.grad is None and view.shape == p.shape and view.device == p.device:
-                return view.view(p.shape)        # a fresh alias: AccumulateGrad takes a tensor nobody else holds
-            return torch.empty_like(p)
-
-        outs = [target(p) if need else None for p, need in zip(params, ctx.needs_input_grad[2:])]
-        dst, src = [], []
-        for r in range(k):
-            if dwcat is not None:
-                if outs[r] is not None:
-                    dst.append(outs[r]); src.append(dwcat[:, :f])
-                if outs[k + r] is not None:
-                    dst.append(outs[k + r]); src.append(dwcat[:, (r + 1) * f:(r + 2) * f])
-            if dbias is not None and outs[2 * k + r] is not None:
-                dst.append(outs[2 * k + r]); src.append(dbias)
-        if dwcat is None:
-            outs[:2 * k] = [None] * (2 * k)
-        if dbias is None:
-            outs[2 * k:] = [None] * k
-        if dst:
-            torch._foreach_copy_(dst, src)
+        k, scale, f = ctx.k, ctx.scale, ctx.feat
+        outs = [None] * (3 * k)
+        if dwcat is not None:
+            n = dwcat.shape[0]
+            blocks = dwcat.reshape(n, k + 1, f).permute(1, 0, 2)               # [k + 1, N, F] view
+            idx = _sage_block_index(k, dwcat.device)                           # [0] * k + [1 .. k]
+            g = blocks.index_select(0, idx)                                    # [2k, N, F], contiguous: one kernel
             if scale != 1.0:
-                torch._foreach_mul_(dst, scale)
+                g.mul_(scale)
+            for r in range(2 * k):
+                outs[r] = g[r]
+        if dbias is not None:
+            gb = dbias.unsqueeze(0).expand(k, -1)
+            gb = gb * scale if scale != 1.0 else gb.clone()      # (never in place: the incoming gradient is not ours)
+            for r in range(k):
+                outs[2 * k + r] = gb[r]
         return (None, None, *outs)
+
+
+_sage_idx_cache = {}
+
+
+def _sage_block_index(k: int, device) -> torch.Tensor:
+    key = (k, str(device))
+    if key not in _sage_idx_cache:
+        _sage_idx_cache[key] = torch.tensor([0] * k + list(range(1, k + 1)), dtype=torch.long, device=device)
+    return _sage_idx_cache[key]
 
 
 def sage_weights(lin_r_weights, lin_l_weights, lin_l_biases, scale: float = 1.0):

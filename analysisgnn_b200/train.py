@@ -51,9 +51,6 @@ class GradArena:
         self.exp_avg_sq = torch.zeros_like(self.grad)
         for p, o in zip(self.params, self.offsets):
             p.grad = self.grad[o:o + p.numel()].view_as(p)
-            # backward functions that produce several parameter gradients at once (ops._SageWeights) write them
-            # straight into the parameter's slot when the parameter has no gradient yet
-            p._agnn_grad_view = self.grad[o:o + p.numel()].view_as(p)
         chunks = []
         for p, o in zip(self.params, self.offsets):
             n = p.numel()

@@ -84,7 +84,7 @@ typedef struct agnn_coo {
 /* Rows with at least AGNN_HEAVY_ROW entries are also listed per (segment, relation) in `heavy` (row ids, in no
  * particular order) with their count in `n_heavy`, when those arrays are given: agnn_gather_reduce splits such
  * rows across many warps instead of letting one warp walk them alone (hub nodes, Zipf-like degree tails). */
-#define AGNN_HEAVY_ROW 512
+#define AGNN_HEAVY_ROW 4096
 
 /* bytes of scratch agnn_csr_build needs for these segments (host arithmetic only) */
 size_t agnn_csr_build_workspace(int n_seg, const agnn_coo_t* segs /* host */);
@@ -131,10 +131,6 @@ typedef struct agnn_rel {
 } agnn_rel_t;
 
 #define AGNN_REL_IDENTITY_IF_EMPTY 1
-/* host hint: the launch averages <= ~2 entries per row (leaf relations, degree-1 graphs).  When EVERY relation of a
- * launch carries it, rows are mapped to half-warps (two rows in flight per warp): such launches are bound by the
- * rowptr -> col -> row dependency chain per row, not by bytes per row. */
-#define AGNN_REL_LOW_DEGREE 2
 
 #define AGNN_SCALE_NONE 0
 #define AGNN_SCALE_MEAN 1
@@ -166,7 +162,7 @@ int agnn_gather_reduce_amax(int32_t n_rows, int32_t n_feat, int dtype, int scale
 /* Scratch for the heavy-row path of a launch whose relations hold `total_edges` edges and `total_heavy_cap` heavy
  * slots in all: (total_edges / AGNN_HEAVY_CHUNK + total_heavy_cap) partial rows of n_feat floats.  Relations are
  * only split when heavy_rows is set AND a workspace is given; otherwise every row is walked by its own warp. */
-#define AGNN_HEAVY_CHUNK 512
+#define AGNN_HEAVY_CHUNK 2048
 size_t agnn_gather_heavy_workspace(int64_t total_edges, int64_t total_heavy_cap, int32_t n_feat);
 
 /* out[i, :] = base[i, :] (if given) + sum_r in[i, in_col_r : +F] / max(deg_r(i), 1)
@@ -355,6 +351,17 @@ int agnn_gemm_group_split_k(int precision, int n_problems, const int64_t* M, con
                             int32_t* split_out);
 int agnn_gemm_grouped(int precision, int a_layout, int b_layout, int n_problems, const agnn_gemm_problem_t* problems,
                       int32_t* tickets, int64_t n_tickets, agnn_stream_t stream);
+
+/* The large products of a step (the fused message-passing layers' forward and grad-input GEMMs: M = nodes of a batch,
+ * N >= 256) on CTA PAIRS: tcgen05.mma.cta_group::2, a 256 x 256 tile per pair, each CTA staging its 128 rows of A and
+ * its half of B -- half the L2 -> shared-memory traffic per flop of agnn_gemm's 128 x 128 tiles, which those shapes
+ * are bound by.  AGNN_GEMM_F16X3 operands only (fp16 hi / lo pairs + the two amax scalars), A K-major, B K-major or
+ * MN-major, fp32 C with 16-byte aligned rows, optional bias / ReLU / amax_out; no split-K, no accumulate.
+ * agnn_gemm_pair_supported tells whether a problem qualifies (host arithmetic). */
+int agnn_gemm_pair_supported(int precision, int a_layout, int64_t M, int64_t N, int64_t K, int flags);
+int agnn_gemm_pair(int b_layout, int64_t M, int64_t N, int64_t K, const void* a_hi, const void* a_lo, int64_t lda,
+                   const float* amax_a, const void* b_hi, const void* b_lo, int64_t ldb, const float* amax_b, float* c,
+                   int64_t ldc, const float* bias, int flags, float* amax_out, agnn_stream_t stream);
 
 /* ------------------------------------------------------------ row-wise normalisation
  * agnn_layernorm_*: nn.LayerNorm of project_dict / project_enc (analysisgnn/models/analysis.py:429-443,

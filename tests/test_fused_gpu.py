@@ -15,13 +15,17 @@ pytestmark = pytest.mark.gpu
 TOL = 4e-6      # fp32-GEMM level (tests/test_gemm_gpu.py) through one LayerNorm + one projection
 
 
-def _ref_stage(x, w, b, norm, relu, mask=None, p=0.0):
+def _ref_stage(x, w, b, norm, relu, mask=None, p=0.0, relu_mask=None):
+    """``relu_mask``: the CUDA side's activation pattern -- a pre-activation within rounding of zero may land on either
+    side in two correct implementations, and the gradient of that unit is then 0 or 1 (tests/util.py)."""
     y = x
     if norm is not None:
         y = nn.functional.layer_norm(y, (y.shape[-1],), norm[0], norm[1], norm[2])
     if mask is not None:
         y = y * mask / (1.0 - p)
     y = y @ w.t() + (b if b is not None else 0.0)
+    if relu_mask is not None:
+        return y * relu_mask
     return y.relu() if relu else y
 
 
@@ -43,10 +47,6 @@ def test_stage_group_matches_torch(rows, with_norm, relu):
     ref_in = [[leaf(x, "cpu", torch.float64), leaf(w, "cpu", torch.float64), leaf(b, "cpu", torch.float64)] +
               ([leaf(nm[0], "cpu", torch.float64), leaf(nm[1], "cpu", torch.float64)] if nm else [])
               for x, w, b, nm in zip(xs, ws, bs, norms)]
-    for t, gy, nm in zip(ref_in, gys, norms):
-        y = _ref_stage(t[0], t[1], t[2], (t[3], t[4], nm[2]) if nm else None, relu)
-        if y.numel():
-            y.backward(gy.double())
     dev_in = [[leaf(x, DEV, torch.float32), leaf(w, DEV, torch.float32), leaf(b, DEV, torch.float32)] +
               ([leaf(nm[0], DEV, torch.float32), leaf(nm[1], DEV, torch.float32)] if nm else [])
               for x, w, b, nm in zip(xs, ws, bs, norms)]
@@ -56,6 +56,11 @@ def test_stage_group_matches_torch(rows, with_norm, relu):
     assert linalg.stats["gemm_launches"] - before == 1          # all members in one grouped launch
     live = [(o, gy) for o, gy in zip(outs, gys) if o.numel()]
     torch.autograd.backward([o for o, _ in live], [gy.to(DEV) for _, gy in live])
+    for t, gy, nm, o in zip(ref_in, gys, norms, outs):          # reference gradients on the CUDA side's ReLU pattern
+        y = _ref_stage(t[0], t[1], t[2], (t[3], t[4], nm[2]) if nm else None, relu,
+                       relu_mask=(o.detach() > 0).double().cpu() if relu else None)
+        if y.numel():
+            y.backward(gy.double())
     for o, t_ref, t_dev, nm in zip(outs, ref_in, dev_in, norms):
         if o.shape[0] == 0:
             continue

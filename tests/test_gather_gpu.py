@@ -192,7 +192,7 @@ def test_f16_pair_output_is_what_the_gemm_consumes(hubs):
 
 @pytest.mark.parametrize("mean", [False, True])
 def test_heavy_rows_are_split_across_warps(mean):
-    """Hub rows (>= HEAVY_ROW = 512 entries) take the multi-warp path: chunk partials + ordered combine.  Same numbers as the
+    """Hub rows (>= HEAVY_ROW entries) take the multi-warp path: chunk partials + ordered combine.  Same numbers as the
     plain formulation, deterministic from run to run, forward and backward."""
     rng = np.random.default_rng(3)
     n_rows, n_cols, f = 300, 5000, 64
@@ -255,22 +255,3 @@ def test_two_heavy_relations_on_one_row_are_summed_in_order(dtype, mean):
         outs.append(out)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert_close(outs[0].double(), want, 2 * FP32_REL if dtype == torch.float32 else BF16_REL, "sum over relations")
-
-
-@pytest.mark.parametrize("f", [64, 128, 256])
-def test_low_degree_launches_use_half_warp_rows(f):
-    """<= ~2 entries per row on average: the host flags the relations AGNN_REL_LOW_DEGREE and rows are mapped to
-    half-warps; same numbers as the plain formulation (forward and transposed backward)."""
-    n_rows, n_cols = 5000, 7000
-    ei = _graph(n_rows, n_cols, 6000, 21)
-    src = torch.randn(n_cols, f)
-    g = torch.randn(n_rows, f)
-    s1 = src.clone().requires_grad_(True)
-    want = oi.sum_into(s1[ei[1]], ei[0], n_rows)
-    want.backward(g)
-    csr = graph.TypedCSR(ei.to(DEV), None, n_rows, n_cols=n_cols)
-    s2 = src.to(DEV).requires_grad_(True)
-    got = ops.segment_sum(s2, csr)
-    got.backward(g.to(DEV))
-    assert_close(got, want, FP32_REL, "forward")
-    assert_close(s2.grad, s1.grad, FP32_REL, "d src")

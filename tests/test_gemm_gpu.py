@@ -163,7 +163,9 @@ def test_grouped_launch_matches_single_launches(operands):
             continue
         _check_fp32(dw, gg.double().t() @ x.double(), gg.t() @ x)
         _check_fp32(dx, gg.double() @ w.double(), gg @ w)
-        assert torch.equal(dw, linalg.mm_tn(go, xo)) and torch.equal(dx, linalg.mm(go, wo))
+        # (the group picks its split counts for the group as a whole: the grad-weight sums are ordered differently
+        # than in a launch of their own, so only the unsplit products are compared bit for bit)
+        assert torch.equal(dx, linalg.mm(go, wo))
 
 
 @pytest.mark.parametrize("in_kernel", [False, True])
