@@ -22,6 +22,7 @@ F32, BF16 = 0, 1
 SCALE_NONE, SCALE_MEAN = 0, 1
 COMBINE_CONCAT, COMBINE_SUM = 0, 1
 REL_IDENTITY_IF_EMPTY = 1
+EDGE_ABSDIFF, EDGE_ABSDIFF_DROW, EDGE_ABSDIFF_DNBR, EDGE_GATE, EDGE_GATE_DROW, EDGE_GATE_DNBR = range(6)
 HEAVY_ROW, HEAVY_CHUNK = 4096, 2048
 GEMM_TF32X3, GEMM_TF32, GEMM_BF16, GEMM_F16X3 = 0, 1, 2, 3
 K_MAJOR, MN_MAJOR = 0, 1
@@ -113,6 +114,9 @@ _PROTOTYPES = {
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "agnn_gather_heavy_workspace": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
+    "agnn_edge_op": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                               C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                               C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "agnn_rowscale_sum": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int, C.POINTER(Rel), C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "agnn_hgt_attn_fwd": (C.c_int, [C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HgtRel), C.c_void_p,

@@ -72,8 +72,9 @@ class SageConvScatter(nn.Module):
 
 class ResGatedGraphConv(nn.Module):
     """analysisgnn/models/core/gnn.py:212-258: ``h1 + (h1 + sum_j sigmoid(W3 x_i + W4 x_j [+ W5 e]) * W2 x_j)``
-    (``h1`` enters twice in the reference, :256-257).  Projections on the tensor-core GEMM, the per-edge
-    gate as elementwise ops, the reduction on the atomics-free segmented kernel."""
+    (``h1`` enters twice in the reference, :256-257).  Projections on the tensor-core GEMM; gate, product and
+    reduction in ONE kernel per direction (agnn_edge_op: the messages live in registers, no [E, F] tensor).  With
+    edge features (``W5 e``, one row per edge by construction) the gate is formed per edge as in the reference."""
 
     def __init__(self, in_features, out_features, bias=True, in_edge_features=None):
         super().__init__()
@@ -96,17 +97,23 @@ class ResGatedGraphConv(nn.Module):
         h2 = self.W2(features if neigh_feats is None else neigh_feats)
         if edge_index is None or edge_index.shape[1] == 0:
             return h1 + h1
-        gate = self.W3(features).index_select(0, edge_index[0]) + self.W4(features).index_select(0, edge_index[1])
         if edge_features is not None and self.in_edge_features is not None:
+            gate = self.W3(features).index_select(0, edge_index[0]) + self.W4(features).index_select(0, edge_index[1])
             gate = gate + self.W5(edge_features)
-        msg = torch.sigmoid(gate) * h2.index_select(0, edge_index[1])
-        s = ops.segment_sum_self(msg, h1, graph.edge_csr(edge_index[0], features.shape[0]))
-        return h1 + s
+            msg = torch.sigmoid(gate) * h2.index_select(0, edge_index[1])
+            s = ops.segment_sum_self(msg, h1, graph.edge_csr(edge_index[0], features.shape[0]))
+            return h1 + s
+        n = features.shape[0]
+        csr = graph.typed_csr(edge_index, None, n, 1, n_cols=h2.shape[0])
+        return h1 + ops.edge_gate_sum(self.W3(features), self.W4(features), h2, csr, self_add=h1)
 
 
 class RelEdgeConv(nn.Module):
     """analysisgnn/models/core/gnn.py:79-106: messages ``edge_linear([h_j || |h_i - h_j|])`` (or given edge
-    features), mean into ``h.clone()``, then ``linear([x || s])``."""
+    features), mean into ``h.clone()``, then ``linear([x || s])``.  Without given edge features the per-edge projection
+    is linear in quantities that can be reduced FIRST: ``sum_j edge_linear([h_j || d_ij]) = edge_linear_w [sum_j h_j ||
+    sum_j d_ij] + deg_i b`` -- two segmented reductions (the second forms ``|h_i - h_j|`` in registers, agnn_edge_op)
+    and a projection over N rows instead of E (E ~ 4.6 N), no [E, 2F] tensor; changes the fp32 summation order only."""
 
     def __init__(self, in_node_features, out_features, bias=True, in_edge_features=None):
         super().__init__()
@@ -122,11 +129,20 @@ class RelEdgeConv(nn.Module):
 
     def forward(self, features, edge_index, edge_features=None):
         h = self.neigh_linear(features)
-        hi, hj = h.index_select(0, edge_index[0]), h.index_select(0, edge_index[1])
-        if edge_features is None:
-            edge_features = torch.abs(hi - hj)
-        msg = self.edge_linear(torch.cat((hj, edge_features), dim=-1))
-        s = ops.segment_mean_self(msg, h, graph.edge_csr(edge_index[0], features.shape[0]))
+        if edge_features is not None:
+            hj = h.index_select(0, edge_index[1])
+            msg = self.edge_linear(torch.cat((hj, edge_features), dim=-1))
+            s = ops.segment_mean_self(msg, h, graph.edge_csr(edge_index[0], features.shape[0]))
+            return self.linear(torch.cat((features, s), dim=-1))
+        n = features.shape[0]
+        csr = graph.typed_csr(edge_index, None, n, 1)
+        s1 = ops.segment_sum(h, csr)                                   # sum_j h_j
+        s2 = ops.edge_absdiff(h, h, csr)                               # sum_j |h_i - h_j|
+        deg = graph.derived(edge_index, ("degree", n), lambda: torch.bincount(edge_index[0], minlength=n).to(h.dtype))
+        msg = ops.linear(torch.cat((s1, s2), dim=-1), self.edge_linear.weight, None)
+        if self.edge_linear.bias is not None:
+            msg = msg + deg.unsqueeze(1) * self.edge_linear.bias
+        s = (h + msg) / deg.clamp(min=1).unsqueeze(1)
         return self.linear(torch.cat((features, s), dim=-1))
 
 
@@ -186,8 +202,8 @@ class OnsetEmbedding(nn.Module):
         if self.add_self_loops:
             loops = torch.arange(0, x.size(0), dtype=torch.long, device=x.device).unsqueeze(0).repeat(2, 1)
             edge_index = torch.cat([edge_index, loops], dim=1)
-        msg = torch.abs(x.index_select(0, edge_index[0]) - x.index_select(0, edge_index[1]))
-        return self.W(ops.segment_mean_self(msg, x, graph.edge_csr(edge_index[0], x.shape[0])))
+        csr = graph.typed_csr(edge_index, None, x.shape[0], 1)
+        return self.W(ops.edge_absdiff(x, x, csr, self_add=x, mean=True))   # |x_i - x_j| formed in registers
 
 
 _FOLDABLE = ("mean", "sum")

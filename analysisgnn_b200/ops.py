@@ -264,6 +264,90 @@ def segment_mean_self(src, self_add, csr: TypedCSR):
 
 
 # ------------------------------------------------------------------------------
+# fused per-edge messages (agnn_edge_op): ResGatedGraphConv / RelEdgeConv / OnsetEmbedding
+# ------------------------------------------------------------------------------
+
+def _edge_op(op, csr_side: CSR, n_rows, f, row0, row1, nbr0, nbr1, self_add=None, mean=False, two_out=False):
+    ok = lambda t: t is None or (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1)
+    if not all(ok(t) for t in (row0, row1, nbr0, nbr1, self_add)):
+        raise _lib.AgnnError("edge_op: operands must be fp32 CUDA matrices with unit column stride")
+    out0 = torch.empty((n_rows, f), dtype=torch.float32, device=row0.device)
+    out1 = torch.empty((n_rows, f), dtype=torch.float32, device=row0.device) if two_out else None
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    ld = lambda t: t.stride(0) if t is not None else 0
+    _lib.check(_lib.lib().agnn_edge_op(op, n_rows, f, csr_side.rowptr[0].data_ptr(), csr_side.col.data_ptr(), ptr(row0),
+                                       ld(row0), ptr(row1), ld(row1), ptr(nbr0), ld(nbr0), ptr(nbr1), ld(nbr1),
+                                       ptr(self_add), ld(self_add), int(mean), out0.data_ptr(), out0.stride(0),
+                                       ptr(out1), ld(out1), _stream(row0)), "agnn_edge_op")
+    _lib.count_launches(1)
+    return (out0, out1) if two_out else out0
+
+
+def _scaled_by_degree(g, csr: TypedCSR):
+    out = torch.empty_like(g)
+    rowscale_sum([Rel(csr.fwd.rowptr[0], csr.fwd.col, g)], g, out, g.shape[1])
+    return out
+
+
+class _EdgeAbsDiff(torch.autograd.Function):
+    """``out_i = s_i (self_i + sum_{j in N(i)} |a_i - b_j|)`` on ``csr.fwd`` (rows = reduce side); ``s_i`` = 1 or
+    ``1 / max(deg_i, 1)``.  Arguments: (a, b, self_add or None, csr, mean)."""
+
+    @staticmethod
+    def forward(ctx, a, b, self_add, csr: TypedCSR, mean: bool):
+        a, b = a.contiguous(), b.contiguous()
+        sa = self_add.contiguous() if self_add is not None else None
+        out = _edge_op(_lib.EDGE_ABSDIFF, csr.fwd, csr.n_rows, a.shape[1], a, None, b, None, sa, mean)
+        ctx.save_for_backward(a, b)
+        ctx.csr, ctx.mean, ctx.has_self = csr, mean, self_add is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        csr, f = ctx.csr, a.shape[1]
+        g = g.contiguous()
+        gs = _scaled_by_degree(g, csr) if ctx.mean else g
+        da = _edge_op(_lib.EDGE_ABSDIFF_DROW, csr.fwd, csr.n_rows, f, gs, a, b, None) if ctx.needs_input_grad[0] else None
+        db = _edge_op(_lib.EDGE_ABSDIFF_DNBR, csr.bwd, csr.n_cols, f, b, None, gs, a) if ctx.needs_input_grad[1] else None
+        return da, db, (gs if ctx.has_self else None), None, None
+
+
+class _EdgeGate(torch.autograd.Function):
+    """``out_i = self_i + sum_{j in N(i)} sigmoid(a_i + b_j) * c_j`` (gnn.py:249-256).  Arguments: (a, b, c, self_add, csr)."""
+
+    @staticmethod
+    def forward(ctx, a, b, c, self_add, csr: TypedCSR):
+        a, b, c = a.contiguous(), b.contiguous(), c.contiguous()
+        sa = self_add.contiguous() if self_add is not None else None
+        out = _edge_op(_lib.EDGE_GATE, csr.fwd, csr.n_rows, a.shape[1], a, None, b, c, sa, False)
+        ctx.save_for_backward(a, b, c)
+        ctx.csr, ctx.has_self = csr, self_add is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, c = ctx.saved_tensors
+        csr, f = ctx.csr, a.shape[1]
+        g = g.contiguous()
+        da = _edge_op(_lib.EDGE_GATE_DROW, csr.fwd, csr.n_rows, f, g, a, b, c) if ctx.needs_input_grad[0] else None
+        db = dc = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            db, dc = _edge_op(_lib.EDGE_GATE_DNBR, csr.bwd, csr.n_cols, f, b, c, g, a, two_out=True)
+        return da, db, dc, (g if ctx.has_self else None), None
+
+
+def edge_absdiff(a, b, csr: TypedCSR, self_add=None, mean: bool = False):
+    """``s_i (self_i + sum_j |a_i - b_j|)``: no per-edge tensor on either pass."""
+    return _EdgeAbsDiff.apply(a, b, self_add, csr, mean)
+
+
+def edge_gate_sum(a, b, c, csr: TypedCSR, self_add=None):
+    """``self_i + sum_j sigmoid(a_i + b_j) * c_j``."""
+    return _EdgeGate.apply(a, b, c, self_add, csr)
+
+
+# ------------------------------------------------------------------------------
 # in-tree HeteroConv{SageConvScatter}: one fused layer
 # ------------------------------------------------------------------------------
 

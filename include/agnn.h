@@ -165,6 +165,28 @@ int agnn_gather_reduce_amax(int32_t n_rows, int32_t n_feat, int dtype, int scale
 #define AGNN_HEAVY_CHUNK 2048
 size_t agnn_gather_heavy_workspace(int64_t total_edges, int64_t total_heavy_cap, int32_t n_feat);
 
+/* Fused per-edge message + segmented reduction for the reference's alternative conv blocks
+ * (analysisgnn/models/core/gnn.py): per row i of a single-relation CSR (rowptr / col as agnn_csr_build writes them),
+ *   out0[i] = s_i * (self_add[i] + sum_{k in row i} msg(i, col[k])),  s_i = 1 / max(deg_i, 1) if mean else 1,
+ * every message formed in registers -- no [E, F] tensor exists on either pass.  row* operands are indexed by the row,
+ * nbr* operands by col[k]; fp32, n_feat a multiple of 4 up to 512.
+ *   AGNN_EDGE_ABSDIFF       msg = |row0_i - nbr0_j|                       OnsetEmbedding (gnn.py:300-311), RelEdgeConv (:99-106)
+ *   AGNN_EDGE_ABSDIFF_DROW  msg = row0_i * sign(row1_i - nbr0_j)          its gradient wrt the row operand (row0 = g, row1 = a)
+ *   AGNN_EDGE_ABSDIFF_DNBR  msg = -nbr0_i * sign(nbr1_i - row0_j)         ... wrt the neighbour operand, on the TRANSPOSED CSR
+ *   AGNN_EDGE_GATE          msg = sigmoid(row0_i + nbr0_j) * nbr1_j       ResGatedGraphConv (gnn.py:243-258)
+ *   AGNN_EDGE_GATE_DROW     msg = row0_i * nbr1_j * s (1 - s), s = sigmoid(row1_i + nbr0_j)     (row0 = g, row1 = a)
+ *   AGNN_EDGE_GATE_DNBR     transposed CSR, row0 = b_j, row1 = c_j, nbr0 = g_i, nbr1 = a_i: out0 = d b_j, out1 = d c_j */
+#define AGNN_EDGE_ABSDIFF 0
+#define AGNN_EDGE_ABSDIFF_DROW 1
+#define AGNN_EDGE_ABSDIFF_DNBR 2
+#define AGNN_EDGE_GATE 3
+#define AGNN_EDGE_GATE_DROW 4
+#define AGNN_EDGE_GATE_DNBR 5
+int agnn_edge_op(int op, int32_t n_rows, int32_t n_feat, const int32_t* rowptr, const int32_t* col, const float* row0,
+                 int64_t ld_row0, const float* row1, int64_t ld_row1, const float* nbr0, int64_t ld_nbr0,
+                 const float* nbr1, int64_t ld_nbr1, const float* self_add, int64_t ld_self, int mean, float* out0,
+                 int64_t ld_out0, float* out1, int64_t ld_out1, agnn_stream_t stream);
+
 /* out[i, :] = base[i, :] (if given) + sum_r in[i, in_col_r : +F] / max(deg_r(i), 1)
  * -- the gradient of the self term of the mean_self reduction (gnn.py:74 backward).
  * Relations flagged AGNN_REL_IDENTITY_IF_EMPTY that are empty are skipped.  Uses rels[r].rowptr,
