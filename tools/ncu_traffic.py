@@ -33,8 +33,8 @@ def main(path):
         v, u = num(r[i]), units[i]
         if v is None:
             return None
-        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3,
-                 "nsecond": 1e-9, "second": 1.0}.get(u, 1.0)
+        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "us": 1e-6, "msecond": 1e-3,
+                 "ms": 1e-3, "nsecond": 1e-9, "ns": 1e-9, "second": 1.0, "s": 1.0}.get(u, 1.0)
         return v * scale
 
     best = {}
@@ -61,7 +61,10 @@ def main(path):
                                algorithmic_bytes=2 * 2 * (m * k + n * k) + 4 * m * n)
     if "gather" in best:
         out["gather_f16"] = dict(best["gather"], source=f"{src} (tools/ncu_targets.py: note rows of the config-2 batch, "
-                                                         "9 relations, fp16 pair output)")
+                                                         "9 relations, fp16 pair output)",
+                                 algorithmic_bytes=1108569428,
+                                 note="the 51 MB source matrix and the column ids stay in the 126 MB L2: DRAM sees the "
+                                      "operand pair being written and little else")
     with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as fh:
         json.dump(out, fh, indent=1)
     print(json.dumps(out, indent=1))
