@@ -12,7 +12,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libagnn.so")
+LIB_PATH = os.environ.get("AGNN_LIB_PATH") or os.path.join(_HERE, "lib", "libagnn.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MAX_SEG = 32
@@ -178,6 +178,10 @@ _PROTOTYPES = {
                                      C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "agnn_split_f16_dropout": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "agnn_split_f16_shifted": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_float, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]),
+    "agnn_sage_weights": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnn_row_blocks": (C.c_int, [C.c_int64]),
     "agnn_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),

@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
                                                          int64_t ld_x, const float* __restrict__ amax,
                                                          __half* __restrict__ hi, __half* __restrict__ lo, int64_t ld_o,
                                                          float drop_p, const uint64_t* __restrict__ rng,
-                                                         uint32_t rng_stream) {
+                                                         uint32_t rng_stream, int seq_len, int shift) {
   const float s = f16_scale_of(__ldg(amax));
   const int64_t total = rows * cols4;
   const bool drop = drop_p > 0.f && rng;
@@ -947,8 +947,14 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     const int64_t r = i / cols4;
     const int c = (int)(i - r * cols4) * 4;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + c));
-    float in[4] = {v.x, v.y, v.z, v.w};
+    float in[4] = {0.f, 0.f, 0.f, 0.f};
+    // shift != 0: output row r holds input row r - shift of the SAME sequence (rows come in sequences of seq_len),
+    // zeros where that row does not exist -- the h_{t-1} (or h_{t+1}) operand of a GRU's recurrent weight gradient
+    const int64_t rs = r - shift;
+    if (shift == 0 || (rs >= 0 && rs < rows && rs / seq_len == r / seq_len)) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + rs * ld_x + c));
+      in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
+    }
     if (drop) {                                   // same mask as agnn_dropout_apply on [rows, cols]
       const uint64_t bits = dropout_bits(key, (uint64_t)i);
 #pragma unroll
@@ -1069,7 +1075,14 @@ extern "C" int agnn_split_f16(const float* x, int64_t rows, int64_t cols, int64_
 extern "C" int agnn_split_f16_dropout(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax,
                                       void* hi, void* lo, int64_t ld_out, float dropout_p, const uint64_t* rng_state,
                                       uint32_t rng_stream, agnn_stream_t stream) {
+  return agnn_split_f16_shifted(x, rows, cols, ld_x, amax, hi, lo, ld_out, dropout_p, rng_state, rng_stream, 1, 0, stream);
+}
+
+extern "C" int agnn_split_f16_shifted(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax,
+                                      void* hi, void* lo, int64_t ld_out, float dropout_p, const uint64_t* rng_state,
+                                      uint32_t rng_stream, int32_t seq_len, int32_t shift, agnn_stream_t stream) {
   if (rows < 0 || cols < 0 || !amax || !hi || !lo) return fail(AGNN_ERR_ARG, "split_f16: bad arguments");
+  if (seq_len < 1 || shift <= -seq_len || shift >= seq_len) return fail(AGNN_ERR_ARG, "split_f16: bad sequence shift");
   if (dropout_p < 0.f || dropout_p >= 1.f) return fail(AGNN_ERR_ARG, "split_f16: dropout needs 0 <= p < 1");
   if (rows == 0 || cols == 0) return AGNN_OK;
   if (cols % 4 || (ld_x * 4) % 16 || (ld_out * 2) % 16 || !aligned16(x) || !aligned16(hi) || !aligned16(lo))
@@ -1078,7 +1091,8 @@ extern "C" int agnn_split_f16_dropout(const float* x, int64_t rows, int64_t cols
   if (blocks > kNumSM * 16) blocks = kNumSM * 16;
   split_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, (int)(cols / 4), ld_x, amax,
                                                                         static_cast<__half*>(hi), static_cast<__half*>(lo),
-                                                                        ld_out, dropout_p, rng_state, rng_stream);
+                                                                        ld_out, dropout_p, rng_state, rng_stream, seq_len,
+                                                                        shift);
   return check_launch("split_f16");
 }
 

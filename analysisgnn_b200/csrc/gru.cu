@@ -22,7 +22,10 @@
 namespace agnn {
 namespace {
 
-constexpr int kSeq = 2;       // sequences per CTA (reuse of the register-resident weights)
+#ifndef AGNN_GRU_SEQ
+#define AGNN_GRU_SEQ 2
+#endif
+constexpr int kSeq = AGNN_GRU_SEQ;   // sequences per CTA (reuse of the register-resident weights; <= 3: 3H threads own kSeq * H units)
 constexpr int kPrefetch = 4;  // time steps of input prefetched ahead
 
 struct GruParams {

@@ -451,6 +451,46 @@ __global__ void __launch_bounds__(kThreads) reduce_partials_kernel(const float* 
 
 __global__ void dropout_advance_kernel(uint64_t* state) { state[1] += 1; }
 
+// fused-layer weight of one destination type: wcat[n, :] = [sum_r Wr_r[n] | Wl_1[n] | .. | Wl_k[n]] * scale,
+// bias[n] = sum_r b_r[n] * scale (sums in relation order)
+struct SageWeightParams {
+  int k, n, f4;
+  float scale;
+  const float* wr[AGNN_MAX_REL];
+  const float* wl[AGNN_MAX_REL];
+  const float* bl[AGNN_MAX_REL];
+  float* wcat;
+  float* bias;
+};
+
+__global__ void __launch_bounds__(kThreads) sage_weights_kernel(const __grid_constant__ SageWeightParams p) {
+  const int row4 = (p.k + 1) * p.f4;
+  const int64_t total = (int64_t)p.n * row4;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total + p.n; i += (int64_t)gridDim.x * kThreads) {
+    if (i >= total) {                               // the bias tail
+      const int r = (int)(i - total);
+      float b = 0.f;
+      for (int j = 0; j < p.k; ++j) b += __ldg(p.bl[j] + r);
+      p.bias[r] = b * p.scale;
+      continue;
+    }
+    const int r = (int)(i / row4), c4 = (int)(i - (int64_t)r * row4);
+    const int blk = c4 / p.f4, c = (c4 - blk * p.f4) * 4;
+    float4 v;
+    if (blk == 0) {
+      v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < p.k; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.wr[j] + (int64_t)r * p.f4 * 4 + c));
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>(p.wl[blk - 1] + (int64_t)r * p.f4 * 4 + c));
+    }
+    *reinterpret_cast<float4*>(p.wcat + (int64_t)r * row4 * 4 + (int64_t)c4 * 4) =
+        make_float4(v.x * p.scale, v.y * p.scale, v.z * p.scale, v.w * p.scale);
+  }
+}
+
 // y = keep ? x / (1 - p) : 0, mask of (rng, stream, row * cols + col); cols % 4 == 0
 __global__ void __launch_bounds__(kThreads) dropout_apply_kernel(const float* __restrict__ x, int64_t ld_x,
                                                                   float* __restrict__ y, int64_t ld_y, int64_t rows,
@@ -579,6 +619,24 @@ extern "C" int agnn_layernorm_bwd_dropout(const float* dy, int64_t ld_dy, const 
                                                                                         (int64_t)blocks * cols, cols);
   }
   return check_launch("layernorm_bwd");
+}
+
+extern "C" int agnn_sage_weights(int k, int32_t n, int32_t f, const float* const* lin_r, const float* const* lin_l,
+                                 const float* const* bias_l, float scale, float* wcat, float* bias, agnn_stream_t stream) {
+  if (k < 1 || k > AGNN_MAX_REL || n < 1 || f < 4 || f % 4 || !lin_r || !lin_l || !bias_l || !wcat || !bias)
+    return fail(AGNN_ERR_ARG, "sage_weights: 1..%d relations, feature count a multiple of 4", AGNN_MAX_REL);
+  SageWeightParams p;
+  p.k = k; p.n = n; p.f4 = f / 4; p.scale = scale; p.wcat = wcat; p.bias = bias;
+  for (int j = 0; j < k; ++j) {
+    if (!lin_r[j] || !lin_l[j] || !bias_l[j] || !aligned16(lin_r[j]) || !aligned16(lin_l[j]))
+      return fail(AGNN_ERR_ARG, "sage_weights: null or unaligned parameter %d", j);
+    p.wr[j] = lin_r[j]; p.wl[j] = lin_l[j]; p.bl[j] = bias_l[j];
+  }
+  if (!aligned16(wcat)) return fail(AGNN_ERR_ARG, "sage_weights: unaligned output");
+  int64_t blocks = ceil_div((int64_t)n * (k + 1) * (f / 4) + n, kThreads);
+  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
+  sage_weights_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("sage_weights");
 }
 
 extern "C" int agnn_dropout_advance(uint64_t* rng_state, agnn_stream_t stream) {

@@ -211,10 +211,11 @@ def f16_ok(x: torch.Tensor) -> bool:
             and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.shape[0] > 0)
 
 
-def split_f16(x: torch.Tensor, amax: Optional[torch.Tensor] = None, dropout=None) -> SplitH:
+def split_f16(x: torch.Tensor, amax: Optional[torch.Tensor] = None, dropout=None, shift=None) -> SplitH:
     """hi = fp16(s x), lo = fp16(s x - hi); ``amax`` (device scalar >= max |x| / 4) is the producer's tag or measured
     when not given.  ``dropout = (p, site)``: the pair of the dropped-out matrix (counter-based mask, 1 / (1 - p)
-    scaling; p < 0.75 keeps the result inside the scale's 4x headroom)."""
+    scaling; p < 0.75 keeps the result inside the scale's 4x headroom).  ``shift = (seq_len, s)``: the pair of the matrix
+    whose row r is row r - s of the same length-``seq_len`` sequence, zeros elsewhere (agnn_split_f16_shifted)."""
     _need_cuda(x)
     if not f16_ok(x):
         raise ValueError("split_f16 needs an fp32 matrix with unit column stride, 16-byte aligned rows and a column "
@@ -227,10 +228,11 @@ def split_f16(x: torch.Tensor, amax: Optional[torch.Tensor] = None, dropout=None
     p, site = dropout if dropout is not None else (0.0, 0)
     if p >= 0.75:
         raise ValueError("fused dropout supports p < 0.75")
-    _lib.check(_lib.lib().agnn_split_f16_dropout(x.data_ptr(), rows, cols, x.stride(0), amax.data_ptr(),
+    seq_len, sh = shift if shift is not None else (1, 0)
+    _lib.check(_lib.lib().agnn_split_f16_shifted(x.data_ptr(), rows, cols, x.stride(0), amax.data_ptr(),
                                                  buf[0].data_ptr(), buf[1].data_ptr(), cols, float(p),
                                                  dropout_state(x.device).data_ptr() if p > 0 else None, int(site),
-                                                 stream), "agnn_split_f16")
+                                                 int(seq_len), int(sh), stream), "agnn_split_f16")
     _lib.count_launches(1)
     return SplitH(buf[0], buf[1], amax)
 

@@ -577,15 +577,27 @@ class _SageWeights(torch.autograd.Function):
     @staticmethod
     def forward(ctx, scale, k, *tensors):
         wr, wl, bl = tensors[:k], tensors[k:2 * k], tensors[2 * k:]
-        if k > 1:
-            root = torch.stack(wr, dim=0).sum(0)
-            bias = torch.stack(bl, dim=0).sum(0)
+        n, f = wl[0].shape
+        fused = (wl[0].is_cuda and wl[0].dtype == torch.float32 and f % 4 == 0 and k <= _lib.MAX_REL
+                 and all(t.is_contiguous() and t.data_ptr() % 16 == 0 for t in tensors[:2 * k])
+                 and all(t.is_contiguous() for t in bl))
+        if fused:                                                  # one launch (agnn_sage_weights)
+            wcat = torch.empty((n, (k + 1) * f), dtype=torch.float32, device=wl[0].device)
+            bias = torch.empty(n, dtype=torch.float32, device=wl[0].device)
+            _lib.check(_lib.lib().agnn_sage_weights(k, n, f, _lib.ptr_array(list(wr)), _lib.ptr_array(list(wl)),
+                                                    _lib.ptr_array(list(bl)), float(scale), wcat.data_ptr(),
+                                                    bias.data_ptr(), _stream(wcat)), "agnn_sage_weights")
+            _lib.count_launches(1)
         else:
-            root, bias = wr[0], bl[0].clone()
-        wcat = torch.cat([root] + list(wl), dim=1)
-        if scale != 1.0:
-            wcat.mul_(scale)
-            bias.mul_(scale)
+            if k > 1:
+                root = torch.stack(wr, dim=0).sum(0)
+                bias = torch.stack(bl, dim=0).sum(0)
+            else:
+                root, bias = wr[0], bl[0].clone()
+            wcat = torch.cat([root] + list(wl), dim=1)
+            if scale != 1.0:
+                wcat.mul_(scale)
+                bias.mul_(scale)
         ctx.scale, ctx.k = scale, k
         ctx.feat = wl[0].shape[1]
         return wcat, bias
@@ -1204,7 +1216,16 @@ class _GRULayer(torch.autograd.Function):
         grads = []
         dx = None
         gi_ops, gh_ops, hp_ops = [], [], []
+        out2 = out.view(b * t, n_dir * h)
         for d in range(n_dir):
+            # dgi meets xs in the grad-weight GEMM: same operand form
+            gi_ops.append((linalg.prepare_auto if isinstance(xs, linalg.SplitH) else linalg.prepare)(dgi[d]))
+            gh_ops.append(linalg.prepare_auto(dgh[d]))               # (split_f16 finds the tags: no amax pass)
+            hd2 = out2[:, d * h:(d + 1) * h]                         # this direction's states, [B T, H] strided view
+            if isinstance(gh_ops[-1], linalg.SplitH) and linalg.f16_ok(hd2):
+                # h_{t-1} (forward direction) / h_{t+1} (reverse): the operand pair straight from the GRU output
+                hp_ops.append(linalg.split_f16(hd2, linalg.const_amax(out.device, 1.0), shift=(t, 1 if d == 0 else -1)))
+                continue
             hd = out[:, :, d * h:(d + 1) * h]
             h_prev = torch.zeros((b, t, h), dtype=out.dtype, device=out.device)
             if t > 1:
@@ -1212,12 +1233,7 @@ class _GRULayer(torch.autograd.Function):
                     h_prev[:, 1:] = hd[:, :-1]
                 else:
                     h_prev[:, :-1] = hd[:, 1:]
-            # dgi meets xs in the grad-weight GEMM: same operand form
-            gi_ops.append((linalg.prepare_auto if isinstance(xs, linalg.SplitH) else linalg.prepare)(dgi[d]))
-            gh_ops.append(linalg.prepare_auto(dgh[d]))               # (split_f16 finds the tags: no amax pass)
-            hp = h_prev.reshape(b * t, h)
-            hp_ops.append(linalg.split_f16(hp, linalg.const_amax(hp.device, 1.0))
-                          if isinstance(gh_ops[-1], linalg.SplitH) and linalg.f16_ok(hp) else hp)
+            hp_ops.append(h_prev.reshape(b * t, h))
         # weight gradients of all directions (input and recurrent) in one grouped launch
         dws = linalg.mm_tn_group(gi_ops + gh_ops, [xs] * n_dir + hp_ops)
         if ctx.needs_input_grad[0]:

@@ -431,6 +431,18 @@ int agnn_dropout_apply(const float* x, int64_t ld_x, float* y, int64_t ld_y, int
 int agnn_split_f16_dropout(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax, void* hi, void* lo,
                            int64_t ld_out, float dropout_p, const uint64_t* rng_state, uint32_t rng_stream,
                            agnn_stream_t stream);
+/* agnn_split_f16_shifted: the pair of the matrix whose row r is input row r - shift of the same sequence (rows come in
+ * sequences of seq_len; zeros where that row does not exist): the h_{t-1} / h_{t+1} operand of a GRU's recurrent
+ * weight gradient straight from the GRU output, without materialising the shifted copy (shift = 0: agnn_split_f16_dropout). */
+int agnn_split_f16_shifted(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* amax, void* hi, void* lo,
+                           int64_t ld_out, float dropout_p, const uint64_t* rng_state, uint32_t rng_stream,
+                           int32_t seq_len, int32_t shift, agnn_stream_t stream);
+/* The fused weight of one destination type of a PyG HeteroConv{SAGEConv} layer from the k relations' parameters
+ * (contiguous fp32 [n, f] / [n]): wcat [n, (k + 1) f] = [sum_r lin_r_r | lin_l_1 | .. | lin_l_k] * scale,
+ * bias [n] = sum_r bias_l_r * scale -- one launch instead of stack / sum / cat per layer and type. */
+int agnn_sage_weights(int k, int32_t n, int32_t f, const float* const* lin_r /* host [k] */,
+                      const float* const* lin_l, const float* const* bias_l, float scale, float* wcat, float* bias,
+                      agnn_stream_t stream);
 int agnn_l2norm_relu_fwd(const float* x, int64_t ld_x, float* y, int64_t ld_y, float* inv_norm, int64_t rows, int cols,
                          int relu_first, float eps, agnn_stream_t stream);
 int agnn_l2norm_relu_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* inv_norm, float* dx,

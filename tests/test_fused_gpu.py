@@ -188,3 +188,43 @@ def test_mlp_group_of_heads_is_one_launch_per_stage():
     # amax passes: the three incoming gradients (random tensors without a tag) and the three zero-padded copies of
     # the odd-width head weights -- none over the intermediate gradients, which carry their producers' tags
     assert linalg.stats.get("amax_passes", 0) - passes <= 6
+
+
+@pytest.mark.parametrize("b,t,h,n_dir", [(700, 30, 128, 2), (5, 1, 128, 1), (33, 7, 64, 2)])
+def test_shifted_split_is_the_previous_state_operand(b, t, h, n_dir):
+    """agnn_split_f16_shifted: the GRU's h_{t-1} (forward) / h_{t+1} (reverse) operand straight from the output
+    [B, T, n_dir H] -- bit-equal to splitting the materialised shifted copy."""
+    g = torch.Generator().manual_seed(5)
+    out = (torch.rand(b, t, n_dir * h, generator=g) * 2 - 1).to(DEV)
+    one = linalg.const_amax(out.device, 1.0)
+    out2 = out.view(b * t, n_dir * h)
+    for d in range(n_dir):
+        hd = out[:, :, d * h:(d + 1) * h]
+        prev = torch.zeros(b, t, h, device=DEV)
+        if t > 1:
+            if d == 0:
+                prev[:, 1:] = hd[:, :-1]
+            else:
+                prev[:, :-1] = hd[:, 1:]
+        want = linalg.split_f16(prev.reshape(b * t, h), one)
+        got = linalg.split_f16(out2[:, d * h:(d + 1) * h], one, shift=(t, 1 if d == 0 else -1))
+        assert torch.equal(got.hi, want.hi) and torch.equal(got.lo, want.lo)
+
+
+@pytest.mark.parametrize("k,n,f,scale", [(1, 256, 256, 1.0), (3, 256, 256, 1.0), (9, 128, 64, 0.5)])
+def test_sage_weight_assembly(k, n, f, scale):
+    """agnn_sage_weights (one launch) against stack / sum / cat, forward and the parameter gradients."""
+    from analysisgnn_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    mk = lambda *s: [torch.randn(*s, generator=g).to(DEV).requires_grad_() for _ in range(k)]
+    wr, wl, bl = mk(n, f), mk(n, f), mk(n)
+    wcat, bias = ops.sage_weights(wr, wl, bl, scale)
+    ref_w = torch.cat([torch.stack([w.double() for w in wr]).sum(0)] + [w.double() for w in wl], dim=1) * scale
+    ref_b = torch.stack([b.double() for b in bl]).sum(0) * scale
+    assert rel_err(wcat, ref_w) < 1e-6 and rel_err(bias, ref_b) < 1e-6
+    gw, gb = torch.randn(wcat.shape, generator=g).to(DEV), torch.randn(n, generator=g).to(DEV)
+    grads = torch.autograd.grad([wcat, bias], wr + wl + bl, [gw, gb])
+    for j in range(k):
+        assert torch.equal(grads[j], gw[:, :f] * scale)
+        assert torch.equal(grads[k + j], gw[:, (j + 1) * f:(j + 2) * f] * scale)
+        assert torch.equal(grads[2 * k + j], gb * scale)
