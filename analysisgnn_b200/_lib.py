@@ -23,7 +23,7 @@ SCALE_NONE, SCALE_MEAN = 0, 1
 COMBINE_CONCAT, COMBINE_SUM = 0, 1
 REL_IDENTITY_IF_EMPTY = 1
 EDGE_ABSDIFF, EDGE_ABSDIFF_DROW, EDGE_ABSDIFF_DNBR, EDGE_GATE, EDGE_GATE_DROW, EDGE_GATE_DNBR = range(6)
-HEAVY_ROW, HEAVY_CHUNK = 4096, 2048
+# HEAVY_ROW / HEAVY_CHUNK: build constants of the library (agnn_heavy_params), resolved on first use (__getattr__ below)
 GEMM_TF32X3, GEMM_TF32, GEMM_BF16, GEMM_F16X3 = 0, 1, 2, 3
 K_MAJOR, MN_MAJOR = 0, 1
 GEMM_RELU, GEMM_ACCUMULATE, GEMM_OUT_BF16 = 1, 2, 4
@@ -114,6 +114,7 @@ _PROTOTYPES = {
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "agnn_gather_heavy_workspace": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
+    "agnn_heavy_params": (None, [C.c_void_p, C.c_void_p]),
     "agnn_edge_op": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
                                C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -290,3 +291,25 @@ def lib() -> C.CDLL:
 def check(rc: int, what: str = "libagnn") -> None:
     if rc != 0:
         raise AgnnError(f"{what} failed ({rc}): {lib().agnn_last_error().decode()}")
+
+
+_heavy = None
+
+
+def heavy_params():
+    """(HEAVY_ROW, HEAVY_CHUNK) the loaded library was built with: rows of at least HEAVY_ROW entries are listed by
+    agnn_csr_build and split into HEAVY_CHUNK-edge chunks by agnn_gather_reduce."""
+    global _heavy
+    if _heavy is None:
+        a, b = C.c_int32(0), C.c_int32(0)
+        lib().agnn_heavy_params(C.byref(a), C.byref(b))
+        _heavy = (int(a.value), int(b.value))
+    return _heavy
+
+
+def __getattr__(name):
+    if name == "HEAVY_ROW":
+        return heavy_params()[0]
+    if name == "HEAVY_CHUNK":
+        return heavy_params()[1]
+    raise AttributeError(name)

@@ -164,11 +164,84 @@ __global__ void __launch_bounds__(kThreads) scan_add_kernel(const __grid_constan
   }
 }
 
+// One block per (segment, relation): the rows with >= AGNN_HEAVY_ROW entries in ascending row order, then (second half
+// of the relation's block in `heavy`) the exclusive prefix of their chunk counts, ceil(deg / AGNN_HEAVY_CHUNK) each:
+// agnn_gather_reduce finds chunk g's row, and a row's slot, by binary search instead of walking the list.
+constexpr int kHeavyThreads = 1024;
+constexpr int kHeavyPerThread = 8;
+
+__global__ void __launch_bounds__(kHeavyThreads) heavy_list_kernel(const __grid_constant__ SegTable tab,
+                                                                    const int32_t* __restrict__ rowptr,
+                                                                    int32_t* __restrict__ heavy,
+                                                                    int32_t* __restrict__ n_heavy) {
+  int r = blockIdx.x, s = 0;
+  while (r >= tab.seg[s].n_rel) r -= tab.seg[s++].n_rel;
+  const agnn_coo_t& g = tab.seg[s];
+  if (g.heavy_cap <= 0) return;
+  const int32_t* rp = rowptr + g.rowptr_off + (int64_t)r * (g.n_rows + 1);
+  int32_t* rows_out = heavy + g.heavy_off + (int64_t)r * 2 * g.heavy_cap;
+  int32_t* chunk_out = rows_out + g.heavy_cap;
+  __shared__ unsigned long long warp_tot[kHeavyThreads / 32];
+  __shared__ unsigned long long carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long carry = 0;                       // (heavy rows so far) << 32 | chunks so far
+  for (int base = 0; base < g.n_rows; base += kHeavyThreads * kHeavyPerThread) {
+    // thread t: rows base + t * kHeavyPerThread .. (consecutive, so slots come out in row order)
+    const int row0 = base + threadIdx.x * kHeavyPerThread;
+    int bound[kHeavyPerThread + 1];
+#pragma unroll
+    for (int i = 0; i <= kHeavyPerThread; ++i) bound[i] = row0 + i <= g.n_rows ? rp[row0 + i] : 0;
+    unsigned long long item[kHeavyPerThread], mine = 0;
+#pragma unroll
+    for (int i = 0; i < kHeavyPerThread; ++i) {
+      const int deg = row0 + i < g.n_rows ? bound[i + 1] - bound[i] : 0;
+      item[i] = deg >= AGNN_HEAVY_ROW
+                    ? (1ull << 32) | (unsigned)((deg + AGNN_HEAVY_CHUNK - 1) / AGNN_HEAVY_CHUNK) : 0ull;
+      mine += item[i];
+    }
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += t;
+      }
+      warp_tot[lane] = wi - w;                         // exclusive over warps
+      if (lane == 31) carry_s = wi;                    // block total
+    }
+    __syncthreads();
+    unsigned long long excl = carry + warp_tot[warp] + incl - mine;
+    if (mine) {
+#pragma unroll
+      for (int i = 0; i < kHeavyPerThread; ++i) {
+        if (item[i]) {
+          const long long slot = (long long)(excl >> 32);
+          if (slot < g.heavy_cap) {
+            rows_out[slot] = row0 + i;
+            chunk_out[slot] = (int32_t)(excl & 0xffffffffu);
+          }
+          excl += item[i];
+        }
+      }
+    }
+    carry += carry_s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_heavy[g.count_off + r] = (int32_t)(carry >> 32);
+}
+
 // thread per key: restore input order inside the row, emit col
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constant__ SegTable tab,
                                                              const int32_t* rowptr, int32_t* col, int32_t* perm,
-                                                             int32_t* long_count, int64_t* long_list,
-                                                             int32_t* heavy, int32_t* n_heavy) {
+                                                             int32_t* long_count, int64_t* long_list) {
   const int s = find_seg(tab.key_tile_start, tab.n_seg, blockIdx.x);
   const agnn_coo_t& g = tab.seg[s];
   const int64_t base = (int64_t)(blockIdx.x - tab.key_tile_start[s]) * kKeysPerTile;
@@ -179,11 +252,6 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constan
     const int beg = rowptr[g.rowptr_off + k], end = rowptr[g.rowptr_off + k + 1];
     const int deg = end - beg;
     if (deg == 0) continue;
-    if (deg >= AGNN_HEAVY_ROW && heavy && n_heavy && g.heavy_cap > 0) {
-      const int r = (int)(k / (g.n_rows + 1)), row = (int)(k % (g.n_rows + 1));
-      const int slot = atomicAdd(&n_heavy[g.count_off + r], 1);
-      if (slot < g.heavy_cap) heavy[g.heavy_off + (int64_t)r * g.heavy_cap + slot] = row;
-    }
     if (deg > kShortRow) {
       const int slot = atomicAdd(long_count, 1);
       long_list[slot] = ((int64_t)s << 40) | k;
@@ -346,21 +414,20 @@ extern "C" int agnn_csr_build(int n_seg, const agnn_coo_t* segs, int32_t* rowptr
   const int key_tiles = tab.key_tile_start[n_seg], edge_blks = tab.edge_blk_start[n_seg];
 
   if (cudaMemsetAsync(long_count, 0, 4, stream) != cudaSuccess) return check_launch("csr_build memset");
-  if (heavy && n_heavy) {
-    for (int s = 0; s < n_seg; ++s)
-      if (segs[s].heavy_cap > 0 &&
-          cudaMemsetAsync(n_heavy + segs[s].count_off, 0, (size_t)segs[s].n_rel * 4, stream) != cudaSuccess)
-        return check_launch("csr_build memset");
-  }
   zero_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, cursor);
   if (edge_blks > 0) edge_kernel<false><<<edge_blks, kThreads, 0, stream>>>(tab, rowptr, cursor, perm, status);
   scan_tile_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, tile_sums);
   scan_sums_kernel<<<n_seg, kThreads, 0, stream>>>(tab, tile_sums);
   scan_add_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, tile_sums);
+  if (heavy && n_heavy) {
+    int n_blocks = 0;
+    for (int s = 0; s < n_seg; ++s) n_blocks += segs[s].n_rel;
+    heavy_list_kernel<<<n_blocks, kHeavyThreads, 0, stream>>>(tab, rowptr, heavy, n_heavy);
+  }
   if (edge_blks > 0) {
     if (!col || !perm) return fail(AGNN_ERR_ARG, "csr_build: null col/perm with edges present");
     edge_kernel<true><<<edge_blks, kThreads, 0, stream>>>(tab, rowptr, cursor, perm, status);
-    finalize_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list, heavy, n_heavy);
+    finalize_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list);
     gather_col_kernel<<<edge_blks, kThreads, 0, stream>>>(tab, col, perm);
     long_rows_kernel<<<kNumSM * 2, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list);
   }

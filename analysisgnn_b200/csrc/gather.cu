@@ -366,161 +366,267 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_sum_kernel(co
 }
 
 // ---- heavy rows: split across warps -------------------------------------------------------------
-// Chunk numbering: relations in order, their heavy entries in list order, kHeavyChunk edges per chunk.
-// Every warp walks the (short) heavy lists to find the chunks it owns; partial sums go to heavy_ws and
-// are combined per row in chunk order by the second kernel (deterministic, no atomics).
+// Chunk numbering: relations in order, their heavy rows in list (= row) order, kHeavyChunk edges per chunk; the
+// list carries the exclusive prefix of the chunk counts (agnn_csr_build), so warp g finds its chunk by a binary
+// search and never walks the lists.  Partial sums go to heavy_ws and are combined per row in chunk order by the second
+// kernel (deterministic, no atomics).
+struct HeavyIndex {
+  int nh;        // lane r: heavy rows of relation r
+  int64_t base;  // lane r: first chunk of relation r in the global numbering
+  int64_t incl;  // lane r: base + chunks of relation r
+  int item_incl; // lane r: heavy rows of relations 0..r
+};
+
+// lane r < n_rel resolves relation r's list; every lane gets the totals through shuffles
+__device__ __forceinline__ HeavyIndex heavy_index(const GatherParams& p, int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  HeavyIndex ix;
+  ix.nh = 0;
+  long long chunks = 0;
+  if (lane < p.n_rel) {
+    const agnn_rel_t& R = p.rel[lane];
+    if (R.heavy_rows && R.heavy_cap > 0) {
+      ix.nh = (int)min((int64_t)__ldg(R.n_heavy), R.heavy_cap);
+      if (ix.nh > 0) {
+        const int row = __ldg(R.heavy_rows + ix.nh - 1);
+        const int deg = __ldg(R.rowptr + row + 1) - __ldg(R.rowptr + row);
+        chunks = (long long)__ldg(R.heavy_rows + R.heavy_cap + ix.nh - 1) + (deg + kHeavyChunk - 1) / kHeavyChunk;
+      }
+    }
+  }
+  long long incl = chunks;
+  int items = ix.nh;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long t = __shfl_up_sync(kFull, incl, d);
+    const int ti = __shfl_up_sync(kFull, items, d);
+    if (lane >= d) { incl += t; items += ti; }
+  }
+  ix.incl = incl;
+  ix.base = incl - chunks;
+  ix.item_incl = items;
+  return ix;
+}
+
+// the last slot h in [0, n) with a[h] <= key (a ascending, a[0] <= key)
+__device__ __forceinline__ int upper_slot(const int32_t* __restrict__ a, int n, int key) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(a + mid) <= key) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads) gather_heavy_partial_kernel(const __grid_constant__ GatherParams p) {
   using VT = Vec16<T>;
   constexpr int E = VT::E;
+  constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int64_t warp_id = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
   const int F = p.n_feat;
-  int64_t g = 0;
-  for (int r = 0; r < p.n_rel; ++r) {
+  const HeavyIndex ix = heavy_index(p, lane);
+  const int64_t total = min((int64_t)__shfl_sync(kFull, ix.incl, 31), p.max_chunks);
+  for (int64_t g = warp_id; g < total; g += n_warps) {
+    int r = 0;
+    for (int q = 0; q < p.n_rel; ++q) r += (__shfl_sync(kFull, ix.incl, q) <= g) ? 1 : 0;
+    r = min(r, p.n_rel - 1);
     const agnn_rel_t& R = p.rel[r];
-    if (!R.heavy_rows) continue;
-    const int nh = (int)min((int64_t)__ldg(R.n_heavy), R.heavy_cap);
+    const int local = (int)(g - __shfl_sync(kFull, ix.base, r));
+    const int nh = __shfl_sync(kFull, ix.nh, r);
+    const int h = upper_slot(R.heavy_rows + R.heavy_cap, nh, local);
+    const int c = local - __ldg(R.heavy_rows + R.heavy_cap + h);
+    const int row = __ldg(R.heavy_rows + h);
+    const int beg = __ldg(R.rowptr + row), end = __ldg(R.rowptr + row + 1);
     const T* src = static_cast<const T*>(R.src);
-    for (int h = 0; h < nh; ++h) {
-      const int row = __ldg(R.heavy_rows + h);
-      const int beg = __ldg(R.rowptr + row), end = __ldg(R.rowptr + row + 1);
-      const int chunks = (end - beg + kHeavyChunk - 1) / kHeavyChunk;
-      for (int c = 0; c < chunks; ++c, ++g) {
-        if (g % n_warps != warp_id || g >= p.max_chunks) continue;
-        float acc[V][E];
+    float acc[V][E];
 #pragma unroll
-        for (int v = 0; v < V; ++v)
+    for (int v = 0; v < V; ++v)
 #pragma unroll
-          for (int e = 0; e < E; ++e) acc[v][e] = 0.f;
-        const int k0 = beg + c * kHeavyChunk, k1 = min(k0 + kHeavyChunk, end);
-        for (int k = k0; k < k1; k += kUnroll) {
-          int idx[kUnroll];
-          float w[kUnroll];
-          float x[kUnroll][V][E];
+      for (int e = 0; e < E; ++e) acc[v][e] = 0.f;
+    const int k0 = beg + c * kHeavyChunk, k1 = min(k0 + kHeavyChunk, end);
+    for (int kb = k0; kb < k1; kb += 32) {
+      // lane t resolves edge kb + t (column id, neighbour-degree weight), then the warp streams the rows
+      int my_idx = -1;
+      float my_w = 1.f;
+      if (kb + lane < k1) {
+        my_idx = __ldg(R.col + kb + lane);
+        if (R.nbr_deg_rowptr) {
+          const int d = __ldg(R.nbr_deg_rowptr + my_idx + 1) - __ldg(R.nbr_deg_rowptr + my_idx);
+          my_w = 1.f / (float)max(d, 1);
+        }
+      }
+      const int n_items = min(32, k1 - kb);
+      for (int i0 = 0; i0 < n_items; i0 += kUnroll) {
+        int idx[kUnroll];
+        float w[kUnroll];
+        float x[kUnroll][V][E];
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u) {
-            idx[u] = (k + u < k1) ? __ldg(R.col + k + u) : -1;
-            w[u] = 1.f;
-            if (idx[u] >= 0 && R.nbr_deg_rowptr) {
-              const int d = __ldg(R.nbr_deg_rowptr + idx[u] + 1) - __ldg(R.nbr_deg_rowptr + idx[u]);
-              w[u] = 1.f / (float)max(d, 1);
+        for (int u = 0; u < kUnroll; ++u) {
+          const int sl = min(i0 + u, 31);
+          const int t = __shfl_sync(kFull, my_idx, sl);
+          idx[u] = (i0 + u < n_items) ? t : -1;
+          w[u] = __shfl_sync(kFull, my_w, sl);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (idx[u] >= 0) {
+            const T* rp = src + (int64_t)idx[u] * R.ld_src;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const int cc = (v * 32 + lane) * E;
+              if (cc < F) VT::load_nc(rp + cc, x[u][v]);
             }
           }
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
-            if (idx[u] >= 0) {
-              const T* rp = src + (int64_t)idx[u] * R.ld_src;
+        for (int u = 0; u < kUnroll; ++u)
+          if (idx[u] >= 0) {
 #pragma unroll
-              for (int v = 0; v < V; ++v) {
-                const int cc = (v * 32 + lane) * E;
-                if (cc < F) VT::load_nc(rp + cc, x[u][v]);
-              }
-            }
+            for (int v = 0; v < V; ++v)
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
-            if (idx[u] >= 0) {
-#pragma unroll
-              for (int v = 0; v < V; ++v)
-#pragma unroll
-                for (int e = 0; e < E; ++e) acc[v][e] = fmaf(w[u], x[u][v][e], acc[v][e]);
-            }
-        }
-        float* wp = p.heavy_ws + g * F;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const int cc = (v * 32 + lane) * E;
-          if (cc < F) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) wp[cc + e] = acc[v][e];
+              for (int e = 0; e < E; ++e) acc[v][e] = fmaf(w[u], x[u][v][e], acc[v][e]);
           }
-        }
+      }
+    }
+    float* wp = p.heavy_ws + g * F;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int cc = (v * 32 + lane) * E;
+      if (cc < F) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) wp[cc + e] = acc[v][e];
       }
     }
   }
 }
 
-// CONCAT: one warp per heavy (relation, row) -- every (relation, row) owns its output slice.  SUM: one warp per heavy
-// ROW: the warp that owns the row's FIRST heavy relation adds the chunk partials of every heavy relation of that row
-// in relation order (chunks in order inside a relation) to what the main kernel wrote (self + light relations) and
-// stores once.  One writer per output element, fixed summation order: no atomics, bit-identical from run to run.
+// The chunk partials of one (relation, heavy row), added up by the whole block: warp w takes chunks w, w + 8, ..
+// (four loads in flight), warp 0 then adds the eight warp sums in warp order -- a fixed order, so the result is
+// bit-identical from run to run, and a hub of a million edges is not one warp's serial chain.  Warp 0 holds the result.
+template <int V, int E>
+__device__ __forceinline__ void block_partials(const float* __restrict__ ws, int64_t g0, int chunks, int F,
+                                               float (*part)[32 * V * E], float (&acc)[V][E]) {
+  constexpr int kWarps = kThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[v][e] = 0.f;
+  for (int c = warp; c < chunks; c += 4 * kWarps) {
+    float x[4][V][E];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int cu = c + u * kWarps;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int cc = (v * 32 + lane) * E;
+#pragma unroll
+        for (int e = 0; e < E; e += 4) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cu < chunks && cc < F) t = *reinterpret_cast<const float4*>(ws + (g0 + cu) * F + cc + e);
+          x[u][v][e] = t.x; x[u][v][e + 1] = t.y; x[u][v][e + 2] = t.z; x[u][v][e + 3] = t.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[v][e] += x[u][v][e];
+  }
+  if (chunks <= 1) return;                              // (block-uniform) warp 0 read the only chunk
+  __syncthreads();                                      // the previous call's readers are done with `part`
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int e = 0; e < E; ++e) part[warp][(v * 32 + lane) * E + e] = acc[v][e];
+  __syncthreads();
+  if (warp == 0) {
+    const int n = min(chunks, kWarps);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        float t = part[0][(v * 32 + lane) * E + e];
+        for (int w = 1; w < n; ++w) t += part[w][(v * 32 + lane) * E + e];
+        acc[v][e] = t;
+      }
+  }
+}
+
+// One block per heavy (relation, row).  CONCAT: every (relation, row) owns its output slice.  SUM: the block of the
+// row's FIRST heavy relation adds the chunk partials of every heavy relation of that row in relation order to what the
+// main kernel wrote (self + light relations) and stores once.  One writer per output element, fixed summation order:
+// no atomics, bit-identical from run to run.
 template <typename T, int V>
 __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __grid_constant__ GatherParams p) {
   using VT = Vec16<T>;
   constexpr int E = VT::E;
+  constexpr unsigned kFull = 0xffffffffu;
+  __shared__ __align__(16) float part[kThreads / 32][32 * V * E];
   const int lane = threadIdx.x & 31;
-  const int64_t warp_id = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  const int64_t n_warps = (int64_t)gridDim.x * (kThreads / 32);
+  const bool writer = threadIdx.x < 32;
   const int F = p.n_feat;
   T* const out = static_cast<T*>(p.out);
   T* const out_lo = static_cast<T*>(p.out_lo);
   const float f16s = p.pair_amax ? f16_scale_of(__ldg(p.pair_amax)) : 0.f;
   const bool sum_mode = p.combine == AGNN_COMBINE_SUM;
   uint32_t hmx = 0;
-  int64_t g = 0, item = 0;
-  for (int r = 0; r < p.n_rel; ++r) {
+  const HeavyIndex ix = heavy_index(p, lane);
+  const int n_items = __shfl_sync(kFull, ix.item_incl, 31);
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int r = 0;
+    for (int q = 0; q < p.n_rel; ++q) r += (__shfl_sync(kFull, ix.item_incl, q) <= item) ? 1 : 0;
+    r = min(r, p.n_rel - 1);
     const agnn_rel_t& R = p.rel[r];
-    if (!R.heavy_rows) continue;
-    const int nh = (int)min((int64_t)__ldg(R.n_heavy), R.heavy_cap);
-    for (int h = 0; h < nh; ++h, ++item) {
-      const int row = __ldg(R.heavy_rows + h);
-      const int beg = __ldg(R.rowptr + row), end = __ldg(R.rowptr + row + 1);
-      const int chunks = (end - beg + kHeavyChunk - 1) / kHeavyChunk;
-      const int64_t g0 = g;
-      g += chunks;
-      if (item % n_warps != warp_id || g > p.max_chunks) continue;
-      if (sum_mode) {
-        // the row belongs to the warp of its first heavy relation
-        bool first = true;
-        for (int q = 0; q < r && first; ++q) {
-          const agnn_rel_t& Q = p.rel[q];
-          if (is_heavy(p, Q, __ldg(Q.rowptr + row + 1) - __ldg(Q.rowptr + row))) first = false;
-        }
-        if (!first) continue;
+    const int h = item - (__shfl_sync(kFull, ix.item_incl, r) - __shfl_sync(kFull, ix.nh, r));
+    const int row = __ldg(R.heavy_rows + h);
+    const int beg = __ldg(R.rowptr + row), end = __ldg(R.rowptr + row + 1);
+    const int chunks = (end - beg + kHeavyChunk - 1) / kHeavyChunk;
+    const int64_t g0 = __shfl_sync(kFull, ix.base, r) + __ldg(R.heavy_rows + R.heavy_cap + h);
+    if (g0 + chunks > p.max_chunks) continue;
+    if (sum_mode) {
+      // the row belongs to the block of its first heavy relation
+      bool first = true;
+      for (int q = 0; q < r && first; ++q) {
+        const agnn_rel_t& Q = p.rel[q];
+        if (is_heavy(p, Q, __ldg(Q.rowptr + row + 1) - __ldg(Q.rowptr + row))) first = false;
       }
-      float acc[V][E];
+      if (!first) continue;
+    }
+    float acc[V][E];
+    block_partials<V, E>(p.heavy_ws, g0, chunks, F, part, acc);
+    const float s = p.scale == AGNN_SCALE_MEAN ? 1.f / (float)max(end - beg, 1) : 1.f;
+    if (!sum_mode) {
+      if (!writer) continue;
+      const int64_t off = (int64_t)row * p.ld_out + R.out_col;
 #pragma unroll
-      for (int v = 0; v < V; ++v)
+      for (int v = 0; v < V; ++v) {
+        const int cc = (v * 32 + lane) * E;
+        if (cc < F) {
+          float o[E];
+          if (p.self_add) {
+            float sv[E];
+            VT::load_nc(static_cast<const T*>(p.self_add) + (int64_t)row * p.ld_self + cc, sv);
 #pragma unroll
-        for (int e = 0; e < E; ++e) acc[v][e] = 0.f;
-      for (int c = 0; c < chunks; ++c) {
-        const float* wp = p.heavy_ws + (g0 + c) * F;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const int cc = (v * 32 + lane) * E;
-          if (cc < F) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) acc[v][e] += wp[cc + e];
+            for (int e = 0; e < E; ++e) acc[v][e] += sv[e];
           }
+#pragma unroll
+          for (int e = 0; e < E; ++e) o[e] = acc[v][e] * s;
+          hmx = absmax_bits<E>(hmx, o);
+          store_split<T>(out, out_lo, off + cc, o, f16s);
         }
       }
-      const float s = p.scale == AGNN_SCALE_MEAN ? 1.f / (float)max(end - beg, 1) : 1.f;
-      if (!sum_mode) {
-        const int64_t off = (int64_t)row * p.ld_out + R.out_col;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const int cc = (v * 32 + lane) * E;
-          if (cc < F) {
-            float o[E];
-            if (p.self_add) {
-              float sv[E];
-              VT::load_nc(static_cast<const T*>(p.self_add) + (int64_t)row * p.ld_self + cc, sv);
-#pragma unroll
-              for (int e = 0; e < E; ++e) acc[v][e] += sv[e];
-            }
-#pragma unroll
-            for (int e = 0; e < E; ++e) o[e] = acc[v][e] * s;
-            hmx = absmax_bits<E>(hmx, o);
-            store_split<T>(out, out_lo, off + cc, o, f16s);
-          }
-        }
-        continue;
-      }
-      // COMBINE_SUM: what the main kernel wrote (self + light relations), then relation r, then the later heavy
-      // relations of the same row in relation order
-      float tot[V][E];
-      const int64_t off = (int64_t)row * p.ld_out + p.rel[0].out_col;
+      continue;
+    }
+    // COMBINE_SUM: what the main kernel wrote (self + light relations), then relation r, then the later heavy
+    // relations of the same row in relation order
+    float tot[V][E];
+    const int64_t off = (int64_t)row * p.ld_out + p.rel[0].out_col;
+    if (writer) {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int cc = (v * 32 + lane) * E;
@@ -536,45 +642,29 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
           for (int e = 0; e < E; ++e) tot[v][e] = fmaf(acc[v][e], s, tot[v][e]);
         }
       }
-      int64_t g2 = g;                                   // chunk base of relation r's entries after (r, h) ...
-      for (int h2 = h + 1; h2 < nh; ++h2) {
-        const int row2 = __ldg(R.heavy_rows + h2);
-        g2 += (__ldg(R.rowptr + row2 + 1) - __ldg(R.rowptr + row2) + kHeavyChunk - 1) / kHeavyChunk;
+    }
+    for (int q = r + 1; q < p.n_rel; ++q) {
+      const agnn_rel_t& Q = p.rel[q];
+      const int b2 = __ldg(Q.rowptr + row), e2 = __ldg(Q.rowptr + row + 1);
+      if (!is_heavy(p, Q, e2 - b2)) continue;
+      const int nq = __shfl_sync(kFull, ix.nh, q);
+      if (nq <= 0) continue;
+      const int h2 = upper_slot(Q.heavy_rows, nq, row);
+      if (__ldg(Q.heavy_rows + h2) != row) continue;      // (list overflow: the main kernel cannot have skipped it)
+      const int ch2 = (e2 - b2 + kHeavyChunk - 1) / kHeavyChunk;
+      const int64_t g2 = __shfl_sync(kFull, ix.base, q) + __ldg(Q.heavy_rows + Q.heavy_cap + h2);
+      if (g2 + ch2 > p.max_chunks) continue;
+      const float s2 = p.scale == AGNN_SCALE_MEAN ? 1.f / (float)max(e2 - b2, 1) : 1.f;
+      float a2[V][E];
+      block_partials<V, E>(p.heavy_ws, g2, ch2, F, part, a2);
+      if (writer) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int e = 0; e < E; ++e) tot[v][e] = fmaf(a2[v][e], s2, tot[v][e]);
       }
-      for (int q = r + 1; q < p.n_rel; ++q) {           // ... then relation q's entries in list order
-        const agnn_rel_t& Q = p.rel[q];
-        if (!Q.heavy_rows) continue;
-        const int nq = (int)min((int64_t)__ldg(Q.n_heavy), Q.heavy_cap);
-        for (int h2 = 0; h2 < nq; ++h2) {
-          const int row2 = __ldg(Q.heavy_rows + h2);
-          const int b2 = __ldg(Q.rowptr + row2), e2 = __ldg(Q.rowptr + row2 + 1);
-          const int ch2 = (e2 - b2 + kHeavyChunk - 1) / kHeavyChunk;
-          if (row2 == row && g2 + ch2 <= p.max_chunks) {
-            const float s2 = p.scale == AGNN_SCALE_MEAN ? 1.f / (float)max(e2 - b2, 1) : 1.f;
-            float a2[V][E];
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-#pragma unroll
-              for (int e = 0; e < E; ++e) a2[v][e] = 0.f;
-            for (int c = 0; c < ch2; ++c) {
-              const float* wp = p.heavy_ws + (g2 + c) * F;
-#pragma unroll
-              for (int v = 0; v < V; ++v) {
-                const int cc = (v * 32 + lane) * E;
-                if (cc < F) {
-#pragma unroll
-                  for (int e = 0; e < E; ++e) a2[v][e] += wp[cc + e];
-                }
-              }
-            }
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-#pragma unroll
-              for (int e = 0; e < E; ++e) tot[v][e] = fmaf(a2[v][e], s2, tot[v][e]);
-          }
-          g2 += ch2;
-        }
-      }
+    }
+    if (writer) {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int cc = (v * 32 + lane) * E;
@@ -591,7 +681,7 @@ __global__ void __launch_bounds__(kThreads) gather_heavy_combine_kernel(const __
 template <typename T, int V>
 int launch_heavy(const GatherParams& p, cudaStream_t stream) {
   gather_heavy_partial_kernel<T, V><<<kNumSM * 4, kThreads, 0, stream>>>(p);
-  gather_heavy_combine_kernel<T, V><<<kNumSM, kThreads, 0, stream>>>(p);
+  gather_heavy_combine_kernel<T, V><<<kNumSM * 4, kThreads, 0, stream>>>(p);
   return check_launch("gather_reduce (heavy rows)");
 }
 
@@ -743,6 +833,11 @@ extern "C" int agnn_gather_reduce_amax(int32_t n_rows, int32_t n_feat, int dtype
   }
   cudaStream_t st = (cudaStream_t)stream;
   return dtype == AGNN_F32 ? dispatch<float>(p, st) : dispatch<__nv_bfloat16>(p, st);
+}
+
+extern "C" void agnn_heavy_params(int32_t* heavy_row, int32_t* heavy_chunk) {
+  if (heavy_row) *heavy_row = kHeavyRow;
+  if (heavy_chunk) *heavy_chunk = kHeavyChunk;
 }
 
 extern "C" size_t agnn_gather_heavy_workspace(int64_t total_edges, int64_t total_heavy_cap, int32_t n_feat) {

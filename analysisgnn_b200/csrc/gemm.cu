@@ -1082,7 +1082,7 @@ extern "C" int agnn_split_f16_shifted(const float* x, int64_t rows, int64_t cols
                                       void* hi, void* lo, int64_t ld_out, float dropout_p, const uint64_t* rng_state,
                                       uint32_t rng_stream, int32_t seq_len, int32_t shift, agnn_stream_t stream) {
   if (rows < 0 || cols < 0 || !amax || !hi || !lo) return fail(AGNN_ERR_ARG, "split_f16: bad arguments");
-  if (seq_len < 1 || shift <= -seq_len || shift >= seq_len) return fail(AGNN_ERR_ARG, "split_f16: bad sequence shift");
+  if (seq_len < 1) return fail(AGNN_ERR_ARG, "split_f16: sequence length must be positive");
   if (dropout_p < 0.f || dropout_p >= 1.f) return fail(AGNN_ERR_ARG, "split_f16: dropout needs 0 <= p < 1");
   if (rows == 0 || cols == 0) return AGNN_OK;
   if (cols % 4 || (ld_x * 4) % 16 || (ld_out * 2) % 16 || !aligned16(x) || !aligned16(hi) || !aligned16(lo))

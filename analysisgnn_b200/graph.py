@@ -60,7 +60,8 @@ class CSR:
     def __init__(self, rowptr, col, perm, seg: Segment, heavy=None, n_heavy=None, heavy_cap=0):
         self.rowptr, self.col, self.perm = rowptr, col, perm
         self.n_rows, self.n_cols, self.n_rel, self.n_edges = seg.n_rows, seg.n_cols, seg.n_rel, seg.n_edges
-        # rows with >= HEAVY_ROW entries, per relation: [n_rel, heavy_cap] row ids + [n_rel] counts (device)
+        # rows with >= HEAVY_ROW entries, per relation: [n_rel, 2 heavy_cap] (ascending row ids, then the exclusive
+        # prefix of their chunk counts) + [n_rel] counts (device)
         self.heavy, self.n_heavy, self.heavy_cap = heavy, n_heavy, heavy_cap
 
 
@@ -79,7 +80,8 @@ def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) 
     perm = torch.empty(max(edge_total, 1), dtype=torch.int32, device=device)
     status = torch.zeros(1, dtype=torch.int32, device=device)
     caps = [s.n_edges // _lib.HEAVY_ROW + 1 for s in segments]
-    heavy = torch.empty(sum(s.n_rel * c for s, c in zip(segments, caps)), dtype=torch.int32, device=device)
+    # per relation: [cap] heavy row ids (ascending) + [cap] exclusive prefix of their chunk counts
+    heavy = torch.empty(sum(s.n_rel * 2 * c for s, c in zip(segments, caps)), dtype=torch.int32, device=device)
     n_heavy = torch.empty(sum(s.n_rel for s in segments), dtype=torch.int32, device=device)
     stream = torch.cuda.current_stream(device).cuda_stream
     out, k_off, e_off, h_off, c_off = [], 0, 0, 0, 0
@@ -96,11 +98,12 @@ def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) 
             arr[i].heavy_off, arr[i].count_off, arr[i].heavy_cap = h_off, c_off, cap
             keys = s.n_rel * (s.n_rows + 1)
             out.append(CSR(rowptr[k_off:k_off + keys].view(s.n_rel, s.n_rows + 1), col[e_off:e_off + s.n_edges],
-                           perm[e_off:e_off + s.n_edges], s, heavy[h_off:h_off + s.n_rel * cap].view(s.n_rel, cap),
+                           perm[e_off:e_off + s.n_edges], s,
+                           heavy[h_off:h_off + s.n_rel * 2 * cap].view(s.n_rel, 2 * cap),
                            n_heavy[c_off:c_off + s.n_rel], cap))
             k_off += keys
             e_off += s.n_edges
-            h_off += s.n_rel * cap
+            h_off += s.n_rel * 2 * cap
             c_off += s.n_rel
         ws_bytes = lib.agnn_csr_build_workspace(len(chunk), arr)
         if ws_bytes == 0:
@@ -109,7 +112,7 @@ def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) 
         _lib.check(lib.agnn_csr_build(len(chunk), arr, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
                                       status.data_ptr(), heavy.data_ptr(), n_heavy.data_ptr(), ws.data_ptr(), ws_bytes,
                                       stream), "agnn_csr_build")
-        _lib.count_launches(8 if any(s.n_edges for s in chunk) else 4)
+        _lib.count_launches(10 if any(s.n_edges for s in chunk) else 6)
     if validate and int(status.item()) != 0:
         raise ValueError("edge_index contains node ids outside [0, num_nodes)")
     return out

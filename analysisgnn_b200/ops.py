@@ -63,7 +63,7 @@ def _pack(rels: Sequence[Rel], n_feat: int, dtype) -> "ctypes.Array":
         arr[i].flags = int(r.flags)
         if r.heavy_rows is not None and r.n_heavy is not None:
             arr[i].heavy_rows, arr[i].n_heavy = r.heavy_rows.data_ptr(), r.n_heavy.data_ptr()
-            arr[i].heavy_cap = int(r.heavy_rows.numel())
+            arr[i].heavy_cap = int(r.heavy_rows.numel()) // 2        # [cap] rows + [cap] chunk prefix
     return arr
 
 
@@ -158,7 +158,7 @@ def gather_reduce(rels: Sequence[Rel], out: torch.Tensor, n_feat: int, mean: boo
         if max(int(r.n_edges) for r in rels) >= _lib.HEAVY_ROW:
             ws_bytes = _lib.lib().agnn_gather_heavy_workspace(
                 sum(int(r.n_edges) for r in rels),
-                sum(int(r.heavy_rows.numel()) for r in rels if r.heavy_rows is not None), n_feat)
+                sum(int(r.heavy_rows.numel()) // 2 for r in rels if r.heavy_rows is not None), n_feat)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
 
     def run():

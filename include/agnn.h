@@ -76,15 +76,24 @@ typedef struct agnn_coo {
   int32_t reserved;
   int64_t rowptr_off; /* element offset of this segment's [n_rel*(n_rows+1)] block in rowptr */
   int64_t edge_off;   /* element offset of this segment's [n_edges] block in col / perm       */
-  int64_t heavy_off;  /* element offset of this segment's [n_rel][heavy_cap] block in `heavy`  */
+  int64_t heavy_off;  /* element offset of this segment's [n_rel][2 * heavy_cap] block in `heavy` */
   int64_t count_off;  /* element offset of this segment's [n_rel] counters in `n_heavy`        */
   int64_t heavy_cap;  /* capacity per relation; n_edges / AGNN_HEAVY_ROW + 1 always suffices   */
 } agnn_coo_t;
 
-/* Rows with at least AGNN_HEAVY_ROW entries are also listed per (segment, relation) in `heavy` (row ids, in no
- * particular order) with their count in `n_heavy`, when those arrays are given: agnn_gather_reduce splits such
- * rows across many warps instead of letting one warp walk them alone (hub nodes, Zipf-like degree tails). */
-#define AGNN_HEAVY_ROW 4096
+/* Rows with at least AGNN_HEAVY_ROW entries are also listed per (segment, relation) when `heavy` and `n_heavy` are
+ * given: the relation's block of 2 * heavy_cap ints holds the row ids in ascending order, then (second half) the
+ * exclusive prefix of their chunk counts ceil(deg / AGNN_HEAVY_CHUNK); `n_heavy` holds the count.
+ * agnn_gather_reduce splits such rows across many warps, one chunk each, instead of letting one warp walk them alone
+ * (hub nodes, Zipf-like degree tails); the prefix lets a warp find its chunk by binary search. */
+#ifndef AGNN_HEAVY_ROW
+#define AGNN_HEAVY_ROW 512
+#endif
+#ifndef AGNN_HEAVY_CHUNK
+#define AGNN_HEAVY_CHUNK 256
+#endif
+/* the two constants this library was built with */
+void agnn_heavy_params(int32_t* heavy_row, int32_t* heavy_chunk);
 
 /* bytes of scratch agnn_csr_build needs for these segments (host arithmetic only) */
 size_t agnn_csr_build_workspace(int n_seg, const agnn_coo_t* segs /* host */);
@@ -125,9 +134,10 @@ typedef struct agnn_rel {
   const int32_t* nbr_deg_rowptr; /* optional [n_src + 1]: neighbour weights     */
   int32_t out_col;
   int32_t flags;
-  const int32_t* heavy_rows; /* optional: rows with >= AGNN_HEAVY_ROW entries (agnn_csr_build) */
+  const int32_t* heavy_rows; /* optional: this relation's block of `heavy` (agnn_csr_build): [heavy_cap] ascending row
+                              * ids, then [heavy_cap] chunk prefix                                                   */
   const int32_t* n_heavy;    /* device counter that goes with heavy_rows                        */
-  int64_t heavy_cap;         /* entries heavy_rows can hold                                     */
+  int64_t heavy_cap;         /* rows the block can list (it is 2 * heavy_cap ints long)         */
 } agnn_rel_t;
 
 #define AGNN_REL_IDENTITY_IF_EMPTY 1
@@ -162,7 +172,6 @@ int agnn_gather_reduce_amax(int32_t n_rows, int32_t n_feat, int dtype, int scale
 /* Scratch for the heavy-row path of a launch whose relations hold `total_edges` edges and `total_heavy_cap` heavy
  * slots in all: (total_edges / AGNN_HEAVY_CHUNK + total_heavy_cap) partial rows of n_feat floats.  Relations are
  * only split when heavy_rows is set AND a workspace is given; otherwise every row is walked by its own warp. */
-#define AGNN_HEAVY_CHUNK 2048
 size_t agnn_gather_heavy_workspace(int64_t total_edges, int64_t total_heavy_cap, int32_t n_feat);
 
 /* Fused per-edge message + segmented reduction for the reference's alternative conv blocks

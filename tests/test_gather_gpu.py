@@ -196,7 +196,8 @@ def test_heavy_rows_are_split_across_warps(mean):
     plain formulation, deterministic from run to run, forward and backward."""
     rng = np.random.default_rng(3)
     n_rows, n_cols, f = 300, 5000, 64
-    row = np.concatenate([np.full(20000, 7), np.full(4096, 11), np.full(4095, 13), rng.integers(0, n_rows, 6000)])
+    hr = _lib.HEAVY_ROW
+    row = np.concatenate([np.full(20000, 7), np.full(hr, 11), np.full(hr - 80, 13), rng.integers(0, n_rows, 6000)])
     rng.shuffle(row)
     col = rng.integers(0, n_cols, len(row))
     ei = torch.as_tensor(np.stack((row, col)), dtype=torch.long)
@@ -209,7 +210,10 @@ def test_heavy_rows_are_split_across_warps(mean):
     csr = graph.TypedCSR(ei.to(DEV), None, n_rows, n_cols=n_cols)
     want_heavy = np.flatnonzero(np.bincount(row, minlength=n_rows) >= _lib.HEAVY_ROW).tolist()
     assert 7 in want_heavy and 11 in want_heavy
-    assert sorted(csr.fwd.heavy[0, :int(csr.fwd.n_heavy[0])].tolist()) == want_heavy
+    n_h, cap = int(csr.fwd.n_heavy[0]), csr.fwd.heavy_cap
+    assert csr.fwd.heavy[0, :n_h].tolist() == want_heavy                     # ascending row order
+    chunks = -(-np.bincount(row, minlength=n_rows)[want_heavy] // _lib.HEAVY_CHUNK)
+    assert csr.fwd.heavy[0, cap:cap + n_h].tolist() == (np.cumsum(chunks) - chunks).tolist()
     s2 = src.to(DEV).requires_grad_(True)
     got = ops.segment_mean_self(s2, base.to(DEV), csr) if mean else ops.segment_sum(s2, csr)
     got.backward(g.to(DEV))
@@ -255,3 +259,38 @@ def test_two_heavy_relations_on_one_row_are_summed_in_order(dtype, mean):
         outs.append(out)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert_close(outs[0].double(), want, 2 * FP32_REL if dtype == torch.float32 else BF16_REL, "sum over relations")
+
+
+@pytest.mark.parametrize("concat", [False, True])
+def test_many_heavy_rows_zipf_degrees(concat):
+    """A Zipf-like degree tail: a hundred rows of 500 .. 6000 entries per relation, three relations whose heavy rows
+    partly coincide.  Chunks are found through the lists' chunk prefix (binary search) -- same numbers as the plain
+    formulation, bit-identical from run to run."""
+    rng = np.random.default_rng(5)
+    n_rows, n_cols, f = 1500, 4000, 128
+    eis = []
+    for r in range(3):
+        hubs = rng.choice(n_rows, 100, replace=False)
+        degs = rng.integers(_lib.HEAVY_ROW - 12, 6000, len(hubs))
+        row = np.concatenate([np.repeat(hubs, degs), rng.integers(0, n_rows, 8000)])
+        rng.shuffle(row)
+        eis.append(torch.as_tensor(np.stack((row, rng.integers(0, n_cols, len(row)))), dtype=torch.long))
+    torch.manual_seed(4)
+    srcs = [torch.randn(n_cols, f) for _ in eis]
+    base = torch.randn(n_rows, f)
+    parts = []
+    for ei, s in zip(eis, srcs):
+        part = torch.zeros(n_rows, f, dtype=torch.float64).index_add_(0, ei[0], s.double()[ei[1]])
+        parts.append(part / torch.bincount(ei[0], minlength=n_rows).clamp(min=1).double().unsqueeze(1))
+    want = torch.cat(parts, dim=1) if concat else base.double() + sum(parts)
+    csrs = [graph.TypedCSR(ei.to(DEV), None, n_rows, n_cols=n_cols) for ei in eis]
+    assert all(int(c.fwd.n_heavy[0]) >= 90 for c in csrs)
+    rels = [ops.rel_of(c.fwd, 0, s.to(DEV), n_edges=ei.shape[1], out_col=(k * f if concat else 0))
+            for k, (c, s, ei) in enumerate(zip(csrs, srcs, eis))]
+    outs = []
+    for _ in range(2):
+        out = torch.empty((n_rows, (3 if concat else 1) * f), dtype=torch.float32, device=DEV)
+        ops.gather_reduce(rels, out, f, mean=True, concat=concat, self_add=None if concat else base.to(DEV))
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert_close(outs[0].double(), want, 2 * FP32_REL, "zipf tail")
