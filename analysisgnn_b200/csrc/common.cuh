@@ -41,6 +41,11 @@ struct Vec16<float> {
     float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  // the 16 bytes as loaded: what a kernel keeps in registers while many loads are in flight (see unpack)
+  __device__ static __forceinline__ uint4 load_raw_nc(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static __forceinline__ void unpack(const uint4& t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
   __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {   // coherent (data of this launch's peers)
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -58,6 +63,17 @@ struct Vec16<__nv_bfloat16> {
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // bf16 -> f32 is a 16-bit shift
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ uint4 load_raw_nc(const __nv_bfloat16* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+  }
+  __device__ static __forceinline__ void unpack(const uint4& t, float (&v)[8]) {   // 4 registers in flight, 8 at use
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
       v[2 * i] = __uint_as_float(w[i] << 16);
       v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }

@@ -214,7 +214,8 @@ int agnn_rowscale_sum(int32_t n_rows, int32_t n_feat, int dtype, int n_rel, cons
  *
  *   s_e   = (q_i,h . k_e,h) * pscale[r(e), h]          (pscale = p_rel / sqrt(D), device array [n_rel*heads])
  *   out_i,h = sum_e exp(s_e - max_i,h) v_e,h / (sum_e exp(s_e - max_i,h) + 1e-16)
- *   row_max / row_den [n_dst*heads] keep max_i,h and the denominator for the backward.
+ *   row_max / row_den [n_dst*heads] keep max_i,h (in log2 units: score * log2 e, the kernels' softmax runs in base 2)
+ *   and the denominator for the backward passes; opaque to callers.
  * k / v are the relation-specific keys / values of the SOURCE type, [n_src, heads*head_dim].
  */
 #define AGNN_HGT_MAX_HEADS 16
