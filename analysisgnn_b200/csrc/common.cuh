@@ -3,6 +3,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -22,6 +23,17 @@ int fail(int code, const char* fmt, ...);
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(AGNN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return AGNN_OK;
+}
+
+// AGNN_SYNC_CHECK=1 (debugging): wait for the stream after a launch and name the kernel that faulted.  Never set
+// inside a CUDA-graph capture.
+inline int sync_check(cudaStream_t st, const char* what) {
+  static const bool on = [] { const char* e = getenv("AGNN_SYNC_CHECK"); return e && *e && *e != '0'; }();
+  if (!on) return AGNN_OK;
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(AGNN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return AGNN_OK;
 }

@@ -14,6 +14,8 @@
 //             rows longer than 32 go to a list that `long_rows` sorts with a block-wide
 //             all-ascending bitonic network (shared memory up to 8192 entries, else in place).
 // HBM traffic per edge: 2 x 24 B COO reads + 4 B perm write/read + 8 B col/perm write.
+#include <climits>
+
 #include "common.cuh"
 
 namespace agnn {
@@ -23,6 +25,7 @@ constexpr int kThreads = 256;
 constexpr int kKeysPerTile = 4096;    // scan tile
 constexpr int kEdgesPerBlock = 1024;  // count / fill
 constexpr int kShortRow = 32;
+constexpr int kRankSort = 8;       // rows up to this long are ordered in registers (finalize)
 constexpr int kSmemSort = 8192;
 
 struct SegTable {
@@ -242,31 +245,46 @@ __global__ void __launch_bounds__(kHeavyThreads) heavy_list_kernel(const __grid_
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const __grid_constant__ SegTable tab,
                                                              const int32_t* rowptr, int32_t* col, int32_t* perm,
                                                              int32_t* long_count, int64_t* long_list) {
-  const int s = find_seg(tab.key_tile_start, tab.n_seg, blockIdx.x);
+  // one key per thread (kKeysPerTile / kThreads blocks per scan tile): the two dependent round trips of a key --
+  // extent, then the row's slots -- are the whole cost, so the more keys in flight the better
+  constexpr int kSub = kKeysPerTile / kThreads;
+  const int tile = blockIdx.x / kSub;
+  const int s = find_seg(tab.key_tile_start, tab.n_seg, tile);
   const agnn_coo_t& g = tab.seg[s];
-  const int64_t base = (int64_t)(blockIdx.x - tab.key_tile_start[s]) * kKeysPerTile;
-  const int64_t n = seg_keys(g);
-  for (int i = threadIdx.x; i < kKeysPerTile; i += kThreads) {
-    const int64_t k = base + i;
-    if (k >= n || (k % (g.n_rows + 1)) == g.n_rows) continue;
-    const int beg = rowptr[g.rowptr_off + k], end = rowptr[g.rowptr_off + k + 1];
-    const int deg = end - beg;
-    if (deg == 0) continue;
-    if (deg > kShortRow) {
-      const int slot = atomicAdd(long_count, 1);
-      long_list[slot] = ((int64_t)s << 40) | k;
-      continue;
+  const int64_t k = (int64_t)(tile - tab.key_tile_start[s]) * kKeysPerTile + (blockIdx.x % kSub) * kThreads + threadIdx.x;
+  if (k >= seg_keys(g) || (k % (g.n_rows + 1)) == g.n_rows) return;
+  const int beg = rowptr[g.rowptr_off + k], end = rowptr[g.rowptr_off + k + 1];
+  const int deg = end - beg;
+  if (deg <= 1) return;
+  if (deg > kShortRow) {
+    const int slot = atomicAdd(long_count, 1);
+    long_list[slot] = ((int64_t)s << 40) | k;
+    return;
+  }
+  int32_t* pp = perm + g.edge_off + beg;
+  if (deg <= kRankSort) {
+    // the usual row of a score graph: all slots loaded at once, every slot's rank = how many are smaller (edge ids are
+    // distinct), one store each -- no dependent global accesses
+    int v[kRankSort];
+#pragma unroll
+    for (int a = 0; a < kRankSort; ++a) v[a] = a < deg ? pp[a] : INT_MAX;
+#pragma unroll
+    for (int a = 0; a < kRankSort; ++a) {
+      int rank = 0;
+#pragma unroll
+      for (int b = 0; b < kRankSort; ++b) rank += (v[b] < v[a]) ? 1 : 0;
+      if (a < deg) pp[rank] = v[a];
     }
-    int32_t* pp = perm + g.edge_off + beg;
-    for (int a = 1; a < deg; ++a) {  // insertion sort: rows arrive almost ordered
-      const int v = pp[a];
-      int b = a - 1;
-      while (b >= 0 && pp[b] > v) {
-        pp[b + 1] = pp[b];
-        --b;
-      }
-      pp[b + 1] = v;
+    return;
+  }
+  for (int a = 1; a < deg; ++a) {  // insertion sort: rows arrive almost ordered
+    const int v = pp[a];
+    int b = a - 1;
+    while (b >= 0 && pp[b] > v) {
+      pp[b + 1] = pp[b];
+      --b;
     }
+    pp[b + 1] = v;
   }
 }
 
@@ -368,7 +386,8 @@ int make_tables(int n_seg, const agnn_coo_t* segs, SegTable& tab, Layout& lay, b
     if (g.rowptr_off + keys > max_key_end) max_key_end = g.rowptr_off + keys;
     edges += g.n_edges;
   }
-  if (key_tiles >= (1ll << 31) || edge_blks >= (1ll << 31)) return fail(AGNN_ERR_UNSUPPORTED, "csr_build: too large");
+  // (finalize launches kKeysPerTile / kThreads = 16 blocks per key tile)
+  if (key_tiles >= (1ll << 27) || edge_blks >= (1ll << 31)) return fail(AGNN_ERR_UNSUPPORTED, "csr_build: too large");
   tab.key_tile_start[n_seg] = (int)key_tiles;
   tab.edge_blk_start[n_seg] = (int)edge_blks;
   lay.cursor_ints = max_key_end;
@@ -414,22 +433,33 @@ extern "C" int agnn_csr_build(int n_seg, const agnn_coo_t* segs, int32_t* rowptr
   const int key_tiles = tab.key_tile_start[n_seg], edge_blks = tab.edge_blk_start[n_seg];
 
   if (cudaMemsetAsync(long_count, 0, 4, stream) != cudaSuccess) return check_launch("csr_build memset");
+#define AGNN_STEP(name) if ((rc = sync_check(stream, "csr_build: " name)) != AGNN_OK) return rc
   zero_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, cursor);
+  AGNN_STEP("zero");
   if (edge_blks > 0) edge_kernel<false><<<edge_blks, kThreads, 0, stream>>>(tab, rowptr, cursor, perm, status);
+  AGNN_STEP("count");
   scan_tile_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, tile_sums);
   scan_sums_kernel<<<n_seg, kThreads, 0, stream>>>(tab, tile_sums);
   scan_add_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, tile_sums);
+  AGNN_STEP("scan");
   if (heavy && n_heavy) {
     int n_blocks = 0;
     for (int s = 0; s < n_seg; ++s) n_blocks += segs[s].n_rel;
     heavy_list_kernel<<<n_blocks, kHeavyThreads, 0, stream>>>(tab, rowptr, heavy, n_heavy);
+    AGNN_STEP("heavy lists");
   }
   if (edge_blks > 0) {
     if (!col || !perm) return fail(AGNN_ERR_ARG, "csr_build: null col/perm with edges present");
     edge_kernel<true><<<edge_blks, kThreads, 0, stream>>>(tab, rowptr, cursor, perm, status);
-    finalize_kernel<<<key_tiles, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list);
+    AGNN_STEP("fill");
+    finalize_kernel<<<key_tiles * (kKeysPerTile / kThreads), kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count,
+                                                                                    long_list);
+    AGNN_STEP("finalize");
     gather_col_kernel<<<edge_blks, kThreads, 0, stream>>>(tab, col, perm);
+    AGNN_STEP("gather col");
     long_rows_kernel<<<kNumSM * 2, kThreads, 0, stream>>>(tab, rowptr, col, perm, long_count, long_list);
+    AGNN_STEP("long rows");
   }
+#undef AGNN_STEP
   return check_launch("csr_build");
 }
