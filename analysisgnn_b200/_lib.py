@@ -236,7 +236,11 @@ _PROTOTYPES = {
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnn_gru_bwd_amax": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agnn_gru_bwd_stepwise": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
+
+GRU_RESIDENT, GRU_STEPWISE = 1, 2      # agnn_gru_supported (include/agnn.h)
 
 _lib = None
 _launches = 0

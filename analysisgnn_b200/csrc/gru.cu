@@ -42,6 +42,10 @@ struct GruParams {
   float* dgi[2];       // [B, T, 3H]
   float* dgh[2];       // [B, T, 3H]
   float* amax[2];      // optional per direction: max |dgi| (>= max |dgh|: dgh = dgi with the n gate times r, |r| <= 1)
+  // wide hidden sizes (one launch per time step, see below)
+  int hidden;
+  const float* w_hh_t[2];  // [H, 3H] = W_hh^T (backward)
+  float* keep;             // [n_dir, B, H]: z_t * dh_t carried to the next backward step
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -293,11 +297,359 @@ __global__ void __launch_bounds__(3 * H, 1) gru_bwd_kernel(const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Wide hidden sizes (multiples of 64 above 128: MetricalConvLayer.seq runs nn.GRU(512, 512) in config 4,
+// analysisgnn/models/core/gnn.py:498).  W_hh no longer fits the registers of one SM (3 MB at H = 512) and 64
+// sequences cannot occupy 148 SMs by sequence alone, so a time step becomes ONE launch over (unit block, sequence
+// block, direction) tiles and the step order is the launch order: no grid barrier, no spinning, and the whole time
+// loop is part of the captured step graph.  Every CTA computes a small product
+//     C[TS sequences, TN columns] = A[TS, K] . B[TN, K]^T
+// with both operands K-major fp32, streamed from L2 through a cp.async ring in 64-float chunks:
+//   forward   A = h_{t-1} (rows of `out`),               B = the r, z, n rows of 8 hidden units of W_hh, K = H;
+//             epilogue = the gates and new state of those 8 units;
+//   backward  A = dgh of the step processed before,      B = 16 rows of W_hh^T,                        K = 3H;
+//             epilogue = dh, the gate derivatives of those 16 units and the carried z * dh.
+// The product runs on the tensor cores at fp32 accuracy: mma.sync m16n8k8 TF32 with every operand split in registers
+// into hi = rna(x), lo = rna(x - hi) and D += A_lo B_hi + A_hi B_lo + A_hi B_hi (the dropped lo x lo term is 2^-22
+// relative).  The tensor core adds into its fp32 accumulator with truncation, so a chain ends after every chunk
+// (12 / 6 MMAs) and the chains are summed with ordinary fp32 adds -- the same rule as the TMEM chains of gemm.cu.
+// (A first version did this product with packed FFMA2 on 4 x 6 register tiles: shared-memory bound at 18 us per
+// step -- measured: LDS.128 costs 4.2 cycles per warp whatever the broadcast pattern, FFMA2 issues at half the FFMA
+// rate -- against 60 us per step for the library RNN; fragments read with conflict-free LDS.32 need a sixth of the
+// shared-memory cycles.)  A warp owns one 8-wide k step of every chunk and the whole tile; the 8 partial tiles meet
+// in shared memory, then thread (sequence, unit pair) finishes the epilogue.
+// Bytes a step pulls from L2 (H = 512, 64 sequences, 2 directions): forward 128 CTAs x (128 KB of h + 48 KB of W_hh),
+// backward 128 x (192 KB of dgh + 96 KB of W_hh^T).
+namespace wide {
+constexpr int kThreads = 256;
+constexpr int KC = 64;            // floats of K per pipeline stage
+constexpr int kStages = 4;
+constexpr int LD = KC + 4;        // row stride = 4 banks: the 8 rows x 4 columns a fragment load touches cover all 32
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(x - __uint_as_float(hi)));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct Operands {
+  const float* a;       // tile row 0 of A
+  int64_t a_stride;     // floats between A rows
+  int a_rows;           // valid rows (the rest read as zero)
+  const float* b;       // B tile row l lives at b + (l / BG) * b_group_stride + (l % BG) * b_row_stride
+  int64_t b_group_stride, b_row_stride;
+  int k;                // multiple of KC
+};
+
+constexpr int KQ = kThreads / 32;  // every warp owns one 8-wide k step of a chunk (KC / 8 == KQ) and the WHOLE tile
+
+template <int TS, int TN>
+constexpr size_t smem_bytes() {
+  constexpr size_t ring = (size_t)kStages * (TS + TN) * LD, part = (size_t)KQ * TS * (TN + 1);
+  return (ring > part ? ring : part) * sizeof(float);
+}
+
+// c_s[q][row][col] (row stride TN + 1, aliasing the ring) = the partial product of warp q's k steps; the caller sums
+// over q after the barrier this function ends with.  Warp = k slice rather than row slab: an operand element is then
+// split into hi / lo by exactly one warp (with row slabs the B fragments were split once per slab: the loop was
+// issue bound, 5.4 instructions per MMA; now 3.4).
+template <int TS, int TN, int BG>
+__device__ __forceinline__ void tile_mma(float* smem, const Operands& op) {
+  constexpr int MT = TS / 16, NT = TN / 8;
+  static_assert(KC / 8 == KQ, "one k step per warp and chunk");
+  constexpr int NA = TS * (KC / 4) / kThreads, NB = (TN * (KC / 4) + kThreads - 1) / kThreads;
+  static_assert(TS * (KC / 4) % kThreads == 0, "A copies per thread");
+  float* a_s = smem;
+  float* b_s = smem + kStages * TS * LD;
+  const int tid = threadIdx.x, lane = tid & 31, kq = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // this thread's copies of a chunk: fixed (row, 16-byte piece) pairs, the source advances by KC per chunk
+  const float* a_src[NA];
+  const float* b_src[NB];
+  uint32_t a_dst[NA], b_dst[NB];
+  bool a_ok[NA], b_ok[NB];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    const int e = tid + i * kThreads, r = e / (KC / 4), f = e % (KC / 4);
+    a_ok[i] = r < op.a_rows;
+    a_src[i] = op.a + (a_ok[i] ? r * op.a_stride + 4 * f : 0);
+    a_dst[i] = (uint32_t)__cvta_generic_to_shared(a_s + r * LD + 4 * f);
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int e = tid + i * kThreads, l = e / (KC / 4), f = e % (KC / 4);
+    b_ok[i] = l < TN;
+    b_src[i] = op.b + (b_ok[i] ? (l / BG) * op.b_group_stride + (l % BG) * op.b_row_stride + 4 * f : 0);
+    b_dst[i] = (uint32_t)__cvta_generic_to_shared(b_s + l * LD + 4 * f);
+  }
+  auto issue = [&](int chunk, int slot) {
+    const int k0 = chunk * KC;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int n = a_ok[i] ? 16 : 0;            // 0 source bytes: the 16 destination bytes are zero-filled
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_dst[i] + slot * (TS * LD * 4)),
+                   "l"(a_src[i] + (a_ok[i] ? k0 : 0)), "r"(n)
+                   : "memory");
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (b_ok[i])
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(b_dst[i] + slot * (TN * LD * 4)),
+                     "l"(b_src[i] + k0)
+                     : "memory");
+  };
+  float tot[MT][NT][4], acc[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tot[mt][nt][i] = acc[mt][nt][i] = 0.f;
+  const int n_chunks = op.k / KC;
+#pragma unroll
+  for (int q = 0; q < kStages - 1; ++q) {
+    if (q < n_chunks) issue(q, q);
+    cp_async_commit();
+  }
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    cp_async_wait<kStages - 2>();     // chunk kc has landed (own copies); the barrier publishes everyone's and
+    __syncthreads();                  // retires the slot refilled below (read in iteration kc - 1)
+    const int nxt = kc + kStages - 1;
+    if (nxt < n_chunks) issue(nxt, nxt % kStages);
+    cp_async_commit();
+    const int slot = kc % kStages;
+    const float* a_t = a_s + (slot * TS + g) * LD + kq * 8 + t;
+    const float* b_t = b_s + (slot * TN + g) * LD + kq * 8 + t;
+    uint32_t bh[NT][2], bl[NT][2];    // B fragments: (k = t, n = g) (k = t + 4, n = g)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      split_tf32(b_t[nt * 8 * LD], bh[nt][0], bl[nt][0]);
+      split_tf32(b_t[nt * 8 * LD + 4], bh[nt][1], bl[nt][1]);
+    }
+    uint32_t ah[MT][4], al[MT][4];    // A fragments: (g, t) (g + 8, t) (g, t + 4) (g + 8, t + 4)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      split_tf32(a_t[mt * 16 * LD], ah[mt][0], al[mt][0]);
+      split_tf32(a_t[(mt * 16 + 8) * LD], ah[mt][1], al[mt][1]);
+      split_tf32(a_t[mt * 16 * LD + 4], ah[mt][2], al[mt][2]);
+      split_tf32(a_t[(mt * 16 + 8) * LD + 4], ah[mt][3], al[mt][3]);
+    }
+    // term-major order: consecutive MMAs go to different accumulators (MT * NT apart on the same one) -- issued
+    // accumulator by accumulator, each MMA waited for the one before it
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
+    if ((kc & 3) == 3 || kc == n_chunks - 1) {   // end the accumulation chain (12 MMAs): fp32 adds round to nearest
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            tot[mt][nt][i] += acc[mt][nt][i];
+            acc[mt][nt][i] = 0.f;
+          }
+    }
+  }
+  __syncthreads();                    // every warp is done with the ring: the partial tiles take its place
+  // C fragment: (g, 2t) (g, 2t + 1) (g + 8, 2t) (g + 8, 2t + 1)
+  float* c_w = smem + ((size_t)kq * TS + g) * (TN + 1) + 2 * t;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      c_w[(mt * 16) * (TN + 1) + nt * 8] = tot[mt][nt][0];
+      c_w[(mt * 16) * (TN + 1) + nt * 8 + 1] = tot[mt][nt][1];
+      c_w[(mt * 16 + 8) * (TN + 1) + nt * 8] = tot[mt][nt][2];
+      c_w[(mt * 16 + 8) * (TN + 1) + nt * 8 + 1] = tot[mt][nt][3];
+    }
+  __syncthreads();
+}
+
+constexpr int FTS = 64, FTN = 24;   // forward tile: 64 sequences x (3 gates x 8 units)
+constexpr int BTS = 32, BTN = 16;   // backward tile: 32 sequences x 16 units
+
+__global__ void __launch_bounds__(kThreads) gru_wide_fwd_kernel(const __grid_constant__ GruParams p, int step) {
+  extern __shared__ __align__(16) float smem[];
+  const float* c_s = smem;
+  const int H = p.hidden, T = p.steps;
+  const int dir = blockIdx.z, u0 = blockIdx.x * 8, row0 = blockIdx.y * FTS;
+  const int t = dir == 0 ? step : T - 1 - step;
+  const int tp = dir == 0 ? t - 1 : t + 1;       // time of h_{prev}
+  const int bl = threadIdx.x >> 2, nq = threadIdx.x & 3;     // epilogue: sequence bl of the tile, units 2 nq, 2 nq + 1
+  const int b = row0 + bl;
+  const int64_t row = (int64_t)b * T + t;
+  // what the epilogue needs from global memory, requested before the product
+  float gi[3][2], bias[3][2], hp[2];
+  if (b < p.batch) {
+#pragma unroll
+    for (int gt = 0; gt < 3; ++gt) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(p.gi[dir] + row * (3 * H) + gt * H + u0 + 2 * nq));
+      const float2 w = __ldg(reinterpret_cast<const float2*>(p.b_hh[dir] + gt * H + u0 + 2 * nq));
+      gi[gt][0] = v.x; gi[gt][1] = v.y; bias[gt][0] = w.x; bias[gt][1] = w.y;
+    }
+    hp[0] = hp[1] = 0.f;
+    if (step > 0) {
+      const float2 v = *reinterpret_cast<const float2*>(p.out + ((int64_t)b * T + tp) * p.ld_out + dir * H + u0 + 2 * nq);
+      hp[0] = v.x; hp[1] = v.y;
+    }
+  }
+  if (step > 0) {                                // h_0 = 0: the first step's product vanishes
+    Operands op;
+    op.a = p.out + ((int64_t)row0 * T + tp) * p.ld_out + dir * H;
+    op.a_stride = (int64_t)T * p.ld_out;
+    op.a_rows = p.batch - row0;
+    op.b = p.w_hh[dir] + (int64_t)u0 * H;        // tile row l = gate * 8 + unit
+    op.b_group_stride = (int64_t)H * H;          // gate block of W_hh
+    op.b_row_stride = H;
+    op.k = H;
+    tile_mma<FTS, FTN, 8>(smem, op);
+  }
+  if (b >= p.batch) return;
+  float gh[3][2];
+#pragma unroll
+  for (int gt = 0; gt < 3; ++gt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v = 0.f;
+      if (step > 0) {
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) v += c_s[((size_t)q * FTS + bl) * (FTN + 1) + gt * 8 + 2 * nq + j];
+      }
+      gh[gt][j] = v + bias[gt][j];
+    }
+  float hn[2], rr[2], zz[2], nn[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    rr[j] = sigmoidf_(gi[0][j] + gh[0][j]);
+    zz[j] = sigmoidf_(gi[1][j] + gh[1][j]);
+    nn[j] = tanhf(gi[2][j] + rr[j] * gh[2][j]);
+    hn[j] = (1.f - zz[j]) * nn[j] + zz[j] * hp[j];
+  }
+  const int u = u0 + 2 * nq;
+  *reinterpret_cast<float2*>(p.out + row * p.ld_out + dir * H + u) = make_float2(hn[0], hn[1]);
+  if (p.gates[dir]) {
+    float* gt = p.gates[dir] + row * (4 * H) + u;
+    *reinterpret_cast<float2*>(gt) = make_float2(rr[0], rr[1]);
+    *reinterpret_cast<float2*>(gt + H) = make_float2(zz[0], zz[1]);
+    *reinterpret_cast<float2*>(gt + 2 * H) = make_float2(nn[0], nn[1]);
+    *reinterpret_cast<float2*>(gt + 3 * H) = make_float2(gh[2][0], gh[2][1]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) gru_wide_bwd_kernel(const __grid_constant__ GruParams p, int step) {
+  extern __shared__ __align__(16) float smem[];
+  const float* c_s = smem;
+  const int H = p.hidden, T = p.steps;
+  const int dir = blockIdx.z, u0 = blockIdx.x * BTN, row0 = blockIdx.y * BTS;
+  const int t = dir == 0 ? T - 1 - step : step;  // reverse of the forward's processing order
+  const int tn = dir == 0 ? t + 1 : t - 1;       // the time the previous backward step processed
+  const int tp = dir == 0 ? t - 1 : t + 1;       // time of h_{prev} in the forward recurrence
+  const int bl = threadIdx.x >> 3, nq = threadIdx.x & 7;     // epilogue: sequence bl of the tile, units 2 nq, 2 nq + 1
+  const int b = row0 + bl, u = u0 + 2 * nq;
+  const int64_t row = (int64_t)b * T + t;
+  float gd[2], r[2], z[2], n[2], ghn[2], hp[2], kp[2];
+  float* keep = p.keep + ((int64_t)dir * p.batch + b) * H + u;
+  if (b < p.batch) {
+    auto ld2 = [](const float* q, float (&o)[2]) { const float2 v = *reinterpret_cast<const float2*>(q); o[0] = v.x; o[1] = v.y; };
+    const float* gt = p.gates[dir] + row * (4 * H) + u;
+    ld2(p.dout + row * p.ld_out + dir * H + u, gd);
+    ld2(gt, r); ld2(gt + H, z); ld2(gt + 2 * H, n); ld2(gt + 3 * H, ghn);
+    hp[0] = hp[1] = kp[0] = kp[1] = 0.f;
+    if (tp >= 0 && tp < T) ld2(p.out + ((int64_t)b * T + tp) * p.ld_out + dir * H + u, hp);
+    if (step > 0) ld2(keep, kp);
+  }
+  if (step > 0) {                                // dh_prev[b, u] = sum_i dgh[b, i] W_hh[i, u]
+    Operands op;
+    op.a = p.dgh[dir] + ((int64_t)row0 * T + tn) * (3 * H);
+    op.a_stride = (int64_t)T * 3 * H;
+    op.a_rows = p.batch - row0;
+    op.b = p.w_hh_t[dir] + (int64_t)u0 * 3 * H;
+    op.b_group_stride = 0;
+    op.b_row_stride = 3 * H;
+    op.k = 3 * H;
+    tile_mma<BTS, BTN, BTN>(smem, op);
+  }
+  float gmax = 0.f;
+  if (b < p.batch) {
+    float dr[2], dz[2], dn[2], dgn[2], kn[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v = 0.f;
+      if (step > 0) {
+#pragma unroll
+        for (int q = 0; q < KQ; ++q) v += c_s[((size_t)q * BTS + bl) * (BTN + 1) + 2 * nq + j];
+      }
+      const float dh = step > 0 ? gd[j] + (kp[j] + v) : gd[j];
+      dn[j] = dh * (1.f - z[j]) * (1.f - n[j] * n[j]);
+      dz[j] = dh * (hp[j] - n[j]) * z[j] * (1.f - z[j]);
+      dr[j] = dn[j] * ghn[j] * r[j] * (1.f - r[j]);
+      dgn[j] = dn[j] * r[j];
+      kn[j] = dh * z[j];
+      gmax = fmaxf(gmax, fmaxf(fabsf(dr[j]), fmaxf(fabsf(dz[j]), fabsf(dn[j]))));
+    }
+    *reinterpret_cast<float2*>(keep) = make_float2(kn[0], kn[1]);
+    float* gi_row = p.dgi[dir] + row * (3 * H) + u;
+    float* gh_row = p.dgh[dir] + row * (3 * H) + u;
+    *reinterpret_cast<float2*>(gi_row) = make_float2(dr[0], dr[1]);
+    *reinterpret_cast<float2*>(gi_row + H) = make_float2(dz[0], dz[1]);
+    *reinterpret_cast<float2*>(gi_row + 2 * H) = make_float2(dn[0], dn[1]);
+    *reinterpret_cast<float2*>(gh_row) = make_float2(dr[0], dr[1]);
+    *reinterpret_cast<float2*>(gh_row + H) = make_float2(dz[0], dz[1]);
+    *reinterpret_cast<float2*>(gh_row + 2 * H) = make_float2(dgn[0], dgn[1]);
+  }
+  if (p.amax[dir]) {
+    uint32_t m = __float_as_uint(gmax);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(p.amax[dir]), m);
+  }
+}
+
+inline bool supported(int hidden) { return hidden > 128 && hidden <= 2048 && hidden % 64 == 0; }
+
+int launch_fwd(const GruParams& p, cudaStream_t st) {
+  constexpr size_t kSmem = smem_bytes<FTS, FTN>();
+  static const cudaError_t attr =
+      cudaFuncSetAttribute(gru_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+  if (attr != cudaSuccess) return fail(AGNN_ERR_CUDA, "gru_fwd: shared-memory attribute: %s", cudaGetErrorString(attr));
+  dim3 grid((unsigned)(p.hidden / 8), (unsigned)ceil_div(p.batch, FTS), (unsigned)p.n_dir);
+  for (int step = 0; step < p.steps; ++step) gru_wide_fwd_kernel<<<grid, kThreads, kSmem, st>>>(p, step);
+  return check_launch("gru_wide_fwd");
+}
+
+int launch_bwd(const GruParams& p, cudaStream_t st) {
+  constexpr size_t kSmem = smem_bytes<BTS, BTN>();
+  static const cudaError_t attr =
+      cudaFuncSetAttribute(gru_wide_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+  if (attr != cudaSuccess) return fail(AGNN_ERR_CUDA, "gru_bwd: shared-memory attribute: %s", cudaGetErrorString(attr));
+  dim3 grid((unsigned)(p.hidden / BTN), (unsigned)ceil_div(p.batch, BTS), (unsigned)p.n_dir);
+  for (int step = 0; step < p.steps; ++step) gru_wide_bwd_kernel<<<grid, kThreads, kSmem, st>>>(p, step);
+  return check_launch("gru_wide_bwd");
+}
+}  // namespace wide
+
 int check_gru(const char* what, int batch, int steps, int hidden, int n_dir) {
   if (batch < 0 || steps < 0 || (n_dir != 1 && n_dir != 2))
     return fail(AGNN_ERR_ARG, "%s: bad sizes (batch=%d steps=%d n_dir=%d)", what, batch, steps, n_dir);
-  if (hidden != 32 && hidden != 64 && hidden != 128)
-    return fail(AGNN_ERR_UNSUPPORTED, "%s: hidden size %d (register-resident W_hh supports 32, 64, 128)", what, hidden);
+  if (hidden != 32 && hidden != 64 && hidden != 128 && !wide::supported(hidden))
+    return fail(AGNN_ERR_UNSUPPORTED, "%s: hidden size %d (register-resident W_hh: 32, 64, 128; per-step launches: "
+                "multiples of 64 up to 2048)", what, hidden);
   return AGNN_OK;
 }
 
@@ -319,7 +671,10 @@ int launch_bwd(const GruParams& p, cudaStream_t st) {
 
 using namespace agnn;
 
-extern "C" int agnn_gru_supported(int hidden) { return hidden == 32 || hidden == 64 || hidden == 128; }
+extern "C" int agnn_gru_supported(int hidden) {
+  if (hidden == 32 || hidden == 64 || hidden == 128) return AGNN_GRU_RESIDENT;
+  return wide::supported(hidden) ? AGNN_GRU_STEPWISE : 0;
+}
 
 extern "C" int agnn_gru_fwd(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* gi,
                             const float* const* w_hh, const float* const* b_hh, float* out, float* const* gates,
@@ -337,6 +692,13 @@ extern "C" int agnn_gru_fwd(int32_t batch, int32_t steps, int32_t hidden, int32_
     p.gates[d] = gates ? gates[d] : nullptr;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  p.hidden = hidden;
+  if (wide::supported(hidden)) {
+    for (int d = 0; d < n_dir; ++d)
+      if (!aligned16(gi[d]) || !aligned16(out) || !aligned16(b_hh[d]))
+        return fail(AGNN_ERR_ARG, "gru_fwd: unaligned operand");
+    return wide::launch_fwd(p, st);
+  }
   if (hidden == 128) return launch_fwd<128>(p, st);
   if (hidden == 64) return launch_fwd<64>(p, st);
   return launch_fwd<32>(p, st);
@@ -353,6 +715,8 @@ extern "C" int agnn_gru_bwd_amax(int32_t batch, int32_t steps, int32_t hidden, i
                                  float* const* dgh, float* const* amax, agnn_stream_t stream) {
   int rc = check_gru("gru_bwd", batch, steps, hidden, n_dir);
   if (rc) return rc;
+  if (wide::supported(hidden))
+    return fail(AGNN_ERR_UNSUPPORTED, "gru_bwd: hidden size %d takes agnn_gru_bwd_stepwise (W_hh^T + carry buffer)", hidden);
   if (!w_hh || !out || !gates || !dout || !dgi || !dgh) return fail(AGNN_ERR_ARG, "gru_bwd: null pointer");
   if (batch == 0 || steps == 0) return AGNN_OK;
   GruParams p;
@@ -368,4 +732,29 @@ extern "C" int agnn_gru_bwd_amax(int32_t batch, int32_t steps, int32_t hidden, i
   if (hidden == 128) return launch_bwd<128>(p, st);
   if (hidden == 64) return launch_bwd<64>(p, st);
   return launch_bwd<32>(p, st);
+}
+
+extern "C" int agnn_gru_bwd_stepwise(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir,
+                                     const float* const* w_hh_t, const float* out, const float* const* gates,
+                                     const float* dout, float* const* dgi, float* const* dgh, float* const* amax,
+                                     float* carry, agnn_stream_t stream) {
+  int rc = check_gru("gru_bwd_stepwise", batch, steps, hidden, n_dir);
+  if (rc) return rc;
+  if (!wide::supported(hidden))
+    return fail(AGNN_ERR_UNSUPPORTED, "gru_bwd_stepwise: hidden size %d takes agnn_gru_bwd", hidden);
+  if (!w_hh_t || !out || !gates || !dout || !dgi || !dgh || !carry) return fail(AGNN_ERR_ARG, "gru_bwd_stepwise: null pointer");
+  if (batch == 0 || steps == 0) return AGNN_OK;
+  GruParams p;
+  memset(&p, 0, sizeof(p));
+  p.batch = batch; p.steps = steps; p.n_dir = n_dir; p.hidden = hidden; p.out = const_cast<float*>(out);
+  p.ld_out = (int64_t)n_dir * hidden; p.dout = dout; p.keep = carry;
+  if (!aligned16(out) || !aligned16(dout) || !aligned16(carry)) return fail(AGNN_ERR_ARG, "gru_bwd_stepwise: unaligned operand");
+  for (int d = 0; d < n_dir; ++d) {
+    if (!w_hh_t[d] || !gates[d] || !dgi[d] || !dgh[d] || !aligned16(w_hh_t[d]) || !aligned16(dgh[d]) ||
+        !aligned16(dgi[d]) || !aligned16(gates[d]))
+      return fail(AGNN_ERR_ARG, "gru_bwd_stepwise: null / unaligned operand");
+    p.w_hh_t[d] = w_hh_t[d]; p.gates[d] = const_cast<float*>(gates[d]); p.dgi[d] = dgi[d]; p.dgh[d] = dgh[d];
+    p.amax[d] = amax ? amax[d] : nullptr;
+  }
+  return wide::launch_bwd(p, (cudaStream_t)stream);
 }

@@ -85,9 +85,10 @@ class MLP(nn.Sequential):
 
 
 class GRU(nn.GRU):
-    """``nn.GRU`` (same parameters / ``state_dict``): batch-first fp32 CUDA inputs with hidden size 32, 64 or
-    128 run on libagnn (tensor-core GEMMs for every projection + agnn_gru_fwd / _bwd for the recurrence);
-    anything else (other sizes, given ``h0``, packed sequences, projections) goes to cuDNN."""
+    """``nn.GRU`` (same parameters / ``state_dict``): batch-first fp32 CUDA inputs run on libagnn (tensor-core GEMMs
+    for every projection + agnn_gru_fwd / _bwd for the recurrence): hidden size 32, 64 or 128 with W_hh resident in
+    registers, multiples of 64 from 192 to 2048 (MetricalConvLayer's 512) as one launch per time step.  Anything else
+    (other sizes, given ``h0``, packed sequences, projections) goes to cuDNN and is counted as a library route."""
 
     def forward(self, x, hx=None):
         if (hx is not None or not isinstance(x, torch.Tensor) or not self.batch_first or self.proj_size != 0

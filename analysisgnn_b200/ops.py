@@ -1185,7 +1185,7 @@ class _GRULayer(torch.autograd.Function):
         _lib.check(_lib.lib().agnn_gru_fwd(b, t, h, n_dir, _lib.ptr_array(gis), _lib.ptr_array(whh),
                                            _lib.ptr_array(bhh), out.data_ptr(), _lib.ptr_array(gates), _stream(x)),
                    "agnn_gru_fwd")
-        _lib.count_launches(1)
+        _lib.count_launches(t if _lib.lib().agnn_gru_supported(h) == _lib.GRU_STEPWISE else 1)
         ctx.save_for_backward(*linalg.pack(xs), out, *gates, *[params[4 * d] for d in range(n_dir)], *whh)
         ctx.n_dir, ctx.dims = n_dir, (b, t, c, h)
         ctx.x_amax = getattr(xs, "amax", None)
@@ -1205,11 +1205,22 @@ class _GRULayer(torch.autograd.Function):
         dgi = [torch.empty((b * t, 3 * h), dtype=out.dtype, device=out.device) for _ in range(n_dir)]
         dgh = [torch.empty((b * t, 3 * h), dtype=out.dtype, device=out.device) for _ in range(n_dir)]
         g_amax = [linalg.new_amax(out.device) for _ in range(n_dir)]
-        _lib.check(_lib.lib().agnn_gru_bwd_amax(b, t, h, n_dir, _lib.ptr_array(whh), out.data_ptr(),
-                                                _lib.ptr_array(gates), dout.data_ptr(), _lib.ptr_array(dgi),
-                                                _lib.ptr_array(dgh), _lib.ptr_array(g_amax), _stream(out)),
-                   "agnn_gru_bwd")
-        _lib.count_launches(1)
+        if _lib.lib().agnn_gru_supported(h) == _lib.GRU_STEPWISE:
+            # wide hidden sizes (MetricalConvLayer's GRU(512, 512)): one launch per time step, W_hh^T read K-major
+            whh_t = [w.t().contiguous() for w in whh]
+            carry = torch.empty((n_dir, b, h), dtype=out.dtype, device=out.device)
+            _lib.check(_lib.lib().agnn_gru_bwd_stepwise(b, t, h, n_dir, _lib.ptr_array(whh_t), out.data_ptr(),
+                                                        _lib.ptr_array(gates), dout.data_ptr(), _lib.ptr_array(dgi),
+                                                        _lib.ptr_array(dgh), _lib.ptr_array(g_amax),
+                                                        carry.data_ptr(), _stream(out)),
+                       "agnn_gru_bwd_stepwise")
+            _lib.count_launches(t)
+        else:
+            _lib.check(_lib.lib().agnn_gru_bwd_amax(b, t, h, n_dir, _lib.ptr_array(whh), out.data_ptr(),
+                                                    _lib.ptr_array(gates), dout.data_ptr(), _lib.ptr_array(dgi),
+                                                    _lib.ptr_array(dgh), _lib.ptr_array(g_amax), _stream(out)),
+                       "agnn_gru_bwd")
+            _lib.count_launches(1)
         for d in range(n_dir):                               # max |dgi| bounds dgh as well
             linalg.tag_amax(dgi[d], g_amax[d])
             linalg.tag_amax(dgh[d], g_amax[d])

@@ -585,15 +585,20 @@ int agnn_sample_hop_draw(int32_t n_rel, int32_t n_nodes, const int32_t* rowptr, 
  * Replaces the sequential part of nn.GRU in the sequence branches (analysisgnn/models/cadence.py:249-260,
  * 276-285; analysisgnn/models/analysis.py:527-537; MetricalConvLayer.seq, analysisgnn/models/core/gnn.py:498,
  * 523).  The input projections gi = X W_ih^T + b_ih of all time steps and every weight / input gradient are
- * agnn_gemm calls made by the caller; these two kernels run the time loop with W_hh resident in registers
- * (hidden size 32, 64 or 128; one layer, n_dir = 1 or 2 directions, h0 = 0, batch-first [B, T, .]).
+ * agnn_gemm calls made by the caller; these kernels run the time loop (one layer, n_dir = 1 or 2 directions, h0 = 0,
+ * batch-first [B, T, .]): hidden size 32, 64 or 128 with W_hh resident in registers for all T steps
+ * (AGNN_GRU_RESIDENT: one launch), multiples of 64 from 192 to 2048 -- MetricalConvLayer's GRU(512, 512) -- as one
+ * launch per time step over (unit block, sequence block, direction) tiles (AGNN_GRU_STEPWISE; agnn_gru_fwd takes both,
+ * the backward of the second kind is agnn_gru_bwd_stepwise).
  * Pointer-array arguments are HOST arrays of n_dir device pointers.
  *   fwd:  out [B, T, n_dir*H]; gates[d] [B, T, 4H] (r, z, n, W_hn h + b_hn) kept for the backward (may be NULL
  *         arrays for inference).
  *   bwd:  from dout, out, gates: dgi[d] = dL/d(gi_d) [B, T, 3H] and dgh[d] = dL/d(W_hh h + b_hh) [B, T, 3H];
  *         then db_ih = colsum(dgi), db_hh = colsum(dgh), dW_ih = dgi^T X, dW_hh = dgh^T H_prev, dX = sum_d dgi_d W_ih_d.
  */
-int agnn_gru_supported(int hidden);
+#define AGNN_GRU_RESIDENT 1
+#define AGNN_GRU_STEPWISE 2
+int agnn_gru_supported(int hidden); /* 0, AGNN_GRU_RESIDENT or AGNN_GRU_STEPWISE */
 int agnn_gru_fwd(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* gi /* host */,
                  const float* const* w_hh /* host */, const float* const* b_hh /* host */, float* out,
                  float* const* gates /* host, optional */, agnn_stream_t stream);
@@ -606,6 +611,13 @@ int agnn_gru_bwd(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, co
 int agnn_gru_bwd_amax(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* w_hh,
                       const float* out, const float* const* gates, const float* dout, float* const* dgi,
                       float* const* dgh, float* const* amax, agnn_stream_t stream);
+/* Backward of an AGNN_GRU_STEPWISE hidden size: same outputs as agnn_gru_bwd_amax.  w_hh_t[d] = W_hh^T of direction d,
+ * [H, 3H] row-major (the carried gradient dgh W_hh reads it K-major); carry = n_dir * B * H floats of scratch (z * dh
+ * handed from one time step's launch to the next). */
+int agnn_gru_bwd_stepwise(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir,
+                          const float* const* w_hh_t /* host */, const float* out, const float* const* gates /* host */,
+                          const float* dout, float* const* dgi /* host */, float* const* dgh /* host */,
+                          float* const* amax /* host, optional */, float* carry, agnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,11 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("hidden,cin,layers,bidir,b,t", [
     (128, 256, 2, True, 5, 40), (64, 32, 1, True, 3, 17), (32, 48, 1, False, 4, 9), (128, 128, 1, True, 1, 1),
     (128, 256, 2, True, 100, 64), (64, 64, 2, False, 7, 130),
-    (128, 256, 2, True, 130, 128)])     # 16 640 rows: the projections take the fp16 operand form (linalg.prepare_auto)
+    (128, 256, 2, True, 130, 128),      # 16 640 rows: the projections take the fp16 operand form (linalg.prepare_auto)
+    # hidden sizes of the per-time-step kernels (agnn_gru_supported == AGNN_GRU_STEPWISE): MetricalConvLayer's 512,
+    # ragged sequence blocks (66 = 64 + 2 sequences forward, 32 + 32 + 2 backward), a single step, one direction
+    (256, 96, 1, True, 5, 23), (512, 512, 1, True, 66, 31), (192, 64, 2, False, 33, 12), (256, 256, 1, True, 3, 1),
+    (512, 512, 1, True, 64, 124)])
 def test_matches_torch_gru(hidden, cin, layers, bidir, b, t):
     torch.manual_seed(hidden + t)
     ref = nn.GRU(cin, hidden, num_layers=layers, batch_first=True, bidirectional=bidir)

@@ -19,27 +19,37 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--batch", type=int, default=100)
     ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--hidden", type=int, default=128)
+    ap.add_argument("--inputs", type=int, default=256)
+    ap.add_argument("--library", action="store_true", help="time torch.nn.GRU (cuDNN, TF32 off) on the same shapes too")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    rnn = GRU(256, 128, num_layers=1, batch_first=True, bidirectional=True).to(dev)
-    x = torch.randn(args.batch, args.steps, 256, device=dev, requires_grad=True)
-    for _ in range(2):
-        rnn(x)[0].square().mean().backward()
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    tf = tb = 0.0
-    for _ in range(args.reps):
-        ev[0].record()
-        y = rnn(x)[0]
-        ev[1].record()
-        y.square().mean().backward()
-        ev[2].record()
+    x = torch.randn(args.batch, args.steps, args.inputs, device=dev, requires_grad=True)
+
+    def time_layer(rnn, what):
+        for _ in range(2):
+            rnn(x)[0].square().mean().backward()
         torch.cuda.synchronize()
-        tf += ev[0].elapsed_time(ev[1])
-        tb += ev[1].elapsed_time(ev[2])
-    print(f"GRU layer B={args.batch} T={args.steps} H=128x2: forward {tf / args.reps:.3f} ms, backward {tb / args.reps:.3f} ms "
-          f"(projections on agnn_gemm + recurrence kernels)")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tf = tb = 0.0
+        for _ in range(args.reps):
+            ev[0].record()
+            y = rnn(x)[0]
+            ev[1].record()
+            y.square().mean().backward()
+            ev[2].record()
+            torch.cuda.synchronize()
+            tf += ev[0].elapsed_time(ev[1])
+            tb += ev[1].elapsed_time(ev[2])
+        print(f"GRU layer B={args.batch} T={args.steps} H={args.hidden}x2: forward {tf / args.reps:.3f} ms, "
+              f"backward {tb / args.reps:.3f} ms ({what})", flush=True)
+
+    rnn = GRU(args.inputs, args.hidden, num_layers=1, batch_first=True, bidirectional=True).to(dev)
+    time_layer(rnn, "projections on agnn_gemm + recurrence kernels; eager launches")
+    if args.library:
+        lib = torch.nn.GRU(args.inputs, args.hidden, num_layers=1, batch_first=True, bidirectional=True).to(dev)
+        time_layer(lib, "torch.nn.GRU: cuDNN, TF32 off")
 
 
 if __name__ == "__main__":
