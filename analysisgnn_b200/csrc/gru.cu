@@ -327,6 +327,13 @@ constexpr int KC = 64;            // floats of K per pipeline stage
 constexpr int kStages = 4;
 constexpr int LD = KC + 4;        // row stride = 4 banks: the 8 rows x 4 columns a fragment load touches cover all 32
 
+// Programmatic dependent launch (launch attribute set by launch_steps): the next time step's grid may be scheduled as
+// soon as every CTA of this one has passed launch_dependents(), and runs its independent prologue until
+// grid_dependency_wait(), which returns when the previous grid has completed and its writes are visible.  Without
+// the attribute both are no-ops.  Hides the launch latency and the cold epilogue loads of a 10-us kernel.
+__device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(x - __uint_as_float(hi)));
@@ -493,6 +500,7 @@ __global__ void __launch_bounds__(kThreads) gru_wide_fwd_kernel(const __grid_con
   const int tp = dir == 0 ? t - 1 : t + 1;       // time of h_{prev}
   const int bl = threadIdx.x >> 2, nq = threadIdx.x & 3;     // epilogue: sequence bl of the tile, units 2 nq, 2 nq + 1
   const int b = row0 + bl;
+  launch_dependents();
   const int64_t row = (int64_t)b * T + t;
   // what the epilogue needs from global memory, requested before the product
   float gi[3][2], bias[3][2], hp[2];
@@ -503,11 +511,14 @@ __global__ void __launch_bounds__(kThreads) gru_wide_fwd_kernel(const __grid_con
       const float2 w = __ldg(reinterpret_cast<const float2*>(p.b_hh[dir] + gt * H + u0 + 2 * nq));
       gi[gt][0] = v.x; gi[gt][1] = v.y; bias[gt][0] = w.x; bias[gt][1] = w.y;
     }
-    hp[0] = hp[1] = 0.f;
-    if (step > 0) {
-      const float2 v = *reinterpret_cast<const float2*>(p.out + ((int64_t)b * T + tp) * p.ld_out + dir * H + u0 + 2 * nq);
-      hp[0] = v.x; hp[1] = v.y;
-    }
+  }
+  // programmatic dependent launch: this grid was allowed to start while the previous time step was still running;
+  // everything above is independent of it, everything below reads what it wrote
+  grid_dependency_wait();
+  hp[0] = hp[1] = 0.f;
+  if (b < p.batch && step > 0) {
+    const float2 v = *reinterpret_cast<const float2*>(p.out + ((int64_t)b * T + tp) * p.ld_out + dir * H + u0 + 2 * nq);
+    hp[0] = v.x; hp[1] = v.y;
   }
   if (step > 0) {                                // h_0 = 0: the first step's product vanishes
     Operands op;
@@ -562,6 +573,7 @@ __global__ void __launch_bounds__(kThreads) gru_wide_bwd_kernel(const __grid_con
   const int tp = dir == 0 ? t - 1 : t + 1;       // time of h_{prev} in the forward recurrence
   const int bl = threadIdx.x >> 3, nq = threadIdx.x & 7;     // epilogue: sequence bl of the tile, units 2 nq, 2 nq + 1
   const int b = row0 + bl, u = u0 + 2 * nq;
+  launch_dependents();
   const int64_t row = (int64_t)b * T + t;
   float gd[2], r[2], z[2], n[2], ghn[2], hp[2], kp[2];
   float* keep = p.keep + ((int64_t)dir * p.batch + b) * H + u;
@@ -572,7 +584,11 @@ __global__ void __launch_bounds__(kThreads) gru_wide_bwd_kernel(const __grid_con
     ld2(gt, r); ld2(gt + H, z); ld2(gt + 2 * H, n); ld2(gt + 3 * H, ghn);
     hp[0] = hp[1] = kp[0] = kp[1] = 0.f;
     if (tp >= 0 && tp < T) ld2(p.out + ((int64_t)b * T + tp) * p.ld_out + dir * H + u, hp);
-    if (step > 0) ld2(keep, kp);
+  }
+  grid_dependency_wait();                        // the loads above do not depend on the previous backward step
+  if (b < p.batch && step > 0) {
+    const float2 v = *reinterpret_cast<const float2*>(keep);
+    kp[0] = v.x; kp[1] = v.y;
   }
   if (step > 0) {                                // dh_prev[b, u] = sum_i dgh[b, i] W_hh[i, u]
     Operands op;
@@ -623,13 +639,41 @@ __global__ void __launch_bounds__(kThreads) gru_wide_bwd_kernel(const __grid_con
 
 inline bool supported(int hidden) { return hidden > 128 && hidden <= 2048 && hidden % 64 == 0; }
 
+// One launch per time step.  Forward steps may overlap the tail of the one before (programmatic dependent launch; one
+// CTA per SM by registers, so a waiting grid only takes the SMs the running one has left: 1.86 -> 1.63 ms for 124 steps).
+// Backward steps may not: two of its CTAs fit an SM, the waiting grids pile up beside the running one and the loop
+// got 9x SLOWER (2.9 -> 27 ms measured).  AGNN_GRU_PDL=0: never, 2: both.
+int launch_steps(void (*kernel)(GruParams, int), dim3 grid, size_t smem, const GruParams& p, cudaStream_t st,
+                 bool allow_overlap) {
+  static const int mode = [] { const char* e = getenv("AGNN_GRU_PDL"); return e && *e ? atoi(e) : 1; }();
+  const bool pdl = mode == 2 || (mode == 1 && allow_overlap);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  for (int step = 0; step < p.steps; ++step) {
+    // step 0 keeps the full stream dependency: its prologue reads what the kernels BEFORE the time loop wrote (gi, dout)
+    cfg.numAttrs = pdl && step > 0 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p, step);
+    if (e != cudaSuccess) return fail(AGNN_ERR_CUDA, "gru time step %d: %s", step, cudaGetErrorString(e));
+  }
+  return AGNN_OK;
+}
+
 int launch_fwd(const GruParams& p, cudaStream_t st) {
   constexpr size_t kSmem = smem_bytes<FTS, FTN>();
   static const cudaError_t attr =
       cudaFuncSetAttribute(gru_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
   if (attr != cudaSuccess) return fail(AGNN_ERR_CUDA, "gru_fwd: shared-memory attribute: %s", cudaGetErrorString(attr));
   dim3 grid((unsigned)(p.hidden / 8), (unsigned)ceil_div(p.batch, FTS), (unsigned)p.n_dir);
-  for (int step = 0; step < p.steps; ++step) gru_wide_fwd_kernel<<<grid, kThreads, kSmem, st>>>(p, step);
+  int rc = launch_steps(gru_wide_fwd_kernel, grid, kSmem, p, st, true);
+  if (rc) return rc;
   return check_launch("gru_wide_fwd");
 }
 
@@ -639,7 +683,8 @@ int launch_bwd(const GruParams& p, cudaStream_t st) {
       cudaFuncSetAttribute(gru_wide_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
   if (attr != cudaSuccess) return fail(AGNN_ERR_CUDA, "gru_bwd: shared-memory attribute: %s", cudaGetErrorString(attr));
   dim3 grid((unsigned)(p.hidden / BTN), (unsigned)ceil_div(p.batch, BTS), (unsigned)p.n_dir);
-  for (int step = 0; step < p.steps; ++step) gru_wide_bwd_kernel<<<grid, kThreads, kSmem, st>>>(p, step);
+  int rc = launch_steps(gru_wide_bwd_kernel, grid, kSmem, p, st, false);
+  if (rc) return rc;
   return check_launch("gru_wide_bwd");
 }
 }  // namespace wide
