@@ -230,6 +230,7 @@ _PROTOTYPES = {
                                        C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_int32] +
                              [C.c_void_p] * 8 + [C.c_size_t, C.c_void_p]),
     "agnn_gru_supported": (C.c_int, [C.c_int]),
+    "agnn_gru_mode": (C.c_int, [C.c_int]),
     "agnn_gru_fwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "agnn_gru_bwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

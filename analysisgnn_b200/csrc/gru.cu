@@ -689,6 +689,410 @@ int launch_bwd(const GruParams& p, cudaStream_t st) {
 }
 }  // namespace wide
 
+// ---------------------------------------------------------------------------------------------------------
+// Hidden size 128 on the tensor cores, 8 sequences per CTA.  The register-resident kernels above give every pair of
+// sequences an SM of its own: 100 of the 148 SMs for the 0.65 - 0.9 ms of each of the four recurrence launches of a
+// step, during which the kernels of the main stream (persistent GEMMs, gathers) run on what is left.  Here a CTA owns
+// 8 sequences of one direction -- one n8 tile -- so 100 sequences x 2 directions are 26 CTAs, and the recurrent product
+//     gh^T[384, 8] = W_hh . h^T[128, 8]          (forward)        dh^T[128, 8] = W_hh^T . dgh^T[384, 8]   (backward)
+// runs as mma.sync m16n8k16 on fp16 hi / lo pairs (3 MMAs per product, fp32-grade: the F16X3 form of gemm.cu):
+//   * W_hh is split ONCE per launch with one power-of-two scale (its amax, reduced by the CTA) and kept as A
+//     FRAGMENTS: three quarters of every warp's fragments in registers (144), the rest in shared memory in fragment
+//     order (two LDS.128 per MMA triple) -- 49 152 words in total, which the registers alone do not hold;
+//   * h is bounded by 1 (scale 2^13), dgh gets a per-step scale from the CTA's maximum; the B operand lives in shared
+//     memory as two [8][128 + 8] fp16 matrices, double buffered, so a time step needs ONE barrier (backward: two);
+//   * warp w owns hidden units [16 w, 16 w + 16): its three (forward) / one (backward) m-tiles hold exactly the r, z, n
+//     pre-activations / the dh of the units whose gates it evaluates, so the accumulators never leave the thread:
+//     lane (g, t) finishes units 16 w + g, 16 w + g + 8 of sequences 2 t, 2 t + 1 and carries their h / dh in
+//     registers at full precision;
+//   * the per-step inputs of those 4 (sequence, unit) items are requested straight into registers before the MMA phase
+//     (8 lanes = one 32-byte sector) and consumed after it: no staging ring.
+// (A first version had the 16 sequences of a CTA on the M side: twice the MMAs per CTA and step, 2.9 us per step, and
+// with 14 CTAs the loop itself became the critical path of the training step: 9.6 -> 10.4 ms.)
+// An accumulation chain is 8 k steps x 3 = 24 MMAs (forward), the limit gemm.cu keeps for the truncating accumulator;
+// the backward's 72 are cut into three chains summed with fp32 adds.
+namespace tc {
+constexpr int H = 128;
+constexpr int kThreads = 256;
+constexpr int kSeqs = 8;              // one n8 tile
+constexpr int LDH = H + 8;            // halves per row of the forward A operand: 68 words = 4 banks per row
+constexpr int LDG = 3 * H + 8;        // backward A operand (dgh): 196 words = 4 banks per row
+constexpr float kHScale = 8192.f;     // |h| <= 1 -> [0, 2^13]
+
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// Gate nonlinearities on the special-function unit: ex2.approx + rcp.approx (2 ulp each) instead of libm's expf / tanhf
+// sequences -- the gate phase of a step is latency bound with two warps per scheduler, and these were 40 % of its
+// instructions.  Absolute error ~2e-7 on values in [-1, 1] (parity tests unchanged).
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+// Four 8 x 8 fp16 matrices = the B fragments {b0, b1} of TWO k steps from an operand stored [n][k]: lane i passes the
+// address of row (i & 7), k offset 8 (i >> 3); lane (g, t) receives the words (row g, k 2t..2t+1) of each matrix.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(smem_row)));
+}
+
+// (x0, x1) * s -> packed fp16 hi pair and lo pair
+__device__ __forceinline__ void split_pair(float x0, float x1, float s, uint32_t& hi, uint32_t& lo) {
+  const float y0 = x0 * s, y1 = x1 * s;
+  const __half2 h = __floats2half2_rn(y0, y1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// max |w| over a [rows x 128] matrix, by the whole CTA (red: 8 floats of shared memory); ends with a barrier
+__device__ __forceinline__ float cta_amax(const float* w, int n4, float* red) {
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n4; i += kThreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < kThreads / 32; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  return m;
+}
+
+// ---- forward -------------------------------------------------------------------------------------------
+// gh^T[384, 8] = W_hh[384, 128] . h^T[128, 8]: the gate rows are the M side (24 m16 tiles, three per warp: the r, z, n
+// rows of its 16 units), the 8 sequences one n8 tile: 3 x 8 x 3 = 72 MMAs per warp and step, none wasted on padding.
+constexpr int FKS = H / 16;           // 8 k steps
+constexpr int FKREG = 6;              // k steps whose W_hh fragments stay in registers (6 x 3 gates x 8 words = 144)
+struct FwdSmem {
+  uint4 wfrag[kThreads / 32][3][FKS - FKREG][2][32];   // {a0, a1, a2, a3} hi / lo per (warp, gate, k step, lane)
+  __half h_hi[2][kSeqs][LDH], h_lo[2][kSeqs][LDH];     // B operand: h as [sequence][unit], double buffered
+  float bias[3 * H];
+  float red[kThreads / 32];
+};
+
+__global__ void __launch_bounds__(kThreads, 1) gru_tc_fwd_kernel(const __grid_constant__ GruParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int dir = blockIdx.y, b0 = blockIdx.x * kSeqs, T = p.steps;
+  const float* W = p.w_hh[dir];
+  const float s_w = f16_scale_of(cta_amax(W, 3 * H * H / 4, sm.red));
+  const float inv = 1.f / (s_w * kHScale);
+  // A fragments (row, k) of gate q, k step ks: (g, 2t..) (g + 8, 2t..) (g, 2t + 8..) (g + 8, 2t + 8..), rows q H + 16 w + .
+  uint32_t wreg[3][FKREG][8];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float* wr = W + (int64_t)(q * H + 16 * w + g) * H + 2 * t;
+#pragma unroll
+    for (int ks = 0; ks < FKS; ++ks) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(wr + (i & 1) * 8 * H + 16 * ks + (i >> 1) * 8));
+        split_pair(v.x, v.y, s_w, hi[i], lo[i]);
+      }
+      if (ks < FKREG) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { wreg[q][ks][i] = hi[i]; wreg[q][ks][4 + i] = lo[i]; }
+      } else {
+        sm.wfrag[w][q][ks - FKREG][0][lane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        sm.wfrag[w][q][ks - FKREG][1][lane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+  for (int i = tid; i < 3 * H; i += kThreads) sm.bias[i] = __ldg(p.b_hh[dir] + i);
+  for (int i = tid; i < 2 * kSeqs * LDH / 2; i += kThreads) {          // h_0 = 0 in both buffers
+    reinterpret_cast<uint32_t*>(&sm.h_hi[0][0][0])[i] = 0u;
+    reinterpret_cast<uint32_t*>(&sm.h_lo[0][0][0])[i] = 0u;
+  }
+  __syncthreads();
+  // this thread finishes units 16 w + g + 8 s2 (s2 = 0, 1) of sequences 2 t + e (e = 0, 1): C fragment [2 s2 + e]
+  float hprev[2][2], bias[3][2];
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    hprev[s2][0] = hprev[s2][1] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) bias[q][s2] = sm.bias[q * H + 16 * w + g + 8 * s2];
+  }
+  const int64_t seq_stride = (int64_t)T * 3 * H;
+  const float* gi_base = p.gi[dir] + (int64_t)(b0 + 2 * t) * seq_stride + 16 * w + g;
+  const bool ok[2] = {b0 + 2 * t < p.batch, b0 + 2 * t + 1 < p.batch};
+  int cur = 0;
+  for (int step = 0; step < T; ++step) {
+    const int tt = dir == 0 ? step : T - 1 - step;
+    // this thread's input projections of the step, requested now and used after the MMA phase
+    float gi[3][2][2];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          gi[q][s2][e] = ok[e] ? __ldg(gi_base + e * seq_stride + (int64_t)tt * (3 * H) + q * H + 8 * s2) : 0.f;
+    float acc[3][4];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
+    if (step > 0) {                                                     // h_0 = 0: nothing to multiply
+      // B fragments (k, n): (2t.., g) (2t + 8.., g) = h[sequence g][units 16 ks + 2t.. / + 8], two k steps per ldmatrix
+      const __half* bh_row = &sm.h_hi[cur][lane & 7][8 * (lane >> 3)];
+      const __half* bl_row = &sm.h_lo[cur][lane & 7][8 * (lane >> 3)];
+      uint32_t bh[4], bl[4];
+#pragma unroll
+      for (int ks = 0; ks < FKS; ++ks) {
+        if ((ks & 1) == 0) {
+          ldmatrix_x4(bh, bh_row + 16 * ks);
+          ldmatrix_x4(bl, bl_row + 16 * ks);
+        }
+        const uint32_t bh0 = bh[2 * (ks & 1)], bh1 = bh[2 * (ks & 1) + 1], bl0 = bl[2 * (ks & 1)], bl1 = bl[2 * (ks & 1) + 1];
+        uint32_t ah[3][4], al[3][4];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (ks < FKREG) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ah[q][i] = wreg[q][ks][i]; al[q][i] = wreg[q][ks][4 + i]; }
+          } else {
+            const uint4 vh = sm.wfrag[w][q][ks - FKREG][0][lane], vl = sm.wfrag[w][q][ks - FKREG][1][lane];
+            ah[q][0] = vh.x; ah[q][1] = vh.y; ah[q][2] = vh.z; ah[q][3] = vh.w;
+            al[q][0] = vl.x; al[q][1] = vl.y; al[q][2] = vl.z; al[q][3] = vl.w;
+          }
+        }
+        // term-major: consecutive MMAs go to different accumulators
+#pragma unroll
+        for (int q = 0; q < 3; ++q) mma_f16(acc[q], al[q], bh0, bh1);   // W_lo h_hi
+#pragma unroll
+        for (int q = 0; q < 3; ++q) mma_f16(acc[q], ah[q], bl0, bl1);   // W_hi h_lo
+#pragma unroll
+        for (int q = 0; q < 3; ++q) mma_f16(acc[q], ah[q], bh0, bh1);   // W_hi h_hi
+      }
+    }
+    const int nxt = cur ^ 1;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int u = 16 * w + g + 8 * s2;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float ghr = acc[0][2 * s2 + e] * inv + bias[0][s2];
+        const float ghz = acc[1][2 * s2 + e] * inv + bias[1][s2];
+        const float ghn = acc[2][2 * s2 + e] * inv + bias[2][s2];
+        const float r = fast_sigmoid(gi[0][s2][e] + ghr);
+        const float z = fast_sigmoid(gi[1][s2][e] + ghz);
+        const float n = fast_tanh(gi[2][s2][e] + r * ghn);
+        const float hn = (1.f - z) * n + z * hprev[s2][e];
+        hprev[s2][e] = hn;
+        const float y = hn * kHScale;
+        const __half hh = __float2half_rn(y);
+        sm.h_hi[nxt][2 * t + e][u] = hh;
+        sm.h_lo[nxt][2 * t + e][u] = __float2half_rn(y - __half2float(hh));
+        if (ok[e]) {
+          const int64_t row = (int64_t)(b0 + 2 * t + e) * T + tt;
+          p.out[row * p.ld_out + dir * H + u] = hn;
+          if (p.gates[dir]) {
+            float* gt = p.gates[dir] + row * (4 * H) + u;
+            gt[0] = r; gt[H] = z; gt[2 * H] = n; gt[3 * H] = ghn;
+          }
+        }
+      }
+    }
+    __syncthreads();                  // the new operand is complete; the old one is no longer read
+    cur = nxt;
+  }
+}
+
+// ---- backward ------------------------------------------------------------------------------------------
+// dh^T[128, 8] = W_hh^T[128, 384] . dgh^T[384, 8]: warp w owns the m16 tile of its 16 units, 24 k steps.  The three
+// product terms accumulate in three separate fragments (independent chains of 24 MMAs each, summed small-first with
+// fp32 adds at the end): one fragment would make the 72 MMAs of a step wait for each other.
+constexpr int BKS = 3 * H / 16;       // 24 k steps
+constexpr int BKREG = 16;             // k steps whose W_hh^T fragments stay in registers (16 x 8 words = 128)
+struct BwdSmem {
+  uint4 wfrag[kThreads / 32][BKS - BKREG][2][32];      // {a0, a1, a2, a3} hi / lo per (warp, k step, lane)
+  __half d_hi[2][kSeqs][LDG], d_lo[2][kSeqs][LDG];     // B operand: dgh as [sequence][gate index], double buffered
+  float red[2][kThreads / 32];                         // per-step maxima of the warps, double buffered
+};
+
+__global__ void __launch_bounds__(kThreads, 1) gru_tc_bwd_kernel(const __grid_constant__ GruParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int dir = blockIdx.y, b0 = blockIdx.x * kSeqs, T = p.steps;
+  const float* W = p.w_hh[dir];
+  const float s_w = f16_scale_of(cta_amax(W, 3 * H * H / 4, sm.red[0]));
+  // A = W_hh^T: A[u][i] = W_hh[i][u]; fragment (row, k): (g, 2t..) (g + 8, 2t..) (g, 2t + 8..) (g + 8, 2t + 8..)
+  uint32_t wreg[BKREG][8];
+#pragma unroll
+  for (int ks = 0; ks < BKS; ++ks) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* wp = W + (int64_t)(16 * ks + 2 * t + (i >> 1) * 8) * H + 16 * w + g + (i & 1) * 8;
+      split_pair(__ldg(wp), __ldg(wp + H), s_w, hi[i], lo[i]);
+    }
+    if (ks < BKREG) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { wreg[ks][i] = hi[i]; wreg[ks][4 + i] = lo[i]; }
+    } else {
+      sm.wfrag[w][ks - BKREG][0][lane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      sm.wfrag[w][ks - BKREG][1][lane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  __syncthreads();
+  // this thread finishes units 16 w + g + 8 s2 (s2 = 0, 1) of sequences 2 t + e (e = 0, 1): C fragment [2 s2 + e]
+  float keep[2][2] = {{0.f, 0.f}, {0.f, 0.f}};          // z * dh of the step before: the direct path to h_prev
+  float inv = 0.f;                                       // 1 / (s_w * scale of the dgh operand in sm.d_*[cur])
+  float gmax = 0.f;
+  const bool ok[2] = {b0 + 2 * t < p.batch, b0 + 2 * t + 1 < p.batch};
+  int cur = 0;
+  for (int step = 0; step < T; ++step) {
+    const int tt = dir == 0 ? T - 1 - step : step;       // reverse of the forward's processing order
+    const int tp = dir == 0 ? tt - 1 : tt + 1;           // time of h_prev in the forward recurrence
+    // this thread's inputs of the step, requested now and used after the MMA phase
+    float gd[2][2], r[2][2], z[2][2], n[2][2], ghn[2][2], hp[2][2];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int u = 16 * w + g + 8 * s2;
+        const int64_t row = (int64_t)(b0 + 2 * t + e) * T + tt;
+        gd[s2][e] = r[s2][e] = z[s2][e] = n[s2][e] = ghn[s2][e] = hp[s2][e] = 0.f;
+        if (ok[e]) {
+          const float* gt = p.gates[dir] + row * (4 * H) + u;
+          gd[s2][e] = __ldg(p.dout + row * p.ld_out + dir * H + u);
+          r[s2][e] = __ldg(gt); z[s2][e] = __ldg(gt + H); n[s2][e] = __ldg(gt + 2 * H); ghn[s2][e] = __ldg(gt + 3 * H);
+          if (tp >= 0 && tp < T) hp[s2][e] = __ldg(p.out + ((int64_t)(b0 + 2 * t + e) * T + tp) * p.ld_out + dir * H + u);
+        }
+      }
+    float acc[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+    if (step > 0) {
+      // B fragments (k, n): (2t.., g) (2t + 8.., g) = dgh[sequence g][gate index 16 ks + 2t.. / + 8]
+      const __half* bh_row = &sm.d_hi[cur][lane & 7][8 * (lane >> 3)];
+      const __half* bl_row = &sm.d_lo[cur][lane & 7][8 * (lane >> 3)];
+      uint32_t bh[4], bl[4];
+#pragma unroll
+      for (int ks = 0; ks < BKS; ++ks) {
+        if ((ks & 1) == 0) {
+          ldmatrix_x4(bh, bh_row + 16 * ks);
+          ldmatrix_x4(bl, bl_row + 16 * ks);
+        }
+        const uint32_t bh0 = bh[2 * (ks & 1)], bh1 = bh[2 * (ks & 1) + 1], bl0 = bl[2 * (ks & 1)], bl1 = bl[2 * (ks & 1) + 1];
+        uint32_t ah[4], al[4];
+        if (ks < BKREG) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { ah[i] = wreg[ks][i]; al[i] = wreg[ks][4 + i]; }
+        } else {
+          const uint4 vh = sm.wfrag[w][ks - BKREG][0][lane], vl = sm.wfrag[w][ks - BKREG][1][lane];
+          ah[0] = vh.x; ah[1] = vh.y; ah[2] = vh.z; ah[3] = vh.w;
+          al[0] = vl.x; al[1] = vl.y; al[2] = vl.z; al[3] = vl.w;
+        }
+        mma_f16(acc[0], al, bh0, bh1);                    // W_lo dgh_hi
+        mma_f16(acc[1], ah, bl0, bl1);                    // W_hi dgh_lo
+        mma_f16(acc[2], ah, bh0, bh1);                    // W_hi dgh_hi
+      }
+    }
+    float dr[2][2], dz[2][2], dn[2][2], dgn[2][2];
+    float smax = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 2 * s2 + e;
+        const float mat = ((acc[0][i] + acc[1][i]) + acc[2][i]) * inv;
+        const float dh = gd[s2][e] + (keep[s2][e] + mat);
+        dn[s2][e] = dh * (1.f - z[s2][e]) * (1.f - n[s2][e] * n[s2][e]);
+        dz[s2][e] = dh * (hp[s2][e] - n[s2][e]) * z[s2][e] * (1.f - z[s2][e]);
+        dr[s2][e] = dn[s2][e] * ghn[s2][e] * r[s2][e] * (1.f - r[s2][e]);
+        dgn[s2][e] = dn[s2][e] * r[s2][e];
+        keep[s2][e] = dh * z[s2][e];
+        smax = fmaxf(smax, fmaxf(fabsf(dr[s2][e]), fmaxf(fabsf(dz[s2][e]), fabsf(dn[s2][e]))));   // >= |dgn|
+        if (ok[e]) {
+          const int u = 16 * w + g + 8 * s2;
+          const int64_t row = ((int64_t)(b0 + 2 * t + e) * T + tt) * (3 * H) + u;
+          p.dgi[dir][row] = dr[s2][e]; p.dgi[dir][row + H] = dz[s2][e]; p.dgi[dir][row + 2 * H] = dn[s2][e];
+          p.dgh[dir][row] = dr[s2][e]; p.dgh[dir][row + H] = dz[s2][e]; p.dgh[dir][row + 2 * H] = dgn[s2][e];
+        }
+      }
+    gmax = fmaxf(gmax, smax);
+    // the operand scale of this step's dgh: the CTA's maximum (padding sequences contribute zeros)
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, d));
+    if (lane == 0) sm.red[step & 1][w] = smax;
+    __syncthreads();
+    float m = sm.red[step & 1][0];
+#pragma unroll
+    for (int i = 1; i < kThreads / 32; ++i) m = fmaxf(m, sm.red[step & 1][i]);
+    const float s_d = f16_scale_of(m);
+    inv = 1.f / (s_w * s_d);
+    const int nxt = cur ^ 1;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int u = 16 * w + g + 8 * s2;
+        const float v[3] = {dr[s2][e], dz[s2][e], dgn[s2][e]};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const float y = v[q] * s_d;
+          const __half hh = __float2half_rn(y);
+          sm.d_hi[nxt][2 * t + e][q * H + u] = hh;
+          sm.d_lo[nxt][2 * t + e][q * H + u] = __float2half_rn(y - __half2float(hh));
+        }
+      }
+    __syncthreads();                  // the new operand is complete; the old one and red[step & 1] are no longer read
+    cur = nxt;
+  }
+  if (p.amax[dir]) {
+    uint32_t m = __float_as_uint(gmax);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (lane == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(p.amax[dir]), m);
+  }
+}
+
+// Which recurrence kernels hidden size 128 takes (agnn_gru_mode; initial value from AGNN_GRU_TC): 0 = register-resident
+// SIMT kernels for both passes, 1 = both passes on the tensor cores, 2 = forward only (default), 3 = backward only.
+// Measured on the headline training step (B200, profiles/README.md): 0: 9.53 ms, 2: 9.19 ms, 1: 9.63 ms -- the forward
+// loop is 0.82 ms on 26 SMs instead of 0.65 ms on 100 and the main stream gets the difference; the backward loop
+// (1.22 ms on 26 SMs against 0.875 ms on 100: a second barrier per step for the operand scale, 632 instead of 443
+// instructions per warp and step) ends later than the main stream's backward and stays on the SIMT kernel.
+inline int& mode() {
+  static int m = [] { const char* e = getenv("AGNN_GRU_TC"); return e && *e ? atoi(e) : 2; }();
+  return m;
+}
+inline bool fwd_enabled() { return mode() == 1 || mode() == 2; }
+inline bool bwd_enabled() { return mode() == 1 || mode() == 3; }
+
+int launch_fwd(const GruParams& p, cudaStream_t st) {
+  static const cudaError_t attr =
+      cudaFuncSetAttribute(gru_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem));
+  if (attr != cudaSuccess) return fail(AGNN_ERR_CUDA, "gru_fwd: shared-memory attribute: %s", cudaGetErrorString(attr));
+  dim3 grid((unsigned)ceil_div(p.batch, kSeqs), (unsigned)p.n_dir);
+  gru_tc_fwd_kernel<<<grid, kThreads, sizeof(FwdSmem), st>>>(p);
+  return check_launch("gru_tc_fwd");
+}
+
+int launch_bwd(const GruParams& p, cudaStream_t st) {
+  static const cudaError_t attr =
+      cudaFuncSetAttribute(gru_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
+  if (attr != cudaSuccess) return fail(AGNN_ERR_CUDA, "gru_bwd: shared-memory attribute: %s", cudaGetErrorString(attr));
+  dim3 grid((unsigned)ceil_div(p.batch, kSeqs), (unsigned)p.n_dir);
+  gru_tc_bwd_kernel<<<grid, kThreads, sizeof(BwdSmem), st>>>(p);
+  return check_launch("gru_tc_bwd");
+}
+}  // namespace tc
+
 int check_gru(const char* what, int batch, int steps, int hidden, int n_dir) {
   if (batch < 0 || steps < 0 || (n_dir != 1 && n_dir != 2))
     return fail(AGNN_ERR_ARG, "%s: bad sizes (batch=%d steps=%d n_dir=%d)", what, batch, steps, n_dir);
@@ -715,6 +1119,12 @@ int launch_bwd(const GruParams& p, cudaStream_t st) {
 }  // namespace agnn
 
 using namespace agnn;
+
+extern "C" int agnn_gru_mode(int mode) {
+  const int old = tc::mode();
+  if (mode >= 0 && mode <= 3) tc::mode() = mode;
+  return old;
+}
 
 extern "C" int agnn_gru_supported(int hidden) {
   if (hidden == 32 || hidden == 64 || hidden == 128) return AGNN_GRU_RESIDENT;
@@ -743,6 +1153,12 @@ extern "C" int agnn_gru_fwd(int32_t batch, int32_t steps, int32_t hidden, int32_
       if (!aligned16(gi[d]) || !aligned16(out) || !aligned16(b_hh[d]))
         return fail(AGNN_ERR_ARG, "gru_fwd: unaligned operand");
     return wide::launch_fwd(p, st);
+  }
+  if (hidden == 128 && tc::fwd_enabled()) {
+    for (int d = 0; d < n_dir; ++d)
+      if (!aligned16(gi[d]) || !aligned16(out) || (gates && gates[d] && !aligned16(gates[d])))
+        return fail(AGNN_ERR_ARG, "gru_fwd: unaligned operand");
+    return tc::launch_fwd(p, st);
   }
   if (hidden == 128) return launch_fwd<128>(p, st);
   if (hidden == 64) return launch_fwd<64>(p, st);
@@ -774,6 +1190,7 @@ extern "C" int agnn_gru_bwd_amax(int32_t batch, int32_t steps, int32_t hidden, i
     p.amax[d] = amax ? amax[d] : nullptr;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (hidden == 128 && tc::bwd_enabled()) return tc::launch_bwd(p, st);
   if (hidden == 128) return launch_bwd<128>(p, st);
   if (hidden == 64) return launch_bwd<64>(p, st);
   return launch_bwd<32>(p, st);

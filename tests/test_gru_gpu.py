@@ -40,6 +40,18 @@ def test_matches_torch_gru(hidden, cin, layers, bidir, b, t):
         assert_close(p.grad, q.grad, tol, n)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("b,t", [(5, 40), (19, 33), (100, 64)])
+def test_both_resident_implementations_of_hidden_128(mode, b, t):
+    """agnn_gru_mode: SIMT / tensor-core kernels per pass (8 sequences per CTA: 5 = one ragged tile, 19 = 2 + 3/8)."""
+    from analysisgnn_b200 import _lib
+    old = _lib.lib().agnn_gru_mode(mode)
+    try:
+        test_matches_torch_gru(128, 96, 2, True, b, t)
+    finally:
+        _lib.lib().agnn_gru_mode(old)
+
+
 def test_unsupported_sizes_use_the_library_rnn():
     torch.manual_seed(0)
     ref = nn.GRU(24, 20, batch_first=True, bidirectional=True)
