@@ -822,12 +822,16 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_fwd_kernel(const __grid_co
 #pragma unroll
     for (int q = 0; q < 3; ++q) bias[q][s2] = sm.bias[q * H + 16 * w + g + 8 * s2];
   }
-  const int64_t seq_stride = (int64_t)T * 3 * H;
-  const float* gi_base = p.gi[dir] + (int64_t)(b0 + 2 * t) * seq_stride + 16 * w + g;
+  // Addresses: fixed offsets from three pointers that move by one time step per iteration
+  const int dsign = dir == 0 ? 1 : -1;
+  const int64_t row0 = (int64_t)(b0 + 2 * t) * T + (dir == 0 ? 0 : T - 1);
+  const int64_t so_gi = (int64_t)T * 3 * H, so_out = (int64_t)T * p.ld_out, so_gt = (int64_t)T * 4 * H;   // sequence e = 1
+  const float* gi_p = p.gi[dir] + row0 * (3 * H) + 16 * w + g;
+  float* out_p = p.out + row0 * p.ld_out + dir * H + 16 * w + g;
+  float* gt_p = p.gates[dir] ? p.gates[dir] + row0 * (4 * H) + 16 * w + g : nullptr;
   const bool ok[2] = {b0 + 2 * t < p.batch, b0 + 2 * t + 1 < p.batch};
   int cur = 0;
   for (int step = 0; step < T; ++step) {
-    const int tt = dir == 0 ? step : T - 1 - step;
     // this thread's input projections of the step, requested now and used after the MMA phase
     float gi[3][2][2];
 #pragma unroll
@@ -835,8 +839,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_fwd_kernel(const __grid_co
 #pragma unroll
       for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
-          gi[q][s2][e] = ok[e] ? __ldg(gi_base + e * seq_stride + (int64_t)tt * (3 * H) + q * H + 8 * s2) : 0.f;
+        for (int e = 0; e < 2; ++e) gi[q][s2][e] = ok[e] ? __ldg(gi_p + e * so_gi + q * H + 8 * s2) : 0.f;
     float acc[3][4];
 #pragma unroll
     for (int q = 0; q < 3; ++q)
@@ -894,10 +897,9 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_fwd_kernel(const __grid_co
         sm.h_hi[nxt][2 * t + e][u] = hh;
         sm.h_lo[nxt][2 * t + e][u] = __float2half_rn(y - __half2float(hh));
         if (ok[e]) {
-          const int64_t row = (int64_t)(b0 + 2 * t + e) * T + tt;
-          p.out[row * p.ld_out + dir * H + u] = hn;
-          if (p.gates[dir]) {
-            float* gt = p.gates[dir] + row * (4 * H) + u;
+          out_p[e * so_out + 8 * s2] = hn;
+          if (gt_p) {
+            float* gt = gt_p + e * so_gt + 8 * s2;
             gt[0] = r; gt[H] = z; gt[2 * H] = n; gt[3 * H] = ghn;
           }
         }
@@ -905,6 +907,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_fwd_kernel(const __grid_co
     }
     __syncthreads();                  // the new operand is complete; the old one is no longer read
     cur = nxt;
+    gi_p += dsign * 3 * H; out_p += (int64_t)dsign * p.ld_out;
+    if (gt_p) gt_p += dsign * 4 * H;
   }
 }
 
@@ -951,24 +955,32 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_bwd_kernel(const __grid_co
   float inv = 0.f;                                       // 1 / (s_w * scale of the dgh operand in sm.d_*[cur])
   float gmax = 0.f;
   const bool ok[2] = {b0 + 2 * t < p.batch, b0 + 2 * t + 1 < p.batch};
+  // Addresses: everything this thread touches in a step sits at fixed offsets from five pointers that move by one
+  // time step per iteration (the forward's order reversed: t = T-1 .. 0 for the forward direction, 0 .. T-1 for the
+  // reverse one); h_prev of the forward recurrence is one more step along the same way.
+  const int dsign = dir == 0 ? -1 : 1;
+  const int64_t row0 = (int64_t)(b0 + 2 * t) * T + (dir == 0 ? T - 1 : 0);
+  const int64_t so_out = (int64_t)T * p.ld_out, so_gt = (int64_t)T * 4 * H, so_g3 = (int64_t)T * 3 * H;   // sequence e = 1
+  const float* dout_p = p.dout + row0 * p.ld_out + dir * H + 16 * w + g;
+  const float* out_p = p.out + row0 * p.ld_out + dir * H + 16 * w + g;
+  const float* gt_p = p.gates[dir] + row0 * (4 * H) + 16 * w + g;
+  float* dgi_p = p.dgi[dir] + row0 * (3 * H) + 16 * w + g;
+  float* dgh_p = p.dgh[dir] + row0 * (3 * H) + 16 * w + g;
+  const int64_t d_out = (int64_t)dsign * p.ld_out;
   int cur = 0;
   for (int step = 0; step < T; ++step) {
-    const int tt = dir == 0 ? T - 1 - step : step;       // reverse of the forward's processing order
-    const int tp = dir == 0 ? tt - 1 : tt + 1;           // time of h_prev in the forward recurrence
     // this thread's inputs of the step, requested now and used after the MMA phase
     float gd[2][2], r[2][2], z[2][2], n[2][2], ghn[2][2], hp[2][2];
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int u = 16 * w + g + 8 * s2;
-        const int64_t row = (int64_t)(b0 + 2 * t + e) * T + tt;
         gd[s2][e] = r[s2][e] = z[s2][e] = n[s2][e] = ghn[s2][e] = hp[s2][e] = 0.f;
         if (ok[e]) {
-          const float* gt = p.gates[dir] + row * (4 * H) + u;
-          gd[s2][e] = __ldg(p.dout + row * p.ld_out + dir * H + u);
+          const float* gt = gt_p + e * so_gt + 8 * s2;
+          gd[s2][e] = __ldg(dout_p + e * so_out + 8 * s2);
           r[s2][e] = __ldg(gt); z[s2][e] = __ldg(gt + H); n[s2][e] = __ldg(gt + 2 * H); ghn[s2][e] = __ldg(gt + 3 * H);
-          if (tp >= 0 && tp < T) hp[s2][e] = __ldg(p.out + ((int64_t)(b0 + 2 * t + e) * T + tp) * p.ld_out + dir * H + u);
+          if (step < T - 1) hp[s2][e] = __ldg(out_p + d_out + e * so_out + 8 * s2);
         }
       }
     float acc[3][4];
@@ -1018,10 +1030,10 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_bwd_kernel(const __grid_co
         keep[s2][e] = dh * z[s2][e];
         smax = fmaxf(smax, fmaxf(fabsf(dr[s2][e]), fmaxf(fabsf(dz[s2][e]), fabsf(dn[s2][e]))));   // >= |dgn|
         if (ok[e]) {
-          const int u = 16 * w + g + 8 * s2;
-          const int64_t row = ((int64_t)(b0 + 2 * t + e) * T + tt) * (3 * H) + u;
-          p.dgi[dir][row] = dr[s2][e]; p.dgi[dir][row + H] = dz[s2][e]; p.dgi[dir][row + 2 * H] = dn[s2][e];
-          p.dgh[dir][row] = dr[s2][e]; p.dgh[dir][row + H] = dz[s2][e]; p.dgh[dir][row + 2 * H] = dgn[s2][e];
+          float* gi_o = dgi_p + e * so_g3 + 8 * s2;
+          float* gh_o = dgh_p + e * so_g3 + 8 * s2;
+          gi_o[0] = dr[s2][e]; gi_o[H] = dz[s2][e]; gi_o[2 * H] = dn[s2][e];
+          gh_o[0] = dr[s2][e]; gh_o[H] = dz[s2][e]; gh_o[2 * H] = dgn[s2][e];
         }
       }
     gmax = fmaxf(gmax, smax);
@@ -1052,6 +1064,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_bwd_kernel(const __grid_co
       }
     __syncthreads();                  // the new operand is complete; the old one and red[step & 1] are no longer read
     cur = nxt;
+    dout_p += d_out; out_p += d_out;
+    gt_p += dsign * 4 * H; dgi_p += dsign * 3 * H; dgh_p += dsign * 3 * H;
   }
   if (p.amax[dir]) {
     uint32_t m = __float_as_uint(gmax);

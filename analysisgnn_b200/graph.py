@@ -65,6 +65,23 @@ class CSR:
         self.heavy, self.n_heavy, self.heavy_cap = heavy, n_heavy, heavy_cap
 
 
+_degree_bound: Optional[int] = None
+
+
+def set_degree_bound(bound: Optional[int]) -> Optional[int]:
+    """Performance hint for the CSRs built from now on (``None`` = unknown, the default): no row of them has more than
+    ``bound`` entries -- e.g. a batch of disjoint ``subgraph_size``-note windows, where every neighbour of a node, every
+    note of a beat / measure and every node of a pooled graph lies inside one window.  Below the library's hub-row
+    threshold (``_lib.HEAVY_ROW``) ``build_csr`` then leaves out the hub-row lists and every aggregation leaves out its two
+    hub-row launches (3 launches -> 1; ~40 launches of a headline training step).  A violated hint costs speed, never
+    correctness: without a list every row, however long, is reduced by its own warp.  Returns the previous value."""
+    global _degree_bound
+    old, _degree_bound = _degree_bound, (None if bound is None else int(bound))
+    if old != _degree_bound:
+        _cache.clear()               # cached CSRs were built under the other promise
+    return old
+
+
 def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) -> List[CSR]:
     """Convert COO segments to CSR on the GPU (one library call per 32 segments)."""
     if not segments:
@@ -79,10 +96,12 @@ def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) 
     col = torch.empty(max(edge_total, 1), dtype=torch.int32, device=device)
     perm = torch.empty(max(edge_total, 1), dtype=torch.int32, device=device)
     status = torch.zeros(1, dtype=torch.int32, device=device)
-    caps = [s.n_edges // _lib.HEAVY_ROW + 1 for s in segments]
+    hubs = _degree_bound is None or _degree_bound >= _lib.HEAVY_ROW     # can a row reach the hub-row threshold?
+    caps = [s.n_edges // _lib.HEAVY_ROW + 1 if hubs else 0 for s in segments]
     # per relation: [cap] heavy row ids (ascending) + [cap] exclusive prefix of their chunk counts
-    heavy = torch.empty(sum(s.n_rel * 2 * c for s, c in zip(segments, caps)), dtype=torch.int32, device=device)
-    n_heavy = torch.empty(sum(s.n_rel for s in segments), dtype=torch.int32, device=device)
+    heavy = torch.empty(sum(s.n_rel * 2 * c for s, c in zip(segments, caps)), dtype=torch.int32, device=device) \
+        if hubs else None
+    n_heavy = torch.empty(sum(s.n_rel for s in segments), dtype=torch.int32, device=device) if hubs else None
     stream = torch.cuda.current_stream(device).cuda_stream
     out, k_off, e_off, h_off, c_off = [], 0, 0, 0, 0
     for lo in range(0, len(segments), _lib.MAX_SEG):
@@ -99,8 +118,8 @@ def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) 
             keys = s.n_rel * (s.n_rows + 1)
             out.append(CSR(rowptr[k_off:k_off + keys].view(s.n_rel, s.n_rows + 1), col[e_off:e_off + s.n_edges],
                            perm[e_off:e_off + s.n_edges], s,
-                           heavy[h_off:h_off + s.n_rel * 2 * cap].view(s.n_rel, 2 * cap),
-                           n_heavy[c_off:c_off + s.n_rel], cap))
+                           heavy[h_off:h_off + s.n_rel * 2 * cap].view(s.n_rel, 2 * cap) if hubs else None,
+                           n_heavy[c_off:c_off + s.n_rel] if hubs else None, cap))
             k_off += keys
             e_off += s.n_edges
             h_off += s.n_rel * 2 * cap
@@ -110,9 +129,10 @@ def build_csr(segments: Sequence[Segment], device=None, validate: bool = False) 
             raise _lib.AgnnError("agnn_csr_build_workspace: " + lib.agnn_last_error().decode())
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
         _lib.check(lib.agnn_csr_build(len(chunk), arr, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
-                                      status.data_ptr(), heavy.data_ptr(), n_heavy.data_ptr(), ws.data_ptr(), ws_bytes,
+                                      status.data_ptr(), heavy.data_ptr() if hubs else None,
+                                      n_heavy.data_ptr() if hubs else None, ws.data_ptr(), ws_bytes,
                                       stream), "agnn_csr_build")
-        _lib.count_launches(10 if any(s.n_edges for s in chunk) else 6)
+        _lib.count_launches((10 if any(s.n_edges for s in chunk) else 6) - (0 if hubs else 1))
     if validate and int(status.item()) != 0:
         raise ValueError("edge_index contains node ids outside [0, num_nodes)")
     return out

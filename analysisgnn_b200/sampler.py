@@ -332,6 +332,8 @@ class StaticBatcher:
         if sizes.min() < s:
             raise ValueError(f"StaticBatcher: every score needs >= {s} notes (shortest has {int(sizes.min())})")
         self.corpus, self.s, self.b, self.reverse = c, s, b, reverse
+        # no CSR row of a batch is longer than a window (graph.set_degree_bound: the caller may pass this on)
+        self.degree_bound = s
         i64 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int64, device=dev)
         self.node_ptr, self.edge_ptr = i64(c.node_ptr), i64(c.edge_ptr)
         n = c.node_ptr[-1]

@@ -294,3 +294,33 @@ def test_many_heavy_rows_zipf_degrees(concat):
         outs.append(out)
     assert torch.equal(outs[0], outs[1])
     assert_close(outs[0].double(), want, 2 * FP32_REL, "zipf tail")
+
+
+def test_degree_bound_hint_only_removes_the_hub_row_launches():
+    """graph.set_degree_bound below the hub-row threshold: no hub-row lists, two launches fewer per aggregation, same
+    values -- also when the hint is WRONG (the 700-entry row is then reduced by its own warp in edge order instead of
+    chunk by chunk: equal up to fp32 summation order; every other row bit for bit)."""
+    from analysisgnn_b200 import _lib, graph, ops
+    torch.manual_seed(3)
+    n, f = 600, 64
+    src = torch.randint(0, n, (9000,), device=DEV)
+    dst = torch.randint(1, n, (9000,), device=DEV)
+    dst[:700] = 0                                            # a hub row: above HEAVY_ROW = 512
+    ei = torch.stack([src, dst])
+    x = torch.randn(n, f, device=DEV)
+    outs, launches = [], []
+    for bound in (None, 500):
+        old = graph.set_degree_bound(bound)
+        try:
+            graph.clear_cache()
+            csr = graph.typed_csr(ei, None, n, 1, reduce_row=1)
+            assert (csr.fwd.heavy is None) == (bound is not None)
+            l0 = _lib.launches()
+            outs.append(ops.segment_sum(x, csr))
+            launches.append(_lib.launches() - l0)
+        finally:
+            graph.set_degree_bound(old)
+            graph.clear_cache()
+    assert torch.equal(outs[0][1:], outs[1][1:])
+    assert_close(outs[1][:1], outs[0][:1], FP32_REL, "hub row")
+    assert launches[1] == launches[0] - 2 and launches[1] >= 1, launches
