@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const float* __
                                                                   const uint64_t* __restrict__ rng, uint32_t rng_stream,
                                                                   float* __restrict__ amax_out) {
   __shared__ float red[kWarps][32 * 4 + 4];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the column reduction behind this kernel may line up
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const uint32_t thr = dropout_threshold(drop_p);
@@ -306,6 +307,7 @@ template <int V>
 __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restrict__ x, int64_t ld_x,
                                                            float* __restrict__ part, int64_t rows, int cols) {
   __shared__ float red[kWarps][32 * 4 + 4];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the column reduction behind this kernel may line up
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc[V][4];
 #pragma unroll
@@ -349,6 +351,7 @@ __global__ void __launch_bounds__(kThreads) grad_prepare_kernel(const float* __r
                                                                  int64_t ld_s, float* __restrict__ part, int64_t rows,
                                                                  int cols, const float* __restrict__ amax) {
   __shared__ float red[kWarps][32 * 4 + 4];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the column reduction behind this kernel may line up
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // amax given: hi / lo are fp16 matrices (ld_s in fp16 elements) receiving the F16X3 operand pair of s g'
   const float f16s = amax ? f16_scale_of(__ldg(amax)) : 0.f;
@@ -425,6 +428,9 @@ __global__ void __launch_bounds__(kThreads) reduce_partials_kernel(const float* 
                                                                     float* __restrict__ out, int64_t set_stride_part,
                                                                     int64_t set_stride_out) {
   __shared__ float red[kWarps][32];
+  // launched as a programmatic dependent of the kernel that writes `part` (launch_reduce_partials): this grid is
+  // already resident when the producer ends, and starts reading once its writes are visible
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const float* p = part + blockIdx.y * set_stride_part;
@@ -447,6 +453,24 @@ __global__ void __launch_bounds__(kThreads) reduce_partials_kernel(const float* 
     for (int w = 0; w < kWarps; ++w) t += red[w][lane];
     out[blockIdx.y * set_stride_out + c] = t;
   }
+}
+
+// The second stage of a column reduction is 8 - 16 CTAs and 4 - 9 us, 44 times per training step, most of it the gap
+// between two dependent launches: the producers announce their dependents at once (griddepcontrol.launch_dependents)
+// and this launch carries the programmatic-serialization attribute, so the gap overlaps the producer's run.
+void launch_reduce_partials(dim3 grid, const float* part, int blocks, int cols, float* out, int64_t set_stride_part,
+                            int64_t set_stride_out, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, reduce_partials_kernel, part, blocks, cols, out, set_stride_part, set_stride_out);
 }
 
 __global__ void dropout_advance_kernel(uint64_t* state) { state[1] += 1; }
@@ -615,8 +639,8 @@ extern "C" int agnn_layernorm_bwd_dropout(const float* dy, int64_t ld_dy, const 
     if (dbeta_part != dgamma_part + (int64_t)blocks * cols || dbeta != dgamma + cols)
       return fail(AGNN_ERR_ARG, "layernorm_bwd: the fused final reduction needs dbeta directly behind dgamma "
                                 "(partials [2][blocks][cols], outputs [2][cols])");
-    reduce_partials_kernel<<<dim3((unsigned)ceil_div(cols, 32), 2), kThreads, 0, st>>>(dgamma_part, blocks, cols, dgamma,
-                                                                                        (int64_t)blocks * cols, cols);
+    launch_reduce_partials(dim3((unsigned)ceil_div(cols, 32), 2), dgamma_part, blocks, cols, dgamma,
+                           (int64_t)blocks * cols, cols, st);
   }
   return check_launch("layernorm_bwd");
 }
@@ -717,7 +741,7 @@ extern "C" int agnn_grad_prepare_f16(const float* g, int64_t ld_g, const float* 
 #define CALL(V) grad_prepare_kernel<V><<<blocks, kThreads, 0, st>>>(g, ld_g, relu_out, ld_o, hi, lo, ld_s, partials, rows, cols, amax)
   AGNN_DISPATCH_V(cols, CALL);
 #undef CALL
-  if (colsum) reduce_partials_kernel<<<dim3((unsigned)ceil_div(cols, 32), 1), kThreads, 0, st>>>(partials, blocks, cols, colsum, 0, 0);
+  if (colsum) launch_reduce_partials(dim3((unsigned)ceil_div(cols, 32), 1), partials, blocks, cols, colsum, 0, 0, st);
   return check_launch("grad_prepare");
 }
 
@@ -730,6 +754,6 @@ extern "C" int agnn_colsum_partials(const float* x, int64_t ld_x, float* partial
 #define CALL(V) colsum_kernel<V><<<blocks, kThreads, 0, st>>>(x, ld_x, partials, rows, cols)
   AGNN_DISPATCH_V(cols, CALL);
 #undef CALL
-  if (out) reduce_partials_kernel<<<dim3((unsigned)ceil_div(cols, 32), 1), kThreads, 0, st>>>(partials, blocks, cols, out, 0, 0);
+  if (out) launch_reduce_partials(dim3((unsigned)ceil_div(cols, 32), 1), partials, blocks, cols, out, 0, 0, st);
   return check_launch("colsum_partials");
 }
