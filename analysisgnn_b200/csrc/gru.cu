@@ -639,14 +639,17 @@ __global__ void __launch_bounds__(kThreads) gru_wide_bwd_kernel(const __grid_con
 
 inline bool supported(int hidden) { return hidden > 128 && hidden <= 2048 && hidden % 64 == 0; }
 
-// One launch per time step.  Forward steps may overlap the tail of the one before (programmatic dependent launch; one
-// CTA per SM by registers, so a waiting grid only takes the SMs the running one has left: 1.86 -> 1.63 ms for 124 steps).
-// Backward steps may not: two of its CTAs fit an SM, the waiting grids pile up beside the running one and the loop
-// got 9x SLOWER (2.9 -> 27 ms measured).  AGNN_GRU_PDL=0: never, 2: both.
-int launch_steps(void (*kernel)(GruParams, int), dim3 grid, size_t smem, const GruParams& p, cudaStream_t st,
-                 bool allow_overlap) {
-  static const int mode = [] { const char* e = getenv("AGNN_GRU_PDL"); return e && *e ? atoi(e) : 1; }();
-  const bool pdl = mode == 2 || (mode == 1 && allow_overlap);
+// One launch per time step, each a programmatic dependent of the one before: its launch latency and cold epilogue
+// loads overlap the previous step's tail (forward 1.86 -> 1.63 ms, backward 2.87 -> 2.59 ms per 124 steps; AGNN_GRU_PDL=0
+// turns it off).  A waiting grid must not sit BESIDE the running one: the forward kernel is one CTA per SM by registers;
+// the backward kernel, of which two fit, asks for more than half an SM of shared memory for that reason -- without
+// the padding the waiting grids piled up on the SMs of the running one and the loop got 9x slower (2.9 -> 27 ms).
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("AGNN_GRU_PDL"); return !(e && *e == '0'); }();
+  return on;
+}
+int launch_steps(void (*kernel)(GruParams, int), dim3 grid, size_t smem, const GruParams& p, cudaStream_t st) {
+  const bool pdl = pdl_enabled();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -672,18 +675,18 @@ int launch_fwd(const GruParams& p, cudaStream_t st) {
       cudaFuncSetAttribute(gru_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
   if (attr != cudaSuccess) return fail(AGNN_ERR_CUDA, "gru_fwd: shared-memory attribute: %s", cudaGetErrorString(attr));
   dim3 grid((unsigned)(p.hidden / 8), (unsigned)ceil_div(p.batch, FTS), (unsigned)p.n_dir);
-  int rc = launch_steps(gru_wide_fwd_kernel, grid, kSmem, p, st, true);
+  int rc = launch_steps(gru_wide_fwd_kernel, grid, kSmem, p, st);
   if (rc) return rc;
   return check_launch("gru_wide_fwd");
 }
 
 int launch_bwd(const GruParams& p, cudaStream_t st) {
-  constexpr size_t kSmem = smem_bytes<BTS, BTN>();
+  const size_t kSmem = pdl_enabled() ? (size_t)120 * 1024 : smem_bytes<BTS, BTN>();   // one CTA per SM: see launch_steps
   static const cudaError_t attr =
       cudaFuncSetAttribute(gru_wide_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
   if (attr != cudaSuccess) return fail(AGNN_ERR_CUDA, "gru_bwd: shared-memory attribute: %s", cudaGetErrorString(attr));
   dim3 grid((unsigned)(p.hidden / BTN), (unsigned)ceil_div(p.batch, BTS), (unsigned)p.n_dir);
-  int rc = launch_steps(gru_wide_bwd_kernel, grid, kSmem, p, st, false);
+  int rc = launch_steps(gru_wide_bwd_kernel, grid, kSmem, p, st);
   if (rc) return rc;
   return check_launch("gru_wide_bwd");
 }

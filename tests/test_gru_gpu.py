@@ -41,13 +41,13 @@ def test_matches_torch_gru(hidden, cin, layers, bidir, b, t):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
-@pytest.mark.parametrize("b,t", [(5, 40), (19, 33), (100, 64)])
-def test_both_resident_implementations_of_hidden_128(mode, b, t):
+@pytest.mark.parametrize("b,t,bidir", [(5, 40, True), (19, 33, True), (100, 64, True), (9, 21, False), (1, 1, True)])
+def test_both_resident_implementations_of_hidden_128(mode, b, t, bidir):
     """agnn_gru_mode: SIMT / tensor-core kernels per pass (8 sequences per CTA: 5 = one ragged tile, 19 = 2 + 3/8)."""
     from analysisgnn_b200 import _lib
     old = _lib.lib().agnn_gru_mode(mode)
     try:
-        test_matches_torch_gru(128, 96, 2, True, b, t)
+        test_matches_torch_gru(128, 96, 2, bidir, b, t)
     finally:
         _lib.lib().agnn_gru_mode(old)
 
