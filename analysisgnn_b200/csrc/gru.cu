@@ -1088,7 +1088,13 @@ inline int& mode() {
   static int m = [] { const char* e = getenv("AGNN_GRU_TC"); return e && *e ? atoi(e) : 2; }();
   return m;
 }
-inline bool fwd_enabled() { return mode() == 1 || mode() == 2; }
+// mode 2 takes the tensor-core forward only when the SIMT kernel would hold more than half of the SMs (one CTA per 2
+// sequences and direction): below that the SM-time it frees is small and its longer loop (0.76 vs 0.65 ms) is the
+// critical path of a short step -- strong scaling of the headline batch over 2 GPUs (50 sequences per rank): 6.25 ms
+// with the SIMT forward, 6.52 ms with the tensor-core one.
+inline bool fwd_enabled(int batch, int n_dir) {
+  return mode() == 1 || (mode() == 2 && ceil_div(batch, kSeq) * n_dir > kNumSM / 2);
+}
 inline bool bwd_enabled() { return mode() == 1 || mode() == 3; }
 
 int launch_fwd(const GruParams& p, cudaStream_t st) {
@@ -1171,7 +1177,7 @@ extern "C" int agnn_gru_fwd(int32_t batch, int32_t steps, int32_t hidden, int32_
         return fail(AGNN_ERR_ARG, "gru_fwd: unaligned operand");
     return wide::launch_fwd(p, st);
   }
-  if (hidden == 128 && tc::fwd_enabled()) {
+  if (hidden == 128 && tc::fwd_enabled(batch, n_dir)) {
     for (int d = 0; d < n_dir; ++d)
       if (!aligned16(gi[d]) || !aligned16(out) || (gates && gates[d] && !aligned16(gates[d])))
         return fail(AGNN_ERR_ARG, "gru_fwd: unaligned operand");

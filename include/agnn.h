@@ -601,8 +601,9 @@ int agnn_sample_hop_draw(int32_t n_rel, int32_t n_nodes, const int32_t* rowptr, 
 int agnn_gru_supported(int hidden); /* 0, AGNN_GRU_RESIDENT or AGNN_GRU_STEPWISE */
 /* Hidden size 128 has two resident implementations: the SIMT kernels (2 sequences per CTA, W_hh in registers as fp32)
  * and tensor-core kernels (8 sequences per CTA, W_hh as fp16 hi / lo MMA fragments, 3 MMAs per product).  mode 0: SIMT
- * for both passes, 1: tensor cores for both, 2: forward on the tensor cores (default; initial value from the
- * environment variable AGNN_GRU_TC), 3: backward only.  Returns the previous mode; any other argument only queries. */
+ * for both passes, 1: tensor cores for both, 2: forward on the tensor cores when the SIMT kernel would hold more than half
+ * of the SMs, i.e. more than 148 (sequence, direction) pairs (default; initial value from the environment variable
+ * AGNN_GRU_TC), 3: backward only.  Returns the previous mode; any other argument only queries. */
 int agnn_gru_mode(int mode);
 int agnn_gru_fwd(int32_t batch, int32_t steps, int32_t hidden, int32_t n_dir, const float* const* gi /* host */,
                  const float* const* w_hh /* host */, const float* const* b_hh /* host */, float* out,
