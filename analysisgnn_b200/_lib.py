@@ -22,6 +22,7 @@ F32, BF16 = 0, 1
 SCALE_NONE, SCALE_MEAN = 0, 1
 COMBINE_CONCAT, COMBINE_SUM = 0, 1
 REL_IDENTITY_IF_EMPTY = 1
+REL_LOW_DEGREE = 2
 EDGE_ABSDIFF, EDGE_ABSDIFF_DROW, EDGE_ABSDIFF_DNBR, EDGE_GATE, EDGE_GATE_DROW, EDGE_GATE_DNBR = range(6)
 # HEAVY_ROW / HEAVY_CHUNK: build constants of the library (agnn_heavy_params), resolved on first use (__getattr__ below)
 GEMM_TF32X3, GEMM_TF32, GEMM_BF16, GEMM_F16X3 = 0, 1, 2, 3

@@ -241,6 +241,105 @@ __global__ void __launch_bounds__(kThreads, V <= 2 ? 4 : 1) gather_reduce_kernel
   }
 }
 
+
+// ---- low-degree single-relation launches -----------------------------------------------------------------
+// A row with one or two entries is a chain of dependent round trips (rowptr -> col -> source row) for 1 - 2 KB: with one
+// row per warp an SM has 32 KB in flight where 7 TB/s x ~1 us of latency asks for ~47 KB, and uniform degree 1 sat at
+// 0.52 - 0.54 of the HBM peak.  Here a warp owns kRows CONSECUTIVE rows at a time: one lane-parallel rowptr load covers
+// all of them, then round k gathers the k-th neighbour of every row that has one -- kRows source rows in flight per warp
+// instead of min(degree, 4).  Taken for one relation flagged AGNN_REL_LOW_DEGREE (the caller knows edges / rows < 1.5)
+// without neighbour weights, copy column or the E == 0 flag; hub rows are left to the hub-row kernels as usual.
+constexpr int kRows = 4;
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kThreads, 2) gather_lowdeg_kernel(const __grid_constant__ GatherParams p) {
+  using VT = Vec16<T>;
+  constexpr int E = VT::E;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int F = p.n_feat;
+  const agnn_rel_t& R = p.rel[0];
+  const T* src = static_cast<const T*>(R.src);
+  T* const out = static_cast<T*>(p.out);
+  T* const out_lo = static_cast<T*>(p.out_lo);
+  const float f16s = p.pair_amax ? f16_scale_of(__ldg(p.pair_amax)) : 0.f;
+  const bool concat = p.combine == AGNN_COMBINE_CONCAT;
+  uint32_t mx = 0;
+  const int warps = gridDim.x * (kThreads / 32);
+  for (int64_t base = (int64_t)(blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * kRows; base < p.n_rows;
+       base += (int64_t)warps * kRows) {
+    const int rp = __ldg(R.rowptr + min(base + lane, (int64_t)p.n_rows));     // lanes 0 .. kRows matter
+    int beg[kRows], deg[kRows];
+    bool skip[kRows];
+    int rounds = 0;
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      beg[i] = __shfl_sync(kFull, rp, i);
+      deg[i] = base + i < p.n_rows ? __shfl_sync(kFull, rp, i + 1) - beg[i] : 0;
+      skip[i] = base + i >= p.n_rows || is_heavy(p, R, deg[i]);
+      if (!skip[i]) rounds = max(rounds, deg[i]);
+    }
+    float acc[kRows][V][E];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i)
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[i][v][e] = 0.f;
+    // round k: the k-th neighbour of every row that has one -- up to kRows source rows in flight.  (A variant that
+    // switched to the general kernel's row-by-row loop when one of the four rows is long cost the uniform case all it had
+    // gained: 128 registers and spills; the hint is therefore only given below 1.5 entries per row.)
+    for (int k = 0; k < rounds; ++k) {
+      int idx[kRows];
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) idx[i] = (!skip[i] && k < deg[i]) ? __ldg(R.col + beg[i] + k) : -1;
+      float x[kRows][V][E];
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (idx[i] >= 0) {
+          const T* rpt = src + (int64_t)idx[i] * R.ld_src;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const int c = (v * 32 + lane) * E;
+            if (c < F) VT::load_nc(rpt + c, x[i][v]);
+          }
+        }
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (idx[i] >= 0) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[i][v][e] += x[i][v][e];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      const int64_t row = base + i;
+      if (row >= p.n_rows) break;
+      if (skip[i] && concat) continue;             // the hub-row kernels write this slice (self term included)
+      const float s = p.scale == AGNN_SCALE_MEAN ? 1.f / (float)max(deg[i], 1) : 1.f;
+      const int64_t off = row * p.ld_out + R.out_col;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int c = (v * 32 + lane) * E;
+        if (c < F) {
+          float o[E], sv[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) sv[e] = 0.f;
+          if (p.self_add) VT::load_nc(static_cast<const T*>(p.self_add) + row * p.ld_self + c, sv);
+#pragma unroll
+          for (int e = 0; e < E; ++e)               // CONCAT: s (self + acc); SUM: self + s acc  (include/agnn.h)
+            o[e] = concat ? (acc[i][v][e] + sv[e]) * s : __fadd_rn(__fmul_rn(acc[i][v][e], s), sv[e]);
+          mx = absmax_bits<E>(mx, o);
+          store_split<T>(out, out_lo, off + c, o, f16s);
+        }
+      }
+    }
+  }
+  if (p.amax_out) publish_amax(p.amax_out, mx);
+}
+
 // ---- COMBINE_SUM fast path ------------------------------------------------------------------------
 // The backward gathers (d x_src = self + sum over all outgoing relations) see 1-2 edges in each of ~9
 // relations per row: walking the relations one after another is a chain of ~4 dependent global loads per
@@ -693,7 +792,16 @@ int launch(const GatherParams& p, cudaStream_t stream) {
   if (blocks > cap) blocks = cap;
   bool flags_set = false;
   for (int r = 0; r < p.n_rel; ++r) flags_set = flags_set || (p.rel[r].flags & AGNN_REL_IDENTITY_IF_EMPTY);
-  if (LANES == 32 && p.combine == AGNN_COMBINE_SUM && !flags_set && p.n_rel > 1) {
+  bool low_degree = false;
+  if constexpr (LANES == 32 && V * Vec16<T>::E <= 8)       // kRows x V x E accumulators + as many in flight: 128 registers
+    low_degree = p.n_rel == 1 && p.rel[0].flags == AGNN_REL_LOW_DEGREE && !p.copy && !p.rel[0].nbr_deg_rowptr;
+  if (low_degree) {
+    if constexpr (LANES == 32 && V * Vec16<T>::E <= 8) {
+      int64_t lb = ceil_div(p.n_rows, (int64_t)kRows * (kThreads / 32));
+      if (lb > (int64_t)kNumSM * 2) lb = (int64_t)kNumSM * 2;                   // 2 resident CTAs per SM, grid-stride beyond
+      gather_lowdeg_kernel<T, V><<<(unsigned)lb, kThreads, 0, stream>>>(p);
+    }
+  } else if (LANES == 32 && p.combine == AGNN_COMBINE_SUM && !flags_set && p.n_rel > 1) {
     gather_sum_kernel<T, V><<<(unsigned)blocks, kThreads, 0, stream>>>(p);      // lane-parallel index phase
   } else {
     gather_reduce_kernel<T, LANES, V><<<(unsigned)blocks, kThreads, 0, stream>>>(p);

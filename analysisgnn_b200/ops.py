@@ -61,6 +61,9 @@ def _pack(rels: Sequence[Rel], n_feat: int, dtype) -> "ctypes.Array":
         arr[i].nbr_deg_rowptr = r.nbr_deg_rowptr.data_ptr() if r.nbr_deg_rowptr is not None else None
         arr[i].out_col = int(r.out_col)
         arr[i].flags = int(r.flags)
+        if (len(rels) == 1 and r.flags == 0 and r.n_edges is not None and r.nbr_deg_rowptr is None
+                and int(r.n_edges) < 1.5 * (int(r.rowptr.numel()) - 1)):
+            arr[i].flags = _lib.REL_LOW_DEGREE           # one relation, < 1.5 entries per row: four rows per warp
         if r.heavy_rows is not None and r.n_heavy is not None:
             arr[i].heavy_rows, arr[i].n_heavy = r.heavy_rows.data_ptr(), r.n_heavy.data_ptr()
             arr[i].heavy_cap = int(r.heavy_rows.numel()) // 2        # [cap] rows + [cap] chunk prefix

@@ -141,6 +141,9 @@ typedef struct agnn_rel {
 } agnn_rel_t;
 
 #define AGNN_REL_IDENTITY_IF_EMPTY 1
+/* hint for a launch of ONE relation: edges / rows < 1.5, so rows are reduced four at a time per warp (four source rows in
+ * flight instead of min(degree, 4)); results are identical, any degree is still handled */
+#define AGNN_REL_LOW_DEGREE 2
 
 #define AGNN_SCALE_NONE 0
 #define AGNN_SCALE_MEAN 1

@@ -324,3 +324,37 @@ def test_degree_bound_hint_only_removes_the_hub_row_launches():
     assert torch.equal(outs[0][1:], outs[1][1:])
     assert_close(outs[1][:1], outs[0][:1], FP32_REL, "hub row")
     assert launches[1] == launches[0] - 2 and launches[1] >= 1, launches
+
+
+@pytest.mark.parametrize("dtype,f", [(torch.float32, 256), (torch.float32, 64), (torch.bfloat16, 256), (torch.float32, 100)])
+@pytest.mark.parametrize("mean,concat,with_self", [(True, True, False), (False, True, True), (True, False, True),
+                                                   (False, False, False)])
+def test_low_degree_launch_equals_the_row_per_warp_kernel(dtype, f, mean, concat, with_self):
+    """One relation with < 1.5 entries per row takes the four-rows-per-warp kernel (AGNN_REL_LOW_DEGREE, set by
+    ops._pack when the edge count is known): same CSR order per row, so bit-identical to the general kernel; rows of
+    0 - 7 entries, a row count that is not a multiple of 4, and a hub row that goes to the hub-row kernels."""
+    from analysisgnn_b200 import graph, ops
+    torch.manual_seed(11)
+    n, n_src = 1003, 700
+    deg = (torch.rand(n) < 0.4).long() + (torch.rand(n) < 0.1).long() * 2
+    deg[5] = 7
+    deg[17] = 600                                            # >= HEAVY_ROW
+    dst = torch.repeat_interleave(torch.arange(n), deg)
+    e = int(dst.numel())
+    assert e < 1.5 * n
+    ei = torch.stack([dst, torch.randint(0, n_src, (e,))]).to(DEV)
+    csr = graph.TypedCSR(ei, None, n, n_cols=n_src)
+    x = torch.randn(n_src, f, device=DEV).to(dtype)
+    sa = torch.randn(n, f, device=DEV).to(dtype) if with_self else None
+    outs = []
+    for known in (e, None):                                  # None: no hint, the general kernel
+        y = torch.full((n, f), float("nan"), device=DEV, dtype=dtype)
+        rel = [ops.rel_of(csr.fwd, 0, x, n_edges=known)]
+        if known is None:
+            rel[0].heavy_rows = rel[0].n_heavy = None        # (the hub-row workspace needs the edge count)
+        ops.gather_reduce(rel, y, f, mean=mean, concat=concat, self_add=sa)
+        outs.append(y)
+    keep = torch.ones(n, dtype=torch.bool, device=DEV)
+    keep[17] = False                                         # chunked (hub-row path) vs edge order: not bit-identical
+    assert torch.equal(outs[0][keep], outs[1][keep])
+    assert_close(outs[0][17:18].float(), outs[1][17:18].float(), FP32_REL if dtype == torch.float32 else BF16_REL, "hub row")
