@@ -365,9 +365,25 @@ class MetricalGNN(nn.Module):
         self.emb_beats.reset_parameters()
         self.emb_measures.reset_parameters()
 
+    # The beat and the measure layer of a metrical step are independent, and each is a chain of small launches (a GRU
+    # time loop of ~120 / ~30 steps, segmented sums, BatchNorm): the measure layer runs on the side stream beside the
+    # beat layer -- in the backward too, autograd replays every node on the stream of its forward.
+    overlap_metrical = True
+
     def _metrical_step(self, k, h, h_beat, h_measure, beat_edges, measure_edges, beat_lengths, measure_lengths):
+        side = ops.side_stream(h.device) if (self.overlap_metrical and h.is_cuda) else None
+        if side is not None:
+            main = torch.cuda.current_stream(h.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                from_measures, h_measure = self.measure_convs[k](h_measure, h, measure_edges, measure_lengths)
         from_beats, h_beat = self.beat_convs[k](h_beat, h, beat_edges, beat_lengths)
-        from_measures, h_measure = self.measure_convs[k](h_measure, h, measure_edges, measure_lengths)
+        if side is not None:
+            main.wait_stream(side)
+            from_measures.record_stream(main)
+            h_measure.record_stream(main)
+        else:
+            from_measures, h_measure = self.measure_convs[k](h_measure, h, measure_edges, measure_lengths)
         h = self.project_metrical[k](torch.cat((h, from_beats, from_measures), dim=-1))
         return ops.l2norm_relu(h, relu_first=True), h_beat, h_measure
 
