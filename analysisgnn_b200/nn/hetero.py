@@ -244,6 +244,7 @@ class HGTConv(nn.Module):
         wk_all = self.k_rel.view(H, n_rel, D, D)
         wv_all = self.v_rel.view(H, n_rel, D, D)
         ys, slot, q_off, kv_off = [], {}, {}, {}
+        proj_x, proj_w, proj_b = [], [], []
         for t, x in x_dict.items():
             out_rels = [et for ets in by_dst.values() for et in ets if et[0] == t]
             if t not in by_dst and not out_rels:
@@ -264,8 +265,13 @@ class HGTConv(nn.Module):
                     for i, et in enumerate(out_rels):
                         kv_off[(et, which)] = width + i * hd
                     width += n_out * hd
-            slot[t] = len(ys)
-            ys.append(ops.linear(x, torch.cat(parts_w, dim=0), torch.cat(parts_b, dim=0)))
+            slot[t] = len(proj_x)
+            proj_x.append(x)
+            proj_w.append(torch.cat(parts_w, dim=0))
+            proj_b.append(torch.cat(parts_b, dim=0))
+        from .. import fused
+        # the wide projections of all node types: one grouped GEMM launch (and one per direction in the backward)
+        ys = fused.stage_group(proj_x, proj_w, proj_b) if proj_x else []
         scale = 1.0 / math.sqrt(D)
         targets, pscales, order = [], [], []
         for dst, ets in by_dst.items():
@@ -281,11 +287,12 @@ class HGTConv(nn.Module):
             order.append(dst)
         aggs = ops.hgt_layer_attention(ys, targets, pscales, H, hd) if targets else ()
         out_dict = {}
-        for dst, agg in zip(order, aggs):
-            o = self.out_lin[dst](F.gelu(agg))
+        outs = fused.stage_group([F.gelu(agg) for agg in aggs], [self.out_lin[dst].weight for dst in order],
+                                 [self.out_lin[dst].bias for dst in order]) if order else []
+        for dst, o in zip(order, outs):
             if o.size(-1) == x_dict[dst].size(-1):
-                a = self.skip[dst].sigmoid()
-                o = a * o + (1 - a) * x_dict[dst]
+                # a * o + (1 - a) * x as one kernel (x + a (o - x)): the gate is a learned scalar per node type
+                o = torch.lerp(x_dict[dst], o, self.skip[dst].sigmoid())
             out_dict[dst] = o
         return out_dict
 
