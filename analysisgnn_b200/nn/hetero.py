@@ -226,26 +226,30 @@ class HGTConv(nn.Module):
             cache[key] = torch.tensor(ids, dtype=torch.long, device=device)
         return cache[key]
 
-    def forward(self, x_dict, ei_dict, csr: Optional[graph.HeteroCSR] = None, only_dst=None):
-        H, D = self.heads, self.out_channels // self.heads
-        hd = H * D
-        n_rel = len(self.edge_types)
-        present = [et for et in self.edge_types if et in ei_dict and et[0] in x_dict and et[2] in x_dict]
-        if csr is None:
-            csr = graph.hetero_csr({et: ei_dict[et] for et in present}, {t: v.shape[0] for t, v in x_dict.items()})
+    def _plan(self, node_types, edge_types, only_dst):
+        """Which relations run and which node types project what -- a function of the KEYS of the batch only."""
+        present = [et for et in self.edge_types if et in edge_types and et[0] in node_types and et[2] in node_types]
         by_dst: Dict[str, List[EdgeType]] = {}
         for et in present:
             if only_dst is None or et[2] in only_dst:
                 by_dst.setdefault(et[2], []).append(et)
-        # One wide projection per node type: q (if the type is a target) and, for every relation leaving
-        # the type, k and v with the relation's per-head k_rel / v_rel folded into the weight,
-        #   (x Wk^T + bk) blockdiag(k_rel[:, r]) = x (blockdiag^T Wk)^T + bk blockdiag,
-        # so all per-node-type and per-relation projections of the layer are one tensor-core GEMM per type.
+        return present, by_dst
+
+    def projection_weights(self, node_types, edge_types, only_dst, device):
+        """One wide projection per node type: q (if the type is a target) and, for every relation leaving the type, k
+        and v with the relation's per-head k_rel / v_rel folded into the weight,
+            (x Wk^T + bk) blockdiag(k_rel[:, r]) = x (blockdiag^T Wk)^T + bk blockdiag,
+        so all per-node-type and per-relation projections of the layer are one tensor-core GEMM per type.  The result
+        depends on parameters only (~190 tiny launches per layer, autograd-tracked): ``HeteroHGTStack`` builds it for
+        all layers on a side stream while the main stream is busy with the batch."""
+        H, D = self.heads, self.out_channels // self.heads
+        hd = H * D
+        n_rel = len(self.edge_types)
+        _, by_dst = self._plan(node_types, edge_types, only_dst)
         wk_all = self.k_rel.view(H, n_rel, D, D)
         wv_all = self.v_rel.view(H, n_rel, D, D)
-        ys, slot, q_off, kv_off = [], {}, {}, {}
-        proj_x, proj_w, proj_b = [], [], []
-        for t, x in x_dict.items():
+        types, proj_w, proj_b, q_off, kv_off = [], [], [], {}, {}
+        for t in node_types:
             out_rels = [et for ets in by_dst.values() for et in ets if et[0] == t]
             if t not in by_dst and not out_rels:
                 continue
@@ -259,16 +263,30 @@ class HGTConv(nn.Module):
                 ids = [self.edge_types.index(et) for et in out_rels]
                 n_out = len(ids)
                 for which, rel_w, rows in ((0, wk_all, slice(0, hd)), (1, wv_all, slice(2 * hd, 3 * hd))):
-                    sel = rel_w.index_select(1, self._rel_ids(ids, x.device))             # [H, R_t, D, D]
+                    sel = rel_w.index_select(1, self._rel_ids(ids, device))               # [H, R_t, D, D]
                     parts_w.append(torch.einsum("hrde,hdi->rhei", sel, w[rows].view(H, D, -1)).reshape(n_out * hd, -1))
                     parts_b.append(torch.einsum("hrde,hd->rhe", sel, b[rows].view(H, D)).reshape(n_out * hd))
                     for i, et in enumerate(out_rels):
                         kv_off[(et, which)] = width + i * hd
                     width += n_out * hd
-            slot[t] = len(proj_x)
-            proj_x.append(x)
+            types.append(t)
             proj_w.append(torch.cat(parts_w, dim=0))
             proj_b.append(torch.cat(parts_b, dim=0))
+        return types, proj_w, proj_b, q_off, kv_off
+
+    def forward(self, x_dict, ei_dict, csr: Optional[graph.HeteroCSR] = None, only_dst=None, weights=None):
+        """``weights``: the result of ``projection_weights`` for this batch's keys, when the caller built it ahead."""
+        H, D = self.heads, self.out_channels // self.heads
+        hd = H * D
+        present, by_dst = self._plan(list(x_dict.keys()), ei_dict.keys(), only_dst)
+        if csr is None:
+            csr = graph.hetero_csr({et: ei_dict[et] for et in present}, {t: v.shape[0] for t, v in x_dict.items()})
+        if weights is None:
+            weights = self.projection_weights(list(x_dict.keys()), ei_dict.keys(), only_dst,
+                                              next(iter(x_dict.values())).device)
+        types, proj_w, proj_b, q_off, kv_off = weights
+        slot = {t: i for i, t in enumerate(types)}
+        proj_x = [x_dict[t] for t in types]
         from .. import fused
         # the wide projections of all node types: one grouped GEMM launch (and one per direction in the backward)
         ys = fused.stage_group(proj_x, proj_w, proj_b) if proj_x else []
@@ -298,6 +316,8 @@ class HGTConv(nn.Module):
 
 
 class HeteroHGTStack(nn.Module):
+    prefetch_weights = True
+
     def __init__(self, metadata, in_channels, hidden_channels, num_layers, heads, dropout=0.0, joint_softmax=True):
         super().__init__()
         self.dropout = dropout
@@ -308,9 +328,30 @@ class HeteroHGTStack(nn.Module):
     def forward(self, x_dict, ei_dict, nodes_per_hop=None, edges_per_hop=None, collect=None, final_types=None):
         structures = _layer_structures(self.convs, x_dict, ei_dict, nodes_per_hop, edges_per_hop)
         last = len(self.convs) - 1
+        # the composite projection weights of every layer depend on parameters only: ~570 tiny launches per step that
+        # run on their own stream beside the batch's work (their backward too: autograd replays a node on its
+        # forward's stream); a layer waits for its own set
+        dev = next(iter(x_dict.values())).device
+        ahead = [None] * len(self.convs)
+        if self.prefetch_weights and dev.type == "cuda":
+            main, side = torch.cuda.current_stream(dev), ops.side_stream(dev, 1)
+            side.wait_stream(main)
+            node_types, edge_types = list(x_dict.keys()), list(ei_dict.keys())
+            with torch.cuda.stream(side):
+                for i, conv in enumerate(self.convs):
+                    w = conv.projection_weights(node_types, edge_types, final_types if i == last else None, dev)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    ahead[i] = (w, ev)
         for i, conv in enumerate(self.convs):
             x_dict, ei_dict = trim_inputs(i, nodes_per_hop, edges_per_hop, x_dict, ei_dict)
-            out = conv(x_dict, ei_dict, csr=structures[i], only_dst=final_types if i == last else None)
+            weights = None
+            if ahead[i] is not None and list(x_dict.keys()) == node_types and list(ei_dict.keys()) == edge_types:
+                weights, ev = ahead[i]
+                main.wait_event(ev)
+                for t in weights[1] + weights[2]:
+                    t.record_stream(main)
+            out = conv(x_dict, ei_dict, csr=structures[i], only_dst=final_types if i == last else None, weights=weights)
             x_dict = {k: F.dropout(v.relu(), self.dropout, self.training) for k, v in out.items()}
             if collect is not None:
                 collect.append(x_dict)

@@ -1145,15 +1145,17 @@ def l2norm_relu(h, relu_first: bool):
     return torch.relu(torch.nn.functional.normalize(h, p=2.0, dim=-1))
 
 
-_side_streams: Dict[int, "torch.cuda.Stream"] = {}
+_side_streams: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
 
 
-def side_stream(device) -> "torch.cuda.Stream":
+def side_stream(device, which: int = 0) -> "torch.cuda.Stream":
+    """Stream ``which`` beside the caller's: 0 = the sequence branch / the measure layers, 1 = weight-only work (the
+    composite projection weights of the HGT layers)."""
     idx = torch.device(device).index
     idx = torch.cuda.current_device() if idx is None else idx
-    if idx not in _side_streams:
-        _side_streams[idx] = torch.cuda.Stream(device=idx)
-    return _side_streams[idx]
+    if (idx, which) not in _side_streams:
+        _side_streams[(idx, which)] = torch.cuda.Stream(device=idx)
+    return _side_streams[(idx, which)]
 
 
 class _GRULayer(torch.autograd.Function):
