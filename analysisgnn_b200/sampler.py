@@ -40,11 +40,12 @@ def rng_u64(seed: int, a: int, b: int, c: int, d: int) -> int:
     return h
 
 
-def window_start(seed: int, graph_id: int, n_nodes: int, size: int) -> int:
-    """``start = randint(0, n - size)`` (chord.py:219) with the counter RNG."""
+def window_start(seed: int, graph_id: int, n_nodes: int, size: int, draw: int = 0) -> int:
+    """``start = randint(0, n - size)`` (chord.py:219) with the counter RNG.  ``draw`` tells apart several windows of
+    one score in the same batch (``subgraph_sample_ratio``); 0 for the first."""
     if n_nodes <= size:
         return 0
-    return rng_u64(seed, 0x57494E, graph_id, 0, 0) % (n_nodes - size + 1)
+    return rng_u64(seed, 0x57494E, graph_id, draw, 0) % (n_nodes - size + 1)
 
 
 def _stream(dev):
@@ -234,13 +235,32 @@ class ScoreGraphLoader:
     REL_NAMES = ("onset", "consecutive", "during", "rest")
 
     def __init__(self, corpus: Corpus, subgraph_size: int, batch_size: int, num_neighbors: Sequence[int] = (),
-                 seed: int = 0, shuffle: bool = True, rank: int = 0, world_size: int = 1):
+                 seed: int = 0, shuffle: bool = True, rank: int = 0, world_size: int = 1,
+                 subgraph_sample_ratio: Optional[float] = None):
         self.corpus, self.subgraph_size, self.batch_size = corpus, subgraph_size, batch_size
         self.num_neighbors, self.seed, self.shuffle = list(num_neighbors), seed, shuffle
         self.rank, self.world_size = rank, world_size
+        # The reference passes ``subgraph_sample_ratio=0.5`` to every MuseNeighborLoader (datamodules/analysis.py:276,
+        # 290, 305, 320).  graphmuse (third party, not in /root/reference) documents it as the number of windows an
+        # epoch draws from a score relative to how many windows fit in it: a score of n notes is visited
+        # ``max(1, ceil(ratio * n / subgraph_size))`` times per epoch, each visit with its own random window.  That
+        # published behaviour is what is restated here (parity unpinned: the third-party source is absent); ``None``
+        # keeps one visit per score.
+        self.subgraph_sample_ratio = subgraph_sample_ratio
+        if subgraph_sample_ratio is None:
+            self.visits = [1] * corpus.n_scores
+        else:
+            if not subgraph_sample_ratio > 0:
+                raise ValueError("subgraph_sample_ratio must be positive")
+            ptr = corpus.node_ptr
+            # integer arithmetic where the ratio allows it (0.5, 2, ...): no float rounding at exact multiples
+            num, den = float(subgraph_sample_ratio).as_integer_ratio()
+            self.visits = [max(1, -((-(ptr[g + 1] - ptr[g]) * num) // (den * subgraph_size)))
+                           for g in range(corpus.n_scores)]
+        self.epoch_size = sum(self.visits)
 
     def __len__(self):
-        return (self.corpus.n_scores + self.batch_size - 1) // self.batch_size
+        return (self.epoch_size + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
         """One epoch of ``HeteroBatch``es (what the Lightning loop iterates over); every ``iter()`` starts the next
@@ -250,29 +270,69 @@ class ScoreGraphLoader:
         for index in range(len(self)):                     # every rank yields len(self) batches (see batch_ids)
             yield HeteroBatch(self.batch(epoch, index))
 
-    def order(self, epoch: int) -> List[int]:
+    def batches(self, epoch: int) -> List[List[int]]:
+        """The epoch's global batches (score ids).  One visit per score: the shuffled score order cut into consecutive
+        batches.  With ``subgraph_sample_ratio``: the shuffled scores are laid out visit by visit (a score's visits
+        next to each other) and position ``j`` goes to batch ``j mod len(self)``, so the visits of one score land in
+        DIFFERENT batches (as long as it has no more visits than the epoch has batches) and batch sizes differ by at
+        most one."""
+        cached = getattr(self, "_batches", None)
+        if cached is not None and cached[0] == epoch:
+            return cached[1]
         ids = list(range(self.corpus.n_scores))
         if self.shuffle:
             ids.sort(key=lambda g: rng_u64(self.seed, 0x5348, epoch, g, 0))
+        n = len(self)
+        if self.subgraph_sample_ratio is None:
+            out = [ids[i * self.batch_size:(i + 1) * self.batch_size] for i in range(n)]
+        else:
+            layout = [g for g in ids for _ in range(self.visits[g])]
+            out = [layout[i::n] for i in range(n)]
+        self._batches = (epoch, out)
+        return out
+
+    def order(self, epoch: int) -> List[int]:
+        """The epoch's visits, batch after batch."""
+        return [g for b in self.batches(epoch) for g in b]
+
+    def _global_batch(self, epoch: int, index: int) -> List[int]:
+        ids = list(self.batches(epoch)[index])
+        if 0 < len(ids) < self.world_size:
+            # a short last batch with fewer scores than ranks: wrap around the epoch order (DistributedSampler's
+            # padding) so that EVERY rank has a share -- ranks must run the same number of steps, or the others
+            # block in the gradient allreduce
+            order = self.order(epoch)
+            ids = ids + [order[i % len(order)] for i in range(self.world_size - len(ids))]
         return ids
 
     def batch_ids(self, epoch: int, index: int) -> List[int]:
         """Scores of global batch ``index`` that this rank takes (data parallel: positions ``g mod W == rank`` of the
         batch, so the ranks' shares are disjoint and together are the global batch).  Host arithmetic only."""
-        order = self.order(epoch)
-        ids = order[index * self.batch_size:(index + 1) * self.batch_size]
-        if 0 < len(ids) < self.world_size:
-            # a short last batch with fewer scores than ranks: wrap around the epoch order (DistributedSampler's
-            # padding) so that EVERY rank has a share -- ranks must run the same number of steps, or the others
-            # block in the gradient allreduce
-            ids = ids + [order[i % len(order)] for i in range(self.world_size - len(ids))]
-        return ids[self.rank::self.world_size]
+        return self._global_batch(epoch, index)[self.rank::self.world_size]
+
+    def batch_draws(self, epoch: int, index: int) -> List[int]:
+        """For every entry of ``batch_ids``: how many earlier positions of the GLOBAL batch hold the same score.  The
+        window start is keyed on it (``window_start(..., draw)``), so two visits of one score that land in the same
+        batch get different windows, and a rank's windows do not depend on the number of ranks."""
+        seen: Dict[int, int] = {}
+        draws = []
+        for g in self._global_batch(epoch, index):
+            draws.append(seen.get(g, 0))
+            seen[g] = draws[-1] + 1
+        return draws[self.rank::self.world_size]
+
+    def window_starts(self, epoch: int, index: int) -> List[int]:
+        """Window start of every entry of ``batch_ids`` (the counter RNG; host arithmetic only)."""
+        c = self.corpus
+        step_seed = rng_u64(self.seed, 0x424154, epoch, index, 0)
+        return [window_start(step_seed, g, c.node_ptr[g + 1] - c.node_ptr[g], self.subgraph_size, k)
+                for g, k in zip(self.batch_ids(epoch, index), self.batch_draws(epoch, index))]
 
     def batch(self, epoch: int, index: int):
         c = self.corpus
         ids = self.batch_ids(epoch, index)
         step_seed = rng_u64(self.seed, 0x424154, epoch, index, 0)
-        starts = [window_start(step_seed, g, c.node_ptr[g + 1] - c.node_ptr[g], self.subgraph_size) for g in ids]
+        starts = self.window_starts(epoch, index)
         edges, _, node_index, slot_ptr = window_subgraphs(c.edges[0], c.edges[1], c.edges[2], c.node_ptr, c.edge_ptr,
                                                           ids, starts, self.subgraph_size)
         n_target = slot_ptr[-1]
@@ -285,6 +345,10 @@ class ScoreGraphLoader:
             out.update(node_index=node_index, edge_index_dict=ei, num_sampled_nodes_dict=None,
                        num_sampled_edges_dict=None)
         else:
+            if len(set(ids)) != len(ids):
+                raise ValueError("ScoreGraphLoader: a score appears twice in one batch (more visits per epoch than "
+                                 "batches); the k-hop sampler grows ONE node set per score -- lower "
+                                 "subgraph_sample_ratio or the batch size")
             s = neighbor_sample(c.csr_by_destination(), c.node_ptr[-1], node_index, self.num_neighbors, step_seed)
             node_index = s["node"]
             ei = {("note", name, "note"): torch.stack((s["src"][k], s["dst"][k]))
@@ -391,8 +455,10 @@ class StaticBatcher:
         if len(ids) != self.b:
             raise ValueError(f"StaticBatcher: batch {index} has {len(ids)} scores on this rank, the static shape is "
                              f"{self.b} (use a corpus size that is a multiple of batch_size x world_size)")
-        step_seed = rng_u64(loader.seed, 0x424154, epoch, index, 0)
-        starts = [window_start(step_seed, g, c.node_ptr[g + 1] - c.node_ptr[g], self.s) for g in ids]
+        if loader.subgraph_size != self.s:
+            raise ValueError(f"StaticBatcher: the loader draws {loader.subgraph_size}-note windows, the static shape "
+                             f"is {self.s}")
+        starts = loader.window_starts(epoch, index)
         self._host[0] = torch.tensor(ids, dtype=torch.int64)
         self._host[1] = torch.tensor(starts, dtype=torch.int64)
         return self._host

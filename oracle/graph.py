@@ -131,11 +131,12 @@ def rng_u64(seed: int, a: int, b: int, c: int, d: int) -> int:
     return h
 
 
-def window_start(seed: int, graph_id: int, n_nodes: int, size: int) -> int:
-    """``start = randint(0, n - size)`` (chord.py:219) with the counter RNG."""
+def window_start(seed: int, graph_id: int, n_nodes: int, size: int, draw: int = 0) -> int:
+    """``start = randint(0, n - size)`` (chord.py:219) with the counter RNG; ``draw`` = which of several windows of
+    the same score in one batch (0 for the first)."""
     if n_nodes <= size:
         return 0
-    return rng_u64(seed, 0x57494E, graph_id, 0, 0) % (n_nodes - size + 1)
+    return rng_u64(seed, 0x57494E, graph_id, draw, 0) % (n_nodes - size + 1)
 
 
 def window_subgraph(edge_index, edge_type, n_nodes, start, size):

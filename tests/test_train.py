@@ -336,3 +336,63 @@ def test_hetero_batch_serves_the_reference_training_step():
     assert valid.all() and batch.node_types == ["note"] and batch["note"].x is x_dict["note"]
     with pytest.raises(AttributeError):
         batch["note"].not_there
+
+
+def test_loader_subgraph_sample_ratio_visits():
+    """``subgraph_sample_ratio`` (the reference passes 0.5 to every loader, datamodules/analysis.py:276): a score of n
+    notes is visited max(1, ceil(ratio n / subgraph_size)) times per epoch; the visits of one score land in different
+    batches and -- should two meet -- draw different windows; ranks split every global batch disjointly whatever the
+    world size, with the same windows; ``None`` leaves the one-visit epoch exactly as it was."""
+    import torch
+    from analysisgnn_b200 import sampler
+    from oracle import graph as og
+    sizes = [40, 100, 101, 199, 200, 201, 450, 1000, 77, 12]
+    node_ptr = [0]
+    for n in sizes:
+        node_ptr.append(node_ptr[-1] + n)
+    corpus = sampler.Corpus(torch.zeros(node_ptr[-1], 2), torch.zeros((3, 0), dtype=torch.long), node_ptr)
+    plain = sampler.ScoreGraphLoader(corpus, subgraph_size=100, batch_size=4, seed=5)
+    assert plain.visits == [1] * len(sizes) and len(plain) == 3
+    assert sorted(plain.order(0)) == list(range(len(sizes)))
+    assert [plain.batch_ids(0, i) for i in range(3)] == [plain.order(0)[4 * i:4 * i + 4] for i in range(3)]
+    assert plain.batch_draws(0, 0) == [0, 0, 0, 0]
+
+    half = sampler.ScoreGraphLoader(corpus, subgraph_size=100, batch_size=4, seed=5, subgraph_sample_ratio=0.5)
+    assert half.visits == [1, 1, 1, 1, 1, 2, 3, 5, 1, 1]            # ceil(n / 200), at least 1
+    two = sampler.ScoreGraphLoader(corpus, subgraph_size=100, batch_size=4, seed=5, subgraph_sample_ratio=2)
+    assert two.visits == [1, 2, 3, 4, 4, 5, 9, 20, 2, 1]            # ceil(n / 50)
+    for loader in (half, two):
+        n_batches = len(loader)
+        assert n_batches == -(-sum(loader.visits) // 4)
+        for epoch in range(2):
+            order = loader.order(epoch)
+            assert sorted(order) == sorted(g for g, v in enumerate(loader.visits) for _ in range(v))
+            got = [loader.batch_ids(epoch, i) for i in range(n_batches)]
+            assert [g for b in got for g in b] == order
+            assert max(map(len, got)) - min(map(len, got)) <= 1
+            for b in got:                                           # no score twice while visits <= batches
+                dup = [g for g in set(b) if b.count(g) > 1]
+                assert all(loader.visits[g] > n_batches for g in dup), (b, dup)
+        assert loader.order(0) != loader.order(1)
+    # the 1000-note score has 20 visits in 13 batches of ``two``: some batch holds it twice, with different draws
+    met = [i for i in range(len(two)) if two.batch_ids(0, i).count(7) > 1]
+    assert met
+    ids, draws, starts = two.batch_ids(0, met[0]), two.batch_draws(0, met[0]), two.window_starts(0, met[0])
+    assert sorted(d for g, d in zip(ids, draws) if g == 7) == list(range(ids.count(7)))
+    step_seed = sampler.rng_u64(two.seed, 0x424154, 0, met[0], 0)
+    assert starts == [og.window_start(step_seed, g, sizes[g], 100, d) for g, d in zip(ids, draws)]
+    assert len({s for g, s in zip(ids, starts) if g == 7}) > 1
+    assert all(0 <= s <= max(sizes[g] - 100, 0) for g, s in zip(ids, starts))
+    # data parallel: disjoint shares, the same windows as the single-rank loader
+    for world in (2, 3):
+        for index in range(len(two)):
+            parts = [sampler.ScoreGraphLoader(corpus, 100, 4, seed=5, rank=r, world_size=world, subgraph_sample_ratio=2)
+                     for r in range(world)]
+            whole = list(zip(two.batch_ids(0, index), two.window_starts(0, index)))
+            shares = [list(zip(p.batch_ids(0, index), p.window_starts(0, index))) for p in parts]
+            assert all(shares), "every rank steps"
+            if len(whole) >= world:
+                assert sorted(x for s in shares for x in s) == sorted(whole)
+                assert all(share == whole[r::world] for r, share in enumerate(shares))
+    with pytest.raises(ValueError):
+        sampler.ScoreGraphLoader(corpus, 100, 4, subgraph_sample_ratio=0.0)
