@@ -37,6 +37,8 @@
 // 128-byte swizzle everywhere.
 #include <cuda.h>
 
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -54,6 +56,7 @@ constexpr int kSmemBudget = 200 * 1024;      // operand stages
 constexpr int kStoreBox = 32;                // epilogue staging: one warp's 32 rows x 32 fp32 columns ...
 constexpr int kStoreBufBytes = kStoreBox * 128;          // ... = 4 KB, 128-byte swizzled, stored by TMA
 constexpr int kStoreBytes = 4 * 2 * kStoreBufBytes;      // 4 epilogue warps x 2 buffers
+constexpr int kSchedSlots = 4;               // work-item ids in flight between the producer and the other roles
 
 struct GemmParams {
   CUtensorMap map_a[2];  // hi, lo
@@ -85,6 +88,8 @@ struct GemmGroup {
   int n_prob;
   int chain_blocks;      // K blocks accumulated in TMEM before the sum is promoted to fp32 registers
   int total_tiles;                 // GEMM work items (tile x split) of all problems
+  int* sched;                      // work-item counter of this launch (zero before and after it), or null = items are
+                                   // dealt round robin by CTA index
   int tile_start[kMaxGroup + 1];   // first work item (tile x split) of every problem
   // split-K with ticket counters: the CTA that stores the LAST partial of an output tile adds the tile's partials in
   // split order and finishes C.  Nobody ever waits for another CTA (two grids spinning on each other's unscheduled
@@ -252,8 +257,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   uint64_t* empty = full + kStages;
   uint64_t* acc_full = empty + kStages;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* sched_full = acc_empty + 2;
+  uint64_t* sched_empty = sched_full + kSchedSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_empty + kSchedSlots);
   int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
+  volatile int* sched_item = last_flag + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = grp.total_tiles;
@@ -274,6 +282,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);   // one arrive per epilogue warp
     }
+    for (int s = 0; s < kSchedSlots; ++s) {
+      mbar_init(&sched_full[s], 1);
+      mbar_init(&sched_empty[s], 5);  // the MMA thread + one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -291,8 +303,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      // Work items are handed out by THIS thread: it draws the next item (a device-wide counter, or CTA index +
+      // k * grid without one), publishes the id to the MMA and epilogue warps through a small ring, and loads it.
+      // With the counter a CTA that starts late (the GRU kernels of the side stream hold whole SMs for a
+      // millisecond, so part of a 148-CTA grid waits for a free SM) simply takes fewer items instead of working
+      // through a fixed 1/148 share after everybody else has finished.  -1 ends the roles.
+      int sslot = 0;
+      uint32_t sphase = 0;
+      int next_static = blockIdx.x;
+      auto draw = [&]() -> int {
+        if (grp.sched) {
+          const int got = atomicAdd(grp.sched, 1);
+          if (got < n_items) return got;
+          // every CTA draws exactly one id >= n_items; the last of them leaves the counter at zero for the next launch
+          if (got == n_items + (int)gridDim.x - 1) atomicExch(grp.sched, 0);
+          return -1;
+        }
+        const int got = next_static < n_items ? next_static : -1;
+        next_static += gridDim.x;
+        return got;
+      };
+      int item = draw();
+      while (true) {
+        mbar_wait(&sched_empty[sslot], sphase ^ 1);
+        sched_item[sslot] = item;
+        mbar_arrive(&sched_full[sslot]);
+        if (++sslot == kSchedSlots) { sslot = 0; sphase ^= 1; }
+        if (item < 0) break;
         const Item it = decode_item(grp, item);
+        item = draw();                               // in flight while this item's loads are issued
         const GemmParams& p = grp.prob[it.g];
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -342,7 +381,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int cc = 0;                                    // chains issued so far (TMEM buffer = cc & 1)
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int sslot = 0;
+      uint32_t sphase = 0;
+      while (true) {
+        mbar_wait(&sched_full[sslot], sphase);
+        const int item = sched_item[sslot];
+        mbar_arrive(&sched_empty[sslot]);
+        if (++sslot == kSchedSlots) { sslot = 0; sphase ^= 1; }
+        if (item < 0) break;
         const Item it = decode_item(grp, item);
         for (int c0 = it.kb0; c0 < it.kb1; c0 += grp.chain_blocks, ++cc) {
           const int c1 = min(c0 + grp.chain_blocks, it.kb1);
@@ -386,7 +432,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     uint8_t* sbuf = store_base + quarter * 2 * kStoreBufBytes;
     int cc = 0;
     int sc = 0;                                    // staged chunks so far (buffer = sc & 1)
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int sslot = 0;
+    uint32_t sphase = 0;
+    while (true) {
+      mbar_wait(&sched_full[sslot], sphase);
+      const int item = sched_item[sslot];
+      __syncwarp();                                // every lane has read the id before the slot is handed back
+      if (lane == 0) mbar_arrive(&sched_empty[sslot]);
+      if (++sslot == kSchedSlots) { sslot = 0; sphase ^= 1; }
+      if (item < 0) break;
       const Item it = decode_item(grp, item);
       const GemmParams& p = grp.prob[it.g];
       const int m0 = it.m0, n0 = it.n0;
@@ -795,6 +849,27 @@ int make_map(CUtensorMap* map, const void* ptr, int fmt, int64_t rows, int64_t c
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) return fail(AGNN_ERR_CUDA, "gemm: cuTensorMapEncodeTiled failed (%d)", (int)rc);
   return AGNN_OK;
+}
+
+// Work-item counters of the launches (GemmGroup::sched).  Every launch leaves its counter at zero, so a counter can be
+// reused as soon as the launch is over; launches that may run at the same time (two streams, or two branches of a
+// captured graph) must not share one, hence a ring of kSchedCounters handed out in call order: a clash needs two
+// launches that many calls apart to overlap.  A static device array: no allocation, nothing to free, capturable.
+constexpr int kSchedCounters = 8192;
+__device__ int g_sched_counters[kSchedCounters];
+
+int* next_sched_counter() {
+  static int* base = [] {
+    void* p = nullptr;
+    return cudaGetSymbolAddress(&p, g_sched_counters) == cudaSuccess ? static_cast<int*>(p) : nullptr;
+  }();
+  static std::atomic<unsigned> next{0};
+  return base ? base + next.fetch_add(1, std::memory_order_relaxed) % kSchedCounters : nullptr;
+}
+
+bool sched_dynamic() {      // AGNN_GEMM_SCHED=static: items dealt round robin by CTA index (the round-1 behaviour)
+  static const bool on = [] { const char* e = getenv("AGNN_GEMM_SCHED"); return !(e && !strcmp(e, "static")); }();
+  return on;
 }
 
 template <int FMT, bool A_MN, bool B_MN, int TERMS>
@@ -1219,6 +1294,7 @@ extern "C" int agnn_gemm_grouped(int precision, int a_layout, int b_layout, int 
   grp.tile_start[grp.n_prob] = (int)items;
   grp.total_tiles = (int)items;
   const int grid = (int)(items < kNumSM ? items : kNumSM);
+  grp.sched = (items > grid && sched_dynamic()) ? next_sched_counter() : nullptr;   // one round: nothing to balance
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (precision == AGNN_GEMM_BF16) rc = dispatch_layout<kFmtBF16, 1>(a_mn, b_mn, grp, grid, st);
