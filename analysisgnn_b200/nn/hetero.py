@@ -15,6 +15,7 @@ Convention (PyG): ``edge_index[0]`` = source j, ``edge_index[1]`` = target i.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -405,6 +406,11 @@ def _head(x, n):
 
 class _HybridBase(nn.Module):
     overlap_sequence_branch = True
+    # The sequence branch is a chain of four ~0.8 ms recurrence kernels on a fraction of the SMs, the graph branch a
+    # row of wide kernels that take every free SM.  On a high-priority stream the chain's CTAs do not queue behind
+    # them.  Measured on the 100 x 500-note step (profiles/r2_u_*): HybridGNN 8.91 -> 8.73 ms; HybridHGT, whose graph
+    # branch is the longer chain, 16.87 -> 17.32 ms -- hence per encoder.  AGNN_SEQ_PRIORITY=0 / 1 overrides both.
+    sequence_branch_high_priority = False
 
     def forward(self, x_dict, edge_index_dict, batch_dict=None, batch_size=None, neighbor_mask_node=None,
                 neighbor_mask_edge=None, return_edge_index=False, edge_attr_dict=None):
@@ -413,7 +419,9 @@ class _HybridBase(nn.Module):
         batch = batch_dict["note"][:batch_size] if batch_dict is not None else \
             torch.zeros(batch_size, dtype=torch.long, device=x_in.device)
         main = torch.cuda.current_stream(x_in.device)
-        side = ops.side_stream(x_in.device) if self.overlap_sequence_branch else None
+        prio = os.environ.get("AGNN_SEQ_PRIORITY", "")
+        prio = self.sequence_branch_high_priority if prio == "" else prio != "0"
+        side = ops.side_stream(x_in.device, 0, prio) if self.overlap_sequence_branch else None
         if side is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
@@ -437,6 +445,8 @@ class HybridGNN(_HybridBase):
     """graphmuse ``HybridGNN(metadata, input_channels, hidden_channels, num_layers, dropout,
     use_jk)`` (call site analysisgnn/models/analysis.py:454-462): HeteroSAGEStack on the
     graph + GRU branch over the target notes, joined by ``Linear(2H, H)`` (cadence.py:301-303)."""
+
+    sequence_branch_high_priority = True
 
     def __init__(self, metadata, input_channels, hidden_channels, num_layers, dropout=0.5, use_jk=False):
         super().__init__()

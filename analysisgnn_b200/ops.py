@@ -1145,17 +1145,20 @@ def l2norm_relu(h, relu_first: bool):
     return torch.relu(torch.nn.functional.normalize(h, p=2.0, dim=-1))
 
 
-_side_streams: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
+_side_streams: Dict[Tuple[int, int, bool], "torch.cuda.Stream"] = {}
 
 
-def side_stream(device, which: int = 0) -> "torch.cuda.Stream":
+def side_stream(device, which: int = 0, high_priority: bool = False) -> "torch.cuda.Stream":
     """Stream ``which`` beside the caller's: 0 = the sequence branch / the measure layers, 1 = weight-only work (the
-    composite projection weights of the HGT layers)."""
+    composite projection weights of the HGT layers).  ``high_priority``: pending CTAs of this stream's kernels are
+    placed before those of the default-priority streams (kept by the kernel nodes of a captured graph); for a
+    branch that is a latency chain of narrow kernels beside wide ones."""
     idx = torch.device(device).index
     idx = torch.cuda.current_device() if idx is None else idx
-    if (idx, which) not in _side_streams:
-        _side_streams[(idx, which)] = torch.cuda.Stream(device=idx)
-    return _side_streams[(idx, which)]
+    key = (idx, which, bool(high_priority))
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=idx, priority=-1 if high_priority else 0)
+    return _side_streams[key]
 
 
 class _GRULayer(torch.autograd.Function):
