@@ -147,11 +147,11 @@ def test_loader_iterates_hetero_batches():
 
 # ------------------------------------------------------------------------------------------ static-shape batches
 
-def _static_setup(n_scores=12, batch=4, size=200, seed=3):
+def _static_setup(n_scores=12, batch=4, size=200, seed=3, ratio=None):
     c = synth.corpus(n_scores, lambda g: size + 40 + 37 * (g % 5), seed, in_features=8)
     corpus = sampler.Corpus(c["x"].to(DEV), c["edges"].to(DEV), c["node_ptr"], extras={k: v.to(DEV) for k, v in c["extras"].items()})
     sb = sampler.StaticBatcher(corpus, size, batch, beat_of=c["beat_of"].to(DEV), measure_of=c["measure_of"].to(DEV))
-    loader = sampler.ScoreGraphLoader(corpus, size, batch, seed=5)
+    loader = sampler.ScoreGraphLoader(corpus, size, batch, seed=5, subgraph_sample_ratio=ratio)
     return c, corpus, sb, loader
 
 
@@ -177,17 +177,22 @@ def _reference_batch(c, ids, starts, size):
     return {k: np.concatenate(v, axis=1) for k, v in out.items()}, counts
 
 
-def test_static_batches_match_the_host_collation():
+@pytest.mark.parametrize("n_scores,ratio", [(12, None), (2, 1.0)])
+def test_static_batches_match_the_host_collation(n_scores, ratio):
     """StaticBatcher: fixed shapes, -1 padding; after dropping the padding the edges are exactly (values AND order) the
-    induced window subgraphs collated score by score, beat / measure nodes are the windows' contiguous id ranges."""
+    induced window subgraphs collated score by score, beat / measure nodes are the windows' contiguous id ranges.
+    Second case: ``subgraph_sample_ratio`` with more visits than batches -- both scores appear twice in the one batch
+    of the epoch, each visit with its own window (slots are independent: nothing is shared between them)."""
     size, batch = 200, 4
-    c, corpus, sb, loader = _static_setup(batch=batch, size=size)
+    c, corpus, sb, loader = _static_setup(n_scores=n_scores, batch=batch, size=size, ratio=ratio)
     shapes = None
     for index in range(len(loader)):
         sel_host = sb.select(loader, 0, index).clone()
         out = sb.batch(sel_host.to(DEV))
         ids, starts = sel_host[0].tolist(), sel_host[1].tolist()
-        assert ids == loader.batch_ids(0, index)
+        assert ids == loader.batch_ids(0, index) and starts == loader.window_starts(0, index)
+        if ratio is not None:
+            assert sorted(ids) == [0, 0, 1, 1] and len(set(zip(ids, starts))) == 4
         want, counts = _reference_batch(c, ids, starts, size)
         eid = out["edge_index_dict"]
         grp = eid.groups[0]
