@@ -853,18 +853,25 @@ int make_map(CUtensorMap* map, const void* ptr, int fmt, int64_t rows, int64_t c
 
 // Work-item counters of the launches (GemmGroup::sched).  Every launch leaves its counter at zero, so a counter can be
 // reused as soon as the launch is over; launches that may run at the same time (two streams, or two branches of a
-// captured graph) must not share one, hence a ring of kSchedCounters handed out in call order: a clash needs two
-// launches that many calls apart to overlap.  A static device array: no allocation, nothing to free, capturable.
-constexpr int kSchedCounters = 8192;
+// captured graph) must not share one, hence a ring handed out in call order: a clash needs two launches half a ring of
+// calls apart to overlap.  Launches recorded into a CUDA graph keep their counter for the life of the graph, so they
+// draw from their own half of the ring: an eager launch on another stream can never meet a replaying graph's counter.
+// A static device array: no allocation, nothing to free, capturable.
+constexpr int kSchedCounters = 16384;
 __device__ int g_sched_counters[kSchedCounters];
 
-int* next_sched_counter() {
+int* next_sched_counter(cudaStream_t st) {
   static int* base = [] {
     void* p = nullptr;
     return cudaGetSymbolAddress(&p, g_sched_counters) == cudaSuccess ? static_cast<int*>(p) : nullptr;
   }();
-  static std::atomic<unsigned> next{0};
-  return base ? base + next.fetch_add(1, std::memory_order_relaxed) % kSchedCounters : nullptr;
+  static std::atomic<unsigned> next_eager{0}, next_captured{0};
+  if (!base) return nullptr;
+  constexpr unsigned kHalf = kSchedCounters / 2;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const bool captured = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+  return captured ? base + kHalf + next_captured.fetch_add(1, std::memory_order_relaxed) % kHalf
+                  : base + next_eager.fetch_add(1, std::memory_order_relaxed) % kHalf;
 }
 
 bool sched_dynamic() {      // AGNN_GEMM_SCHED=static: items dealt round robin by CTA index (the round-1 behaviour)
@@ -1294,8 +1301,8 @@ extern "C" int agnn_gemm_grouped(int precision, int a_layout, int b_layout, int 
   grp.tile_start[grp.n_prob] = (int)items;
   grp.total_tiles = (int)items;
   const int grid = (int)(items < kNumSM ? items : kNumSM);
-  grp.sched = (items > grid && sched_dynamic()) ? next_sched_counter() : nullptr;   // one round: nothing to balance
   cudaStream_t st = (cudaStream_t)stream;
+  grp.sched = (items > grid && sched_dynamic()) ? next_sched_counter(st) : nullptr;   // one round: nothing to balance
   int rc;
   if (precision == AGNN_GEMM_BF16) rc = dispatch_layout<kFmtBF16, 1>(a_mn, b_mn, grp, grid, st);
   else if (precision == AGNN_GEMM_F16X3) rc = dispatch_layout<kFmtF16, 3>(a_mn, b_mn, grp, grid, st);
