@@ -24,8 +24,8 @@
 //
 // Grouped launches (agnn_gemm_grouped): up to AGNN_GEMM_MAX_GROUP independent problems of one precision / layout
 // combination share ONE persistent launch -- the per-node-type projections (project_dict), the task heads, the
-// destination types of a message-passing layer, the directions of a GRU layer; tiles of all problems are dealt round
-// robin to the CTAs.  Split-K partials are combined INSIDE the launch: the CTA that stores the last partial of an
+// destination types of a message-passing layer, the directions of a GRU layer; the CTAs draw the tiles of all problems,
+// in order, from a per-launch device counter (GemmGroup::sched; by CTA index without one).  Split-K partials are combined INSIDE the launch: the CTA that stores the last partial of an
 // output tile (a ticket counter per tile) adds the partials in split order -- deterministic, no second kernel.
 // The epilogue can also emit max |C| (amax_out) so that a consumer that needs the fp16 operand scale of C does not
 // re-read it.
