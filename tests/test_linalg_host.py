@@ -97,3 +97,35 @@ def test_there_is_no_backend_switch_and_strict_mode_raises_on_library_routes():
             _lib.library_route("probe")
     finally:
         _lib.set_strict(old)
+
+
+def test_gemm_work_item_counter_protocol():
+    """The hand-out protocol of gemm_kernel's work-item counter (csrc/gemm.cu, GemmGroup::sched), replayed on the host
+    under random interleavings: every CTA draws ids with fetch-and-add until it gets one >= n_items, the CTA that draws
+    n_items + grid - 1 (the last draw of the launch) writes zero.  Whatever the order -- CTAs that start late, CTAs
+    that never get an item -- every item is handed out exactly once and the counter is zero afterwards, which is what
+    lets the next launch reuse it without a memset."""
+    import random
+    for trial in range(200):
+        rng = random.Random(trial)
+        n_items, grid = rng.randint(1, 400), rng.randint(1, 148)
+        counter = [0]
+        got, done = [[] for _ in range(grid)], [False] * grid
+        started = [False] * grid
+        resets = 0
+        while not all(done):
+            cta = rng.choice([c for c in range(grid) if not done[c]])
+            if not started[cta] and rng.random() < 0.7 and any(started):      # some CTAs wait for an SM for a long time
+                continue
+            started[cta] = True
+            drawn = counter[0]
+            counter[0] += 1                                   # atomicAdd
+            if drawn < n_items:
+                got[cta].append(drawn)
+                continue
+            if drawn == n_items + grid - 1:
+                counter[0] = 0                                # atomicExch by the last draw
+                resets += 1
+            done[cta] = True
+        assert sorted(i for g in got for i in g) == list(range(n_items))
+        assert counter[0] == 0 and resets == 1
